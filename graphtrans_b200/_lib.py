@@ -1,0 +1,110 @@
+"""ctypes binding of the C ABI declared in include/graphtrans_b200.h.
+
+There is NO fallback: if the shared library is missing or a call fails the product path raises
+(`RuntimeError`), it never routes through PyTorch eager ops or the CPU oracle.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libgraphtrans_b200.so")
+
+GT_F32, GT_BF16 = 0, 1
+EDGE_NONE, EDGE_LINEAR, EDGE_TABLE = 0, 1, 2
+CONV_GCN, CONV_GIN = 0, 1
+EPI_RELU, EPI_ACCUM, EPI_OUT_F32, EPI_RESID_F32 = 1, 2, 4, 8
+
+P, I, L, F = c_void_p, c_int, c_int64, c_float
+I32 = c_int32
+
+# name -> argtypes; every export returns int (0 ok). Kept in the order of include/graphtrans_b200.h
+SIGNATURES = {
+    "gt_csr_build": [P, L, L, P, P, P, P, P, P, P, P],
+    "gt_edge_type": [P, L, I32, P, P, P],
+    "gt_batch_plan": [P, L, L, L, P, P, P, P, P, P, P, P, P, P],
+    "gt_embed_sum_fwd": [I, P, L, I32, I32, I32, P, P, P, P, P],
+    "gt_embed_sum_bwd": [I, P, L, I32, I32, I32, P, P, P, P, P],
+    "gt_aggregate_fwd": [I, I, P, P, L, I32, I32, P, P, P, P, I, P, I32, P, P, P, P, P, P],
+    "gt_aggregate_bwd": [I, I, P, P, P, L, I32, I32, P, P, P, P, I, P, I32, P, P, P, P, P, P, P, P, P, P],
+    "gt_segment_sum": [I, P, P, L, I32, P, P],
+    "gt_add_graph_vec": [I, P, P, P, L, I32, P, P],
+    "gt_colstats": [I, P, L, I32, P, P],
+    "gt_bn_finalize": [P, L, I32, I32, P, P, P, P, P, F, F, I, P, P],
+    "gt_bn_apply_fwd": [I, P, L, I32, I32, P, I, P, P, P, P, P],
+    "gt_bn_bwd_reduce": [I, P, P, L, I32, I32, P, I, P, P],
+    "gt_bn_bwd_apply": [I, P, P, L, I32, I32, P, P, I, I, P, P, P, P, P],
+    "gt_gemm": [I, P, I, L, P, I, L, P, L, L, L, L, L, P, P, L, I, I, P],
+    "gt_relu_bwd": [I, P, P, L, P, P],
+    "gt_colsum": [I, P, L, L, L, P, P],
+    "gt_cast_pad": [I, P, L, L, L, I, P, L, L, L, P],
+    "gt_layernorm_fwd": [I, P, P, P, P, L, I32, P, P, F, P, P, P, P],
+    "gt_layernorm_bwd": [I, P, P, P, P, L, I32, P, P, P, P, P, P],
+    "gt_gather_rows": [I, P, P, P, L, I32, P, P],
+    "gt_scatter_rows": [I, P, P, L, I32, P, P, P],
+    "gt_pad_batch_fwd": [I, P, P, L, L, I32, P, P, P],
+    "gt_pad_batch_bwd": [I, P, P, P, L, L, L, I32, P, P],
+    "gt_mha_fwd": [I, P, P, P, P, L, L, I32, I32, F, P, P, I, P],
+    "gt_mha_bwd": [I, P, P, P, P, P, P, P, L, L, I32, I32, F, P, P, I, P],
+    "gt_pna_reduce_fwd": [I, P, P, L, I32, I32, P, P, P, P, P, P],
+    "gt_pna_reduce_bwd": [I, P, P, P, P, L, I32, I32, P, P, P, P, P, P, P],
+}
+
+_lib = None
+launch_count = 0  # kernels-launching C-ABI calls issued (bench.py reports it)
+
+
+def load():
+    """Load the shared library (raises if it has not been built)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"graphtrans_b200: {LIB_PATH} is missing - build it with `make` (or "
+            "`python -c 'import __graft_entry__ as g; g.build()'`). There is no fallback path.")
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.gt_version.restype = c_int
+    lib.gt_last_error.restype = c_char_p
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here = header/library mismatch
+        fn.argtypes = argtypes
+        fn.restype = c_int
+    _lib = lib
+    return lib
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def dt_of(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return GT_F32
+    if t.dtype == torch.bfloat16:
+        return GT_BF16
+    raise TypeError(f"graphtrans_b200: unsupported activation dtype {t.dtype}")
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name, *args):
+    """Invoke an export on torch's current CUDA stream; non-zero return -> RuntimeError."""
+    global launch_count
+    lib = load()
+    rc = getattr(lib, name)(*args, stream())
+    launch_count += 1
+    if rc != 0:
+        raise RuntimeError(f"{name} failed (rc={rc}): {lib.gt_last_error().decode()}")
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("graphtrans_b200 runs on CUDA tensors only (no CPU fallback)")

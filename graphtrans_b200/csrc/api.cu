@@ -1,0 +1,21 @@
+// Error plumbing + version for the C ABI (include/graphtrans_b200.h).
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace gt {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return (int)e;
+}
+}  // namespace gt
+
+extern "C" int gt_version(void) { return 100; }
+extern "C" const char* gt_last_error(void) { return gt::g_err; }

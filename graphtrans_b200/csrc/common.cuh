@@ -1,0 +1,93 @@
+// Shared helpers for the graphtrans_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/graphtrans_b200.h"
+
+namespace gt {
+
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define GT_CHECK_ARG(cond, ...)                \
+    do {                                       \
+        if (!(cond)) {                         \
+            gt::set_error(__VA_ARGS__);        \
+            return -1;                         \
+        }                                      \
+    } while (0)
+
+#define GT_LAUNCH_CHECK(name)                                   \
+    do {                                                        \
+        cudaError_t e__ = cudaGetLastError();                   \
+        if (e__ != cudaSuccess) return gt::cuda_fail(e__, name); \
+    } while (0)
+
+constexpr int kNumSMs = 148;
+constexpr int VEC = 4;  // elements per vector access for feature rows (ld % 4 == 0)
+
+using bf16 = __nv_bfloat16;
+
+template <typename T> struct DType;
+template <> struct DType<float> { static constexpr int id = GT_F32; };
+template <> struct DType<bf16> { static constexpr int id = GT_BF16; };
+
+__device__ __forceinline__ float to_f(float v) { return v; }
+__device__ __forceinline__ float to_f(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+// 4-element vector load/store converting to/from fp32 registers
+__device__ __forceinline__ void ld4(const float* p, float (&v)[4]) {
+    float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void ld4(const bf16* p, float (&v)[4]) {
+    uint2 t = *reinterpret_cast<const uint2*>(p);
+    __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&t.x);
+    __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&t.y);
+    float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+    v[0] = fa.x; v[1] = fa.y; v[2] = fb.x; v[3] = fb.y;
+}
+__device__ __forceinline__ void st4(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void st4(bf16* p, const float (&v)[4]) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);
+    __nv_bfloat162 b = __floats2bfloat162_rn(v[2], v[3]);
+    uint2 t;
+    t.x = *reinterpret_cast<uint32_t*>(&a);
+    t.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = t;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+inline int blocks_for(int64_t work_items, int per_block, int max_blocks = kNumSMs * 16) {
+    int64_t b = (work_items + per_block - 1) / per_block;
+    if (b < 1) b = 1;
+    if (b > max_blocks) b = max_blocks;
+    return (int)b;
+}
+
+#define GT_DISPATCH_DT(dt, ...)                                      \
+    do {                                                             \
+        if ((dt) == GT_F32) { using T = float; __VA_ARGS__; }        \
+        else if ((dt) == GT_BF16) { using T = gt::bf16; __VA_ARGS__; } \
+        else { gt::set_error("bad dtype %d", (int)(dt)); return -1; } \
+    } while (0)
+
+}  // namespace gt

@@ -1,0 +1,736 @@
+// Row-wise / column-wise helper kernels around the two hot stages: per-graph segment sums
+// (PyG global_add_pool, reference modules/gnn_module.py:219), virtual-node broadcast (:199),
+// BatchNorm1d train/eval forward + backward (gnn_module.py:58,84,164,167; conv.py:19),
+// LayerNorm (+ residual, + token gather) forward/backward (modules/transformer_encoder.py:56-57
+// and the norms inside nn.TransformerEncoderLayer), embedding-sum node encoders
+// (dataset/utils.py:28-30; ogb AtomEncoder), pad_batch gather/scatter (modules/utils.py:5-29).
+// All are HBM-bound elementwise/reduction passes with 8/16-byte vector accesses.
+#include "common.cuh"
+
+namespace gt {
+
+// ------------------------------------------------------------------ segment sum / broadcast
+// block = 128 threads = 4 warps; the block owns 32 consecutive rows; thread t owns the channel
+// vectors t, t+128, ...; consecutive rows of one graph are summed in registers and flushed
+// with one atomicAdd per (graph run, channel).
+template <typename T>
+__global__ void k_segment_sum(const T* __restrict__ x, const int32_t* __restrict__ node_graph, int N, int ld,
+                              float* __restrict__ out) {
+    const int r0 = blockIdx.x * 32;
+    const int r1 = min(r0 + 32, N);
+    for (int c0 = threadIdx.x * 4; c0 < ld; c0 += blockDim.x * 4) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        int g = node_graph[r0];
+        for (int r = r0; r < r1; ++r) {
+            const int gr = node_graph[r];
+            if (gr != g) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) atomicAdd(out + (int64_t)g * ld + c0 + q, acc[q]), acc[q] = 0.f;
+                g = gr;
+            }
+            float v[4];
+            ld4(x + (int64_t)r * ld + c0, v);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[q] += v[q];
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) atomicAdd(out + (int64_t)g * ld + c0 + q, acc[q]);
+    }
+}
+
+template <typename T>
+__global__ void k_add_graph_vec(const T* __restrict__ x, const float* __restrict__ v,
+                                const int32_t* __restrict__ node_graph, int64_t N, int ld, T* __restrict__ y) {
+    const int vpr = ld / 4;
+    const int64_t total = N * vpr;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / vpr;
+        const int c0 = (int)(i - r * vpr) * 4;
+        float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4];
+        if (x) ld4(x + r * ld + c0, a);
+        ld4(v + (int64_t)node_graph[r] * ld + c0, b);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) a[q] += b[q];
+        st4(y + r * ld + c0, a);
+    }
+}
+
+// ------------------------------------------------------------------ column statistics (BN)
+// grid-stride over row blocks; thread owns one 4-channel vector column group; fp32 partials per
+// thread over <= ROWS_PER_BLOCK rows, then one fp64 atomic per (block, channel).
+constexpr int STAT_ROWS = 64;
+template <typename T, bool SQ>
+__global__ void k_colstats(const T* __restrict__ x, int64_t M, int ld, double* __restrict__ stats) {
+    const int64_t r0 = (int64_t)blockIdx.y * STAT_ROWS;
+    const int64_t r1 = min(r0 + STAT_ROWS, M);
+    const int c0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (c0 >= ld) return;
+    float s[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int64_t r = r0; r < r1; ++r) {
+        float v[4];
+        ld4(x + r * ld + c0, v);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            s[q] += v[q];
+            if (SQ) s2[q] = fmaf(v[q], v[q], s2[q]);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        atomicAdd(stats + c0 + q, (double)s[q]);
+        if (SQ) atomicAdd(stats + ld + c0 + q, (double)s2[q]);
+    }
+}
+
+__global__ void k_bn_finalize(const double* __restrict__ stats, int64_t M, int d, int ld,
+                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                              float* running_mean, float* running_var, int64_t* nbt, float momentum, float eps,
+                              int training, float* __restrict__ ssmr) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == 0 && training && nbt) *nbt += 1;
+    if (c >= ld) return;
+    float scale = 0.f, shift = 0.f, mean = 0.f, rstd = 0.f;
+    if (c < d) {
+        if (training) {
+            const double mu = stats[c] / (double)M;
+            double var = stats[ld + c] / (double)M - mu * mu;
+            if (var < 0) var = 0;
+            mean = (float)mu;
+            rstd = (float)(1.0 / sqrt(var + (double)eps));
+            if (running_mean) {
+                const double unb = M > 1 ? var * ((double)M / (double)(M - 1)) : var;
+                running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+                running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+            }
+        } else {
+            mean = running_mean[c];
+            rstd = rsqrtf(running_var[c] + eps);
+        }
+        scale = gamma[c] * rstd;
+        shift = beta[c] - mean * scale;
+    }
+    ssmr[c] = scale;
+    ssmr[ld + c] = shift;
+    ssmr[2 * ld + c] = mean;
+    ssmr[3 * ld + c] = rstd;
+}
+
+template <typename T>
+__global__ void k_bn_apply(const T* __restrict__ x, int64_t M, int ld, const float* __restrict__ ssmr, int relu,
+                           const T* __restrict__ resid, const float* __restrict__ gvec,
+                           const int32_t* __restrict__ node_graph, T* __restrict__ y) {
+    const int vpr = ld / 4;
+    const int64_t total = M * vpr;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / vpr;
+        const int c0 = (int)(i - r * vpr) * 4;
+        float v[4], sc[4], sh[4];
+        ld4(x + r * ld + c0, v);
+        ld4(ssmr + c0, sc);
+        ld4(ssmr + ld + c0, sh);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            v[q] = fmaf(v[q], sc[q], sh[q]);
+            if (relu) v[q] = fmaxf(v[q], 0.f);
+        }
+        if (resid) {
+            float t[4];
+            ld4(resid + r * ld + c0, t);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) v[q] += t[q];
+        }
+        if (gvec) {
+            float t[4];
+            ld4(gvec + (int64_t)node_graph[r] * ld + c0, t);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) v[q] += t[q];
+        }
+        st4(y + r * ld + c0, v);
+    }
+}
+
+template <typename T>
+__global__ void k_bn_bwd_reduce(const T* __restrict__ x, const T* __restrict__ dy, int64_t M, int ld,
+                                const float* __restrict__ ssmr, int relu, double* __restrict__ red) {
+    const int64_t r0 = (int64_t)blockIdx.y * STAT_ROWS;
+    const int64_t r1 = min(r0 + STAT_ROWS, M);
+    const int c0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (c0 >= ld) return;
+    float sc[4], sh[4], mu[4], rs[4];
+    ld4(ssmr + c0, sc);
+    ld4(ssmr + ld + c0, sh);
+    ld4(ssmr + 2 * ld + c0, mu);
+    ld4(ssmr + 3 * ld + c0, rs);
+    float s[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int64_t r = r0; r < r1; ++r) {
+        float v[4], g[4];
+        ld4(x + r * ld + c0, v);
+        ld4(dy + r * ld + c0, g);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (relu && fmaf(v[q], sc[q], sh[q]) <= 0.f) g[q] = 0.f;
+            s[q] += g[q];
+            s2[q] = fmaf(g[q], (v[q] - mu[q]) * rs[q], s2[q]);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        atomicAdd(red + c0 + q, (double)s[q]);
+        atomicAdd(red + ld + c0 + q, (double)s2[q]);
+    }
+}
+
+template <typename T>
+__global__ void k_bn_bwd_apply(const T* __restrict__ x, const T* __restrict__ dy, int64_t M, int d, int ld,
+                               const float* __restrict__ ssmr, const float* __restrict__ gamma, int relu,
+                               int training, const double* __restrict__ red, T* __restrict__ dx,
+                               float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    const int vpr = ld / 4;
+    const int64_t total = M * vpr;
+    const float invM = 1.f / (float)M;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / vpr;
+        const int c0 = (int)(i - r * vpr) * 4;
+        float v[4], g[4], sc[4], sh[4], mu[4], rs[4], o[4];
+        ld4(x + r * ld + c0, v);
+        ld4(dy + r * ld + c0, g);
+        ld4(ssmr + c0, sc);
+        ld4(ssmr + ld + c0, sh);
+        ld4(ssmr + 2 * ld + c0, mu);
+        ld4(ssmr + 3 * ld + c0, rs);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (relu && fmaf(v[q], sc[q], sh[q]) <= 0.f) g[q] = 0.f;
+            if (training) {
+                const float xh = (v[q] - mu[q]) * rs[q];
+                const float m0 = (float)red[c0 + q] * invM, m1 = (float)red[ld + c0 + q] * invM;
+                o[q] = sc[q] * (g[q] - m0 - xh * m1);  // sc = gamma * rstd
+            } else {
+                o[q] = sc[q] * g[q];
+            }
+        }
+        st4(dx + r * ld + c0, o);
+        if (r == 0) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (c0 + q < d) {
+                    dgamma[c0 + q] = (float)red[ld + c0 + q];
+                    dbeta[c0 + q] = (float)red[c0 + q];
+                }
+        }
+    }
+    (void)gamma;
+}
+
+// ------------------------------------------------------------------ LayerNorm (+resid, +gather)
+// one warp per row, d <= 1024, d % 4 == 0; lane owns vectors lane, lane+32, ...
+constexpr int LN_MAXV = 8;  // d <= 1024
+template <typename T, int MAXV>
+__global__ void k_layernorm_fwd(const T* __restrict__ x, const T* __restrict__ resid,
+                                const int32_t* __restrict__ in_rows, const float* __restrict__ cls, int64_t M,
+                                int d, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                T* __restrict__ y, T* __restrict__ presum, float* __restrict__ mean_rstd) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const int nv = d / 4;
+    int64_t src = row;
+    if (in_rows) src = in_rows[row];
+    float v[MAXV][4];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) {
+        const int vi = lane + k * 32;
+        if (vi < nv) {
+            if (src >= 0) ld4(x + src * d + vi * 4, v[k]);
+            else if (src == -1 && cls) ld4(cls + vi * 4, v[k]);
+            else v[k][0] = v[k][1] = v[k][2] = v[k][3] = 0.f;
+            if (resid) {
+                float t[4];
+                ld4(resid + row * d + vi * 4, t);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) v[k][q] += t[q];
+            }
+            if (presum) st4(presum + row * d + vi * 4, v[k]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) s += v[k][q];
+        }
+    }
+    const float mean = warp_sum(s) / (float)d;
+    float s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k)
+        if (lane + k * 32 < nv)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float t = v[k][q] - mean;
+                s2 = fmaf(t, t, s2);
+            }
+    const float rstd = rsqrtf(warp_sum(s2) / (float)d + eps);
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) {
+        const int vi = lane + k * 32;
+        if (vi < nv) {
+            float g[4], b[4], o[4];
+            ld4(gamma + vi * 4, g);
+            ld4(beta + vi * 4, b);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) o[q] = fmaf((v[k][q] - mean) * rstd, g[q], b[q]);
+            st4(y + row * d + vi * 4, o);
+        }
+    }
+    if (lane == 0 && mean_rstd) {
+        mean_rstd[2 * row] = mean;
+        mean_rstd[2 * row + 1] = rstd;
+    }
+}
+
+// block = 8 warps; each warp loops over rows (grid-stride); per-lane dgamma/dbeta partials kept in
+// registers and flushed once per block through shared memory + atomics.
+template <typename T, int MAXV>
+__global__ void k_layernorm_bwd(const T* __restrict__ dy, const T* __restrict__ presum,
+                                const float* __restrict__ mean_rstd, const int32_t* __restrict__ out_rows,
+                                int64_t M, int d, const float* __restrict__ gamma, T* __restrict__ dx,
+                                float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dcls) {
+    extern __shared__ float sh[];  // [2*d]
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int nv = d / 4;
+    for (int i = threadIdx.x; i < 2 * d; i += blockDim.x) sh[i] = 0.f;
+    __syncthreads();
+    float ag[MAXV][4], ab[MAXV][4];
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) ag[k][q] = ab[k][q] = 0.f;
+    for (int64_t row = blockIdx.x * (int64_t)nw + wid; row < M; row += (int64_t)gridDim.x * nw) {
+        const float mean = mean_rstd[2 * row], rstd = mean_rstd[2 * row + 1];
+        float xh[MAXV][4], gy[MAXV][4];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < MAXV; ++k) {
+            const int vi = lane + k * 32;
+            if (vi < nv) {
+                float g[4], t[4], u[4];
+                ld4(gamma + vi * 4, g);
+                ld4(dy + row * d + vi * 4, t);
+                ld4(presum + row * d + vi * 4, u);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    xh[k][q] = (u[q] - mean) * rstd;
+                    ab[k][q] += t[q];
+                    ag[k][q] = fmaf(t[q], xh[k][q], ag[k][q]);
+                    gy[k][q] = t[q] * g[q];
+                    s1 += gy[k][q];
+                    s2 = fmaf(gy[k][q], xh[k][q], s2);
+                }
+            }
+        }
+        s1 = warp_sum(s1) / (float)d;
+        s2 = warp_sum(s2) / (float)d;
+        int64_t dst = row;
+        if (out_rows) dst = out_rows[row];
+#pragma unroll
+        for (int k = 0; k < MAXV; ++k) {
+            const int vi = lane + k * 32;
+            if (vi < nv) {
+                float o[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) o[q] = rstd * (gy[k][q] - s1 - xh[k][q] * s2);
+                if (dst >= 0) st4(dx + dst * d + vi * 4, o);
+                else if (dst == -1 && dcls) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) atomicAdd(dcls + vi * 4 + q, o[q]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) {
+        const int vi = lane + k * 32;
+        if (vi < nv)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                atomicAdd(&sh[vi * 4 + q], ag[k][q]);
+                atomicAdd(&sh[d + vi * 4 + q], ab[k][q]);
+            }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < d; i += blockDim.x) {
+        atomicAdd(dgamma + i, sh[i]);
+        atomicAdd(dbeta + i, sh[d + i]);
+    }
+}
+
+// ------------------------------------------------------------------ row gather / scatter
+template <typename T>
+__global__ void k_gather_rows(const T* __restrict__ src, const int32_t* __restrict__ rows,
+                              const float* __restrict__ cls, int64_t M, int ld, T* __restrict__ dst) {
+    const int vpr = ld / 4;
+    const int64_t total = M * vpr;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / vpr;
+        const int c0 = (int)(i - r * vpr) * 4;
+        const int64_t s = rows[r];
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (s >= 0) ld4(src + s * ld + c0, v);
+        else if (s == -1 && cls) ld4(cls + c0, v);
+        st4(dst + r * ld + c0, v);
+    }
+}
+
+// ddst[rows[r]] = dsrc[r] for rows >= 0 (a permutation: no conflicts); rows == -1 accumulate into dcls
+template <typename T>
+__global__ void k_scatter_rows(const T* __restrict__ dsrc, const int32_t* __restrict__ rows, int64_t M, int ld,
+                               T* __restrict__ ddst, float* __restrict__ dcls) {
+    const int vpr = ld / 4;
+    const int64_t total = M * vpr;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / vpr;
+        const int c0 = (int)(i - r * vpr) * 4;
+        const int64_t s = rows[r];
+        if (s == -2) continue;
+        float v[4];
+        ld4(dsrc + r * ld + c0, v);
+        if (s >= 0) st4(ddst + s * ld + c0, v);
+        else if (dcls) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) atomicAdd(dcls + c0 + q, v[q]);
+        }
+    }
+}
+
+// public pad_batch layout (reference modules/utils.py:5-29): padded[p, g, :] = h[off_g + n_g - S + p]
+// for p >= S - min(n_g, S), else 0; mask[g, p] = 1 where padded.
+template <typename T>
+__global__ void k_pad_fwd(const T* __restrict__ h, const int32_t* __restrict__ node_off, int64_t B, int64_t S,
+                          int ld, T* __restrict__ padded, uint8_t* __restrict__ mask) {
+    const int vpr = ld / 4;
+    const int64_t total = S * B * vpr;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t pg = i / vpr;
+        const int c0 = (int)(i - pg * vpr) * 4;
+        const int64_t p = pg / B, g = pg - p * B;
+        const int32_t off = node_off[g], n = node_off[g + 1] - off;
+        const int64_t k = n < S ? n : S;
+        const bool valid = p >= S - k;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (valid) ld4(h + ((int64_t)off + n - S + p) * ld + c0, v);
+        st4(padded + pg * ld + c0, v);
+        if (c0 == 0 && mask) mask[g * S + p] = valid ? 0 : 1;
+    }
+}
+
+template <typename T>
+__global__ void k_pad_bwd(const T* __restrict__ dpadded, const int32_t* __restrict__ node_off,
+                          const int32_t* __restrict__ node_graph, int64_t B, int64_t S, int64_t N, int ld,
+                          T* __restrict__ dh) {
+    const int vpr = ld / 4;
+    const int64_t total = N * vpr;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / vpr;
+        const int c0 = (int)(i - r * vpr) * 4;
+        const int g = node_graph[r];
+        const int32_t off = node_off[g], n = node_off[g + 1] - off;
+        const int64_t p = r - off - n + S;  // padded position of node r
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (p >= 0) ld4(dpadded + (p * B + g) * ld + c0, v);
+        st4(dh + r * ld + c0, v);
+    }
+}
+
+// ------------------------------------------------------------------ embedding-sum node encoders
+constexpr int EMB_MAXCOL = 12;
+struct EmbCols {
+    const int64_t* idx[EMB_MAXCOL];
+    int64_t stride[EMB_MAXCOL];
+    int64_t clamp[EMB_MAXCOL];
+    const float* table[EMB_MAXCOL];
+    float* dtable[EMB_MAXCOL];
+    int ncol;
+};
+
+template <typename T>
+__global__ void k_embed_fwd(EmbCols cols, int64_t N, int d, int ld, T* __restrict__ out) {
+    const int vpr = ld / 4;
+    const int64_t total = N * vpr;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / vpr;
+        const int c0 = (int)(i - r * vpr) * 4;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        if (c0 < d) {  // d % 4 == 0 is required for table rows
+            for (int c = 0; c < cols.ncol; ++c) {
+                int64_t id = cols.idx[c][r * cols.stride[c]];
+                if (id > cols.clamp[c]) id = cols.clamp[c];
+                float v[4];
+                ld4(cols.table[c] + id * d + c0, v);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[q] += v[q];
+            }
+        }
+        st4(out + r * ld + c0, acc);
+    }
+}
+
+template <typename T>
+__global__ void k_embed_bwd(EmbCols cols, int64_t N, int d, int ld, const T* __restrict__ dout) {
+    const int vpr = d / 4;
+    const int64_t total = N * vpr;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / vpr;
+        const int c0 = (int)(i - r * vpr) * 4;
+        float g[4];
+        ld4(dout + r * ld + c0, g);
+        for (int c = 0; c < cols.ncol; ++c) {
+            int64_t id = cols.idx[c][r * cols.stride[c]];
+            if (id > cols.clamp[c]) id = cols.clamp[c];
+            float* row = cols.dtable[c] + id * d + c0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) atomicAdd(row + q, g[q]);
+        }
+    }
+}
+
+// dz = dy where y > 0 else 0 (backward of a ReLU fused into a producer's epilogue)
+template <typename T>
+__global__ void k_relu_bwd(const T* __restrict__ dy, const T* __restrict__ y, int64_t n4, T* __restrict__ dz) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        float g[4], v[4];
+        ld4(dy + i * 4, g);
+        ld4(y + i * 4, v);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) g[q] = v[q] > 0.f ? g[q] : 0.f;
+        st4(dz + i * 4, g);
+    }
+}
+
+template <typename TI, typename TO>
+__global__ void k_cast_pad(const TI* __restrict__ src, int64_t rows_in, int64_t cols_in, int64_t ld_in,
+                           TO* __restrict__ dst, int64_t rows_out, int64_t cols_out, int64_t ld_out) {
+    const int64_t total = rows_out * cols_out;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / cols_out, c = i - r * cols_out;
+        float v = 0.f;
+        if (r < rows_in && c < cols_in) v = to_f(src[r * ld_in + c]);
+        dst[r * ld_out + c] = from_f<TO>(v);
+    }
+}
+
+// out[n] = sum_m X[m, n]; block (32 x 8): 32 columns, 8 row lanes, grid.y row slabs + atomics
+template <typename T>
+__global__ void k_colsum(const T* __restrict__ X, int64_t M, int64_t N, int64_t ld, float* __restrict__ out) {
+    __shared__ float sh[8][33];
+    const int64_t c = blockIdx.x * 32 + threadIdx.x;
+    const int64_t rows_per = (M + gridDim.y - 1) / gridDim.y;
+    const int64_t r0 = blockIdx.y * rows_per, r1 = min(r0 + rows_per, M);
+    float s = 0.f;
+    if (c < N)
+        for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) s += to_f(X[r * ld + c]);
+    sh[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < N) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += sh[k][threadIdx.x];
+        atomicAdd(out + c, t);
+    }
+}
+
+}  // namespace gt
+
+using namespace gt;
+
+#define ST ((cudaStream_t)stream)
+
+extern "C" int gt_segment_sum(int dt, const void* x, const int32_t* node_graph, int64_t N, int32_t ld, float* out,
+                              void* stream) {
+    GT_CHECK_ARG(N > 0 && ld > 0 && ld % 4 == 0, "gt_segment_sum: bad shape");
+    GT_DISPATCH_DT(dt, (k_segment_sum<T><<<(int)((N + 31) / 32), 128, 0, ST>>>((const T*)x, node_graph, (int)N, ld, out)));
+    GT_LAUNCH_CHECK("gt_segment_sum");
+    return 0;
+}
+
+extern "C" int gt_add_graph_vec(int dt, const void* x, const float* v, const int32_t* node_graph, int64_t N,
+                                int32_t ld, void* y, void* stream) {
+    GT_CHECK_ARG(N > 0 && ld > 0 && ld % 4 == 0, "gt_add_graph_vec: bad shape");
+    GT_DISPATCH_DT(dt, (k_add_graph_vec<T><<<blocks_for(N * (ld / 4), 256), 256, 0, ST>>>((const T*)x, v, node_graph, N, ld, (T*)y)));
+    GT_LAUNCH_CHECK("gt_add_graph_vec");
+    return 0;
+}
+
+extern "C" int gt_colstats(int dt, const void* x, int64_t M, int32_t ld, double* stats, void* stream) {
+    GT_CHECK_ARG(M > 0 && ld > 0 && ld % 4 == 0, "gt_colstats: bad shape");
+    dim3 grid((ld / 4 + 63) / 64, (unsigned)((M + STAT_ROWS - 1) / STAT_ROWS));
+    GT_DISPATCH_DT(dt, (k_colstats<T, true><<<grid, 64, 0, ST>>>((const T*)x, M, ld, stats)));
+    GT_LAUNCH_CHECK("gt_colstats");
+    return 0;
+}
+
+extern "C" int gt_bn_finalize(const double* stats, int64_t M, int32_t d, int32_t ld, const float* gamma,
+                              const float* beta, float* running_mean, float* running_var, int64_t* nbt,
+                              float momentum, float eps, int training, float* ssmr, void* stream) {
+    GT_CHECK_ARG(M > 0 && d > 0 && ld >= d, "gt_bn_finalize: bad shape");
+    GT_CHECK_ARG(training || (running_mean && running_var), "gt_bn_finalize: eval mode needs running stats");
+    k_bn_finalize<<<(ld + 127) / 128, 128, 0, ST>>>(stats, M, d, ld, gamma, beta, running_mean, running_var, nbt,
+                                                    momentum, eps, training, ssmr);
+    GT_LAUNCH_CHECK("gt_bn_finalize");
+    return 0;
+}
+
+extern "C" int gt_bn_apply_fwd(int dt, const void* x, int64_t M, int32_t d, int32_t ld, const float* ssmr, int relu,
+                               const void* resid, const float* gvec, const int32_t* node_graph, void* y,
+                               void* stream) {
+    GT_CHECK_ARG(M > 0 && ld >= d && ld % 4 == 0, "gt_bn_apply_fwd: bad shape");
+    GT_CHECK_ARG(!gvec || node_graph, "gt_bn_apply_fwd: gvec needs node_graph");
+    GT_DISPATCH_DT(dt, (k_bn_apply<T><<<blocks_for(M * (ld / 4), 256), 256, 0, ST>>>((const T*)x, M, ld, ssmr, relu, (const T*)resid, gvec, node_graph, (T*)y)));
+    GT_LAUNCH_CHECK("gt_bn_apply_fwd");
+    return 0;
+}
+
+extern "C" int gt_bn_bwd_reduce(int dt, const void* x, const void* dy, int64_t M, int32_t d, int32_t ld,
+                                const float* ssmr, int relu, double* red, void* stream) {
+    GT_CHECK_ARG(M > 0 && ld >= d && ld % 4 == 0, "gt_bn_bwd_reduce: bad shape");
+    dim3 grid((ld / 4 + 63) / 64, (unsigned)((M + STAT_ROWS - 1) / STAT_ROWS));
+    GT_DISPATCH_DT(dt, (k_bn_bwd_reduce<T><<<grid, 64, 0, ST>>>((const T*)x, (const T*)dy, M, ld, ssmr, relu, red)));
+    GT_LAUNCH_CHECK("gt_bn_bwd_reduce");
+    return 0;
+}
+
+extern "C" int gt_bn_bwd_apply(int dt, const void* x, const void* dy, int64_t M, int32_t d, int32_t ld,
+                               const float* ssmr, const float* gamma, int relu, int training, const double* red,
+                               void* dx, float* dgamma, float* dbeta, void* stream) {
+    GT_CHECK_ARG(M > 0 && ld >= d && ld % 4 == 0, "gt_bn_bwd_apply: bad shape");
+    GT_DISPATCH_DT(dt, (k_bn_bwd_apply<T><<<blocks_for(M * (ld / 4), 256), 256, 0, ST>>>((const T*)x, (const T*)dy, M, d, ld, ssmr, gamma, relu, training, red, (T*)dx, dgamma, dbeta)));
+    GT_LAUNCH_CHECK("gt_bn_bwd_apply");
+    return 0;
+}
+
+extern "C" int gt_layernorm_fwd(int dt, const void* x, const void* resid, const int32_t* in_rows, const float* cls,
+                                int64_t M, int32_t d, const float* gamma, const float* beta, float eps, void* y,
+                                void* presum, float* mean_rstd, void* stream) {
+    GT_CHECK_ARG(M > 0 && d > 0 && d % 4 == 0 && d <= LN_MAXV * 128, "gt_layernorm_fwd: d=%d must be a multiple of 4 and <= %d", d, LN_MAXV * 128);
+    GT_DISPATCH_DT(dt, {
+        if (d <= 256) k_layernorm_fwd<T, 2><<<(int)((M + 7) / 8), 256, 0, ST>>>((const T*)x, (const T*)resid, in_rows, cls, M, d, gamma, beta, eps, (T*)y, (T*)presum, mean_rstd);
+        else k_layernorm_fwd<T, LN_MAXV><<<(int)((M + 7) / 8), 256, 0, ST>>>((const T*)x, (const T*)resid, in_rows, cls, M, d, gamma, beta, eps, (T*)y, (T*)presum, mean_rstd);
+    });
+    GT_LAUNCH_CHECK("gt_layernorm_fwd");
+    return 0;
+}
+
+extern "C" int gt_layernorm_bwd(int dt, const void* dy, const void* presum, const float* mean_rstd,
+                                const int32_t* out_rows, int64_t M, int32_t d, const float* gamma, void* dx,
+                                float* dgamma, float* dbeta, float* dcls, void* stream) {
+    GT_CHECK_ARG(M > 0 && d > 0 && d % 4 == 0 && d <= LN_MAXV * 128, "gt_layernorm_bwd: bad d=%d", d);
+    const int grid = blocks_for(M, 8 * 4, kNumSMs * 4);
+    GT_DISPATCH_DT(dt, {
+        if (d <= 256) k_layernorm_bwd<T, 2><<<grid, 256, 2 * d * sizeof(float), ST>>>((const T*)dy, (const T*)presum, mean_rstd, out_rows, M, d, gamma, (T*)dx, dgamma, dbeta, dcls);
+        else k_layernorm_bwd<T, LN_MAXV><<<grid, 256, 2 * d * sizeof(float), ST>>>((const T*)dy, (const T*)presum, mean_rstd, out_rows, M, d, gamma, (T*)dx, dgamma, dbeta, dcls);
+    });
+    GT_LAUNCH_CHECK("gt_layernorm_bwd");
+    return 0;
+}
+
+extern "C" int gt_gather_rows(int dt, const void* src, const int32_t* rows, const float* cls, int64_t M, int32_t ld,
+                              void* dst, void* stream) {
+    GT_CHECK_ARG(M > 0 && ld > 0 && ld % 4 == 0, "gt_gather_rows: bad shape");
+    GT_DISPATCH_DT(dt, (k_gather_rows<T><<<blocks_for(M * (ld / 4), 256), 256, 0, ST>>>((const T*)src, rows, cls, M, ld, (T*)dst)));
+    GT_LAUNCH_CHECK("gt_gather_rows");
+    return 0;
+}
+
+extern "C" int gt_scatter_rows(int dt, const void* dsrc, const int32_t* rows, int64_t M, int32_t ld, void* ddst,
+                               float* dcls, void* stream) {
+    GT_CHECK_ARG(M > 0 && ld > 0 && ld % 4 == 0, "gt_scatter_rows: bad shape");
+    GT_DISPATCH_DT(dt, (k_scatter_rows<T><<<blocks_for(M * (ld / 4), 256), 256, 0, ST>>>((const T*)dsrc, rows, M, ld, (T*)ddst, dcls)));
+    GT_LAUNCH_CHECK("gt_scatter_rows");
+    return 0;
+}
+
+extern "C" int gt_pad_batch_fwd(int dt, const void* h, const int32_t* node_off, int64_t B, int64_t S, int32_t ld,
+                                void* padded, uint8_t* mask, void* stream) {
+    GT_CHECK_ARG(B > 0 && S > 0 && ld > 0 && ld % 4 == 0, "gt_pad_batch_fwd: bad shape");
+    GT_DISPATCH_DT(dt, (k_pad_fwd<T><<<blocks_for(S * B * (ld / 4), 256), 256, 0, ST>>>((const T*)h, node_off, B, S, ld, (T*)padded, mask)));
+    GT_LAUNCH_CHECK("gt_pad_batch_fwd");
+    return 0;
+}
+
+extern "C" int gt_pad_batch_bwd(int dt, const void* dpadded, const int32_t* node_off, const int32_t* node_graph,
+                                int64_t B, int64_t S, int64_t N, int32_t ld, void* dh, void* stream) {
+    GT_CHECK_ARG(B > 0 && S > 0 && N > 0 && ld % 4 == 0, "gt_pad_batch_bwd: bad shape");
+    GT_DISPATCH_DT(dt, (k_pad_bwd<T><<<blocks_for(N * (ld / 4), 256), 256, 0, ST>>>((const T*)dpadded, node_off, node_graph, B, S, N, ld, (T*)dh)));
+    GT_LAUNCH_CHECK("gt_pad_batch_bwd");
+    return 0;
+}
+
+static int fill_cols(EmbCols& c, int32_t ncol, const int64_t* const* idx, const int64_t* stride,
+                     const int64_t* clamp, const float* const* table, float* const* dtable) {
+    GT_CHECK_ARG(ncol >= 1 && ncol <= EMB_MAXCOL, "embed: ncol=%d not in 1..%d", ncol, EMB_MAXCOL);
+    c.ncol = ncol;
+    for (int i = 0; i < ncol; ++i) {
+        c.idx[i] = idx[i];
+        c.stride[i] = stride[i];
+        c.clamp[i] = clamp[i];
+        c.table[i] = table ? table[i] : nullptr;
+        c.dtable[i] = dtable ? dtable[i] : nullptr;
+    }
+    return 0;
+}
+
+extern "C" int gt_embed_sum_fwd(int dt, void* out, int64_t N, int32_t d, int32_t ld, int32_t ncol,
+                                const int64_t* const* idx_host, const int64_t* stride_host,
+                                const int64_t* clamp_host, const float* const* table_host, void* stream) {
+    GT_CHECK_ARG(N > 0 && d % 4 == 0 && ld >= d && ld % 4 == 0, "gt_embed_sum_fwd: d=%d must be a multiple of 4", d);
+    EmbCols c;
+    if (int r = fill_cols(c, ncol, idx_host, stride_host, clamp_host, table_host, nullptr)) return r;
+    GT_DISPATCH_DT(dt, (k_embed_fwd<T><<<blocks_for(N * (ld / 4), 256), 256, 0, ST>>>(c, N, d, ld, (T*)out)));
+    GT_LAUNCH_CHECK("gt_embed_sum_fwd");
+    return 0;
+}
+
+extern "C" int gt_embed_sum_bwd(int dt, const void* dout, int64_t N, int32_t d, int32_t ld, int32_t ncol,
+                                const int64_t* const* idx_host, const int64_t* stride_host,
+                                const int64_t* clamp_host, float* const* dtable_host, void* stream) {
+    GT_CHECK_ARG(N > 0 && d % 4 == 0 && ld >= d && ld % 4 == 0, "gt_embed_sum_bwd: bad shape");
+    EmbCols c;
+    if (int r = fill_cols(c, ncol, idx_host, stride_host, clamp_host, nullptr, dtable_host)) return r;
+    GT_DISPATCH_DT(dt, (k_embed_bwd<T><<<blocks_for(N * (d / 4), 256), 256, 0, ST>>>(c, N, d, ld, (const T*)dout)));
+    GT_LAUNCH_CHECK("gt_embed_sum_bwd");
+    return 0;
+}
+
+template <typename TI>
+static void cast_pad_out(int dt_out, const TI* src, int64_t ri, int64_t ci, int64_t li, void* dst, int64_t ro,
+                         int64_t co, int64_t lo, cudaStream_t st) {
+    const int grid = blocks_for(ro * co, 256);
+    if (dt_out == GT_F32) k_cast_pad<TI, float><<<grid, 256, 0, st>>>(src, ri, ci, li, (float*)dst, ro, co, lo);
+    else k_cast_pad<TI, bf16><<<grid, 256, 0, st>>>(src, ri, ci, li, (bf16*)dst, ro, co, lo);
+}
+
+extern "C" int gt_cast_pad(int dt_in, const void* src, int64_t rows_in, int64_t cols_in, int64_t ld_in, int dt_out,
+                           void* dst, int64_t rows_out, int64_t cols_out, int64_t ld_out, void* stream) {
+    GT_CHECK_ARG(rows_out >= rows_in && cols_out >= cols_in && ld_out >= cols_out && ld_in >= cols_in, "gt_cast_pad: bad shape");
+    GT_CHECK_ARG((dt_in == GT_F32 || dt_in == GT_BF16) && (dt_out == GT_F32 || dt_out == GT_BF16), "gt_cast_pad: bad dtype");
+    if (rows_out * cols_out == 0) return 0;
+    if (dt_in == GT_F32) cast_pad_out<float>(dt_out, (const float*)src, rows_in, cols_in, ld_in, dst, rows_out, cols_out, ld_out, ST);
+    else cast_pad_out<bf16>(dt_out, (const bf16*)src, rows_in, cols_in, ld_in, dst, rows_out, cols_out, ld_out, ST);
+    GT_LAUNCH_CHECK("gt_cast_pad");
+    return 0;
+}
+
+extern "C" int gt_relu_bwd(int dt, const void* dy, const void* y, int64_t n, void* dz, void* stream) {
+    GT_CHECK_ARG(n > 0 && n % 4 == 0, "gt_relu_bwd: element count must be a positive multiple of 4");
+    GT_DISPATCH_DT(dt, (k_relu_bwd<T><<<blocks_for(n / 4, 256), 256, 0, ST>>>((const T*)dy, (const T*)y, n / 4, (T*)dz)));
+    GT_LAUNCH_CHECK("gt_relu_bwd");
+    return 0;
+}
+
+extern "C" int gt_colsum(int dt, const void* X, int64_t M, int64_t N, int64_t ld, float* out, void* stream) {
+    GT_CHECK_ARG(M > 0 && N > 0 && ld >= N, "gt_colsum: bad shape");
+    cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * N, ST);
+    if (e != cudaSuccess) return cuda_fail(e, "gt_colsum memset");
+    int slabs = (int)((M + 255) / 256);
+    if (slabs > 64) slabs = 64;
+    dim3 grid((unsigned)((N + 31) / 32), slabs), block(32, 8);
+    GT_DISPATCH_DT(dt, (k_colsum<T><<<grid, block, 0, ST>>>((const T*)X, M, N, ld, out)));
+    GT_LAUNCH_CHECK("gt_colsum");
+    return 0;
+}

@@ -1,0 +1,82 @@
+"""GINConv / GCNConv with the reference's constructor, parameters and forward signature
+(reference modules/conv.py:10-71), executed by the fused gather -> edge-embed -> ReLU ->
+segmented-sum kernel (gt_aggregate_*) plus the dense kernels (gt_gemm).  No [E, d] message or
+edge-embedding tensor is ever materialised."""
+import torch
+
+from .. import ops
+from .._lib import CONV_GCN, CONV_GIN, EDGE_LINEAR, EDGE_NONE, EDGE_TABLE
+
+
+def _edge_encoder_args(edge_encoder, edge_attr, plan, d, ld):
+    """Translate the reference's edge_encoder_cls products into the kernel's three edge kinds."""
+    if isinstance(edge_encoder, torch.nn.Linear):            # reference dataset/code.py:117
+        if edge_encoder.in_features <= 4:
+            return dict(edge_kind=EDGE_LINEAR, edge_attr=edge_attr.to(torch.float32), edge_w=edge_encoder.weight,
+                        edge_b=edge_encoder.bias)
+    elif hasattr(edge_encoder, "bond_embedding_list"):        # ogb BondEncoder, reference dataset/mol.py:84
+        embs = [e.weight for e in edge_encoder.bond_embedding_list][: edge_attr.shape[1]]
+        dims = [w.shape[0] for w in embs]
+        table = embs[0]
+        for w in embs[1:]:                                     # mixed-radix combined table (tiny: <= 60 rows)
+            table = (table.unsqueeze(1) + w.unsqueeze(0)).reshape(-1, d)
+        return dict(edge_kind=EDGE_TABLE, etype=plan.edge_type(edge_attr, dims), table=ops.pad_cols(table, ld))
+    elif not isinstance(edge_encoder, torch.nn.Module):       # `zero` closure, reference dataset/tud.py:67-71
+        ee = edge_encoder(edge_attr)
+        if isinstance(ee, (int, float)) and ee == 0:
+            return dict(edge_kind=EDGE_NONE)
+        raise RuntimeError("unsupported edge encoder product")
+    # any other module: one table row per edge (same kernel, gradients flow back through autograd)
+    ee = edge_encoder(edge_attr)
+    etype = torch.arange(ee.shape[0], dtype=torch.int32, device=ee.device)
+    return dict(edge_kind=EDGE_TABLE, etype=etype, table=ops.pad_cols(ee.to(torch.float32), ld))
+
+
+class _ConvBase(torch.nn.Module):
+    def _prep(self, x, edge_index, plan):
+        d = self.emb_dim
+        ld = ops.ldp(d)
+        logical = x.shape[1] != ld or x.dtype != ops.act_dtype()
+        if logical:
+            x = ops.pad_cols(x, ld, ops.act_dtype())
+        if plan is None:
+            plan = ops.GraphPlan(edge_index, torch.zeros(x.shape[0], dtype=torch.long, device=x.device), 1)
+        return x, plan, d, ld, logical
+
+
+### GIN convolution along the graph structure
+class GINConv(_ConvBase):
+    def __init__(self, emb_dim: int, edge_encoder_cls):
+        super().__init__()
+        self.emb_dim = emb_dim
+        self.mlp = torch.nn.Sequential(
+            torch.nn.Linear(emb_dim, 2 * emb_dim), torch.nn.BatchNorm1d(2 * emb_dim), torch.nn.ReLU(),
+            torch.nn.Linear(2 * emb_dim, emb_dim))
+        self.eps = torch.nn.Parameter(torch.Tensor([0]))
+        self.edge_encoder = edge_encoder_cls(emb_dim)
+
+    def forward(self, x, edge_index, edge_attr, plan=None):
+        x, plan, d, ld, logical = self._prep(x, edge_index, plan)
+        enc = _edge_encoder_args(self.edge_encoder, edge_attr, plan, d, ld)
+        z = ops.aggregate(x, plan, CONV_GIN, d, self.eps, **enc)          # (1+eps) x + sum relu(x_j + e)
+        z = ops.linear(z, self.mlp[0].weight, self.mlp[0].bias)
+        z = ops.batch_norm(z, self.mlp[1], relu=True)
+        out = ops.linear(z, self.mlp[3].weight, self.mlp[3].bias)
+        return out[:, :d].float() if logical else out
+
+
+### GCN convolution along the graph structure
+class GCNConv(_ConvBase):
+    def __init__(self, emb_dim, edge_encoder_cls):
+        super().__init__()
+        self.emb_dim = emb_dim
+        self.linear = torch.nn.Linear(emb_dim, emb_dim)
+        self.root_emb = torch.nn.Embedding(1, emb_dim)
+        self.edge_encoder = edge_encoder_cls(emb_dim)
+
+    def forward(self, x, edge_index, edge_attr, plan=None):
+        x, plan, d, ld, logical = self._prep(x, edge_index, plan)
+        enc = _edge_encoder_args(self.edge_encoder, edge_attr, plan, d, ld)
+        xl = ops.linear(x, self.linear.weight, self.linear.bias)
+        out = ops.aggregate(xl, plan, CONV_GCN, d, self.root_emb.weight, **enc)
+        return out[:, :d].float() if logical else out

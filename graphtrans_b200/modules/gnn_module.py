@@ -1,0 +1,152 @@
+"""GNN stacks with the reference's API (reference modules/gnn_module.py:18-248): node encoder ->
+L x (conv -> BatchNorm1d -> ReLU -> dropout [-> residual]) -> JK, optional virtual node.  The
+layer loop is re-expressed over physical [N, ld] matrices; BN-apply, ReLU, residual and the
+next layer's virtual-node broadcast are one kernel (gt_bn_apply_fwd)."""
+import torch
+
+from .. import ops
+from .conv import GCNConv, GINConv
+
+
+def _encode(node_encoder, batched_data):
+    x = batched_data.x
+    node_depth = batched_data.node_depth if hasattr(batched_data, "node_depth") else None
+    if node_encoder is None:
+        return x
+    return node_encoder(x) if node_depth is None else node_encoder(x, node_depth.view(-1,))
+
+
+def _plan_of(batched_data, max_input_len=1000):
+    plan = getattr(batched_data, "_gt_plan", None)
+    if plan is None or plan.L != int(max_input_len):
+        plan = ops.GraphPlan(batched_data.edge_index, batched_data.batch, getattr(batched_data, "num_graphs", None),
+                             max_input_len)
+    return plan
+
+
+class _GNNBase(torch.nn.Module):
+    @staticmethod
+    def need_deg():
+        return False
+
+    def _init_common(self, num_layer, emb_dim, node_encoder, edge_encoder_cls, drop_ratio, JK, residual, gnn_type):
+        self.num_layer = num_layer
+        self.emb_dim = emb_dim
+        self.drop_ratio = drop_ratio
+        self.JK = JK
+        self.residual = residual
+        if self.num_layer < 2:
+            raise ValueError("Number of GNN layers must be greater than 1.")
+        self.node_encoder = node_encoder
+        self.convs = torch.nn.ModuleList()
+        self.batch_norms = torch.nn.ModuleList()
+        for _ in range(num_layer):
+            if gnn_type == "gin":
+                self.convs.append(GINConv(emb_dim, edge_encoder_cls))
+            elif gnn_type == "gcn":
+                self.convs.append(GCNConv(emb_dim, edge_encoder_cls))
+            else:
+                raise ValueError("Undefined GNN type called {}".format(gnn_type))
+            self.batch_norms.append(torch.nn.BatchNorm1d(emb_dim))
+
+    def _input(self, batched_data, perturb):
+        d, ld = self.emb_dim, ops.ldp(self.emb_dim)
+        if isinstance(self.node_encoder, torch.nn.Linear):     # TU datasets, reference dataset/tud.py:65
+            h = ops.linear(ops.pad_cols(batched_data.x, ops.ldp(batched_data.x.shape[1]), ops.act_dtype()),
+                           self.node_encoder.weight, self.node_encoder.bias)
+        else:
+            h = _encode(self.node_encoder, batched_data)
+            if h.shape[1] != ld or h.dtype != ops.act_dtype():
+                h = ops.pad_cols(h, ld, ops.act_dtype())
+        if perturb is not None:                                   # FLAG, reference gnn_module.py:78,191
+            h = h + ops.pad_cols(perturb, ld, h.dtype)
+        return h
+
+    def _jk(self, h_list):
+        """returns (list of physical matrices to concatenate logically, logical width of each)"""
+        if self.JK == "last":
+            return [h_list[-1]]
+        if self.JK == "sum":                                     # omits the final layer (gnn_module.py:100-103)
+            out = h_list[0]
+            for layer in range(1, self.num_layer):
+                out = out + h_list[layer]
+            return [out]
+        if self.JK == "cat":
+            return [h_list[0], h_list[-1]]
+        raise ValueError(self.JK)
+
+    def forward(self, batched_data, perturb=None):
+        parts = self.forward_parts(batched_data, perturb)
+        d = self.emb_dim
+        return torch.cat([p[:, :d].float() for p in parts], dim=-1)
+
+
+### GNN to generate node embedding
+class GNN_node(_GNNBase):
+    def __init__(self, num_layer, emb_dim, node_encoder, edge_encoder_cls, drop_ratio=0.5, JK="last", residual=False,
+                 gnn_type="gin"):
+        super().__init__()
+        self._init_common(num_layer, emb_dim, node_encoder, edge_encoder_cls, drop_ratio, JK, residual, gnn_type)
+
+    def forward_parts(self, batched_data, perturb=None, plan=None):
+        plan = plan or _plan_of(batched_data)
+        edge_index, edge_attr = batched_data.edge_index, batched_data.edge_attr
+        h_list = [self._input(batched_data, perturb)]
+        for layer in range(self.num_layer):
+            h = self.convs[layer](h_list[layer], edge_index, edge_attr, plan=plan)
+            h = ops.batch_norm(h, self.batch_norms[layer], relu=layer != self.num_layer - 1,
+                               resid=h_list[layer] if self.residual else None,
+                               drop_p=self.drop_ratio if self.training else 0.0)
+            h_list.append(h)
+        return self._jk(h_list)
+
+
+### Virtual GNN to generate node embedding
+class GNN_node_Virtualnode(_GNNBase):
+    def __init__(self, num_layer, emb_dim, node_encoder, edge_encoder_cls, drop_ratio=0.5, JK="last", residual=False,
+                 gnn_type="gin"):
+        super().__init__()
+        self._init_common(num_layer, emb_dim, node_encoder, edge_encoder_cls, drop_ratio, JK, residual, gnn_type)
+        ### set the initial virtual node embedding to 0.
+        self.virtualnode_embedding = torch.nn.Embedding(1, emb_dim)
+        torch.nn.init.constant_(self.virtualnode_embedding.weight.data, 0)
+        ### List of MLPs to transform virtual node at every layer
+        self.mlp_virtualnode_list = torch.nn.ModuleList()
+        for _ in range(num_layer - 1):
+            self.mlp_virtualnode_list.append(torch.nn.Sequential(
+                torch.nn.Linear(emb_dim, 2 * emb_dim), torch.nn.BatchNorm1d(2 * emb_dim), torch.nn.ReLU(),
+                torch.nn.Linear(2 * emb_dim, emb_dim), torch.nn.BatchNorm1d(emb_dim), torch.nn.ReLU()))
+
+    def forward_parts(self, batched_data, perturb=None, plan=None):
+        plan = plan or _plan_of(batched_data)
+        edge_index, edge_attr = batched_data.edge_index, batched_data.edge_attr
+        d, ld = self.emb_dim, ops.ldp(self.emb_dim)
+        h0 = self._input(batched_data, perturb)
+        # per-graph virtual-node state, fp32 [B, ld] (the VN MLP always runs in fp32: its BatchNorm
+        # is over only B rows and amplifies low-precision noise)
+        vn = ops.pad_cols(self.virtualnode_embedding.weight, ld).expand(plan.B, ld)
+        h_list = [ops.add_graph_vec(h0, vn, plan)]              # h + vn[batch]  (gnn_module.py:199)
+        drop = self.drop_ratio if self.training else 0.0
+        for layer in range(self.num_layer):
+            hv = h_list[layer]
+            vn_next = None
+            if layer < self.num_layer - 1:                       # gnn_module.py:217-229
+                mlp = self.mlp_virtualnode_list[layer]
+                t = ops.segment_sum(hv, plan, init=vn)            # global_add_pool(h_list[layer]) + vn
+                t = ops.batch_norm(ops.linear(t, mlp[0].weight, mlp[0].bias), mlp[1], relu=True)
+                t = ops.batch_norm(ops.linear(t, mlp[3].weight, mlp[3].bias), mlp[4], relu=True, drop_p=drop)
+                vn_next = vn + t if self.residual else t
+            h = self.convs[layer](hv, edge_index, edge_attr, plan=plan)
+            # BN -> ReLU (not last) -> dropout -> (+residual) -> (+ next layer's vn[batch]) in one kernel
+            h = ops.batch_norm(h, self.batch_norms[layer], relu=layer != self.num_layer - 1,
+                               resid=hv if self.residual else None, gvec=vn_next, plan=plan, drop_p=drop)
+            h_list.append(h)
+            vn = vn_next
+        return self._jk(h_list)
+
+
+def GNNNodeEmbedding(virtual_node, *args, **kwargs):
+    if virtual_node:
+        return GNN_node_Virtualnode(*args, **kwargs)
+    else:
+        return GNN_node(*args, **kwargs)

@@ -1,0 +1,582 @@
+"""Autograd-visible operators over the C-ABI kernels (host side of the hot path).
+
+Every forward AND backward here is a hand-written sm_100a kernel reached through
+graphtrans_b200._lib.call; torch is used for memory (torch.empty/zeros) and for autograd
+bookkeeping only.  Feature matrices are physical [rows, ld] tensors with ld = ldp(d) (logical
+width d, zero pad columns), see include/graphtrans_b200.h.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import torch
+
+from . import _lib
+from ._lib import (CONV_GCN, CONV_GIN, EDGE_LINEAR, EDGE_NONE, EDGE_TABLE, EPI_ACCUM, EPI_OUT_F32,
+                   EPI_RELU, GT_BF16, GT_F32, call, dt_of, ptr)
+
+_PRECISION = os.environ.get("GT_PRECISION", "fp32")
+GEMM_IMPL = int(os.environ.get("GT_GEMM_IMPL", "0"))   # 0 auto, 1 CUDA-core, 2 tcgen05 only
+MHA_IMPL = int(os.environ.get("GT_MHA_IMPL", "0"))
+
+
+def set_precision(p: str):
+    """'fp32': fp32 activations + exact fp32 contractions (parity mode, <=1e-3 contract);
+    'bf16': bf16 activations, tcgen05 bf16 contractions with fp32 accumulate (throughput mode)."""
+    global _PRECISION
+    assert p in ("fp32", "bf16")
+    _PRECISION = p
+
+
+def precision() -> str:
+    return _PRECISION
+
+
+def act_dtype() -> torch.dtype:
+    return torch.bfloat16 if _PRECISION == "bf16" else torch.float32
+
+
+def ldp(d: int) -> int:
+    """physical leading dimension: logical width rounded up to 8 elements (16 B in bf16)."""
+    return (d + 7) // 8 * 8
+
+
+def pad_cols(x: torch.Tensor, ld: int, dtype=None) -> torch.Tensor:
+    """[rows, d] (any float dtype, any stride) -> contiguous [rows, ld] of `dtype`, zero padded."""
+    dtype = dtype or x.dtype
+    rows, d = x.shape
+    if d == ld and x.dtype == dtype and x.is_contiguous():
+        return x
+    return _CastPadFn.apply(x, ld, dtype)
+
+
+class _CastPadFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, ld, dtype):
+        x = x.contiguous() if x.stride(-1) != 1 else x
+        rows, d = x.shape
+        out = torch.empty(rows, ld, dtype=dtype, device=x.device)
+        call("gt_cast_pad", dt_of(x), ptr(x), rows, d, x.stride(0), dt_of(out), ptr(out), rows, ld, ld)
+        ctx.meta = (d, x.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        d, dtype = ctx.meta
+        g = g.contiguous()
+        rows, ld = g.shape
+        out = torch.empty(rows, d, dtype=dtype, device=g.device)
+        call("gt_cast_pad", dt_of(g), ptr(g), rows, d, ld, dt_of(out), ptr(out), rows, d, d)
+        return out, None, None
+
+
+def cast_to(x: torch.Tensor, dtype) -> torch.Tensor:
+    """dtype change of a physical [rows, ld] matrix (differentiable)."""
+    if x.dtype == dtype:
+        return x
+    return _CastPadFn.apply(x, x.shape[1], dtype)
+
+
+# ----------------------------------------------------------------------------- graph plan
+class GraphPlan:
+    """Integer metadata of one batch: both CSRs and the packed-token plan. Built on device by
+    gt_csr_build / gt_batch_plan without any host synchronisation (B comes from
+    `batch.num_graphs` when present, otherwise one .item() like reference gnn_module.py:195)."""
+
+    def __init__(self, edge_index, batch, num_graphs=None, max_input_len=1000, edge_attr=None):
+        _lib.require_cuda(edge_index, batch)
+        dev = batch.device
+        N = batch.numel()
+        E = edge_index.shape[1]
+        B = int(num_graphs) if num_graphs is not None else int(batch[-1].item()) + 1
+        self.N, self.E, self.B, self.L = N, E, B, int(max_input_len)
+        i32 = dict(dtype=torch.int32, device=dev)
+        ei = edge_index.contiguous()
+        self.rowptr_dst = torch.empty(N + 1, **i32)
+        self.rowptr_src = torch.empty(N + 1, **i32)
+        self.src_by_dst = torch.empty(max(E, 1), **i32)
+        self.eid_by_dst = torch.empty(max(E, 1), **i32)
+        self.dst_by_src = torch.empty(max(E, 1), **i32)
+        self.eid_by_src = torch.empty(max(E, 1), **i32)
+        work = torch.empty(2 * (N + 1), **i32)
+        call("gt_csr_build", ptr(ei), E, N, ptr(self.rowptr_dst), ptr(self.src_by_dst), ptr(self.eid_by_dst),
+             ptr(self.rowptr_src), ptr(self.dst_by_src), ptr(self.eid_by_src), ptr(work))
+        self.node_off = torch.empty(B + 1, **i32)
+        self.kept = torch.empty(B, **i32)
+        self.tok_off = torch.empty(B + 1, **i32)
+        self.n_rows = N + B  # static upper bound of packed token rows (exact when nothing is truncated)
+        self.tok2node = torch.empty(self.n_rows, **i32)
+        self.tok_graph = torch.empty(self.n_rows, **i32)
+        self.node_graph = torch.empty(N, **i32)
+        self.node2tok = torch.empty(N, **i32)
+        self.cls_rows = torch.empty(B, **i32)
+        self.scalars = torch.empty(4, **i32)
+        b = batch.contiguous()
+        call("gt_batch_plan", ptr(b), N, B, self.L, ptr(self.node_off), ptr(self.kept), ptr(self.tok_off),
+             ptr(self.tok2node), ptr(self.tok_graph), ptr(self.node_graph), ptr(self.node2tok),
+             ptr(self.cls_rows), ptr(self.scalars))
+        self._etype = {}
+        self._S = None
+
+    def edge_type(self, edge_attr: torch.Tensor, dims) -> torch.Tensor:
+        """combined categorical edge id (mixed radix over `dims`) for table edge encoders."""
+        key = (edge_attr.data_ptr(), tuple(dims))
+        if key not in self._etype:
+            mult, m = [], 1
+            for dsz in reversed(dims):
+                mult.append(m)
+                m *= dsz
+            mult = list(reversed(mult))
+            et = torch.empty(max(self.E, 1), dtype=torch.int32, device=edge_attr.device)
+            ea = edge_attr.contiguous()
+            arr = (ctypes.c_int32 * len(mult))(*mult)
+            call("gt_edge_type", ptr(ea), self.E, len(mult), arr, ptr(et))
+            self._etype[key] = et
+        return self._etype[key]
+
+    @property
+    def S(self) -> int:
+        """padded length min(max n_i, L) - needs one device->host read (public pad_batch API only)."""
+        if self._S is None:
+            self._S = int(self.scalars[0].item())
+        return self._S
+
+
+# ----------------------------------------------------------------------------- node encoders
+class _EmbedSumFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, meta, *tables):
+        idx, strides, clamps, N, d, ld, dtype = meta
+        out = torch.empty(N, ld, dtype=dtype, device=tables[0].device)
+        n = len(tables)
+        a_idx = (ctypes.c_void_p * n)(*[t.data_ptr() for t in idx])
+        a_str = (ctypes.c_int64 * n)(*strides)
+        a_clp = (ctypes.c_int64 * n)(*clamps)
+        a_tab = (ctypes.c_void_p * n)(*[t.data_ptr() for t in tables])
+        call("gt_embed_sum_fwd", dt_of(out), ptr(out), N, d, ld, n, a_idx, a_str, a_clp, a_tab)
+        ctx.meta = meta
+        ctx.shapes = [t.shape for t in tables]
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        idx, strides, clamps, N, d, ld, dtype = ctx.meta
+        g = g.contiguous()
+        n = len(idx)
+        grads = [torch.zeros(s, dtype=torch.float32, device=g.device) for s in ctx.shapes]
+        a_idx = (ctypes.c_void_p * n)(*[t.data_ptr() for t in idx])
+        a_str = (ctypes.c_int64 * n)(*strides)
+        a_clp = (ctypes.c_int64 * n)(*clamps)
+        a_tab = (ctypes.c_void_p * n)(*[t.data_ptr() for t in grads])
+        call("gt_embed_sum_bwd", dt_of(g), ptr(g), N, d, ld, n, a_idx, a_str, a_clp, a_tab)
+        return (None, *grads)
+
+
+def embed_sum(index_cols, tables, clamps=None):
+    """out[i] = sum_c tables[c][min(index_cols[c][i], clamp_c)] -> physical [N, ldp(d)].
+    index_cols: list of int64 1-D views (any stride) of length N."""
+    d = tables[0].shape[1]
+    N = index_cols[0].shape[0]
+    if d % 4:
+        raise RuntimeError("embedding width must be a multiple of 4")
+    strides = [c.stride(0) if c.dim() else 1 for c in index_cols]
+    clamps = clamps or [t.shape[0] - 1 for t in tables]
+    meta = (list(index_cols), strides, list(clamps), N, d, ldp(d), act_dtype())
+    return _EmbedSumFn.apply(meta, *[t.contiguous() for t in tables])
+
+
+# ----------------------------------------------------------------------------- dense layers
+def _gemm(A, a_mn, lda, Bm, b_mn, ldb, C, ldc, M, N, K, n_fill, bias, resid, ldr, flags, impl=None):
+    call("gt_gemm", dt_of(A), ptr(A), int(a_mn), lda, ptr(Bm), int(b_mn), ldb, ptr(C), ldc, M, N, K, n_fill,
+         ptr(bias), ptr(resid), ldr, flags, GEMM_IMPL if impl is None else impl)
+
+
+class _LinearFn(torch.autograd.Function):
+    """y = x W^T + b (optional fused ReLU). x physical [M, ld_in] (logical K = W.shape[1]);
+    y physical [M, ldp(N)] in x.dtype (or fp32 when out_f32)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, relu, out_f32, resid=None):
+        x = x.contiguous()
+        M, ld_in = x.shape
+        N, K = weight.shape
+        if K > ld_in:
+            raise RuntimeError(f"linear: input width {ld_in} < in_features {K}")
+        if x.dtype == torch.float32:
+            w = weight.contiguous()
+            ldw = K
+        else:  # bf16 operand copy of the fp32 master weight, K padded so rows stay 16-B aligned
+            w = torch.empty(N, ld_in, dtype=x.dtype, device=x.device)
+            call("gt_cast_pad", GT_F32, ptr(weight.contiguous()), N, K, K, dt_of(w), ptr(w), N, ld_in, ld_in)
+            ldw = ld_in
+        ld_out = ldp(N)
+        out_dtype = torch.float32 if out_f32 else x.dtype
+        y = torch.empty(M, ld_out, dtype=out_dtype, device=x.device)
+        flags = (EPI_RELU if relu else 0) | (EPI_OUT_F32 if out_f32 and x.dtype != torch.float32 else 0)
+        if resid is not None:
+            resid = resid.contiguous()
+            if resid.dtype != out_dtype or resid.shape != y.shape:
+                raise RuntimeError("linear: resid must match the output")
+        _gemm(x, 0, ld_in, w, 0, ldw, y, ld_out, M, N, K, ld_out, bias, resid, ld_out, flags)
+        ctx.save_for_backward(x, w, y if relu else None)
+        ctx.meta = (M, N, K, ld_in, ldw, ld_out, relu, bias is not None, resid is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w, y = ctx.saved_tensors
+        M, N, K, ld_in, ldw, ld_out, relu, has_bias, has_resid = ctx.meta
+        gy = gy.contiguous()
+        g_res = gy if has_resid else None
+        if gy.dtype != x.dtype:  # fp32 head logits: bring the gradient to the operand dtype
+            g2 = torch.empty(M, ld_out, dtype=x.dtype, device=x.device)
+            call("gt_cast_pad", dt_of(gy), ptr(gy), M, ld_out, ld_out, dt_of(g2), ptr(g2), M, ld_out, ld_out)
+            gy = g2
+        if relu:
+            yy = y if y.dtype == gy.dtype else None
+            gz = torch.empty_like(gy)
+            call("gt_relu_bwd", dt_of(gy), ptr(gy), ptr(yy), gy.numel(), ptr(gz))
+            gy = gz
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty(M, ld_in, dtype=x.dtype, device=x.device)
+            # dX[m,k] = sum_n dY[m,n] W[n,k]: B operand = W read "MN-major" (k contiguous)
+            _gemm(gy, 0, ld_out, w, 1, ldw, gx, ld_in, M, K, N, ld_in, None, None, 0, 0)
+        if ctx.needs_input_grad[1]:
+            gw = torch.zeros(N, K, dtype=torch.float32, device=x.device)
+            # dW[n,k] = sum_m dY[m,n] X[m,k]: both operands MN-major, split-K over the rows
+            _gemm(gy, 1, ld_out, x, 1, ld_in, gw, K, N, K, M, K, None, None, 0, EPI_ACCUM | EPI_OUT_F32)
+        if has_bias and ctx.needs_input_grad[2]:
+            gb = torch.empty(N, dtype=torch.float32, device=x.device)
+            call("gt_colsum", dt_of(gy), ptr(gy), M, N, ld_out, ptr(gb))
+        return gx, gw, gb, None, None, g_res
+
+
+def linear(x, weight, bias=None, relu=False, out_f32=False, resid=None):
+    return _LinearFn.apply(x, weight, bias, relu, out_f32, resid)
+
+
+# ----------------------------------------------------------------------------- aggregation
+class _AggregateFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, plan, conv, d, edge_kind, edge_attr, edge_w, edge_b, etype, table, self_param):
+        x = x.contiguous()
+        N, ld = x.shape
+        out = torch.empty_like(x)
+        kdim = edge_w.shape[1] if edge_kind == EDGE_LINEAR else 0
+        if edge_kind == EDGE_LINEAR:
+            edge_attr = edge_attr.contiguous()
+            edge_w = edge_w.contiguous()
+        if edge_kind == EDGE_TABLE:
+            table = table.contiguous()
+            if table.shape[1] != ld or table.dtype != torch.float32:
+                raise RuntimeError("edge table must be fp32 [ntypes, ld]")
+        sp = self_param.contiguous().view(-1)
+        call("gt_aggregate_fwd", dt_of(x), conv, ptr(x), ptr(out), N, d, ld, ptr(plan.rowptr_dst),
+             ptr(plan.src_by_dst), ptr(plan.eid_by_dst), ptr(plan.rowptr_src), edge_kind, ptr(edge_attr), kdim,
+             ptr(edge_w), ptr(edge_b), ptr(etype), ptr(table), ptr(sp))
+        ctx.save_for_backward(x, edge_attr, edge_w, edge_b, etype, table, sp)
+        ctx.meta = (plan, conv, d, edge_kind, kdim, self_param.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, edge_attr, edge_w, edge_b, etype, table, sp = ctx.saved_tensors
+        plan, conv, d, edge_kind, kdim, sp_shape = ctx.meta
+        g = g.contiguous()
+        N, ld = x.shape
+        dx = torch.empty_like(x)
+        f32 = dict(dtype=torch.float32, device=x.device)
+        dw = torch.zeros(d, kdim, **f32) if edge_kind == EDGE_LINEAR else None
+        db = torch.zeros(d, **f32) if edge_kind == EDGE_LINEAR else None
+        dtab = torch.zeros_like(table) if edge_kind == EDGE_TABLE else None
+        dself = torch.zeros(sp.numel(), **f32)
+        call("gt_aggregate_bwd", dt_of(x), conv, ptr(x), ptr(g), ptr(dx), N, d, ld, ptr(plan.rowptr_dst),
+             ptr(plan.rowptr_src), ptr(plan.dst_by_src), ptr(plan.eid_by_src), edge_kind, ptr(edge_attr), kdim,
+             ptr(edge_w), ptr(edge_b), ptr(etype), ptr(table), ptr(sp), ptr(dw), ptr(db), ptr(dtab), ptr(dself))
+        return dx, None, None, None, None, None, dw, db, None, dtab, dself.view(sp_shape)
+
+
+def aggregate(x, plan, conv, d, self_param, edge_kind=EDGE_NONE, edge_attr=None, edge_w=None, edge_b=None,
+              etype=None, table=None):
+    return _AggregateFn.apply(x, plan, conv, d, edge_kind, edge_attr, edge_w, edge_b, etype, table, self_param)
+
+
+# ----------------------------------------------------------------------------- segment ops
+class _SegmentSumFn(torch.autograd.Function):
+    """global_add_pool: [N, ld] -> fp32 [B, ld]"""
+
+    @staticmethod
+    def forward(ctx, x, plan, init=None):
+        x = x.contiguous()
+        N, ld = x.shape
+        out = torch.zeros(plan.B, ld, dtype=torch.float32, device=x.device) if init is None else init.clone()
+        call("gt_segment_sum", dt_of(x), ptr(x), ptr(plan.node_graph), N, ld, ptr(out))
+        ctx.meta = (plan, x.dtype, N, ld)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        plan, dtype, N, ld = ctx.meta
+        g = g.contiguous()
+        dx = torch.empty(N, ld, dtype=dtype, device=g.device)
+        call("gt_add_graph_vec", dt_of(dx), None, ptr(g), ptr(plan.node_graph), N, ld, ptr(dx))
+        return dx, None, g
+
+
+def segment_sum(x, plan, init=None):
+    """out[g] = init[g] + sum_{i in g} x[i]  (global_add_pool; fp32 [B, ld])"""
+    return _SegmentSumFn.apply(x, plan, init)
+
+
+class _AddGraphVecFn(torch.autograd.Function):
+    """y[i] = x[i] + v[graph(i)], v fp32 [B, ld]"""
+
+    @staticmethod
+    def forward(ctx, x, v, plan):
+        x = x.contiguous()
+        v = v.contiguous()
+        N, ld = x.shape
+        y = torch.empty_like(x)
+        call("gt_add_graph_vec", dt_of(x), ptr(x), ptr(v), ptr(plan.node_graph), N, ld, ptr(y))
+        ctx.meta = (plan, N, ld)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        plan, N, ld = ctx.meta
+        g = g.contiguous()
+        dv = None
+        if ctx.needs_input_grad[1]:
+            dv = torch.zeros(plan.B, ld, dtype=torch.float32, device=g.device)
+            call("gt_segment_sum", dt_of(g), ptr(g), ptr(plan.node_graph), N, ld, ptr(dv))
+        return g, dv, None
+
+
+def add_graph_vec(x, v, plan):
+    return _AddGraphVecFn.apply(x, v, plan)
+
+
+# ----------------------------------------------------------------------------- BatchNorm1d
+class _BatchNormFn(torch.autograd.Function):
+    """y = act(BN(x)) [+ resid] [+ gvec[graph]] on physical [M, ld]; train mode uses batch stats
+    and updates the running buffers in place exactly like nn.BatchNorm1d."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, nbt, training, momentum, eps, relu, resid,
+                gvec, plan):
+        x = x.contiguous()
+        M, ld = x.shape
+        d = gamma.shape[0]
+        dev = x.device
+        ssmr = torch.empty(4 * ld, dtype=torch.float32, device=dev)
+        stats = None
+        if training:
+            stats = torch.zeros(2 * ld, dtype=torch.float64, device=dev)
+            call("gt_colstats", dt_of(x), ptr(x), M, ld, ptr(stats))
+        call("gt_bn_finalize", ptr(stats), M, d, ld, ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var),
+             ptr(nbt), float(momentum), float(eps), int(training), ptr(ssmr))
+        y = torch.empty_like(x)
+        if resid is not None:
+            resid = resid.contiguous()
+        if gvec is not None:
+            gvec = gvec.contiguous()
+        call("gt_bn_apply_fwd", dt_of(x), ptr(x), M, d, ld, ptr(ssmr), int(relu), ptr(resid), ptr(gvec),
+             ptr(plan.node_graph) if gvec is not None else None, ptr(y))
+        ctx.save_for_backward(x, ssmr, gamma)
+        ctx.meta = (M, d, ld, relu, training, plan, resid is not None, gvec is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, ssmr, gamma = ctx.saved_tensors
+        M, d, ld, relu, training, plan, has_resid, has_gvec = ctx.meta
+        g = g.contiguous()
+        dev = x.device
+        red = torch.zeros(2 * ld, dtype=torch.float64, device=dev)
+        call("gt_bn_bwd_reduce", dt_of(x), ptr(x), ptr(g), M, d, ld, ptr(ssmr), int(relu), ptr(red))
+        dx = torch.empty_like(x)
+        dgamma = torch.empty(d, dtype=torch.float32, device=dev)
+        dbeta = torch.empty(d, dtype=torch.float32, device=dev)
+        call("gt_bn_bwd_apply", dt_of(x), ptr(x), ptr(g), M, d, ld, ptr(ssmr), ptr(gamma), int(relu),
+             int(training), ptr(red), ptr(dx), ptr(dgamma), ptr(dbeta))
+        dres = g if has_resid else None
+        dgv = None
+        if has_gvec and ctx.needs_input_grad[11]:
+            dgv = torch.zeros(plan.B, ld, dtype=torch.float32, device=dev)
+            call("gt_segment_sum", dt_of(g), ptr(g), ptr(plan.node_graph), M, ld, ptr(dgv))
+        return dx, dgamma, dbeta, None, None, None, None, None, None, None, dres, dgv, None
+
+
+def batch_norm(x, bn: torch.nn.BatchNorm1d, relu=False, resid=None, gvec=None, plan=None):
+    training = bn.training or bn.running_mean is None
+    return _BatchNormFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked,
+                              training, bn.momentum, bn.eps, relu, resid, gvec, plan)
+
+
+# ----------------------------------------------------------------------------- LayerNorm / tokens
+class _LayerNormFn(torch.autograd.Function):
+    """y = LN(x[in_rows] (+cls for -1 rows) + resid). Rows = len(in_rows) if given else x rows."""
+
+    @staticmethod
+    def forward(ctx, x, resid, gamma, beta, eps, in_rows, cls, n_rows):
+        x = x.contiguous()
+        d = gamma.shape[0]
+        if x.shape[1] != d:
+            raise RuntimeError("layer_norm expects unpadded rows (d_model % 8 == 0)")
+        M = n_rows if in_rows is not None else x.shape[0]
+        dev = x.device
+        y = torch.empty(M, d, dtype=x.dtype, device=dev)
+        presum = torch.empty(M, d, dtype=x.dtype, device=dev) if (resid is not None or in_rows is not None) else None
+        mr = torch.empty(2 * M, dtype=torch.float32, device=dev)
+        if resid is not None:
+            resid = resid.contiguous()
+        clsv = cls.contiguous().view(-1) if cls is not None else None
+        call("gt_layernorm_fwd", dt_of(x), ptr(x), ptr(resid), ptr(in_rows), ptr(clsv), M, d, ptr(gamma), ptr(beta),
+             float(eps), ptr(y), ptr(presum), ptr(mr))
+        ctx.save_for_backward(presum if presum is not None else x, mr, gamma)
+        ctx.meta = (M, d, in_rows, x.shape[0], resid is not None, cls.shape if cls is not None else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        presum, mr, gamma = ctx.saved_tensors
+        M, d, rows, x_rows, has_resid, cls_shape = ctx.meta
+        g = g.contiguous()
+        dev = g.device
+        if rows is not None:
+            dx = torch.zeros(x_rows, d, dtype=g.dtype, device=dev)
+        else:
+            dx = torch.empty(M, d, dtype=g.dtype, device=dev)
+        dgamma = torch.zeros(d, dtype=torch.float32, device=dev)
+        dbeta = torch.zeros(d, dtype=torch.float32, device=dev)
+        dcls = torch.zeros(d, dtype=torch.float32, device=dev) if cls_shape is not None else None
+        call("gt_layernorm_bwd", dt_of(g), ptr(g), ptr(presum), ptr(mr), ptr(rows), M, d, ptr(gamma), ptr(dx),
+             ptr(dgamma), ptr(dbeta), ptr(dcls))
+        return (dx, dx if has_resid else None, dgamma, dbeta, None, None,
+                dcls.view(cls_shape) if dcls is not None else None, None)
+
+
+def layer_norm(x, ln: torch.nn.LayerNorm, resid=None, in_rows=None, cls=None, n_rows=None):
+    return _LayerNormFn.apply(x, resid, ln.weight, ln.bias, ln.eps, in_rows, cls, n_rows)
+
+
+class _GatherRowsFn(torch.autograd.Function):
+    """dst[r] = src[rows[r]] (rows -1 -> cls vector, -2 -> zeros)"""
+
+    @staticmethod
+    def forward(ctx, src, rows, cls, n_rows):
+        src = src.contiguous()
+        ld = src.shape[1]
+        dst = torch.empty(n_rows, ld, dtype=src.dtype, device=src.device)
+        clsv = cls.contiguous().view(-1) if cls is not None else None
+        call("gt_gather_rows", dt_of(src), ptr(src), ptr(rows), ptr(clsv), n_rows, ld, ptr(dst))
+        ctx.meta = (rows, src.shape[0], ld, n_rows, cls.shape if cls is not None else None)
+        return dst
+
+    @staticmethod
+    def backward(ctx, g):
+        rows, src_rows, ld, n_rows, cls_shape = ctx.meta
+        g = g.contiguous()
+        dsrc = torch.zeros(src_rows, ld, dtype=g.dtype, device=g.device)
+        dcls = torch.zeros(ld, dtype=torch.float32, device=g.device) if cls_shape is not None else None
+        call("gt_scatter_rows", dt_of(g), ptr(g), ptr(rows), n_rows, ld, ptr(dsrc), ptr(dcls))
+        return dsrc, None, dcls.view(cls_shape) if dcls is not None else None, None
+
+
+def gather_rows(src, rows, cls=None, n_rows=None):
+    return _GatherRowsFn.apply(src, rows, cls, n_rows if n_rows is not None else rows.numel())
+
+
+class _PadBatchFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h, plan, S):
+        h = h.contiguous()
+        N, ld = h.shape
+        padded = torch.empty(S, plan.B, ld, dtype=h.dtype, device=h.device)
+        mask = torch.empty(plan.B, S, dtype=torch.uint8, device=h.device)
+        call("gt_pad_batch_fwd", dt_of(h), ptr(h), ptr(plan.node_off), plan.B, S, ld, ptr(padded), ptr(mask))
+        ctx.meta = (plan, S, N, ld)
+        ctx.mark_non_differentiable(mask)
+        return padded, mask
+
+    @staticmethod
+    def backward(ctx, g, _gm):
+        plan, S, N, ld = ctx.meta
+        g = g.contiguous()
+        dh = torch.empty(N, ld, dtype=g.dtype, device=g.device)
+        call("gt_pad_batch_bwd", dt_of(g), ptr(g), ptr(plan.node_off), ptr(plan.node_graph), plan.B, S, N, ld,
+             ptr(dh))
+        return dh, None, None
+
+
+def pad_batch_dense(h, plan, S):
+    return _PadBatchFn.apply(h, plan, S)
+
+
+# ----------------------------------------------------------------------------- attention
+class _MHAFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv, plan, nhead, key_start=None):
+        qkv = qkv.contiguous()
+        n_rows, d3 = qkv.shape
+        d = d3 // 3
+        dh = d // nhead
+        scale = float(dh) ** -0.5
+        out = torch.empty(n_rows, d, dtype=qkv.dtype, device=qkv.device)
+        lse = torch.empty(nhead * n_rows, dtype=torch.float32, device=qkv.device)
+        call("gt_mha_fwd", dt_of(qkv), ptr(qkv), ptr(plan.tok_graph), ptr(plan.tok_off), ptr(key_start), n_rows,
+             plan.B, nhead, dh, scale, ptr(out), ptr(lse), MHA_IMPL)
+        ctx.save_for_backward(qkv, out, lse)
+        ctx.meta = (plan, nhead, dh, scale, key_start)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        qkv, out, lse = ctx.saved_tensors
+        plan, nhead, dh, scale, key_start = ctx.meta
+        g = g.contiguous()
+        n_rows = qkv.shape[0]
+        dqkv = torch.empty_like(qkv)
+        delta = torch.empty(nhead * n_rows, dtype=torch.float32, device=qkv.device)
+        call("gt_mha_bwd", dt_of(qkv), ptr(qkv), ptr(out), ptr(g), ptr(lse), ptr(plan.tok_graph), ptr(plan.tok_off),
+             ptr(key_start), n_rows, plan.B, nhead, dh, scale, ptr(dqkv), ptr(delta), MHA_IMPL)
+        return dqkv, None, None, None
+
+
+def mha_packed(qkv, plan, nhead, key_start=None):
+    """`plan` needs .tok_graph, .tok_off and .B (GraphPlan or any object with those fields)."""
+    return _MHAFn.apply(qkv, plan, nhead, key_start)
+
+
+# ----------------------------------------------------------------------------- PNA reduce
+class _PNAReduceFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pj, pi, plan, d):
+        pj, pi = pj.contiguous(), pi.contiguous()
+        N, ld = pj.shape
+        out = torch.empty(N, 4 * ld, dtype=pj.dtype, device=pj.device)
+        amax = torch.empty(N, ld, dtype=torch.int32, device=pj.device)
+        amin = torch.empty(N, ld, dtype=torch.int32, device=pj.device)
+        call("gt_pna_reduce_fwd", dt_of(pj), ptr(pj), ptr(pi), N, d, ld, ptr(plan.rowptr_dst), ptr(plan.src_by_dst),
+             ptr(out), ptr(amax), ptr(amin))
+        ctx.save_for_backward(pj, pi, out, amax, amin)
+        ctx.meta = (plan, d)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        pj, pi, out, amax, amin = ctx.saved_tensors
+        plan, d = ctx.meta
+        g = g.contiguous()
+        N, ld = pj.shape
+        dpj = torch.zeros(N, ld, dtype=torch.float32, device=pj.device)
+        dpi = torch.empty_like(pi)
+        call("gt_pna_reduce_bwd", dt_of(pj), ptr(pj), ptr(pi), ptr(out), ptr(g), N, d, ld, ptr(plan.rowptr_dst),
+             ptr(plan.src_by_dst), ptr(amax), ptr(amin), ptr(dpj), ptr(dpi))
+        return cast_to(dpj, pj.dtype), dpi, None, None
+
+
+def pna_reduce(pj, pi, plan, d):
+    return _PNAReduceFn.apply(pj, pi, plan, d)

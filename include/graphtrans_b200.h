@@ -1,0 +1,213 @@
+/*
+ * graphtrans_b200 — C ABI of the B200 (sm_100a) GraphTrans forward/backward hot path.
+ *
+ * The reference (ucbrise/graphtrans) is pure Python: it has no FFI of its own.  Every entry
+ * point below replaces the third-party op that the cited reference call site reaches
+ * (SURVEY.md §2.2 / §8a); the Python host mirror in graphtrans_b200/{models,modules} binds them
+ * with ctypes (graphtrans_b200/_lib.py) exactly as INTEGRATION.md shows.
+ *
+ * Conventions
+ *  - every export returns int: 0 ok, <0 argument/shape/alignment error, >0 cudaError_t;
+ *    gt_last_error() gives the thread-local message.  Nothing throws, exits or prints.
+ *  - all pointers are DEVICE pointers owned by the caller (PyTorch's allocator); the library
+ *    borrows them for the duration of the enqueue and keeps no global mutable state.
+ *  - everything is asynchronous on `stream` (a cudaStream_t), performs no allocation and no
+ *    synchronisation, and is CUDA-graph capturable.
+ *  - feature matrices are row-major [rows, ld] with logical width d <= ld; ld % 4 == 0 and
+ *    16-byte aligned bases.  Columns d..ld-1 are kept zero by every kernel.
+ *  - `dt` is the activation dtype (GT_F32 / GT_BF16); parameters, statistics and parameter
+ *    gradients are always fp32 (statistics accumulators fp64).
+ */
+#ifndef GRAPHTRANS_B200_H
+#define GRAPHTRANS_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { GT_F32 = 0, GT_BF16 = 1 };
+/* edge-encoder kinds (reference dataset/tud.py:67-71, dataset/code.py:117, dataset/mol.py:84) */
+enum { GT_EDGE_NONE = 0, GT_EDGE_LINEAR = 1, GT_EDGE_TABLE = 2 };
+/* aggregation kinds */
+enum { GT_CONV_GCN = 0, GT_CONV_GIN = 1 };
+/* GEMM epilogue flags */
+enum { GT_EPI_RELU = 1, GT_EPI_ACCUM = 2, GT_EPI_OUT_F32 = 4, GT_EPI_RESID_F32 = 8 };
+
+int gt_version(void);
+const char* gt_last_error(void);
+
+/* ---- graph preparation (integer; replaces PyG MessagePassing's index handling and
+ *      torch_geometric.utils.degree, reference modules/conv.py:28,57,63) --------------------
+ * edge_index: int64 [2,E] (row 0 = source, row 1 = target).  Builds, with a stable counting
+ * sort, the target-sorted CSR (rowptr_dst[N+1], src_by_dst[E], eid_by_dst[E]) used by the
+ * forward aggregation and the source-sorted CSR (rowptr_src, dst_by_src, eid_by_src) used by
+ * its adjoint.  out-degree(i) = rowptr_src[i+1]-rowptr_src[i]; in-degree likewise.
+ * work: int32 [2*(N+1)] scratch. */
+int gt_csr_build(const int64_t* edge_index, int64_t E, int64_t N,
+                 int32_t* rowptr_dst, int32_t* src_by_dst, int32_t* eid_by_dst,
+                 int32_t* rowptr_src, int32_t* dst_by_src, int32_t* eid_by_src,
+                 int32_t* work, void* stream);
+
+/* combined edge-type id for table edge encoders: etype[e] = sum_c attr[e,c] * mult[c]
+ * (ogb BondEncoder, reference dataset/mol.py:84: 5*6*2 = 60 combinations). */
+int gt_edge_type(const int64_t* edge_attr, int64_t E, int32_t ncol, const int32_t* mult_host,
+                 int32_t* etype, void* stream);
+
+/* ---- batch plan (integer, bit-exact; closed form of reference modules/utils.py:5-29) ------
+ * batch: int64 [N] sorted graph ids, B graphs, L = max_input_len.
+ * node_off[B+1]; kept[B] = min(n_i, L); tok_off[B+1] = exclusive scan of kept+1 (packed
+ * token layout: graph i owns token rows [tok_off[i], tok_off[i+1]), its last row is <CLS>);
+ * tok2node[N+B]: node id, -1 for <CLS>, -2 for unused tail rows; tok_graph[N+B]: graph id or
+ * -1; node_graph[N]: int32 copy of batch; node2tok[N]: token row of a node or -1 when truncated
+ * away; cls_rows[B]: token row of each graph's <CLS>;
+ * scalars[4] = {S = min(max n_i, L), n_tok, max n_i, 0}. */
+int gt_batch_plan(const int64_t* batch, int64_t N, int64_t B, int64_t L,
+                  int32_t* node_off, int32_t* kept, int32_t* tok_off, int32_t* tok2node,
+                  int32_t* tok_graph, int32_t* node_graph, int32_t* node2tok, int32_t* cls_rows,
+                  int32_t* scalars, void* stream);
+
+/* ---- node encoders (reference dataset/utils.py:28-30 ASTNodeEncoder, ogb AtomEncoder) ------
+ * out[i,:] = sum_c table_c[min(idx_c[i*stride_c], clamp_c), :].  ncol <= 12.  All arrays of
+ * per-column descriptors are HOST arrays. */
+int gt_embed_sum_fwd(int dt, void* out, int64_t N, int32_t d, int32_t ld, int32_t ncol,
+                     const int64_t* const* idx_host, const int64_t* stride_host,
+                     const int64_t* clamp_host, const float* const* table_host, void* stream);
+int gt_embed_sum_bwd(int dt, const void* dout, int64_t N, int32_t d, int32_t ld, int32_t ncol,
+                     const int64_t* const* idx_host, const int64_t* stride_host,
+                     const int64_t* clamp_host, float* const* dtable_host, void* stream);
+
+/* ---- stage 1: message-passing aggregation (reference modules/conv.py:26-33, 50-68) ---------
+ * GCN: out[i] = sum_{e:(j->i)} rsqrt(deg_j) rsqrt(deg_i) relu(x[j]+ee_e) + relu(x[i]+root)/deg_i,
+ *      deg = out-degree + 1 (conv.py:57);   GIN: out[i] = (1+eps) x[i] + sum relu(x[j]+ee_e).
+ * Edge embedding ee_e is recomputed in-kernel: LINEAR: ee = b + W[:, :kdim] attr_e (W is the
+ * nn.Linear weight [d,kdim], attr fp32 [E,kdim], kdim <= 4); TABLE: ee = table[etype_e] (fp32
+ * [ntypes, ld]); NONE: 0.  `self_param`: root_emb [d] (GCN) or eps [1] (GIN), fp32. */
+int gt_aggregate_fwd(int dt, int conv, const void* x, void* out, int64_t N, int32_t d, int32_t ld,
+                     const int32_t* rowptr_dst, const int32_t* src_by_dst, const int32_t* eid_by_dst,
+                     const int32_t* rowptr_src,
+                     int edge_kind, const float* edge_attr, int32_t kdim, const float* edge_w,
+                     const float* edge_b, const int32_t* etype, const float* table,
+                     const float* self_param, void* stream);
+/* adjoint: dx (same dtype), and fp32 accumulators (must be zeroed by the caller):
+ * d_edge_w [d,kdim], d_edge_b [d] (LINEAR) or d_table [ntypes, ld] (TABLE), d_self ([d] or [1]). */
+int gt_aggregate_bwd(int dt, int conv, const void* x, const void* dout, void* dx, int64_t N,
+                     int32_t d, int32_t ld,
+                     const int32_t* rowptr_dst, const int32_t* rowptr_src, const int32_t* dst_by_src,
+                     const int32_t* eid_by_src,
+                     int edge_kind, const float* edge_attr, int32_t kdim, const float* edge_w,
+                     const float* edge_b, const int32_t* etype, const float* table,
+                     const float* self_param,
+                     float* d_edge_w, float* d_edge_b, float* d_table, float* d_self, void* stream);
+
+/* ---- per-graph segment ops (PyG global_add_pool / vn[batch], reference
+ *      modules/gnn_module.py:199,219) --------------------------------------------------------
+ * segment_sum: out[g,:] (fp32 [B,ld], pre-zeroed unless init given) += sum_{i in g} x[i,:] */
+int gt_segment_sum(int dt, const void* x, const int32_t* node_graph, int64_t N, int32_t ld,
+                   float* out, void* stream);
+/* y[i,:] = x[i,:] + v[node_graph[i],:]   (v fp32 [B,ld]); x may be NULL (pure broadcast) */
+int gt_add_graph_vec(int dt, const void* x, const float* v, const int32_t* node_graph, int64_t N,
+                     int32_t ld, void* y, void* stream);
+
+/* ---- BatchNorm1d, train/eval (reference modules/gnn_module.py:58,84,164,167; conv.py:19) ---
+ * colstats: stats[0:ld] += sum_rows x, stats[ld:2ld] += sum_rows x^2 (fp64, pre-zeroed). */
+int gt_colstats(int dt, const void* x, int64_t M, int32_t ld, double* stats, void* stream);
+/* finalize: from stats (train) or running stats (eval) produce scale/shift (y = x*scale+shift)
+ * and mean/rstd; in train mode update running_mean/var (momentum, unbiased var) and ++nbt. */
+int gt_bn_finalize(const double* stats, int64_t M, int32_t d, int32_t ld, const float* gamma,
+                   const float* beta, float* running_mean, float* running_var, int64_t* nbt,
+                   float momentum, float eps, int training, float* scale_shift_mean_rstd,
+                   void* stream);
+/* y = act(x*scale+shift) [+ resid] [+ gvec[node_graph]] ; act = relu if relu!=0 */
+int gt_bn_apply_fwd(int dt, const void* x, int64_t M, int32_t d, int32_t ld, const float* ssmr,
+                    int relu, const void* resid, const float* gvec, const int32_t* node_graph,
+                    void* y, void* stream);
+/* backward pass 1: g = dy * relu'(x*scale+shift); red[0:ld] += sum g, red[ld:2ld] += sum g*xhat */
+int gt_bn_bwd_reduce(int dt, const void* x, const void* dy, int64_t M, int32_t d, int32_t ld,
+                     const float* ssmr, int relu, double* red, void* stream);
+/* backward pass 2: dx = gamma*rstd*(g - red0/M - xhat*red1/M) (train) or g*scale (eval);
+ * dgamma = red1, dbeta = red0 (fp32 [d]) */
+int gt_bn_bwd_apply(int dt, const void* x, const void* dy, int64_t M, int32_t d, int32_t ld,
+                    const float* ssmr, const float* gamma, int relu, int training, const double* red,
+                    void* dx, float* dgamma, float* dbeta, void* stream);
+
+/* ---- dense contraction (replaces nn.Linear -> cuBLAS, reference modules/conv.py:18-20,44;
+ *      modules/gnn_module.py:161-170; models/gnn_transformer.py:70,85-88; the in/out
+ *      projections and FFN inside nn.TransformerEncoderLayer) --------------------------------
+ * C[m,n] = sum_k A(m,k) B(n,k) (+ bias[n]) (+ resid[m,n]) (relu) ; columns N..n_fill-1 := 0.
+ * a_mn / b_mn: operand stored "MN-major" (element (m,k) at A[k*lda+m]) instead of K-major
+ * (A[m*lda+k]).  A/B dtype = dt; C dtype = dt unless GT_EPI_OUT_F32; GT_EPI_ACCUM adds into C
+ * (fp32 C only; used with splits > 1).  impl: 0 = auto (tcgen05 when eligible), 1 = CUDA-core
+ * reference kernel, 2 = tcgen05 only (error when not eligible). */
+int gt_gemm(int dt, const void* A, int a_mn, int64_t lda, const void* B, int b_mn, int64_t ldb,
+            void* C, int64_t ldc, int64_t M, int64_t N, int64_t K, int64_t n_fill,
+            const float* bias, const void* resid, int64_t ldr, int flags, int impl, void* stream);
+/* dz = dy * (y > 0): backward of a ReLU that was fused into a GEMM epilogue; n % 4 == 0 */
+int gt_relu_bwd(int dt, const void* dy, const void* y, int64_t n, void* dz, void* stream);
+/* out[n] = sum_m X[m,n]  (bias gradients) ; out fp32 [N] overwritten */
+int gt_colsum(int dt, const void* X, int64_t M, int64_t N, int64_t ld, float* out, void* stream);
+/* dst[r, 0:cols_out] = cast(src[r, 0:cols_in]) zero padded to cols_out; rows_out >= rows_in zero padded */
+int gt_cast_pad(int dt_in, const void* src, int64_t rows_in, int64_t cols_in, int64_t ld_in,
+                int dt_out, void* dst, int64_t rows_out, int64_t cols_out, int64_t ld_out, void* stream);
+
+/* ---- token packing + LayerNorm (reference modules/utils.py:5-29 pad_batch,
+ *      modules/transformer_encoder.py:50-57 CLS append + norm_input) --------------------------
+ * layernorm over rows of [M,d] (ld == d): y = LN(x [+ resid]) * gamma + beta ; saves the
+ * pre-norm sum (needed by backward) only implicitly through mean/rstd + xhat recompute.
+ * in_rows (optional int32 [M]): row r reads x[in_rows[r]] (negative -> row of zeros/cls). */
+int gt_layernorm_fwd(int dt, const void* x, const void* resid, const int32_t* in_rows,
+                     const float* cls, int64_t M, int32_t d, const float* gamma, const float* beta,
+                     float eps, void* y, void* presum, float* mean_rstd, void* stream);
+/* dx_sum = dLN/d(presum); dgamma/dbeta accumulated (pre-zeroed fp32 [d]).
+ * out_rows (optional): scatter row r of dx to dx[out_rows[r]] (rows < 0: -1 accumulates into
+ * dcls (fp32 [d], pre-zeroed), -2 dropped); untouched rows of dx must be pre-zeroed by caller. */
+int gt_layernorm_bwd(int dt, const void* dy, const void* presum, const float* mean_rstd,
+                     const int32_t* out_rows, int64_t M, int32_t d, const float* gamma,
+                     void* dx, float* dgamma, float* dbeta, float* dcls, void* stream);
+/* plain row gather/scatter for tokens when no input LayerNorm is configured, and for the
+ * public pad_batch API: dst[r,:] = src[rows[r],:] (rows<0 -> cls or zeros). */
+int gt_gather_rows(int dt, const void* src, const int32_t* rows, const float* cls, int64_t M,
+                   int32_t ld, void* dst, void* stream);
+int gt_scatter_rows(int dt, const void* dsrc, const int32_t* rows, int64_t M, int32_t ld,
+                    void* ddst, float* dcls, void* stream);
+/* public pad_batch layout: padded [S,B,ld] and mask uint8 [B,S] from node features */
+int gt_pad_batch_fwd(int dt, const void* h, const int32_t* node_off, int64_t B, int64_t S, int32_t ld,
+                     void* padded, uint8_t* mask, void* stream);
+int gt_pad_batch_bwd(int dt, const void* dpadded, const int32_t* node_off, const int32_t* node_graph,
+                     int64_t B, int64_t S, int64_t N, int32_t ld, void* dh, void* stream);
+
+/* ---- stage 2: masked multi-head self-attention over packed tokens (replaces
+ *      F.multi_head_attention_forward, reference modules/transformer_encoder.py:28-32,59) -----
+ * qkv [n_rows, 3*d] (q | k | v, heads contiguous inside each), per-row graph id tok_graph and
+ * per-graph token ranges tok_off; keys of a row = all token rows of its graph (padding never
+ * exists in the packed layout, so the -inf key mask of the reference is implicit).
+ * key_start (optional int32 [B]): first valid key row of each graph when the rows of a graph
+ * begin with padding (dense left-padded layout of the public TransformerNodeEncoder API);
+ * NULL = tok_off[g].  out [n_rows, d]; lse fp32 [nhead, n_rows].
+ * impl: 0 auto, 1 CUDA-core, 2 tcgen05. */
+int gt_mha_fwd(int dt, const void* qkv, const int32_t* tok_graph, const int32_t* tok_off,
+               const int32_t* key_start, int64_t n_rows, int64_t B, int32_t nhead, int32_t dh,
+               float scale, void* out, float* lse, int impl, void* stream);
+int gt_mha_bwd(int dt, const void* qkv, const void* out, const void* dout, const float* lse,
+               const int32_t* tok_graph, const int32_t* tok_off, const int32_t* key_start,
+               int64_t n_rows, int64_t B, int32_t nhead, int32_t dh, float scale, void* dqkv,
+               float* delta, int impl, void* stream);
+
+/* ---- PNA multi-aggregator reduce (reference modules/pna_layer.py:131-167 via
+ *      modules/pna/pna_module.py:43-51; aggregators.py:11-34; scalers.py:10-31) ---------------
+ * pj, pi: per-node tower projections [N, ld] (W_j x_j and W_i x_i + b); for
+ * every target i and channel c over in-edges: mean, max, min, std of m = pi[i] + pj[src];
+ * empty segment -> mean=max=min=0, std=sqrt(1e-5).  out [N, 4*ld] = (mean|max|min|std);
+ * argmax/argmin int32 [N, ld] saved for the backward. */
+int gt_pna_reduce_fwd(int dt, const void* pj, const void* pi, int64_t N, int32_t d, int32_t ld,
+                      const int32_t* rowptr_dst, const int32_t* src_by_dst,
+                      void* out, int32_t* argmax, int32_t* argmin, void* stream);
+/* dpj, dpi from dout [N,4*ld]; dpj accumulated with atomics (fp32 [N,ld], pre-zeroed) */
+int gt_pna_reduce_bwd(int dt, const void* pj, const void* pi, const void* out, const void* dout,
+                      int64_t N, int32_t d, int32_t ld, const int32_t* rowptr_dst,
+                      const int32_t* src_by_dst, const int32_t* argmax, const int32_t* argmin,
+                      float* dpj, void* dpi, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
