@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""graphs/sec forward+backward of the GraphTrans hot path on N B200s (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config molpcba|code2|syn|code2-pna|nci1]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...      # the reference's CPU path (oracle port) on the host cores
+
+One "step" = zero_grad -> forward -> loss -> backward (+ bucketed NCCL gradient allreduce when
+N > 1) over one synthetic batch of the named config.  Rank 0 prints ONE JSON line.
+  value : whole-job graphs/s with the batches already resident in HBM (CUDA events, max over ranks)
+  e2e   : same metric through the public model API with HOST (pinned) batches: H2D copy of the
+          step's batch and a D2H read of the loss inside the timed region
+  roofline     : dominant hot-stage kernel class, achieved = algorithmic bytes|flops (SURVEY §8d,
+                 DESIGN.md) / CUDA-event time of those launches, peak from MEASURED_PEAKS.json
+  cpu_baseline : the CPU oracle (port of the reference's PyTorch path) timed on the host cores
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from graphtrans_b200 import synth  # noqa: E402
+
+METRIC = "graphs/sec fwd+bwd"
+UNIT = "graphs/s"
+# CPU sample sizes (graphs per step) keeping the reference arm / cpu_baseline to ~10-30 s of CPU work
+CPU_SAMPLE_B = {"molpcba": 128, "code2": 8, "syn": 32, "code2-pna": 8, "nci1": 32}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="molpcba", choices=list(synth.CONFIGS))
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--batch", type=int, default=None, help="graphs per GPU per step (default: the config's)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--distinct-batches", type=int, default=4)
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], tensor=p.get("bf16_tflops_sustained", p["bf16_tflops"]), source="measured")
+    return dict(hbm=6650.0, tensor=1590.0, source="fallback")
+
+
+def config_args(ns):
+    args = synth.make_args(ns.config)
+    if ns.config == "code2-pna":
+        probe = synth.make_batch(args, B=args.batch_size, seed=1234)
+        args.deg = synth.in_degree_histogram(probe, 800)
+    return args
+
+
+# ----------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """samples SM clock + throttle reasons of this process's GPU every 100 ms via NVML"""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # noqa: BLE001
+            self.nv, self.err = None, repr(e)
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40,
+                 "sw_thermal_slowdown": 0x20, "hw_power_brake": 0x80, "sync_boost": 0x10, "app_clocks": 0x2}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.1)
+
+    def start(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "no NVML samples"}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------------- CPU arm
+def cpu_reference_run(ns, steps, warmup):
+    """Times the CPU oracle (restatement of the reference's PyTorch/PyG path, fp32, all host
+    threads) on a bounded sample of the workload. -> (graphs/s, ms/step, description dict)"""
+    from graphtrans_b200 import factory
+    from oracle import graphtrans_oracle as O
+    args = config_args(ns)
+    args.gnn_dropout = 0.0           # the oracle has no dropout (identity); the product runs the configured p
+    args.transformer_dropout = 0.0
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    Bs = min(CPU_SAMPLE_B[ns.config], ns.batch or args.batch_size)
+    batch = synth.make_batch(args, B=Bs, seed=0)
+    torch.manual_seed(0)
+    sd = factory.build_model(args).state_dict()
+    for _ in range(warmup):
+        O.fwd_bwd(sd, args, batch, dtype=torch.float32)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.fwd_bwd(sd, args, batch, dtype=torch.float32)
+    dt = (time.perf_counter() - t0) / steps
+    return Bs / dt, dt * 1e3, dict(cores=cores, threads=torch.get_num_threads(), kind="port",
+                                   sample=f"{Bs} of {ns.batch or args.batch_size} graphs/step ({ns.config} shape, seed 0), "
+                                          f"fp32, dropout 0, {warmup} warm-up + {steps} timed fwd+bwd steps of "
+                                          f"oracle/graphtrans_oracle.py")
+
+
+def main_reference(ns):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = ns.steps, ns.warmup
+    # bound the arm to a few minutes whatever K the driver passes: cap total CPU steps
+    est_steps = min(steps, 10)
+    gps, ms, desc = cpu_reference_run(ns, est_steps, min(warmup, 2))
+    args = synth.make_args(ns.config)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": gps, "unit": UNIT, "n_gpus": ns.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": ns.scaling, "vs_baseline": None,
+        "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": workload_name(ns, args), "timed_steps": est_steps,
+                   "note": "CPU path of the reference (oracle port; the reference is pure Python and its "
+                           "third-party deps are not installable here, so there is no oracle/_ref)"},
+        "cpu_baseline": {"value": gps, "unit": UNIT, "cores": desc["cores"], "kind": desc["kind"],
+                         "sample": desc["sample"]},
+        "e2e": {"value": gps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(ns, args):
+    B = ns.batch or args.batch_size
+    return (f"{ns.config}: GraphTrans {args.gnn_type.upper() if args.model_type == 'gnn-transformer' else 'PNA'}"
+            f"{'-Virtual' if args.gnn_virtual_node else ''} JK={args.gnn_JK} d_g={args.gnn_emb_dim} "
+            f"L_g={args.gnn_num_layer} d={args.d_model} L_t={args.num_encoder_layers} B={B}/GPU")
+
+
+# ----------------------------------------------------------------------------------- GPU arm
+def algorithmic(args, batch, es):
+    """per-step algorithmic work of the two hot stages for one batch"""
+    N = batch.batch.numel()
+    E = batch.edge_index.shape[1]
+    ea = 0 if batch.edge_attr is None else batch.edge_attr.numel() * batch.edge_attr.element_size()
+    d_g = args.gnn_emb_dim
+    n = torch.bincount(batch.batch)
+    t = n.clamp(max=int(args.max_input_len)) + (1 if args.graph_pooling == "cls" else 0)
+    sum_t2 = float((t.double() ** 2).sum())
+    if args.model_type == "pna-transformer":
+        agg_bytes = N * d_g * es * 3 + 13 * N * d_g * es + 16 * E      # x, pi, pj read; 13F x towers written
+    else:
+        agg_bytes = 2 * N * d_g * es + 16 * E + ea
+    return dict(N=N, E=E, agg_bytes_per_launch=agg_bytes, mha_fwd_flops=4.0 * args.d_model * sum_t2,
+                mha_bwd_flops=8.0 * args.d_model * sum_t2, tokens=int(t.sum()))
+
+
+def main_b200(ns):
+    from graphtrans_b200 import _lib, factory, ops
+    from graphtrans_b200.ddp import GradBuckets
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != ns.gpus:
+        if world == 1 and ns.gpus > 1:
+            raise SystemExit("launch with torchrun for --gpus > 1")
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+    ops.set_precision(ns.precision)
+    args = config_args(ns)
+    B = ns.batch or args.batch_size
+    if ns.scaling == "strong" and world > 1:
+        B = max(2, B // world)
+    lossf = factory.loss_fn(args)
+    torch.manual_seed(0)
+    model = factory.build_model(args).to(dev).train()
+    buckets = GradBuckets(model, n_buckets=4)
+    host_batches = [synth.make_batch(args, B=B, seed=1000 * rank + i).pin_memory() for i in range(ns.distinct_batches)]
+    dev_batches = [b.to(dev) for b in host_batches]
+    ops.manual_seed(1234 + rank, dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)    # > 126 MB L2
+
+    def step(b):
+        buckets.zero_grad()
+        loss = lossf(model(b), b)
+        loss.backward()
+        buckets.finish()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    K, W = ns.steps, ns.warmup
+    for i in range(max(W, 3)):
+        step(dev_batches[i % len(dev_batches)])
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    k0 = _lib.kernel_count
+    evs = []
+    barrier()
+    wall0 = time.perf_counter()
+    for i in range(K):
+        flush.zero_()                                  # L2 flush between timed iterations (outside the events)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step(dev_batches[i % len(dev_batches)])
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = _lib.kernel_count - k0
+    t_dev = sum(a.elapsed_time(b) for a, b in evs) * 1e-3
+    clocks = sampler.stop()
+    tt = torch.tensor([t_dev], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_dev = float(tt)
+    value = B * world * K / t_dev
+
+    # ---- end to end: host (pinned) batches through the public API, H2D + loss D2H inside the timed region
+    e2e = None
+    if not ns.no_e2e:
+        for i in range(2):
+            float(step(host_batches[i % len(host_batches)].to(dev, non_blocking=True)))
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(K):
+            b = host_batches[i % len(host_batches)].to(dev, non_blocking=True)
+            float(step(b))                              # .item(): device->host read of the loss
+        barrier()
+        te = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": B * world * K / float(te), "unit": UNIT,
+               "h2d_bytes_per_step": int(statistics.mean(b.nbytes() for b in host_batches)),
+               "d2h_bytes_per_step": 4}
+
+    # ---- roofline pass (rank 0, separate from the timed region): CUDA events around every C-ABI call
+    roof, roof_all = None, None
+    if not ns.no_roofline and rank == 0:
+        pk = peaks()
+        es = 2 if ns.precision == "bf16" else 4
+        b = dev_batches[0]
+        alg = algorithmic(args, host_batches[0], es)
+        for _ in range(2):
+            step(b)
+        torch.cuda.synchronize()
+        reps = 5
+        _lib.start_profile()
+        for _ in range(reps):
+            step(b)
+        rec = _lib.stop_profile()
+        tot = {}
+        flops = {}
+        for name, ms, a in rec:
+            cls = name
+            tot.setdefault(cls, [0.0, 0])
+            tot[cls][0] += ms
+            tot[cls][1] += 1
+            if name == "gt_gemm":
+                flops["gt_gemm"] = flops.get("gt_gemm", 0.0) + 2.0 * a[9] * a[10] * a[11]
+        step_ms = sum(v[0] for v in tot.values()) / reps
+        roof_all = []
+        agg_names = [n for n in tot if n.startswith("gt_aggregate") or n.startswith("gt_pna_reduce")]
+        if agg_names:
+            ms = sum(tot[n][0] for n in agg_names)
+            cnt = sum(tot[n][1] for n in agg_names)
+            ach = alg["agg_bytes_per_launch"] * cnt / (ms * 1e-3) / 1e9
+            roof_all.append({"kernel": "aggregate fwd+bwd (" + "/".join(sorted(agg_names)) + ")", "bound": "hbm",
+                             "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
+                             "traffic": None, "avg_launch_us": ms / cnt * 1e3, "share_of_step": ms / reps / step_ms,
+                             "algorithmic_bytes_per_launch": alg["agg_bytes_per_launch"], "peak_source": pk["source"]})
+        if "gt_mha_fwd" in tot:
+            ms = tot["gt_mha_fwd"][0] + tot["gt_mha_bwd"][0]
+            cnt = tot["gt_mha_fwd"][1]
+            ach = (alg["mha_fwd_flops"] + alg["mha_bwd_flops"]) * cnt / (ms * 1e-3) / 1e12
+            roof_all.append({"kernel": "masked MHA fwd+bwd (gt_mha_fwd/gt_mha_bwd)", "bound": "tensor", "achieved": ach,
+                             "peak": pk["tensor"], "unit": "TFLOP/s", "frac": ach / pk["tensor"], "traffic": None,
+                             "avg_launch_us": ms / (2 * cnt) * 1e3, "share_of_step": ms / reps / step_ms,
+                             "useful_flops_fwd": alg["mha_fwd_flops"], "peak_source": pk["source"]})
+        if "gt_gemm" in tot:
+            ms, cnt = tot["gt_gemm"]
+            ach = flops["gt_gemm"] / (ms * 1e-3) / 1e12
+            roof_all.append({"kernel": "dense contractions (gt_gemm)", "bound": "tensor", "achieved": ach,
+                             "peak": pk["tensor"], "unit": "TFLOP/s", "frac": ach / pk["tensor"], "traffic": None,
+                             "avg_launch_us": ms / cnt * 1e3, "share_of_step": ms / reps / step_ms,
+                             "peak_source": pk["source"]})
+        roof_all.sort(key=lambda r: -r["share_of_step"])
+        roof = dict(roof_all[0]) if roof_all else None
+        others = sorted(((n, v[0] / reps) for n, v in tot.items()), key=lambda x: -x[1])
+        if roof is not None:
+            roof["step_ms_sum_of_calls"] = step_ms
+            roof["top_calls_ms_per_step"] = {n: round(ms, 4) for n, ms in others[:8]}
+
+    cpu = None
+    if not ns.no_cpu_baseline and rank == 0:
+        gps, ms, desc = cpu_reference_run(ns, 3, 1)
+        cpu = {"value": gps, "unit": UNIT, "cores": desc["cores"], "kind": desc["kind"], "sample": desc["sample"],
+               "ms_per_step": ms}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(W, 3),
+            "ms_per_step": t_dev / K * 1e3, "higher_is_better": True, "scaling": ns.scaling, "vs_baseline": None,
+            "dtype": ns.precision, "data": "synthetic",
+            "config": {"workload": workload_name(ns, args), "l2": "256 MiB buffer written between timed steps",
+                       "distinct_batches": len(dev_batches), "dropout": {"gnn": args.gnn_dropout,
+                                                                         "transformer": args.transformer_dropout},
+                       "step": "zero_grad+forward+loss+backward" + ("+NCCL gradient allreduce (4 buckets)" if world > 1 else ""),
+                       "wall_ms_per_step_incl_flush": wall / K * 1e3},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "roofline_kernels": roof_all,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    ns = parse()
+    if ns.impl == "reference":
+        main_reference(ns)
+    else:
+        main_b200(ns)

@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
+from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_uint64, c_void_p
 
 import torch
 
@@ -21,12 +21,15 @@ EPI_RELU, EPI_ACCUM, EPI_OUT_F32, EPI_RESID_F32 = 1, 2, 4, 8
 
 P, I, L, F = c_void_p, c_int, c_int64, c_float
 I32 = c_int32
+U64 = c_uint64
 
 # name -> argtypes; every export returns int (0 ok). Kept in the order of include/graphtrans_b200.h
 SIGNATURES = {
     "gt_csr_build": [P, L, L, P, P, P, P, P, P, P, P],
     "gt_edge_type": [P, L, I32, P, P, P],
-    "gt_batch_plan": [P, L, L, L, P, P, P, P, P, P, P, P, P, P],
+    "gt_rng_advance": [P, P],
+    "gt_dropout": [I, P, L, P, F, P, U64, P],
+    "gt_batch_plan": [P, L, L, L, I32, P, P, P, P, P, P, P, P, P, P],
     "gt_embed_sum_fwd": [I, P, L, I32, I32, I32, P, P, P, P, P],
     "gt_embed_sum_bwd": [I, P, L, I32, I32, I32, P, P, P, P, P],
     "gt_aggregate_fwd": [I, I, P, P, L, I32, I32, P, P, P, P, I, P, I32, P, P, P, P, P, P],
@@ -35,9 +38,9 @@ SIGNATURES = {
     "gt_add_graph_vec": [I, P, P, P, L, I32, P, P],
     "gt_colstats": [I, P, L, I32, P, P],
     "gt_bn_finalize": [P, L, I32, I32, P, P, P, P, P, F, F, I, P, P],
-    "gt_bn_apply_fwd": [I, P, L, I32, I32, P, I, P, P, P, P, P],
-    "gt_bn_bwd_reduce": [I, P, P, L, I32, I32, P, I, P, P],
-    "gt_bn_bwd_apply": [I, P, P, L, I32, I32, P, P, I, I, P, P, P, P, P],
+    "gt_bn_apply_fwd": [I, P, L, I32, I32, P, I, P, P, P, P, F, P, U64, P],
+    "gt_bn_bwd_reduce": [I, P, P, L, I32, I32, P, I, P, F, P, U64, P],
+    "gt_bn_bwd_apply": [I, P, P, L, I32, I32, P, P, I, I, P, P, P, P, F, P, U64, P],
     "gt_gemm": [I, P, I, L, P, I, L, P, L, L, L, L, L, P, P, L, I, I, P],
     "gt_relu_bwd": [I, P, P, L, P, P],
     "gt_colsum": [I, P, L, L, L, P, P],
@@ -48,14 +51,20 @@ SIGNATURES = {
     "gt_scatter_rows": [I, P, P, L, I32, P, P, P],
     "gt_pad_batch_fwd": [I, P, P, L, L, I32, P, P, P],
     "gt_pad_batch_bwd": [I, P, P, P, L, L, L, I32, P, P],
-    "gt_mha_fwd": [I, P, P, P, P, L, L, I32, I32, F, P, P, I, P],
-    "gt_mha_bwd": [I, P, P, P, P, P, P, P, L, L, I32, I32, F, P, P, I, P],
-    "gt_pna_reduce_fwd": [I, P, P, L, I32, I32, P, P, P, P, P, P],
-    "gt_pna_reduce_bwd": [I, P, P, P, P, L, I32, I32, P, P, P, P, P, P, P],
+    "gt_mha_fwd": [I, P, P, P, P, L, L, I32, I32, F, P, P, F, P, U64, I, P],
+    "gt_mha_bwd": [I, P, P, P, P, P, P, P, L, L, I32, I32, F, P, P, F, P, U64, I, P],
+    "gt_pna_reduce_fwd": [I, P, P, P, L, I32, I32, I32, P, P, F, P, I32, P, P, P],
+    "gt_pna_reduce_bwd": [I, P, P, P, L, I32, I32, I32, I32, P, P, F, P, P, P, P, P, P],
 }
 
+# kernels launched per export (everything not listed launches exactly one); cudaMemsetAsync nodes
+# are not counted
+KERNELS_PER_CALL = {"gt_csr_build": 4, "gt_batch_plan": 3, "gt_mha_bwd": 2}
+
 _lib = None
-launch_count = 0  # kernels-launching C-ABI calls issued (bench.py reports it)
+launch_count = 0   # C-ABI calls issued
+kernel_count = 0   # kernels those calls launched (bench.py reports it as gpu_launches)
+_profile = None    # when a list: (name, start_event, end_event, info) per call (bench.py roofline pass)
 
 
 def load():
@@ -96,12 +105,33 @@ def stream():
 
 def call(name, *args):
     """Invoke an export on torch's current CUDA stream; non-zero return -> RuntimeError."""
-    global launch_count
+    global launch_count, kernel_count
     lib = load()
-    rc = getattr(lib, name)(*args, stream())
+    if _profile is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*args, stream())
+        e1.record()
+        _profile.append((name, e0, e1, args))
+    else:
+        rc = getattr(lib, name)(*args, stream())
     launch_count += 1
+    kernel_count += KERNELS_PER_CALL.get(name, 1)
     if rc != 0:
         raise RuntimeError(f"{name} failed (rc={rc}): {lib.gt_last_error().decode()}")
+
+
+def start_profile():
+    global _profile
+    _profile = []
+
+
+def stop_profile():
+    """-> list of (export name, milliseconds, call args); synchronises the device"""
+    global _profile
+    rec, _profile = _profile, None
+    torch.cuda.synchronize()
+    return [(n, e0.elapsed_time(e1), a) for n, e0, e1, a in rec]
 
 
 def require_cuda(*tensors):

@@ -11,10 +11,16 @@ namespace gt {
 
 int mha_tc_fwd_launch(int dt, const void* qkv, const int32_t* tok_graph, const int32_t* tok_off, const int32_t* key_start,
                       int64_t n_rows, int64_t B, int32_t nhead, int32_t dh, float scale, void* out, float* lse,
-                      cudaStream_t st);  // attn_tc.cu; -2 = not eligible
+                      float drop_p, const uint64_t* rng, uint64_t salt, cudaStream_t st);  // attn_tc.cu; -2 = not eligible
 int mha_tc_bwd_launch(int dt, const void* qkv, const void* out, const void* dout, const float* lse,
                       const int32_t* tok_graph, const int32_t* tok_off, const int32_t* key_start, int64_t n_rows,
-                      int64_t B, int32_t nhead, int32_t dh, float scale, void* dqkv, float* delta, cudaStream_t st);
+                      int64_t B, int32_t nhead, int32_t dh, float scale, void* dqkv, float* delta, float drop_p,
+                      const uint64_t* rng, uint64_t salt, cudaStream_t st);
+
+// dropout element index of probability P[h, query row, key row] (shared by every MHA kernel)
+__device__ __forceinline__ uint64_t att_drop_idx(int h, int64_t q, int64_t k, int64_t n_rows) {
+    return ((uint64_t)h * (uint64_t)n_rows + (uint64_t)q) * (uint64_t)n_rows + (uint64_t)k;
+}
 
 constexpr int ATT_WARPS = 4;
 constexpr int ATT_MAXDH = 64;
@@ -36,8 +42,10 @@ __device__ __forceinline__ float dot_row(const float* __restrict__ a_sm, const T
 template <typename T>
 __global__ void __launch_bounds__(ATT_WARPS * 32)
 k_mha_fwd(const T* __restrict__ qkv, const int32_t* __restrict__ tok_graph, const int32_t* __restrict__ tok_off,
-          const int32_t* __restrict__ key_start, int64_t n_rows, int nhead, int dh, float scale, T* __restrict__ out, float* __restrict__ lse) {
+          const int32_t* __restrict__ key_start, int64_t n_rows, int nhead, int dh, float scale, T* __restrict__ out, float* __restrict__ lse,
+          float drop_p, const uint64_t* __restrict__ rng, uint64_t salt) {
     __shared__ float sq[ATT_WARPS][ATT_MAXDH];
+    const Drop dr = make_drop(rng, salt, drop_p);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int64_t item = blockIdx.x * (int64_t)ATT_WARPS + wid;
     if (item >= n_rows * nhead) return;
@@ -65,9 +73,10 @@ k_mha_fwd(const T* __restrict__ qkv, const int32_t* __restrict__ tok_graph, cons
         l = l * corr + warp_sum(p);
         o0 *= corr;
         o1 *= corr;
+        const float pd = (valid && dr.on) ? p * drop1(dr, att_drop_idx(h, t, j, n_rows)) : p;
         const int cnt = min(32, ke - kb);
         for (int jj = 0; jj < cnt; ++jj) {
-            const float pj = __shfl_sync(0xffffffffu, p, jj);
+            const float pj = __shfl_sync(0xffffffffu, pd, jj);
             const T* vrow = qkv + (int64_t)(kb + jj) * ld3 + 2 * d + h * dh;
             if (lane < dh) o0 = fmaf(pj, to_f(vrow[lane]), o0);
             if (lane + 32 < dh) o1 = fmaf(pj, to_f(vrow[lane + 32]), o1);
@@ -86,9 +95,11 @@ __global__ void __launch_bounds__(ATT_WARPS * 32)
 k_mha_bwd_dq(const T* __restrict__ qkv, const T* __restrict__ out, const T* __restrict__ dout,
              const float* __restrict__ lse, const int32_t* __restrict__ tok_graph,
              const int32_t* __restrict__ tok_off, const int32_t* __restrict__ key_start, int64_t n_rows, int nhead,
-             int dh, float scale, T* __restrict__ dqkv, float* __restrict__ delta) {
+             int dh, float scale, T* __restrict__ dqkv, float* __restrict__ delta, float drop_p,
+             const uint64_t* __restrict__ rng, uint64_t salt) {
     __shared__ float sq[ATT_WARPS][ATT_MAXDH];
     __shared__ float sdo[ATT_WARPS][ATT_MAXDH];
+    const Drop dr = make_drop(rng, salt, drop_p);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int64_t item = blockIdx.x * (int64_t)ATT_WARPS + wid;
     if (item >= n_rows * nhead) return;
@@ -125,7 +136,8 @@ k_mha_bwd_dq(const T* __restrict__ qkv, const T* __restrict__ out, const T* __re
         if (j < ke) {
             const float s = dot_row(sq[wid], qkv + (int64_t)j * ld3 + d + h * dh, dh);
             const float p = __expf(s - L);
-            const float dp = dot_row(sdo[wid], qkv + (int64_t)j * ld3 + 2 * d + h * dh, dh);
+            float dp = dot_row(sdo[wid], qkv + (int64_t)j * ld3 + 2 * d + h * dh, dh);
+            if (dr.on) dp *= drop1(dr, att_drop_idx(h, t, j, n_rows));
             ds = p * (dp - dl);
         }
         const int cnt = min(32, ke - kb);
@@ -146,7 +158,9 @@ __global__ void __launch_bounds__(ATT_WARPS * 32)
 k_mha_bwd_dkv(const T* __restrict__ qkv, const T* __restrict__ dout, const float* __restrict__ lse,
               const float* __restrict__ delta, const int32_t* __restrict__ tok_graph,
               const int32_t* __restrict__ tok_off, const int32_t* __restrict__ key_start, int64_t n_rows, int nhead,
-              int dh, float scale, T* __restrict__ dqkv) {
+              int dh, float scale, T* __restrict__ dqkv, float drop_p, const uint64_t* __restrict__ rng,
+              uint64_t salt) {
+    const Drop dr = make_drop(rng, salt, drop_p);
     __shared__ float sk[ATT_WARPS][ATT_MAXDH];
     __shared__ float sv[ATT_WARPS][ATT_MAXDH];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -177,8 +191,10 @@ k_mha_bwd_dkv(const T* __restrict__ qkv, const T* __restrict__ dout, const float
         if (i < qe) {
             const float s = dot_row(sk[wid], qkv + (int64_t)i * ld3 + h * dh, dh);
             p = __expf(s - lse[(int64_t)h * n_rows + i]);
-            const float dp = dot_row(sv[wid], dout + (int64_t)i * d + h * dh, dh);
+            const float m = dr.on ? drop1(dr, att_drop_idx(h, i, j, n_rows)) : 1.f;
+            const float dp = dot_row(sv[wid], dout + (int64_t)i * d + h * dh, dh) * m;
             ds = p * (dp - delta[(int64_t)h * n_rows + i]);
+            p *= m;  // dV uses the dropped probabilities
         }
         const int cnt = min(32, qe - qb);
         for (int ii = 0; ii < cnt; ++ii) {
@@ -220,35 +236,36 @@ using namespace gt;
 
 extern "C" int gt_mha_fwd(int dt, const void* qkv, const int32_t* tok_graph, const int32_t* tok_off,
                           const int32_t* key_start, int64_t n_rows, int64_t B, int32_t nhead, int32_t dh, float scale,
-                          void* out, float* lse, int impl, void* stream) {
+                          void* out, float* lse, float drop_p, const uint64_t* rng_state, uint64_t salt, int impl,
+                          void* stream) {
     if (int r = check_mha("gt_mha_fwd", n_rows, B, nhead, dh)) return r;
     cudaStream_t st = (cudaStream_t)stream;
     if (impl != 1) {
-        const int r = mha_tc_fwd_launch(dt, qkv, tok_graph, tok_off, key_start, n_rows, B, nhead, dh, scale, out, lse, st);
+        const int r = mha_tc_fwd_launch(dt, qkv, tok_graph, tok_off, key_start, n_rows, B, nhead, dh, scale, out, lse, drop_p, rng_state, salt, st);
         if (r != -2) return r;
         GT_CHECK_ARG(impl != 2, "gt_mha_fwd: not eligible for the tcgen05 kernel (%s)", gt_last_error());
     }
     const int grid = (int)((n_rows * nhead + ATT_WARPS - 1) / ATT_WARPS);
-    GT_DISPATCH_DT(dt, (k_mha_fwd<T><<<grid, ATT_WARPS * 32, 0, st>>>((const T*)qkv, tok_graph, tok_off, key_start, n_rows, nhead, dh, scale, (T*)out, lse)));
+    GT_DISPATCH_DT(dt, (k_mha_fwd<T><<<grid, ATT_WARPS * 32, 0, st>>>((const T*)qkv, tok_graph, tok_off, key_start, n_rows, nhead, dh, scale, (T*)out, lse, drop_p, rng_state, salt)));
     GT_LAUNCH_CHECK("gt_mha_fwd(simt)");
     return 0;
 }
 
 extern "C" int gt_mha_bwd(int dt, const void* qkv, const void* out, const void* dout, const float* lse,
                           const int32_t* tok_graph, const int32_t* tok_off, const int32_t* key_start, int64_t n_rows,
-                          int64_t B, int32_t nhead, int32_t dh, float scale, void* dqkv, float* delta, int impl,
-                          void* stream) {
+                          int64_t B, int32_t nhead, int32_t dh, float scale, void* dqkv, float* delta, float drop_p,
+                          const uint64_t* rng_state, uint64_t salt, int impl, void* stream) {
     if (int r = check_mha("gt_mha_bwd", n_rows, B, nhead, dh)) return r;
     cudaStream_t st = (cudaStream_t)stream;
     if (impl != 1) {
-        const int r = mha_tc_bwd_launch(dt, qkv, out, dout, lse, tok_graph, tok_off, key_start, n_rows, B, nhead, dh, scale, dqkv, delta, st);
+        const int r = mha_tc_bwd_launch(dt, qkv, out, dout, lse, tok_graph, tok_off, key_start, n_rows, B, nhead, dh, scale, dqkv, delta, drop_p, rng_state, salt, st);
         if (r != -2) return r;
         GT_CHECK_ARG(impl != 2, "gt_mha_bwd: not eligible for the tcgen05 kernel (%s)", gt_last_error());
     }
     const int grid = (int)((n_rows * nhead + ATT_WARPS - 1) / ATT_WARPS);
     GT_DISPATCH_DT(dt, {
-        k_mha_bwd_dq<T><<<grid, ATT_WARPS * 32, 0, st>>>((const T*)qkv, (const T*)out, (const T*)dout, lse, tok_graph, tok_off, key_start, n_rows, nhead, dh, scale, (T*)dqkv, delta);
-        k_mha_bwd_dkv<T><<<grid, ATT_WARPS * 32, 0, st>>>((const T*)qkv, (const T*)dout, lse, delta, tok_graph, tok_off, key_start, n_rows, nhead, dh, scale, (T*)dqkv);
+        k_mha_bwd_dq<T><<<grid, ATT_WARPS * 32, 0, st>>>((const T*)qkv, (const T*)out, (const T*)dout, lse, tok_graph, tok_off, key_start, n_rows, nhead, dh, scale, (T*)dqkv, delta, drop_p, rng_state, salt);
+        k_mha_bwd_dkv<T><<<grid, ATT_WARPS * 32, 0, st>>>((const T*)qkv, (const T*)dout, lse, delta, tok_graph, tok_off, key_start, n_rows, nhead, dh, scale, (T*)dqkv, drop_p, rng_state, salt);
     });
     GT_LAUNCH_CHECK("gt_mha_bwd(simt)");
     return 0;

@@ -65,6 +65,14 @@ __device__ __forceinline__ void st4(bf16* p, const float (&v)[4]) {
     *reinterpret_cast<uint2*>(p) = t;
 }
 
+// V-wide (4 or 1) variants for rows whose logical sub-blocks are not multiples of 4
+template <int V, typename T> __device__ __forceinline__ void ldv(const T* p, float (&v)[V]) {
+    if constexpr (V == 4) ld4(p, v); else v[0] = to_f(p[0]);
+}
+template <int V, typename T> __device__ __forceinline__ void stv(T* p, const float (&v)[V]) {
+    if constexpr (V == 4) st4(p, v); else p[0] = from_f<T>(v[0]);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -74,6 +82,49 @@ __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
+}
+
+
+// ---- counter-based dropout RNG (replaces torch's Philox stream; reference nn.Dropout / F.dropout
+// sites gnn_module.py:86-90,205-209,227-229 and the 4 dropout sites of nn.TransformerEncoderLayer).
+// rng_state is a DEVICE array {seed, step}: reading it on the device keeps every kernel
+// CUDA-graph replayable (gt_rng_advance bumps `step` inside the graph); `salt` identifies the
+// call site inside a step, `idx` the element (vector) inside the call.  splitmix64 finaliser.
+struct Drop {
+    uint64_t key;
+    uint32_t thresh16;  // keep iff 16-bit field >= thresh16
+    float inv_keep;
+    bool on;
+};
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ Drop make_drop(const uint64_t* __restrict__ rng_state, uint64_t salt, float p) {
+    Drop d;
+    d.on = p > 0.f && rng_state != nullptr;
+    d.key = 0;
+    d.thresh16 = 0;
+    d.inv_keep = 1.f;
+    if (d.on) {
+        d.key = mix64(rng_state[0] ^ mix64(rng_state[1] * 0x9E3779B97F4A7C15ull + salt));
+        d.thresh16 = (uint32_t)(p * 65536.f);
+        d.inv_keep = 1.f / (1.f - p);
+    }
+    return d;
+}
+// scale factors (0 or 1/(1-p)) of the 4 elements of vector `vec_idx`
+__device__ __forceinline__ void drop4(const Drop& d, uint64_t vec_idx, float (&s)[4]) {
+    if (!d.on) { s[0] = s[1] = s[2] = s[3] = 1.f; return; }
+    const uint64_t r = mix64(d.key + vec_idx * 0x9E3779B97F4A7C15ull);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) s[q] = ((uint32_t)(r >> (16 * q)) & 0xffffu) >= d.thresh16 ? d.inv_keep : 0.f;
+}
+__device__ __forceinline__ float drop1(const Drop& d, uint64_t idx) {
+    if (!d.on) return 1.f;
+    const uint64_t r = mix64(d.key + idx * 0x9E3779B97F4A7C15ull);
+    return ((uint32_t)(r >> 24) & 0xffffu) >= d.thresh16 ? d.inv_keep : 0.f;
 }
 
 inline int blocks_for(int64_t work_items, int per_block, int max_blocks = kNumSMs * 16) {

@@ -124,7 +124,7 @@ __global__ void k_plan_bounds(const int64_t* __restrict__ batch, int64_t N, int6
 }
 
 // single block: fix empty graphs, kept = min(n, L), tok_off = exclusive scan of kept+1, scalars
-__global__ void k_plan_scan(int64_t N, int64_t B, int64_t L, int32_t* node_off, int32_t* kept,
+__global__ void k_plan_scan(int64_t N, int64_t B, int64_t L, int cls, int32_t* node_off, int32_t* kept,
                             int32_t* tok_off, int32_t* scalars) {
     __shared__ int32_t warp_tot[32];
     __shared__ int32_t carry_s, max_s;
@@ -145,7 +145,7 @@ __global__ void k_plan_scan(int64_t N, int64_t B, int64_t L, int32_t* node_off, 
             n = node_off[g + 1] - node_off[g];
             k = n < L ? n : (int32_t)L;
             kept[g] = k;
-            v = k + 1;
+            v = k + cls;
             local_max = max(local_max, n);
         }
         int32_t incl = v;
@@ -183,7 +183,7 @@ __global__ void k_plan_scan(int64_t N, int64_t B, int64_t L, int32_t* node_off, 
     }
 }
 
-__global__ void k_plan_maps(int64_t N, int64_t B, const int32_t* __restrict__ node_off,
+__global__ void k_plan_maps(int64_t N, int64_t B, int cls, const int32_t* __restrict__ node_off,
                             const int32_t* __restrict__ kept, const int32_t* __restrict__ tok_off,
                             const int32_t* __restrict__ node_graph, int32_t* tok2node, int32_t* tok_graph,
                             int32_t* node2tok, int32_t* cls_rows) {
@@ -202,12 +202,13 @@ __global__ void k_plan_maps(int64_t N, int64_t B, const int32_t* __restrict__ no
             }
             const int32_t g = (int32_t)lo, local = (int32_t)t - tok_off[g], k = kept[g];
             tok_graph[t] = g;
-            if (local == k) {
+            if (local == k) {  // only reachable when cls != 0
                 tok2node[t] = -1;
                 cls_rows[g] = (int32_t)t;
             } else {
                 const int32_t n = node_off[g + 1] - node_off[g];
                 tok2node[t] = node_off[g] + (n - k) + local;
+                if (!cls && local == k - 1) cls_rows[g] = (int32_t)t;  // pooling == "last": the last node row
             }
         }
         if (t < N) {
@@ -259,7 +260,7 @@ extern "C" int gt_edge_type(const int64_t* edge_attr, int64_t E, int32_t ncol, c
     return 0;
 }
 
-extern "C" int gt_batch_plan(const int64_t* batch, int64_t N, int64_t B, int64_t L, int32_t* node_off,
+extern "C" int gt_batch_plan(const int64_t* batch, int64_t N, int64_t B, int64_t L, int32_t cls, int32_t* node_off,
                              int32_t* kept, int32_t* tok_off, int32_t* tok2node, int32_t* tok_graph,
                              int32_t* node_graph, int32_t* node2tok, int32_t* cls_rows, int32_t* scalars,
                              void* stream) {
@@ -268,8 +269,8 @@ extern "C" int gt_batch_plan(const int64_t* batch, int64_t N, int64_t B, int64_t
     cudaError_t e = cudaMemsetAsync(node_off, 0xff, sizeof(int32_t) * (B + 1), st);
     if (e != cudaSuccess) return cuda_fail(e, "gt_batch_plan memset");
     k_plan_bounds<<<blocks_for(N, 256), 256, 0, st>>>(batch, N, B, node_off, node_graph);
-    k_plan_scan<<<1, 1024, 0, st>>>(N, B, L, node_off, kept, tok_off, scalars);
-    k_plan_maps<<<blocks_for(N + B, 256), 256, 0, st>>>(N, B, node_off, kept, tok_off, node_graph, tok2node,
+    k_plan_scan<<<1, 1024, 0, st>>>(N, B, L, cls ? 1 : 0, node_off, kept, tok_off, scalars);
+    k_plan_maps<<<blocks_for(N + B, 256), 256, 0, st>>>(N, B, cls ? 1 : 0, node_off, kept, tok_off, node_graph, tok2node,
                                                         tok_graph, node2tok, cls_rows);
     GT_LAUNCH_CHECK("gt_batch_plan");
     return 0;

@@ -118,9 +118,11 @@ __global__ void k_bn_finalize(const double* __restrict__ stats, int64_t M, int d
 template <typename T>
 __global__ void k_bn_apply(const T* __restrict__ x, int64_t M, int ld, const float* __restrict__ ssmr, int relu,
                            const T* __restrict__ resid, const float* __restrict__ gvec,
-                           const int32_t* __restrict__ node_graph, T* __restrict__ y) {
+                           const int32_t* __restrict__ node_graph, T* __restrict__ y, float drop_p,
+                           const uint64_t* __restrict__ rng, uint64_t salt) {
     const int vpr = ld / 4;
     const int64_t total = M * vpr;
+    const Drop dr = make_drop(rng, salt, drop_p);
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = i / vpr;
         const int c0 = (int)(i - r * vpr) * 4;
@@ -132,6 +134,12 @@ __global__ void k_bn_apply(const T* __restrict__ x, int64_t M, int ld, const flo
         for (int q = 0; q < 4; ++q) {
             v[q] = fmaf(v[q], sc[q], sh[q]);
             if (relu) v[q] = fmaxf(v[q], 0.f);
+        }
+        if (dr.on) {
+            float ds[4];
+            drop4(dr, (uint64_t)i, ds);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) v[q] *= ds[q];
         }
         if (resid) {
             float t[4];
@@ -151,7 +159,10 @@ __global__ void k_bn_apply(const T* __restrict__ x, int64_t M, int ld, const flo
 
 template <typename T>
 __global__ void k_bn_bwd_reduce(const T* __restrict__ x, const T* __restrict__ dy, int64_t M, int ld,
-                                const float* __restrict__ ssmr, int relu, double* __restrict__ red) {
+                                const float* __restrict__ ssmr, int relu, double* __restrict__ red, float drop_p,
+                                const uint64_t* __restrict__ rng, uint64_t salt) {
+    const Drop dr = make_drop(rng, salt, drop_p);
+    const int vpr = ld / 4;
     const int64_t r0 = (int64_t)blockIdx.y * STAT_ROWS;
     const int64_t r1 = min(r0 + STAT_ROWS, M);
     const int c0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
@@ -166,8 +177,11 @@ __global__ void k_bn_bwd_reduce(const T* __restrict__ x, const T* __restrict__ d
         float v[4], g[4];
         ld4(x + r * ld + c0, v);
         ld4(dy + r * ld + c0, g);
+        float ds[4];
+        drop4(dr, (uint64_t)(r * vpr + c0 / 4), ds);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
+            g[q] *= ds[q];
             if (relu && fmaf(v[q], sc[q], sh[q]) <= 0.f) g[q] = 0.f;
             s[q] += g[q];
             s2[q] = fmaf(g[q], (v[q] - mu[q]) * rs[q], s2[q]);
@@ -184,7 +198,9 @@ template <typename T>
 __global__ void k_bn_bwd_apply(const T* __restrict__ x, const T* __restrict__ dy, int64_t M, int d, int ld,
                                const float* __restrict__ ssmr, const float* __restrict__ gamma, int relu,
                                int training, const double* __restrict__ red, T* __restrict__ dx,
-                               float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                               float* __restrict__ dgamma, float* __restrict__ dbeta, float drop_p,
+                               const uint64_t* __restrict__ rng, uint64_t salt) {
+    const Drop dr = make_drop(rng, salt, drop_p);
     const int vpr = ld / 4;
     const int64_t total = M * vpr;
     const float invM = 1.f / (float)M;
@@ -198,8 +214,11 @@ __global__ void k_bn_bwd_apply(const T* __restrict__ x, const T* __restrict__ dy
         ld4(ssmr + ld + c0, sh);
         ld4(ssmr + 2 * ld + c0, mu);
         ld4(ssmr + 3 * ld + c0, rs);
+        float ds[4];
+        drop4(dr, (uint64_t)i, ds);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
+            g[q] *= ds[q];
             if (relu && fmaf(v[q], sc[q], sh[q]) <= 0.f) g[q] = 0.f;
             if (training) {
                 const float xh = (v[q] - mu[q]) * rs[q];
@@ -503,6 +522,23 @@ __global__ void k_relu_bwd(const T* __restrict__ dy, const T* __restrict__ y, in
     }
 }
 
+// y = x * keep_mask / (1 - p): standalone dropout (its own adjoint with the same salt)
+template <typename T>
+__global__ void k_dropout(const T* __restrict__ x, int64_t n4, T* __restrict__ y, float p,
+                          const uint64_t* __restrict__ rng, uint64_t salt) {
+    const Drop dr = make_drop(rng, salt, p);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        float v[4], ds[4];
+        ld4(x + i * 4, v);
+        drop4(dr, (uint64_t)i, ds);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] *= ds[q];
+        st4(y + i * 4, v);
+    }
+}
+
+__global__ void k_rng_advance(uint64_t* rng) { rng[1] += 1; }
+
 template <typename TI, typename TO>
 __global__ void k_cast_pad(const TI* __restrict__ src, int64_t rows_in, int64_t cols_in, int64_t ld_in,
                            TO* __restrict__ dst, int64_t rows_out, int64_t cols_out, int64_t ld_out) {
@@ -578,28 +614,30 @@ extern "C" int gt_bn_finalize(const double* stats, int64_t M, int32_t d, int32_t
 
 extern "C" int gt_bn_apply_fwd(int dt, const void* x, int64_t M, int32_t d, int32_t ld, const float* ssmr, int relu,
                                const void* resid, const float* gvec, const int32_t* node_graph, void* y,
-                               void* stream) {
+                               float drop_p, const uint64_t* rng_state, uint64_t salt, void* stream) {
     GT_CHECK_ARG(M > 0 && ld >= d && ld % 4 == 0, "gt_bn_apply_fwd: bad shape");
     GT_CHECK_ARG(!gvec || node_graph, "gt_bn_apply_fwd: gvec needs node_graph");
-    GT_DISPATCH_DT(dt, (k_bn_apply<T><<<blocks_for(M * (ld / 4), 256), 256, 0, ST>>>((const T*)x, M, ld, ssmr, relu, (const T*)resid, gvec, node_graph, (T*)y)));
+    GT_DISPATCH_DT(dt, (k_bn_apply<T><<<blocks_for(M * (ld / 4), 256), 256, 0, ST>>>((const T*)x, M, ld, ssmr, relu, (const T*)resid, gvec, node_graph, (T*)y, drop_p, rng_state, salt)));
     GT_LAUNCH_CHECK("gt_bn_apply_fwd");
     return 0;
 }
 
 extern "C" int gt_bn_bwd_reduce(int dt, const void* x, const void* dy, int64_t M, int32_t d, int32_t ld,
-                                const float* ssmr, int relu, double* red, void* stream) {
+                                const float* ssmr, int relu, double* red, float drop_p,
+                                const uint64_t* rng_state, uint64_t salt, void* stream) {
     GT_CHECK_ARG(M > 0 && ld >= d && ld % 4 == 0, "gt_bn_bwd_reduce: bad shape");
     dim3 grid((ld / 4 + 63) / 64, (unsigned)((M + STAT_ROWS - 1) / STAT_ROWS));
-    GT_DISPATCH_DT(dt, (k_bn_bwd_reduce<T><<<grid, 64, 0, ST>>>((const T*)x, (const T*)dy, M, ld, ssmr, relu, red)));
+    GT_DISPATCH_DT(dt, (k_bn_bwd_reduce<T><<<grid, 64, 0, ST>>>((const T*)x, (const T*)dy, M, ld, ssmr, relu, red, drop_p, rng_state, salt)));
     GT_LAUNCH_CHECK("gt_bn_bwd_reduce");
     return 0;
 }
 
 extern "C" int gt_bn_bwd_apply(int dt, const void* x, const void* dy, int64_t M, int32_t d, int32_t ld,
                                const float* ssmr, const float* gamma, int relu, int training, const double* red,
-                               void* dx, float* dgamma, float* dbeta, void* stream) {
+                               void* dx, float* dgamma, float* dbeta, float drop_p, const uint64_t* rng_state,
+                               uint64_t salt, void* stream) {
     GT_CHECK_ARG(M > 0 && ld >= d && ld % 4 == 0, "gt_bn_bwd_apply: bad shape");
-    GT_DISPATCH_DT(dt, (k_bn_bwd_apply<T><<<blocks_for(M * (ld / 4), 256), 256, 0, ST>>>((const T*)x, (const T*)dy, M, d, ld, ssmr, gamma, relu, training, red, (T*)dx, dgamma, dbeta)));
+    GT_DISPATCH_DT(dt, (k_bn_bwd_apply<T><<<blocks_for(M * (ld / 4), 256), 256, 0, ST>>>((const T*)x, (const T*)dy, M, d, ld, ssmr, gamma, relu, training, red, (T*)dx, dgamma, dbeta, drop_p, rng_state, salt)));
     GT_LAUNCH_CHECK("gt_bn_bwd_apply");
     return 0;
 }
@@ -720,6 +758,22 @@ extern "C" int gt_relu_bwd(int dt, const void* dy, const void* y, int64_t n, voi
     GT_CHECK_ARG(n > 0 && n % 4 == 0, "gt_relu_bwd: element count must be a positive multiple of 4");
     GT_DISPATCH_DT(dt, (k_relu_bwd<T><<<blocks_for(n / 4, 256), 256, 0, ST>>>((const T*)dy, (const T*)y, n / 4, (T*)dz)));
     GT_LAUNCH_CHECK("gt_relu_bwd");
+    return 0;
+}
+
+extern "C" int gt_dropout(int dt, const void* x, int64_t n, void* y, float drop_p, const uint64_t* rng_state,
+                          uint64_t salt, void* stream) {
+    GT_CHECK_ARG(n > 0 && n % 4 == 0, "gt_dropout: element count must be a positive multiple of 4");
+    GT_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "gt_dropout: p=%f not in [0,1)", drop_p);
+    GT_DISPATCH_DT(dt, (k_dropout<T><<<blocks_for(n / 4, 256), 256, 0, ST>>>((const T*)x, n / 4, (T*)y, drop_p, rng_state, salt)));
+    GT_LAUNCH_CHECK("gt_dropout");
+    return 0;
+}
+
+extern "C" int gt_rng_advance(uint64_t* rng_state, void* stream) {
+    GT_CHECK_ARG(rng_state != nullptr, "gt_rng_advance: null state");
+    k_rng_advance<<<1, 1, 0, ST>>>(rng_state);
+    GT_LAUNCH_CHECK("gt_rng_advance");
     return 0;
 }
 

@@ -1,0 +1,113 @@
+"""Data-parallel batch sharding: one process per GPU, gradients allreduced over NCCL (NVLink 5 /
+NVSwitch) in a few contiguous fp32 buckets, launched on a side stream as soon as the last gradient
+of a bucket has been produced by the backward pass (reverse layer order), with the 1/G scale
+folded into the reduction (ReduceOp.AVG).  The reference is single-GPU (the only trace is the
+commented-out nn.DataParallel at reference main.py:174); per-rank math = the reference on that
+rank's shard, BatchNorm statistics stay local (plain DistributedDataParallel behaviour),
+SURVEY §8e.  There is no data-path collective: graphs are independent units.
+
+Works with any torch.distributed backend ('nccl' on GPUs; 'gloo' in the CPU tests of the bucket
+logic, where AVG is emulated by SUM + scale).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+class GradBuckets:
+    def __init__(self, model: torch.nn.Module, n_buckets: int = 4, overlap: bool = True, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        dev = self.params[0].device
+        total = sum(p.numel() for p in self.params)
+        # one flat fp32 gradient arena; every p.grad is a view into it (no copies around the allreduce)
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        # bucket boundaries: parameters() order is forward order, so the LAST bucket completes first
+        target = (total + n_buckets - 1) // n_buckets
+        self.buckets = []          # (lo, hi, [param indices])
+        lo, cur, idxs = 0, 0, []
+        off = 0
+        self._bucket_of = {}
+        for i, p in enumerate(self.params):
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+            cur += p.numel()
+            idxs.append(i)
+            if cur >= target and len(self.buckets) < n_buckets - 1:
+                self.buckets.append((lo, off, idxs))
+                lo, cur, idxs = off, 0, []
+        if idxs:
+            self.buckets.append((lo, off, idxs))
+        for b, (_, _, ids) in enumerate(self.buckets):
+            for i in ids:
+                self._bucket_of[i] = b
+        self.overlap = overlap and self.world > 1 and dev.type == "cuda"
+        self.comm_stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
+        self._pending = [0] * len(self.buckets)
+        self._work = []
+        self._launched = [False] * len(self.buckets)
+        if self.overlap:
+            for i, p in enumerate(self.params):
+                p.register_post_accumulate_grad_hook(self._make_hook(i))
+        self.reset()
+
+    # ------------------------------------------------------------------
+    def reset(self):
+        self._pending = [len(ids) for _, _, ids in self.buckets]
+        self._launched = [False] * len(self.buckets)
+        self._work = []
+
+    def zero_grad(self):
+        """one memset for every gradient (and re-arm the hooks)"""
+        self.flat.zero_()
+        self.reset()
+
+    def _make_hook(self, i):
+        def hook(_p):
+            b = self._bucket_of[i]
+            self._pending[b] -= 1
+            if self._pending[b] == 0:
+                self._launch(b)
+        return hook
+
+    def _launch(self, b):
+        if self._launched[b] or self.world == 1:
+            return
+        self._launched[b] = True
+        lo, hi, _ = self.buckets[b]
+        chunk = self.flat[lo:hi]
+        if self.comm_stream is not None:
+            self.comm_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.comm_stream):
+                self._allreduce(chunk)
+        else:
+            self._allreduce(chunk)
+
+    def _allreduce(self, chunk):
+        if dist.get_backend(self.group) == "nccl":
+            self._work.append(dist.all_reduce(chunk, op=dist.ReduceOp.AVG, group=self.group, async_op=True))
+        else:
+            dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group)
+            chunk.div_(self.world)
+
+    def finish(self):
+        """call after backward(): launches whatever the hooks did not (parameters without a gradient
+        this step, or overlap disabled) and makes the compute stream wait for the reductions."""
+        if self.world == 1:
+            return
+        for b in reversed(range(len(self.buckets))):
+            self._launch(b)
+        for w in self._work:
+            w.wait()
+        if self.comm_stream is not None:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        self._work = []
+
+
+def shard_range(n_graphs: int, rank: int, world: int):
+    """contiguous graph range of `rank` (B/G graphs per rank, remainder to the first ranks)"""
+    base, rem = divmod(n_graphs, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)

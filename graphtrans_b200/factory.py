@@ -1,0 +1,60 @@
+"""Model / loss construction exactly as the reference's driver does it (reference main.py:126-171
+with dataset/code.py:117-133, dataset/mol.py:83-85, dataset/tud.py:65-73), for the synthetic
+dataset kinds of graphtrans_b200.synth.  The losses are the caller-side functions of the
+reference's dataset adapters (dataset/code.py:39-45, dataset/mol.py:24-31, dataset/tud.py:25-27)
+operating on the fp32 logits the model returns."""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import synth
+from .encoders import ASTNodeEncoder, AtomEncoder, BondEncoder
+from .models import MODELS
+
+
+def build_model(args):
+    ds = args.dataset
+    if ds == "code2":
+        node_encoder = ASTNodeEncoder(args.gnn_emb_dim, num_nodetypes=getattr(args, "num_nodetypes", synth.CODE2_NUM_NODETYPES),
+                                      num_nodeattributes=getattr(args, "num_nodeattrs", synth.CODE2_NUM_NODEATTRS),
+                                      max_depth=synth.CODE2_MAX_DEPTH)
+        edge_encoder_cls = lambda emb_dim: nn.Linear(2, emb_dim)  # noqa: E731
+    elif ds in ("mol", "syn"):
+        node_encoder = AtomEncoder(args.gnn_emb_dim)
+        edge_encoder_cls = lambda emb_dim: BondEncoder(emb_dim=emb_dim)  # noqa: E731
+    elif ds == "nci1":
+        node_encoder = nn.Linear(37, args.gnn_emb_dim)
+
+        def edge_encoder_cls(_):
+            def zero(_):
+                return 0
+            return zero
+    else:
+        raise ValueError(ds)
+    return MODELS[args.model_type](num_tasks=args.num_tasks, args=args, node_encoder=node_encoder,
+                                   edge_encoder_cls=edge_encoder_cls)
+
+
+def loss_fn(args):
+    ds = args.dataset
+    if ds == "code2":
+        def calc_loss(pred_list, batch, m=1.0):
+            loss = 0
+            for i in range(len(pred_list)):
+                loss += F.cross_entropy(pred_list[i].to(torch.float32), batch.y_arr[:, i])
+            return loss / len(pred_list) / m
+        return calc_loss
+    if ds in ("mol", "syn"):
+        def calc_loss(pred, batch, m=1.0):
+            # mean over labelled (non-NaN) entries as dataset/mol.py:24-31, written without the boolean
+            # gather (pred[is_labeled] forces a device->host sync): masked sum / count
+            is_labeled = batch.y == batch.y
+            y = torch.where(is_labeled, batch.y, torch.zeros_like(batch.y)).to(torch.float32)
+            per = F.binary_cross_entropy_with_logits(pred.to(torch.float32), y, reduction="none")
+            return (per * is_labeled).sum() / is_labeled.sum() / m
+        return calc_loss
+    if ds == "nci1":
+        def calc_loss(pred, batch, m=1.0):
+            return F.cross_entropy(pred, batch.y) / m
+        return calc_loss
+    raise ValueError(ds)

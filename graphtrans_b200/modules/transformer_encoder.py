@@ -65,7 +65,9 @@ class TransformerNodeEncoder(nn.Module):
         """h_node: [N, d] node states (gnn2transformer output) -> [B, d] encoder output at the pooled
         position (<CLS> row, or the last node when pooling == 'last')."""
         cls = self.cls_embedding
-        rows = plan.tok2node if cls is not None else plan.tok2node_nocls
+        if plan.cls != (cls is not None):
+            raise RuntimeError("GraphPlan was built with a different <CLS> setting than the encoder")
+        rows = plan.tok2node
         if self.norm_input is not None:
             x = ops.layer_norm(h_node, self.norm_input, in_rows=rows, cls=cls, n_rows=plan.n_rows)
         else:

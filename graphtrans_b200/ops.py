@@ -37,6 +37,61 @@ def act_dtype() -> torch.dtype:
     return torch.bfloat16 if _PRECISION == "bf16" else torch.float32
 
 
+# ----------------------------------------------------------------------------- dropout RNG
+_rng = {}          # device index -> int64[2] tensor {seed, step} (read by the kernels on the device)
+_salt = [0]        # call-site counter inside one step
+
+
+def rng_state(device) -> torch.Tensor:
+    idx = torch.device(device).index or 0
+    st = _rng.get(idx)
+    if st is None:
+        st = torch.tensor([torch.initial_seed() & 0x7FFFFFFFFFFFFFFF, 0], dtype=torch.int64, device=device)
+        _rng[idx] = st
+    return st
+
+
+def manual_seed(seed: int, device="cuda"):
+    rng_state(device).copy_(torch.tensor([seed & 0x7FFFFFFFFFFFFFFF, 0], dtype=torch.int64))
+
+
+def begin_step(device):
+    """advance the device-side dropout step counter (one launch; graph-capturable) and restart the
+    per-step call-site salts.  Called by the model at the top of every training forward."""
+    _salt[0] = 0
+    call("gt_rng_advance", ptr(rng_state(device)))
+
+
+def next_salt() -> int:
+    _salt[0] += 1
+    return _salt[0]
+
+
+class _DropoutFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, p, salt):
+        x = x.contiguous()
+        y = torch.empty_like(x)
+        call("gt_dropout", dt_of(x), ptr(x), x.numel(), ptr(y), float(p), ptr(rng_state(x.device)), salt)
+        ctx.meta = (p, salt)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        p, salt = ctx.meta
+        g = g.contiguous()
+        dx = torch.empty_like(g)
+        call("gt_dropout", dt_of(g), ptr(g), g.numel(), ptr(dx), float(p), ptr(rng_state(g.device)), salt)
+        return dx, None, None
+
+
+def dropout(x, p):
+    """F.dropout(x, p, training=True) on a physical matrix (numel % 4 == 0)."""
+    if not p:
+        return x
+    return _DropoutFn.apply(x, p, next_salt())
+
+
 def ldp(d: int) -> int:
     """physical leading dimension: logical width rounded up to 8 elements (16 B in bf16)."""
     return (d + 7) // 8 * 8
@@ -84,13 +139,13 @@ class GraphPlan:
     gt_csr_build / gt_batch_plan without any host synchronisation (B comes from
     `batch.num_graphs` when present, otherwise one .item() like reference gnn_module.py:195)."""
 
-    def __init__(self, edge_index, batch, num_graphs=None, max_input_len=1000, edge_attr=None):
+    def __init__(self, edge_index, batch, num_graphs=None, max_input_len=1000, cls=True):
         _lib.require_cuda(edge_index, batch)
         dev = batch.device
         N = batch.numel()
         E = edge_index.shape[1]
         B = int(num_graphs) if num_graphs is not None else int(batch[-1].item()) + 1
-        self.N, self.E, self.B, self.L = N, E, B, int(max_input_len)
+        self.N, self.E, self.B, self.L, self.cls = N, E, B, int(max_input_len), bool(cls)
         i32 = dict(dtype=torch.int32, device=dev)
         ei = edge_index.contiguous()
         self.rowptr_dst = torch.empty(N + 1, **i32)
@@ -113,7 +168,7 @@ class GraphPlan:
         self.cls_rows = torch.empty(B, **i32)
         self.scalars = torch.empty(4, **i32)
         b = batch.contiguous()
-        call("gt_batch_plan", ptr(b), N, B, self.L, ptr(self.node_off), ptr(self.kept), ptr(self.tok_off),
+        call("gt_batch_plan", ptr(b), N, B, self.L, int(self.cls), ptr(self.node_off), ptr(self.kept), ptr(self.tok_off),
              ptr(self.tok2node), ptr(self.tok_graph), ptr(self.node_graph), ptr(self.node2tok),
              ptr(self.cls_rows), ptr(self.scalars))
         self._etype = {}
@@ -187,29 +242,32 @@ def embed_sum(index_cols, tables, clamps=None):
 
 
 # ----------------------------------------------------------------------------- dense layers
-def _gemm(A, a_mn, lda, Bm, b_mn, ldb, C, ldc, M, N, K, n_fill, bias, resid, ldr, flags, impl=None):
-    call("gt_gemm", dt_of(A), ptr(A), int(a_mn), lda, ptr(Bm), int(b_mn), ldb, ptr(C), ldc, M, N, K, n_fill,
-         ptr(bias), ptr(resid), ldr, flags, GEMM_IMPL if impl is None else impl)
+def _gemm_raw(dt, A, a_mn, lda, Bm, b_mn, ldb, C, ldc, M, N, K, n_fill, bias, resid, ldr, flags, impl=None):
+    """raw-pointer gt_gemm (A, Bm, C are device addresses so strided sub-blocks need no copies)"""
+    call("gt_gemm", dt, A, int(a_mn), lda, Bm, int(b_mn), ldb, C, ldc, M, N, K, n_fill, ptr(bias), ptr(resid), ldr,
+         flags, GEMM_IMPL if impl is None else impl)
 
 
 class _LinearFn(torch.autograd.Function):
-    """y = x W^T + b (optional fused ReLU). x physical [M, ld_in] (logical K = W.shape[1]);
-    y physical [M, ldp(N)] in x.dtype (or fp32 when out_f32)."""
+    """y = x W[:, off:off+K]^T + b (optional fused ReLU / residual). x physical [M, ld_in] (logical
+    K columns); y physical [M, ldp(N)] in x.dtype (or fp32 when out_f32).  `off` selects a column
+    block of the weight (JK=cat: gnn2transformer applied to the parts without concatenating)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, relu, out_f32, resid=None):
+    def forward(ctx, x, weight, bias, relu, out_f32, resid, off, K):
         x = x.contiguous()
         M, ld_in = x.shape
-        N, K = weight.shape
+        N, Kw = weight.shape
+        K = Kw - off if K is None else K
         if K > ld_in:
             raise RuntimeError(f"linear: input width {ld_in} < in_features {K}")
+        wf = weight.contiguous()
         if x.dtype == torch.float32:
-            w = weight.contiguous()
-            ldw = K
-        else:  # bf16 operand copy of the fp32 master weight, K padded so rows stay 16-B aligned
+            w, ldw, wptr = wf, Kw, wf.data_ptr() + off * 4
+        else:  # bf16 operand copy of the fp32 master weight block, K padded so rows stay 16-B aligned
             w = torch.empty(N, ld_in, dtype=x.dtype, device=x.device)
-            call("gt_cast_pad", GT_F32, ptr(weight.contiguous()), N, K, K, dt_of(w), ptr(w), N, ld_in, ld_in)
-            ldw = ld_in
+            call("gt_cast_pad", GT_F32, wf.data_ptr() + off * 4, N, K, Kw, dt_of(w), ptr(w), N, ld_in, ld_in)
+            ldw, wptr = ld_in, w.data_ptr()
         ld_out = ldp(N)
         out_dtype = torch.float32 if out_f32 else x.dtype
         y = torch.empty(M, ld_out, dtype=out_dtype, device=x.device)
@@ -218,15 +276,18 @@ class _LinearFn(torch.autograd.Function):
             resid = resid.contiguous()
             if resid.dtype != out_dtype or resid.shape != y.shape:
                 raise RuntimeError("linear: resid must match the output")
-        _gemm(x, 0, ld_in, w, 0, ldw, y, ld_out, M, N, K, ld_out, bias, resid, ld_out, flags)
+            if out_dtype == torch.float32 and x.dtype != torch.float32:
+                flags |= _lib.EPI_RESID_F32
+        _gemm_raw(dt_of(x), x.data_ptr(), 0, ld_in, wptr, 0, ldw, y.data_ptr(), ld_out, M, N, K, ld_out, bias, resid,
+                  ld_out, flags)
         ctx.save_for_backward(x, w, y if relu else None)
-        ctx.meta = (M, N, K, ld_in, ldw, ld_out, relu, bias is not None, resid is not None)
+        ctx.meta = (M, N, K, Kw, off, ld_in, ldw, ld_out, relu, bias is not None, resid is not None)
         return y
 
     @staticmethod
     def backward(ctx, gy):
         x, w, y = ctx.saved_tensors
-        M, N, K, ld_in, ldw, ld_out, relu, has_bias, has_resid = ctx.meta
+        M, N, K, Kw, off, ld_in, ldw, ld_out, relu, has_bias, has_resid = ctx.meta
         gy = gy.contiguous()
         g_res = gy if has_resid else None
         if gy.dtype != x.dtype:  # fp32 head logits: bring the gradient to the operand dtype
@@ -234,27 +295,33 @@ class _LinearFn(torch.autograd.Function):
             call("gt_cast_pad", dt_of(gy), ptr(gy), M, ld_out, ld_out, dt_of(g2), ptr(g2), M, ld_out, ld_out)
             gy = g2
         if relu:
-            yy = y if y.dtype == gy.dtype else None
+            if y.dtype != gy.dtype:
+                raise RuntimeError("linear: relu with a widened output is not supported")
             gz = torch.empty_like(gy)
-            call("gt_relu_bwd", dt_of(gy), ptr(gy), ptr(yy), gy.numel(), ptr(gz))
+            call("gt_relu_bwd", dt_of(gy), ptr(gy), ptr(y), gy.numel(), ptr(gz))
             gy = gz
+        wptr = w.data_ptr() + (off * 4 if x.dtype == torch.float32 else 0)
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
             gx = torch.empty(M, ld_in, dtype=x.dtype, device=x.device)
             # dX[m,k] = sum_n dY[m,n] W[n,k]: B operand = W read "MN-major" (k contiguous)
-            _gemm(gy, 0, ld_out, w, 1, ldw, gx, ld_in, M, K, N, ld_in, None, None, 0, 0)
+            _gemm_raw(dt_of(x), gy.data_ptr(), 0, ld_out, wptr, 1, ldw, gx.data_ptr(), ld_in, M, K, N, ld_in, None,
+                      None, 0, 0)
         if ctx.needs_input_grad[1]:
-            gw = torch.zeros(N, K, dtype=torch.float32, device=x.device)
+            gw = torch.zeros(N, Kw, dtype=torch.float32, device=x.device)
             # dW[n,k] = sum_m dY[m,n] X[m,k]: both operands MN-major, split-K over the rows
-            _gemm(gy, 1, ld_out, x, 1, ld_in, gw, K, N, K, M, K, None, None, 0, EPI_ACCUM | EPI_OUT_F32)
+            _gemm_raw(dt_of(x), gy.data_ptr(), 1, ld_out, x.data_ptr(), 1, ld_in, gw.data_ptr() + off * 4, Kw, N, K, M,
+                      K, None, None, 0, EPI_ACCUM | EPI_OUT_F32)
         if has_bias and ctx.needs_input_grad[2]:
             gb = torch.empty(N, dtype=torch.float32, device=x.device)
             call("gt_colsum", dt_of(gy), ptr(gy), M, N, ld_out, ptr(gb))
-        return gx, gw, gb, None, None, g_res
+        return gx, gw, gb, None, None, g_res, None, None
 
 
-def linear(x, weight, bias=None, relu=False, out_f32=False, resid=None):
-    return _LinearFn.apply(x, weight, bias, relu, out_f32, resid)
+def linear(x, weight, bias=None, relu=False, out_f32=False, resid=None, drop_p=0.0, w_col_off=0, K=None):
+    """drop(act(x W[:, off:off+K]^T + b)) [+ resid]; dropout together with resid is not a reference pattern"""
+    y = _LinearFn.apply(x, weight, bias, relu, out_f32, resid, w_col_off, K)
+    return dropout(y, drop_p) if drop_p else y
 
 
 # ----------------------------------------------------------------------------- aggregation
@@ -365,7 +432,7 @@ class _BatchNormFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, gamma, beta, running_mean, running_var, nbt, training, momentum, eps, relu, resid,
-                gvec, plan):
+                gvec, plan, drop_p, salt):
         x = x.contiguous()
         M, ld = x.shape
         d = gamma.shape[0]
@@ -382,37 +449,42 @@ class _BatchNormFn(torch.autograd.Function):
             resid = resid.contiguous()
         if gvec is not None:
             gvec = gvec.contiguous()
+        rng = ptr(rng_state(dev)) if drop_p else None
         call("gt_bn_apply_fwd", dt_of(x), ptr(x), M, d, ld, ptr(ssmr), int(relu), ptr(resid), ptr(gvec),
-             ptr(plan.node_graph) if gvec is not None else None, ptr(y))
+             ptr(plan.node_graph) if gvec is not None else None, ptr(y), float(drop_p), rng, salt)
         ctx.save_for_backward(x, ssmr, gamma)
-        ctx.meta = (M, d, ld, relu, training, plan, resid is not None, gvec is not None)
+        ctx.meta = (M, d, ld, relu, training, plan, resid is not None, gvec is not None, float(drop_p), salt)
         return y
 
     @staticmethod
     def backward(ctx, g):
         x, ssmr, gamma = ctx.saved_tensors
-        M, d, ld, relu, training, plan, has_resid, has_gvec = ctx.meta
+        M, d, ld, relu, training, plan, has_resid, has_gvec, drop_p, salt = ctx.meta
         g = g.contiguous()
         dev = x.device
+        rng = ptr(rng_state(dev)) if drop_p else None
         red = torch.zeros(2 * ld, dtype=torch.float64, device=dev)
-        call("gt_bn_bwd_reduce", dt_of(x), ptr(x), ptr(g), M, d, ld, ptr(ssmr), int(relu), ptr(red))
+        call("gt_bn_bwd_reduce", dt_of(x), ptr(x), ptr(g), M, d, ld, ptr(ssmr), int(relu), ptr(red), drop_p, rng,
+             salt)
         dx = torch.empty_like(x)
         dgamma = torch.empty(d, dtype=torch.float32, device=dev)
         dbeta = torch.empty(d, dtype=torch.float32, device=dev)
         call("gt_bn_bwd_apply", dt_of(x), ptr(x), ptr(g), M, d, ld, ptr(ssmr), ptr(gamma), int(relu),
-             int(training), ptr(red), ptr(dx), ptr(dgamma), ptr(dbeta))
+             int(training), ptr(red), ptr(dx), ptr(dgamma), ptr(dbeta), drop_p, rng, salt)
         dres = g if has_resid else None
         dgv = None
         if has_gvec and ctx.needs_input_grad[11]:
             dgv = torch.zeros(plan.B, ld, dtype=torch.float32, device=dev)
             call("gt_segment_sum", dt_of(g), ptr(g), ptr(plan.node_graph), M, ld, ptr(dgv))
-        return dx, dgamma, dbeta, None, None, None, None, None, None, None, dres, dgv, None
+        return dx, dgamma, dbeta, None, None, None, None, None, None, None, dres, dgv, None, None, None
 
 
-def batch_norm(x, bn: torch.nn.BatchNorm1d, relu=False, resid=None, gvec=None, plan=None):
+def batch_norm(x, bn: torch.nn.BatchNorm1d, relu=False, resid=None, gvec=None, plan=None, drop_p=0.0):
+    """drop(act(BN(x))) [+ resid] [+ gvec[graph]] in one kernel"""
     training = bn.training or bn.running_mean is None
     return _BatchNormFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked,
-                              training, bn.momentum, bn.eps, relu, resid, gvec, plan)
+                              training, bn.momentum, bn.eps, relu, resid, gvec, plan, drop_p,
+                              next_salt() if drop_p else 0)
 
 
 # ----------------------------------------------------------------------------- LayerNorm / tokens
@@ -458,7 +530,10 @@ class _LayerNormFn(torch.autograd.Function):
                 dcls.view(cls_shape) if dcls is not None else None, None)
 
 
-def layer_norm(x, ln: torch.nn.LayerNorm, resid=None, in_rows=None, cls=None, n_rows=None):
+def layer_norm(x, ln: torch.nn.LayerNorm, resid=None, in_rows=None, cls=None, n_rows=None, drop_p=0.0):
+    """LN(drop(x)[in_rows] + resid)"""
+    if drop_p:
+        x = dropout(x, drop_p)
     return _LayerNormFn.apply(x, resid, ln.weight, ln.bias, ln.eps, in_rows, cls, n_rows)
 
 
@@ -518,7 +593,7 @@ def pad_batch_dense(h, plan, S):
 # ----------------------------------------------------------------------------- attention
 class _MHAFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, qkv, plan, nhead, key_start=None):
+    def forward(ctx, qkv, plan, nhead, key_start, drop_p, salt):
         qkv = qkv.contiguous()
         n_rows, d3 = qkv.shape
         d = d3 // 3
@@ -527,56 +602,131 @@ class _MHAFn(torch.autograd.Function):
         out = torch.empty(n_rows, d, dtype=qkv.dtype, device=qkv.device)
         lse = torch.empty(nhead * n_rows, dtype=torch.float32, device=qkv.device)
         call("gt_mha_fwd", dt_of(qkv), ptr(qkv), ptr(plan.tok_graph), ptr(plan.tok_off), ptr(key_start), n_rows,
-             plan.B, nhead, dh, scale, ptr(out), ptr(lse), MHA_IMPL)
+             plan.B, nhead, dh, scale, ptr(out), ptr(lse), float(drop_p),
+             ptr(rng_state(qkv.device)) if drop_p else None, salt, MHA_IMPL)
         ctx.save_for_backward(qkv, out, lse)
-        ctx.meta = (plan, nhead, dh, scale, key_start)
+        ctx.meta = (plan, nhead, dh, scale, key_start, float(drop_p), salt)
         return out
 
     @staticmethod
     def backward(ctx, g):
         qkv, out, lse = ctx.saved_tensors
-        plan, nhead, dh, scale, key_start = ctx.meta
+        plan, nhead, dh, scale, key_start, drop_p, salt = ctx.meta
         g = g.contiguous()
         n_rows = qkv.shape[0]
         dqkv = torch.empty_like(qkv)
         delta = torch.empty(nhead * n_rows, dtype=torch.float32, device=qkv.device)
         call("gt_mha_bwd", dt_of(qkv), ptr(qkv), ptr(out), ptr(g), ptr(lse), ptr(plan.tok_graph), ptr(plan.tok_off),
-             ptr(key_start), n_rows, plan.B, nhead, dh, scale, ptr(dqkv), ptr(delta), MHA_IMPL)
-        return dqkv, None, None, None
+             ptr(key_start), n_rows, plan.B, nhead, dh, scale, ptr(dqkv), ptr(delta), drop_p,
+             ptr(rng_state(qkv.device)) if drop_p else None, salt, MHA_IMPL)
+        return dqkv, None, None, None, None, None
 
 
-def mha_packed(qkv, plan, nhead, key_start=None):
+def mha_packed(qkv, plan, nhead, key_start=None, drop_p=0.0):
     """`plan` needs .tok_graph, .tok_off and .B (GraphPlan or any object with those fields)."""
-    return _MHAFn.apply(qkv, plan, nhead, key_start)
+    return _MHAFn.apply(qkv, plan, nhead, key_start, drop_p, next_salt() if drop_p else 0)
 
 
-# ----------------------------------------------------------------------------- PNA reduce
+# ----------------------------------------------------------------------------- PNA
+class _TowerLinearFn(torch.autograd.Function):
+    """Block-diagonal ("tower") linear: y[:, t*Fo:(t+1)*Fo] = x[:, xo_t : xo_t+K] W_t[:, wo:wo+K]^T (+ b_t),
+    xo_t = t*x_tower_stride.  One gt_gemm per tower on strided views (no copies).  Used for the PNA
+    pre-MLP halves (W_i / W_j of pre_nns[t].0) and post-MLP (post_nns[t].0)."""
+
+    @staticmethod
+    def forward(ctx, x, x_tower_stride, K, w_col_off, use_bias, n_towers, *wb):
+        ws, bs = wb[:n_towers], wb[n_towers:]
+        x = x.contiguous()
+        M, ldx = x.shape
+        Fo = ws[0].shape[0]
+        ld_out = ldp(n_towers * Fo)
+        y = torch.empty(M, ld_out, dtype=x.dtype, device=x.device)
+        if ld_out > n_towers * Fo:
+            y[:, n_towers * Fo:].zero_()
+        es = x.element_size()
+        wop = []
+        for t in range(n_towers):
+            w = ws[t].contiguous()
+            if x.dtype != torch.float32:   # low-precision operand copy of the fp32 master weight
+                wl = torch.empty(w.shape, dtype=x.dtype, device=x.device)
+                call("gt_cast_pad", GT_F32, ptr(w), w.shape[0], w.shape[1], w.shape[1], dt_of(wl), ptr(wl),
+                     w.shape[0], w.shape[1], w.shape[1])
+                w = wl
+            wop.append(w)
+            _gemm_raw(dt_of(x), x.data_ptr() + t * x_tower_stride * es, 0, ldx,
+                      w.data_ptr() + w_col_off * es, 0, w.shape[1], y.data_ptr() + t * Fo * es, ld_out, M, Fo, K, Fo,
+                      bs[t] if use_bias else None, None, 0, 0)
+        ctx.save_for_backward(x, *wop)
+        ctx.meta = (x_tower_stride, K, w_col_off, use_bias, n_towers, Fo, ld_out, [w.shape for w in ws])
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, *wop = ctx.saved_tensors
+        xs, K, wo, use_bias, T, Fo, ld_out, wshapes = ctx.meta
+        gy = gy.contiguous()
+        M, ldx = x.shape
+        es = x.element_size()
+        gx = torch.zeros_like(x)
+        gws, gbs = [], []
+        for t in range(T):
+            w = wop[t]
+            gyp = gy.data_ptr() + t * Fo * es
+            # dX_t[m,k] = sum_n dY_t[m,n] W_t[n, wo+k]
+            _gemm_raw(dt_of(x), gyp, 0, ld_out, w.data_ptr() + wo * es, 1, w.shape[1],
+                      gx.data_ptr() + t * xs * es, ldx, M, K, Fo, K, None, None, 0, 0)
+            gw = torch.zeros(wshapes[t], dtype=torch.float32, device=x.device)
+            _gemm_raw(dt_of(x), gyp, 1, ld_out, x.data_ptr() + t * xs * es, 1, ldx,
+                      gw.data_ptr() + wo * 4, gw.shape[1], Fo, K, M, K, None, None, 0, EPI_ACCUM | EPI_OUT_F32)
+            gws.append(gw)
+            if use_bias:
+                gb = torch.empty(Fo, dtype=torch.float32, device=x.device)
+                lib_call_colsum(gy, t * Fo, M, Fo, ld_out, gb)
+                gbs.append(gb)
+            else:
+                gbs.append(None)
+        return (gx, None, None, None, None, None, *gws, *gbs)
+
+
+def lib_call_colsum(g, col_off, M, n, ld, out):
+    call("gt_colsum", dt_of(g), g.data_ptr() + col_off * g.element_size(), M, n, ld, ptr(out))
+
+
+def tower_linear(x, weights, biases, x_tower_stride, K, w_col_off=0):
+    use_bias = biases is not None
+    bs = list(biases) if use_bias else [None] * len(weights)
+    return _TowerLinearFn.apply(x, x_tower_stride, K, w_col_off, use_bias, len(weights), *weights, *bs)
+
+
 class _PNAReduceFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, pj, pi, plan, d):
-        pj, pi = pj.contiguous(), pi.contiguous()
+    def forward(ctx, x, pj, pi, plan, towers, F, delta):
+        x, pj, pi = x.contiguous(), pj.contiguous(), pi.contiguous()
         N, ld = pj.shape
-        out = torch.empty(N, 4 * ld, dtype=pj.dtype, device=pj.device)
+        ld_out = towers * 13 * F
+        out = torch.empty(N, ld_out, dtype=pj.dtype, device=pj.device)
         amax = torch.empty(N, ld, dtype=torch.int32, device=pj.device)
         amin = torch.empty(N, ld, dtype=torch.int32, device=pj.device)
-        call("gt_pna_reduce_fwd", dt_of(pj), ptr(pj), ptr(pi), N, d, ld, ptr(plan.rowptr_dst), ptr(plan.src_by_dst),
-             ptr(out), ptr(amax), ptr(amin))
-        ctx.save_for_backward(pj, pi, out, amax, amin)
-        ctx.meta = (plan, d)
+        call("gt_pna_reduce_fwd", dt_of(pj), ptr(x), ptr(pj), ptr(pi), N, towers, F, ld, ptr(plan.rowptr_dst),
+             ptr(plan.src_by_dst), float(delta), ptr(out), ld_out, ptr(amax), ptr(amin))
+        ctx.save_for_backward(pj, out, amax, amin)
+        ctx.meta = (plan, towers, F, float(delta), ld_out)
         return out
 
     @staticmethod
     def backward(ctx, g):
-        pj, pi, out, amax, amin = ctx.saved_tensors
-        plan, d = ctx.meta
+        pj, out, amax, amin = ctx.saved_tensors
+        plan, towers, F, delta, ld_out = ctx.meta
         g = g.contiguous()
         N, ld = pj.shape
         dpj = torch.zeros(N, ld, dtype=torch.float32, device=pj.device)
-        dpi = torch.empty_like(pi)
-        call("gt_pna_reduce_bwd", dt_of(pj), ptr(pj), ptr(pi), ptr(out), ptr(g), N, d, ld, ptr(plan.rowptr_dst),
-             ptr(plan.src_by_dst), ptr(amax), ptr(amin), ptr(dpj), ptr(dpi))
-        return cast_to(dpj, pj.dtype), dpi, None, None
+        dpi = torch.empty_like(pj)
+        dx = torch.empty_like(pj)
+        call("gt_pna_reduce_bwd", dt_of(pj), ptr(pj), ptr(out), ptr(g), N, towers, F, ld, ld_out,
+             ptr(plan.rowptr_dst), ptr(plan.src_by_dst), delta, ptr(amax), ptr(amin), ptr(dpj), ptr(dpi), ptr(dx))
+        return dx, cast_to(dpj, pj.dtype), dpi, None, None, None, None
 
 
-def pna_reduce(pj, pi, plan, d):
-    return _PNAReduceFn.apply(pj, pi, plan, d)
+def pna_reduce(x, pj, pi, plan, towers, F, delta):
+    """[N, towers*13F]: per tower [x_t | scaled (mean,max,min,std) x 3 scalers] (post-MLP operand)"""
+    return _PNAReduceFn.apply(x, pj, pi, plan, towers, F, delta)

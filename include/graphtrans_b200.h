@@ -53,15 +53,29 @@ int gt_csr_build(const int64_t* edge_index, int64_t E, int64_t N,
 int gt_edge_type(const int64_t* edge_attr, int64_t E, int32_t ncol, const int32_t* mult_host,
                  int32_t* etype, void* stream);
 
+/* ---- dropout RNG state -------------------------------------------------------------------
+ * rng_state: DEVICE uint64[2] = {seed, step}.  Every kernel that takes (drop_p, rng_state, salt)
+ * derives its keep mask from (seed, step, salt, element index) with a counter-based hash, so
+ * forward and backward agree by construction and CUDA-graph replays see fresh masks once
+ * gt_rng_advance (step += 1) is part of the graph.  drop_p == 0 or rng_state == NULL: no dropout.
+ * Replaces nn.Dropout / F.dropout (reference modules/gnn_module.py:86-90,205-209,227-229;
+ * the four dropout sites of nn.TransformerEncoderLayer, modules/transformer_encoder.py:28-32). */
+int gt_rng_advance(uint64_t* rng_state, void* stream);
+/* y = x * keep / (1 - p), n % 4 == 0 elements; the same call on dy is the backward */
+int gt_dropout(int dt, const void* x, int64_t n, void* y, float drop_p, const uint64_t* rng_state,
+               uint64_t salt, void* stream);
+
 /* ---- batch plan (integer, bit-exact; closed form of reference modules/utils.py:5-29) ------
- * batch: int64 [N] sorted graph ids, B graphs, L = max_input_len.
- * node_off[B+1]; kept[B] = min(n_i, L); tok_off[B+1] = exclusive scan of kept+1 (packed
- * token layout: graph i owns token rows [tok_off[i], tok_off[i+1]), its last row is <CLS>);
+ * batch: int64 [N] sorted graph ids, B graphs, L = max_input_len, cls = 1 when a <CLS> row is
+ * appended per graph (graph_pooling == "cls", reference modules/transformer_encoder.py:50-55).
+ * node_off[B+1]; kept[B] = min(n_i, L); tok_off[B+1] = exclusive scan of kept+cls (packed
+ * token layout: graph i owns token rows [tok_off[i], tok_off[i+1]), its last row is <CLS> or,
+ * with cls = 0, its last node);
  * tok2node[N+B]: node id, -1 for <CLS>, -2 for unused tail rows; tok_graph[N+B]: graph id or
  * -1; node_graph[N]: int32 copy of batch; node2tok[N]: token row of a node or -1 when truncated
- * away; cls_rows[B]: token row of each graph's <CLS>;
+ * away; cls_rows[B]: token row of each graph's pooled position (<CLS>, or last node if cls = 0);
  * scalars[4] = {S = min(max n_i, L), n_tok, max n_i, 0}. */
-int gt_batch_plan(const int64_t* batch, int64_t N, int64_t B, int64_t L,
+int gt_batch_plan(const int64_t* batch, int64_t N, int64_t B, int64_t L, int32_t cls,
                   int32_t* node_off, int32_t* kept, int32_t* tok_off, int32_t* tok2node,
                   int32_t* tok_graph, int32_t* node_graph, int32_t* node2tok, int32_t* cls_rows,
                   int32_t* scalars, void* stream);
@@ -117,18 +131,21 @@ int gt_bn_finalize(const double* stats, int64_t M, int32_t d, int32_t ld, const 
                    const float* beta, float* running_mean, float* running_var, int64_t* nbt,
                    float momentum, float eps, int training, float* scale_shift_mean_rstd,
                    void* stream);
-/* y = act(x*scale+shift) [+ resid] [+ gvec[node_graph]] ; act = relu if relu!=0 */
+/* y = drop(act(x*scale+shift)) [+ resid] [+ gvec[node_graph]] ; act = relu if relu!=0 */
 int gt_bn_apply_fwd(int dt, const void* x, int64_t M, int32_t d, int32_t ld, const float* ssmr,
                     int relu, const void* resid, const float* gvec, const int32_t* node_graph,
-                    void* y, void* stream);
-/* backward pass 1: g = dy * relu'(x*scale+shift); red[0:ld] += sum g, red[ld:2ld] += sum g*xhat */
+                    void* y, float drop_p, const uint64_t* rng_state, uint64_t salt, void* stream);
+/* backward pass 1: g = dy * keep/(1-p) * relu'(x*scale+shift); red[0:ld] += sum g,
+ * red[ld:2ld] += sum g*xhat */
 int gt_bn_bwd_reduce(int dt, const void* x, const void* dy, int64_t M, int32_t d, int32_t ld,
-                     const float* ssmr, int relu, double* red, void* stream);
+                     const float* ssmr, int relu, double* red, float drop_p, const uint64_t* rng_state,
+                     uint64_t salt, void* stream);
 /* backward pass 2: dx = gamma*rstd*(g - red0/M - xhat*red1/M) (train) or g*scale (eval);
  * dgamma = red1, dbeta = red0 (fp32 [d]) */
 int gt_bn_bwd_apply(int dt, const void* x, const void* dy, int64_t M, int32_t d, int32_t ld,
                     const float* ssmr, const float* gamma, int relu, int training, const double* red,
-                    void* dx, float* dgamma, float* dbeta, void* stream);
+                    void* dx, float* dgamma, float* dbeta, float drop_p, const uint64_t* rng_state,
+                    uint64_t salt, void* stream);
 
 /* ---- dense contraction (replaces nn.Linear -> cuBLAS, reference modules/conv.py:18-20,44;
  *      modules/gnn_module.py:161-170; models/gnn_transformer.py:70,85-88; the in/out
@@ -182,30 +199,37 @@ int gt_pad_batch_bwd(int dt, const void* dpadded, const int32_t* node_off, const
  * exists in the packed layout, so the -inf key mask of the reference is implicit).
  * key_start (optional int32 [B]): first valid key row of each graph when the rows of a graph
  * begin with padding (dense left-padded layout of the public TransformerNodeEncoder API);
- * NULL = tok_off[g].  out [n_rows, d]; lse fp32 [nhead, n_rows].
+ * NULL = tok_off[g].  out [n_rows, d]; lse fp32 [nhead, n_rows].  Dropout on the attention
+ * probabilities (after softmax, as F.multi_head_attention_forward does) with drop_p/rng/salt.
  * impl: 0 auto, 1 CUDA-core, 2 tcgen05. */
 int gt_mha_fwd(int dt, const void* qkv, const int32_t* tok_graph, const int32_t* tok_off,
                const int32_t* key_start, int64_t n_rows, int64_t B, int32_t nhead, int32_t dh,
-               float scale, void* out, float* lse, int impl, void* stream);
+               float scale, void* out, float* lse, float drop_p, const uint64_t* rng_state,
+               uint64_t salt, int impl, void* stream);
 int gt_mha_bwd(int dt, const void* qkv, const void* out, const void* dout, const float* lse,
                const int32_t* tok_graph, const int32_t* tok_off, const int32_t* key_start,
                int64_t n_rows, int64_t B, int32_t nhead, int32_t dh, float scale, void* dqkv,
-               float* delta, int impl, void* stream);
+               float* delta, float drop_p, const uint64_t* rng_state, uint64_t salt, int impl,
+               void* stream);
 
 /* ---- PNA multi-aggregator reduce (reference modules/pna_layer.py:131-167 via
  *      modules/pna/pna_module.py:43-51; aggregators.py:11-34; scalers.py:10-31) ---------------
- * pj, pi: per-node tower projections [N, ld] (W_j x_j and W_i x_i + b); for
- * every target i and channel c over in-edges: mean, max, min, std of m = pi[i] + pj[src];
- * empty segment -> mean=max=min=0, std=sqrt(1e-5).  out [N, 4*ld] = (mean|max|min|std);
- * argmax/argmin int32 [N, ld] saved for the backward. */
-int gt_pna_reduce_fwd(int dt, const void* pj, const void* pi, int64_t N, int32_t d, int32_t ld,
-                      const int32_t* rowptr_dst, const int32_t* src_by_dst,
-                      void* out, int32_t* argmax, int32_t* argmin, void* stream);
-/* dpj, dpi from dout [N,4*ld]; dpj accumulated with atomics (fp32 [N,ld], pre-zeroed) */
-int gt_pna_reduce_bwd(int dt, const void* pj, const void* pi, const void* out, const void* dout,
-                      int64_t N, int32_t d, int32_t ld, const int32_t* rowptr_dst,
-                      const int32_t* src_by_dst, const int32_t* argmax, const int32_t* argmin,
-                      float* dpj, void* dpi, void* stream);
+ * x [N, ld]: layer input viewed as `towers` towers of F channels (d = towers*F <= ld, F % 4 == 0);
+ * pj, pi [N, ld]: per-node tower projections W_j x_j and W_i x_i + b.  For every
+ * target i and channel over its in-edges: mean, max, min, std of m = pi[i] + pj[src]; empty
+ * segment -> mean = max = min = 0, std = sqrt(1e-5).  delta = avg_deg['log'] (pna_layer.py:92-97).
+ * out [N, ld_out >= towers*13F]: per tower [x_t | 1*(mean,max,min,std) | amp*(..) | att*(..)],
+ * i.e. exactly the operand of post_nns[t]; argmax/argmin int32 [N, ld] saved for the backward. */
+int gt_pna_reduce_fwd(int dt, const void* x, const void* pj, const void* pi, int64_t N, int32_t towers,
+                      int32_t F, int32_t ld, const int32_t* rowptr_dst, const int32_t* src_by_dst,
+                      float delta, void* out, int32_t ld_out, int32_t* argmax, int32_t* argmin,
+                      void* stream);
+/* from dout [N, ld_out]: dpj accumulated with atomics (fp32 [N, ld], pre-zeroed), dpi [N, ld] and
+ * the pass-through dx [N, ld] (gradient of the x_t slots) overwritten */
+int gt_pna_reduce_bwd(int dt, const void* pj, const void* out, const void* dout, int64_t N,
+                      int32_t towers, int32_t F, int32_t ld, int32_t ld_out, const int32_t* rowptr_dst,
+                      const int32_t* src_by_dst, float delta, const int32_t* argmax,
+                      const int32_t* argmin, float* dpj, void* dpi, void* dx, void* stream);
 
 #ifdef __cplusplus
 }

@@ -150,11 +150,37 @@ def cases():
     return out
 
 
+def pad_batch_cases(out_dir):
+    """integer/index fixture: the reference's own pad_batch / unpad_batch Python loops
+    (reference modules/utils.py:5-53) on ragged batches incl. truncation and 1-node graphs."""
+    from modules.utils import pad_batch, unpad_batch
+    cases = []
+    g = torch.Generator().manual_seed(0)
+    for sizes in ([1], [3, 1, 5], [2, 9, 4, 1, 7], [12, 30, 1, 2, 2, 17], [5] * 4):
+        for L in (1, 3, 7, 1000):
+            for d in (4, 6):
+                n = torch.tensor(sizes)
+                batch = torch.repeat_interleave(torch.arange(len(sizes)), n)
+                h = torch.randn(int(n.sum()), d, generator=g)
+                padded, mask, num_nodes, masks, max_n = pad_batch(h, batch, L, get_mask=True)
+                prev = torch.randn(int(n.sum()), d, generator=g)
+                un = unpad_batch(padded, prev, num_nodes, masks, max_n)
+                cases.append(dict(sizes=sizes, L=L, h=h, batch=batch, padded=padded, mask=mask,
+                                  num_nodes=[int(v) for v in num_nodes], max_num_nodes=int(max_n), prev=prev,
+                                  unpadded=un))
+    torch.save(cases, os.path.join(out_dir, "_pad_batch_ref.pt"))
+    print(f"_pad_batch_ref: {len(cases)} cases")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "tests", "golden"))
+    ap.add_argument("--only-pad", action="store_true")
     ns = ap.parse_args()
     os.makedirs(ns.out, exist_ok=True)
+    pad_batch_cases(ns.out)
+    if ns.only_pad:
+        return
     for name, (args, batch) in cases().items():
         res = run_reference(args, batch)
         fixture = dict(name=name, args=vars(args), batch={k: v for k, v in batch.__dict__.items()}, **res)

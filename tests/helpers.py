@@ -8,7 +8,8 @@ import torch
 from graphtrans_b200.synth import GraphBatch
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-GOLDEN_CASES = sorted(os.path.basename(p)[:-3] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.pt")))
+GOLDEN_CASES = sorted(os.path.basename(p)[:-3] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.pt"))
+                      if not os.path.basename(p).startswith("_"))
 
 
 def load_golden(name):

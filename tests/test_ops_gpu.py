@@ -1,0 +1,187 @@
+"""Operator-level GPU tests through the C ABI against plain fp32/fp64 torch references of the same
+op (dense contraction layouts and epilogues, packed masked attention fwd/bwd, dropout masks)."""
+import math
+
+import pytest
+import torch
+
+from graphtrans_b200 import _lib, ops
+from graphtrans_b200._lib import EPI_ACCUM, EPI_OUT_F32, EPI_RELU, call, dt_of, ptr
+from tests.helpers import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 1), (1, 0)])
+@pytest.mark.parametrize("M,N,K", [(70, 36, 300), (129, 600, 304), (513, 128, 64), (5, 5002, 128)])
+def test_gemm_layouts(dtype, a_mn, b_mn, M, N, K):
+    torch.manual_seed(0)
+    A = torch.randn((K, M) if a_mn else (M, K), device="cuda").to(dtype)
+    Bm = torch.randn((K, N) if b_mn else (N, K), device="cuda").to(dtype)
+    bias = torch.randn(N, device="cuda")
+    ldc = (N + 7) // 8 * 8
+    C = torch.full((M, ldc), 7.0, device="cuda", dtype=dtype)
+    call("gt_gemm", dt_of(A), ptr(A), a_mn, A.shape[1], ptr(Bm), b_mn, Bm.shape[1], ptr(C), ldc, M, N, K, ldc,
+         ptr(bias), None, 0, EPI_RELU, ops.GEMM_IMPL)
+    Af = (A.t() if a_mn else A).double()
+    Bf = (Bm.t() if b_mn else Bm).double()
+    ref = torch.relu(Af @ Bf.t() + bias.double())
+    assert rel_l2(C[:, :N], ref) < (1e-5 if dtype == torch.float32 else 6e-3)
+    assert (C[:, N:] == 0).all()            # pad columns are kept zero
+
+
+def test_gemm_splitk_accumulate():
+    torch.manual_seed(1)
+    M, N, K = 40, 24, 5000
+    A = torch.randn(K, M, device="cuda")
+    Bm = torch.randn(K, N, device="cuda")
+    C = torch.zeros(M, N, device="cuda")
+    call("gt_gemm", 0, ptr(A), 1, M, ptr(Bm), 1, N, ptr(C), N, M, N, K, N, None, None, 0, EPI_ACCUM | EPI_OUT_F32,
+         ops.GEMM_IMPL)
+    assert rel_l2(C, A.double().t() @ Bm.double()) < 1e-5
+
+
+def _ref_attention(qkv, tok_off, nhead):
+    n, d3 = qkv.shape
+    d = d3 // 3
+    dh = d // nhead
+    out = torch.zeros(n, d, dtype=qkv.dtype, device=qkv.device)
+    for g in range(len(tok_off) - 1):
+        lo, hi = tok_off[g], tok_off[g + 1]
+        q, k, v = qkv[lo:hi].split(d, dim=1)
+        q = q.view(-1, nhead, dh).transpose(0, 1) * dh ** -0.5
+        k = k.view(-1, nhead, dh).transpose(0, 1)
+        v = v.view(-1, nhead, dh).transpose(0, 1)
+        p = torch.softmax(q @ k.transpose(1, 2), -1)
+        out[lo:hi] = (p @ v).transpose(0, 1).reshape(hi - lo, d)
+    return out
+
+
+class _Plan:
+    pass
+
+
+def _packed_plan(lens, extra=3):
+    p = _Plan()
+    off = [0]
+    for n in lens:
+        off.append(off[-1] + n)
+    p.B = len(lens)
+    p.tok_off = torch.tensor(off, dtype=torch.int32, device="cuda")
+    tg = sum(([g] * n for g, n in enumerate(lens)), []) + [-1] * extra
+    p.tok_graph = torch.tensor(tg, dtype=torch.int32, device="cuda")
+    return p, off
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("nhead,dh", [(4, 32), (4, 64), (2, 8)])
+def test_mha_packed_fwd_bwd(dtype, nhead, dh):
+    torch.manual_seed(0)
+    lens = [1, 2, 33, 70, 129, 5]
+    plan, off = _packed_plan(lens)
+    n = off[-1] + 3
+    d = nhead * dh
+    qkv = torch.randn(n, 3 * d, device="cuda").to(dtype).requires_grad_(True)
+    out = ops.mha_packed(qkv, plan, nhead)
+    w = torch.randn(n, d, device="cuda").to(dtype)
+    w[off[-1]:] = 0
+    (out.float() * w.float()).sum().backward()
+    q64 = qkv.detach().double().requires_grad_(True)
+    ref = _ref_attention(q64, off, nhead)
+    (ref * w.double()).sum().backward()
+    tol = 1e-5 if dtype == torch.float32 else 2e-2
+    assert rel_l2(out[:off[-1]].detach(), ref[:off[-1]].detach()) < tol
+    assert (out[off[-1]:] == 0).all()
+    assert rel_l2(qkv.grad[:off[-1]], q64.grad[:off[-1]]) < tol
+    assert (qkv.grad[off[-1]:] == 0).all()
+
+
+def test_mha_key_start_dense_layout():
+    """left-padded dense layout of the public TransformerNodeEncoder API: rows before key_start are
+    never keys (the reference's -inf key_padding_mask) and receive zero K/V gradient"""
+    torch.manual_seed(3)
+    nhead, dh, T = 4, 16, 12
+    lens_valid = [12, 5, 1]
+    plan, off = _packed_plan([T] * 3, extra=0)
+    ks = torch.tensor([off[g] + T - lens_valid[g] for g in range(3)], dtype=torch.int32, device="cuda")
+    d = nhead * dh
+    qkv = torch.randn(3 * T, 3 * d, device="cuda", requires_grad=True)
+    out = ops.mha_packed(qkv, plan, nhead, key_start=ks)
+    w = torch.randn_like(out)
+    (out * w).sum().backward()
+    q64 = qkv.detach().double().requires_grad_(True)
+    outs = []
+    for g in range(3):
+        blk = q64[off[g]:off[g + 1]]
+        q, k, v = blk.split(d, 1)
+        q = q.view(T, nhead, dh).transpose(0, 1) * dh ** -0.5
+        k = k.view(T, nhead, dh).transpose(0, 1)
+        v = v.view(T, nhead, dh).transpose(0, 1)
+        s = q @ k.transpose(1, 2)
+        s[:, :, :T - lens_valid[g]] = float("-inf")
+        outs.append((torch.softmax(s, -1) @ v).transpose(0, 1).reshape(T, d))
+    ref = torch.cat(outs)
+    (ref * w.double()).sum().backward()
+    assert rel_l2(out.detach(), ref.detach()) < 1e-5
+    assert rel_l2(qkv.grad, q64.grad) < 1e-5
+
+
+@pytest.mark.parametrize("p", [0.1, 0.3, 0.5])
+def test_dropout_kernel(p):
+    ops.manual_seed(123)
+    ops.begin_step("cuda")
+    x = torch.ones(1 << 20, 8, device="cuda", requires_grad=True)
+    y = ops.dropout(x, p)
+    keep = (y != 0).float().mean().item()
+    assert abs(keep - (1 - p)) < 3e-3
+    assert torch.allclose(y[y != 0], torch.tensor(1 / (1 - p), device="cuda"))
+    y.sum().backward()
+    assert torch.equal(x.grad, y.detach())            # the backward re-creates the same mask
+    y2 = ops.dropout(x, p)                            # next call site: a different mask
+    assert not torch.equal(y2, y)
+    ops.begin_step("cuda")                            # next step: different again
+    y3 = ops.dropout(x, p)
+    assert not torch.equal(y3, y)
+    # rows / columns are not correlated (hash quality smoke test)
+    m = (y.detach() != 0).float()
+    assert abs(m.mean(0) - (1 - p)).max() < 5e-3
+
+
+def test_mha_dropout_matches_masked_reference():
+    """the kernel's keep mask is recovered from a run with V = identity blocks, then the dropped
+    attention is checked against softmax * mask / (1-p) in fp64, forward and backward"""
+    torch.manual_seed(4)
+    nhead, dh, n = 1, 64, 48
+    p = 0.3
+    plan, off = _packed_plan([n], extra=0)
+    d = nhead * dh
+    ops.manual_seed(9)
+    ops.begin_step("cuda")
+    qkv = torch.randn(n, 3 * d, device="cuda")
+    # pass 1: Q = K = 0 -> uniform probabilities 1/n; V = I (n <= dh) -> out[i, j] = mask[i, j] / (n (1-p))
+    probe = torch.zeros_like(qkv)
+    probe[:, 2 * d:2 * d + n] = torch.eye(n, device="cuda")
+    salt = 77
+    out = ops._MHAFn.apply(probe, plan, nhead, None, p, salt)
+    mask = (out[:, :n] > 0).double()
+    assert abs(mask.mean().item() - (1 - p)) < 0.05
+    qkv.requires_grad_(True)
+    out = ops._MHAFn.apply(qkv, plan, nhead, None, p, salt)
+    w = torch.randn_like(out)
+    (out * w).sum().backward()
+    q64 = qkv.detach().double().requires_grad_(True)
+    q, k, v = q64.split(d, 1)
+    pr = torch.softmax((q * dh ** -0.5) @ k.t(), -1) * mask / (1 - p)
+    ref = pr @ v
+    (ref * w.double()).sum().backward()
+    assert rel_l2(out.detach(), ref.detach()) < 1e-5
+    assert rel_l2(qkv.grad, q64.grad) < 1e-5
+
+
+def test_errors_are_loud():
+    x = torch.zeros(4, 6, device="cuda")
+    with pytest.raises(RuntimeError, match="gt_dropout"):
+        call("gt_dropout", 0, ptr(x), 3, ptr(x), 0.5, None, 0)
+    with pytest.raises(TypeError):
+        _lib.dt_of(torch.zeros(1, dtype=torch.float16))
