@@ -268,12 +268,12 @@ def main_b200(ns):
     e2e = None
     if not ns.no_e2e:
         for i in range(2):
-            float(step(host_batches[i % len(host_batches)].to(dev, non_blocking=True)))
+            float(step(host_batches[i % len(host_batches)].to(dev, non_blocking=True)).detach())
         barrier()
         t0 = time.perf_counter()
         for i in range(K):
             b = host_batches[i % len(host_batches)].to(dev, non_blocking=True)
-            float(step(b))                              # .item(): device->host read of the loss
+            float(step(b).detach())                     # .item(): device->host read of the loss
         barrier()
         te = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
         if world > 1:

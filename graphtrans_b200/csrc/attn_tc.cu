@@ -1,15 +1,301 @@
-// tcgen05 attention placeholder (see gemm_tc.cu note).
-#include "common.cuh"
+// Stage 2 on tensor cores: masked multi-head self-attention over PACKED tokens with tcgen05 / TMEM / TMA
+// (bf16 operands, fp32 accumulate).  Replaces F.multi_head_attention_forward's bmm / masked_fill / softmax / bmm
+// (reference modules/transformer_encoder.py:28-32,59).
+//
+// Work item = (128 consecutive packed token rows, head).  Token rows are sorted by graph and the keys of a row
+// are exactly the rows of its graph, so the keys a 128-row query tile can see form ONE contiguous row range
+// [tok_off[g_first], tok_off[g_last + 1]): the kernel streams that range in 128-key tiles and masks with the
+// per-row bounds [lo, hi) (block-diagonal attention; the reference's -inf key-padding mask is implicit).
+//
+//   warp 0     : TMA producer - Q tile once, K / V tiles through small rings (cp.async.bulk.tensor.2d, swizzled)
+//   warp 1     : MMA issuer   - S = Q K^T (128x128xdh) into TMEM, then O_j = P V_j (128 x dh x 128) into TMEM
+//   warps 2..5 : softmax      - one thread per query row: tcgen05.ld S -> scale/mask -> online max/sum (exp2) ->
+//                               dropout -> P (bf16) into swizzled smem as the A operand of the PV MMA; the running
+//                               output lives in registers: o = o * corr + O_j (O_j read back with tcgen05.ld)
+// The backward follows FlashAttention-2's recompute scheme with the same roles (see k_mha_tc_bwd_*).
+#include "tc_common.cuh"
+
 namespace gt {
-int mha_tc_fwd_launch(int, const void*, const int32_t*, const int32_t*, const int32_t*, int64_t, int64_t, int32_t, int32_t, float,
-                      void*, float*, float, const uint64_t*, uint64_t, cudaStream_t) {
-    set_error("tcgen05 attention not built");
-    return -2;
+
+__device__ __forceinline__ uint64_t att_drop_idx_tc(int h, int64_t q, int64_t k, int64_t n_rows) {
+    return ((uint64_t)h * (uint64_t)n_rows + (uint64_t)q) * (uint64_t)n_rows + (uint64_t)k;
 }
+
+namespace tc {
+
+constexpr int ATT_THREADS = 192;
+constexpr int BQ = 128, BKV = 128;
+constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+
+// K-major operand tile with `pitch`-byte rows (pitch = 64: SWIZZLE_64B, 128: SWIZZLE_128B)
+__device__ __forceinline__ uint64_t desc_k(uint32_t saddr, uint32_t pitch) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)((8 * pitch) >> 4) << 32) | (1ull << 46) |
+           ((pitch == 128 ? 2ull : 4ull) << 61);
+}
+// MN-major operand tile: k rows of `pitch` bytes holding pitch/2 contiguous m|n elements (one chunk wide)
+__device__ __forceinline__ uint64_t desc_mn(uint32_t saddr, uint32_t pitch) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)((8 * pitch) >> 4) << 32) | (1ull << 46) |
+           ((pitch == 128 ? 2ull : 4ull) << 61);
+}
+__device__ __forceinline__ uint32_t idesc_f16(bool a_mn, bool b_mn, int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// byte offset of the 16-byte chunk holding elements [c, c+8) of row r in a [128 x 128] bf16 K-major operand stored
+// as two 64-column SWIZZLE_128B blocks of 16 KB
+__device__ __forceinline__ uint32_t p_chunk_off(int r, int c) {
+    return (uint32_t)(c >> 6) * 16384u + (uint32_t)r * 128u + ((((uint32_t)(c & 63) >> 3) ^ ((uint32_t)r & 7u)) << 4);
+}
+
+struct AttnParams {
+    const int32_t* tok_graph;
+    const int32_t* tok_off;
+    void* out;
+    float* lse;
+    const uint64_t* rng;
+    uint64_t salt;
+    int64_t n_rows;
+    int B, nhead, d;
+    float scale_log2, drop_p;
+};
+
+template <int DH>
+__global__ void __launch_bounds__(ATT_THREADS)
+k_mha_tc_fwd(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p) {
+    constexpr int PITCH = DH * 2;                 // bytes per operand row
+    constexpr int TILE = 128 * PITCH;             // Q / K / V tile bytes
+    constexpr int KST = 2, VST = (DH == 64 ? 1 : 2);
+    constexpr uint32_t TMEM_COLS = 256;           // S: [0,128), O_j: [128, 128+DH)
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t q_full, k_full[KST], k_empty[KST], v_full[VST], v_empty[VST], s_full, p_full, o_full;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ int kv_lo_s, nkv_s;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * BQ, h = blockIdx.y;
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t q_s = base, k_s = q_s + TILE, v_s = k_s + KST * TILE, p_s = v_s + VST * TILE;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&q_full, 1);
+        for (int s = 0; s < KST; ++s) mbar_init(&k_full[s], 1), mbar_init(&k_empty[s], 1);
+        for (int s = 0; s < VST; ++s) mbar_init(&v_full[s], 1), mbar_init(&v_empty[s], 1);
+        mbar_init(&s_full, 1);
+        mbar_init(&p_full, 128);
+        mbar_init(&o_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_async_smem();
+        // contiguous key-row range visible from this query tile
+        const int n_tok = p.tok_off[p.B];
+        int lo = 0, n = 0;
+        if (q0 < n_tok) {
+            const int g0 = p.tok_graph[q0];
+            const int last = min(q0 + BQ - 1, n_tok - 1);
+            const int g1 = p.tok_graph[last];
+            lo = p.tok_off[g0];
+            n = (p.tok_off[g1 + 1] - lo + BKV - 1) / BKV;
+        }
+        kv_lo_s = lo;
+        nkv_s = n;
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    const int kv_lo = kv_lo_s, nkv = nkv_s;
+
+    if (warp == 0) {
+        if (lane == 0 && nkv > 0) {  // ===== TMA producer =====
+            mbar_expect_tx(&q_full, TILE);
+            tma_load_2d(q_s, &tma_qkv, &q_full, h * DH, q0);
+            for (int j = 0; j < nkv; ++j) {
+                const int ks = j % KST, vs = j % VST;
+                mbar_wait(&k_empty[ks], ((uint32_t)(j / KST) & 1u) ^ 1u);
+                mbar_expect_tx(&k_full[ks], TILE);
+                tma_load_2d(k_s + ks * TILE, &tma_qkv, &k_full[ks], p.d + h * DH, kv_lo + j * BKV);
+                mbar_wait(&v_empty[vs], ((uint32_t)(j / VST) & 1u) ^ 1u);
+                mbar_expect_tx(&v_full[vs], TILE);
+                tma_load_2d(v_s + vs * TILE, &tma_qkv, &v_full[vs], 2 * p.d + h * DH, kv_lo + j * BKV);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && nkv > 0) {  // ===== MMA issuer =====
+            const uint32_t id_s = idesc_f16(false, false, BQ, BKV);   // S = Q K^T   : A, B K-major (k = dh)
+            const uint32_t id_o = idesc_f16(false, true, BQ, DH);     // O = P V     : A K-major (k = key), B MN-major
+            mbar_wait(&q_full, 0);
+            for (int j = 0; j < nkv; ++j) {
+                const int ks = j % KST, vs = j % VST;
+                mbar_wait(&k_full[ks], (uint32_t)(j / KST) & 1u);
+                tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < DH / 16; ++k)
+                    umma_f16(tmem, desc_k(q_s + k * 32, PITCH), desc_k(k_s + ks * TILE + k * 32, PITCH), id_s, k > 0);
+                umma_commit(&k_empty[ks]);
+                umma_commit(&s_full);
+                mbar_wait(&p_full, (uint32_t)j & 1u);      // P_j is in smem and S_j has been consumed
+                mbar_wait(&v_full[vs], (uint32_t)(j / VST) & 1u);
+                tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < BKV / 16; ++k)
+                    umma_f16(tmem + 128, desc_k(p_s + (k >> 2) * 16384 + (k & 3) * 32, 128),
+                             desc_mn(v_s + vs * TILE + k * 16 * PITCH, PITCH), id_o, k > 0);
+                umma_commit(&v_empty[vs]);
+                umma_commit(&o_full);
+            }
+        }
+    } else {  // ===== softmax warps: one thread per query row =====
+        const int qd = warp & 3;
+        const int r = qd * 32 + lane;              // row inside the tile = TMEM lane
+        const int64_t row = (int64_t)q0 + r;
+        const uint32_t t_lane = tmem + ((uint32_t)(qd * 32) << 16);
+        int lo = 0, hi = 0;
+        if (row < p.n_rows) {
+            const int g = p.tok_graph[row];
+            if (g >= 0) lo = p.tok_off[g], hi = p.tok_off[g + 1];
+        }
+        const Drop dr = make_drop(p.rng, p.salt, p.drop_p);
+        float m = -INFINITY, l = 0.f;
+        float o[DH];
+#pragma unroll
+        for (int i = 0; i < DH; ++i) o[i] = 0.f;
+        for (int j = 0; j < nkv; ++j) {
+            const int kv0 = kv_lo + j * BKV;
+            mbar_wait(&s_full, (uint32_t)j & 1u);
+            tc_fence_after();
+            // pass 1: row maximum over the valid keys of this tile
+            float mt = -INFINITY;
+#pragma unroll 1
+            for (int c = 0; c < BKV; c += 16) {
+                uint32_t rr[16];
+                tmem_ld16(t_lane + c, rr);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int key = kv0 + c + i;
+                    if (key >= lo && key < hi) mt = fmaxf(mt, __uint_as_float(rr[i]));
+                }
+            }
+            const float m_new = fmaxf(m, mt * p.scale_log2);
+            const float corr = (m_new == -INFINITY) ? 1.f : exp2f(m - m_new);
+            const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+            // pass 2: probabilities -> P (bf16, swizzled K-major smem), row sum
+            float lt = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < BKV; c += 16) {
+                uint32_t rr[16];
+                tmem_ld16(t_lane + c, rr);
+                float pv[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int key = kv0 + c + i;
+                    const bool valid = key >= lo && key < hi;
+                    float e = valid ? exp2f(fmaf(__uint_as_float(rr[i]), p.scale_log2, -m_use)) : 0.f;
+                    lt += e;
+                    if (dr.on && valid) e *= drop1(dr, att_drop_idx_tc(h, row, key, p.n_rows));
+                    pv[i] = e;
+                }
+#pragma unroll
+                for (int i = 0; i < 16; i += 8) {
+                    __nv_bfloat162 h0 = __floats2bfloat162_rn(pv[i], pv[i + 1]), h1 = __floats2bfloat162_rn(pv[i + 2], pv[i + 3]);
+                    __nv_bfloat162 h2 = __floats2bfloat162_rn(pv[i + 4], pv[i + 5]), h3 = __floats2bfloat162_rn(pv[i + 6], pv[i + 7]);
+                    const uint32_t a = p_s + p_chunk_off(r, c + i);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(*reinterpret_cast<uint32_t*>(&h0)),
+                                 "r"(*reinterpret_cast<uint32_t*>(&h1)), "r"(*reinterpret_cast<uint32_t*>(&h2)),
+                                 "r"(*reinterpret_cast<uint32_t*>(&h3)) : "memory");
+                }
+            }
+            l = l * corr + lt;
+            m = m_new;
+            fence_async_smem();      // generic-proxy smem writes -> visible to the tensor core (async proxy)
+            tc_fence_before();
+            mbar_arrive(&p_full);
+            // accumulate this tile's P V
+            mbar_wait(&o_full, (uint32_t)j & 1u);
+            tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < DH; c += 16) {
+                uint32_t rr[16];
+                tmem_ld16(t_lane + 128 + c, rr);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) o[c + i] = fmaf(o[c + i], corr, __uint_as_float(rr[i]));
+            }
+            tc_fence_before();
+        }
+        if (row < p.n_rows) {
+            const float inv = l > 0.f ? 1.f / l : 0.f;
+            bf16* op = (bf16*)p.out + row * p.d + h * DH;
+#pragma unroll
+            for (int i = 0; i < DH; i += 8) {
+                uint4 pk;
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(o[i] * inv, o[i + 1] * inv), h1 = __floats2bfloat162_rn(o[i + 2] * inv, o[i + 3] * inv);
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(o[i + 4] * inv, o[i + 5] * inv), h3 = __floats2bfloat162_rn(o[i + 6] * inv, o[i + 7] * inv);
+                pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                *reinterpret_cast<uint4*>(op + i) = pk;
+            }
+            p.lse[(int64_t)h * p.n_rows + row] = l > 0.f ? (m + log2f(l)) * LN2 : 0.f;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+template <int DH>
+static cudaError_t launch_fwd(const CUtensorMap& map, const AttnParams& p, cudaStream_t st) {
+    constexpr int TILE = 128 * DH * 2;
+    constexpr int KST = 2, VST = (DH == 64 ? 1 : 2);
+    const size_t smem = (size_t)(1 + KST + VST) * TILE + 32768 + 1024;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_mha_tc_fwd<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr = true;
+    }
+    dim3 grid((unsigned)((p.n_rows + BQ - 1) / BQ), (unsigned)p.nhead);
+    k_mha_tc_fwd<DH><<<grid, ATT_THREADS, smem, st>>>(map, p);
+    return cudaGetLastError();
+}
+
+}  // namespace tc
+
+int mha_tc_fwd_launch(int dt, const void* qkv, const int32_t* tok_graph, const int32_t* tok_off, const int32_t* key_start,
+                      int64_t n_rows, int64_t B, int32_t nhead, int32_t dh, float scale, void* out, float* lse, float drop_p,
+                      const uint64_t* rng, uint64_t salt, cudaStream_t st) {
+    using namespace tc;
+    if (dt != GT_BF16) { set_error("tcgen05 attention takes bf16 activations"); return -2; }
+    if (dh != 32 && dh != 64) { set_error("tcgen05 attention is built for head dims 32 and 64"); return -2; }
+    if (key_start) { set_error("dense left-padded layout (key_start) runs on the CUDA-core kernel"); return -2; }
+    const int d = nhead * dh;
+    if (((uintptr_t)qkv & 15) || ((uintptr_t)out & 15) || n_rows >= (1ll << 31)) { set_error("alignment"); return -2; }
+    CUtensorMap map;
+    if (!make_map(&map, qkv, (uint64_t)3 * d, (uint64_t)n_rows, (uint64_t)3 * d, (uint32_t)dh, 128, dh * 2)) {
+        set_error("cuTensorMapEncodeTiled failed or unavailable");
+        return -2;
+    }
+    AttnParams p;
+    p.tok_graph = tok_graph; p.tok_off = tok_off; p.out = out; p.lse = lse; p.rng = rng; p.salt = salt;
+    p.n_rows = n_rows; p.B = (int)B; p.nhead = nhead; p.d = d;
+    p.scale_log2 = scale * LOG2E; p.drop_p = drop_p;
+    const cudaError_t e = dh == 64 ? launch_fwd<64>(map, p, st) : launch_fwd<32>(map, p, st);
+    if (e != cudaSuccess) return cuda_fail(e, "gt_mha_fwd(tcgen05)");
+    return 0;
+}
+
 int mha_tc_bwd_launch(int, const void*, const void*, const void*, const float*, const int32_t*, const int32_t*,
                       const int32_t*, int64_t, int64_t, int32_t, int32_t, float, void*, float*, float, const uint64_t*,
                       uint64_t, cudaStream_t) {
-    set_error("tcgen05 attention not built");
+    set_error("tcgen05 attention backward not built");
     return -2;
 }
 }  // namespace gt

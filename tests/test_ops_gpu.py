@@ -185,3 +185,83 @@ def test_errors_are_loud():
         call("gt_dropout", 0, ptr(x), 3, ptr(x), 0.5, None, 0)
     with pytest.raises(TypeError):
         _lib.dt_of(torch.zeros(1, dtype=torch.float16))
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 1), (1, 0)])
+@pytest.mark.parametrize("M,N,K", [(136, 304, 1000), (128, 64, 64), (1000, 608, 304), (264, 5008, 256), (72, 200, 40)])
+@pytest.mark.parametrize("out_f32", [False, True])
+def test_gemm_tcgen05_forced(a_mn, b_mn, M, N, K, out_f32):
+    """impl=2: the tcgen05/TMEM/TMA kernel only (an ineligible call would raise), every operand
+    major-ness, ragged tiles in M, N and K, bias + residual + ReLU epilogue, bf16 and fp32 outputs"""
+    torch.manual_seed(0)
+    A = (torch.randn((K, M) if a_mn else (M, K), device="cuda")).bfloat16()
+    Bm = (torch.randn((K, N) if b_mn else (N, K), device="cuda")).bfloat16()
+    bias = torch.randn(N, device="cuda")
+    odt = torch.float32 if out_f32 else torch.bfloat16
+    resid = torch.randn(M, N, device="cuda").to(odt)
+    C = torch.full((M, N), 7.0, device="cuda", dtype=odt)
+    flags = EPI_RELU | (EPI_OUT_F32 | _lib.EPI_RESID_F32 if out_f32 else 0)
+    call("gt_gemm", 1, ptr(A), a_mn, A.shape[1], ptr(Bm), b_mn, Bm.shape[1], ptr(C), N, M, N, K, N, ptr(bias),
+         ptr(resid), N, flags, 2)
+    Af = (A.t() if a_mn else A).double()
+    Bf = (Bm.t() if b_mn else Bm).double()
+    ref = torch.relu(Af @ Bf.t() + bias.double() + resid.double())
+    assert rel_l2(C, ref) < (5e-3 if not out_f32 else 1e-5 * K ** 0.5 + 1e-6)
+
+
+@pytest.mark.parametrize("M,N,K", [(600, 304, 13512), (128, 608, 530000), (5008, 256, 128)])
+def test_gemm_tcgen05_splitk_weight_gradient(M, N, K):
+    """dW[n,k] = sum_rows dY[row,n] X[row,k]: both operands MN-major, split-K with vector fp32 reductions"""
+    torch.manual_seed(1)
+    dY = torch.randn(K, M, device="cuda").bfloat16()
+    X = torch.randn(K, N, device="cuda").bfloat16()
+    C = torch.zeros(M, N, device="cuda")
+    call("gt_gemm", 1, ptr(dY), 1, M, ptr(X), 1, N, ptr(C), N, M, N, K, N, None, None, 0, EPI_ACCUM | EPI_OUT_F32, 2)
+    ref = dY.double().t() @ X.double()
+    assert rel_l2(C, ref) < 1e-4
+
+
+def _mha_raw(qkv, plan, nhead, impl, drop_p=0.0, salt=0):
+    n, d3 = qkv.shape
+    d = d3 // 3
+    dh = d // nhead
+    out = torch.empty(n, d, dtype=qkv.dtype, device="cuda")
+    lse = torch.empty(nhead * n, dtype=torch.float32, device="cuda")
+    call("gt_mha_fwd", dt_of(qkv), ptr(qkv), ptr(plan.tok_graph), ptr(plan.tok_off), None, n, plan.B, nhead, dh,
+         dh ** -0.5, ptr(out), ptr(lse), drop_p, ptr(ops.rng_state("cuda")) if drop_p else None, salt, impl)
+    return out, lse
+
+
+@pytest.mark.parametrize("nhead,dh", [(4, 32), (4, 64)])
+@pytest.mark.parametrize("lens", [[1, 2, 33, 70, 129, 5], [27] * 40, [753, 300, 8, 1001], [128, 128, 256]])
+def test_mha_tcgen05_forward(nhead, dh, lens):
+    """impl=2 (tcgen05/TMEM/TMA kernel only) against the fp64 reference and the CUDA-core kernel:
+    block-diagonal packing of short graphs, long graphs spanning many key tiles, tile-aligned lengths"""
+    torch.manual_seed(0)
+    plan, off = _packed_plan(lens, extra=5)
+    n = off[-1] + 5
+    d = nhead * dh
+    qkv = torch.randn(n, 3 * d, device="cuda").bfloat16()
+    out, lse = _mha_raw(qkv, plan, nhead, 2)
+    ref = _ref_attention(qkv.double(), off, nhead)
+    assert rel_l2(out[:off[-1]], ref[:off[-1]]) < 1e-2
+    assert (out[off[-1]:] == 0).all()
+    out1, lse1 = _mha_raw(qkv, plan, nhead, 1)
+    assert rel_l2(out[:off[-1]], out1[:off[-1]].double()) < 1e-2
+    lse, lse1 = lse.view(nhead, n)[:, :off[-1]], lse1.view(nhead, n)[:, :off[-1]]
+    assert (lse - lse1).abs().max() < 2e-2
+
+
+def test_mha_tcgen05_dropout_mask_matches_cuda_core_kernel():
+    """both kernels derive the keep mask from the same counter-based hash of (head, query row, key row)"""
+    torch.manual_seed(0)
+    nhead, dh = 4, 32
+    plan, off = _packed_plan([50, 90, 200], extra=0)
+    qkv = torch.randn(off[-1], 3 * nhead * dh, device="cuda").bfloat16()
+    ops.manual_seed(3)
+    ops.begin_step("cuda")
+    o2, _ = _mha_raw(qkv, plan, nhead, 2, 0.3, 11)
+    o1, _ = _mha_raw(qkv, plan, nhead, 1, 0.3, 11)
+    assert rel_l2(o2, o1.double()) < 1.5e-2
+    o3, _ = _mha_raw(qkv, plan, nhead, 2, 0.3, 12)
+    assert rel_l2(o3, o1.double()) > 0.2

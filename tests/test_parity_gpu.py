@@ -141,11 +141,12 @@ def test_dropout_training_step_is_finite_and_seeded():
         model.zero_grad()
         loss = lossf(model(batch), batch)
         loss.backward()
-        return float(loss), model.gnn2transformer.weight.grad.clone()
+        return float(loss.detach()), model.gnn2transformer.weight.grad.clone()
 
     l1, g1 = step(7)
     l2, g2 = step(7)
     l3, g3 = step(8)
-    assert l1 == l2 and torch.equal(g1, g2)
-    assert l1 != l3
+    # same seed -> same masks (the only run-to-run noise left is fp32 atomic summation order)
+    assert abs(l1 - l2) < 1e-5 and rel_l2(g1, g2) < 1e-4
+    assert abs(l1 - l3) > 1e-4 and rel_l2(g3, g1) > 1e-2
     assert all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)
