@@ -267,6 +267,282 @@ static cudaError_t launch_fwd(const CUtensorMap& map, const AttnParams& p, cudaS
     return cudaGetLastError();
 }
 
+
+// ------------------------------------------------------------------------------------------ backward
+// delta[h, row] = sum_c dO[row, h*dh + c] * O[row, h*dh + c]   (one warp per (row, head))
+__global__ void __launch_bounds__(256)
+k_mha_delta(const bf16* __restrict__ out, const bf16* __restrict__ dout, int64_t n_rows, int nhead, int dh,
+            float* __restrict__ delta) {
+    const int lane = threadIdx.x & 31;
+    const int64_t item = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (item >= n_rows * nhead) return;
+    const int64_t row = item / nhead;
+    const int h = (int)(item - row * nhead);
+    const int64_t off = row * (int64_t)(nhead * dh) + h * dh;
+    float s = 0.f;
+    for (int c = lane * 2; c < dh; c += 64) {
+        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(out + off + c));
+        const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dout + off + c));
+        s = fmaf(a.x, b.x, fmaf(a.y, b.y, s));
+    }
+    s = warp_sum(s);
+    if (lane == 0) delta[(int64_t)h * n_rows + row] = s;
+}
+
+struct AttnBwdParams {
+    const int32_t* tok_graph;
+    const int32_t* tok_off;
+    const float* lse;
+    const float* delta;
+    void* dqkv;
+    const uint64_t* rng;
+    uint64_t salt;
+    int64_t n_rows;
+    int B, nhead, d;
+    float scale, scale_log2, drop_p;
+};
+
+// FlashAttention-2 style recompute backward.  S = Q K^T and dP = dO V^T are formed with query rows on the TMEM
+// lanes (thread = query row) in both modes:
+//   DKV = false : the CTA owns a 128-row QUERY tile (Q, dO resident), streams the key tiles (K, V) and
+//                 accumulates dQ += dS K                                     (A = dS K-major from smem, B = K MN-major)
+//   DKV = true  : the CTA owns a 128-row KEY tile (K, V resident), streams the query tiles (Q, dO) and
+//                 accumulates dV += P^T dO, dK += dS^T Q                     (A = P|dS MN-major from smem, B MN-major)
+// with P = exp2(S*scale*log2e - lse*log2e), dS = P o (dP*keep - delta).
+template <int DH, bool DKV>
+__global__ void __launch_bounds__(ATT_THREADS)
+k_mha_tc_bwd(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant__ CUtensorMap tma_do, const AttnBwdParams p) {
+    constexpr int PITCH = DH * 2;
+    constexpr int TILE = 128 * PITCH;
+    constexpr int STG = 2;
+    constexpr uint32_t TMEM_COLS = 512;           // S [0,128) | dP [128,256) | acc0 [256,256+DH) | acc1 [320,320+DH)
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t own_full, st_full[STG], st_empty[STG], sdp_full, pds_full, acc_done;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ int st_lo_s, nst_s;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t0 = blockIdx.x * 128, h = blockIdx.y;      // first row of the owned tile (query rows or key rows)
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t own_x = base, own_y = own_x + TILE;    // dQ: Q, dO   | dKV: K, V
+    const uint32_t st_s = own_y + TILE;                   // ring: stage s -> X at st_s + 2*s*TILE, Y right after
+    const uint32_t ds_s = st_s + 2 * STG * TILE;          // dS  [128 q x 128 keys] bf16, two swizzled 64-key blocks
+    const uint32_t pp_s = ds_s + 32768;                   // P   (DKV only)
+
+    if (threadIdx.x == 0) {
+        mbar_init(&own_full, 1);
+        for (int s = 0; s < STG; ++s) mbar_init(&st_full[s], 1), mbar_init(&st_empty[s], 1);
+        mbar_init(&sdp_full, 1);
+        mbar_init(&pds_full, 128);
+        mbar_init(&acc_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_async_smem();
+        // rows of the OTHER kind that interact with the owned tile: the rows of the graphs it touches (symmetric)
+        const int n_tok = p.tok_off[p.B];
+        int lo = 0, n = 0;
+        if (t0 < n_tok) {
+            const int g0 = p.tok_graph[t0];
+            const int g1 = p.tok_graph[min(t0 + 127, n_tok - 1)];
+            lo = p.tok_off[g0];
+            n = (p.tok_off[g1 + 1] - lo + 127) / 128;
+        }
+        st_lo_s = lo;
+        nst_s = n;
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    const int st_lo = st_lo_s, nst = nst_s;
+    const int colQ = h * DH, colK = p.d + h * DH, colV = 2 * p.d + h * DH;
+
+    if (warp == 0) {
+        if (lane == 0 && nst > 0) {  // ===== TMA producer =====
+            mbar_expect_tx(&own_full, 2 * TILE);
+            if (!DKV) {
+                tma_load_2d(own_x, &tma_qkv, &own_full, colQ, t0);
+                tma_load_2d(own_y, &tma_do, &own_full, colQ, t0);
+            } else {
+                tma_load_2d(own_x, &tma_qkv, &own_full, colK, t0);
+                tma_load_2d(own_y, &tma_qkv, &own_full, colV, t0);
+            }
+            for (int t = 0; t < nst; ++t) {
+                const int s = t % STG;
+                mbar_wait(&st_empty[s], ((uint32_t)(t / STG) & 1u) ^ 1u);
+                mbar_expect_tx(&st_full[s], 2 * TILE);
+                const uint32_t x = st_s + 2 * s * TILE, y = x + TILE;
+                const int r0 = st_lo + t * 128;
+                if (!DKV) {
+                    tma_load_2d(x, &tma_qkv, &st_full[s], colK, r0);
+                    tma_load_2d(y, &tma_qkv, &st_full[s], colV, r0);
+                } else {
+                    tma_load_2d(x, &tma_qkv, &st_full[s], colQ, r0);
+                    tma_load_2d(y, &tma_do, &st_full[s], colQ, r0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && nst > 0) {  // ===== MMA issuer =====
+            const uint32_t id_s = idesc_f16(false, false, 128, 128);
+            const uint32_t id_acc = idesc_f16(DKV, true, 128, DH);
+            mbar_wait(&own_full, 0);
+            for (int t = 0; t < nst; ++t) {
+                const int s = t % STG;
+                const uint32_t x = st_s + 2 * s * TILE, y = x + TILE;
+                const uint32_t q_a = DKV ? x : own_x, k_a = DKV ? own_x : x, do_a = DKV ? y : own_y, v_a = DKV ? own_y : y;
+                mbar_wait(&st_full[s], (uint32_t)(t / STG) & 1u);
+                if (t > 0) mbar_wait(&acc_done, (uint32_t)(t - 1) & 1u);   // S/dP columns are free again
+                tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < DH / 16; ++k)
+                    umma_f16(tmem, desc_k(q_a + k * 32, PITCH), desc_k(k_a + k * 32, PITCH), id_s, k > 0);
+#pragma unroll
+                for (int k = 0; k < DH / 16; ++k)
+                    umma_f16(tmem + 128, desc_k(do_a + k * 32, PITCH), desc_k(v_a + k * 32, PITCH), id_s, k > 0);
+                umma_commit(&sdp_full);
+                mbar_wait(&pds_full, (uint32_t)t & 1u);
+                tc_fence_after();
+                if (!DKV) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)   // dQ += dS K : k = key
+                        umma_f16(tmem + 256, desc_k(ds_s + (k >> 2) * 16384 + (k & 3) * 32, 128),
+                                 desc_mn(k_a + k * 16 * PITCH, PITCH), id_acc, (t > 0 || k > 0));
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)   // dK += dS^T Q : m = key, k = query row
+                        umma_f16(tmem + 256, desc_mnmajor(ds_s + k * 2048, 16384), desc_mn(q_a + k * 16 * PITCH, PITCH), id_acc,
+                                 (t > 0 || k > 0));
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)   // dV += P^T dO
+                        umma_f16(tmem + 320, desc_mnmajor(pp_s + k * 2048, 16384), desc_mn(do_a + k * 16 * PITCH, PITCH), id_acc,
+                                 (t > 0 || k > 0));
+                }
+                umma_commit(&st_empty[s]);
+                umma_commit(&acc_done);
+            }
+        }
+    } else {  // ===== math warps: thread = query row of the current (S, dP) tile =====
+        const int qd = warp & 3;
+        const int r = qd * 32 + lane;
+        const uint32_t t_lane = tmem + ((uint32_t)(qd * 32) << 16);
+        const Drop dr = make_drop(p.rng, p.salt, p.drop_p);
+        for (int t = 0; t < nst; ++t) {
+            const int64_t qrow = DKV ? (int64_t)st_lo + t * 128 + r : (int64_t)t0 + r;
+            const int kv0 = DKV ? t0 : st_lo + t * 128;
+            int lo = 0, hi = 0;
+            float lse2 = 0.f, dl = 0.f;
+            if (qrow < p.n_rows) {
+                const int g = p.tok_graph[qrow];
+                if (g >= 0) {
+                    lo = p.tok_off[g], hi = p.tok_off[g + 1];
+                    lse2 = p.lse[(int64_t)h * p.n_rows + qrow] * LOG2E;
+                    dl = p.delta[(int64_t)h * p.n_rows + qrow];
+                }
+            }
+            if (t > 0) mbar_wait(&acc_done, (uint32_t)(t - 1) & 1u);   // previous P / dS tiles have been consumed
+            mbar_wait(&sdp_full, (uint32_t)t & 1u);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < 128; c += 16) {
+                uint32_t rs[16], rp[16];
+                tmem_ld16(t_lane + c, rs);
+                tmem_ld16(t_lane + 128 + c, rp);
+                float pv[16], dsv[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int key = kv0 + c + i;
+                    const bool valid = key >= lo && key < hi;
+                    float pr = valid ? exp2f(fmaf(__uint_as_float(rs[i]), p.scale_log2, -lse2)) : 0.f;
+                    float dp = __uint_as_float(rp[i]);
+                    if (dr.on && valid) {
+                        const float mk = drop1(dr, att_drop_idx_tc(h, qrow, key, p.n_rows));
+                        dp *= mk;
+                        dsv[i] = pr * (dp - dl);
+                        pr *= mk;
+                    } else {
+                        dsv[i] = valid ? pr * (dp - dl) : 0.f;
+                    }
+                    pv[i] = pr;
+                }
+#pragma unroll
+                for (int i = 0; i < 16; i += 8) {
+                    const uint32_t off = p_chunk_off(r, c + i);
+                    __nv_bfloat162 h0 = __floats2bfloat162_rn(dsv[i], dsv[i + 1]), h1 = __floats2bfloat162_rn(dsv[i + 2], dsv[i + 3]);
+                    __nv_bfloat162 h2 = __floats2bfloat162_rn(dsv[i + 4], dsv[i + 5]), h3 = __floats2bfloat162_rn(dsv[i + 6], dsv[i + 7]);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ds_s + off), "r"(*reinterpret_cast<uint32_t*>(&h0)),
+                                 "r"(*reinterpret_cast<uint32_t*>(&h1)), "r"(*reinterpret_cast<uint32_t*>(&h2)),
+                                 "r"(*reinterpret_cast<uint32_t*>(&h3)) : "memory");
+                    if (DKV) {
+                        h0 = __floats2bfloat162_rn(pv[i], pv[i + 1]), h1 = __floats2bfloat162_rn(pv[i + 2], pv[i + 3]);
+                        h2 = __floats2bfloat162_rn(pv[i + 4], pv[i + 5]), h3 = __floats2bfloat162_rn(pv[i + 6], pv[i + 7]);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pp_s + off), "r"(*reinterpret_cast<uint32_t*>(&h0)),
+                                     "r"(*reinterpret_cast<uint32_t*>(&h1)), "r"(*reinterpret_cast<uint32_t*>(&h2)),
+                                     "r"(*reinterpret_cast<uint32_t*>(&h3)) : "memory");
+                    }
+                }
+            }
+            fence_async_smem();
+            tc_fence_before();
+            mbar_arrive(&pds_full);
+        }
+        // epilogue: the accumulators' TMEM lanes are the owned tile's rows
+        const int64_t row = (int64_t)t0 + r;
+        if (nst > 0) {
+            mbar_wait(&acc_done, (uint32_t)(nst - 1) & 1u);
+            tc_fence_after();
+        }
+        bf16* gp = (bf16*)p.dqkv + row * (int64_t)(3 * p.d);
+#pragma unroll
+        for (int a = 0; a < (DKV ? 2 : 1); ++a) {
+            const int col = !DKV ? colQ : (a == 0 ? colK : colV);
+            const float mul = (DKV && a == 1) ? 1.f : p.scale;
+#pragma unroll
+            for (int c = 0; c < DH; c += 16) {
+                uint32_t rr[16];
+                if (nst > 0) tmem_ld16(t_lane + 256 + a * 64 + c, rr);
+                if (row < p.n_rows) {
+#pragma unroll
+                    for (int i = 0; i < 16; i += 8) {
+                        float v[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) v[e] = nst > 0 ? __uint_as_float(rr[i + e]) * mul : 0.f;
+                        uint4 pk;
+                        __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+                        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
+                        pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                        pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                        *reinterpret_cast<uint4*>(gp + col + c + i) = pk;
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+template <int DH, bool DKV>
+static cudaError_t launch_bwd(const CUtensorMap& mq, const CUtensorMap& md, const AttnBwdParams& p, cudaStream_t st) {
+    constexpr int TILE = 128 * DH * 2;
+    const size_t smem = (size_t)(2 + 2 * 2) * TILE + 32768 * (DKV ? 2 : 1) + 1024;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_mha_tc_bwd<DH, DKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr = true;
+    }
+    dim3 grid((unsigned)((p.n_rows + 127) / 128), (unsigned)p.nhead);
+    k_mha_tc_bwd<DH, DKV><<<grid, ATT_THREADS, smem, st>>>(mq, md, p);
+    return cudaGetLastError();
+}
+
 }  // namespace tc
 
 int mha_tc_fwd_launch(int dt, const void* qkv, const int32_t* tok_graph, const int32_t* tok_off, const int32_t* key_start,
@@ -292,10 +568,36 @@ int mha_tc_fwd_launch(int dt, const void* qkv, const int32_t* tok_graph, const i
     return 0;
 }
 
-int mha_tc_bwd_launch(int, const void*, const void*, const void*, const float*, const int32_t*, const int32_t*,
-                      const int32_t*, int64_t, int64_t, int32_t, int32_t, float, void*, float*, float, const uint64_t*,
-                      uint64_t, cudaStream_t) {
-    set_error("tcgen05 attention backward not built");
-    return -2;
+int mha_tc_bwd_launch(int dt, const void* qkv, const void* out, const void* dout, const float* lse, const int32_t* tok_graph,
+                      const int32_t* tok_off, const int32_t* key_start, int64_t n_rows, int64_t B, int32_t nhead, int32_t dh,
+                      float scale, void* dqkv, float* delta, float drop_p, const uint64_t* rng, uint64_t salt, cudaStream_t st) {
+    using namespace tc;
+    if (dt != GT_BF16) { set_error("tcgen05 attention takes bf16 activations"); return -2; }
+    if (dh != 32 && dh != 64) { set_error("tcgen05 attention is built for head dims 32 and 64"); return -2; }
+    if (key_start) { set_error("dense left-padded layout (key_start) runs on the CUDA-core kernel"); return -2; }
+    const int d = nhead * dh;
+    if (((uintptr_t)qkv & 15) || ((uintptr_t)dout & 15) || ((uintptr_t)dqkv & 15) || n_rows >= (1ll << 31)) { set_error("alignment"); return -2; }
+    CUtensorMap mq, md;
+    if (!make_map(&mq, qkv, (uint64_t)3 * d, (uint64_t)n_rows, (uint64_t)3 * d, (uint32_t)dh, 128, dh * 2) ||
+        !make_map(&md, dout, (uint64_t)d, (uint64_t)n_rows, (uint64_t)d, (uint32_t)dh, 128, dh * 2)) {
+        set_error("cuTensorMapEncodeTiled failed or unavailable");
+        return -2;
+    }
+    const int64_t items = n_rows * nhead;
+    k_mha_delta<<<(unsigned)((items + 7) / 8), 256, 0, st>>>((const bf16*)out, (const bf16*)dout, n_rows, nhead, dh, delta);
+    AttnBwdParams p;
+    p.tok_graph = tok_graph; p.tok_off = tok_off; p.lse = lse; p.delta = delta; p.dqkv = dqkv; p.rng = rng; p.salt = salt;
+    p.n_rows = n_rows; p.B = (int)B; p.nhead = nhead; p.d = d;
+    p.scale = scale; p.scale_log2 = scale * LOG2E; p.drop_p = drop_p;
+    cudaError_t e;
+    if (dh == 64) {
+        e = launch_bwd<64, false>(mq, md, p, st);
+        if (e == cudaSuccess) e = launch_bwd<64, true>(mq, md, p, st);
+    } else {
+        e = launch_bwd<32, false>(mq, md, p, st);
+        if (e == cudaSuccess) e = launch_bwd<32, true>(mq, md, p, st);
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "gt_mha_bwd(tcgen05)");
+    return 0;
 }
 }  // namespace gt

@@ -265,3 +265,47 @@ def test_mha_tcgen05_dropout_mask_matches_cuda_core_kernel():
     assert rel_l2(o2, o1.double()) < 1.5e-2
     o3, _ = _mha_raw(qkv, plan, nhead, 2, 0.3, 12)
     assert rel_l2(o3, o1.double()) > 0.2
+
+
+def _mha_bwd_raw(qkv, out, dout, lse, plan, nhead, impl, drop_p=0.0, salt=0):
+    n, d3 = qkv.shape
+    d = d3 // 3
+    dh = d // nhead
+    dqkv = torch.full_like(qkv, float("nan"))
+    delta = torch.empty(nhead * n, dtype=torch.float32, device="cuda")
+    call("gt_mha_bwd", dt_of(qkv), ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(plan.tok_graph), ptr(plan.tok_off), None,
+         n, plan.B, nhead, dh, dh ** -0.5, ptr(dqkv), ptr(delta), drop_p,
+         ptr(ops.rng_state("cuda")) if drop_p else None, salt, impl)
+    return dqkv
+
+
+@pytest.mark.parametrize("nhead,dh", [(4, 32), (4, 64)])
+@pytest.mark.parametrize("lens", [[1, 2, 33, 70, 129, 5], [27] * 40, [753, 300, 8, 1001], [128, 128, 256]])
+@pytest.mark.parametrize("drop_p", [0.0, 0.3])
+def test_mha_tcgen05_backward(nhead, dh, lens, drop_p):
+    """impl=2 backward (dQ kernel + dK/dV kernel on tcgen05) against fp64 autograd (p = 0) and against the
+    CUDA-core backward under the same dropout mask (p > 0)"""
+    torch.manual_seed(0)
+    plan, off = _packed_plan(lens, extra=5)
+    n = off[-1] + 5
+    d = nhead * dh
+    qkv = torch.randn(n, 3 * d, device="cuda").bfloat16()
+    dout = torch.randn(n, d, device="cuda").bfloat16()
+    dout[off[-1]:] = 0
+    ops.manual_seed(5)
+    ops.begin_step("cuda")
+    out, lse = _mha_raw(qkv, plan, nhead, 2, drop_p, 21)
+    dq2 = _mha_bwd_raw(qkv, out, dout, lse, plan, nhead, 2, drop_p, 21)
+    assert torch.isfinite(dq2.float()).all()
+    assert (dq2[off[-1]:] == 0).all()
+    dq1 = _mha_bwd_raw(qkv, out, dout, lse, plan, nhead, 1, drop_p, 21)
+    for blk in range(3):
+        a, b = dq2[:off[-1], blk * d:(blk + 1) * d], dq1[:off[-1], blk * d:(blk + 1) * d]
+        assert rel_l2(a, b.double()) < 2e-2, blk
+    if drop_p == 0.0:
+        q64 = qkv.double().requires_grad_(True)
+        ref = _ref_attention(q64, off, nhead)
+        (ref * dout.double()).sum().backward()
+        for blk in range(3):
+            a, b = dq2[:off[-1], blk * d:(blk + 1) * d], q64.grad[:off[-1], blk * d:(blk + 1) * d]
+            assert rel_l2(a, b) < 2e-2, blk
