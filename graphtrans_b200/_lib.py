@@ -33,7 +33,7 @@ SIGNATURES = {
     "gt_embed_sum_fwd": [I, P, L, I32, I32, I32, P, P, P, P, P],
     "gt_embed_sum_bwd": [I, P, L, I32, I32, I32, P, P, P, P, P],
     "gt_aggregate_fwd": [I, I, P, P, L, I32, I32, P, P, P, P, I, P, I32, P, P, P, P, P, P],
-    "gt_aggregate_bwd": [I, I, P, P, P, L, I32, I32, P, P, P, P, I, P, I32, P, P, P, P, P, P, P, P, P, P],
+    "gt_aggregate_bwd": [I, I, P, P, P, L, I32, I32, P, P, P, P, I, P, I32, P, P, P, P, I32, P, P, P, P, P, P],
     "gt_segment_sum": [I, P, P, L, I32, P, P],
     "gt_add_graph_vec": [I, P, P, P, L, I32, P, P],
     "gt_colstats": [I, P, L, I32, P, P],

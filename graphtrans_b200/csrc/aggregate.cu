@@ -11,6 +11,7 @@ namespace gt {
 
 constexpr int AGG_WARPS = 8;
 constexpr int MAX_KDIM = 4;
+constexpr int AGG_TAB_ROWS = 64;   // ogb BondEncoder: 5*6*2 = 60 combined edge types
 
 struct EdgeEnc {
     const float* attr;   // [E, kdim] fp32 (LINEAR)
@@ -19,6 +20,7 @@ struct EdgeEnc {
     const int32_t* etype;  // [E]           (TABLE)
     const float* table;  // [ntypes, ld]    (TABLE)
     int kdim;
+    int ntypes;          // rows of `table` (adjoint only: <= AGG_TAB_ROWS rows are reduced in shared memory)
 };
 
 template <int EK>
@@ -116,6 +118,10 @@ k_agg_bwd(const T* __restrict__ x, const T* __restrict__ dout, T* __restrict__ d
     __shared__ float sh_self[128];
     __shared__ float sh_b[128];
     __shared__ float sh_w[MAX_KDIM][128];
+    // table-edge gradients: a handful of rows shared by every edge would serialise global atomics, so they are
+    // reduced per block in shared memory (lanes own distinct channels: no intra-warp conflicts) and flushed once
+    __shared__ float sh_tab[EK == GT_EDGE_TABLE ? AGG_TAB_ROWS * 128 : 1];
+    const bool tab_smem = EK == GT_EDGE_TABLE && en.ntypes <= AGG_TAB_ROWS;
     const int lane = threadIdx.x & 31;
     const int warp = blockIdx.x * AGG_WARPS + (threadIdx.x >> 5);
     const int nwarps = gridDim.x * AGG_WARPS;
@@ -131,6 +137,8 @@ k_agg_bwd(const T* __restrict__ x, const T* __restrict__ dout, T* __restrict__ d
 #pragma unroll
             for (int k = 0; k < MAX_KDIM; ++k) sh_w[k][threadIdx.x] = 0.f;
         }
+        if (tab_smem)
+            for (int i = threadIdx.x; i < en.ntypes * 128; i += blockDim.x) sh_tab[i] = 0.f;
         __syncthreads();
         if (active) {
             EdgeRegs<EK> er;
@@ -179,7 +187,8 @@ k_agg_bwd(const T* __restrict__ x, const T* __restrict__ dout, T* __restrict__ d
                             for (int k = 0; k < MAX_KDIM; ++k) a_w[k][q] = fmaf(a[k], gm[q], a_w[k][q]);
                         }
                     } else if (EK == GT_EDGE_TABLE) {
-                        float* row = d_table + (int64_t)en.etype[eid] * ld + c0;
+                        const int ty = en.etype[eid];
+                        float* row = tab_smem ? sh_tab + ty * 128 + lane * 4 : d_table + (int64_t)ty * ld + c0;
 #pragma unroll
                         for (int q = 0; q < 4; ++q)
                             if (gm[q] != 0.f) atomicAdd(row + q, gm[q]);
@@ -216,6 +225,13 @@ k_agg_bwd(const T* __restrict__ x, const T* __restrict__ dout, T* __restrict__ d
             }
         }
         __syncthreads();
+        if (tab_smem) {
+            for (int i = threadIdx.x; i < en.ntypes * 128; i += blockDim.x) {
+                const int c = ch * 128 + (i & 127);
+                const float v = sh_tab[i];
+                if (c < d && v != 0.f) atomicAdd(d_table + (int64_t)(i >> 7) * ld + c, v);
+            }
+        }
         if (threadIdx.x < 128) {
             const int c = ch * 128 + threadIdx.x;
             if (c < d) {
@@ -280,7 +296,7 @@ extern "C" int gt_aggregate_fwd(int dt, int conv, const void* x, void* out, int6
                                 const float* edge_w, const float* edge_b, const int32_t* etype,
                                 const float* table, const float* self_param, void* stream) {
     if (int r = check_common("gt_aggregate_fwd", conv, N, d, ld, edge_kind, kdim)) return r;
-    EdgeEnc en{edge_attr, edge_w, edge_b, etype, table, kdim};
+    EdgeEnc en{edge_attr, edge_w, edge_b, etype, table, kdim, 0};
     cudaStream_t st = (cudaStream_t)stream;
     GT_DISPATCH_DT(dt, {
         if (conv == GT_CONV_GCN)
@@ -296,11 +312,12 @@ extern "C" int gt_aggregate_bwd(int dt, int conv, const void* x, const void* dou
                                 int32_t ld, const int32_t* rowptr_dst, const int32_t* rowptr_src,
                                 const int32_t* dst_by_src, const int32_t* eid_by_src, int edge_kind,
                                 const float* edge_attr, int32_t kdim, const float* edge_w, const float* edge_b,
-                                const int32_t* etype, const float* table, const float* self_param,
+                                const int32_t* etype, const float* table, int32_t ntypes, const float* self_param,
                                 float* d_edge_w, float* d_edge_b, float* d_table, float* d_self, void* stream) {
     (void)rowptr_dst;
     if (int r = check_common("gt_aggregate_bwd", conv, N, d, ld, edge_kind, kdim)) return r;
-    EdgeEnc en{edge_attr, edge_w, edge_b, etype, table, kdim};
+    GT_CHECK_ARG(edge_kind != GT_EDGE_TABLE || ntypes > 0, "gt_aggregate_bwd: ntypes must be the row count of the edge table");
+    EdgeEnc en{edge_attr, edge_w, edge_b, etype, table, kdim, ntypes};
     cudaStream_t st = (cudaStream_t)stream;
     GT_DISPATCH_DT(dt, {
         if (conv == GT_CONV_GCN)

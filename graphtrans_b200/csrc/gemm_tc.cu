@@ -284,10 +284,13 @@ int gemm_tc_launch(int dt, const void* A, int a_mn, int64_t lda, const void* B, 
     p.kb_per_split = (p.kb_total + splits - 1) / splits;
     grid.z = (unsigned)((p.kb_total + p.kb_per_split - 1) / p.kb_per_split);
     p.BN = BN;
-    p.stages = p.kb_per_split < MAX_STAGES ? p.kb_per_split : MAX_STAGES;
     const size_t stage_bytes = A_TILE_BYTES + (size_t)BN * BK * 2;
-    if (p.stages == MAX_STAGES && 2 * (MAX_STAGES * stage_bytes + 1024) > 220 * 1024 && 2 * (3 * stage_bytes + 1024) <= 220 * 1024)
-        p.stages = 3;  // let two CTAs share an SM so one's epilogue overlaps the other's main loop
+    // ring depth: enough to cover TMA latency, but small enough that two CTAs share an SM (<= ~112 KB each) so one
+    // CTA's prologue / epilogue overlaps the other's main loop; these GEMMs have only 1-10 k-blocks per CTA
+    int fit = (int)((112 * 1024 - 1024) / stage_bytes);
+    if (fit < 2) fit = 2;
+    if (fit > MAX_STAGES) fit = MAX_STAGES;
+    p.stages = p.kb_per_split < fit ? p.kb_per_split : fit;
     const size_t smem = p.stages * stage_bytes + 1024;
     p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
               ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);

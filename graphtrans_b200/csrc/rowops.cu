@@ -58,28 +58,49 @@ __global__ void k_add_graph_vec(const T* __restrict__ x, const float* __restrict
 // ------------------------------------------------------------------ column statistics (BN)
 // grid-stride over row blocks; thread owns one 4-channel vector column group; fp32 partials per
 // thread over <= ROWS_PER_BLOCK rows, then one fp64 atomic per (block, channel).
-constexpr int STAT_ROWS = 64;
-template <typename T, bool SQ>
-__global__ void k_colstats(const T* __restrict__ x, int64_t M, int ld, double* __restrict__ stats) {
-    const int64_t r0 = (int64_t)blockIdx.y * STAT_ROWS;
-    const int64_t r1 = min(r0 + STAT_ROWS, M);
-    const int c0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (c0 >= ld) return;
-    float s[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int64_t r = r0; r < r1; ++r) {
-        float v[4];
-        ld4(x + r * ld + c0, v);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            s[q] += v[q];
-            if (SQ) s2[q] = fmaf(v[q], v[q], s2[q]);
-        }
-    }
+// block = 256 threads = 8 row lanes x 32 column lanes; a column lane owns one 4-channel vector, so a warp reads
+// 256/512 contiguous bytes of a row and a block covers 128 channels of a slab of rows.  fp32 partials per thread,
+// shared-memory tree over the 8 row lanes, then ONE fp64 atomic per (block, channel) - deterministic enough for
+// statistics and ~300 blocks keep every SM busy.
+constexpr int STAT_TY = 8;
+__device__ __forceinline__ void stat_flush(float (&s)[4], float (&s2)[4], int tx, int ty, int c0, int ld,
+                                           double* __restrict__ out) {
+    __shared__ float sh[2][STAT_TY][128 + 4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        atomicAdd(stats + c0 + q, (double)s[q]);
-        if (SQ) atomicAdd(stats + ld + c0 + q, (double)s2[q]);
+        sh[0][ty][tx * 4 + q] = s[q];
+        sh[1][ty][tx * 4 + q] = s2[q];
     }
+    __syncthreads();
+    const int t = ty * 32 + tx;   // 256 threads -> 2 x 128 (which, channel)
+    const int which = t >> 7, ch = t & 127;
+    float a = 0.f;
+#pragma unroll
+    for (int k = 0; k < STAT_TY; ++k) a += sh[which][k][ch];
+    const int c = (c0 - tx * 4) + ch;
+    if (c < ld) atomicAdd(out + which * ld + c, (double)a);
+}
+
+template <typename T, bool SQ>
+__global__ void __launch_bounds__(256)
+k_colstats(const T* __restrict__ x, int64_t M, int ld, int64_t rows_per_block, double* __restrict__ stats) {
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c0 = blockIdx.x * 128 + tx * 4;
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+    const int64_t r1 = min(r0 + rows_per_block, M);
+    float s[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+    if (c0 < ld) {
+        for (int64_t r = r0 + ty; r < r1; r += STAT_TY) {
+            float v[4];
+            ld4(x + r * ld + c0, v);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                s[q] += v[q];
+                if (SQ) s2[q] = fmaf(v[q], v[q], s2[q]);
+            }
+        }
+    }
+    stat_flush(s, s2, tx, ty, c0, ld, stats);
 }
 
 __global__ void k_bn_finalize(const double* __restrict__ stats, int64_t M, int d, int ld,
@@ -158,40 +179,39 @@ __global__ void k_bn_apply(const T* __restrict__ x, int64_t M, int ld, const flo
 }
 
 template <typename T>
-__global__ void k_bn_bwd_reduce(const T* __restrict__ x, const T* __restrict__ dy, int64_t M, int ld,
-                                const float* __restrict__ ssmr, int relu, double* __restrict__ red, float drop_p,
-                                const uint64_t* __restrict__ rng, uint64_t salt) {
+__global__ void __launch_bounds__(256)
+k_bn_bwd_reduce(const T* __restrict__ x, const T* __restrict__ dy, int64_t M, int ld, int64_t rows_per_block,
+                const float* __restrict__ ssmr, int relu, double* __restrict__ red, float drop_p,
+                const uint64_t* __restrict__ rng, uint64_t salt) {
     const Drop dr = make_drop(rng, salt, drop_p);
     const int vpr = ld / 4;
-    const int64_t r0 = (int64_t)blockIdx.y * STAT_ROWS;
-    const int64_t r1 = min(r0 + STAT_ROWS, M);
-    const int c0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (c0 >= ld) return;
-    float sc[4], sh[4], mu[4], rs[4];
-    ld4(ssmr + c0, sc);
-    ld4(ssmr + ld + c0, sh);
-    ld4(ssmr + 2 * ld + c0, mu);
-    ld4(ssmr + 3 * ld + c0, rs);
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c0 = blockIdx.x * 128 + tx * 4;
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+    const int64_t r1 = min(r0 + rows_per_block, M);
     float s[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int64_t r = r0; r < r1; ++r) {
-        float v[4], g[4];
-        ld4(x + r * ld + c0, v);
-        ld4(dy + r * ld + c0, g);
-        float ds[4];
-        drop4(dr, (uint64_t)(r * vpr + c0 / 4), ds);
+    if (c0 < ld) {
+        float sc[4], sh[4], mu[4], rs[4];
+        ld4(ssmr + c0, sc);
+        ld4(ssmr + ld + c0, sh);
+        ld4(ssmr + 2 * ld + c0, mu);
+        ld4(ssmr + 3 * ld + c0, rs);
+        for (int64_t r = r0 + ty; r < r1; r += STAT_TY) {
+            float v[4], g[4];
+            ld4(x + r * ld + c0, v);
+            ld4(dy + r * ld + c0, g);
+            float ds[4];
+            drop4(dr, (uint64_t)(r * vpr + c0 / 4), ds);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            g[q] *= ds[q];
-            if (relu && fmaf(v[q], sc[q], sh[q]) <= 0.f) g[q] = 0.f;
-            s[q] += g[q];
-            s2[q] = fmaf(g[q], (v[q] - mu[q]) * rs[q], s2[q]);
+            for (int q = 0; q < 4; ++q) {
+                g[q] *= ds[q];
+                if (relu && fmaf(v[q], sc[q], sh[q]) <= 0.f) g[q] = 0.f;
+                s[q] += g[q];
+                s2[q] = fmaf(g[q], (v[q] - mu[q]) * rs[q], s2[q]);
+            }
         }
     }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        atomicAdd(red + c0 + q, (double)s[q]);
-        atomicAdd(red + ld + c0 + q, (double)s2[q]);
-    }
+    stat_flush(s, s2, tx, ty, c0, ld, red);
 }
 
 template <typename T>
@@ -233,8 +253,8 @@ __global__ void k_bn_bwd_apply(const T* __restrict__ x, const T* __restrict__ dy
 #pragma unroll
             for (int q = 0; q < 4; ++q)
                 if (c0 + q < d) {
-                    dgamma[c0 + q] = (float)red[ld + c0 + q];
-                    dbeta[c0 + q] = (float)red[c0 + q];
+                    dgamma[c0 + q] += (float)red[ld + c0 + q];   // accumulate semantics (single writer per channel)
+                    dbeta[c0 + q] += (float)red[c0 + q];
                 }
         }
     }
@@ -490,21 +510,55 @@ __global__ void k_embed_fwd(EmbCols cols, int64_t N, int d, int ld, T* __restric
     }
 }
 
+// Gradient of the embedding sums.  Tables with few rows (atom / bond / node-type / depth vocabularies) would
+// serialise global atomics on a handful of addresses, so a block owns (EMB_NB nodes x 32 channels), accumulates
+// those tables in shared memory (a warp handles one node: 32 lanes = 32 distinct channels, no intra-warp
+// conflicts) and flushes once; large tables (Code2 attribute vocabulary, 10030 rows) take global atomics directly.
+constexpr int EMB_NB = 512;
+constexpr int EMB_SMALL_ROWS = 128;      // per-table threshold
+constexpr int EMB_SMEM_ROWS = 512;       // total rows staged per block (64 KB)
 template <typename T>
-__global__ void k_embed_bwd(EmbCols cols, int64_t N, int d, int ld, const T* __restrict__ dout) {
-    const int vpr = d / 4;
-    const int64_t total = N * vpr;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = i / vpr;
-        const int c0 = (int)(i - r * vpr) * 4;
-        float g[4];
-        ld4(dout + r * ld + c0, g);
+__global__ void __launch_bounds__(256)
+k_embed_bwd(EmbCols cols, int64_t N, int d, int ld, const T* __restrict__ dout) {
+    extern __shared__ float sh_tab[];    // [rows_small][32]
+    __shared__ int row_base[EMB_MAXCOL]; // first smem row of column c, -1 = global atomics
+    __shared__ int rows_small_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        int acc = 0;
         for (int c = 0; c < cols.ncol; ++c) {
-            int64_t id = cols.idx[c][r * cols.stride[c]];
-            if (id > cols.clamp[c]) id = cols.clamp[c];
-            float* row = cols.dtable[c] + id * d + c0;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) atomicAdd(row + q, g[q]);
+            const int rows = (int)cols.clamp[c] + 1;
+            if (rows <= EMB_SMALL_ROWS && acc + rows <= EMB_SMEM_ROWS) row_base[c] = acc, acc += rows;
+            else row_base[c] = -1;
+        }
+        rows_small_s = acc;
+    }
+    __syncthreads();
+    const int rows_small = rows_small_s;
+    for (int i = threadIdx.x; i < rows_small * 32; i += blockDim.x) sh_tab[i] = 0.f;
+    __syncthreads();
+    const int ch = blockIdx.y * 32 + lane;
+    const int64_t n0 = (int64_t)blockIdx.x * EMB_NB, n1 = min(n0 + EMB_NB, N);
+    if (ch < d) {
+        for (int64_t r = n0 + warp; r < n1; r += 8) {
+            const float g = to_f(dout[r * ld + ch]);
+            for (int c = 0; c < cols.ncol; ++c) {
+                int64_t id = cols.idx[c][r * cols.stride[c]];
+                if (id > cols.clamp[c]) id = cols.clamp[c];
+                if (row_base[c] >= 0) atomicAdd(&sh_tab[(row_base[c] + (int)id) * 32 + lane], g);
+                else atomicAdd(cols.dtable[c] + id * d + ch, g);
+            }
+        }
+    }
+    __syncthreads();
+    if (ch < d) {
+        for (int c = 0; c < cols.ncol; ++c) {
+            if (row_base[c] < 0) continue;
+            const int rows = (int)cols.clamp[c] + 1;
+            for (int rr = warp; rr < rows; rr += 8) {
+                const float v = sh_tab[(row_base[c] + rr) * 32 + lane];
+                if (v != 0.f) atomicAdd(cols.dtable[c] + (int64_t)rr * d + ch, v);
+            }
         }
     }
 }
@@ -577,6 +631,18 @@ using namespace gt;
 
 #define ST ((cudaStream_t)stream)
 
+// column-reduction grid: x = 128-channel groups, y = row slabs sized for ~2 blocks per SM
+static dim3 stat_grid(int64_t M, int ld, int64_t* rows_per_block) {
+    const int gx = (ld + 127) / 128;
+    int64_t gy = (2 * kNumSMs + gx - 1) / gx;
+    const int64_t max_gy = (M + 4 * STAT_TY - 1) / (4 * STAT_TY);   // at least 32 rows per block
+    if (gy > max_gy) gy = max_gy;
+    if (gy < 1) gy = 1;
+    *rows_per_block = (M + gy - 1) / gy;
+    gy = (M + *rows_per_block - 1) / *rows_per_block;
+    return dim3((unsigned)gx, (unsigned)gy);
+}
+
 extern "C" int gt_segment_sum(int dt, const void* x, const int32_t* node_graph, int64_t N, int32_t ld, float* out,
                               void* stream) {
     GT_CHECK_ARG(N > 0 && ld > 0 && ld % 4 == 0, "gt_segment_sum: bad shape");
@@ -595,8 +661,9 @@ extern "C" int gt_add_graph_vec(int dt, const void* x, const float* v, const int
 
 extern "C" int gt_colstats(int dt, const void* x, int64_t M, int32_t ld, double* stats, void* stream) {
     GT_CHECK_ARG(M > 0 && ld > 0 && ld % 4 == 0, "gt_colstats: bad shape");
-    dim3 grid((ld / 4 + 63) / 64, (unsigned)((M + STAT_ROWS - 1) / STAT_ROWS));
-    GT_DISPATCH_DT(dt, (k_colstats<T, true><<<grid, 64, 0, ST>>>((const T*)x, M, ld, stats)));
+    int64_t rpb;
+    const dim3 grid = stat_grid(M, ld, &rpb);
+    GT_DISPATCH_DT(dt, (k_colstats<T, true><<<grid, 256, 0, ST>>>((const T*)x, M, ld, rpb, stats)));
     GT_LAUNCH_CHECK("gt_colstats");
     return 0;
 }
@@ -626,8 +693,9 @@ extern "C" int gt_bn_bwd_reduce(int dt, const void* x, const void* dy, int64_t M
                                 const float* ssmr, int relu, double* red, float drop_p,
                                 const uint64_t* rng_state, uint64_t salt, void* stream) {
     GT_CHECK_ARG(M > 0 && ld >= d && ld % 4 == 0, "gt_bn_bwd_reduce: bad shape");
-    dim3 grid((ld / 4 + 63) / 64, (unsigned)((M + STAT_ROWS - 1) / STAT_ROWS));
-    GT_DISPATCH_DT(dt, (k_bn_bwd_reduce<T><<<grid, 64, 0, ST>>>((const T*)x, (const T*)dy, M, ld, ssmr, relu, red, drop_p, rng_state, salt)));
+    int64_t rpb;
+    const dim3 grid = stat_grid(M, ld, &rpb);
+    GT_DISPATCH_DT(dt, (k_bn_bwd_reduce<T><<<grid, 256, 0, ST>>>((const T*)x, (const T*)dy, M, ld, rpb, ssmr, relu, red, drop_p, rng_state, salt)));
     GT_LAUNCH_CHECK("gt_bn_bwd_reduce");
     return 0;
 }
@@ -730,7 +798,13 @@ extern "C" int gt_embed_sum_bwd(int dt, const void* dout, int64_t N, int32_t d, 
     GT_CHECK_ARG(N > 0 && d % 4 == 0 && ld >= d && ld % 4 == 0, "gt_embed_sum_bwd: bad shape");
     EmbCols c;
     if (int r = fill_cols(c, ncol, idx_host, stride_host, clamp_host, nullptr, dtable_host)) return r;
-    GT_DISPATCH_DT(dt, (k_embed_bwd<T><<<blocks_for(N * (d / 4), 256), 256, 0, ST>>>(c, N, d, ld, (const T*)dout)));
+    dim3 grid((unsigned)((N + EMB_NB - 1) / EMB_NB), (unsigned)((d + 31) / 32));
+    const size_t smem = (size_t)EMB_SMEM_ROWS * 32 * sizeof(float);
+    GT_DISPATCH_DT(dt, {
+        static bool attr = false;
+        if (!attr) { cudaFuncSetAttribute(k_embed_bwd<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+        k_embed_bwd<T><<<grid, 256, smem, ST>>>(c, N, d, ld, (const T*)dout);
+    });
     GT_LAUNCH_CHECK("gt_embed_sum_bwd");
     return 0;
 }
@@ -779,8 +853,6 @@ extern "C" int gt_rng_advance(uint64_t* rng_state, void* stream) {
 
 extern "C" int gt_colsum(int dt, const void* X, int64_t M, int64_t N, int64_t ld, float* out, void* stream) {
     GT_CHECK_ARG(M > 0 && N > 0 && ld >= N, "gt_colsum: bad shape");
-    cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * N, ST);
-    if (e != cudaSuccess) return cuda_fail(e, "gt_colsum memset");
     int slabs = (int)((M + 255) / 256);
     if (slabs > 64) slabs = 64;
     dim3 grid((unsigned)((N + 31) / 32), slabs), block(32, 8);

@@ -32,6 +32,10 @@ class GradBuckets:
         self._bucket_of = {}
         for i, p in enumerate(self.params):
             p.grad = self.flat[off:off + p.numel()].view_as(p)
+            # fused gradient delivery (ops._grad_target): the backward kernels accumulate straight into the arena
+            p._gt_main_grad = p.grad
+            p._gt_uses = getattr(p, "_gt_uses", 1)
+            p._gt_grad_ready = self._make_ready(i)
             off += p.numel()
             cur += p.numel()
             idxs.append(i)
@@ -54,7 +58,18 @@ class GradBuckets:
         self.reset()
 
     # ------------------------------------------------------------------
+    def _make_ready(self, i):
+        def ready():
+            self._uses_left[i] -= 1
+            if self._uses_left[i] == 0 and self.overlap:
+                b = self._bucket_of[i]
+                self._pending[b] -= 1
+                if self._pending[b] == 0:
+                    self._launch(b)
+        return ready
+
     def reset(self):
+        self._uses_left = [getattr(p, "_gt_uses", 1) for p in self.params]
         self._pending = [len(ids) for _, _, ids in self.buckets]
         self._launched = [False] * len(self.buckets)
         self._work = []
@@ -103,7 +118,7 @@ class GradBuckets:
             w.wait()
         if self.comm_stream is not None:
             torch.cuda.current_stream().wait_stream(self.comm_stream)
-        self._work = []
+        self.reset()       # re-arm: a CUDA-graph replay of the step does not re-run zero_grad() on the host
 
 
 def shard_range(n_graphs: int, rank: int, world: int):

@@ -39,6 +39,8 @@ class _GraphTransBase(BaseModel):
         gnn_emb_dim = 2 * args.gnn_emb_dim if args.gnn_JK == "cat" else args.gnn_emb_dim
         self._gnn_dim = args.gnn_emb_dim
         self.gnn2transformer = nn.Linear(gnn_emb_dim, args.d_model)
+        # JK=cat applies the weight once per part (two gradient contributions per step, ops._grad_done)
+        self.gnn2transformer.weight._gt_uses = 2 if args.gnn_JK == "cat" else 1
         self.transformer_encoder = TransformerNodeEncoder(args)
         self.num_encoder_layers = args.num_encoder_layers
         if self.num_encoder_layers < 1:

@@ -122,8 +122,7 @@ class GNN_node_Virtualnode(_GNNBase):
         edge_index, edge_attr = batched_data.edge_index, batched_data.edge_attr
         d, ld = self.emb_dim, ops.ldp(self.emb_dim)
         h0 = self._input(batched_data, perturb)
-        # per-graph virtual-node state, fp32 [B, ld] (the VN MLP always runs in fp32: its BatchNorm
-        # is over only B rows and amplifies low-precision noise)
+        # per-graph virtual-node state, fp32 [B, ld]
         vn = ops.pad_cols(self.virtualnode_embedding.weight, ld).expand(plan.B, ld)
         h_list = [ops.add_graph_vec(h0, vn, plan)]              # h + vn[batch]  (gnn_module.py:199)
         drop = self.drop_ratio if self.training else 0.0
@@ -133,8 +132,10 @@ class GNN_node_Virtualnode(_GNNBase):
             if layer < self.num_layer - 1:                       # gnn_module.py:217-229
                 mlp = self.mlp_virtualnode_list[layer]
                 t = ops.segment_sum(hv, plan, init=vn)            # global_add_pool(h_list[layer]) + vn
+                t = ops.cast_to(t, ops.act_dtype())               # the MLP runs in the activation dtype
                 t = ops.batch_norm(ops.linear(t, mlp[0].weight, mlp[0].bias), mlp[1], relu=True)
                 t = ops.batch_norm(ops.linear(t, mlp[3].weight, mlp[3].bias), mlp[4], relu=True, drop_p=drop)
+                t = ops.cast_to(t, torch.float32)                 # the virtual-node state itself stays fp32
                 vn_next = vn + t if self.residual else t
             h = self.convs[layer](hv, edge_index, edge_attr, plan=plan)
             # BN -> ReLU (not last) -> dropout -> (+residual) -> (+ next layer's vn[batch]) in one kernel

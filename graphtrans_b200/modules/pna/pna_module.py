@@ -33,6 +33,8 @@ class PNAConv(nn.Module):
         self.pre_nns = nn.ModuleList([nn.Sequential(nn.Linear(2 * self.F_in, self.F_in)) for _ in range(towers)])
         self.post_nns = nn.ModuleList([nn.Sequential(nn.Linear(13 * self.F_in, self.F_out)) for _ in range(towers)])
         self.lin = nn.Linear(out_channels, out_channels)
+        for m in self.pre_nns:          # W_i and W_j halves are applied separately: two gradient contributions
+            m[0].weight._gt_uses = 2
 
     def forward(self, x, edge_index=None, plan=None):
         """x: physical [N, ldp(d)] activation matrix; returns the same layout."""

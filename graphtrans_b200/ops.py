@@ -60,11 +60,71 @@ def begin_step(device):
     per-step call-site salts.  Called by the model at the top of every training forward."""
     _salt[0] = 0
     call("gt_rng_advance", ptr(rng_state(device)))
+    a = _arena(device)
+    if a["off"] or not a["armed"]:
+        a["buf"].zero_()
+    a["off"], a["armed"] = 0, True
 
 
 def next_salt() -> int:
     _salt[0] += 1
     return _salt[0]
+
+
+# ----------------------------------------------------------------------------- fused gradient delivery
+# A parameter may carry `_gt_main_grad` (an fp32 tensor of its shape, normally a view into the flat arena of
+# graphtrans_b200.ddp.GradBuckets, zeroed once per step).  The backward kernels then ACCUMULATE the parameter
+# gradient straight into it and return None to autograd: no temporary, no zero fill, no autograd add kernel.
+# `_gt_grad_ready()` (if present) tells the bucket manager that one expected contribution has landed.
+def _main_grad(param):
+    return getattr(param, "_gt_main_grad", None) if param is not None else None
+
+
+def _grad_target(param, shape=None):
+    """-> (tensor to accumulate into, value to return to autograd)"""
+    mg = _main_grad(param)
+    if mg is not None:
+        return mg, None
+    # returned to autograd, which may keep it as .grad: must be ordinary memory (never the step arena)
+    g = torch.zeros(tuple(param.shape if shape is None else shape), dtype=torch.float32, device=param.device)
+    return g, g
+
+
+def _grad_done(param):
+    cb = getattr(param, "_gt_grad_ready", None)
+    if cb is not None:
+        cb()
+
+
+# small zero-initialised scratch that never leaves an op (BatchNorm statistics / backward reductions): carved from
+# one arena that begin_step() clears with a single memset instead of one fill kernel per buffer
+_ZERO_ARENA_BYTES = 8 << 20
+_zero_arena = {}
+
+
+def _arena(device):
+    idx = torch.device(device).index or 0
+    a = _zero_arena.get(idx)
+    if a is None:
+        a = {"buf": torch.zeros(_ZERO_ARENA_BYTES, dtype=torch.uint8, device=device), "off": 0, "armed": False}
+        _zero_arena[idx] = a
+    return a
+
+
+def zeros_small(numel, dtype, device):
+    esz = 8 if dtype == torch.float64 else 4
+    nbytes = (numel * esz + 255) // 256 * 256
+    a = _arena(device)
+    if not a["armed"] or a["off"] + nbytes > _ZERO_ARENA_BYTES:
+        return torch.zeros(numel, dtype=dtype, device=device)
+    off = a["off"]
+    a["off"] = off + nbytes
+    return a["buf"][off:off + numel * esz].view(dtype)
+
+
+def zeros_f32(shape, device):
+    """fresh zeroed fp32 tensor that may be handed to autograd (ordinary allocation)"""
+    return torch.zeros(shape, dtype=torch.float32, device=device)
 
 
 class _DropoutFn(torch.autograd.Function):
@@ -211,7 +271,7 @@ class _EmbedSumFn(torch.autograd.Function):
         a_tab = (ctypes.c_void_p * n)(*[t.data_ptr() for t in tables])
         call("gt_embed_sum_fwd", dt_of(out), ptr(out), N, d, ld, n, a_idx, a_str, a_clp, a_tab)
         ctx.meta = meta
-        ctx.shapes = [t.shape for t in tables]
+        ctx.tables = tables
         return out
 
     @staticmethod
@@ -219,13 +279,15 @@ class _EmbedSumFn(torch.autograd.Function):
         idx, strides, clamps, N, d, ld, dtype = ctx.meta
         g = g.contiguous()
         n = len(idx)
-        grads = [torch.zeros(s, dtype=torch.float32, device=g.device) for s in ctx.shapes]
+        targets = [_grad_target(t) for t in ctx.tables]
         a_idx = (ctypes.c_void_p * n)(*[t.data_ptr() for t in idx])
         a_str = (ctypes.c_int64 * n)(*strides)
         a_clp = (ctypes.c_int64 * n)(*clamps)
-        a_tab = (ctypes.c_void_p * n)(*[t.data_ptr() for t in grads])
+        a_tab = (ctypes.c_void_p * n)(*[t[0].data_ptr() for t in targets])
         call("gt_embed_sum_bwd", dt_of(g), ptr(g), N, d, ld, n, a_idx, a_str, a_clp, a_tab)
-        return (None, *grads)
+        for t in ctx.tables:
+            _grad_done(t)
+        return (None, *[t[1] for t in targets])
 
 
 def embed_sum(index_cols, tables, clamps=None):
@@ -238,7 +300,7 @@ def embed_sum(index_cols, tables, clamps=None):
     strides = [c.stride(0) if c.dim() else 1 for c in index_cols]
     clamps = clamps or [t.shape[0] - 1 for t in tables]
     meta = (list(index_cols), strides, list(clamps), N, d, ldp(d), act_dtype())
-    return _EmbedSumFn.apply(meta, *[t.contiguous() for t in tables])
+    return _EmbedSumFn.apply(meta, *tables)
 
 
 # ----------------------------------------------------------------------------- dense layers
@@ -281,6 +343,7 @@ class _LinearFn(torch.autograd.Function):
         _gemm_raw(dt_of(x), x.data_ptr(), 0, ld_in, wptr, 0, ldw, y.data_ptr(), ld_out, M, N, K, ld_out, bias, resid,
                   ld_out, flags)
         ctx.save_for_backward(x, w, y if relu else None)
+        ctx.params = (weight, bias)
         ctx.meta = (M, N, K, Kw, off, ld_in, ldw, ld_out, relu, bias is not None, resid is not None)
         return y
 
@@ -307,14 +370,17 @@ class _LinearFn(torch.autograd.Function):
             # dX[m,k] = sum_n dY[m,n] W[n,k]: B operand = W read "MN-major" (k contiguous)
             _gemm_raw(dt_of(x), gy.data_ptr(), 0, ld_out, wptr, 1, ldw, gx.data_ptr(), ld_in, M, K, N, ld_in, None,
                       None, 0, 0)
+        weight, bias = ctx.params
         if ctx.needs_input_grad[1]:
-            gw = torch.zeros(N, Kw, dtype=torch.float32, device=x.device)
-            # dW[n,k] = sum_m dY[m,n] X[m,k]: both operands MN-major, split-K over the rows
-            _gemm_raw(dt_of(x), gy.data_ptr(), 1, ld_out, x.data_ptr(), 1, ld_in, gw.data_ptr() + off * 4, Kw, N, K, M,
+            tgt, gw = _grad_target(weight)
+            # dW[n,k] = sum_m dY[m,n] X[m,k]: both operands MN-major, split-K over the rows, accumulated in place
+            _gemm_raw(dt_of(x), gy.data_ptr(), 1, ld_out, x.data_ptr(), 1, ld_in, tgt.data_ptr() + off * 4, Kw, N, K, M,
                       K, None, None, 0, EPI_ACCUM | EPI_OUT_F32)
+            _grad_done(weight)
         if has_bias and ctx.needs_input_grad[2]:
-            gb = torch.empty(N, dtype=torch.float32, device=x.device)
-            call("gt_colsum", dt_of(gy), ptr(gy), M, N, ld_out, ptr(gb))
+            tgt, gb = _grad_target(bias)
+            call("gt_colsum", dt_of(gy), ptr(gy), M, N, ld_out, ptr(tgt))
+            _grad_done(bias)
         return gx, gw, gb, None, None, g_res, None, None
 
 
@@ -332,6 +398,7 @@ class _AggregateFn(torch.autograd.Function):
         N, ld = x.shape
         out = torch.empty_like(x)
         kdim = edge_w.shape[1] if edge_kind == EDGE_LINEAR else 0
+        edge_w_param = edge_w
         if edge_kind == EDGE_LINEAR:
             edge_attr = edge_attr.contiguous()
             edge_w = edge_w.contiguous()
@@ -344,6 +411,7 @@ class _AggregateFn(torch.autograd.Function):
              ptr(plan.src_by_dst), ptr(plan.eid_by_dst), ptr(plan.rowptr_src), edge_kind, ptr(edge_attr), kdim,
              ptr(edge_w), ptr(edge_b), ptr(etype), ptr(table), ptr(sp))
         ctx.save_for_backward(x, edge_attr, edge_w, edge_b, etype, table, sp)
+        ctx.params = (edge_w_param, edge_b, self_param)
         ctx.meta = (plan, conv, d, edge_kind, kdim, self_param.shape)
         return out
 
@@ -354,15 +422,19 @@ class _AggregateFn(torch.autograd.Function):
         g = g.contiguous()
         N, ld = x.shape
         dx = torch.empty_like(x)
-        f32 = dict(dtype=torch.float32, device=x.device)
-        dw = torch.zeros(d, kdim, **f32) if edge_kind == EDGE_LINEAR else None
-        db = torch.zeros(d, **f32) if edge_kind == EDGE_LINEAR else None
-        dtab = torch.zeros_like(table) if edge_kind == EDGE_TABLE else None
-        dself = torch.zeros(sp.numel(), **f32)
+        pw, pb, pself = ctx.params
+        tw = tb = (None, None)
+        if edge_kind == EDGE_LINEAR:
+            tw, tb = _grad_target(pw), _grad_target(pb)
+        dtab = zeros_f32(tuple(table.shape), x.device) if edge_kind == EDGE_TABLE else None
+        tself = _grad_target(pself)
         call("gt_aggregate_bwd", dt_of(x), conv, ptr(x), ptr(g), ptr(dx), N, d, ld, ptr(plan.rowptr_dst),
              ptr(plan.rowptr_src), ptr(plan.dst_by_src), ptr(plan.eid_by_src), edge_kind, ptr(edge_attr), kdim,
-             ptr(edge_w), ptr(edge_b), ptr(etype), ptr(table), ptr(sp), ptr(dw), ptr(db), ptr(dtab), ptr(dself))
-        return dx, None, None, None, None, None, dw, db, None, dtab, dself.view(sp_shape)
+             ptr(edge_w), ptr(edge_b), ptr(etype), ptr(table), table.shape[0] if edge_kind == EDGE_TABLE else 0, ptr(sp),
+             ptr(tw[0]), ptr(tb[0]), ptr(dtab), ptr(tself[0]))
+        for prm in (pw, pb, pself):
+            _grad_done(prm)
+        return dx, None, None, None, None, None, tw[1], tb[1], None, dtab, tself[1]
 
 
 def aggregate(x, plan, conv, d, self_param, edge_kind=EDGE_NONE, edge_attr=None, edge_w=None, edge_b=None,
@@ -378,7 +450,7 @@ class _SegmentSumFn(torch.autograd.Function):
     def forward(ctx, x, plan, init=None):
         x = x.contiguous()
         N, ld = x.shape
-        out = torch.zeros(plan.B, ld, dtype=torch.float32, device=x.device) if init is None else init.clone()
+        out = zeros_f32((plan.B, ld), x.device) if init is None else init.clone()
         call("gt_segment_sum", dt_of(x), ptr(x), ptr(plan.node_graph), N, ld, ptr(out))
         ctx.meta = (plan, x.dtype, N, ld)
         return out
@@ -416,7 +488,7 @@ class _AddGraphVecFn(torch.autograd.Function):
         g = g.contiguous()
         dv = None
         if ctx.needs_input_grad[1]:
-            dv = torch.zeros(plan.B, ld, dtype=torch.float32, device=g.device)
+            dv = zeros_f32((plan.B, ld), g.device)
             call("gt_segment_sum", dt_of(g), ptr(g), ptr(plan.node_graph), N, ld, ptr(dv))
         return g, dv, None
 
@@ -440,7 +512,7 @@ class _BatchNormFn(torch.autograd.Function):
         ssmr = torch.empty(4 * ld, dtype=torch.float32, device=dev)
         stats = None
         if training:
-            stats = torch.zeros(2 * ld, dtype=torch.float64, device=dev)
+            stats = zeros_small(2 * ld, torch.float64, dev)
             call("gt_colstats", dt_of(x), ptr(x), M, ld, ptr(stats))
         call("gt_bn_finalize", ptr(stats), M, d, ld, ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var),
              ptr(nbt), float(momentum), float(eps), int(training), ptr(ssmr))
@@ -453,6 +525,7 @@ class _BatchNormFn(torch.autograd.Function):
         call("gt_bn_apply_fwd", dt_of(x), ptr(x), M, d, ld, ptr(ssmr), int(relu), ptr(resid), ptr(gvec),
              ptr(plan.node_graph) if gvec is not None else None, ptr(y), float(drop_p), rng, salt)
         ctx.save_for_backward(x, ssmr, gamma)
+        ctx.params = (gamma, beta)
         ctx.meta = (M, d, ld, relu, training, plan, resid is not None, gvec is not None, float(drop_p), salt)
         return y
 
@@ -463,18 +536,20 @@ class _BatchNormFn(torch.autograd.Function):
         g = g.contiguous()
         dev = x.device
         rng = ptr(rng_state(dev)) if drop_p else None
-        red = torch.zeros(2 * ld, dtype=torch.float64, device=dev)
+        red = zeros_small(2 * ld, torch.float64, dev)
         call("gt_bn_bwd_reduce", dt_of(x), ptr(x), ptr(g), M, d, ld, ptr(ssmr), int(relu), ptr(red), drop_p, rng,
              salt)
         dx = torch.empty_like(x)
-        dgamma = torch.empty(d, dtype=torch.float32, device=dev)
-        dbeta = torch.empty(d, dtype=torch.float32, device=dev)
+        pg, pb = ctx.params
+        (tg, dgamma), (tb, dbeta) = _grad_target(pg), _grad_target(pb)
         call("gt_bn_bwd_apply", dt_of(x), ptr(x), ptr(g), M, d, ld, ptr(ssmr), ptr(gamma), int(relu),
-             int(training), ptr(red), ptr(dx), ptr(dgamma), ptr(dbeta), drop_p, rng, salt)
+             int(training), ptr(red), ptr(dx), ptr(tg), ptr(tb), drop_p, rng, salt)
+        _grad_done(pg)
+        _grad_done(pb)
         dres = g if has_resid else None
         dgv = None
         if has_gvec and ctx.needs_input_grad[11]:
-            dgv = torch.zeros(plan.B, ld, dtype=torch.float32, device=dev)
+            dgv = zeros_f32((plan.B, ld), dev)
             call("gt_segment_sum", dt_of(g), ptr(g), ptr(plan.node_graph), M, ld, ptr(dgv))
         return dx, dgamma, dbeta, None, None, None, None, None, None, None, dres, dgv, None, None, None
 
@@ -508,6 +583,7 @@ class _LayerNormFn(torch.autograd.Function):
         call("gt_layernorm_fwd", dt_of(x), ptr(x), ptr(resid), ptr(in_rows), ptr(clsv), M, d, ptr(gamma), ptr(beta),
              float(eps), ptr(y), ptr(presum), ptr(mr))
         ctx.save_for_backward(presum if presum is not None else x, mr, gamma)
+        ctx.params = (gamma, beta, cls)
         ctx.meta = (M, d, in_rows, x.shape[0], resid is not None, cls.shape if cls is not None else None)
         return y
 
@@ -521,13 +597,15 @@ class _LayerNormFn(torch.autograd.Function):
             dx = torch.zeros(x_rows, d, dtype=g.dtype, device=dev)
         else:
             dx = torch.empty(M, d, dtype=g.dtype, device=dev)
-        dgamma = torch.zeros(d, dtype=torch.float32, device=dev)
-        dbeta = torch.zeros(d, dtype=torch.float32, device=dev)
-        dcls = torch.zeros(d, dtype=torch.float32, device=dev) if cls_shape is not None else None
+        pg, pb, pcls = ctx.params
+        (tg, dgamma), (tb, dbeta) = _grad_target(pg), _grad_target(pb)
+        tcls, dcls = _grad_target(pcls) if cls_shape is not None else (None, None)
         call("gt_layernorm_bwd", dt_of(g), ptr(g), ptr(presum), ptr(mr), ptr(rows), M, d, ptr(gamma), ptr(dx),
-             ptr(dgamma), ptr(dbeta), ptr(dcls))
-        return (dx, dx if has_resid else None, dgamma, dbeta, None, None,
-                dcls.view(cls_shape) if dcls is not None else None, None)
+             ptr(tg), ptr(tb), ptr(tcls))
+        for prm in (pg, pb, pcls):
+            if prm is not None:
+                _grad_done(prm)
+        return (dx, dx if has_resid else None, dgamma, dbeta, None, None, dcls, None)
 
 
 def layer_norm(x, ln: torch.nn.LayerNorm, resid=None, in_rows=None, cls=None, n_rows=None, drop_p=0.0):
@@ -548,6 +626,7 @@ class _GatherRowsFn(torch.autograd.Function):
         clsv = cls.contiguous().view(-1) if cls is not None else None
         call("gt_gather_rows", dt_of(src), ptr(src), ptr(rows), ptr(clsv), n_rows, ld, ptr(dst))
         ctx.meta = (rows, src.shape[0], ld, n_rows, cls.shape if cls is not None else None)
+        ctx.cls = cls
         return dst
 
     @staticmethod
@@ -555,9 +634,11 @@ class _GatherRowsFn(torch.autograd.Function):
         rows, src_rows, ld, n_rows, cls_shape = ctx.meta
         g = g.contiguous()
         dsrc = torch.zeros(src_rows, ld, dtype=g.dtype, device=g.device)
-        dcls = torch.zeros(ld, dtype=torch.float32, device=g.device) if cls_shape is not None else None
-        call("gt_scatter_rows", dt_of(g), ptr(g), ptr(rows), n_rows, ld, ptr(dsrc), ptr(dcls))
-        return dsrc, None, dcls.view(cls_shape) if dcls is not None else None, None
+        tcls, dcls = _grad_target(ctx.cls) if cls_shape is not None else (None, None)
+        call("gt_scatter_rows", dt_of(g), ptr(g), ptr(rows), n_rows, ld, ptr(dsrc), ptr(tcls))
+        if cls_shape is not None:
+            _grad_done(ctx.cls)
+        return dsrc, None, dcls, None
 
 
 def gather_rows(src, rows, cls=None, n_rows=None):
@@ -657,6 +738,7 @@ class _TowerLinearFn(torch.autograd.Function):
                       w.data_ptr() + w_col_off * es, 0, w.shape[1], y.data_ptr() + t * Fo * es, ld_out, M, Fo, K, Fo,
                       bs[t] if use_bias else None, None, 0, 0)
         ctx.save_for_backward(x, *wop)
+        ctx.params = (ws, bs)
         ctx.meta = (x_tower_stride, K, w_col_off, use_bias, n_towers, Fo, ld_out, [w.shape for w in ws])
         return y
 
@@ -669,19 +751,22 @@ class _TowerLinearFn(torch.autograd.Function):
         es = x.element_size()
         gx = torch.zeros_like(x)
         gws, gbs = [], []
+        pws, pbs = ctx.params
         for t in range(T):
             w = wop[t]
             gyp = gy.data_ptr() + t * Fo * es
             # dX_t[m,k] = sum_n dY_t[m,n] W_t[n, wo+k]
             _gemm_raw(dt_of(x), gyp, 0, ld_out, w.data_ptr() + wo * es, 1, w.shape[1],
                       gx.data_ptr() + t * xs * es, ldx, M, K, Fo, K, None, None, 0, 0)
-            gw = torch.zeros(wshapes[t], dtype=torch.float32, device=x.device)
+            tgt, gw = _grad_target(pws[t])
             _gemm_raw(dt_of(x), gyp, 1, ld_out, x.data_ptr() + t * xs * es, 1, ldx,
-                      gw.data_ptr() + wo * 4, gw.shape[1], Fo, K, M, K, None, None, 0, EPI_ACCUM | EPI_OUT_F32)
+                      tgt.data_ptr() + wo * 4, wshapes[t][1], Fo, K, M, K, None, None, 0, EPI_ACCUM | EPI_OUT_F32)
+            _grad_done(pws[t])
             gws.append(gw)
             if use_bias:
-                gb = torch.empty(Fo, dtype=torch.float32, device=x.device)
-                lib_call_colsum(gy, t * Fo, M, Fo, ld_out, gb)
+                tgt, gb = _grad_target(pbs[t])
+                lib_call_colsum(gy, t * Fo, M, Fo, ld_out, tgt)
+                _grad_done(pbs[t])
                 gbs.append(gb)
             else:
                 gbs.append(None)

@@ -109,7 +109,7 @@ int gt_aggregate_bwd(int dt, int conv, const void* x, const void* dout, void* dx
                      const int32_t* rowptr_dst, const int32_t* rowptr_src, const int32_t* dst_by_src,
                      const int32_t* eid_by_src,
                      int edge_kind, const float* edge_attr, int32_t kdim, const float* edge_w,
-                     const float* edge_b, const int32_t* etype, const float* table,
+                     const float* edge_b, const int32_t* etype, const float* table, int32_t ntypes,
                      const float* self_param,
                      float* d_edge_w, float* d_edge_b, float* d_table, float* d_self, void* stream);
 
@@ -141,7 +141,7 @@ int gt_bn_bwd_reduce(int dt, const void* x, const void* dy, int64_t M, int32_t d
                      const float* ssmr, int relu, double* red, float drop_p, const uint64_t* rng_state,
                      uint64_t salt, void* stream);
 /* backward pass 2: dx = gamma*rstd*(g - red0/M - xhat*red1/M) (train) or g*scale (eval);
- * dgamma = red1, dbeta = red0 (fp32 [d]) */
+ * dgamma += red1, dbeta += red0 (fp32 [d], accumulated so that gradients can be summed in place) */
 int gt_bn_bwd_apply(int dt, const void* x, const void* dy, int64_t M, int32_t d, int32_t ld,
                     const float* ssmr, const float* gamma, int relu, int training, const double* red,
                     void* dx, float* dgamma, float* dbeta, float drop_p, const uint64_t* rng_state,
@@ -160,7 +160,7 @@ int gt_gemm(int dt, const void* A, int a_mn, int64_t lda, const void* B, int b_m
             const float* bias, const void* resid, int64_t ldr, int flags, int impl, void* stream);
 /* dz = dy * (y > 0): backward of a ReLU that was fused into a GEMM epilogue; n % 4 == 0 */
 int gt_relu_bwd(int dt, const void* dy, const void* y, int64_t n, void* dz, void* stream);
-/* out[n] = sum_m X[m,n]  (bias gradients) ; out fp32 [N] overwritten */
+/* out[n] += sum_m X[m,n]  (bias gradients) ; out fp32 [N] is ACCUMULATED into (caller zeroes a fresh buffer) */
 int gt_colsum(int dt, const void* X, int64_t M, int64_t N, int64_t ld, float* out, void* stream);
 /* dst[r, 0:cols_out] = cast(src[r, 0:cols_in]) zero padded to cols_out; rows_out >= rows_in zero padded */
 int gt_cast_pad(int dt_in, const void* src, int64_t rows_in, int64_t cols_in, int64_t ld_in,

@@ -20,13 +20,19 @@ GRAD_TOL = 1e-3
 WORST_TOL = 5e-3
 
 
-def run_product(args, batch, init_sd, precision="fp32", train=True):
+def run_product(args, batch, init_sd, precision="fp32", train=True, buckets=False):
     ops.set_precision(precision)
     model = factory.build_model(args).cuda()
     model.load_state_dict(init_sd, strict=True)
     model.train(train)
     b = batch.clone().to("cuda")
-    model.zero_grad()
+    if buckets:   # fused gradient delivery into the flat DDP arena (graphtrans_b200.ddp.GradBuckets)
+        from graphtrans_b200.ddp import GradBuckets
+        gb = GradBuckets(model, n_buckets=3)
+        gb.flat.fill_(123.0)      # zero_grad() must clear it
+        gb.zero_grad()
+    else:
+        model.zero_grad()
     pred = model(b)
     loss = factory.loss_fn(args)(pred, b)
     loss.backward()
@@ -56,6 +62,18 @@ def test_golden_fwd_bwd_fp32(name):
         pe = model(fx["batch"].clone().to("cuda"))
     for a, b in zip(as_list(pe), as_list(fx["logits_eval"])):
         assert rel_l2(a, b) < LOGIT_TOL
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_golden_grads_delivered_into_flat_arena(name):
+    """same parity bar when the backward kernels accumulate parameter gradients straight into the
+    flat allreduce arena (no autograd accumulation kernels)"""
+    fx = load_golden(name)
+    model, pred, loss, grads, bufs = run_product(fx["args"], fx["batch"], fx["init_sd"], buckets=True)
+    glob, worst, key = grad_report(grads, fx["grads"])
+    assert glob < GRAD_TOL and worst < WORST_TOL, (glob, worst, key)
+    for k, p in model.named_parameters():
+        assert p.grad.data_ptr() == p._gt_main_grad.data_ptr(), k
 
 
 @pytest.mark.parametrize("name", ["gcn_virtual_cat_code2", "gin_virtual_cat_mol", "pna_code2"])
