@@ -44,6 +44,7 @@ SIGNATURES = {
     "gt_gemm": [I, P, I, L, P, I, L, P, L, L, L, L, L, P, P, L, I, I, P],
     "gt_relu_bwd": [I, P, P, L, P, P],
     "gt_colsum": [I, P, L, L, L, P, P],
+    "gt_cast_multi": [P, I32, L, P],
     "gt_cast_pad": [I, P, L, L, L, I, P, L, L, L, P],
     "gt_layernorm_fwd": [I, P, P, P, P, L, I32, P, P, F, P, P, P, P],
     "gt_layernorm_bwd": [I, P, P, P, P, L, I32, P, P, P, P, P, P],

@@ -17,9 +17,9 @@ int mha_tc_bwd_launch(int dt, const void* qkv, const void* out, const void* dout
                       int64_t B, int32_t nhead, int32_t dh, float scale, void* dqkv, float* delta, float drop_p,
                       const uint64_t* rng, uint64_t salt, cudaStream_t st);
 
-// dropout element index of probability P[h, query row, key row] (shared by every MHA kernel)
-__device__ __forceinline__ uint64_t att_drop_idx(int h, int64_t q, int64_t k, int64_t n_rows) {
-    return ((uint64_t)h * (uint64_t)n_rows + (uint64_t)q) * (uint64_t)n_rows + (uint64_t)k;
+// dropout row id of the probabilities P[h, query row, :] (shared by every MHA kernel, see common.cuh drop_elem)
+__device__ __forceinline__ uint64_t att_row_id(int h, int64_t q, int64_t n_rows) {
+    return (uint64_t)h * (uint64_t)n_rows + (uint64_t)q;
 }
 
 constexpr int ATT_WARPS = 4;
@@ -63,6 +63,7 @@ k_mha_fwd(const T* __restrict__ qkv, const int32_t* __restrict__ tok_graph, cons
     for (int c = lane; c < dh; c += 32) sq[wid][c] = to_f(qkv[t * ld3 + h * dh + c]) * scale;
     __syncwarp();
     float m = -INFINITY, l = 0.f, o0 = 0.f, o1 = 0.f;
+    const uint32_t rk = drop_row_key(dr, att_row_id(h, t, n_rows));
     for (int kb = ks; kb < ke; kb += 32) {
         const int j = kb + lane;
         const bool valid = j < ke;
@@ -73,7 +74,7 @@ k_mha_fwd(const T* __restrict__ qkv, const int32_t* __restrict__ tok_graph, cons
         l = l * corr + warp_sum(p);
         o0 *= corr;
         o1 *= corr;
-        const float pd = (valid && dr.on) ? p * drop1(dr, att_drop_idx(h, t, j, n_rows)) : p;
+        const float pd = (valid && dr.on) ? p * drop_elem(dr, rk, (uint32_t)j) : p;
         const int cnt = min(32, ke - kb);
         for (int jj = 0; jj < cnt; ++jj) {
             const float pj = __shfl_sync(0xffffffffu, pd, jj);
@@ -129,6 +130,7 @@ k_mha_bwd_dq(const T* __restrict__ qkv, const T* __restrict__ out, const T* __re
     __syncwarp();
     if (lane == 0) delta[(int64_t)h * n_rows + t] = dl;
     const float L = lse[(int64_t)h * n_rows + t];
+    const uint32_t rk = drop_row_key(dr, att_row_id(h, t, n_rows));
     float a0 = 0.f, a1 = 0.f;
     for (int kb = ks; kb < ke; kb += 32) {
         const int j = kb + lane;
@@ -137,7 +139,7 @@ k_mha_bwd_dq(const T* __restrict__ qkv, const T* __restrict__ out, const T* __re
             const float s = dot_row(sq[wid], qkv + (int64_t)j * ld3 + d + h * dh, dh);
             const float p = __expf(s - L);
             float dp = dot_row(sdo[wid], qkv + (int64_t)j * ld3 + 2 * d + h * dh, dh);
-            if (dr.on) dp *= drop1(dr, att_drop_idx(h, t, j, n_rows));
+            if (dr.on) dp *= drop_elem(dr, rk, (uint32_t)j);
             ds = p * (dp - dl);
         }
         const int cnt = min(32, ke - kb);
@@ -191,7 +193,7 @@ k_mha_bwd_dkv(const T* __restrict__ qkv, const T* __restrict__ dout, const float
         if (i < qe) {
             const float s = dot_row(sk[wid], qkv + (int64_t)i * ld3 + h * dh, dh);
             p = __expf(s - lse[(int64_t)h * n_rows + i]);
-            const float m = dr.on ? drop1(dr, att_drop_idx(h, i, j, n_rows)) : 1.f;
+            const float m = dr.on ? drop_elem(dr, drop_row_key(dr, att_row_id(h, i, n_rows)), (uint32_t)j) : 1.f;
             const float dp = dot_row(sv[wid], dout + (int64_t)i * d + h * dh, dh) * m;
             ds = p * (dp - delta[(int64_t)h * n_rows + i]);
             p *= m;  // dV uses the dropped probabilities

@@ -17,8 +17,8 @@
 
 namespace gt {
 
-__device__ __forceinline__ uint64_t att_drop_idx_tc(int h, int64_t q, int64_t k, int64_t n_rows) {
-    return ((uint64_t)h * (uint64_t)n_rows + (uint64_t)q) * (uint64_t)n_rows + (uint64_t)k;
+__device__ __forceinline__ uint64_t att_row_id_tc(int h, int64_t q, int64_t n_rows) {   // == attn_simt.cu att_row_id
+    return (uint64_t)h * (uint64_t)n_rows + (uint64_t)q;
 }
 
 namespace tc {
@@ -40,9 +40,6 @@ __device__ __forceinline__ uint64_t desc_mn(uint32_t saddr, uint32_t pitch) {
 __device__ __forceinline__ uint32_t idesc_f16(bool a_mn, bool b_mn, int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -163,6 +160,11 @@ k_mha_tc_fwd(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p) {
             if (g >= 0) lo = p.tok_off[g], hi = p.tok_off[g + 1];
         }
         const Drop dr = make_drop(p.rng, p.salt, p.drop_p);
+        const uint32_t rk = drop_row_key(dr, att_row_id_tc(h, row, p.n_rows));
+        // key range any row of this WARP can see: 16-key chunks outside it are skipped (graphs are short compared
+        // with the 128-key tile in the molecule workloads, so most chunks of a tile are fully masked)
+        const int wlo = __reduce_min_sync(0xffffffffu, hi > lo ? lo : 0x7fffffff);
+        const int whi = __reduce_max_sync(0xffffffffu, hi > lo ? hi : 0);
         float m = -INFINITY, l = 0.f;
         float o[DH];
 #pragma unroll
@@ -175,6 +177,7 @@ k_mha_tc_fwd(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p) {
             float mt = -INFINITY;
 #pragma unroll 1
             for (int c = 0; c < BKV; c += 16) {
+                if (kv0 + c + 16 <= wlo || kv0 + c >= whi) continue;   // warp-uniform
                 uint32_t rr[16];
                 tmem_ld16(t_lane + c, rr);
 #pragma unroll
@@ -190,6 +193,11 @@ k_mha_tc_fwd(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p) {
             float lt = 0.f;
 #pragma unroll 1
             for (int c = 0; c < BKV; c += 16) {
+                if (kv0 + c + 16 <= wlo || kv0 + c >= whi) {              // fully masked for this warp: P = 0
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(p_s + p_chunk_off(r, c)), "r"(0u) : "memory");
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(p_s + p_chunk_off(r, c + 8)), "r"(0u) : "memory");
+                    continue;
+                }
                 uint32_t rr[16];
                 tmem_ld16(t_lane + c, rr);
                 float pv[16];
@@ -199,7 +207,7 @@ k_mha_tc_fwd(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p) {
                     const bool valid = key >= lo && key < hi;
                     float e = valid ? exp2f(fmaf(__uint_as_float(rr[i]), p.scale_log2, -m_use)) : 0.f;
                     lt += e;
-                    if (dr.on && valid) e *= drop1(dr, att_drop_idx_tc(h, row, key, p.n_rows));
+                    if (dr.on && valid) e *= drop_elem(dr, rk, (uint32_t)key);
                     pv[i] = e;
                 }
 #pragma unroll
@@ -443,11 +451,23 @@ k_mha_tc_bwd(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant_
                     dl = p.delta[(int64_t)h * p.n_rows + qrow];
                 }
             }
+            const uint32_t rk = drop_row_key(dr, att_row_id_tc(h, qrow, p.n_rows));
+            const int wlo = __reduce_min_sync(0xffffffffu, hi > lo ? lo : 0x7fffffff);
+            const int whi = __reduce_max_sync(0xffffffffu, hi > lo ? hi : 0);
             if (t > 0) mbar_wait(&acc_done, (uint32_t)(t - 1) & 1u);   // previous P / dS tiles have been consumed
             mbar_wait(&sdp_full, (uint32_t)t & 1u);
             tc_fence_after();
 #pragma unroll 1
             for (int c = 0; c < 128; c += 16) {
+                if (kv0 + c + 16 <= wlo || kv0 + c >= whi) {   // fully masked for this warp (warp-uniform): dS = P = 0
+#pragma unroll
+                    for (int i = 0; i < 16; i += 8) {
+                        const uint32_t off = p_chunk_off(r, c + i);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(ds_s + off), "r"(0u) : "memory");
+                        if (DKV) asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(pp_s + off), "r"(0u) : "memory");
+                    }
+                    continue;
+                }
                 uint32_t rs[16], rp[16];
                 tmem_ld16(t_lane + c, rs);
                 tmem_ld16(t_lane + 128 + c, rp);
@@ -459,7 +479,7 @@ k_mha_tc_bwd(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant_
                     float pr = valid ? exp2f(fmaf(__uint_as_float(rs[i]), p.scale_log2, -lse2)) : 0.f;
                     float dp = __uint_as_float(rp[i]);
                     if (dr.on && valid) {
-                        const float mk = drop1(dr, att_drop_idx_tc(h, qrow, key, p.n_rows));
+                        const float mk = drop_elem(dr, rk, (uint32_t)key);
                         dp *= mk;
                         dsv[i] = pr * (dp - dl);
                         pr *= mk;

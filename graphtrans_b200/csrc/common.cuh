@@ -121,6 +121,17 @@ __device__ __forceinline__ void drop4(const Drop& d, uint64_t vec_idx, float (&s
 #pragma unroll
     for (int q = 0; q < 4; ++q) s[q] = ((uint32_t)(r >> (16 * q)) & 0xffffu) >= d.thresh16 ? d.inv_keep : 0.f;
 }
+// attention probabilities: element (row_id = head * n_rows + query row, col = key row).  The 64-bit part of the hash
+// is paid once per row, the per-element part is a 32-bit murmur3 finaliser (7 integer ops) - shared by the CUDA-core
+// and the tcgen05 attention kernels so that forward and backward of either kind see the same mask.
+__device__ __forceinline__ uint32_t drop_row_key(const Drop& d, uint64_t row_id) {
+    return d.on ? (uint32_t)(mix64(d.key + row_id * 0x9E3779B97F4A7C15ull) >> 32) : 0u;
+}
+__device__ __forceinline__ float drop_elem(const Drop& d, uint32_t row_key, uint32_t col) {
+    uint32_t x = row_key ^ (col * 0x9E3779B1u);
+    x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+    return (x >> 16) >= d.thresh16 ? d.inv_keep : 0.f;
+}
 __device__ __forceinline__ float drop1(const Drop& d, uint64_t idx) {
     if (!d.on) return 1.f;
     const uint64_t r = mix64(d.key + idx * 0x9E3779B97F4A7C15ull);

@@ -593,6 +593,32 @@ __global__ void k_dropout(const T* __restrict__ x, int64_t n4, T* __restrict__ y
 
 __global__ void k_rng_advance(uint64_t* rng) { rng[1] += 1; }
 
+// one launch casting MANY fp32 parameter matrices to zero-padded bf16 operand copies.  desc (device, int64[6] per
+// tensor): src, dst, rows, cols, ld_dst, first block; a block converts 2048 consecutive destination elements.
+constexpr int CASTM_PER_BLOCK = 2048;
+__global__ void __launch_bounds__(256)
+k_cast_multi(const int64_t* __restrict__ desc, int n) {
+    int lo = 0, hi = n;   // largest i with desc[i].first_block <= blockIdx.x
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (desc[mid * 6 + 5] <= (int64_t)blockIdx.x) lo = mid; else hi = mid;
+    }
+    const int64_t* dsc = desc + lo * 6;
+    const float* src = reinterpret_cast<const float*>(dsc[0]);
+    bf16* dst = reinterpret_cast<bf16*>(dsc[1]);
+    const int64_t rows = dsc[2], cols = dsc[3], ld = dsc[4];
+    const int64_t base = ((int64_t)blockIdx.x - dsc[5]) * CASTM_PER_BLOCK;
+    const int64_t total = rows * ld;
+#pragma unroll
+    for (int k = 0; k < CASTM_PER_BLOCK / 256; ++k) {
+        const int64_t i = base + k * 256 + threadIdx.x;
+        if (i < total) {
+            const int64_t r = i / ld, c = i - r * ld;
+            dst[i] = __float2bfloat16_rn(c < cols ? src[r * cols + c] : 0.f);
+        }
+    }
+}
+
 template <typename TI, typename TO>
 __global__ void k_cast_pad(const TI* __restrict__ src, int64_t rows_in, int64_t cols_in, int64_t ld_in,
                            TO* __restrict__ dst, int64_t rows_out, int64_t cols_out, int64_t ld_out) {
@@ -825,6 +851,13 @@ extern "C" int gt_cast_pad(int dt_in, const void* src, int64_t rows_in, int64_t 
     if (dt_in == GT_F32) cast_pad_out<float>(dt_out, (const float*)src, rows_in, cols_in, ld_in, dst, rows_out, cols_out, ld_out, ST);
     else cast_pad_out<bf16>(dt_out, (const bf16*)src, rows_in, cols_in, ld_in, dst, rows_out, cols_out, ld_out, ST);
     GT_LAUNCH_CHECK("gt_cast_pad");
+    return 0;
+}
+
+extern "C" int gt_cast_multi(const int64_t* desc_dev, int32_t n, int64_t total_blocks, void* stream) {
+    GT_CHECK_ARG(desc_dev && n > 0 && total_blocks > 0 && total_blocks < (1ll << 31), "gt_cast_multi: bad arguments");
+    k_cast_multi<<<(unsigned)total_blocks, 256, 0, ST>>>(desc_dev, n);
+    GT_LAUNCH_CHECK("gt_cast_multi");
     return 0;
 }
 

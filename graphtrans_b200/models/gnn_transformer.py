@@ -58,6 +58,7 @@ class _GraphTransBase(BaseModel):
         else:
             for _ in range(args.max_seq_len):
                 self.graph_pred_linear_list.append(torch.nn.Linear(args.d_model, self.num_tasks))
+        ops.w16.register(self)   # bf16 operand copies of every Linear / in_proj weight, refreshed once per step
 
     def _gnn2transformer(self, parts):
         """Linear over the logical concatenation of the JK parts without materialising the concat:

@@ -55,11 +55,66 @@ def manual_seed(seed: int, device="cuda"):
     rng_state(device).copy_(torch.tensor([seed & 0x7FFFFFFFFFFFFFFF, 0], dtype=torch.int64))
 
 
+# ----------------------------------------------------------------------------- bf16 operand copies of the weights
+class _W16Registry:
+    """All registered fp32 master weights get a zero-padded bf16 operand copy ([rows, ldp(cols)]) that ONE kernel
+    (gt_cast_multi) refreshes at the top of every forward, instead of one cast kernel per nn.Linear call."""
+
+    def __init__(self):
+        self.params, self.copies, self.desc, self.ptrs, self.blocks = [], {}, None, None, 0
+
+    def register(self, module: torch.nn.Module):
+        seen = {id(p) for p in self.params}
+        for m in module.modules():
+            cand = []
+            if isinstance(m, torch.nn.Linear):
+                cand.append(m.weight)
+            if isinstance(m, torch.nn.MultiheadAttention) and m.in_proj_weight is not None:
+                cand.append(m.in_proj_weight)
+            for w in cand:
+                if id(w) not in seen:
+                    seen.add(id(w))
+                    self.params.append(w)
+        self.desc = None
+
+    def _build(self, device):
+        recs, blk = [], 0
+        self.copies = {}
+        for w in self.params:
+            if not w.is_cuda or w.dtype != torch.float32 or not w.is_contiguous():
+                continue
+            rows, cols = w.shape
+            ld = ldp(cols)
+            c = torch.empty(rows, ld, dtype=torch.bfloat16, device=w.device)
+            self.copies[id(w)] = (c, ld)
+            recs.append([w.data_ptr(), c.data_ptr(), rows, cols, ld, blk])
+            blk += (rows * ld + 2047) // 2048
+        self.blocks = blk
+        self.ptrs = tuple(w.data_ptr() for w in self.params)
+        self.desc = torch.tensor(recs, dtype=torch.int64, device=device) if recs else None
+
+    def refresh(self, device):
+        if not self.params:
+            return
+        if self.desc is None or self.ptrs != tuple(w.data_ptr() for w in self.params):
+            self._build(device)
+        if self.desc is not None:
+            call("gt_cast_multi", ptr(self.desc), self.desc.shape[0], self.blocks)
+
+    def lookup(self, w):
+        return self.copies.get(id(w))
+
+
+w16 = _W16Registry()
+
+
 def begin_step(device):
     """advance the device-side dropout step counter (one launch; graph-capturable) and restart the
     per-step call-site salts.  Called by the model at the top of every training forward."""
     _salt[0] = 0
     call("gt_rng_advance", ptr(rng_state(device)))
+    if _PRECISION == "bf16":
+        w16.refresh(device)
     a = _arena(device)
     if a["off"] or not a["armed"]:
         a["buf"].zero_()
@@ -326,10 +381,15 @@ class _LinearFn(torch.autograd.Function):
         wf = weight.contiguous()
         if x.dtype == torch.float32:
             w, ldw, wptr = wf, Kw, wf.data_ptr() + off * 4
-        else:  # bf16 operand copy of the fp32 master weight block, K padded so rows stay 16-B aligned
-            w = torch.empty(N, ld_in, dtype=x.dtype, device=x.device)
-            call("gt_cast_pad", GT_F32, wf.data_ptr() + off * 4, N, K, Kw, dt_of(w), ptr(w), N, ld_in, ld_in)
-            ldw, wptr = ld_in, w.data_ptr()
+        else:
+            ent = w16.lookup(weight) if off % 8 == 0 else None
+            if ent is not None:   # operand copy refreshed once per step by gt_cast_multi (begin_step)
+                w, ldw = ent
+                wptr = w.data_ptr() + off * 2
+            else:  # bf16 operand copy of the fp32 master weight block, K padded so rows stay 16-B aligned
+                w = torch.empty(N, ld_in, dtype=x.dtype, device=x.device)
+                call("gt_cast_pad", GT_F32, wf.data_ptr() + off * 4, N, K, Kw, dt_of(w), ptr(w), N, ld_in, ld_in)
+                ldw, wptr = ld_in, w.data_ptr()
         ld_out = ldp(N)
         out_dtype = torch.float32 if out_f32 else x.dtype
         y = torch.empty(M, ld_out, dtype=out_dtype, device=x.device)
@@ -344,6 +404,7 @@ class _LinearFn(torch.autograd.Function):
                   ld_out, flags)
         ctx.save_for_backward(x, w, y if relu else None)
         ctx.params = (weight, bias)
+        ctx.woff = wptr - w.data_ptr()      # byte offset of the operand block inside the saved weight tensor
         ctx.meta = (M, N, K, Kw, off, ld_in, ldw, ld_out, relu, bias is not None, resid is not None)
         return y
 
@@ -363,7 +424,7 @@ class _LinearFn(torch.autograd.Function):
             gz = torch.empty_like(gy)
             call("gt_relu_bwd", dt_of(gy), ptr(gy), ptr(y), gy.numel(), ptr(gz))
             gy = gz
-        wptr = w.data_ptr() + (off * 4 if x.dtype == torch.float32 else 0)
+        wptr = w.data_ptr() + ctx.woff
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
             gx = torch.empty(M, ld_in, dtype=x.dtype, device=x.device)

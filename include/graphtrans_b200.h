@@ -166,6 +166,12 @@ int gt_colsum(int dt, const void* X, int64_t M, int64_t N, int64_t ld, float* ou
 int gt_cast_pad(int dt_in, const void* src, int64_t rows_in, int64_t cols_in, int64_t ld_in,
                 int dt_out, void* dst, int64_t rows_out, int64_t cols_out, int64_t ld_out, void* stream);
 
+/* every fp32 master weight of the model -> its zero-padded bf16 operand copy in ONE launch (once per step; replaces
+ * what torch autocast does per nn.Linear call).  desc_dev: DEVICE int64[n][6] = {src fp32 [rows, cols] contiguous,
+ * dst bf16 [rows, ld_dst], rows, cols, ld_dst, first block}; a block covers 2048 destination elements and
+ * total_blocks = sum over tensors of ceil(rows*ld_dst / 2048). */
+int gt_cast_multi(const int64_t* desc_dev, int32_t n, int64_t total_blocks, void* stream);
+
 /* ---- token packing + LayerNorm (reference modules/utils.py:5-29 pad_batch,
  *      modules/transformer_encoder.py:50-57 CLS append + norm_input) --------------------------
  * layernorm over rows of [M,d] (ld == d): y = LN(x [+ resid]) * gamma + beta ; saves the
