@@ -41,19 +41,20 @@ SIGNATURES = {
     "gt_bn_apply_fwd": [I, P, L, I32, I32, P, I, P, P, P, P, F, P, U64, P],
     "gt_bn_bwd_reduce": [I, P, P, L, I32, I32, P, I, P, F, P, U64, P],
     "gt_bn_bwd_apply": [I, P, P, L, I32, I32, P, P, I, I, P, P, P, P, F, P, U64, P],
-    "gt_gemm": [I, P, I, L, P, I, L, P, L, L, L, L, L, P, P, L, I, I, P],
-    "gt_relu_bwd": [I, P, P, L, P, P],
+    "gt_gemm": [I, P, I, L, P, I, L, P, L, L, L, L, L, P, P, L, I, F, P, U64, I, P],
+    "gt_relu_bwd": [I, P, P, L, P, F, P],
     "gt_colsum": [I, P, L, L, L, P, P],
     "gt_cast_multi": [P, I32, L, P],
     "gt_cast_pad": [I, P, L, L, L, I, P, L, L, L, P],
-    "gt_layernorm_fwd": [I, P, P, P, P, L, I32, P, P, F, P, P, P, P],
-    "gt_layernorm_bwd": [I, P, P, P, P, L, I32, P, P, P, P, P, P],
+    "gt_layernorm_fwd": [I, P, P, P, P, L, I32, P, P, F, P, P, P, F, P, U64, P],
+    "gt_layernorm_bwd": [I, P, P, P, P, L, I32, P, P, P, P, P, P, F, P, U64, P],
     "gt_gather_rows": [I, P, P, P, L, I32, P, P],
     "gt_scatter_rows": [I, P, P, L, I32, P, P, P],
     "gt_pad_batch_fwd": [I, P, P, L, L, I32, P, P, P],
     "gt_pad_batch_bwd": [I, P, P, P, L, L, L, I32, P, P],
-    "gt_mha_fwd": [I, P, P, P, P, L, L, I32, I32, F, P, P, F, P, U64, I, P],
-    "gt_mha_bwd": [I, P, P, P, P, P, P, P, L, L, I32, I32, F, P, P, F, P, U64, I, P],
+    "gt_mha_meta": [P, P, L, L, P, P, P],
+    "gt_mha_fwd": [I, P, P, P, P, P, P, L, L, I32, I32, F, P, P, F, P, U64, I, P],
+    "gt_mha_bwd": [I, P, P, P, P, P, P, P, P, P, L, L, I32, I32, F, P, P, F, P, U64, I, P],
     "gt_pna_reduce_fwd": [I, P, P, P, L, I32, I32, I32, P, P, F, P, I32, P, P, P],
     "gt_pna_reduce_bwd": [I, P, P, P, L, I32, I32, I32, I32, P, P, F, P, P, P, P, P, P],
 }

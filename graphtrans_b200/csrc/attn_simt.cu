@@ -9,11 +9,14 @@
 
 namespace gt {
 
+int mha_meta_launch(const int32_t* tok_graph, const int32_t* tok_off, int64_t n_rows, int64_t B, int32_t* row_bounds,
+                    int32_t* tile_bounds, cudaStream_t st);
 int mha_tc_fwd_launch(int dt, const void* qkv, const int32_t* tok_graph, const int32_t* tok_off, const int32_t* key_start,
-                      int64_t n_rows, int64_t B, int32_t nhead, int32_t dh, float scale, void* out, float* lse,
+                      const int32_t* row_bounds, const int32_t* tile_bounds, int64_t n_rows, int64_t B, int32_t nhead, int32_t dh, float scale, void* out, float* lse,
                       float drop_p, const uint64_t* rng, uint64_t salt, cudaStream_t st);  // attn_tc.cu; -2 = not eligible
 int mha_tc_bwd_launch(int dt, const void* qkv, const void* out, const void* dout, const float* lse,
-                      const int32_t* tok_graph, const int32_t* tok_off, const int32_t* key_start, int64_t n_rows,
+                      const int32_t* tok_graph, const int32_t* tok_off, const int32_t* key_start,
+                      const int32_t* row_bounds, const int32_t* tile_bounds, int64_t n_rows,
                       int64_t B, int32_t nhead, int32_t dh, float scale, void* dqkv, float* delta, float drop_p,
                       const uint64_t* rng, uint64_t salt, cudaStream_t st);
 
@@ -236,14 +239,20 @@ static int check_mha(const char* fn, int64_t n_rows, int64_t B, int nhead, int d
 
 using namespace gt;
 
+extern "C" int gt_mha_meta(const int32_t* tok_graph, const int32_t* tok_off, int64_t n_rows, int64_t B,
+                           int32_t* row_bounds, int32_t* tile_bounds, void* stream) {
+    GT_CHECK_ARG(n_rows > 0 && B > 0 && row_bounds && tile_bounds, "gt_mha_meta: bad arguments");
+    return mha_meta_launch(tok_graph, tok_off, n_rows, B, row_bounds, tile_bounds, (cudaStream_t)stream);
+}
+
 extern "C" int gt_mha_fwd(int dt, const void* qkv, const int32_t* tok_graph, const int32_t* tok_off,
-                          const int32_t* key_start, int64_t n_rows, int64_t B, int32_t nhead, int32_t dh, float scale,
+                          const int32_t* key_start, const int32_t* row_bounds, const int32_t* tile_bounds, int64_t n_rows, int64_t B, int32_t nhead, int32_t dh, float scale,
                           void* out, float* lse, float drop_p, const uint64_t* rng_state, uint64_t salt, int impl,
                           void* stream) {
     if (int r = check_mha("gt_mha_fwd", n_rows, B, nhead, dh)) return r;
     cudaStream_t st = (cudaStream_t)stream;
     if (impl != 1) {
-        const int r = mha_tc_fwd_launch(dt, qkv, tok_graph, tok_off, key_start, n_rows, B, nhead, dh, scale, out, lse, drop_p, rng_state, salt, st);
+        const int r = mha_tc_fwd_launch(dt, qkv, tok_graph, tok_off, key_start, row_bounds, tile_bounds, n_rows, B, nhead, dh, scale, out, lse, drop_p, rng_state, salt, st);
         if (r != -2) return r;
         GT_CHECK_ARG(impl != 2, "gt_mha_fwd: not eligible for the tcgen05 kernel (%s)", gt_last_error());
     }
@@ -254,13 +263,14 @@ extern "C" int gt_mha_fwd(int dt, const void* qkv, const int32_t* tok_graph, con
 }
 
 extern "C" int gt_mha_bwd(int dt, const void* qkv, const void* out, const void* dout, const float* lse,
-                          const int32_t* tok_graph, const int32_t* tok_off, const int32_t* key_start, int64_t n_rows,
+                          const int32_t* tok_graph, const int32_t* tok_off, const int32_t* key_start,
+                          const int32_t* row_bounds, const int32_t* tile_bounds, int64_t n_rows,
                           int64_t B, int32_t nhead, int32_t dh, float scale, void* dqkv, float* delta, float drop_p,
                           const uint64_t* rng_state, uint64_t salt, int impl, void* stream) {
     if (int r = check_mha("gt_mha_bwd", n_rows, B, nhead, dh)) return r;
     cudaStream_t st = (cudaStream_t)stream;
     if (impl != 1) {
-        const int r = mha_tc_bwd_launch(dt, qkv, out, dout, lse, tok_graph, tok_off, key_start, n_rows, B, nhead, dh, scale, dqkv, delta, drop_p, rng_state, salt, st);
+        const int r = mha_tc_bwd_launch(dt, qkv, out, dout, lse, tok_graph, tok_off, key_start, row_bounds, tile_bounds, n_rows, B, nhead, dh, scale, dqkv, delta, drop_p, rng_state, salt, st);
         if (r != -2) return r;
         GT_CHECK_ARG(impl != 2, "gt_mha_bwd: not eligible for the tcgen05 kernel (%s)", gt_last_error());
     }

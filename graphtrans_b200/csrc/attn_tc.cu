@@ -52,6 +52,8 @@ __device__ __forceinline__ uint32_t p_chunk_off(int r, int c) {
 struct AttnParams {
     const int32_t* tok_graph;
     const int32_t* tok_off;
+    const int2* row_bounds;    // optional (gt_mha_meta): [lo, hi) key rows of every token row
+    const int2* tile_bounds;   // optional: (first interacting row, number of 128-row tiles) of every 128-row tile
     void* out;
     float* lse;
     const uint64_t* rng;
@@ -88,9 +90,12 @@ k_mha_tc_fwd(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_async_smem();
         // contiguous key-row range visible from this query tile
-        const int n_tok = p.tok_off[p.B];
         int lo = 0, n = 0;
-        if (q0 < n_tok) {
+        if (p.tile_bounds) {
+            const int2 tb = p.tile_bounds[blockIdx.x];
+            lo = tb.x, n = tb.y;
+        } else if (q0 < p.tok_off[p.B]) {
+            const int n_tok = p.tok_off[p.B];
             const int g0 = p.tok_graph[q0];
             const int last = min(q0 + BQ - 1, n_tok - 1);
             const int g1 = p.tok_graph[last];
@@ -156,8 +161,13 @@ k_mha_tc_fwd(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p) {
         const uint32_t t_lane = tmem + ((uint32_t)(qd * 32) << 16);
         int lo = 0, hi = 0;
         if (row < p.n_rows) {
-            const int g = p.tok_graph[row];
-            if (g >= 0) lo = p.tok_off[g], hi = p.tok_off[g + 1];
+            if (p.row_bounds) {
+                const int2 rb = p.row_bounds[row];
+                lo = rb.x, hi = rb.y;
+            } else {
+                const int g = p.tok_graph[row];
+                if (g >= 0) lo = p.tok_off[g], hi = p.tok_off[g + 1];
+            }
         }
         const Drop dr = make_drop(p.rng, p.salt, p.drop_p);
         const uint32_t rk = drop_row_key(dr, att_row_id_tc(h, row, p.n_rows));
@@ -276,6 +286,29 @@ static cudaError_t launch_fwd(const CUtensorMap& map, const AttnParams& p, cudaS
 }
 
 
+// per-step attention metadata (once per batch instead of three dependent loads in every CTA of every layer):
+// row_bounds[row] = [lo, hi) token rows of the row's graph (0,0 for tail rows); tile_bounds[t] = (first row, number
+// of 128-row tiles) of the contiguous row range that interacts with rows [128 t, 128 t + 128)
+__global__ void k_mha_meta(const int32_t* __restrict__ tok_graph, const int32_t* __restrict__ tok_off, int64_t n_rows, int B,
+                           int2* __restrict__ row_bounds, int2* __restrict__ tile_bounds) {
+    const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (row >= n_rows) return;
+    const int g = tok_graph[row];
+    int2 rb = make_int2(0, 0);
+    if (g >= 0) rb = make_int2(tok_off[g], tok_off[g + 1]);
+    row_bounds[row] = rb;
+    if ((row & 127) == 0) {
+        const int n_tok = tok_off[B];
+        int2 tb = make_int2(0, 0);
+        if (row < n_tok) {
+            const int g1 = tok_graph[min((int64_t)row + 127, (int64_t)n_tok - 1)];
+            tb.x = rb.x;
+            tb.y = (tok_off[g1 + 1] - rb.x + 127) / 128;
+        }
+        tile_bounds[row >> 7] = tb;
+    }
+}
+
 // ------------------------------------------------------------------------------------------ backward
 // delta[h, row] = sum_c dO[row, h*dh + c] * O[row, h*dh + c]   (one warp per (row, head))
 __global__ void __launch_bounds__(256)
@@ -300,6 +333,8 @@ k_mha_delta(const bf16* __restrict__ out, const bf16* __restrict__ dout, int64_t
 struct AttnBwdParams {
     const int32_t* tok_graph;
     const int32_t* tok_off;
+    const int2* row_bounds;
+    const int2* tile_bounds;
     const float* lse;
     const float* delta;
     void* dqkv;
@@ -346,9 +381,12 @@ k_mha_tc_bwd(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant_
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_async_smem();
         // rows of the OTHER kind that interact with the owned tile: the rows of the graphs it touches (symmetric)
-        const int n_tok = p.tok_off[p.B];
         int lo = 0, n = 0;
-        if (t0 < n_tok) {
+        if (p.tile_bounds) {
+            const int2 tb = p.tile_bounds[blockIdx.x];
+            lo = tb.x, n = tb.y;
+        } else if (t0 < p.tok_off[p.B]) {
+            const int n_tok = p.tok_off[p.B];
             const int g0 = p.tok_graph[t0];
             const int g1 = p.tok_graph[min(t0 + 127, n_tok - 1)];
             lo = p.tok_off[g0];
@@ -444,9 +482,14 @@ k_mha_tc_bwd(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant_
             int lo = 0, hi = 0;
             float lse2 = 0.f, dl = 0.f;
             if (qrow < p.n_rows) {
-                const int g = p.tok_graph[qrow];
-                if (g >= 0) {
-                    lo = p.tok_off[g], hi = p.tok_off[g + 1];
+                if (p.row_bounds) {
+                    const int2 rb = p.row_bounds[qrow];
+                    lo = rb.x, hi = rb.y;
+                } else {
+                    const int g = p.tok_graph[qrow];
+                    if (g >= 0) lo = p.tok_off[g], hi = p.tok_off[g + 1];
+                }
+                if (hi > lo) {
                     lse2 = p.lse[(int64_t)h * p.n_rows + qrow] * LOG2E;
                     dl = p.delta[(int64_t)h * p.n_rows + qrow];
                 }
@@ -565,7 +608,16 @@ static cudaError_t launch_bwd(const CUtensorMap& mq, const CUtensorMap& md, cons
 
 }  // namespace tc
 
+int mha_meta_launch(const int32_t* tok_graph, const int32_t* tok_off, int64_t n_rows, int64_t B, int32_t* row_bounds,
+                    int32_t* tile_bounds, cudaStream_t st) {
+    tc::k_mha_meta<<<(unsigned)((n_rows + 255) / 256), 256, 0, st>>>(tok_graph, tok_off, n_rows, (int)B, (int2*)row_bounds,
+                                                                   (int2*)tile_bounds);
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : cuda_fail(e, "gt_mha_meta");
+}
+
 int mha_tc_fwd_launch(int dt, const void* qkv, const int32_t* tok_graph, const int32_t* tok_off, const int32_t* key_start,
+                      const int32_t* row_bounds, const int32_t* tile_bounds,
                       int64_t n_rows, int64_t B, int32_t nhead, int32_t dh, float scale, void* out, float* lse, float drop_p,
                       const uint64_t* rng, uint64_t salt, cudaStream_t st) {
     using namespace tc;
@@ -581,6 +633,7 @@ int mha_tc_fwd_launch(int dt, const void* qkv, const int32_t* tok_graph, const i
     }
     AttnParams p;
     p.tok_graph = tok_graph; p.tok_off = tok_off; p.out = out; p.lse = lse; p.rng = rng; p.salt = salt;
+    p.row_bounds = (const int2*)row_bounds; p.tile_bounds = (const int2*)tile_bounds;
     p.n_rows = n_rows; p.B = (int)B; p.nhead = nhead; p.d = d;
     p.scale_log2 = scale * LOG2E; p.drop_p = drop_p;
     const cudaError_t e = dh == 64 ? launch_fwd<64>(map, p, st) : launch_fwd<32>(map, p, st);
@@ -589,7 +642,8 @@ int mha_tc_fwd_launch(int dt, const void* qkv, const int32_t* tok_graph, const i
 }
 
 int mha_tc_bwd_launch(int dt, const void* qkv, const void* out, const void* dout, const float* lse, const int32_t* tok_graph,
-                      const int32_t* tok_off, const int32_t* key_start, int64_t n_rows, int64_t B, int32_t nhead, int32_t dh,
+                      const int32_t* tok_off, const int32_t* key_start, const int32_t* row_bounds, const int32_t* tile_bounds,
+                      int64_t n_rows, int64_t B, int32_t nhead, int32_t dh,
                       float scale, void* dqkv, float* delta, float drop_p, const uint64_t* rng, uint64_t salt, cudaStream_t st) {
     using namespace tc;
     if (dt != GT_BF16) { set_error("tcgen05 attention takes bf16 activations"); return -2; }
@@ -607,6 +661,7 @@ int mha_tc_bwd_launch(int dt, const void* qkv, const void* out, const void* dout
     k_mha_delta<<<(unsigned)((items + 7) / 8), 256, 0, st>>>((const bf16*)out, (const bf16*)dout, n_rows, nhead, dh, delta);
     AttnBwdParams p;
     p.tok_graph = tok_graph; p.tok_off = tok_off; p.lse = lse; p.delta = delta; p.dqkv = dqkv; p.rng = rng; p.salt = salt;
+    p.row_bounds = (const int2*)row_bounds; p.tile_bounds = (const int2*)tile_bounds;
     p.n_rows = n_rows; p.B = (int)B; p.nhead = nhead; p.d = d;
     p.scale = scale; p.scale_log2 = scale * LOG2E; p.drop_p = drop_p;
     cudaError_t e;

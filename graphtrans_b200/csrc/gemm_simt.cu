@@ -10,7 +10,8 @@ namespace gt {
 
 int gemm_tc_launch(int dt, const void* A, int a_mn, int64_t lda, const void* B, int b_mn, int64_t ldb, void* C,
                    int64_t ldc, int64_t M, int64_t N, int64_t K, int64_t n_fill, const float* bias,
-                   const void* resid, int64_t ldr, int flags, cudaStream_t st);  // gemm_tc.cu; -2 = not eligible
+                   const void* resid, int64_t ldr, int flags, float drop_p, const uint64_t* rng, uint64_t salt,
+                   cudaStream_t st);  // gemm_tc.cu; -2 = not eligible
 
 constexpr int SBM = 64, SBN = 64, SBK = 16;
 
@@ -18,7 +19,9 @@ template <typename T, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(256)
 k_gemm_simt(const T* __restrict__ A, int64_t lda, const T* __restrict__ B, int64_t ldb, void* __restrict__ Cv,
             int64_t ldc, int64_t M, int64_t N, int64_t K, int64_t n_fill, const float* __restrict__ bias,
-            const void* __restrict__ resid, int64_t ldr, int flags, int64_t k_per_split) {
+            const void* __restrict__ resid, int64_t ldr, int flags, int64_t k_per_split, float drop_p,
+            const uint64_t* __restrict__ rng, uint64_t salt) {
+    const Drop dr = make_drop(rng, salt, drop_p);
     __shared__ float As[SBK][SBM + 4];
     __shared__ float Bs[SBK][SBN + 4];
     const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
@@ -82,6 +85,8 @@ k_gemm_simt(const T* __restrict__ A, int64_t lda, const T* __restrict__ B, int64
     for (int i = 0; i < 4; ++i) {
         const int64_t m = m0 + ty * 4 + i;
         if (m >= M) continue;
+        float dsc[4];   // epilogue dropout: element (m, n) belongs to vector m*(ldc/4) + n/4 (n0 + tx*4 is 4-aligned)
+        drop4(dr, (uint64_t)(m * (ldc >> 2) + ((n0 + tx * 4) >> 2)), dsc);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int64_t n = n0 + tx * 4 + j;
@@ -92,6 +97,7 @@ k_gemm_simt(const T* __restrict__ A, int64_t lda, const T* __restrict__ B, int64
                     if (resid) v += (flags & GT_EPI_RESID_F32) ? ((const float*)resid)[m * ldr + n] : to_f(((const T*)resid)[m * ldr + n]);
                 }
                 if (flags & GT_EPI_RELU) v = fmaxf(v, 0.f);
+                v *= dsc[j];
                 if (out_f32) {
                     float* c = (float*)Cv + m * ldc + n;
                     if (accum) atomicAdd(c, v); else *c = v;
@@ -108,7 +114,7 @@ k_gemm_simt(const T* __restrict__ A, int64_t lda, const T* __restrict__ B, int64
 template <typename T>
 static int launch_simt(const T* A, int a_mn, int64_t lda, const T* B, int b_mn, int64_t ldb, void* C, int64_t ldc,
                        int64_t M, int64_t N, int64_t K, int64_t n_fill, const float* bias, const void* resid,
-                       int64_t ldr, int flags, cudaStream_t st) {
+                       int64_t ldr, int flags, float drop_p, const uint64_t* rng, uint64_t salt, cudaStream_t st) {
     const int64_t ncols = n_fill > N ? n_fill : N;
     dim3 grid((unsigned)((ncols + SBN - 1) / SBN), (unsigned)((M + SBM - 1) / SBM), 1);
     int64_t kps = K;
@@ -122,7 +128,7 @@ static int launch_simt(const T* A, int a_mn, int64_t lda, const T* B, int b_mn, 
         kps = ((K + splits - 1) / splits + SBK - 1) / SBK * SBK;
         grid.z = (unsigned)((K + kps - 1) / kps);
     }
-#define L(AM, BM_) k_gemm_simt<T, AM, BM_><<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, n_fill, bias, resid, ldr, flags, kps)
+#define L(AM, BM_) k_gemm_simt<T, AM, BM_><<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, n_fill, bias, resid, ldr, flags, kps, drop_p, rng, salt)
     if (a_mn && b_mn) L(true, true);
     else if (a_mn) L(true, false);
     else if (b_mn) L(false, true);
@@ -137,17 +143,19 @@ using namespace gt;
 
 extern "C" int gt_gemm(int dt, const void* A, int a_mn, int64_t lda, const void* B, int b_mn, int64_t ldb, void* C,
                        int64_t ldc, int64_t M, int64_t N, int64_t K, int64_t n_fill, const float* bias,
-                       const void* resid, int64_t ldr, int flags, int impl, void* stream) {
+                       const void* resid, int64_t ldr, int flags, float drop_p, const uint64_t* rng_state, uint64_t salt,
+                       int impl, void* stream) {
     GT_CHECK_ARG(M > 0 && N > 0 && K > 0, "gt_gemm: bad shape M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
     GT_CHECK_ARG(!(flags & GT_EPI_ACCUM) || (flags & GT_EPI_OUT_F32) || dt == GT_F32, "gt_gemm: ACCUM needs an fp32 C");
     GT_CHECK_ARG(!((flags & GT_EPI_ACCUM) && (flags & GT_EPI_RELU)), "gt_gemm: ACCUM and RELU are exclusive");
+    GT_CHECK_ARG(!(drop_p > 0.f) || (!(flags & GT_EPI_ACCUM) && ldc % 4 == 0), "gt_gemm: epilogue dropout needs ldc %% 4 == 0 and no ACCUM");
     cudaStream_t st = (cudaStream_t)stream;
     if (impl != 1) {
-        const int r = gemm_tc_launch(dt, A, a_mn, lda, B, b_mn, ldb, C, ldc, M, N, K, n_fill, bias, resid, ldr, flags, st);
+        const int r = gemm_tc_launch(dt, A, a_mn, lda, B, b_mn, ldb, C, ldc, M, N, K, n_fill, bias, resid, ldr, flags, drop_p, rng_state, salt, st);
         if (r != -2) return r;
         GT_CHECK_ARG(impl != 2, "gt_gemm: shape/layout not eligible for the tcgen05 kernel (%s)", gt_last_error());
     }
-    GT_DISPATCH_DT(dt, launch_simt<T>((const T*)A, a_mn, lda, (const T*)B, b_mn, ldb, C, ldc, M, N, K, n_fill, bias, resid, ldr, flags, st));
+    GT_DISPATCH_DT(dt, launch_simt<T>((const T*)A, a_mn, lda, (const T*)B, b_mn, ldb, C, ldc, M, N, K, n_fill, bias, resid, ldr, flags, drop_p, rng_state, salt, st));
     GT_LAUNCH_CHECK("gt_gemm(simt)");
     return 0;
 }

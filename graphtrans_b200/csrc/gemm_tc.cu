@@ -27,9 +27,12 @@ namespace tc {
 constexpr int BM = 128, BK = 64;
 constexpr int A_TILE_BYTES = BM * BK * 2;  // 16 KB
 constexpr int MAX_STAGES = 4;
-constexpr int THREADS = 192;
+constexpr int EPI_WARPS = 8;                                   // two per TMEM lane group: they alternate column slabs
+constexpr int THREADS = 64 + 32 * EPI_WARPS;
 constexpr int STG_PITCH = 68;                                  // floats per staged row: 64 + 4 pad (bank-conflict free)
-constexpr int STG_BYTES = 4 * 32 * STG_PITCH * 4;              // 4 epilogue warps x [32 x 68] fp32 = 34816 B
+constexpr int STG_WARP_BYTES = 9216;                           // per epilogue warp: >= 32 x 68 fp32 (8704 B), 1 KB multiple so the
+                                                               // two 4 KB TMA-store slabs inside it are 1024-byte aligned (swizzle)
+constexpr int STG_BYTES = EPI_WARPS * STG_WARP_BYTES;
 
 struct Params {
     void* C;
@@ -40,13 +43,18 @@ struct Params {
     int vec_c, vec_r;       // 16-byte vector access allowed on C / resid rows
     int kb_total, kb_per_split;
     int BN, stages;
+    float drop_p;                        // epilogue dropout after the activation (vector index m*(ldc/4) + n/4)
+    const uint64_t* rng;
+    uint64_t salt;
+    int tma_store;                       // epilogue writes C through TMA bulk stores / reductions (fast path)
     int m_tiles, n_tiles, total_tiles;   // work list: tile t -> n = t % n_tiles, m = (t / n_tiles) % m_tiles, split = rest
     uint32_t idesc, tmem_cols, acc_stride;
 };
 
 template <bool A_MN, bool B_MN, bool OUT_BF16>
 __global__ void __launch_bounds__(THREADS)
-k_gemm_tc(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const Params p) {
+k_gemm_tc(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+          const __grid_constant__ CUtensorMap tma_c, const Params p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tmem_full_bar[2], tmem_empty_bar[2];
     __shared__ uint32_t tmem_base_s;
@@ -65,7 +73,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUt
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&tmem_full_bar[b], 1);
-            mbar_init(&tmem_empty_bar[b], 4);   // one arrival per epilogue warp
+            mbar_init(&tmem_empty_bar[b], EPI_WARPS);   // one arrival per epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -134,20 +142,21 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUt
                 umma_commit(&tmem_full_bar[buf]);  // accumulator of this tile complete
             }
         }
-    } else {  // ===== epilogue warps 2..5: TMEM lane group = warp % 4 =====
+    } else {  // ===== epilogue warps 2..9: TMEM lane group = warp % 4, column-slab parity = (warp - 2) / 4 =====
         // TMEM gives each thread one accumulator ROW (32 lanes x 16 columns per tcgen05.ld); storing rows straight
         // from registers would scatter 16-byte pieces over 32 rows per instruction.  Each warp therefore stages a
         // [32 rows x 64 columns] fp32 slab in its private shared-memory region and streams it out with 16 lanes per
         // row (256 B contiguous fp32 / 128 B bf16), applying bias / residual / ReLU / conversion on the way out
         // with coalesced reads.
-        const int q = warp & 3;
+        const int q = warp & 3, sub = (warp - 2) >> 2;
         const bool accum = p.flags & GT_EPI_ACCUM;
         const bool relu = p.flags & GT_EPI_RELU;
         const bool resid_f32 = p.flags & GT_EPI_RESID_F32;
         const int ncols = max(p.N, p.n_fill);
-        float* stg = reinterpret_cast<float*>(smem_raw + ((smem_base - smem_u32(smem_raw)) + (uint32_t)p.stages * stage_bytes)) + q * (32 * STG_PITCH);
+        float* stg = reinterpret_cast<float*>(smem_raw + ((smem_base - smem_u32(smem_raw)) + (uint32_t)p.stages * stage_bytes) + (warp - 2) * STG_WARP_BYTES);
         const int seg = lane & 15, half = lane >> 4;
-        int ti = 0;
+        const Drop dr = make_drop(p.rng, p.salt, p.drop_p);
+        int ti = 0, slab_i = 0;
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++ti) {
             const int n0 = (t % p.n_tiles) * p.BN, m0 = ((t / p.n_tiles) % p.m_tiles) * BM;
             const bool first = (t / (p.n_tiles * p.m_tiles)) == 0;
@@ -155,7 +164,86 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUt
             const uint32_t acc = tmem_base + (uint32_t)buf * p.acc_stride + ((uint32_t)(q * 32) << 16);
             mbar_wait(&tmem_full_bar[buf], (uint32_t)(ti >> 1) & 1u);
             tc_fence_after();
-            for (int c0 = 0; c0 < p.BN; c0 += 64) {
+            if (p.tma_store) {
+                // fast path: thread = accumulator row.  TMEM -> registers -> (bias, ReLU, convert) -> this warp's
+                // [32 rows x 128 B] 128B-swizzled staging slab -> one TMA bulk store (or fp32 reduce-add for split-K)
+                // per slab, double-buffered so the next slab is produced while the previous one drains.
+                constexpr int SLAB_COLS = OUT_BF16 ? 64 : 32;
+                uint8_t* sbase = reinterpret_cast<uint8_t*>(stg);          // 2 x 4 KB of this warp's region
+                const uint32_t s_u32 = smem_u32(sbase);
+                const uint32_t rsw = (uint32_t)lane & 7u;
+                for (int c0 = sub * SLAB_COLS; c0 < p.BN; c0 += 2 * SLAB_COLS) {   // BN % SLAB_COLS == 0 on this path
+                    const int n_slab = n0 + c0;
+                    if (n_slab >= ncols) break;   // warp-uniform
+                    const uint32_t sb = s_u32 + (uint32_t)(slab_i & 1) * 4096u;
+                    if (lane == 0) tma_wait_group_read<1>();   // the store that last used this buffer has read it
+                    __syncwarp();
+#pragma unroll
+                    for (int c32 = 0; c32 < SLAB_COLS; c32 += 32) {
+                      uint32_t r32[32];
+                      tmem_ld32(acc + (uint32_t)(c0 + c32), r32);
+#pragma unroll
+                      for (int cc = 0; cc < 32; cc += 16) {
+                        const int c = c32 + cc;
+                        float v[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r32[cc + i]);
+                        if (first && p.bias) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                if (n_slab + c + i < p.N) v[i] += __ldg(p.bias + n_slab + c + i);
+                        }
+                        if (relu) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+                        }
+                        if (dr.on) {
+                            const uint64_t vbase = (uint64_t)(m0 + q * 32 + lane) * (uint64_t)(p.ldc >> 2) + (uint64_t)((n_slab + c) >> 2);
+#pragma unroll
+                            for (int i = 0; i < 16; i += 4) {
+                                float dsc[4];
+                                drop4(dr, vbase + (i >> 2), dsc);
+                                v[i] *= dsc[0]; v[i + 1] *= dsc[1]; v[i + 2] *= dsc[2]; v[i + 3] *= dsc[3];
+                            }
+                        }
+                        if (OUT_BF16) {
+#pragma unroll
+                            for (int i = 0; i < 16; i += 8) {
+                                __nv_bfloat162 h0 = __floats2bfloat162_rn(v[i], v[i + 1]), h1 = __floats2bfloat162_rn(v[i + 2], v[i + 3]);
+                                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[i + 4], v[i + 5]), h3 = __floats2bfloat162_rn(v[i + 6], v[i + 7]);
+                                const uint32_t ch = (uint32_t)(c + i) >> 3;
+                                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sb + (uint32_t)lane * 128u + ((ch ^ rsw) << 4)),
+                                             "r"(*reinterpret_cast<uint32_t*>(&h0)), "r"(*reinterpret_cast<uint32_t*>(&h1)),
+                                             "r"(*reinterpret_cast<uint32_t*>(&h2)), "r"(*reinterpret_cast<uint32_t*>(&h3)) : "memory");
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; i += 4) {
+                                const uint32_t ch = (uint32_t)(c + i) >> 2;
+                                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sb + (uint32_t)lane * 128u + ((ch ^ rsw) << 4)),
+                                             "r"(__float_as_uint(v[i])), "r"(__float_as_uint(v[i + 1])), "r"(__float_as_uint(v[i + 2])),
+                                             "r"(__float_as_uint(v[i + 3])) : "memory");
+                            }
+                        }
+                      }
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (accum) tma_reduce_add_2d(&tma_c, sb, n_slab, m0 + q * 32);
+                        else tma_store_2d(&tma_c, sb, n_slab, m0 + q * 32);
+                        tma_commit_group();
+                    }
+                    ++slab_i;
+                }
+                // this warp's share of the TMEM buffer has been read (wait::ld inside tmem_ld32): hand it back
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+                continue;
+            }
+            bool released = false;
+            for (int c0 = sub * 64; c0 < p.BN; c0 += 128) {
                 const int n_slab = n0 + c0;
                 if (n_slab >= ncols) break;               // warp-uniform
                 const int w_slab = min(64, p.BN - c0);    // multiple of 16
@@ -168,10 +256,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUt
                         *reinterpret_cast<float4*>(dst + i) = make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]),
                                                                         __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
                 }
-                if (c0 + 64 >= p.BN || n_slab + 64 >= ncols) {   // last slab of the tile: TMEM buffer fully read
+                if (c0 + 128 >= p.BN || n_slab + 128 >= ncols) {   // this warp's last slab of the tile: its TMEM reads are done
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+                    released = true;
                 } else {
                     __syncwarp();
                 }
@@ -220,6 +309,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUt
 #pragma unroll
                         for (int i = 0; i < 4; ++i) v[i] = fmaxf(v[i], 0.f);
                     }
+                    if (dr.on) {
+                        float dsc[4];
+                        drop4(dr, (uint64_t)m * (uint64_t)(p.ldc >> 2) + (uint64_t)(n >> 2), dsc);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) v[i] *= dsc[i];
+                    }
                     if (OUT_BF16) {
                         bf16* cp = (bf16*)p.C + (int64_t)m * p.ldc + n;
                         if (full4 && p.vec_c) {
@@ -254,7 +349,13 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUt
                 }
                 __syncwarp();   // the slab region is reused by the next slab / tile
             }
+            if (!released) {   // a warp without a slab in this tile still owes its arrival
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+            }
         }
+        if (p.tma_store && lane == 0) tma_wait_group_all();   // staged slabs must be drained before the CTA exits
     }
     tc_fence_before();
     __syncthreads();
@@ -266,15 +367,16 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUt
 
 // ---------------------------------------------------------------------------------------- host side
 template <bool A_MN, bool B_MN>
-static cudaError_t launch(const CUtensorMap& ma, const CUtensorMap& mb, const Params& p, dim3 grid, size_t smem, bool out_bf16, cudaStream_t st) {
+static cudaError_t launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const Params& p, dim3 grid, size_t smem,
+                          bool out_bf16, cudaStream_t st) {
     if (out_bf16) {
         static bool attr = false;
         if (!attr) { cudaFuncSetAttribute(k_gemm_tc<A_MN, B_MN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); attr = true; }
-        k_gemm_tc<A_MN, B_MN, true><<<grid, THREADS, smem, st>>>(ma, mb, p);
+        k_gemm_tc<A_MN, B_MN, true><<<grid, THREADS, smem, st>>>(ma, mb, mc, p);
     } else {
         static bool attr = false;
         if (!attr) { cudaFuncSetAttribute(k_gemm_tc<A_MN, B_MN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); attr = true; }
-        k_gemm_tc<A_MN, B_MN, false><<<grid, THREADS, smem, st>>>(ma, mb, p);
+        k_gemm_tc<A_MN, B_MN, false><<<grid, THREADS, smem, st>>>(ma, mb, mc, p);
     }
     return cudaGetLastError();
 }
@@ -284,7 +386,7 @@ static cudaError_t launch(const CUtensorMap& ma, const CUtensorMap& mb, const Pa
 // returns 0 ok, -2 = shape/layout/dtype not eligible (caller falls back to the CUDA-core kernel), >0 CUDA error
 int gemm_tc_launch(int dt, const void* A, int a_mn, int64_t lda, const void* B, int b_mn, int64_t ldb, void* C, int64_t ldc,
                    int64_t M, int64_t N, int64_t K, int64_t n_fill, const float* bias, const void* resid, int64_t ldr, int flags,
-                   cudaStream_t st) {
+                   float drop_p, const uint64_t* rng, uint64_t salt, cudaStream_t st) {
     using namespace tc;
     if (dt != GT_BF16) { set_error("tcgen05 GEMM takes bf16 operands"); return -2; }
     if (((uintptr_t)A | (uintptr_t)B) & 15 || lda % 8 || ldb % 8) { set_error("operands need 16-byte aligned rows"); return -2; }
@@ -294,11 +396,17 @@ int gemm_tc_launch(int dt, const void* A, int a_mn, int64_t lda, const void* B, 
     const int64_t ncols = n_fill > N ? n_fill : N;
     // output tile width: the fewest tiles of <= 256 columns, rounded to the UMMA N granularity of 16 (wide tiles keep
     // the operand re-read factor, i.e. L2 traffic, low; an MN-major B tile is loaded as ceil(BN/64) TMA boxes)
+    // The TMA-store epilogue (rows 16-byte aligned, no residual operand) moves whole [32 x 128 B] boxes, so there BN
+    // is a multiple of the slab width (64 bf16 / 32 fp32 columns); padded columns only cost MMA issue slots.
+    const int csz0 = out_bf16 ? 2 : 4;
+    const bool tma_ok = ((uintptr_t)C % 16 == 0) && ((ldc * csz0) % 16 == 0) && !resid;
+    const int gran = tma_ok ? (out_bf16 ? 64 : 32) : 16;
     const int64_t nt = (ncols + 255) / 256;
-    const int BN = (int)(((ncols + nt - 1) / nt + 15) / 16 * 16);
+    const int BN = (int)(((ncols + nt - 1) / nt + gran - 1) / gran * gran);
     Params p;
     p.C = C; p.bias = bias; p.resid = resid; p.ldc = ldc; p.ldr = ldr;
     p.M = (int)M; p.N = (int)N; p.n_fill = (int)n_fill; p.flags = flags;
+    p.drop_p = drop_p; p.rng = rng; p.salt = salt;
     const int csz = out_bf16 ? 2 : 4;
     p.vec_c = ((uintptr_t)C % 16 == 0) && ((ldc * csz) % 16 == 0);
     const int rsz = (flags & GT_EPI_RESID_F32) ? 4 : 2;
@@ -335,12 +443,18 @@ int gemm_tc_launch(int dt, const void* A, int a_mn, int64_t lda, const void* B, 
     ok = ok && (b_mn ? make_map(&mb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, 64)
                      : make_map(&mb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64, (uint32_t)BN));
     if (!ok) { set_error("cuTensorMapEncodeTiled failed or unavailable"); return -2; }
+    // output through TMA when rows are 16-byte aligned and there is no residual operand; [32 x 128 B] boxes per warp.
+    // The map's column extent is max(N, n_fill): columns N..n_fill-1 receive the (zero) accumulators of B's OOB rows.
+    CUtensorMap mc = ma;
+    p.tma_store = tma_ok;
+    if (p.tma_store && !make_map(&mc, C, (uint64_t)ncols, (uint64_t)M, (uint64_t)ldc, out_bf16 ? 64 : 32, 32, 128, !out_bf16))
+        p.tma_store = 0;
 
     cudaError_t e;
-    if (a_mn && b_mn) e = launch<true, true>(ma, mb, p, grid, smem, out_bf16, st);
-    else if (a_mn) e = launch<true, false>(ma, mb, p, grid, smem, out_bf16, st);
-    else if (b_mn) e = launch<false, true>(ma, mb, p, grid, smem, out_bf16, st);
-    else e = launch<false, false>(ma, mb, p, grid, smem, out_bf16, st);
+    if (a_mn && b_mn) e = launch<true, true>(ma, mb, mc, p, grid, smem, out_bf16, st);
+    else if (a_mn) e = launch<true, false>(ma, mb, mc, p, grid, smem, out_bf16, st);
+    else if (b_mn) e = launch<false, true>(ma, mb, mc, p, grid, smem, out_bf16, st);
+    else e = launch<false, false>(ma, mb, mc, p, grid, smem, out_bf16, st);
     if (e != cudaSuccess) return cuda_fail(e, "gt_gemm(tcgen05)");
     return 0;
 }

@@ -214,49 +214,55 @@ k_bn_bwd_reduce(const T* __restrict__ x, const T* __restrict__ dy, int64_t M, in
     stat_flush(s, s2, tx, ty, c0, ld, red);
 }
 
+// thread = one 4-channel vector of a 128-channel group (per-channel constants stay in registers), rows strided by 8
 template <typename T>
-__global__ void k_bn_bwd_apply(const T* __restrict__ x, const T* __restrict__ dy, int64_t M, int d, int ld,
-                               const float* __restrict__ ssmr, const float* __restrict__ gamma, int relu,
-                               int training, const double* __restrict__ red, T* __restrict__ dx,
-                               float* __restrict__ dgamma, float* __restrict__ dbeta, float drop_p,
-                               const uint64_t* __restrict__ rng, uint64_t salt) {
+__global__ void __launch_bounds__(256)
+k_bn_bwd_apply(const T* __restrict__ x, const T* __restrict__ dy, int64_t M, int d, int ld, int64_t rows_per_block,
+               const float* __restrict__ ssmr, const float* __restrict__ gamma, int relu, int training,
+               const double* __restrict__ red, T* __restrict__ dx, float* __restrict__ dgamma,
+               float* __restrict__ dbeta, float drop_p, const uint64_t* __restrict__ rng, uint64_t salt) {
     const Drop dr = make_drop(rng, salt, drop_p);
     const int vpr = ld / 4;
-    const int64_t total = M * vpr;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c0 = blockIdx.x * 128 + tx * 4;
+    if (c0 >= ld) return;
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_block, r1 = min(r0 + rows_per_block, M);
     const float invM = 1.f / (float)M;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = i / vpr;
-        const int c0 = (int)(i - r * vpr) * 4;
-        float v[4], g[4], sc[4], sh[4], mu[4], rs[4], o[4];
+    float sc[4], sh[4], mu[4], rs[4], m0[4], m1[4];
+    ld4(ssmr + c0, sc);
+    ld4(ssmr + ld + c0, sh);
+    ld4(ssmr + 2 * ld + c0, mu);
+    ld4(ssmr + 3 * ld + c0, rs);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        m0[q] = (float)red[c0 + q] * invM;
+        m1[q] = (float)red[ld + c0 + q] * invM;
+    }
+    for (int64_t r = r0 + ty; r < r1; r += STAT_TY) {
+        float v[4], g[4], o[4], ds[4];
         ld4(x + r * ld + c0, v);
         ld4(dy + r * ld + c0, g);
-        ld4(ssmr + c0, sc);
-        ld4(ssmr + ld + c0, sh);
-        ld4(ssmr + 2 * ld + c0, mu);
-        ld4(ssmr + 3 * ld + c0, rs);
-        float ds[4];
-        drop4(dr, (uint64_t)i, ds);
+        drop4(dr, (uint64_t)(r * vpr + c0 / 4), ds);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             g[q] *= ds[q];
             if (relu && fmaf(v[q], sc[q], sh[q]) <= 0.f) g[q] = 0.f;
             if (training) {
                 const float xh = (v[q] - mu[q]) * rs[q];
-                const float m0 = (float)red[c0 + q] * invM, m1 = (float)red[ld + c0 + q] * invM;
-                o[q] = sc[q] * (g[q] - m0 - xh * m1);  // sc = gamma * rstd
+                o[q] = sc[q] * (g[q] - m0[q] - xh * m1[q]);  // sc = gamma * rstd
             } else {
                 o[q] = sc[q] * g[q];
             }
         }
         st4(dx + r * ld + c0, o);
-        if (r == 0) {
+    }
+    if (blockIdx.y == 0 && ty == 0) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (c0 + q < d) {
-                    dgamma[c0 + q] += (float)red[ld + c0 + q];   // accumulate semantics (single writer per channel)
-                    dbeta[c0 + q] += (float)red[c0 + q];
-                }
-        }
+        for (int q = 0; q < 4; ++q)
+            if (c0 + q < d) {
+                dgamma[c0 + q] += (float)red[ld + c0 + q];   // accumulate semantics (single writer per channel)
+                dbeta[c0 + q] += (float)red[c0 + q];
+            }
     }
     (void)gamma;
 }
@@ -268,7 +274,9 @@ template <typename T, int MAXV>
 __global__ void k_layernorm_fwd(const T* __restrict__ x, const T* __restrict__ resid,
                                 const int32_t* __restrict__ in_rows, const float* __restrict__ cls, int64_t M,
                                 int d, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                                T* __restrict__ y, T* __restrict__ presum, float* __restrict__ mean_rstd) {
+                                T* __restrict__ y, T* __restrict__ presum, float* __restrict__ mean_rstd, float drop_p,
+                                const uint64_t* __restrict__ rng, uint64_t salt) {
+    const Drop dr = make_drop(rng, salt, drop_p);
     const int lane = threadIdx.x & 31;
     const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= M) return;
@@ -284,6 +292,12 @@ __global__ void k_layernorm_fwd(const T* __restrict__ x, const T* __restrict__ r
             if (src >= 0) ld4(x + src * d + vi * 4, v[k]);
             else if (src == -1 && cls) ld4(cls + vi * 4, v[k]);
             else v[k][0] = v[k][1] = v[k][2] = v[k][3] = 0.f;
+            if (dr.on) {   // LN(drop(x) + resid): dropout on the sub-layer output before the residual add
+                float ds[4];
+                drop4(dr, (uint64_t)(row * nv + vi), ds);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) v[k][q] *= ds[q];
+            }
             if (resid) {
                 float t[4];
                 ld4(resid + row * d + vi * 4, t);
@@ -330,7 +344,9 @@ template <typename T, int MAXV>
 __global__ void k_layernorm_bwd(const T* __restrict__ dy, const T* __restrict__ presum,
                                 const float* __restrict__ mean_rstd, const int32_t* __restrict__ out_rows,
                                 int64_t M, int d, const float* __restrict__ gamma, T* __restrict__ dx,
-                                float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dcls) {
+                                float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dcls,
+                                T* __restrict__ dx_drop, float drop_p, const uint64_t* __restrict__ rng, uint64_t salt) {
+    const Drop dr = make_drop(rng, salt, drop_p);
     extern __shared__ float sh[];  // [2*d]
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const int nv = d / 4;
@@ -375,8 +391,16 @@ __global__ void k_layernorm_bwd(const T* __restrict__ dy, const T* __restrict__ 
                 float o[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) o[q] = rstd * (gy[k][q] - s1 - xh[k][q] * s2);
-                if (dst >= 0) st4(dx + dst * d + vi * 4, o);
-                else if (dst == -1 && dcls) {
+                if (dst >= 0) {
+                    st4(dx + dst * d + vi * 4, o);
+                    if (dx_drop) {   // gradient of the dropped operand: same mask as the forward
+                        float ds[4];
+                        drop4(dr, (uint64_t)(row * nv + vi), ds);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) o[q] *= ds[q];
+                        st4(dx_drop + dst * d + vi * 4, o);
+                    }
+                } else if (dst == -1 && dcls) {
 #pragma unroll
                     for (int q = 0; q < 4; ++q) atomicAdd(dcls + vi * 4 + q, o[q]);
                 }
@@ -520,7 +544,7 @@ constexpr int EMB_SMEM_ROWS = 512;       // total rows staged per block (64 KB)
 template <typename T>
 __global__ void __launch_bounds__(256)
 k_embed_bwd(EmbCols cols, int64_t N, int d, int ld, const T* __restrict__ dout) {
-    extern __shared__ float sh_tab[];    // [rows_small][32]
+    extern __shared__ float sh_tab[];    // [rows_small][32] then the block's index tile int32 [ncol][EMB_NB]
     __shared__ int row_base[EMB_MAXCOL]; // first smem row of column c, -1 = global atomics
     __shared__ int rows_small_s;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -536,17 +560,29 @@ k_embed_bwd(EmbCols cols, int64_t N, int d, int ld, const T* __restrict__ dout) 
     __syncthreads();
     const int rows_small = rows_small_s;
     for (int i = threadIdx.x; i < rows_small * 32; i += blockDim.x) sh_tab[i] = 0.f;
+    const int64_t n0 = (int64_t)blockIdx.x * EMB_NB, n1 = min(n0 + EMB_NB, N);
+    // stage the (clamped) indices of this node block once: every thread issues independent loads, instead of each
+    // warp walking node by node through dependent 8-byte index loads
+    int32_t* sh_idx = reinterpret_cast<int32_t*>(sh_tab + EMB_SMEM_ROWS * 32);
+    for (int i = threadIdx.x; i < cols.ncol * EMB_NB; i += blockDim.x) {
+        const int c = i / EMB_NB;
+        const int64_t r = n0 + (i - c * EMB_NB);
+        int64_t id = 0;
+        if (r < n1) {
+            id = cols.idx[c][r * cols.stride[c]];
+            if (id > cols.clamp[c]) id = cols.clamp[c];
+        }
+        sh_idx[i] = (int32_t)id;
+    }
     __syncthreads();
     const int ch = blockIdx.y * 32 + lane;
-    const int64_t n0 = (int64_t)blockIdx.x * EMB_NB, n1 = min(n0 + EMB_NB, N);
     if (ch < d) {
         for (int64_t r = n0 + warp; r < n1; r += 8) {
             const float g = to_f(dout[r * ld + ch]);
             for (int c = 0; c < cols.ncol; ++c) {
-                int64_t id = cols.idx[c][r * cols.stride[c]];
-                if (id > cols.clamp[c]) id = cols.clamp[c];
-                if (row_base[c] >= 0) atomicAdd(&sh_tab[(row_base[c] + (int)id) * 32 + lane], g);
-                else atomicAdd(cols.dtable[c] + id * d + ch, g);
+                const int id = sh_idx[c * EMB_NB + (int)(r - n0)];
+                if (row_base[c] >= 0) atomicAdd(&sh_tab[(row_base[c] + id) * 32 + lane], g);
+                else atomicAdd(cols.dtable[c] + (int64_t)id * d + ch, g);
             }
         }
     }
@@ -565,13 +601,13 @@ k_embed_bwd(EmbCols cols, int64_t N, int d, int ld, const T* __restrict__ dout) 
 
 // dz = dy where y > 0 else 0 (backward of a ReLU fused into a producer's epilogue)
 template <typename T>
-__global__ void k_relu_bwd(const T* __restrict__ dy, const T* __restrict__ y, int64_t n4, T* __restrict__ dz) {
+__global__ void k_relu_bwd(const T* __restrict__ dy, const T* __restrict__ y, int64_t n4, T* __restrict__ dz, float scale) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
         float g[4], v[4];
         ld4(dy + i * 4, g);
         ld4(y + i * 4, v);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) g[q] = v[q] > 0.f ? g[q] : 0.f;
+        for (int q = 0; q < 4; ++q) g[q] = v[q] > 0.f ? g[q] * scale : 0.f;
         st4(dz + i * 4, g);
     }
 }
@@ -648,6 +684,35 @@ __global__ void k_colsum(const T* __restrict__ X, int64_t M, int64_t N, int64_t 
 #pragma unroll
         for (int k = 0; k < 8; ++k) t += sh[k][threadIdx.x];
         atomicAdd(out + c, t);
+    }
+}
+
+// vectorised variant (rows 8/16-byte aligned, ld % 4 == 0): 8 row lanes x 32 column lanes x 4 channels like k_colstats
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_colsum_v(const T* __restrict__ X, int64_t M, int N, int64_t ld, int64_t rows_per_block, float* __restrict__ out) {
+    __shared__ float sh[STAT_TY][128 + 4];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c0 = blockIdx.x * 128 + tx * 4;
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_block, r1 = min(r0 + rows_per_block, M);
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    if (c0 < N) {   // N % 4 may be non-zero: the row tail up to ld is readable (ld % 4 == 0) and masked at the flush
+        for (int64_t r = r0 + ty; r < r1; r += STAT_TY) {
+            float v[4];
+            ld4(X + r * ld + c0, v);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) s[q] += v[q];
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) sh[ty][tx * 4 + q] = s[q];
+    __syncthreads();
+    if (threadIdx.x < 128) {
+        float a = 0.f;
+#pragma unroll
+        for (int k = 0; k < STAT_TY; ++k) a += sh[k][threadIdx.x];
+        const int c = blockIdx.x * 128 + threadIdx.x;
+        if (c < N) atomicAdd(out + c, a);
     }
 }
 
@@ -731,18 +796,21 @@ extern "C" int gt_bn_bwd_apply(int dt, const void* x, const void* dy, int64_t M,
                                void* dx, float* dgamma, float* dbeta, float drop_p, const uint64_t* rng_state,
                                uint64_t salt, void* stream) {
     GT_CHECK_ARG(M > 0 && ld >= d && ld % 4 == 0, "gt_bn_bwd_apply: bad shape");
-    GT_DISPATCH_DT(dt, (k_bn_bwd_apply<T><<<blocks_for(M * (ld / 4), 256), 256, 0, ST>>>((const T*)x, (const T*)dy, M, d, ld, ssmr, gamma, relu, training, red, (T*)dx, dgamma, dbeta, drop_p, rng_state, salt)));
+    int64_t rpb;
+    const dim3 grid = stat_grid(M, ld, &rpb);
+    GT_DISPATCH_DT(dt, (k_bn_bwd_apply<T><<<grid, 256, 0, ST>>>((const T*)x, (const T*)dy, M, d, ld, rpb, ssmr, gamma, relu, training, red, (T*)dx, dgamma, dbeta, drop_p, rng_state, salt)));
     GT_LAUNCH_CHECK("gt_bn_bwd_apply");
     return 0;
 }
 
 extern "C" int gt_layernorm_fwd(int dt, const void* x, const void* resid, const int32_t* in_rows, const float* cls,
                                 int64_t M, int32_t d, const float* gamma, const float* beta, float eps, void* y,
-                                void* presum, float* mean_rstd, void* stream) {
+                                void* presum, float* mean_rstd, float drop_p, const uint64_t* rng_state, uint64_t salt,
+                                void* stream) {
     GT_CHECK_ARG(M > 0 && d > 0 && d % 4 == 0 && d <= LN_MAXV * 128, "gt_layernorm_fwd: d=%d must be a multiple of 4 and <= %d", d, LN_MAXV * 128);
     GT_DISPATCH_DT(dt, {
-        if (d <= 256) k_layernorm_fwd<T, 2><<<(int)((M + 7) / 8), 256, 0, ST>>>((const T*)x, (const T*)resid, in_rows, cls, M, d, gamma, beta, eps, (T*)y, (T*)presum, mean_rstd);
-        else k_layernorm_fwd<T, LN_MAXV><<<(int)((M + 7) / 8), 256, 0, ST>>>((const T*)x, (const T*)resid, in_rows, cls, M, d, gamma, beta, eps, (T*)y, (T*)presum, mean_rstd);
+        if (d <= 256) k_layernorm_fwd<T, 2><<<(int)((M + 7) / 8), 256, 0, ST>>>((const T*)x, (const T*)resid, in_rows, cls, M, d, gamma, beta, eps, (T*)y, (T*)presum, mean_rstd, drop_p, rng_state, salt);
+        else k_layernorm_fwd<T, LN_MAXV><<<(int)((M + 7) / 8), 256, 0, ST>>>((const T*)x, (const T*)resid, in_rows, cls, M, d, gamma, beta, eps, (T*)y, (T*)presum, mean_rstd, drop_p, rng_state, salt);
     });
     GT_LAUNCH_CHECK("gt_layernorm_fwd");
     return 0;
@@ -750,12 +818,14 @@ extern "C" int gt_layernorm_fwd(int dt, const void* x, const void* resid, const 
 
 extern "C" int gt_layernorm_bwd(int dt, const void* dy, const void* presum, const float* mean_rstd,
                                 const int32_t* out_rows, int64_t M, int32_t d, const float* gamma, void* dx,
-                                float* dgamma, float* dbeta, float* dcls, void* stream) {
+                                float* dgamma, float* dbeta, float* dcls, void* dx_drop, float drop_p,
+                                const uint64_t* rng_state, uint64_t salt, void* stream) {
+    GT_CHECK_ARG(!dx_drop || !out_rows, "gt_layernorm_bwd: dropout and row scatter are exclusive");
     GT_CHECK_ARG(M > 0 && d > 0 && d % 4 == 0 && d <= LN_MAXV * 128, "gt_layernorm_bwd: bad d=%d", d);
     const int grid = blocks_for(M, 8 * 4, kNumSMs * 4);
     GT_DISPATCH_DT(dt, {
-        if (d <= 256) k_layernorm_bwd<T, 2><<<grid, 256, 2 * d * sizeof(float), ST>>>((const T*)dy, (const T*)presum, mean_rstd, out_rows, M, d, gamma, (T*)dx, dgamma, dbeta, dcls);
-        else k_layernorm_bwd<T, LN_MAXV><<<grid, 256, 2 * d * sizeof(float), ST>>>((const T*)dy, (const T*)presum, mean_rstd, out_rows, M, d, gamma, (T*)dx, dgamma, dbeta, dcls);
+        if (d <= 256) k_layernorm_bwd<T, 2><<<grid, 256, 2 * d * sizeof(float), ST>>>((const T*)dy, (const T*)presum, mean_rstd, out_rows, M, d, gamma, (T*)dx, dgamma, dbeta, dcls, (T*)dx_drop, drop_p, rng_state, salt);
+        else k_layernorm_bwd<T, LN_MAXV><<<grid, 256, 2 * d * sizeof(float), ST>>>((const T*)dy, (const T*)presum, mean_rstd, out_rows, M, d, gamma, (T*)dx, dgamma, dbeta, dcls, (T*)dx_drop, drop_p, rng_state, salt);
     });
     GT_LAUNCH_CHECK("gt_layernorm_bwd");
     return 0;
@@ -825,7 +895,7 @@ extern "C" int gt_embed_sum_bwd(int dt, const void* dout, int64_t N, int32_t d, 
     EmbCols c;
     if (int r = fill_cols(c, ncol, idx_host, stride_host, clamp_host, nullptr, dtable_host)) return r;
     dim3 grid((unsigned)((N + EMB_NB - 1) / EMB_NB), (unsigned)((d + 31) / 32));
-    const size_t smem = (size_t)EMB_SMEM_ROWS * 32 * sizeof(float);
+    const size_t smem = (size_t)EMB_SMEM_ROWS * 32 * sizeof(float) + (size_t)EMB_MAXCOL * EMB_NB * sizeof(int32_t);
     GT_DISPATCH_DT(dt, {
         static bool attr = false;
         if (!attr) { cudaFuncSetAttribute(k_embed_bwd<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
@@ -861,9 +931,9 @@ extern "C" int gt_cast_multi(const int64_t* desc_dev, int32_t n, int64_t total_b
     return 0;
 }
 
-extern "C" int gt_relu_bwd(int dt, const void* dy, const void* y, int64_t n, void* dz, void* stream) {
+extern "C" int gt_relu_bwd(int dt, const void* dy, const void* y, int64_t n, void* dz, float scale, void* stream) {
     GT_CHECK_ARG(n > 0 && n % 4 == 0, "gt_relu_bwd: element count must be a positive multiple of 4");
-    GT_DISPATCH_DT(dt, (k_relu_bwd<T><<<blocks_for(n / 4, 256), 256, 0, ST>>>((const T*)dy, (const T*)y, n / 4, (T*)dz)));
+    GT_DISPATCH_DT(dt, (k_relu_bwd<T><<<blocks_for(n / 4, 256), 256, 0, ST>>>((const T*)dy, (const T*)y, n / 4, (T*)dz, scale)));
     GT_LAUNCH_CHECK("gt_relu_bwd");
     return 0;
 }
@@ -886,6 +956,14 @@ extern "C" int gt_rng_advance(uint64_t* rng_state, void* stream) {
 
 extern "C" int gt_colsum(int dt, const void* X, int64_t M, int64_t N, int64_t ld, float* out, void* stream) {
     GT_CHECK_ARG(M > 0 && N > 0 && ld >= N, "gt_colsum: bad shape");
+    const int esz = dt == GT_BF16 ? 2 : 4;
+    if (ld % 4 == 0 && (uintptr_t)X % (4 * esz) == 0 && (N + 3) / 4 * 4 <= ld) {
+        int64_t rpb;
+        const dim3 grid = stat_grid(M, (int)((N + 3) / 4 * 4), &rpb);
+        GT_DISPATCH_DT(dt, (k_colsum_v<T><<<grid, 256, 0, ST>>>((const T*)X, M, (int)N, ld, rpb, out)));
+        GT_LAUNCH_CHECK("gt_colsum");
+        return 0;
+    }
     int slabs = (int)((M + 255) / 256);
     if (slabs > 64) slabs = 64;
     dim3 grid((unsigned)((N + 31) / 32), slabs), block(32, 8);

@@ -288,6 +288,11 @@ class GraphPlan:
              ptr(self.cls_rows), ptr(self.scalars))
         self._etype = {}
         self._S = None
+        # attention metadata of the packed layout (row key ranges, tile ranges): once per batch for all layers
+        self.row_bounds = torch.empty(2 * self.n_rows, **i32)
+        self.tile_bounds = torch.empty(2 * ((self.n_rows + 127) // 128), **i32)
+        call("gt_mha_meta", ptr(self.tok_graph), ptr(self.tok_off), self.n_rows, B, ptr(self.row_bounds),
+             ptr(self.tile_bounds))
 
     def edge_type(self, edge_attr: torch.Tensor, dims) -> torch.Tensor:
         """combined categorical edge id (mixed radix over `dims`) for table edge encoders."""
@@ -359,10 +364,11 @@ def embed_sum(index_cols, tables, clamps=None):
 
 
 # ----------------------------------------------------------------------------- dense layers
-def _gemm_raw(dt, A, a_mn, lda, Bm, b_mn, ldb, C, ldc, M, N, K, n_fill, bias, resid, ldr, flags, impl=None):
+def _gemm_raw(dt, A, a_mn, lda, Bm, b_mn, ldb, C, ldc, M, N, K, n_fill, bias, resid, ldr, flags, impl=None,
+              drop_p=0.0, rng=None, salt=0):
     """raw-pointer gt_gemm (A, Bm, C are device addresses so strided sub-blocks need no copies)"""
     call("gt_gemm", dt, A, int(a_mn), lda, Bm, int(b_mn), ldb, C, ldc, M, N, K, n_fill, ptr(bias), ptr(resid), ldr,
-         flags, GEMM_IMPL if impl is None else impl)
+         flags, float(drop_p), rng, salt, GEMM_IMPL if impl is None else impl)
 
 
 class _LinearFn(torch.autograd.Function):
@@ -371,7 +377,7 @@ class _LinearFn(torch.autograd.Function):
     block of the weight (JK=cat: gnn2transformer applied to the parts without concatenating)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, relu, out_f32, resid, off, K):
+    def forward(ctx, x, weight, bias, relu, out_f32, resid, off, K, drop_p, salt):
         x = x.contiguous()
         M, ld_in = x.shape
         N, Kw = weight.shape
@@ -401,7 +407,8 @@ class _LinearFn(torch.autograd.Function):
             if out_dtype == torch.float32 and x.dtype != torch.float32:
                 flags |= _lib.EPI_RESID_F32
         _gemm_raw(dt_of(x), x.data_ptr(), 0, ld_in, wptr, 0, ldw, y.data_ptr(), ld_out, M, N, K, ld_out, bias, resid,
-                  ld_out, flags)
+                  ld_out, flags, drop_p=drop_p, rng=ptr(rng_state(x.device)) if drop_p else None, salt=salt)
+        ctx.drop_p = drop_p
         ctx.save_for_backward(x, w, y if relu else None)
         ctx.params = (weight, bias)
         ctx.woff = wptr - w.data_ptr()      # byte offset of the operand block inside the saved weight tensor
@@ -422,7 +429,8 @@ class _LinearFn(torch.autograd.Function):
             if y.dtype != gy.dtype:
                 raise RuntimeError("linear: relu with a widened output is not supported")
             gz = torch.empty_like(gy)
-            call("gt_relu_bwd", dt_of(gy), ptr(gy), ptr(y), gy.numel(), ptr(gz))
+            # a dropped element has y == 0, so the ReLU test also applies the keep mask; only the 1/(1-p) scale is left
+            call("gt_relu_bwd", dt_of(gy), ptr(gy), ptr(y), gy.numel(), ptr(gz), 1.0 / (1.0 - ctx.drop_p))
             gy = gz
         wptr = w.data_ptr() + ctx.woff
         gx = gw = gb = None
@@ -442,13 +450,16 @@ class _LinearFn(torch.autograd.Function):
             tgt, gb = _grad_target(bias)
             call("gt_colsum", dt_of(gy), ptr(gy), M, N, ld_out, ptr(tgt))
             _grad_done(bias)
-        return gx, gw, gb, None, None, g_res, None, None
+        return gx, gw, gb, None, None, g_res, None, None, None, None
 
 
 def linear(x, weight, bias=None, relu=False, out_f32=False, resid=None, drop_p=0.0, w_col_off=0, K=None):
-    """drop(act(x W[:, off:off+K]^T + b)) [+ resid]; dropout together with resid is not a reference pattern"""
-    y = _LinearFn.apply(x, weight, bias, relu, out_f32, resid, w_col_off, K)
-    return dropout(y, drop_p) if drop_p else y
+    """drop(act(x W[:, off:off+K]^T + b)) [+ resid]; drop(relu(.)) runs in the GEMM epilogue (the FFN pattern of
+    nn.TransformerEncoderLayer); dropout without ReLU / together with resid is not a reference pattern"""
+    fused = bool(drop_p) and relu and resid is None
+    y = _LinearFn.apply(x, weight, bias, relu, out_f32, resid, w_col_off, K, float(drop_p) if fused else 0.0,
+                        next_salt() if fused else 0)
+    return dropout(y, drop_p) if (drop_p and not fused) else y
 
 
 # ----------------------------------------------------------------------------- aggregation
@@ -628,7 +639,7 @@ class _LayerNormFn(torch.autograd.Function):
     """y = LN(x[in_rows] (+cls for -1 rows) + resid). Rows = len(in_rows) if given else x rows."""
 
     @staticmethod
-    def forward(ctx, x, resid, gamma, beta, eps, in_rows, cls, n_rows):
+    def forward(ctx, x, resid, gamma, beta, eps, in_rows, cls, n_rows, drop_p, salt):
         x = x.contiguous()
         d = gamma.shape[0]
         if x.shape[1] != d:
@@ -636,13 +647,14 @@ class _LayerNormFn(torch.autograd.Function):
         M = n_rows if in_rows is not None else x.shape[0]
         dev = x.device
         y = torch.empty(M, d, dtype=x.dtype, device=dev)
-        presum = torch.empty(M, d, dtype=x.dtype, device=dev) if (resid is not None or in_rows is not None) else None
+        presum = torch.empty(M, d, dtype=x.dtype, device=dev) if (resid is not None or in_rows is not None or drop_p) else None
         mr = torch.empty(2 * M, dtype=torch.float32, device=dev)
         if resid is not None:
             resid = resid.contiguous()
         clsv = cls.contiguous().view(-1) if cls is not None else None
         call("gt_layernorm_fwd", dt_of(x), ptr(x), ptr(resid), ptr(in_rows), ptr(clsv), M, d, ptr(gamma), ptr(beta),
-             float(eps), ptr(y), ptr(presum), ptr(mr))
+             float(eps), ptr(y), ptr(presum), ptr(mr), float(drop_p), ptr(rng_state(dev)) if drop_p else None, salt)
+        ctx.drop = (float(drop_p), salt)
         ctx.save_for_backward(presum if presum is not None else x, mr, gamma)
         ctx.params = (gamma, beta, cls)
         ctx.meta = (M, d, in_rows, x.shape[0], resid is not None, cls.shape if cls is not None else None)
@@ -661,19 +673,22 @@ class _LayerNormFn(torch.autograd.Function):
         pg, pb, pcls = ctx.params
         (tg, dgamma), (tb, dbeta) = _grad_target(pg), _grad_target(pb)
         tcls, dcls = _grad_target(pcls) if cls_shape is not None else (None, None)
+        drop_p, salt = ctx.drop
+        dxd = torch.empty_like(dx) if drop_p else None     # gradient of the dropped operand (same mask as forward)
         call("gt_layernorm_bwd", dt_of(g), ptr(g), ptr(presum), ptr(mr), ptr(rows), M, d, ptr(gamma), ptr(dx),
-             ptr(tg), ptr(tb), ptr(tcls))
+             ptr(tg), ptr(tb), ptr(tcls), ptr(dxd), drop_p, ptr(rng_state(dev)) if drop_p else None, salt)
         for prm in (pg, pb, pcls):
             if prm is not None:
                 _grad_done(prm)
-        return (dx, dx if has_resid else None, dgamma, dbeta, None, None, dcls, None)
+        return (dxd if drop_p else dx, dx if has_resid else None, dgamma, dbeta, None, None, dcls, None, None, None)
 
 
 def layer_norm(x, ln: torch.nn.LayerNorm, resid=None, in_rows=None, cls=None, n_rows=None, drop_p=0.0):
-    """LN(drop(x)[in_rows] + resid)"""
-    if drop_p:
-        x = dropout(x, drop_p)
-    return _LayerNormFn.apply(x, resid, ln.weight, ln.bias, ln.eps, in_rows, cls, n_rows)
+    """LN(drop(x) + resid) - the dropout runs inside the LayerNorm kernels (no gather together with dropout)"""
+    if drop_p and in_rows is not None:
+        x, drop_p = dropout(x, drop_p), 0.0
+    return _LayerNormFn.apply(x, resid, ln.weight, ln.bias, ln.eps, in_rows, cls, n_rows, float(drop_p),
+                              next_salt() if drop_p else 0)
 
 
 class _GatherRowsFn(torch.autograd.Function):
@@ -743,7 +758,9 @@ class _MHAFn(torch.autograd.Function):
         scale = float(dh) ** -0.5
         out = torch.empty(n_rows, d, dtype=qkv.dtype, device=qkv.device)
         lse = torch.empty(nhead * n_rows, dtype=torch.float32, device=qkv.device)
-        call("gt_mha_fwd", dt_of(qkv), ptr(qkv), ptr(plan.tok_graph), ptr(plan.tok_off), ptr(key_start), n_rows,
+        meta = (getattr(plan, "row_bounds", None), getattr(plan, "tile_bounds", None)) if key_start is None else (None, None)
+        call("gt_mha_fwd", dt_of(qkv), ptr(qkv), ptr(plan.tok_graph), ptr(plan.tok_off), ptr(key_start), ptr(meta[0]),
+             ptr(meta[1]), n_rows,
              plan.B, nhead, dh, scale, ptr(out), ptr(lse), float(drop_p),
              ptr(rng_state(qkv.device)) if drop_p else None, salt, MHA_IMPL)
         ctx.save_for_backward(qkv, out, lse)
@@ -758,8 +775,9 @@ class _MHAFn(torch.autograd.Function):
         n_rows = qkv.shape[0]
         dqkv = torch.empty_like(qkv)
         delta = torch.empty(nhead * n_rows, dtype=torch.float32, device=qkv.device)
+        meta = (getattr(plan, "row_bounds", None), getattr(plan, "tile_bounds", None)) if key_start is None else (None, None)
         call("gt_mha_bwd", dt_of(qkv), ptr(qkv), ptr(out), ptr(g), ptr(lse), ptr(plan.tok_graph), ptr(plan.tok_off),
-             ptr(key_start), n_rows, plan.B, nhead, dh, scale, ptr(dqkv), ptr(delta), drop_p,
+             ptr(key_start), ptr(meta[0]), ptr(meta[1]), n_rows, plan.B, nhead, dh, scale, ptr(dqkv), ptr(delta), drop_p,
              ptr(rng_state(qkv.device)) if drop_p else None, salt, MHA_IMPL)
         return dqkv, None, None, None, None, None
 

@@ -153,13 +153,16 @@ int gt_bn_bwd_apply(int dt, const void* x, const void* dy, int64_t M, int32_t d,
  * C[m,n] = sum_k A(m,k) B(n,k) (+ bias[n]) (+ resid[m,n]) (relu) ; columns N..n_fill-1 := 0.
  * a_mn / b_mn: operand stored "MN-major" (element (m,k) at A[k*lda+m]) instead of K-major
  * (A[m*lda+k]).  A/B dtype = dt; C dtype = dt unless GT_EPI_OUT_F32; GT_EPI_ACCUM adds into C
- * (fp32 C only; used with splits > 1).  impl: 0 = auto (tcgen05 when eligible), 1 = CUDA-core
+ * (fp32 C only; used with splits > 1).  drop_p/rng_state/salt: dropout applied after the activation
+ * (drop(relu(x W^T + b)), the FFN of nn.TransformerEncoderLayer); needs ldc % 4 == 0.  impl: 0 = auto (tcgen05 when eligible), 1 = CUDA-core
  * reference kernel, 2 = tcgen05 only (error when not eligible). */
 int gt_gemm(int dt, const void* A, int a_mn, int64_t lda, const void* B, int b_mn, int64_t ldb,
             void* C, int64_t ldc, int64_t M, int64_t N, int64_t K, int64_t n_fill,
-            const float* bias, const void* resid, int64_t ldr, int flags, int impl, void* stream);
-/* dz = dy * (y > 0): backward of a ReLU that was fused into a GEMM epilogue; n % 4 == 0 */
-int gt_relu_bwd(int dt, const void* dy, const void* y, int64_t n, void* dz, void* stream);
+            const float* bias, const void* resid, int64_t ldr, int flags, float drop_p,
+            const uint64_t* rng_state, uint64_t salt, int impl, void* stream);
+/* dz = dy * (y > 0) * scale: backward of a ReLU (+ dropout: a dropped element has y == 0, scale = 1/(1-p)) that
+ * was fused into a GEMM epilogue; n % 4 == 0 */
+int gt_relu_bwd(int dt, const void* dy, const void* y, int64_t n, void* dz, float scale, void* stream);
 /* out[n] += sum_m X[m,n]  (bias gradients) ; out fp32 [N] is ACCUMULATED into (caller zeroes a fresh buffer) */
 int gt_colsum(int dt, const void* X, int64_t M, int64_t N, int64_t ld, float* out, void* stream);
 /* dst[r, 0:cols_out] = cast(src[r, 0:cols_in]) zero padded to cols_out; rows_out >= rows_in zero padded */
@@ -174,18 +177,22 @@ int gt_cast_multi(const int64_t* desc_dev, int32_t n, int64_t total_blocks, void
 
 /* ---- token packing + LayerNorm (reference modules/utils.py:5-29 pad_batch,
  *      modules/transformer_encoder.py:50-57 CLS append + norm_input) --------------------------
- * layernorm over rows of [M,d] (ld == d): y = LN(x [+ resid]) * gamma + beta ; saves the
+ * layernorm over rows of [M,d] (ld == d): y = LN(drop(x) [+ resid]) * gamma + beta (dropout on the sub-layer output
+ * as in norm1(src + dropout1(src2)), reference nn.TransformerEncoderLayer) ; saves the
  * pre-norm sum (needed by backward) only implicitly through mean/rstd + xhat recompute.
  * in_rows (optional int32 [M]): row r reads x[in_rows[r]] (negative -> row of zeros/cls). */
 int gt_layernorm_fwd(int dt, const void* x, const void* resid, const int32_t* in_rows,
                      const float* cls, int64_t M, int32_t d, const float* gamma, const float* beta,
-                     float eps, void* y, void* presum, float* mean_rstd, void* stream);
-/* dx_sum = dLN/d(presum); dgamma/dbeta accumulated (pre-zeroed fp32 [d]).
+                     float eps, void* y, void* presum, float* mean_rstd, float drop_p,
+                     const uint64_t* rng_state, uint64_t salt, void* stream);
+/* dx_sum = dLN/d(presum); dx_drop (optional, needs out_rows == NULL) = dx_sum * keep/(1-p) = gradient of the dropped
+ * operand x; dgamma/dbeta accumulated (pre-zeroed fp32 [d]).
  * out_rows (optional): scatter row r of dx to dx[out_rows[r]] (rows < 0: -1 accumulates into
  * dcls (fp32 [d], pre-zeroed), -2 dropped); untouched rows of dx must be pre-zeroed by caller. */
 int gt_layernorm_bwd(int dt, const void* dy, const void* presum, const float* mean_rstd,
                      const int32_t* out_rows, int64_t M, int32_t d, const float* gamma,
-                     void* dx, float* dgamma, float* dbeta, float* dcls, void* stream);
+                     void* dx, float* dgamma, float* dbeta, float* dcls, void* dx_drop, float drop_p,
+                     const uint64_t* rng_state, uint64_t salt, void* stream);
 /* plain row gather/scatter for tokens when no input LayerNorm is configured, and for the
  * public pad_batch API: dst[r,:] = src[rows[r],:] (rows<0 -> cls or zeros). */
 int gt_gather_rows(int dt, const void* src, const int32_t* rows, const float* cls, int64_t M,
@@ -208,12 +215,18 @@ int gt_pad_batch_bwd(int dt, const void* dpadded, const int32_t* node_off, const
  * NULL = tok_off[g].  out [n_rows, d]; lse fp32 [nhead, n_rows].  Dropout on the attention
  * probabilities (after softmax, as F.multi_head_attention_forward does) with drop_p/rng/salt.
  * impl: 0 auto, 1 CUDA-core, 2 tcgen05. */
+/* optional per-batch metadata for the tcgen05 kernels (computed once per step, reused by every layer and head):
+ * row_bounds int32 [n_rows][2] = key-row range [lo, hi) of every token row; tile_bounds int32 [ceil(n_rows/128)][2]
+ * = (first row, number of 128-row tiles) of the row range interacting with each 128-row tile.  NULL = derive in-kernel. */
+int gt_mha_meta(const int32_t* tok_graph, const int32_t* tok_off, int64_t n_rows, int64_t B,
+                int32_t* row_bounds, int32_t* tile_bounds, void* stream);
 int gt_mha_fwd(int dt, const void* qkv, const int32_t* tok_graph, const int32_t* tok_off,
-               const int32_t* key_start, int64_t n_rows, int64_t B, int32_t nhead, int32_t dh,
+               const int32_t* key_start, const int32_t* row_bounds, const int32_t* tile_bounds, int64_t n_rows, int64_t B, int32_t nhead, int32_t dh,
                float scale, void* out, float* lse, float drop_p, const uint64_t* rng_state,
                uint64_t salt, int impl, void* stream);
 int gt_mha_bwd(int dt, const void* qkv, const void* out, const void* dout, const float* lse,
                const int32_t* tok_graph, const int32_t* tok_off, const int32_t* key_start,
+               const int32_t* row_bounds, const int32_t* tile_bounds,
                int64_t n_rows, int64_t B, int32_t nhead, int32_t dh, float scale, void* dqkv,
                float* delta, float drop_p, const uint64_t* rng_state, uint64_t salt, int impl,
                void* stream);

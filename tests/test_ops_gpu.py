@@ -23,7 +23,7 @@ def test_gemm_layouts(dtype, a_mn, b_mn, M, N, K):
     ldc = (N + 7) // 8 * 8
     C = torch.full((M, ldc), 7.0, device="cuda", dtype=dtype)
     call("gt_gemm", dt_of(A), ptr(A), a_mn, A.shape[1], ptr(Bm), b_mn, Bm.shape[1], ptr(C), ldc, M, N, K, ldc,
-         ptr(bias), None, 0, EPI_RELU, ops.GEMM_IMPL)
+         ptr(bias), None, 0, EPI_RELU, 0.0, None, 0, ops.GEMM_IMPL)
     Af = (A.t() if a_mn else A).double()
     Bf = (Bm.t() if b_mn else Bm).double()
     ref = torch.relu(Af @ Bf.t() + bias.double())
@@ -38,7 +38,7 @@ def test_gemm_splitk_accumulate():
     Bm = torch.randn(K, N, device="cuda")
     C = torch.zeros(M, N, device="cuda")
     call("gt_gemm", 0, ptr(A), 1, M, ptr(Bm), 1, N, ptr(C), N, M, N, K, N, None, None, 0, EPI_ACCUM | EPI_OUT_F32,
-         ops.GEMM_IMPL)
+         0.0, None, 0, ops.GEMM_IMPL)
     assert rel_l2(C, A.double().t() @ Bm.double()) < 1e-5
 
 
@@ -202,7 +202,7 @@ def test_gemm_tcgen05_forced(a_mn, b_mn, M, N, K, out_f32):
     C = torch.full((M, N), 7.0, device="cuda", dtype=odt)
     flags = EPI_RELU | (EPI_OUT_F32 | _lib.EPI_RESID_F32 if out_f32 else 0)
     call("gt_gemm", 1, ptr(A), a_mn, A.shape[1], ptr(Bm), b_mn, Bm.shape[1], ptr(C), N, M, N, K, N, ptr(bias),
-         ptr(resid), N, flags, 2)
+         ptr(resid), N, flags, 0.0, None, 0, 2)
     Af = (A.t() if a_mn else A).double()
     Bf = (Bm.t() if b_mn else Bm).double()
     ref = torch.relu(Af @ Bf.t() + bias.double() + resid.double())
@@ -216,7 +216,7 @@ def test_gemm_tcgen05_splitk_weight_gradient(M, N, K):
     dY = torch.randn(K, M, device="cuda").bfloat16()
     X = torch.randn(K, N, device="cuda").bfloat16()
     C = torch.zeros(M, N, device="cuda")
-    call("gt_gemm", 1, ptr(dY), 1, M, ptr(X), 1, N, ptr(C), N, M, N, K, N, None, None, 0, EPI_ACCUM | EPI_OUT_F32, 2)
+    call("gt_gemm", 1, ptr(dY), 1, M, ptr(X), 1, N, ptr(C), N, M, N, K, N, None, None, 0, EPI_ACCUM | EPI_OUT_F32, 0.0, None, 0, 2)
     ref = dY.double().t() @ X.double()
     assert rel_l2(C, ref) < 1e-4
 
@@ -227,7 +227,7 @@ def _mha_raw(qkv, plan, nhead, impl, drop_p=0.0, salt=0):
     dh = d // nhead
     out = torch.empty(n, d, dtype=qkv.dtype, device="cuda")
     lse = torch.empty(nhead * n, dtype=torch.float32, device="cuda")
-    call("gt_mha_fwd", dt_of(qkv), ptr(qkv), ptr(plan.tok_graph), ptr(plan.tok_off), None, n, plan.B, nhead, dh,
+    call("gt_mha_fwd", dt_of(qkv), ptr(qkv), ptr(plan.tok_graph), ptr(plan.tok_off), None, None, None, n, plan.B, nhead, dh,
          dh ** -0.5, ptr(out), ptr(lse), drop_p, ptr(ops.rng_state("cuda")) if drop_p else None, salt, impl)
     return out, lse
 
@@ -274,7 +274,7 @@ def _mha_bwd_raw(qkv, out, dout, lse, plan, nhead, impl, drop_p=0.0, salt=0):
     dqkv = torch.full_like(qkv, float("nan"))
     delta = torch.empty(nhead * n, dtype=torch.float32, device="cuda")
     call("gt_mha_bwd", dt_of(qkv), ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(plan.tok_graph), ptr(plan.tok_off), None,
-         n, plan.B, nhead, dh, dh ** -0.5, ptr(dqkv), ptr(delta), drop_p,
+         None, None, n, plan.B, nhead, dh, dh ** -0.5, ptr(dqkv), ptr(delta), drop_p,
          ptr(ops.rng_state("cuda")) if drop_p else None, salt, impl)
     return dqkv
 
@@ -309,3 +309,73 @@ def test_mha_tcgen05_backward(nhead, dh, lens, drop_p):
         for blk in range(3):
             a, b = dq2[:off[-1], blk * d:(blk + 1) * d], q64.grad[:off[-1], blk * d:(blk + 1) * d]
             assert rel_l2(a, b) < 2e-2, blk
+
+
+@pytest.mark.parametrize("impl,dtype", [(1, torch.float32), (1, torch.bfloat16), (2, torch.bfloat16)])
+def test_gemm_epilogue_dropout_matches_standalone_mask(impl, dtype):
+    """drop(relu(x W^T + b)) in the GEMM epilogue uses the same (vector index -> keep) map as gt_dropout on the
+    output matrix, on the CUDA-core and on both tcgen05 epilogue paths; linear() backward re-derives it from y == 0"""
+    torch.manual_seed(0)
+    M, N, K, p = 300, 136, 64, 0.3
+    ops.manual_seed(17)
+    ops.begin_step("cuda")
+    x = torch.randn(M, K, device="cuda").to(dtype)
+    w = torch.randn(N, K, device="cuda").to(dtype)
+    b = torch.randn(N, device="cuda")
+    y_ref = torch.empty(M, N, device="cuda", dtype=dtype)
+    call("gt_gemm", dt_of(x), ptr(x), 0, K, ptr(w), 0, K, ptr(y_ref), N, M, N, K, N, ptr(b), None, 0, EPI_RELU, 0.0, None, 0, impl)
+    want = torch.empty_like(y_ref)
+    call("gt_dropout", dt_of(y_ref), ptr(y_ref), y_ref.numel(), ptr(want), p, ptr(ops.rng_state("cuda")), 5)
+    got = torch.empty_like(y_ref)
+    call("gt_gemm", dt_of(x), ptr(x), 0, K, ptr(w), 0, K, ptr(got), N, M, N, K, N, ptr(b), None, 0, EPI_RELU, p,
+         ptr(ops.rng_state("cuda")), 5, impl)
+    assert rel_l2(got, want.double()) < (1e-6 if dtype == torch.float32 else 1e-2)
+    assert ((got == 0) == (want == 0)).all()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_linear_relu_dropout_and_layernorm_dropout_autograd(dtype):
+    """fused dropout sites of the transformer layer against torch autograd with the recovered masks"""
+    torch.manual_seed(1)
+    ops.set_precision("fp32" if dtype == torch.float32 else "bf16")
+    try:
+        M, d, f, p = 200, 64, 128, 0.25
+        ops.manual_seed(3)
+        ops.begin_step("cuda")
+        x = torch.randn(M, d, device="cuda").to(dtype).requires_grad_(True)
+        w1 = torch.randn(f, d, device="cuda", requires_grad=True)
+        b1 = torch.randn(f, device="cuda", requires_grad=True)
+        ln = torch.nn.LayerNorm(d).cuda()
+        a = torch.randn(M, d, device="cuda").to(dtype).requires_grad_(True)
+        h = ops.linear(x, w1, b1, relu=True, drop_p=p)
+        y = ops.layer_norm(a, ln, resid=x, drop_p=p)
+        gh, gy = torch.randn_like(h), torch.randn_like(y)
+        (h.float() * gh.float()).sum().backward(retain_graph=True)
+        gx_h, gw1 = x.grad.clone(), w1.grad.clone()
+        x.grad = None
+        (y.float() * gy.float()).sum().backward()
+        # reference with masks recovered from the outputs
+        xr = x.detach().double().requires_grad_(True)
+        w1r, b1r = w1.detach().double().requires_grad_(True), b1.detach().double()
+        pre = torch.relu(xr @ (w1r.to(dtype).double() if dtype != torch.float32 else w1r).t() + b1r)
+        mask_h = (h.detach() != 0) | (pre.detach() == 0)
+        href = pre * mask_h / (1 - p)
+        (href * gh.double()).sum().backward()
+        tol = 1e-5 if dtype == torch.float32 else 2e-2
+        assert rel_l2(h.detach(), href.detach()) < tol
+        assert rel_l2(gx_h, xr.grad) < tol and rel_l2(gw1, w1r.grad) < tol
+        pos = pre.detach() > 0
+        keep = abs((h.detach() != 0)[pos].double().mean().item() - (1 - p))
+        assert keep < 0.03
+        # layer norm: recover the mask of `a` from the gradient (d a = d presum * mask / (1-p))
+        ar = a.detach().double().requires_grad_(True)
+        xr2 = x.detach().double().requires_grad_(True)
+        ratio = (a.grad.double() / x.grad.double())
+        mask_a = ratio.abs() > 0.5
+        yref = torch.nn.functional.layer_norm(ar * mask_a / (1 - p) + xr2, (d,), ln.weight.double(), ln.bias.double())
+        (yref * gy.double()).sum().backward()
+        assert rel_l2(y.detach(), yref.detach()) < tol
+        assert rel_l2(a.grad, ar.grad) < tol and rel_l2(x.grad, xr2.grad) < tol
+        assert abs(mask_a.double().mean().item() - (1 - p)) < 0.03
+    finally:
+        ops.set_precision("fp32")

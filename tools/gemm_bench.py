@@ -20,7 +20,7 @@ def bench(name, M, N, K, a_mn, b_mn, flags=0, reps=50):
     C = torch.zeros(M, ldc, device="cuda", dtype=torch.float32 if out_f32 else torch.bfloat16)
     bias = torch.randn(N, device="cuda") if not (flags & EPI_ACCUM) else None
     def run():
-        call("gt_gemm", 1, ptr(A), a_mn, lda, ptr(B), b_mn, ldb, ptr(C), ldc, M, N, K, ldc, ptr(bias), None, 0, flags, 2)
+        call("gt_gemm", 1, ptr(A), a_mn, lda, ptr(B), b_mn, ldb, ptr(C), ldc, M, N, K, ldc, ptr(bias), None, 0, flags, 0.0, None, 0, 2)
     for _ in range(5): run()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
