@@ -63,15 +63,21 @@ struct AttnParams {
     float scale_log2, drop_p;
 };
 
+// Forward, two-phase ("max first") streaming softmax.  Phase 1 streams the key tiles once and only takes the row
+// maxima of S = Q K^T; phase 2 streams them again, forms P = exp2(S * scale*log2e - m) with the FINAL maximum and
+// accumulates O += P V directly in TMEM.  With the maximum known up front there is no running rescale: the output
+// accumulator never leaves TMEM until the end, the softmax threads never wait for the P V MMA, and S is released as
+// soon as it sits in registers so that the next Q K^T overlaps the exponentials.  The extra Q K^T costs tensor-core
+// time that is idle anyway (this kernel is bound by the softmax threads, not by the MMAs).
 template <int DH>
 __global__ void __launch_bounds__(ATT_THREADS)
 k_mha_tc_fwd(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p) {
     constexpr int PITCH = DH * 2;                 // bytes per operand row
     constexpr int TILE = 128 * PITCH;             // Q / K / V tile bytes
     constexpr int KST = 2, VST = (DH == 64 ? 1 : 2);
-    constexpr uint32_t TMEM_COLS = 256;           // S: [0,128), O_j: [128, 128+DH)
+    constexpr uint32_t TMEM_COLS = 256;           // S: [0,128), O: [128, 128+DH)
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t q_full, k_full[KST], k_empty[KST], v_full[VST], v_empty[VST], s_full, p_full, o_full;
+    __shared__ uint64_t q_full, k_full[KST], k_empty[KST], v_full[VST], v_empty[VST], s_full, s_free, p_full, p_empty, o_full;
     __shared__ uint32_t tmem_base_s;
     __shared__ int kv_lo_s, nkv_s;
 
@@ -85,7 +91,9 @@ k_mha_tc_fwd(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p) {
         for (int s = 0; s < KST; ++s) mbar_init(&k_full[s], 1), mbar_init(&k_empty[s], 1);
         for (int s = 0; s < VST; ++s) mbar_init(&v_full[s], 1), mbar_init(&v_empty[s], 1);
         mbar_init(&s_full, 1);
+        mbar_init(&s_free, 128);
         mbar_init(&p_full, 128);
+        mbar_init(&p_empty, 1);
         mbar_init(&o_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_async_smem();
@@ -116,41 +124,62 @@ k_mha_tc_fwd(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p) {
     const int kv_lo = kv_lo_s, nkv = nkv_s;
 
     if (warp == 0) {
-        if (lane == 0 && nkv > 0) {  // ===== TMA producer =====
+        if (lane == 0 && nkv > 0) {  // ===== TMA producer: K tiles twice (phase 1, phase 2), V tiles in phase 2 =====
             mbar_expect_tx(&q_full, TILE);
             tma_load_2d(q_s, &tma_qkv, &q_full, h * DH, q0);
-            for (int j = 0; j < nkv; ++j) {
-                const int ks = j % KST, vs = j % VST;
-                mbar_wait(&k_empty[ks], ((uint32_t)(j / KST) & 1u) ^ 1u);
+            for (int it = 0; it < 2 * nkv; ++it) {
+                const int j = it < nkv ? it : it - nkv;
+                const int ks = it % KST;
+                mbar_wait(&k_empty[ks], ((uint32_t)(it / KST) & 1u) ^ 1u);
                 mbar_expect_tx(&k_full[ks], TILE);
                 tma_load_2d(k_s + ks * TILE, &tma_qkv, &k_full[ks], p.d + h * DH, kv_lo + j * BKV);
-                mbar_wait(&v_empty[vs], ((uint32_t)(j / VST) & 1u) ^ 1u);
-                mbar_expect_tx(&v_full[vs], TILE);
-                tma_load_2d(v_s + vs * TILE, &tma_qkv, &v_full[vs], 2 * p.d + h * DH, kv_lo + j * BKV);
+                if (it >= nkv) {
+                    const int vs = j % VST;
+                    mbar_wait(&v_empty[vs], ((uint32_t)(j / VST) & 1u) ^ 1u);
+                    mbar_expect_tx(&v_full[vs], TILE);
+                    tma_load_2d(v_s + vs * TILE, &tma_qkv, &v_full[vs], 2 * p.d + h * DH, kv_lo + j * BKV);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0 && nkv > 0) {  // ===== MMA issuer =====
             const uint32_t id_s = idesc_f16(false, false, BQ, BKV);   // S = Q K^T   : A, B K-major (k = dh)
-            const uint32_t id_o = idesc_f16(false, true, BQ, DH);     // O = P V     : A K-major (k = key), B MN-major
+            const uint32_t id_o = idesc_f16(false, true, BQ, DH);     // O += P V    : A K-major (k = key), B MN-major
             mbar_wait(&q_full, 0);
-            for (int j = 0; j < nkv; ++j) {
-                const int ks = j % KST, vs = j % VST;
-                mbar_wait(&k_full[ks], (uint32_t)(j / KST) & 1u);
+            for (int it = 0; it < 2 * nkv; ++it) {
+                const int ks = it % KST;
+                mbar_wait(&k_full[ks], (uint32_t)(it / KST) & 1u);
+                if (it > 0) mbar_wait(&s_free, (uint32_t)(it - 1) & 1u);   // previous S sits in the softmax registers
                 tc_fence_after();
 #pragma unroll
                 for (int k = 0; k < DH / 16; ++k)
                     umma_f16(tmem, desc_k(q_s + k * 32, PITCH), desc_k(k_s + ks * TILE + k * 32, PITCH), id_s, k > 0);
                 umma_commit(&k_empty[ks]);
                 umma_commit(&s_full);
-                mbar_wait(&p_full, (uint32_t)j & 1u);      // P_j is in smem and S_j has been consumed
-                mbar_wait(&v_full[vs], (uint32_t)(j / VST) & 1u);
+                // P V of the previous phase-2 tile: issued after the next Q K^T so the softmax threads get S first
+                const int jp = it - nkv - 1;
+                if (jp >= 0) {
+                    const int vs = jp % VST;
+                    mbar_wait(&p_full, (uint32_t)jp & 1u);
+                    mbar_wait(&v_full[vs], (uint32_t)(jp / VST) & 1u);
+                    tc_fence_after();
+#pragma unroll
+                    for (int k = 0; k < BKV / 16; ++k)
+                        umma_f16(tmem + 128, desc_k(p_s + (k >> 2) * 16384 + (k & 3) * 32, 128),
+                                 desc_mn(v_s + vs * TILE + k * 16 * PITCH, PITCH), id_o, (jp > 0 || k > 0));
+                    umma_commit(&v_empty[vs]);
+                    umma_commit(&p_empty);
+                }
+            }
+            {   // P V of the last tile
+                const int jp = nkv - 1, vs = jp % VST;
+                mbar_wait(&p_full, (uint32_t)jp & 1u);
+                mbar_wait(&v_full[vs], (uint32_t)(jp / VST) & 1u);
                 tc_fence_after();
 #pragma unroll
                 for (int k = 0; k < BKV / 16; ++k)
                     umma_f16(tmem + 128, desc_k(p_s + (k >> 2) * 16384 + (k & 3) * 32, 128),
-                             desc_mn(v_s + vs * TILE + k * 16 * PITCH, PITCH), id_o, k > 0);
-                umma_commit(&v_empty[vs]);
+                             desc_mn(v_s + vs * TILE + k * 16 * PITCH, PITCH), id_o, (jp > 0 || k > 0));
                 umma_commit(&o_full);
             }
         }
@@ -171,81 +200,93 @@ k_mha_tc_fwd(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p) {
         }
         const Drop dr = make_drop(p.rng, p.salt, p.drop_p);
         const uint32_t rk = drop_row_key(dr, att_row_id_tc(h, row, p.n_rows));
-        // key range any row of this WARP can see: 16-key chunks outside it are skipped (graphs are short compared
-        // with the 128-key tile in the molecule workloads, so most chunks of a tile are fully masked)
+        // key range any row of this WARP can see: 32-key groups outside it are skipped (graphs are short compared
+        // with the 128-key tile in the molecule workloads, so most of a tile is fully masked for a given warp)
         const int wlo = __reduce_min_sync(0xffffffffu, hi > lo ? lo : 0x7fffffff);
         const int whi = __reduce_max_sync(0xffffffffu, hi > lo ? hi : 0);
-        float m = -INFINITY, l = 0.f;
-        float o[DH];
-#pragma unroll
-        for (int i = 0; i < DH; ++i) o[i] = 0.f;
+        // ---- phase 1: row maxima
+        float m = -INFINITY;
         for (int j = 0; j < nkv; ++j) {
             const int kv0 = kv_lo + j * BKV;
             mbar_wait(&s_full, (uint32_t)j & 1u);
             tc_fence_after();
-            // pass 1: row maximum over the valid keys of this tile
-            float mt = -INFINITY;
 #pragma unroll 1
-            for (int c = 0; c < BKV; c += 16) {
-                if (kv0 + c + 16 <= wlo || kv0 + c >= whi) continue;   // warp-uniform
-                uint32_t rr[16];
-                tmem_ld16(t_lane + c, rr);
+            for (int c = 0; c < BKV; c += 32) {
+                if (kv0 + c + 32 <= wlo || kv0 + c >= whi) continue;   // warp-uniform
+                uint32_t rr[32];
+                tmem_ld32(t_lane + c, rr);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
+                for (int i = 0; i < 32; ++i) {
                     const int key = kv0 + c + i;
-                    if (key >= lo && key < hi) mt = fmaxf(mt, __uint_as_float(rr[i]));
+                    if (key >= lo && key < hi) m = fmaxf(m, __uint_as_float(rr[i]));
                 }
             }
-            const float m_new = fmaxf(m, mt * p.scale_log2);
-            const float corr = (m_new == -INFINITY) ? 1.f : exp2f(m - m_new);
-            const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-            // pass 2: probabilities -> P (bf16, swizzled K-major smem), row sum
-            float lt = 0.f;
+            tc_fence_before();
+            mbar_arrive(&s_free);
+        }
+        const float m_use = (m == -INFINITY) ? 0.f : m * p.scale_log2;
+        // ---- phase 2: probabilities with the final maximum; O accumulates in TMEM
+        float l = 0.f;
+        for (int j = 0; j < nkv; ++j) {
+            const int kv0 = kv_lo + j * BKV;
+            mbar_wait(&s_full, (uint32_t)(nkv + j) & 1u);
+            tc_fence_after();
+            if (j > 0) mbar_wait(&p_empty, (uint32_t)(j - 1) & 1u);   // P V of the previous tile has read the P buffer
 #pragma unroll 1
-            for (int c = 0; c < BKV; c += 16) {
-                if (kv0 + c + 16 <= wlo || kv0 + c >= whi) {              // fully masked for this warp: P = 0
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(p_s + p_chunk_off(r, c)), "r"(0u) : "memory");
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(p_s + p_chunk_off(r, c + 8)), "r"(0u) : "memory");
+            for (int c = 0; c < BKV; c += 32) {
+                if (kv0 + c + 32 <= wlo || kv0 + c >= whi) {           // fully masked for this warp: P = 0
+#pragma unroll
+                    for (int i = 0; i < 32; i += 8)
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(p_s + p_chunk_off(r, c + i)), "r"(0u) : "memory");
                     continue;
                 }
-                uint32_t rr[16];
-                tmem_ld16(t_lane + c, rr);
-                float pv[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int key = kv0 + c + i;
-                    const bool valid = key >= lo && key < hi;
-                    float e = valid ? exp2f(fmaf(__uint_as_float(rr[i]), p.scale_log2, -m_use)) : 0.f;
-                    lt += e;
-                    if (dr.on && valid) e *= drop_elem(dr, rk, (uint32_t)key);
-                    pv[i] = e;
+                uint32_t rr[32];
+                tmem_ld32(t_lane + c, rr);
+                if (c + 32 >= BKV || kv0 + c + 32 >= whi) {            // last group this warp reads: S may be overwritten
+                    tc_fence_before();
+                    mbar_arrive(&s_free);
                 }
 #pragma unroll
-                for (int i = 0; i < 16; i += 8) {
-                    __nv_bfloat162 h0 = __floats2bfloat162_rn(pv[i], pv[i + 1]), h1 = __floats2bfloat162_rn(pv[i + 2], pv[i + 3]);
-                    __nv_bfloat162 h2 = __floats2bfloat162_rn(pv[i + 4], pv[i + 5]), h3 = __floats2bfloat162_rn(pv[i + 6], pv[i + 7]);
-                    const uint32_t a = p_s + p_chunk_off(r, c + i);
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(*reinterpret_cast<uint32_t*>(&h0)),
-                                 "r"(*reinterpret_cast<uint32_t*>(&h1)), "r"(*reinterpret_cast<uint32_t*>(&h2)),
-                                 "r"(*reinterpret_cast<uint32_t*>(&h3)) : "memory");
+                for (int i0 = 0; i0 < 32; i0 += 8) {
+                    float pv[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int key = kv0 + c + i0 + i;
+                        const bool valid = key >= lo && key < hi;
+                        float e = valid ? exp2f(fmaf(__uint_as_float(rr[i0 + i]), p.scale_log2, -m_use)) : 0.f;
+                        l += e;
+                        if (dr.on && valid) e *= drop_elem(dr, rk, (uint32_t)key);
+                        pv[i] = e;
+                    }
+                    __nv_bfloat162 h0 = __floats2bfloat162_rn(pv[0], pv[1]), h1 = __floats2bfloat162_rn(pv[2], pv[3]);
+                    __nv_bfloat162 h2 = __floats2bfloat162_rn(pv[4], pv[5]), h3 = __floats2bfloat162_rn(pv[6], pv[7]);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_s + p_chunk_off(r, c + i0)),
+                                 "r"(*reinterpret_cast<uint32_t*>(&h0)), "r"(*reinterpret_cast<uint32_t*>(&h1)),
+                                 "r"(*reinterpret_cast<uint32_t*>(&h2)), "r"(*reinterpret_cast<uint32_t*>(&h3)) : "memory");
                 }
             }
-            l = l * corr + lt;
-            m = m_new;
+            if (kv0 >= whi || kv0 + BKV <= wlo) {   // this warp read nothing of the tile: it still owes the S release
+                tc_fence_before();
+                mbar_arrive(&s_free);
+            }
             fence_async_smem();      // generic-proxy smem writes -> visible to the tensor core (async proxy)
-            tc_fence_before();
             mbar_arrive(&p_full);
-            // accumulate this tile's P V
-            mbar_wait(&o_full, (uint32_t)j & 1u);
+        }
+        float o[DH];
+        if (nkv > 0) {
+            mbar_wait(&o_full, 0);
             tc_fence_after();
 #pragma unroll
-            for (int c = 0; c < DH; c += 16) {
-                uint32_t rr[16];
-                tmem_ld16(t_lane + 128 + c, rr);
+            for (int c = 0; c < DH; c += 32) {
+                uint32_t rr[32];
+                tmem_ld32(t_lane + 128 + c, rr);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) o[c + i] = fmaf(o[c + i], corr, __uint_as_float(rr[i]));
+                for (int i = 0; i < 32; ++i) o[c + i] = __uint_as_float(rr[i]);
             }
             tc_fence_before();
+        } else {
+#pragma unroll
+            for (int i = 0; i < DH; ++i) o[i] = 0.f;
         }
         if (row < p.n_rows) {
             const float inv = l > 0.f ? 1.f / l : 0.f;
@@ -259,7 +300,7 @@ k_mha_tc_fwd(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p) {
                 pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
                 *reinterpret_cast<uint4*>(op + i) = pk;
             }
-            p.lse[(int64_t)h * p.n_rows + row] = l > 0.f ? (m + log2f(l)) * LN2 : 0.f;
+            p.lse[(int64_t)h * p.n_rows + row] = l > 0.f ? (m_use + log2f(l)) * LN2 : 0.f;
         }
     }
     tc_fence_before();
