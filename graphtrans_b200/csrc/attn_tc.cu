@@ -23,7 +23,16 @@ __device__ __forceinline__ uint64_t att_row_id_tc(int h, int64_t q, int64_t n_ro
 
 namespace tc {
 
-constexpr int ATT_THREADS = 192;
+constexpr int ATT_THREADS = 192;          // backward kernels: TMA warp, MMA warp, 4 math warps
+constexpr int ATT_FWD_THREADS = 320;      // forward: TMA warp, MMA warp, 8 softmax warps (2 per TMEM lane group)
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 constexpr int BQ = 128, BKV = 128;
 constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
 
@@ -70,7 +79,7 @@ struct AttnParams {
 // soon as it sits in registers so that the next Q K^T overlaps the exponentials.  The extra Q K^T costs tensor-core
 // time that is idle anyway (this kernel is bound by the softmax threads, not by the MMAs).
 template <int DH>
-__global__ void __launch_bounds__(ATT_THREADS)
+__global__ void __launch_bounds__(ATT_FWD_THREADS, 2)
 k_mha_tc_fwd(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p) {
     constexpr int PITCH = DH * 2;                 // bytes per operand row
     constexpr int TILE = 128 * PITCH;             // Q / K / V tile bytes
@@ -80,6 +89,7 @@ k_mha_tc_fwd(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p) {
     __shared__ uint64_t q_full, k_full[KST], k_empty[KST], v_full[VST], v_empty[VST], s_full, s_free, p_full, p_empty, o_full;
     __shared__ uint32_t tmem_base_s;
     __shared__ int kv_lo_s, nkv_s;
+    __shared__ float xchg[2][128];                // row max / row sum exchange between the two column halves
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * BQ, h = blockIdx.y;
@@ -91,8 +101,8 @@ k_mha_tc_fwd(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p) {
         for (int s = 0; s < KST; ++s) mbar_init(&k_full[s], 1), mbar_init(&k_empty[s], 1);
         for (int s = 0; s < VST; ++s) mbar_init(&v_full[s], 1), mbar_init(&v_empty[s], 1);
         mbar_init(&s_full, 1);
-        mbar_init(&s_free, 128);
-        mbar_init(&p_full, 128);
+        mbar_init(&s_free, 256);
+        mbar_init(&p_full, 256);
         mbar_init(&p_empty, 1);
         mbar_init(&o_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -183,11 +193,14 @@ k_mha_tc_fwd(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p) {
                 umma_commit(&o_full);
             }
         }
-    } else {  // ===== softmax warps: one thread per query row =====
-        const int qd = warp & 3;
+    } else {  // ===== softmax warps 2..9: thread = (query row, half of the 128 key columns of every tile) =====
+        // Two warps share a TMEM lane group (= 32 query rows) and split the key columns of each tile; with the
+        // two-phase scheme they only have to meet twice: once to combine the row maxima, once for the row sums.
+        const int qd = warp & 3, half = (warp - 2) >> 2;
         const int r = qd * 32 + lane;              // row inside the tile = TMEM lane
         const int64_t row = (int64_t)q0 + r;
         const uint32_t t_lane = tmem + ((uint32_t)(qd * 32) << 16);
+        const int cb = half * 64;                  // this warp's columns: [cb, cb + 64) of every key tile
         int lo = 0, hi = 0;
         if (row < p.n_rows) {
             if (p.row_bounds) {
@@ -211,20 +224,28 @@ k_mha_tc_fwd(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p) {
             mbar_wait(&s_full, (uint32_t)j & 1u);
             tc_fence_after();
 #pragma unroll 1
-            for (int c = 0; c < BKV; c += 32) {
+            for (int c = cb; c < cb + 64; c += 32) {
                 if (kv0 + c + 32 <= wlo || kv0 + c >= whi) continue;   // warp-uniform
                 uint32_t rr[32];
                 tmem_ld32(t_lane + c, rr);
+                const int k0 = kv0 + c;
+                if (k0 >= lo && k0 + 32 <= hi) {                        // whole group valid for this row
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int key = kv0 + c + i;
-                    if (key >= lo && key < hi) m = fmaxf(m, __uint_as_float(rr[i]));
+                    for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(rr[i]));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (k0 + i >= lo && k0 + i < hi) m = fmaxf(m, __uint_as_float(rr[i]));
                 }
             }
             tc_fence_before();
             mbar_arrive(&s_free);
         }
+        xchg[half][r] = m;
+        named_bar_sync(1, 256);
+        m = fmaxf(xchg[0][r], xchg[1][r]);
         const float m_use = (m == -INFINITY) ? 0.f : m * p.scale_log2;
+        named_bar_sync(1, 256);                     // xchg is reused for the row sums
         // ---- phase 2: probabilities with the final maximum; O accumulates in TMEM
         float l = 0.f;
         for (int j = 0; j < nkv; ++j) {
@@ -233,30 +254,49 @@ k_mha_tc_fwd(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p) {
             tc_fence_after();
             if (j > 0) mbar_wait(&p_empty, (uint32_t)(j - 1) & 1u);   // P V of the previous tile has read the P buffer
 #pragma unroll 1
-            for (int c = 0; c < BKV; c += 32) {
+            for (int c = cb; c < cb + 64; c += 32) {
+                const bool last = c + 32 >= cb + 64;
                 if (kv0 + c + 32 <= wlo || kv0 + c >= whi) {           // fully masked for this warp: P = 0
 #pragma unroll
                     for (int i = 0; i < 32; i += 8)
                         asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(p_s + p_chunk_off(r, c + i)), "r"(0u) : "memory");
+                    if (last) {
+                        tc_fence_before();
+                        mbar_arrive(&s_free);
+                    }
                     continue;
                 }
                 uint32_t rr[32];
                 tmem_ld32(t_lane + c, rr);
-                if (c + 32 >= BKV || kv0 + c + 32 >= whi) {            // last group this warp reads: S may be overwritten
+                if (last) {                                            // this thread's share of S sits in registers
                     tc_fence_before();
                     mbar_arrive(&s_free);
                 }
 #pragma unroll
                 for (int i0 = 0; i0 < 32; i0 += 8) {
                     float pv[8];
+                    const int k0 = kv0 + c + i0;
+                    if (k0 >= lo && k0 + 8 <= hi) {                    // 8 valid keys: no per-element masking
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int key = kv0 + c + i0 + i;
-                        const bool valid = key >= lo && key < hi;
-                        float e = valid ? exp2f(fmaf(__uint_as_float(rr[i0 + i]), p.scale_log2, -m_use)) : 0.f;
-                        l += e;
-                        if (dr.on && valid) e *= drop_elem(dr, rk, (uint32_t)key);
-                        pv[i] = e;
+                        for (int i = 0; i < 8; ++i) {
+                            float e = ex2_approx(fmaf(__uint_as_float(rr[i0 + i]), p.scale_log2, -m_use));
+                            l += e;
+                            if (dr.on) e *= drop_elem(dr, rk, (uint32_t)(k0 + i));
+                            pv[i] = e;
+                        }
+                    } else if (k0 + 8 <= lo || k0 >= hi) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) pv[i] = 0.f;
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int key = k0 + i;
+                            const bool valid = key >= lo && key < hi;
+                            float e = valid ? ex2_approx(fmaf(__uint_as_float(rr[i0 + i]), p.scale_log2, -m_use)) : 0.f;
+                            l += e;
+                            if (dr.on && valid) e *= drop_elem(dr, rk, (uint32_t)key);
+                            pv[i] = e;
+                        }
                     }
                     __nv_bfloat162 h0 = __floats2bfloat162_rn(pv[0], pv[1]), h1 = __floats2bfloat162_rn(pv[2], pv[3]);
                     __nv_bfloat162 h2 = __floats2bfloat162_rn(pv[4], pv[5]), h3 = __floats2bfloat162_rn(pv[6], pv[7]);
@@ -265,34 +305,39 @@ k_mha_tc_fwd(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p) {
                                  "r"(*reinterpret_cast<uint32_t*>(&h2)), "r"(*reinterpret_cast<uint32_t*>(&h3)) : "memory");
                 }
             }
-            if (kv0 >= whi || kv0 + BKV <= wlo) {   // this warp read nothing of the tile: it still owes the S release
-                tc_fence_before();
-                mbar_arrive(&s_free);
-            }
             fence_async_smem();      // generic-proxy smem writes -> visible to the tensor core (async proxy)
             mbar_arrive(&p_full);
         }
-        float o[DH];
+        xchg[half][r] = l;
+        named_bar_sync(1, 256);
+        l = xchg[0][r] + xchg[1][r];
+        // ---- output: each of the two warps of a lane group normalises and stores half of the head dimension
+        constexpr int OC = DH / 2;
+        float o[OC];
         if (nkv > 0) {
             mbar_wait(&o_full, 0);
             tc_fence_after();
-#pragma unroll
-            for (int c = 0; c < DH; c += 32) {
+            if (OC == 32) {
                 uint32_t rr[32];
-                tmem_ld32(t_lane + 128 + c, rr);
+                tmem_ld32(t_lane + 128 + half * OC, rr);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) o[c + i] = __uint_as_float(rr[i]);
+                for (int i = 0; i < OC; ++i) o[i] = __uint_as_float(rr[i]);
+            } else {
+                uint32_t rr[16];
+                tmem_ld16(t_lane + 128 + half * OC, rr);
+#pragma unroll
+                for (int i = 0; i < OC; ++i) o[i] = __uint_as_float(rr[i]);
             }
             tc_fence_before();
         } else {
 #pragma unroll
-            for (int i = 0; i < DH; ++i) o[i] = 0.f;
+            for (int i = 0; i < OC; ++i) o[i] = 0.f;
         }
         if (row < p.n_rows) {
             const float inv = l > 0.f ? 1.f / l : 0.f;
-            bf16* op = (bf16*)p.out + row * p.d + h * DH;
+            bf16* op = (bf16*)p.out + row * p.d + h * DH + half * OC;
 #pragma unroll
-            for (int i = 0; i < DH; i += 8) {
+            for (int i = 0; i < OC; i += 8) {
                 uint4 pk;
                 __nv_bfloat162 h0 = __floats2bfloat162_rn(o[i] * inv, o[i + 1] * inv), h1 = __floats2bfloat162_rn(o[i + 2] * inv, o[i + 3] * inv);
                 __nv_bfloat162 h2 = __floats2bfloat162_rn(o[i + 4] * inv, o[i + 5] * inv), h3 = __floats2bfloat162_rn(o[i + 6] * inv, o[i + 7] * inv);
@@ -300,7 +345,7 @@ k_mha_tc_fwd(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p) {
                 pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
                 *reinterpret_cast<uint4*>(op + i) = pk;
             }
-            p.lse[(int64_t)h * p.n_rows + row] = l > 0.f ? (m_use + log2f(l)) * LN2 : 0.f;
+            if (half == 0) p.lse[(int64_t)h * p.n_rows + row] = l > 0.f ? (m_use + log2f(l)) * LN2 : 0.f;
         }
     }
     tc_fence_before();
@@ -322,7 +367,7 @@ static cudaError_t launch_fwd(const CUtensorMap& map, const AttnParams& p, cudaS
         attr = true;
     }
     dim3 grid((unsigned)((p.n_rows + BQ - 1) / BQ), (unsigned)p.nhead);
-    k_mha_tc_fwd<DH><<<grid, ATT_THREADS, smem, st>>>(map, p);
+    k_mha_tc_fwd<DH><<<grid, ATT_FWD_THREADS, smem, st>>>(map, p);
     return cudaGetLastError();
 }
 
@@ -386,37 +431,51 @@ struct AttnBwdParams {
     float scale, scale_log2, drop_p;
 };
 
-// FlashAttention-2 style recompute backward.  S = Q K^T and dP = dO V^T are formed with query rows on the TMEM
-// lanes (thread = query row) in both modes:
-//   DKV = false : the CTA owns a 128-row QUERY tile (Q, dO resident), streams the key tiles (K, V) and
-//                 accumulates dQ += dS K                                     (A = dS K-major from smem, B = K MN-major)
-//   DKV = true  : the CTA owns a 128-row KEY tile (K, V resident), streams the query tiles (Q, dO) and
-//                 accumulates dV += P^T dO, dK += dS^T Q                     (A = P|dS MN-major from smem, B MN-major)
-// with P = exp2(S*scale*log2e - lse*log2e), dS = P o (dP*keep - delta).
+// FlashAttention-2 style recompute backward in two kernels that share one body.  The CTA OWNS 128 rows (their
+// accumulators live on the 128 TMEM lanes, thread = owned row) and STREAMS the interacting rows of the other kind in
+// tiles of 64:
+//   DKV = false : owns 128 QUERY rows (Q, dO resident), streams key tiles (K, V):
+//                   S  = Q K^T,  dP  = dO V^T   [128 q x 64 keys];   dQ += dS K
+//   DKV = true  : owns 128 KEY rows (K, V resident), streams query tiles (Q, dO), transposed formulation:
+//                   S^T = K Q^T, dP^T = V dO^T  [128 keys x 64 q];   dK += dS^T Q,  dV += P^T dO
+// with P = exp2(S*scale*log2e - lse*log2e), dS = P o (dP*keep - delta).  In both modes the per-element math tile
+// [128 owned x 64 streamed] is written as one 128B-swizzled K-major smem operand (k = streamed index) and the streamed
+// tile is the MN-major B operand of the accumulation MMA, so the two modes differ only in which index is the query.
+// TMEM: S 64 + dP 64 + 2 x 64 accumulator columns = 256, smem 96 KB -> two CTAs per SM.
+struct ColMeta {     // DKV mode: per streamed QUERY column
+    float lse2[64];
+    float delta[64];
+    uint32_t rk[64];
+};
+
 template <int DH, bool DKV>
-__global__ void __launch_bounds__(ATT_THREADS)
-k_mha_tc_bwd(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant__ CUtensorMap tma_do, const AttnBwdParams p) {
+__global__ void __launch_bounds__(ATT_THREADS, 2)
+k_mha_tc_bwd(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant__ CUtensorMap tma_do,
+             const __grid_constant__ CUtensorMap tma_qkv64, const __grid_constant__ CUtensorMap tma_do64, const AttnBwdParams p) {
     constexpr int PITCH = DH * 2;
-    constexpr int TILE = 128 * PITCH;
+    constexpr int TILE = 128 * PITCH;             // owned tile bytes
+    constexpr int STILE = 64 * PITCH;             // streamed tile bytes
     constexpr int STG = 2;
-    constexpr uint32_t TMEM_COLS = 512;           // S [0,128) | dP [128,256) | acc0 [256,256+DH) | acc1 [320,320+DH)
+    constexpr uint32_t TMEM_COLS = 256;           // S [0,64) | dP [64,128) | acc0 [128,128+DH) | acc1 [192,192+DH)
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t own_full, st_full[STG], st_empty[STG], sdp_full, pds_full, acc_done;
+    __shared__ uint64_t own_full, st_full[STG], st_empty[STG], sdp_full, sdp_free, pds_full, acc_done;
     __shared__ uint32_t tmem_base_s;
     __shared__ int st_lo_s, nst_s;
+    __shared__ ColMeta cmeta[2];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int t0 = blockIdx.x * 128, h = blockIdx.y;      // first row of the owned tile (query rows or key rows)
+    const int t0 = blockIdx.x * 128, h = blockIdx.y;      // first owned row (query rows or key rows)
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t own_x = base, own_y = own_x + TILE;    // dQ: Q, dO   | dKV: K, V
-    const uint32_t st_s = own_y + TILE;                   // ring: stage s -> X at st_s + 2*s*TILE, Y right after
-    const uint32_t ds_s = st_s + 2 * STG * TILE;          // dS  [128 q x 128 keys] bf16, two swizzled 64-key blocks
-    const uint32_t pp_s = ds_s + 32768;                   // P   (DKV only)
+    const uint32_t st_s = own_y + TILE;                   // ring: stage s -> X at st_s + 2*s*STILE, Y right after
+    const uint32_t ds_s = st_s + 2 * STG * STILE;         // dS (or dS^T) [128 x 64] bf16, one swizzled 16 KB block
+    const uint32_t pp_s = ds_s + 16384;                   // P^T (DKV only)
 
     if (threadIdx.x == 0) {
         mbar_init(&own_full, 1);
         for (int s = 0; s < STG; ++s) mbar_init(&st_full[s], 1), mbar_init(&st_empty[s], 1);
         mbar_init(&sdp_full, 1);
+        mbar_init(&sdp_free, 128);
         mbar_init(&pds_full, 128);
         mbar_init(&acc_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -434,7 +493,7 @@ k_mha_tc_bwd(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant_
             n = (p.tok_off[g1 + 1] - lo + 127) / 128;
         }
         st_lo_s = lo;
-        nst_s = n;
+        nst_s = 2 * n;      // 64-row streamed tiles
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(TMEM_COLS) : "memory");
@@ -460,129 +519,165 @@ k_mha_tc_bwd(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant_
             for (int t = 0; t < nst; ++t) {
                 const int s = t % STG;
                 mbar_wait(&st_empty[s], ((uint32_t)(t / STG) & 1u) ^ 1u);
-                mbar_expect_tx(&st_full[s], 2 * TILE);
-                const uint32_t x = st_s + 2 * s * TILE, y = x + TILE;
-                const int r0 = st_lo + t * 128;
+                mbar_expect_tx(&st_full[s], 2 * STILE);
+                const uint32_t x = st_s + 2 * s * STILE, y = x + STILE;
+                const int r0 = st_lo + t * 64;
                 if (!DKV) {
-                    tma_load_2d(x, &tma_qkv, &st_full[s], colK, r0);
-                    tma_load_2d(y, &tma_qkv, &st_full[s], colV, r0);
+                    tma_load_2d(x, &tma_qkv64, &st_full[s], colK, r0);
+                    tma_load_2d(y, &tma_qkv64, &st_full[s], colV, r0);
                 } else {
-                    tma_load_2d(x, &tma_qkv, &st_full[s], colQ, r0);
-                    tma_load_2d(y, &tma_do, &st_full[s], colQ, r0);
+                    tma_load_2d(x, &tma_qkv64, &st_full[s], colQ, r0);
+                    tma_load_2d(y, &tma_do64, &st_full[s], colQ, r0);
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0 && nst > 0) {  // ===== MMA issuer =====
-            const uint32_t id_s = idesc_f16(false, false, 128, 128);
-            const uint32_t id_acc = idesc_f16(DKV, true, 128, DH);
-            mbar_wait(&own_full, 0);
-            for (int t = 0; t < nst; ++t) {
+            const uint32_t id_s = idesc_f16(false, false, 128, 64);     // [128 owned x 64 streamed], k = dh
+            const uint32_t id_acc = idesc_f16(false, true, 128, DH);    // A = math tile K-major (k = streamed), B MN-major
+            auto issue_sdp = [&](int t) {
                 const int s = t % STG;
-                const uint32_t x = st_s + 2 * s * TILE, y = x + TILE;
-                const uint32_t q_a = DKV ? x : own_x, k_a = DKV ? own_x : x, do_a = DKV ? y : own_y, v_a = DKV ? own_y : y;
+                const uint32_t x = st_s + 2 * s * STILE, y = x + STILE;
                 mbar_wait(&st_full[s], (uint32_t)(t / STG) & 1u);
-                if (t > 0) mbar_wait(&acc_done, (uint32_t)(t - 1) & 1u);   // S/dP columns are free again
+                if (t > 0) mbar_wait(&sdp_free, (uint32_t)(t - 1) & 1u);   // previous S / dP sit in registers
                 tc_fence_after();
 #pragma unroll
                 for (int k = 0; k < DH / 16; ++k)
-                    umma_f16(tmem, desc_k(q_a + k * 32, PITCH), desc_k(k_a + k * 32, PITCH), id_s, k > 0);
+                    umma_f16(tmem, desc_k(own_x + k * 32, PITCH), desc_k(x + k * 32, PITCH), id_s, k > 0);
 #pragma unroll
                 for (int k = 0; k < DH / 16; ++k)
-                    umma_f16(tmem + 128, desc_k(do_a + k * 32, PITCH), desc_k(v_a + k * 32, PITCH), id_s, k > 0);
+                    umma_f16(tmem + 64, desc_k(own_y + k * 32, PITCH), desc_k(y + k * 32, PITCH), id_s, k > 0);
                 umma_commit(&sdp_full);
+            };
+            mbar_wait(&own_full, 0);
+            issue_sdp(0);
+            for (int t = 0; t < nst; ++t) {
+                if (t + 1 < nst) issue_sdp(t + 1);     // next S / dP run while the math warps work on tile t
+                const int s = t % STG;
+                const uint32_t x = st_s + 2 * s * STILE, y = x + STILE;
                 mbar_wait(&pds_full, (uint32_t)t & 1u);
                 tc_fence_after();
-                if (!DKV) {
 #pragma unroll
-                    for (int k = 0; k < 8; ++k)   // dQ += dS K : k = key
-                        umma_f16(tmem + 256, desc_k(ds_s + (k >> 2) * 16384 + (k & 3) * 32, 128),
-                                 desc_mn(k_a + k * 16 * PITCH, PITCH), id_acc, (t > 0 || k > 0));
-                } else {
+                for (int k = 0; k < 4; ++k)   // dQ += dS K   |   dK += dS^T Q      (k = streamed index)
+                    umma_f16(tmem + 128, desc_k(ds_s + k * 32, 128), desc_mn(x + k * 16 * PITCH, PITCH), id_acc, (t > 0 || k > 0));
+                if (DKV) {
 #pragma unroll
-                    for (int k = 0; k < 8; ++k)   // dK += dS^T Q : m = key, k = query row
-                        umma_f16(tmem + 256, desc_mnmajor(ds_s + k * 2048, 16384), desc_mn(q_a + k * 16 * PITCH, PITCH), id_acc,
-                                 (t > 0 || k > 0));
-#pragma unroll
-                    for (int k = 0; k < 8; ++k)   // dV += P^T dO
-                        umma_f16(tmem + 320, desc_mnmajor(pp_s + k * 2048, 16384), desc_mn(do_a + k * 16 * PITCH, PITCH), id_acc,
-                                 (t > 0 || k > 0));
+                    for (int k = 0; k < 4; ++k)   // dV += P^T dO
+                        umma_f16(tmem + 192, desc_k(pp_s + k * 32, 128), desc_mn(y + k * 16 * PITCH, PITCH), id_acc, (t > 0 || k > 0));
                 }
                 umma_commit(&st_empty[s]);
                 umma_commit(&acc_done);
             }
         }
-    } else {  // ===== math warps: thread = query row of the current (S, dP) tile =====
+    } else {  // ===== math warps: thread = owned row =====
         const int qd = warp & 3;
         const int r = qd * 32 + lane;
+        const int64_t orow = (int64_t)t0 + r;
         const uint32_t t_lane = tmem + ((uint32_t)(qd * 32) << 16);
         const Drop dr = make_drop(p.rng, p.salt, p.drop_p);
-        for (int t = 0; t < nst; ++t) {
-            const int64_t qrow = DKV ? (int64_t)st_lo + t * 128 + r : (int64_t)t0 + r;
-            const int kv0 = DKV ? t0 : st_lo + t * 128;
-            int lo = 0, hi = 0;
-            float lse2 = 0.f, dl = 0.f;
-            if (qrow < p.n_rows) {
-                if (p.row_bounds) {
-                    const int2 rb = p.row_bounds[qrow];
-                    lo = rb.x, hi = rb.y;
-                } else {
-                    const int g = p.tok_graph[qrow];
-                    if (g >= 0) lo = p.tok_off[g], hi = p.tok_off[g + 1];
-                }
-                if (hi > lo) {
-                    lse2 = p.lse[(int64_t)h * p.n_rows + qrow] * LOG2E;
-                    dl = p.delta[(int64_t)h * p.n_rows + qrow];
-                }
+        // owned row: its graph's row range [lo, hi) is both "the keys a query sees" and "the queries a key is seen by"
+        int lo = 0, hi = 0;
+        if (orow < p.n_rows) {
+            if (p.row_bounds) {
+                const int2 rb = p.row_bounds[orow];
+                lo = rb.x, hi = rb.y;
+            } else {
+                const int g = p.tok_graph[orow];
+                if (g >= 0) lo = p.tok_off[g], hi = p.tok_off[g + 1];
             }
-            const uint32_t rk = drop_row_key(dr, att_row_id_tc(h, qrow, p.n_rows));
-            const int wlo = __reduce_min_sync(0xffffffffu, hi > lo ? lo : 0x7fffffff);
-            const int whi = __reduce_max_sync(0xffffffffu, hi > lo ? hi : 0);
-            if (t > 0) mbar_wait(&acc_done, (uint32_t)(t - 1) & 1u);   // previous P / dS tiles have been consumed
+        }
+        float lse2 = 0.f, dl = 0.f;       // dQ mode: per owned query row
+        uint32_t rk = 0;
+        if (!DKV && hi > lo) {
+            lse2 = p.lse[(int64_t)h * p.n_rows + orow] * LOG2E;
+            dl = p.delta[(int64_t)h * p.n_rows + orow];
+            rk = drop_row_key(dr, att_row_id_tc(h, orow, p.n_rows));
+        }
+        const int wlo = __reduce_min_sync(0xffffffffu, hi > lo ? lo : 0x7fffffff);
+        const int whi = __reduce_max_sync(0xffffffffu, hi > lo ? hi : 0);
+        const int tid = threadIdx.x - 64;     // 0..127 among the math warps
+        for (int t = 0; t < nst; ++t) {
+            const int c0 = st_lo + t * 64;    // first streamed row of this tile
+            if (DKV) {                         // per-column query metadata of this tile
+                ColMeta& cm = cmeta[t & 1];
+                if (tid < 64) {
+                    const int64_t q = (int64_t)c0 + tid;
+                    float a = 0.f, b = 0.f;
+                    uint32_t k = 0;
+                    if (q < p.n_rows) {
+                        a = p.lse[(int64_t)h * p.n_rows + q] * LOG2E;
+                        b = p.delta[(int64_t)h * p.n_rows + q];
+                        k = drop_row_key(dr, att_row_id_tc(h, q, p.n_rows));
+                    }
+                    cm.lse2[tid] = a, cm.delta[tid] = b, cm.rk[tid] = k;
+                }
+                named_bar_sync(1, 128);
+            }
             mbar_wait(&sdp_full, (uint32_t)t & 1u);
             tc_fence_after();
+            if (t > 0) mbar_wait(&acc_done, (uint32_t)(t - 1) & 1u);   // previous dS / P tiles have been consumed
 #pragma unroll 1
-            for (int c = 0; c < 128; c += 16) {
-                if (kv0 + c + 16 <= wlo || kv0 + c >= whi) {   // fully masked for this warp (warp-uniform): dS = P = 0
+            for (int c = 0; c < 64; c += 32) {
+                const bool last = c == 32;
+                if (c0 + c + 32 <= wlo || c0 + c >= whi) {   // fully masked for this warp (warp-uniform): dS = P = 0
 #pragma unroll
-                    for (int i = 0; i < 16; i += 8) {
+                    for (int i = 0; i < 32; i += 8) {
                         const uint32_t off = p_chunk_off(r, c + i);
                         asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(ds_s + off), "r"(0u) : "memory");
                         if (DKV) asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(pp_s + off), "r"(0u) : "memory");
                     }
+                    if (last) {
+                        tc_fence_before();
+                        mbar_arrive(&sdp_free);
+                    }
                     continue;
                 }
-                uint32_t rs[16], rp[16];
-                tmem_ld16(t_lane + c, rs);
-                tmem_ld16(t_lane + 128 + c, rp);
-                float pv[16], dsv[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int key = kv0 + c + i;
-                    const bool valid = key >= lo && key < hi;
-                    float pr = valid ? exp2f(fmaf(__uint_as_float(rs[i]), p.scale_log2, -lse2)) : 0.f;
-                    float dp = __uint_as_float(rp[i]);
-                    if (dr.on && valid) {
-                        const float mk = drop_elem(dr, rk, (uint32_t)key);
-                        dp *= mk;
-                        dsv[i] = pr * (dp - dl);
-                        pr *= mk;
-                    } else {
-                        dsv[i] = valid ? pr * (dp - dl) : 0.f;
-                    }
-                    pv[i] = pr;
+                uint32_t rs[32], rp[32];
+                tmem_ld32(t_lane + c, rs);
+                tmem_ld32(t_lane + 64 + c, rp);
+                if (last) {
+                    tc_fence_before();
+                    mbar_arrive(&sdp_free);
                 }
 #pragma unroll
-                for (int i = 0; i < 16; i += 8) {
-                    const uint32_t off = p_chunk_off(r, c + i);
-                    __nv_bfloat162 h0 = __floats2bfloat162_rn(dsv[i], dsv[i + 1]), h1 = __floats2bfloat162_rn(dsv[i + 2], dsv[i + 3]);
-                    __nv_bfloat162 h2 = __floats2bfloat162_rn(dsv[i + 4], dsv[i + 5]), h3 = __floats2bfloat162_rn(dsv[i + 6], dsv[i + 7]);
+                for (int i0 = 0; i0 < 32; i0 += 8) {
+                    float pv[8], dsv[8];
+                    const int s0 = c0 + c + i0;          // streamed index of the first element of this group
+                    const bool all_in = s0 >= lo && s0 + 8 <= hi;
+                    if (!all_in && (s0 + 8 <= lo || s0 >= hi)) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) pv[i] = dsv[i] = 0.f;
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int sidx = s0 + i;
+                            const bool valid = all_in || (sidx >= lo && sidx < hi);
+                            const float l2 = DKV ? cmeta[t & 1].lse2[c + i0 + i] : lse2;
+                            const float de = DKV ? cmeta[t & 1].delta[c + i0 + i] : dl;
+                            float pr = valid ? ex2_approx(fmaf(__uint_as_float(rs[i0 + i]), p.scale_log2, -l2)) : 0.f;
+                            float dp = __uint_as_float(rp[i0 + i]);
+                            if (dr.on) {
+                                // mask element (query, key): dQ mode query = owned row, key = streamed; dKV the reverse
+                                const float mk = DKV ? drop_elem(dr, cmeta[t & 1].rk[c + i0 + i], (uint32_t)orow)
+                                                     : drop_elem(dr, rk, (uint32_t)sidx);
+                                dp *= mk;
+                                dsv[i] = pr * (dp - de);
+                                pr *= mk;
+                            } else {
+                                dsv[i] = pr * (dp - de);
+                            }
+                            pv[i] = pr;
+                        }
+                    }
+                    const uint32_t off = p_chunk_off(r, c + i0);
+                    __nv_bfloat162 h0 = __floats2bfloat162_rn(dsv[0], dsv[1]), h1 = __floats2bfloat162_rn(dsv[2], dsv[3]);
+                    __nv_bfloat162 h2 = __floats2bfloat162_rn(dsv[4], dsv[5]), h3 = __floats2bfloat162_rn(dsv[6], dsv[7]);
                     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ds_s + off), "r"(*reinterpret_cast<uint32_t*>(&h0)),
                                  "r"(*reinterpret_cast<uint32_t*>(&h1)), "r"(*reinterpret_cast<uint32_t*>(&h2)),
                                  "r"(*reinterpret_cast<uint32_t*>(&h3)) : "memory");
                     if (DKV) {
-                        h0 = __floats2bfloat162_rn(pv[i], pv[i + 1]), h1 = __floats2bfloat162_rn(pv[i + 2], pv[i + 3]);
-                        h2 = __floats2bfloat162_rn(pv[i + 4], pv[i + 5]), h3 = __floats2bfloat162_rn(pv[i + 6], pv[i + 7]);
+                        h0 = __floats2bfloat162_rn(pv[0], pv[1]), h1 = __floats2bfloat162_rn(pv[2], pv[3]);
+                        h2 = __floats2bfloat162_rn(pv[4], pv[5]), h3 = __floats2bfloat162_rn(pv[6], pv[7]);
                         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pp_s + off), "r"(*reinterpret_cast<uint32_t*>(&h0)),
                                      "r"(*reinterpret_cast<uint32_t*>(&h1)), "r"(*reinterpret_cast<uint32_t*>(&h2)),
                                      "r"(*reinterpret_cast<uint32_t*>(&h3)) : "memory");
@@ -590,27 +685,25 @@ k_mha_tc_bwd(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant_
                 }
             }
             fence_async_smem();
-            tc_fence_before();
             mbar_arrive(&pds_full);
         }
-        // epilogue: the accumulators' TMEM lanes are the owned tile's rows
-        const int64_t row = (int64_t)t0 + r;
+        // epilogue: the accumulators' TMEM lanes are the owned rows
         if (nst > 0) {
             mbar_wait(&acc_done, (uint32_t)(nst - 1) & 1u);
             tc_fence_after();
         }
-        bf16* gp = (bf16*)p.dqkv + row * (int64_t)(3 * p.d);
+        bf16* gp = (bf16*)p.dqkv + orow * (int64_t)(3 * p.d);
 #pragma unroll
         for (int a = 0; a < (DKV ? 2 : 1); ++a) {
             const int col = !DKV ? colQ : (a == 0 ? colK : colV);
             const float mul = (DKV && a == 1) ? 1.f : p.scale;
 #pragma unroll
-            for (int c = 0; c < DH; c += 16) {
-                uint32_t rr[16];
-                if (nst > 0) tmem_ld16(t_lane + 256 + a * 64 + c, rr);
-                if (row < p.n_rows) {
+            for (int c = 0; c < DH; c += 32) {
+                uint32_t rr[32];
+                if (nst > 0) tmem_ld32(t_lane + 128 + a * 64 + c, rr);
+                if (orow < p.n_rows) {
 #pragma unroll
-                    for (int i = 0; i < 16; i += 8) {
+                    for (int i = 0; i < 32; i += 8) {
                         float v[8];
 #pragma unroll
                         for (int e = 0; e < 8; ++e) v[e] = nst > 0 ? __uint_as_float(rr[i + e]) * mul : 0.f;
@@ -634,16 +727,17 @@ k_mha_tc_bwd(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant_
 }
 
 template <int DH, bool DKV>
-static cudaError_t launch_bwd(const CUtensorMap& mq, const CUtensorMap& md, const AttnBwdParams& p, cudaStream_t st) {
-    constexpr int TILE = 128 * DH * 2;
-    const size_t smem = (size_t)(2 + 2 * 2) * TILE + 32768 * (DKV ? 2 : 1) + 1024;
+static cudaError_t launch_bwd(const CUtensorMap& mq, const CUtensorMap& md, const CUtensorMap& mq64, const CUtensorMap& md64,
+                              const AttnBwdParams& p, cudaStream_t st) {
+    constexpr int TILE = 128 * DH * 2, STILE = 64 * DH * 2;
+    const size_t smem = (size_t)2 * TILE + (size_t)4 * STILE + 16384 * (DKV ? 2 : 1) + 1024;
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(k_mha_tc_bwd<DH, DKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr = true;
     }
     dim3 grid((unsigned)((p.n_rows + 127) / 128), (unsigned)p.nhead);
-    k_mha_tc_bwd<DH, DKV><<<grid, ATT_THREADS, smem, st>>>(mq, md, p);
+    k_mha_tc_bwd<DH, DKV><<<grid, ATT_THREADS, smem, st>>>(mq, md, mq64, md64, p);
     return cudaGetLastError();
 }
 
@@ -692,9 +786,11 @@ int mha_tc_bwd_launch(int dt, const void* qkv, const void* out, const void* dout
     if (key_start) { set_error("dense left-padded layout (key_start) runs on the CUDA-core kernel"); return -2; }
     const int d = nhead * dh;
     if (((uintptr_t)qkv & 15) || ((uintptr_t)dout & 15) || ((uintptr_t)dqkv & 15) || n_rows >= (1ll << 31)) { set_error("alignment"); return -2; }
-    CUtensorMap mq, md;
+    CUtensorMap mq, md, mq64, md64;   // owned tiles: 128-row boxes; streamed tiles: 64-row boxes
     if (!make_map(&mq, qkv, (uint64_t)3 * d, (uint64_t)n_rows, (uint64_t)3 * d, (uint32_t)dh, 128, dh * 2) ||
-        !make_map(&md, dout, (uint64_t)d, (uint64_t)n_rows, (uint64_t)d, (uint32_t)dh, 128, dh * 2)) {
+        !make_map(&md, dout, (uint64_t)d, (uint64_t)n_rows, (uint64_t)d, (uint32_t)dh, 128, dh * 2) ||
+        !make_map(&mq64, qkv, (uint64_t)3 * d, (uint64_t)n_rows, (uint64_t)3 * d, (uint32_t)dh, 64, dh * 2) ||
+        !make_map(&md64, dout, (uint64_t)d, (uint64_t)n_rows, (uint64_t)d, (uint32_t)dh, 64, dh * 2)) {
         set_error("cuTensorMapEncodeTiled failed or unavailable");
         return -2;
     }
@@ -707,11 +803,11 @@ int mha_tc_bwd_launch(int dt, const void* qkv, const void* out, const void* dout
     p.scale = scale; p.scale_log2 = scale * LOG2E; p.drop_p = drop_p;
     cudaError_t e;
     if (dh == 64) {
-        e = launch_bwd<64, false>(mq, md, p, st);
-        if (e == cudaSuccess) e = launch_bwd<64, true>(mq, md, p, st);
+        e = launch_bwd<64, false>(mq, md, mq64, md64, p, st);
+        if (e == cudaSuccess) e = launch_bwd<64, true>(mq, md, mq64, md64, p, st);
     } else {
-        e = launch_bwd<32, false>(mq, md, p, st);
-        if (e == cudaSuccess) e = launch_bwd<32, true>(mq, md, p, st);
+        e = launch_bwd<32, false>(mq, md, mq64, md64, p, st);
+        if (e == cudaSuccess) e = launch_bwd<32, true>(mq, md, mq64, md64, p, st);
     }
     if (e != cudaSuccess) return cuda_fail(e, "gt_mha_bwd(tcgen05)");
     return 0;
