@@ -32,13 +32,15 @@ SIGNATURES = {
     "gt_batch_plan": [P, L, L, L, I32, P, P, P, P, P, P, P, P, P, P],
     "gt_embed_sum_fwd": [I, P, L, I32, I32, I32, P, P, P, P, P],
     "gt_embed_sum_bwd": [I, P, L, I32, I32, I32, P, P, P, P, P],
-    "gt_aggregate_fwd": [I, I, P, P, L, I32, I32, P, P, P, P, I, P, I32, P, P, P, P, P, P],
-    "gt_aggregate_bwd": [I, I, P, P, P, L, I32, I32, P, P, P, P, I, P, I32, P, P, P, P, I32, P, P, P, P, P, P],
+    "gt_aggregate_fwd": [I, I, P, P, L, I32, I32, P, P, P, P, I, P, I32, P, P, P, P, P, P, P, P, P],
+    "gt_aggregate_bwd": [I, I, P, P, P, L, I32, I32, P, P, P, P, I, P, I32, P, P, P, P, I32, P, P, P, P, P, P, P, P, P],
+    "gt_edge_slots": [P, P, P, P, L, L, P, P, I32, P, P, P, P],
     "gt_segment_sum": [I, P, P, L, I32, P, P],
     "gt_add_graph_vec": [I, P, P, P, L, I32, P, P],
     "gt_colstats": [I, P, L, I32, P, P],
     "gt_bn_finalize": [P, L, I32, I32, P, P, P, P, P, F, F, I, P, P],
     "gt_bn_apply_fwd": [I, P, L, I32, I32, P, I, P, P, P, P, F, P, U64, P],
+    "gt_bn_norm_fwd": [I, P, L, I32, I32, P, P, P, P, P, P, F, F, I, I, P, P, P, P, P, F, P, U64, P],
     "gt_bn_bwd_reduce": [I, P, P, L, I32, I32, P, I, P, F, P, U64, P],
     "gt_bn_bwd_apply": [I, P, P, L, I32, I32, P, P, I, I, P, P, P, P, F, P, U64, P],
     "gt_gemm": [I, P, I, L, P, I, L, P, L, L, L, L, L, P, P, L, I, F, P, U64, I, P],

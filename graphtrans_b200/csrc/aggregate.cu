@@ -5,6 +5,8 @@
 // channels (8/16-byte vector loads), the per-edge message relu(x_j + ee_e) is recomputed from a
 // tiny edge-encoder table instead of materialising [E, d] tensors, and the sum is formed in
 // registers in CSR order (deterministic, no atomics on the feature path).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace gt {
@@ -21,6 +23,11 @@ struct EdgeEnc {
     const float* table;  // [ntypes, ld]    (TABLE)
     int kdim;
     int ntypes;          // rows of `table` (adjoint only: <= AGG_TAB_ROWS rows are reduced in shared memory)
+    // optional per-CSR-slot copies (gt_edge_slots, once per batch, reused by every layer): they remove the dependent
+    // "slot -> edge id -> attribute" / "slot -> neighbour -> degree" loads from the per-edge chain
+    const float* norm_slot;     // GCN: deg(src)^-1/2 deg(dst)^-1/2 of the edge in this slot
+    const int32_t* etype_slot;  // TABLE: combined edge type of the edge in this slot
+    const float* attr_slot;     // LINEAR: [E, kdim] attributes in slot order
 };
 
 template <int EK>
@@ -36,6 +43,22 @@ struct EdgeRegs {  // per-lane edge-encoder parameters of the current 4-channel 
 #pragma unroll
                 for (int k = 0; k < MAX_KDIM; ++k) w[k][q] = (ok && k < en.kdim) ? en.w[(c0 + q) * en.kdim + k] : 0.f;
             }
+        }
+    }
+    // same with the edge attributes / type already fetched (edge-batched kernels)
+    __device__ __forceinline__ void embed_pre(const EdgeEnc& en, const float (&a)[MAX_KDIM], int ty, int c0, int ld, float (&ee)[4]) const {
+        if (EK == GT_EDGE_NONE) {
+            ee[0] = ee[1] = ee[2] = ee[3] = 0.f;
+        } else if (EK == GT_EDGE_LINEAR) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float v = b[q];
+#pragma unroll
+                for (int k = 0; k < MAX_KDIM; ++k) v = fmaf(a[k], w[k][q], v);
+                ee[q] = v;
+            }
+        } else {
+            ld4(en.table + (int64_t)ty * ld + c0, ee);
         }
     }
     __device__ __forceinline__ void embed(const EdgeEnc& en, int eid, int c0, int ld, float (&ee)[4], float (&a)[MAX_KDIM]) const {
@@ -250,16 +273,301 @@ k_agg_bwd(const T* __restrict__ x, const T* __restrict__ dout, T* __restrict__ d
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Edge-batched variants (ld <= 128 * NCH, NCH <= 4): the per-edge chain "edge slot -> neighbour id -> degree / edge
+// attribute -> feature row" is a sequence of dependent L2 round trips when one warp walks its edges one by one.  Here
+// the 32 lanes first fetch up to 32 edges of the node IN PARALLEL (neighbour ids, GCN norms, edge attributes / types),
+// then the warp walks them with register shuffles, and every edge issues the loads of ALL channel chunks of the
+// neighbour row back to back (the whole 600-byte row per edge, several edges in flight through the unrolled loop).
+template <typename T, int CONV, int EK, int NCH>
+__global__ void __launch_bounds__(AGG_WARPS * 32)
+k_agg_fwd2(const T* __restrict__ x, T* __restrict__ out, int N, int d, int ld,
+           const int32_t* __restrict__ rp_dst, const int32_t* __restrict__ src_by_dst,
+           const int32_t* __restrict__ eid_by_dst, const int32_t* __restrict__ rp_src, EdgeEnc en,
+           const float* __restrict__ self_param, int nch) {
+    // NCH = 1: a warp owns ONE 128-channel chunk (warp % nch) of its nodes, neighbouring warps take the other chunks of
+    // the same node (keeps the register footprint small enough for 2-3 resident blocks per SM)
+    const int lane = threadIdx.x & 31;
+    const int gwarp = blockIdx.x * AGG_WARPS + (threadIdx.x >> 5);
+    const int cbase = (gwarp % nch) * 128;
+    const int warp = gwarp / nch;
+    const int nwarps = gridDim.x * AGG_WARPS / nch;
+    const float eps1 = (CONV == GT_CONV_GIN) ? 1.f + self_param[0] : 0.f;
+    EdgeRegs<EK> er[NCH];
+    float root[NCH][4];
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+        const int c0 = cbase + k * 128 + lane * 4;
+        if (c0 < ld) er[k].load(en, c0, d);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) root[k][q] = (CONV == GT_CONV_GCN && c0 + q < d) ? self_param[c0 + q] : 0.f;
+    }
+    for (int i = warp; i < N; i += nwarps) {
+        const int b = rp_dst[i], e = rp_dst[i + 1];
+        float dis_i = 1.f, inv_deg_i = 1.f;
+        if (CONV == GT_CONV_GCN) {
+            const float deg_i = (float)(rp_src[i + 1] - rp_src[i] + 1);
+            dis_i = rsqrtf(deg_i);
+            inv_deg_i = 1.f / deg_i;
+        }
+        float acc[NCH][4];
+#pragma unroll
+        for (int k = 0; k < NCH; ++k)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[k][q] = 0.f;
+        for (int base = b; base < e; base += 32) {
+            const int p = base + lane;
+            const bool have = p < e;
+            const int j_l = have ? src_by_dst[p] : 0;
+            float nrm_l = 1.f, a_l[MAX_KDIM] = {0.f, 0.f, 0.f, 0.f};
+            int ty_l = 0;
+            if (have) {
+                if (CONV == GT_CONV_GCN)
+                    nrm_l = en.norm_slot ? en.norm_slot[p] : dis_i * rsqrtf((float)(rp_src[j_l + 1] - rp_src[j_l] + 1));
+                if (EK == GT_EDGE_LINEAR) {
+                    const float* ap = en.attr_slot ? en.attr_slot + (int64_t)p * en.kdim : en.attr + (int64_t)eid_by_dst[p] * en.kdim;
+#pragma unroll
+                    for (int k = 0; k < MAX_KDIM; ++k)
+                        if (k < en.kdim) a_l[k] = ap[k];
+                } else if (EK == GT_EDGE_TABLE) {
+                    ty_l = en.etype_slot ? en.etype_slot[p] : en.etype[eid_by_dst[p]];
+                }
+            }
+            const int cnt = min(32, e - base);
+#pragma unroll 4
+            for (int t = 0; t < cnt; ++t) {
+                const int j = __shfl_sync(0xffffffffu, j_l, t);
+                const float nrm = CONV == GT_CONV_GCN ? __shfl_sync(0xffffffffu, nrm_l, t) : 1.f;
+                float a[MAX_KDIM] = {0.f, 0.f, 0.f, 0.f};
+                int ty = 0;
+                if (EK == GT_EDGE_LINEAR) {
+#pragma unroll
+                    for (int k = 0; k < MAX_KDIM; ++k) a[k] = __shfl_sync(0xffffffffu, a_l[k], t);
+                } else if (EK == GT_EDGE_TABLE) {
+                    ty = __shfl_sync(0xffffffffu, ty_l, t);
+                }
+#pragma unroll
+                for (int k = 0; k < NCH; ++k) {
+                    const int c0 = cbase + k * 128 + lane * 4;
+                    if (c0 < ld) {
+                        float xv[4], ee[4];
+                        ld4(x + (int64_t)j * ld + c0, xv);
+                        er[k].embed_pre(en, a, ty, c0, ld, ee);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) acc[k][q] = fmaf(nrm, fmaxf(xv[q] + ee[q], 0.f), acc[k][q]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) {
+            const int c0 = cbase + k * 128 + lane * 4;
+            if (c0 < ld) {
+                float xi[4];
+                ld4(x + (int64_t)i * ld + c0, xi);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (CONV == GT_CONV_GCN) acc[k][q] = fmaf(fmaxf(xi[q] + root[k][q], 0.f), inv_deg_i, acc[k][q]);
+                    else acc[k][q] = fmaf(eps1, xi[q], acc[k][q]);
+                }
+                st4(out + (int64_t)i * ld + c0, acc[k]);
+            }
+        }
+    }
+}
+
+// adjoint, edge-batched: one warp per SOURCE node j, its out-edges fetched 32 at a time.  Edge-table gradients are
+// reduced per block in a dynamic shared-memory table [ntypes][ld] (lanes own distinct channels: conflict-free inside a
+// warp); Linear edge-encoder gradients in registers, then shared memory, then one global atomic per (block, element).
+template <typename T, int CONV, int EK, int NCH>
+__global__ void __launch_bounds__(AGG_WARPS * 32)
+k_agg_bwd2(const T* __restrict__ x, const T* __restrict__ dout, T* __restrict__ dx, int N, int d, int ld,
+           const int32_t* __restrict__ rp_src, const int32_t* __restrict__ dst_by_src,
+           const int32_t* __restrict__ eid_by_src, EdgeEnc en, const float* __restrict__ self_param,
+           float* __restrict__ d_edge_w, float* __restrict__ d_edge_b, float* __restrict__ d_table,
+           float* __restrict__ d_self, int nch) {
+    extern __shared__ float sh_dyn[];   // TABLE: [ntypes][ld];  LINEAR / GCN: [(2 + MAX_KDIM)][128 * nch]
+    const int lane = threadIdx.x & 31;
+    const int gwarp = blockIdx.x * AGG_WARPS + (threadIdx.x >> 5);
+    const int cbase = (gwarp % nch) * 128;   // this warp's 128-channel chunk (see k_agg_fwd2)
+    const int warp = gwarp / nch;
+    const int nwarps = gridDim.x * AGG_WARPS / nch;
+    const int W = 128 * nch;
+    float* sh_tab = sh_dyn;
+    float* sh_par = sh_dyn + (EK == GT_EDGE_TABLE ? en.ntypes * ld : 0);   // [self | b | w0..w3][W]
+    const int n_par = (2 + MAX_KDIM) * W;
+    for (int i = threadIdx.x; i < (EK == GT_EDGE_TABLE ? en.ntypes * ld : 0) + n_par; i += blockDim.x) sh_dyn[i] = 0.f;
+    __syncthreads();
+    const float eps1 = (CONV == GT_CONV_GIN) ? 1.f + self_param[0] : 0.f;
+    float deps = 0.f;
+    EdgeRegs<EK> er[NCH];
+    float root[NCH][4], a_self[NCH][4], a_b[NCH][4], a_w[NCH][MAX_KDIM][4];
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+        const int c0 = cbase + k * 128 + lane * 4;
+        if (c0 < ld) er[k].load(en, c0, d);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            root[k][q] = (CONV == GT_CONV_GCN && c0 + q < d) ? self_param[c0 + q] : 0.f;
+            a_self[k][q] = a_b[k][q] = 0.f;
+#pragma unroll
+            for (int kk = 0; kk < MAX_KDIM; ++kk) a_w[k][kk][q] = 0.f;
+        }
+    }
+    for (int j = warp; j < N; j += nwarps) {
+        const int b = rp_src[j], e = rp_src[j + 1];
+        float dis_j = 1.f, inv_deg_j = 1.f;
+        if (CONV == GT_CONV_GCN) {
+            const float deg_j = (float)(e - b + 1);
+            dis_j = rsqrtf(deg_j);
+            inv_deg_j = 1.f / deg_j;
+        }
+        float xj[NCH][4], acc[NCH][4];
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) {
+            const int c0 = cbase + k * 128 + lane * 4;
+            if (c0 < ld) ld4(x + (int64_t)j * ld + c0, xj[k]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[k][q] = 0.f;
+        }
+        for (int base = b; base < e; base += 32) {
+            const int p = base + lane;
+            const bool have = p < e;
+            const int i_l = have ? dst_by_src[p] : 0;
+            float nrm_l = 1.f, a_l[MAX_KDIM] = {0.f, 0.f, 0.f, 0.f};
+            int ty_l = 0;
+            if (have) {
+                if (CONV == GT_CONV_GCN)
+                    nrm_l = en.norm_slot ? en.norm_slot[p] : dis_j * rsqrtf((float)(rp_src[i_l + 1] - rp_src[i_l] + 1));
+                if (EK == GT_EDGE_LINEAR) {
+                    const float* ap = en.attr_slot ? en.attr_slot + (int64_t)p * en.kdim : en.attr + (int64_t)eid_by_src[p] * en.kdim;
+#pragma unroll
+                    for (int k = 0; k < MAX_KDIM; ++k)
+                        if (k < en.kdim) a_l[k] = ap[k];
+                } else if (EK == GT_EDGE_TABLE) {
+                    ty_l = en.etype_slot ? en.etype_slot[p] : en.etype[eid_by_src[p]];
+                }
+            }
+            const int cnt = min(32, e - base);
+#pragma unroll 4
+            for (int t = 0; t < cnt; ++t) {
+                const int i = __shfl_sync(0xffffffffu, i_l, t);
+                const float nrm = CONV == GT_CONV_GCN ? __shfl_sync(0xffffffffu, nrm_l, t) : 1.f;
+                float a[MAX_KDIM] = {0.f, 0.f, 0.f, 0.f};
+                int ty = 0;
+                if (EK == GT_EDGE_LINEAR) {
+#pragma unroll
+                    for (int k = 0; k < MAX_KDIM; ++k) a[k] = __shfl_sync(0xffffffffu, a_l[k], t);
+                } else if (EK == GT_EDGE_TABLE) {
+                    ty = __shfl_sync(0xffffffffu, ty_l, t);
+                }
+#pragma unroll
+                for (int k = 0; k < NCH; ++k) {
+                    const int c0 = cbase + k * 128 + lane * 4;
+                    if (c0 < ld) {
+                        float g[4], ee[4], gm[4];
+                        ld4(dout + (int64_t)i * ld + c0, g);
+                        er[k].embed_pre(en, a, ty, c0, ld, ee);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            gm[q] = (xj[k][q] + ee[q] > 0.f) ? nrm * g[q] : 0.f;
+                            acc[k][q] += gm[q];
+                        }
+                        if (EK == GT_EDGE_LINEAR) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                a_b[k][q] += gm[q];
+#pragma unroll
+                                for (int kk = 0; kk < MAX_KDIM; ++kk) a_w[k][kk][q] = fmaf(a[kk], gm[q], a_w[k][kk][q]);
+                            }
+                        } else if (EK == GT_EDGE_TABLE) {
+                            float* row = sh_tab + ty * ld + c0;
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                if (gm[q] != 0.f) atomicAdd(row + q, gm[q]);
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) {
+            const int c0 = cbase + k * 128 + lane * 4;
+            if (c0 < ld) {
+                float gj[4];
+                ld4(dout + (int64_t)j * ld + c0, gj);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (CONV == GT_CONV_GCN) {
+                        const float gs = (xj[k][q] + root[k][q] > 0.f) ? gj[q] * inv_deg_j : 0.f;
+                        acc[k][q] += gs;
+                        a_self[k][q] += gs;
+                    } else {
+                        acc[k][q] = fmaf(eps1, gj[q], acc[k][q]);
+                        deps = fmaf(xj[k][q], gj[q], deps);
+                    }
+                }
+                st4(dx + (int64_t)j * ld + c0, acc[k]);
+            }
+        }
+    }
+    // block-level reduction of the parameter gradients, then one global atomic per (block, element)
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+        const int cw = cbase + k * 128 + lane * 4;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (CONV == GT_CONV_GCN) atomicAdd(&sh_par[cw + q], a_self[k][q]);
+            if (EK == GT_EDGE_LINEAR) {
+                atomicAdd(&sh_par[W + cw + q], a_b[k][q]);
+#pragma unroll
+                for (int kk = 0; kk < MAX_KDIM; ++kk)
+                    if (kk < en.kdim) atomicAdd(&sh_par[(2 + kk) * W + cw + q], a_w[k][kk][q]);
+            }
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < d; c += blockDim.x) {
+        if (CONV == GT_CONV_GCN) atomicAdd(&d_self[c], sh_par[c]);
+        if (EK == GT_EDGE_LINEAR) {
+            atomicAdd(&d_edge_b[c], sh_par[W + c]);
+            for (int kk = 0; kk < en.kdim; ++kk) atomicAdd(&d_edge_w[c * en.kdim + kk], sh_par[(2 + kk) * W + c]);
+        }
+    }
+    if (EK == GT_EDGE_TABLE) {
+        for (int i = threadIdx.x; i < en.ntypes * ld; i += blockDim.x) {
+            const float v = sh_tab[i];
+            if (v != 0.f && (i % ld) < d) atomicAdd(d_table + i, v);
+        }
+    }
+    if (CONV == GT_CONV_GIN) {
+        deps = warp_sum(deps);
+        if (lane == 0 && deps != 0.f) atomicAdd(d_self, deps);
+    }
+}
+
 template <typename T, int CONV>
 static int launch_fwd(int ek, const T* x, T* out, int N, int d, int ld, const int32_t* rp_dst,
                       const int32_t* src_by_dst, const int32_t* eid_by_dst, const int32_t* rp_src,
                       EdgeEnc en, const float* self_param, cudaStream_t st) {
     const int grid = blocks_for(N, AGG_WARPS, kNumSMs * 8);
+    const int nch = (ld + 127) / 128;
+#define L2(EK, NCH) k_agg_fwd2<T, CONV, EK, NCH><<<grid2, AGG_WARPS * 32, 0, st>>>(x, out, N, d, ld, rp_dst, src_by_dst, eid_by_dst, rp_src, en, self_param, nch)
+#define L2N(EK) L2(EK, 1)
+    // (node, 128-channel chunk) items: the global warp count must be a multiple of nch
+    const int grid2 = (blocks_for((int64_t)N * nch, AGG_WARPS, kNumSMs * 8) + nch - 1) / nch * nch;
 #define L(EK) k_agg_fwd<T, CONV, EK><<<grid, AGG_WARPS * 32, 0, st>>>(x, out, N, d, ld, rp_dst, src_by_dst, eid_by_dst, rp_src, en, self_param)
-    if (ek == GT_EDGE_NONE) L(GT_EDGE_NONE);
+    static const int variant = getenv("GT_AGG_VARIANT") ? atoi(getenv("GT_AGG_VARIANT")) : 0;   // tuning knob: 1 = per-edge kernels
+    if (nch <= 4 && variant != 1) {
+        if (ek == GT_EDGE_NONE) L2N(GT_EDGE_NONE);
+        else if (ek == GT_EDGE_LINEAR) L2N(GT_EDGE_LINEAR);
+        else L2N(GT_EDGE_TABLE);
+    } else if (ek == GT_EDGE_NONE) L(GT_EDGE_NONE);
     else if (ek == GT_EDGE_LINEAR) L(GT_EDGE_LINEAR);
     else L(GT_EDGE_TABLE);
 #undef L
+#undef L2N
+#undef L2
     return 0;
 }
 
@@ -268,12 +576,34 @@ static int launch_bwd(int ek, const T* x, const T* dout, T* dx, int N, int d, in
                       const int32_t* dst_by_src, const int32_t* eid_by_src, EdgeEnc en,
                       const float* self_param, float* dw, float* db, float* dtab, float* dself,
                       cudaStream_t st) {
-    const int grid = blocks_for(N, AGG_WARPS, kNumSMs * 8);
+    int grid = blocks_for(N, AGG_WARPS, kNumSMs * 8);
+    const int nch = (ld + 127) / 128;
+    const size_t smem2 = sizeof(float) * ((size_t)(2 + MAX_KDIM) * 128 * nch + (ek == GT_EDGE_TABLE ? (size_t)en.ntypes * ld : 0));
+#define L2(EK, NCH) do { \
+        static bool attr = false; \
+        if (!attr) { cudaFuncSetAttribute(k_agg_bwd2<T, CONV, EK, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr = true; } \
+        k_agg_bwd2<T, CONV, EK, NCH><<<grid, AGG_WARPS * 32, smem2, st>>>(x, dout, dx, N, d, ld, rp_src, dst_by_src, eid_by_src, en, self_param, dw, db, dtab, dself, nch); \
+    } while (0)
+#define L2N(EK) L2(EK, 1)
 #define L(EK) k_agg_bwd<T, CONV, EK><<<grid, AGG_WARPS * 32, 0, st>>>(x, dout, dx, N, d, ld, rp_src, dst_by_src, eid_by_src, en, self_param, dw, db, dtab, dself)
-    if (ek == GT_EDGE_NONE) L(GT_EDGE_NONE);
+    static const int variant = getenv("GT_AGG_VARIANT") ? atoi(getenv("GT_AGG_VARIANT")) : 0;
+    // measured (tools/agg_bench.py): with an edge-type table the block-private [ntypes][ld] shared-memory table of the
+    // batched kernel costs too much occupancy (84 vs 53 us on the molpcba batch); the per-edge kernel keeps its
+    // 32 KB per-chunk table.  Linear / no edge encoder: the batched kernel wins (62 vs 73 us on the code2 batch).
+    if (nch <= 4 && smem2 <= 100 * 1024 && variant != 1 && (ek != GT_EDGE_TABLE || variant == 2)) {
+        // every block flushes its private gradient tables once: keep the block count near the resident capacity
+        const int cap = kNumSMs * (smem2 > 48 * 1024 ? 2 : 8);
+        grid = blocks_for((int64_t)N * nch, AGG_WARPS, cap);
+        grid = (grid + nch - 1) / nch * nch;     // global warp count must be a multiple of nch
+        if (ek == GT_EDGE_NONE) L2N(GT_EDGE_NONE);
+        else if (ek == GT_EDGE_LINEAR) L2N(GT_EDGE_LINEAR);
+        else L2N(GT_EDGE_TABLE);
+    } else if (ek == GT_EDGE_NONE) L(GT_EDGE_NONE);
     else if (ek == GT_EDGE_LINEAR) L(GT_EDGE_LINEAR);
     else L(GT_EDGE_TABLE);
 #undef L
+#undef L2N
+#undef L2
     return 0;
 }
 
@@ -294,9 +624,10 @@ extern "C" int gt_aggregate_fwd(int dt, int conv, const void* x, void* out, int6
                                 const int32_t* rowptr_dst, const int32_t* src_by_dst, const int32_t* eid_by_dst,
                                 const int32_t* rowptr_src, int edge_kind, const float* edge_attr, int32_t kdim,
                                 const float* edge_w, const float* edge_b, const int32_t* etype,
-                                const float* table, const float* self_param, void* stream) {
+                                const float* table, const float* self_param, const float* norm_slot,
+                                const int32_t* etype_slot, const float* attr_slot, void* stream) {
     if (int r = check_common("gt_aggregate_fwd", conv, N, d, ld, edge_kind, kdim)) return r;
-    EdgeEnc en{edge_attr, edge_w, edge_b, etype, table, kdim, 0};
+    EdgeEnc en{edge_attr, edge_w, edge_b, etype, table, kdim, 0, norm_slot, etype_slot, attr_slot};
     cudaStream_t st = (cudaStream_t)stream;
     GT_DISPATCH_DT(dt, {
         if (conv == GT_CONV_GCN)
@@ -313,11 +644,12 @@ extern "C" int gt_aggregate_bwd(int dt, int conv, const void* x, const void* dou
                                 const int32_t* dst_by_src, const int32_t* eid_by_src, int edge_kind,
                                 const float* edge_attr, int32_t kdim, const float* edge_w, const float* edge_b,
                                 const int32_t* etype, const float* table, int32_t ntypes, const float* self_param,
-                                float* d_edge_w, float* d_edge_b, float* d_table, float* d_self, void* stream) {
+                                float* d_edge_w, float* d_edge_b, float* d_table, float* d_self, const float* norm_slot,
+                                const int32_t* etype_slot, const float* attr_slot, void* stream) {
     (void)rowptr_dst;
     if (int r = check_common("gt_aggregate_bwd", conv, N, d, ld, edge_kind, kdim)) return r;
     GT_CHECK_ARG(edge_kind != GT_EDGE_TABLE || ntypes > 0, "gt_aggregate_bwd: ntypes must be the row count of the edge table");
-    EdgeEnc en{edge_attr, edge_w, edge_b, etype, table, kdim, ntypes};
+    EdgeEnc en{edge_attr, edge_w, edge_b, etype, table, kdim, ntypes, norm_slot, etype_slot, attr_slot};
     cudaStream_t st = (cudaStream_t)stream;
     GT_DISPATCH_DT(dt, {
         if (conv == GT_CONV_GCN)
@@ -326,5 +658,48 @@ extern "C" int gt_aggregate_bwd(int dt, int conv, const void* x, const void* dou
             launch_bwd<T, GT_CONV_GIN>(edge_kind, (const T*)x, (const T*)dout, (T*)dx, (int)N, d, ld, rowptr_src, dst_by_src, eid_by_src, en, self_param, d_edge_w, d_edge_b, d_table, d_self, st);
     });
     GT_LAUNCH_CHECK("gt_aggregate_bwd");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ per-slot edge data
+namespace gt {
+__global__ void k_edge_slots(const int32_t* __restrict__ rp_src, const int32_t* __restrict__ nbr_a,
+                             const int32_t* __restrict__ nbr_b_of_slot_rowptr, int64_t E, int64_t N,
+                             const int32_t* __restrict__ eid_slot, const int32_t* __restrict__ etype,
+                             const float* __restrict__ attr, int kdim, float* __restrict__ norm_slot,
+                             int32_t* __restrict__ etype_slot, float* __restrict__ attr_slot,
+                             const int32_t* __restrict__ rowptr_slot) {
+    (void)nbr_b_of_slot_rowptr;
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < E; p += (int64_t)gridDim.x * blockDim.x) {
+        const int eid = eid_slot[p];
+        if (etype_slot) etype_slot[p] = etype[eid];
+        if (attr_slot)
+            for (int k = 0; k < kdim; ++k) attr_slot[p * kdim + k] = attr[(int64_t)eid * kdim + k];
+        if (norm_slot) {
+            // owner row of slot p: binary search in the slot CSR row pointers; the other endpoint is nbr_a[p]
+            int64_t lo = 0, hi = N;
+            while (hi - lo > 1) {
+                const int64_t mid = (lo + hi) >> 1;
+                if (rowptr_slot[mid] <= p) lo = mid; else hi = mid;
+            }
+            const int a = (int)lo, b = nbr_a[p];
+            norm_slot[p] = rsqrtf((float)(rp_src[a + 1] - rp_src[a] + 1)) * rsqrtf((float)(rp_src[b + 1] - rp_src[b] + 1));
+        }
+    }
+}
+}  // namespace gt
+
+extern "C" int gt_edge_slots(const int32_t* rowptr_slot, const int32_t* nbr_slot, const int32_t* eid_slot,
+                             const int32_t* rowptr_src, int64_t E, int64_t N, const int32_t* etype,
+                             const float* edge_attr, int32_t kdim, float* norm_slot, int32_t* etype_slot,
+                             float* attr_slot, void* stream) {
+    GT_CHECK_ARG(E >= 0 && N > 0 && kdim >= 0 && kdim <= MAX_KDIM, "gt_edge_slots: bad arguments");
+    GT_CHECK_ARG(!etype_slot || etype, "gt_edge_slots: etype_slot needs etype");
+    GT_CHECK_ARG(!attr_slot || (edge_attr && kdim > 0), "gt_edge_slots: attr_slot needs edge_attr");
+    if (E == 0) return 0;
+    k_edge_slots<<<blocks_for(E, 256), 256, 0, (cudaStream_t)stream>>>(rowptr_src, nbr_slot, nullptr, E, N, eid_slot, etype,
+                                                                     edge_attr, kdim, norm_slot, etype_slot, attr_slot,
+                                                                     rowptr_slot);
+    GT_LAUNCH_CHECK("gt_edge_slots");
     return 0;
 }

@@ -178,6 +178,86 @@ __global__ void k_bn_apply(const T* __restrict__ x, int64_t M, int ld, const flo
     }
 }
 
+// fused finalize + apply: every thread owns one 4-channel vector of a 128-channel group, derives scale / shift of its
+// channels from the fp64 batch statistics (train) or the running statistics (eval) once, then streams its row slab.
+// Block (x, 0) also writes scale|shift|mean|rstd for the backward and updates the running statistics in place.
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_bn_norm_fwd(const T* __restrict__ x, int64_t M, int d, int ld, int64_t rows_per_block, const double* __restrict__ stats,
+              const float* __restrict__ gamma, const float* __restrict__ beta, float* running_mean, float* running_var,
+              int64_t* nbt, float momentum, float eps, int training, int relu, const T* __restrict__ resid,
+              const float* __restrict__ gvec, const int32_t* __restrict__ node_graph, T* __restrict__ y,
+              float* __restrict__ ssmr, float drop_p, const uint64_t* __restrict__ rng, uint64_t salt) {
+    const Drop dr = make_drop(rng, salt, drop_p);
+    const int vpr = ld / 4;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c0 = blockIdx.x * 128 + tx * 4;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && training && nbt) *nbt += 1;
+    if (c0 >= ld) return;
+    float sc[4], sh[4];
+    const bool writer = blockIdx.y == 0 && ty == 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int c = c0 + q;
+        float scale = 0.f, shift = 0.f, mean = 0.f, rstd = 0.f;
+        if (c < d) {
+            if (training) {
+                const double mu = stats[c] / (double)M;
+                double var = stats[ld + c] / (double)M - mu * mu;
+                if (var < 0) var = 0;
+                mean = (float)mu;
+                rstd = (float)(1.0 / sqrt(var + (double)eps));
+                if (writer && running_mean) {
+                    const double unb = M > 1 ? var * ((double)M / (double)(M - 1)) : var;
+                    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+                    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+                }
+            } else {
+                mean = running_mean[c];
+                rstd = rsqrtf(running_var[c] + eps);
+            }
+            scale = gamma[c] * rstd;
+            shift = beta[c] - mean * scale;
+        }
+        sc[q] = scale, sh[q] = shift;
+        if (writer) {
+            ssmr[c] = scale;
+            ssmr[ld + c] = shift;
+            ssmr[2 * ld + c] = mean;
+            ssmr[3 * ld + c] = rstd;
+        }
+    }
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_block, r1 = min(r0 + rows_per_block, M);
+    for (int64_t r = r0 + ty; r < r1; r += STAT_TY) {
+        float v[4];
+        ld4(x + r * ld + c0, v);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            v[q] = fmaf(v[q], sc[q], sh[q]);
+            if (relu) v[q] = fmaxf(v[q], 0.f);
+        }
+        if (dr.on) {
+            float ds[4];
+            drop4(dr, (uint64_t)(r * vpr + c0 / 4), ds);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) v[q] *= ds[q];
+        }
+        if (resid) {
+            float t[4];
+            ld4(resid + r * ld + c0, t);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) v[q] += t[q];
+        }
+        if (gvec) {
+            float t[4];
+            ld4(gvec + (int64_t)node_graph[r] * ld + c0, t);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) v[q] += t[q];
+        }
+        st4(y + r * ld + c0, v);
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 k_bn_bwd_reduce(const T* __restrict__ x, const T* __restrict__ dy, int64_t M, int ld, int64_t rows_per_block,
@@ -777,6 +857,21 @@ extern "C" int gt_bn_apply_fwd(int dt, const void* x, int64_t M, int32_t d, int3
     GT_CHECK_ARG(!gvec || node_graph, "gt_bn_apply_fwd: gvec needs node_graph");
     GT_DISPATCH_DT(dt, (k_bn_apply<T><<<blocks_for(M * (ld / 4), 256), 256, 0, ST>>>((const T*)x, M, ld, ssmr, relu, (const T*)resid, gvec, node_graph, (T*)y, drop_p, rng_state, salt)));
     GT_LAUNCH_CHECK("gt_bn_apply_fwd");
+    return 0;
+}
+
+extern "C" int gt_bn_norm_fwd(int dt, const void* x, int64_t M, int32_t d, int32_t ld, const double* stats,
+                              const float* gamma, const float* beta, float* running_mean, float* running_var,
+                              int64_t* nbt, float momentum, float eps, int training, int relu, const void* resid,
+                              const float* gvec, const int32_t* node_graph, void* y, float* ssmr, float drop_p,
+                              const uint64_t* rng_state, uint64_t salt, void* stream) {
+    GT_CHECK_ARG(M > 0 && d > 0 && ld >= d && ld % 4 == 0, "gt_bn_norm_fwd: bad shape");
+    GT_CHECK_ARG(training ? stats != nullptr : (running_mean && running_var), "gt_bn_norm_fwd: missing statistics");
+    GT_CHECK_ARG(!gvec || node_graph, "gt_bn_norm_fwd: gvec needs node_graph");
+    int64_t rpb;
+    const dim3 grid = stat_grid(M, ld, &rpb);
+    GT_DISPATCH_DT(dt, (k_bn_norm_fwd<T><<<grid, 256, 0, ST>>>((const T*)x, M, d, ld, rpb, stats, gamma, beta, running_mean, running_var, nbt, momentum, eps, training, relu, (const T*)resid, gvec, node_graph, (T*)y, ssmr, drop_p, rng_state, salt)));
+    GT_LAUNCH_CHECK("gt_bn_norm_fwd");
     return 0;
 }
 

@@ -287,6 +287,7 @@ class GraphPlan:
              ptr(self.tok2node), ptr(self.tok_graph), ptr(self.node_graph), ptr(self.node2tok),
              ptr(self.cls_rows), ptr(self.scalars))
         self._etype = {}
+        self._slots = {}
         self._S = None
         # attention metadata of the packed layout (row key ranges, tile ranges): once per batch for all layers
         self.row_bounds = torch.empty(2 * self.n_rows, **i32)
@@ -309,6 +310,28 @@ class GraphPlan:
             call("gt_edge_type", ptr(ea), self.E, len(mult), arr, ptr(et))
             self._etype[key] = et
         return self._etype[key]
+
+    def edge_slots(self, conv, edge_kind, edge_attr=None, etype=None):
+        """per-slot copies of the per-edge data for both CSRs (computed once per batch and encoder kind, reused by
+        all layers): ((norm, etype, attr) in target-sorted order, (norm, etype, attr) in source-sorted order)"""
+        key = (conv, edge_kind, 0 if edge_attr is None else edge_attr.data_ptr(), 0 if etype is None else etype.data_ptr())
+        hit = self._slots.get(key)
+        if hit is not None:
+            return hit
+        E, dev = max(self.E, 1), self.rowptr_dst.device
+        kdim = edge_attr.shape[1] if edge_kind == EDGE_LINEAR else 0
+        res = []
+        for rp, nbr, eid in ((self.rowptr_dst, self.src_by_dst, self.eid_by_dst),
+                             (self.rowptr_src, self.dst_by_src, self.eid_by_src)):
+            norm = torch.empty(E, dtype=torch.float32, device=dev) if conv == CONV_GCN else None
+            ets = torch.empty(E, dtype=torch.int32, device=dev) if edge_kind == EDGE_TABLE else None
+            ats = torch.empty(E, kdim, dtype=torch.float32, device=dev) if edge_kind == EDGE_LINEAR else None
+            if norm is not None or ets is not None or ats is not None:
+                call("gt_edge_slots", ptr(rp), ptr(nbr), ptr(eid), ptr(self.rowptr_src), self.E, self.N, ptr(etype),
+                     ptr(edge_attr) if edge_kind == EDGE_LINEAR else None, kdim, ptr(norm), ptr(ets), ptr(ats))
+            res.append((norm, ets, ats))
+        self._slots[key] = tuple(res)
+        return self._slots[key]
 
     @property
     def S(self) -> int:
@@ -479,9 +502,12 @@ class _AggregateFn(torch.autograd.Function):
             if table.shape[1] != ld or table.dtype != torch.float32:
                 raise RuntimeError("edge table must be fp32 [ntypes, ld]")
         sp = self_param.contiguous().view(-1)
+        slots = plan.edge_slots(conv, edge_kind, edge_attr if edge_kind == EDGE_LINEAR else None, etype)
         call("gt_aggregate_fwd", dt_of(x), conv, ptr(x), ptr(out), N, d, ld, ptr(plan.rowptr_dst),
              ptr(plan.src_by_dst), ptr(plan.eid_by_dst), ptr(plan.rowptr_src), edge_kind, ptr(edge_attr), kdim,
-             ptr(edge_w), ptr(edge_b), ptr(etype), ptr(table), ptr(sp))
+             ptr(edge_w), ptr(edge_b), ptr(etype), ptr(table), ptr(sp), ptr(slots[0][0]), ptr(slots[0][1]),
+             ptr(slots[0][2]))
+        ctx.slots = slots[1]
         ctx.save_for_backward(x, edge_attr, edge_w, edge_b, etype, table, sp)
         ctx.params = (edge_w_param, edge_b, self_param)
         ctx.meta = (plan, conv, d, edge_kind, kdim, self_param.shape)
@@ -503,7 +529,7 @@ class _AggregateFn(torch.autograd.Function):
         call("gt_aggregate_bwd", dt_of(x), conv, ptr(x), ptr(g), ptr(dx), N, d, ld, ptr(plan.rowptr_dst),
              ptr(plan.rowptr_src), ptr(plan.dst_by_src), ptr(plan.eid_by_src), edge_kind, ptr(edge_attr), kdim,
              ptr(edge_w), ptr(edge_b), ptr(etype), ptr(table), table.shape[0] if edge_kind == EDGE_TABLE else 0, ptr(sp),
-             ptr(tw[0]), ptr(tb[0]), ptr(dtab), ptr(tself[0]))
+             ptr(tw[0]), ptr(tb[0]), ptr(dtab), ptr(tself[0]), ptr(ctx.slots[0]), ptr(ctx.slots[1]), ptr(ctx.slots[2]))
         for prm in (pw, pb, pself):
             _grad_done(prm)
         return dx, None, None, None, None, None, tw[1], tb[1], None, dtab, tself[1]
@@ -586,16 +612,15 @@ class _BatchNormFn(torch.autograd.Function):
         if training:
             stats = zeros_small(2 * ld, torch.float64, dev)
             call("gt_colstats", dt_of(x), ptr(x), M, ld, ptr(stats))
-        call("gt_bn_finalize", ptr(stats), M, d, ld, ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var),
-             ptr(nbt), float(momentum), float(eps), int(training), ptr(ssmr))
         y = torch.empty_like(x)
         if resid is not None:
             resid = resid.contiguous()
         if gvec is not None:
             gvec = gvec.contiguous()
         rng = ptr(rng_state(dev)) if drop_p else None
-        call("gt_bn_apply_fwd", dt_of(x), ptr(x), M, d, ld, ptr(ssmr), int(relu), ptr(resid), ptr(gvec),
-             ptr(plan.node_graph) if gvec is not None else None, ptr(y), float(drop_p), rng, salt)
+        call("gt_bn_norm_fwd", dt_of(x), ptr(x), M, d, ld, ptr(stats), ptr(gamma), ptr(beta), ptr(running_mean),
+             ptr(running_var), ptr(nbt), float(momentum), float(eps), int(training), int(relu), ptr(resid), ptr(gvec),
+             ptr(plan.node_graph) if gvec is not None else None, ptr(y), ptr(ssmr), float(drop_p), rng, salt)
         ctx.save_for_backward(x, ssmr, gamma)
         ctx.params = (gamma, beta)
         ctx.meta = (M, d, ld, relu, training, plan, resid is not None, gvec is not None, float(drop_p), salt)

@@ -101,7 +101,8 @@ int gt_aggregate_fwd(int dt, int conv, const void* x, void* out, int64_t N, int3
                      const int32_t* rowptr_src,
                      int edge_kind, const float* edge_attr, int32_t kdim, const float* edge_w,
                      const float* edge_b, const int32_t* etype, const float* table,
-                     const float* self_param, void* stream);
+                     const float* self_param, const float* norm_slot, const int32_t* etype_slot,
+                     const float* attr_slot, void* stream);
 /* adjoint: dx (same dtype), and fp32 accumulators (must be zeroed by the caller):
  * d_edge_w [d,kdim], d_edge_b [d] (LINEAR) or d_table [ntypes, ld] (TABLE), d_self ([d] or [1]). */
 int gt_aggregate_bwd(int dt, int conv, const void* x, const void* dout, void* dx, int64_t N,
@@ -111,7 +112,16 @@ int gt_aggregate_bwd(int dt, int conv, const void* x, const void* dout, void* dx
                      int edge_kind, const float* edge_attr, int32_t kdim, const float* edge_w,
                      const float* edge_b, const int32_t* etype, const float* table, int32_t ntypes,
                      const float* self_param,
-                     float* d_edge_w, float* d_edge_b, float* d_table, float* d_self, void* stream);
+                     float* d_edge_w, float* d_edge_b, float* d_table, float* d_self, const float* norm_slot,
+                     const int32_t* etype_slot, const float* attr_slot, void* stream);
+/* per-CSR-slot copies of the per-edge data, computed once per batch and reused by every layer (optional; NULL
+ * arguments to gt_aggregate_* mean "follow the indirection in-kernel").  For the CSR given by (rowptr_slot, nbr_slot,
+ * eid_slot) - target-sorted for the forward, source-sorted for the adjoint: norm_slot[p] = GCN norm of the edge in
+ * slot p (deg = out-degree + 1 from rowptr_src), etype_slot[p] = etype[eid], attr_slot[p,:] = edge_attr[eid,:]. */
+int gt_edge_slots(const int32_t* rowptr_slot, const int32_t* nbr_slot, const int32_t* eid_slot,
+                  const int32_t* rowptr_src, int64_t E, int64_t N, const int32_t* etype,
+                  const float* edge_attr, int32_t kdim, float* norm_slot, int32_t* etype_slot,
+                  float* attr_slot, void* stream);
 
 /* ---- per-graph segment ops (PyG global_add_pool / vn[batch], reference
  *      modules/gnn_module.py:199,219) --------------------------------------------------------
@@ -135,6 +145,14 @@ int gt_bn_finalize(const double* stats, int64_t M, int32_t d, int32_t ld, const 
 int gt_bn_apply_fwd(int dt, const void* x, int64_t M, int32_t d, int32_t ld, const float* ssmr,
                     int relu, const void* resid, const float* gvec, const int32_t* node_graph,
                     void* y, float drop_p, const uint64_t* rng_state, uint64_t salt, void* stream);
+/* gt_bn_finalize + gt_bn_apply_fwd in one launch (the path the modules use): scale/shift are derived from `stats`
+ * (train, from gt_colstats) or the running statistics (eval) inside the kernel; ssmr [4*ld] is written for the
+ * backward, running statistics / num_batches_tracked are updated in train mode. */
+int gt_bn_norm_fwd(int dt, const void* x, int64_t M, int32_t d, int32_t ld, const double* stats,
+                   const float* gamma, const float* beta, float* running_mean, float* running_var,
+                   int64_t* nbt, float momentum, float eps, int training, int relu, const void* resid,
+                   const float* gvec, const int32_t* node_graph, void* y, float* ssmr, float drop_p,
+                   const uint64_t* rng_state, uint64_t salt, void* stream);
 /* backward pass 1: g = dy * keep/(1-p) * relu'(x*scale+shift); red[0:ld] += sum g,
  * red[ld:2ld] += sum g*xhat */
 int gt_bn_bwd_reduce(int dt, const void* x, const void* dy, int64_t M, int32_t d, int32_t ld,
