@@ -104,7 +104,7 @@ def dt_of(t: torch.Tensor) -> int:
 
 
 def stream():
-    return torch.cuda.current_stream().cuda_stream
+    return torch.cuda.current_stream().cuda_stream   # follows torch.cuda.stream(...) contexts (side streams, capture)
 
 
 def call(name, *args):

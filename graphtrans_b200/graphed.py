@@ -51,6 +51,7 @@ class GraphedStep:
         self.buckets.zero_grad()
         loss = self.loss_fn(self.model(b), b)
         loss.backward()
+        ops.join_wgrad_stream()       # weight gradients issued on the side stream (ops.enable_wgrad_stream)
         return loss.detach()
 
     def _capture(self, batch, sig):

@@ -41,12 +41,23 @@ class PNAConv(nn.Module):
         F, T = self.F_in, self.towers
         pre_w = [m[0].weight for m in self.pre_nns]
         pre_b = [m[0].bias for m in self.pre_nns]
+        post_w = [m[0].weight for m in self.post_nns]
+        post_b = [m[0].bias for m in self.post_nns]
         # W_pre [x_i || x_j] = W_i x_i + W_j x_j: project per NODE, then reduce over in-edges
-        pi = ops.tower_linear(x, pre_w, pre_b, F, F, w_col_off=0)
-        pj = ops.tower_linear(x, pre_w, None, F, F, w_col_off=F)
-        agg = ops.pna_reduce(x, pj, pi, plan, T, F, self.avg_deg["log"])      # [N, T*13F]
-        y = ops.tower_linear(agg, [m[0].weight for m in self.post_nns], [m[0].bias for m in self.post_nns],
-                             13 * F, 13 * F)
+        if ops.precision() == "bf16" and (T * F) % 8 == 0 and (13 * F * T) % 8 == 0:
+            # tensor-core path: the four towers as ONE block-diagonal contraction per stage (tower slices of width F
+            # are not 16-byte aligned for F = 68, whole matrices are); the off-diagonal zero blocks only cost MMA slots
+            w_i = torch.block_diag(*[w[:, :F] for w in pre_w])             # [T*F, T*F]
+            w_j = torch.block_diag(*[w[:, F:] for w in pre_w])
+            pi = ops.linear(x, w_i, torch.cat(pre_b))
+            pj = ops.linear(x, w_j)
+            agg = ops.pna_reduce(x, pj, pi, plan, T, F, self.avg_deg["log"])  # [N, T*13F]
+            y = ops.linear(agg, torch.block_diag(*post_w), torch.cat(post_b))
+        else:
+            pi = ops.tower_linear(x, pre_w, pre_b, F, F, w_col_off=0)
+            pj = ops.tower_linear(x, pre_w, None, F, F, w_col_off=F)
+            agg = ops.pna_reduce(x, pj, pi, plan, T, F, self.avg_deg["log"])  # [N, T*13F]
+            y = ops.tower_linear(agg, post_w, post_b, 13 * F, 13 * F)
         return ops.linear(y, self.lin.weight, self.lin.bias)
 
 

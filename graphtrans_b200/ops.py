@@ -126,6 +126,48 @@ def next_salt() -> int:
     return _salt[0]
 
 
+# ----------------------------------------------------------------------------- weight-gradient side stream
+# Weight / bias gradients are off the critical path of the backward pass (nothing upstream consumes them), so they
+# can run on a second stream next to the memory-bound kernels of the next layer (BN / LayerNorm backward, aggregation
+# adjoint ...), which co-reside on an SM with the one-CTA-per-SM persistent GEMM.  Opt-in: whoever enables it must
+# call join_wgrad_stream() after backward() and before reading gradients (GraphedStep and bench.py do).
+_wgrad = {"stream": None}
+
+
+def enable_wgrad_stream(on=True, device="cuda"):
+    _wgrad["stream"] = torch.cuda.Stream(device=device) if on else None
+
+
+def join_wgrad_stream():
+    st = _wgrad["stream"]
+    if st is not None:
+        torch.cuda.current_stream().wait_stream(st)
+
+
+class _WgradCtx:
+    """`with _WgradCtx(tensors...)`: run the enclosed launches on the side stream (if enabled), ordered after
+    everything issued so far on the current stream; the tensors are kept alive for that stream."""
+
+    def __init__(self, *tensors):
+        self.tensors = [t for t in tensors if t is not None]
+        self.ctx = None
+
+    def __enter__(self):
+        st = _wgrad["stream"]
+        if st is not None:
+            st.wait_stream(torch.cuda.current_stream())
+            for t in self.tensors:
+                t.record_stream(st)
+            self.ctx = torch.cuda.stream(st)
+            self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+        return False
+
+
 # ----------------------------------------------------------------------------- fused gradient delivery
 # A parameter may carry `_gt_main_grad` (an fp32 tensor of its shape, normally a view into the flat arena of
 # graphtrans_b200.ddp.GradBuckets, zeroed once per step).  The backward kernels then ACCUMULATE the parameter
@@ -367,9 +409,11 @@ class _EmbedSumFn(torch.autograd.Function):
         a_str = (ctypes.c_int64 * n)(*strides)
         a_clp = (ctypes.c_int64 * n)(*clamps)
         a_tab = (ctypes.c_void_p * n)(*[t[0].data_ptr() for t in targets])
-        call("gt_embed_sum_bwd", dt_of(g), ptr(g), N, d, ld, n, a_idx, a_str, a_clp, a_tab)
-        for t in ctx.tables:
-            _grad_done(t)
+        side_ok = all(_main_grad(t) is not None for t in ctx.tables)   # leaf-only gradients: off the critical path
+        with (_WgradCtx(g) if side_ok else _WgradCtx()):
+            call("gt_embed_sum_bwd", dt_of(g), ptr(g), N, d, ld, n, a_idx, a_str, a_clp, a_tab)
+            for t in ctx.tables:
+                _grad_done(t)
         return (None, *[t[1] for t in targets])
 
 
@@ -463,16 +507,19 @@ class _LinearFn(torch.autograd.Function):
             _gemm_raw(dt_of(x), gy.data_ptr(), 0, ld_out, wptr, 1, ldw, gx.data_ptr(), ld_in, M, K, N, ld_in, None,
                       None, 0, 0)
         weight, bias = ctx.params
-        if ctx.needs_input_grad[1]:
-            tgt, gw = _grad_target(weight)
-            # dW[n,k] = sum_m dY[m,n] X[m,k]: both operands MN-major, split-K over the rows, accumulated in place
-            _gemm_raw(dt_of(x), gy.data_ptr(), 1, ld_out, x.data_ptr(), 1, ld_in, tgt.data_ptr() + off * 4, Kw, N, K, M,
-                      K, None, None, 0, EPI_ACCUM | EPI_OUT_F32)
-            _grad_done(weight)
-        if has_bias and ctx.needs_input_grad[2]:
-            tgt, gb = _grad_target(bias)
-            call("gt_colsum", dt_of(gy), ptr(gy), M, N, ld_out, ptr(tgt))
-            _grad_done(bias)
+        # parameter gradients accumulated in place need no ordering with the rest of the backward: side stream
+        side_ok = _main_grad(weight) is not None and (not has_bias or _main_grad(bias) is not None)
+        with (_WgradCtx(gy, x) if side_ok else _WgradCtx()):
+            if ctx.needs_input_grad[1]:
+                tgt, gw = _grad_target(weight)
+                # dW[n,k] = sum_m dY[m,n] X[m,k]: both operands MN-major, split-K over the rows, accumulated in place
+                _gemm_raw(dt_of(x), gy.data_ptr(), 1, ld_out, x.data_ptr(), 1, ld_in, tgt.data_ptr() + off * 4, Kw, N, K,
+                          M, K, None, None, 0, EPI_ACCUM | EPI_OUT_F32)
+                _grad_done(weight)
+            if has_bias and ctx.needs_input_grad[2]:
+                tgt, gb = _grad_target(bias)
+                call("gt_colsum", dt_of(gy), ptr(gy), M, N, ld_out, ptr(tgt))
+                _grad_done(bias)
         return gx, gw, gb, None, None, g_res, None, None, None, None
 
 

@@ -20,7 +20,7 @@ GRAD_TOL = 1e-3
 WORST_TOL = 5e-3
 
 
-def run_product(args, batch, init_sd, precision="fp32", train=True, buckets=False):
+def run_product(args, batch, init_sd, precision="fp32", train=True, buckets=False, wgrad_stream=False):
     ops.set_precision(precision)
     model = factory.build_model(args).cuda()
     model.load_state_dict(init_sd, strict=True)
@@ -33,9 +33,15 @@ def run_product(args, batch, init_sd, precision="fp32", train=True, buckets=Fals
         gb.zero_grad()
     else:
         model.zero_grad()
-    pred = model(b)
-    loss = factory.loss_fn(args)(pred, b)
-    loss.backward()
+    if wgrad_stream:
+        ops.enable_wgrad_stream(True)
+    try:
+        pred = model(b)
+        loss = factory.loss_fn(args)(pred, b)
+        loss.backward()
+        ops.join_wgrad_stream()
+    finally:
+        ops.enable_wgrad_stream(False)
     torch.cuda.synchronize()
     grads = {k: (p.grad.detach().clone() if p.grad is not None else torch.zeros_like(p))
              for k, p in model.named_parameters()}
@@ -62,6 +68,17 @@ def test_golden_fwd_bwd_fp32(name):
         pe = model(fx["batch"].clone().to("cuda"))
     for a, b in zip(as_list(pe), as_list(fx["logits_eval"])):
         assert rel_l2(a, b) < LOGIT_TOL
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_golden_grads_with_wgrad_side_stream(name):
+    """weight / bias / embedding gradients issued on the second stream (ops.enable_wgrad_stream): same parity bar"""
+    fx = load_golden(name)
+    _, pred, loss, grads, _ = run_product(fx["args"], fx["batch"], fx["init_sd"], buckets=True, wgrad_stream=True)
+    for a, b in zip(as_list(pred), as_list(fx["logits"])):
+        assert rel_l2(a.detach(), b) < LOGIT_TOL
+    glob, worst, key = grad_report(grads, fx["grads"])
+    assert glob < GRAD_TOL and worst < WORST_TOL, (glob, worst, key)
 
 
 @pytest.mark.parametrize("name", GOLDEN_CASES)
