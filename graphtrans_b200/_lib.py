@@ -36,6 +36,7 @@ SIGNATURES = {
     "gt_aggregate_bwd": [I, I, P, P, P, L, I32, I32, P, P, P, P, I, P, I32, P, P, P, P, I32, P, P, P, P, P, P, P, P, P],
     "gt_edge_slots": [P, P, P, P, L, L, P, P, I32, P, P, P, P],
     "gt_segment_sum": [I, P, P, L, I32, P, P],
+    "gt_segment_sum_sorted": [I, P, P, L, I32, P, P],
     "gt_add_graph_vec": [I, P, P, P, L, I32, P, P],
     "gt_colstats": [I, P, L, I32, P, P],
     "gt_bn_finalize": [P, L, I32, I32, P, P, P, P, P, F, F, I, P, P],
@@ -57,6 +58,10 @@ SIGNATURES = {
     "gt_mha_meta": [P, P, L, L, P, P, P],
     "gt_mha_fwd": [I, P, P, P, P, P, P, L, L, I32, I32, F, P, P, F, P, U64, I, P],
     "gt_mha_bwd": [I, P, P, P, P, P, P, P, P, P, L, L, I32, I32, F, P, P, F, P, U64, I, P],
+    "gt_bce_masked_fwd": [P, P, L, I32, L, L, P, P, P],
+    "gt_bce_masked_bwd": [P, P, L, I32, L, L, P, P, P, L, I32, P],
+    "gt_ce_fwd": [P, P, L, L, I32, L, P, P, P, P],
+    "gt_ce_bwd": [P, P, L, L, I32, L, P, P, P, L, I32, P],
     "gt_pna_reduce_fwd": [I, P, P, P, L, I32, I32, I32, P, P, F, P, I32, P, P, P],
     "gt_pna_reduce_bwd": [I, P, P, P, L, I32, I32, I32, I32, P, P, F, P, P, P, P, P, P],
 }

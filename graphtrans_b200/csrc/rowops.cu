@@ -38,6 +38,31 @@ __global__ void k_segment_sum(const T* __restrict__ x, const int32_t* __restrict
     }
 }
 
+// sorted variant (graphs own contiguous row ranges [node_off[g], node_off[g+1])): one warp per (graph, 128-channel
+// chunk) sums its rows in registers and is the single writer of out[g, chunk] - no atomics, deterministic
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_segment_sum_sorted(const T* __restrict__ x, const int32_t* __restrict__ node_off, int B, int ld, int nch,
+                     float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int item = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (item >= B * nch) return;
+    const int g = item / nch, c0 = (item - g * nch) * 128 + lane * 4;
+    if (c0 >= ld) return;
+    const int r0 = node_off[g], r1 = node_off[g + 1];
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (int r = r0; r < r1; ++r) {
+        float v[4];
+        ld4(x + (int64_t)r * ld + c0, v);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[q] += v[q];
+    }
+    float* o = out + (int64_t)g * ld + c0;
+    float4 cur = *reinterpret_cast<float4*>(o);
+    *reinterpret_cast<float4*>(o) = make_float4(cur.x + acc[0], cur.y + acc[1], cur.z + acc[2], cur.w + acc[3]);
+}
+
 template <typename T>
 __global__ void k_add_graph_vec(const T* __restrict__ x, const float* __restrict__ v,
                                 const int32_t* __restrict__ node_graph, int64_t N, int ld, T* __restrict__ y) {
@@ -822,6 +847,15 @@ extern "C" int gt_segment_sum(int dt, const void* x, const int32_t* node_graph, 
     return 0;
 }
 
+extern "C" int gt_segment_sum_sorted(int dt, const void* x, const int32_t* node_off, int64_t B, int32_t ld, float* out,
+                                     void* stream) {
+    GT_CHECK_ARG(B > 0 && ld > 0 && ld % 4 == 0, "gt_segment_sum_sorted: bad shape");
+    const int nch = (ld + 127) / 128;
+    GT_DISPATCH_DT(dt, (k_segment_sum_sorted<T><<<(unsigned)((B * nch + 7) / 8), 256, 0, ST>>>((const T*)x, node_off, (int)B, ld, nch, out)));
+    GT_LAUNCH_CHECK("gt_segment_sum_sorted");
+    return 0;
+}
+
 extern "C" int gt_add_graph_vec(int dt, const void* x, const float* v, const int32_t* node_graph, int64_t N,
                                 int32_t ld, void* y, void* stream) {
     GT_CHECK_ARG(N > 0 && ld > 0 && ld % 4 == 0, "gt_add_graph_vec: bad shape");
@@ -917,10 +951,12 @@ extern "C" int gt_layernorm_bwd(int dt, const void* dy, const void* presum, cons
                                 const uint64_t* rng_state, uint64_t salt, void* stream) {
     GT_CHECK_ARG(!dx_drop || !out_rows, "gt_layernorm_bwd: dropout and row scatter are exclusive");
     GT_CHECK_ARG(M > 0 && d > 0 && d % 4 == 0 && d <= LN_MAXV * 128, "gt_layernorm_bwd: bad d=%d", d);
-    const int grid = blocks_for(M, 8 * 4, kNumSMs * 4);
+    // every block ends with 2*d global atomics for dgamma / dbeta: at most one 16-warp block per SM keeps the
+    // serialised L2 atomics per address at <= 148 while 16 warps still cover the memory latency
+    const int grid = blocks_for(M, 16 * 2, kNumSMs);
     GT_DISPATCH_DT(dt, {
-        if (d <= 256) k_layernorm_bwd<T, 2><<<grid, 256, 2 * d * sizeof(float), ST>>>((const T*)dy, (const T*)presum, mean_rstd, out_rows, M, d, gamma, (T*)dx, dgamma, dbeta, dcls, (T*)dx_drop, drop_p, rng_state, salt);
-        else k_layernorm_bwd<T, LN_MAXV><<<grid, 256, 2 * d * sizeof(float), ST>>>((const T*)dy, (const T*)presum, mean_rstd, out_rows, M, d, gamma, (T*)dx, dgamma, dbeta, dcls, (T*)dx_drop, drop_p, rng_state, salt);
+        if (d <= 256) k_layernorm_bwd<T, 2><<<grid, 512, 2 * d * sizeof(float), ST>>>((const T*)dy, (const T*)presum, mean_rstd, out_rows, M, d, gamma, (T*)dx, dgamma, dbeta, dcls, (T*)dx_drop, drop_p, rng_state, salt);
+        else k_layernorm_bwd<T, LN_MAXV><<<grid, 512, 2 * d * sizeof(float), ST>>>((const T*)dy, (const T*)presum, mean_rstd, out_rows, M, d, gamma, (T*)dx, dgamma, dbeta, dcls, (T*)dx_drop, drop_p, rng_state, salt);
     });
     GT_LAUNCH_CHECK("gt_layernorm_bwd");
     return 0;

@@ -36,25 +36,34 @@ def build_model(args):
 
 
 def loss_fn(args):
+    """the reference's calc_loss(pred, batch, m=1.0) per dataset kind; on CUDA tensors the fused device-resident
+    kernels (gt_ce_*, gt_bce_masked_*) are used, otherwise the reference's torch formulation"""
+    from . import ops
     ds = args.dataset
     if ds == "code2":
         def calc_loss(pred_list, batch, m=1.0):
             loss = 0
             for i in range(len(pred_list)):
-                loss += F.cross_entropy(pred_list[i].to(torch.float32), batch.y_arr[:, i])
+                if pred_list[i].is_cuda:
+                    loss = loss + ops.cross_entropy_mean(pred_list[i], batch.y_arr[:, i])
+                else:
+                    loss = loss + F.cross_entropy(pred_list[i].to(torch.float32), batch.y_arr[:, i])
             return loss / len(pred_list) / m
         return calc_loss
     if ds in ("mol", "syn"):
         def calc_loss(pred, batch, m=1.0):
-            # mean over labelled (non-NaN) entries as dataset/mol.py:24-31, written without the boolean
-            # gather (pred[is_labeled] forces a device->host sync): masked sum / count
+            # mean over labelled (non-NaN) entries as dataset/mol.py:24-31 (the reference's boolean gather
+            # pred[is_labeled] forces a device->host sync; the kernel counts and sums on the device)
+            if pred.is_cuda:
+                return ops.bce_with_logits_masked_mean(pred, batch.y) / m
             is_labeled = batch.y == batch.y
-            y = torch.where(is_labeled, batch.y, torch.zeros_like(batch.y)).to(torch.float32)
-            per = F.binary_cross_entropy_with_logits(pred.to(torch.float32), y, reduction="none")
-            return (per * is_labeled).sum() / is_labeled.sum() / m
+            return F.binary_cross_entropy_with_logits(pred.to(torch.float32)[is_labeled],
+                                                      batch.y.to(torch.float32)[is_labeled]) / m
         return calc_loss
     if ds == "nci1":
         def calc_loss(pred, batch, m=1.0):
+            if pred.is_cuda:
+                return ops.cross_entropy_mean(pred, batch.y) / m
             return F.cross_entropy(pred, batch.y) / m
         return calc_loss
     raise ValueError(ds)

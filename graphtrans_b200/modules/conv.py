@@ -17,10 +17,11 @@ def _edge_encoder_args(edge_encoder, edge_attr, plan, d, ld):
     elif hasattr(edge_encoder, "bond_embedding_list"):        # ogb BondEncoder, reference dataset/mol.py:84
         embs = [e.weight for e in edge_encoder.bond_embedding_list][: edge_attr.shape[1]]
         dims = [w.shape[0] for w in embs]
-        table = embs[0]
-        for w in embs[1:]:                                     # mixed-radix combined table (tiny: <= 60 rows)
-            table = (table.unsqueeze(1) + w.unsqueeze(0)).reshape(-1, d)
-        return dict(edge_kind=EDGE_TABLE, etype=plan.edge_type(edge_attr, dims), table=ops.pad_cols(table, ld))
+        # combined mixed-radix table (tiny: <= 60 rows): row t = sum_c emb_c[digit_c(t)], one gt_embed_sum launch
+        # forward and one backward instead of a chain of broadcast adds
+        digits = _mixed_radix_digits(tuple(dims), edge_attr.device)
+        table = ops.embed_sum(digits, embs, dtype=torch.float32)
+        return dict(edge_kind=EDGE_TABLE, etype=plan.edge_type(edge_attr, dims), table=table)
     elif not isinstance(edge_encoder, torch.nn.Module):       # `zero` closure, reference dataset/tud.py:67-71
         ee = edge_encoder(edge_attr)
         if isinstance(ee, (int, float)) and ee == 0:
@@ -30,6 +31,25 @@ def _edge_encoder_args(edge_encoder, edge_attr, plan, d, ld):
     ee = edge_encoder(edge_attr)
     etype = torch.arange(ee.shape[0], dtype=torch.int32, device=ee.device)
     return dict(edge_kind=EDGE_TABLE, etype=etype, table=ops.pad_cols(ee.to(torch.float32), ld))
+
+
+_DIGITS = {}
+
+
+def _mixed_radix_digits(dims, device):
+    """digit_c(t) of every combined edge type t in [0, prod(dims)) - cached int64 index columns"""
+    key = (dims, str(device))
+    if key not in _DIGITS:
+        total = 1
+        for v in dims:
+            total *= v
+        t = torch.arange(total, dtype=torch.long, device=device)
+        cols, div = [], total
+        for v in dims:
+            div //= v
+            cols.append(((t // div) % v).contiguous())
+        _DIGITS[key] = cols
+    return _DIGITS[key]
 
 
 class _ConvBase(torch.nn.Module):

@@ -417,16 +417,16 @@ class _EmbedSumFn(torch.autograd.Function):
         return (None, *[t[1] for t in targets])
 
 
-def embed_sum(index_cols, tables, clamps=None):
-    """out[i] = sum_c tables[c][min(index_cols[c][i], clamp_c)] -> physical [N, ldp(d)].
-    index_cols: list of int64 1-D views (any stride) of length N."""
+def embed_sum(index_cols, tables, clamps=None, dtype=None):
+    """out[i] = sum_c tables[c][min(index_cols[c][i], clamp_c)] -> physical [N, ldp(d)] (activation dtype unless
+    `dtype` is given).  index_cols: list of int64 1-D views (any stride) of length N."""
     d = tables[0].shape[1]
     N = index_cols[0].shape[0]
     if d % 4:
         raise RuntimeError("embedding width must be a multiple of 4")
     strides = [c.stride(0) if c.dim() else 1 for c in index_cols]
     clamps = clamps or [t.shape[0] - 1 for t in tables]
-    meta = (list(index_cols), strides, list(clamps), N, d, ldp(d), act_dtype())
+    meta = (list(index_cols), strides, list(clamps), N, d, ldp(d), dtype or act_dtype())
     return _EmbedSumFn.apply(meta, *tables)
 
 
@@ -596,7 +596,7 @@ class _SegmentSumFn(torch.autograd.Function):
         x = x.contiguous()
         N, ld = x.shape
         out = zeros_f32((plan.B, ld), x.device) if init is None else init.clone()
-        call("gt_segment_sum", dt_of(x), ptr(x), ptr(plan.node_graph), N, ld, ptr(out))
+        call("gt_segment_sum_sorted", dt_of(x), ptr(x), ptr(plan.node_off), plan.B, ld, ptr(out))
         ctx.meta = (plan, x.dtype, N, ld)
         return out
 
@@ -634,7 +634,7 @@ class _AddGraphVecFn(torch.autograd.Function):
         dv = None
         if ctx.needs_input_grad[1]:
             dv = zeros_f32((plan.B, ld), g.device)
-            call("gt_segment_sum", dt_of(g), ptr(g), ptr(plan.node_graph), N, ld, ptr(dv))
+            call("gt_segment_sum_sorted", dt_of(g), ptr(g), ptr(plan.node_off), plan.B, ld, ptr(dv))
         return g, dv, None
 
 
@@ -694,7 +694,7 @@ class _BatchNormFn(torch.autograd.Function):
         dgv = None
         if has_gvec and ctx.needs_input_grad[11]:
             dgv = zeros_f32((plan.B, ld), dev)
-            call("gt_segment_sum", dt_of(g), ptr(g), ptr(plan.node_graph), M, ld, ptr(dgv))
+            call("gt_segment_sum_sorted", dt_of(g), ptr(g), ptr(plan.node_off), plan.B, ld, ptr(dgv))
         return dx, dgamma, dbeta, None, None, None, None, None, None, None, dres, dgv, None, None, None
 
 
@@ -966,3 +966,65 @@ class _PNAReduceFn(torch.autograd.Function):
 def pna_reduce(x, pj, pi, plan, towers, F, delta):
     """[N, towers*13F]: per tower [x_t | scaled (mean,max,min,std) x 3 scalers] (post-MLP operand)"""
     return _PNAReduceFn.apply(x, pj, pi, plan, towers, F, delta)
+
+
+# ----------------------------------------------------------------------------- fused losses
+class _BCEMaskedFn(torch.autograd.Function):
+    """mean over labelled (non-NaN) entries of BCE-with-logits (reference dataset/mol.py:24-31), device-resident"""
+
+    @staticmethod
+    def forward(ctx, x, y):
+        if x.dtype != torch.float32 or x.stride(-1) != 1:
+            x = x.float().contiguous()
+        y = y.to(torch.float32)
+        if y.stride(-1) != 1:
+            y = y.contiguous()
+        rows, cols = x.shape
+        acc = torch.zeros(3, dtype=torch.float32, device=x.device)
+        loss = torch.empty((), dtype=torch.float32, device=x.device)
+        call("gt_bce_masked_fwd", ptr(x), ptr(y), rows, cols, x.stride(0), y.stride(0), ptr(acc), ptr(loss))
+        ctx.save_for_backward(x, y, acc)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        x, y, acc = ctx.saved_tensors
+        rows, cols = x.shape
+        dx = torch.empty(rows, cols, dtype=torch.float32, device=x.device)
+        g = g.contiguous()
+        call("gt_bce_masked_bwd", ptr(x), ptr(y), rows, cols, x.stride(0), y.stride(0), ptr(acc), ptr(g), ptr(dx), cols, cols)
+        return dx, None
+
+
+def bce_with_logits_masked_mean(pred, y):
+    return _BCEMaskedFn.apply(pred, y)
+
+
+class _CEFn(torch.autograd.Function):
+    """mean cross-entropy over rows (reference dataset/code.py:39-45 per head, dataset/tud.py:25-27)"""
+
+    @staticmethod
+    def forward(ctx, x, target):
+        if x.dtype != torch.float32 or x.stride(-1) != 1:
+            x = x.float().contiguous()
+        rows, cols = x.shape
+        acc = torch.zeros(3, dtype=torch.float32, device=x.device)
+        lse = torch.empty(rows, dtype=torch.float32, device=x.device)
+        loss = torch.empty((), dtype=torch.float32, device=x.device)
+        call("gt_ce_fwd", ptr(x), ptr(target), target.stride(0), rows, cols, x.stride(0), ptr(lse), ptr(acc), ptr(loss))
+        ctx.save_for_backward(x, target, lse)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        x, target, lse = ctx.saved_tensors
+        rows, cols = x.shape
+        dx = torch.empty(rows, cols, dtype=torch.float32, device=x.device)
+        g = g.contiguous()
+        call("gt_ce_bwd", ptr(x), ptr(target), target.stride(0), rows, cols, x.stride(0), ptr(lse), ptr(g), ptr(dx), cols, cols)
+        return dx, None
+
+
+def cross_entropy_mean(pred, target):
+    """pred [rows, classes] fp32 (row-strided views are fine), target int64 [rows] (any stride)"""
+    return _CEFn.apply(pred, target)

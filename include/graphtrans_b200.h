@@ -128,6 +128,10 @@ int gt_edge_slots(const int32_t* rowptr_slot, const int32_t* nbr_slot, const int
  * segment_sum: out[g,:] (fp32 [B,ld], pre-zeroed unless init given) += sum_{i in g} x[i,:] */
 int gt_segment_sum(int dt, const void* x, const int32_t* node_graph, int64_t N, int32_t ld,
                    float* out, void* stream);
+/* same for graphs that own contiguous row ranges [node_off[g], node_off[g+1]) (PyG batches are sorted): one warp per
+ * (graph, 128-channel chunk), single writer, no atomics (deterministic); out [B, ld] fp32 is accumulated into */
+int gt_segment_sum_sorted(int dt, const void* x, const int32_t* node_off, int64_t B, int32_t ld, float* out,
+                          void* stream);
 /* y[i,:] = x[i,:] + v[node_graph[i],:]   (v fp32 [B,ld]); x may be NULL (pure broadcast) */
 int gt_add_graph_vec(int dt, const void* x, const float* v, const int32_t* node_graph, int64_t N,
                      int32_t ld, void* y, void* stream);
@@ -267,6 +271,21 @@ int gt_pna_reduce_bwd(int dt, const void* pj, const void* out, const void* dout,
                       int32_t towers, int32_t F, int32_t ld, int32_t ld_out, const int32_t* rowptr_dst,
                       const int32_t* src_by_dst, float delta, const int32_t* argmax,
                       const int32_t* argmin, float* dpj, void* dpi, void* dx, void* stream);
+
+/* ---- fused losses of the reference's dataset adapters (caller side of the path; device-resident, no host sync) ----
+ * BCE-with-logits averaged over the labelled (non-NaN) entries (reference dataset/mol.py:24-31): x, y fp32
+ * [rows, cols] with row pitches ldx / ldy; acc fp32 [3] zeroed by the caller (sum, count, block ticket); loss fp32 [1].
+ * Backward: dx [rows, dcols >= cols] (pad columns := 0) = g[0] * (sigmoid(x) - y) / count on labelled entries. */
+int gt_bce_masked_fwd(const float* x, const float* y, int64_t rows, int32_t cols, int64_t ldx, int64_t ldy,
+                      float* acc, float* loss, void* stream);
+int gt_bce_masked_bwd(const float* x, const float* y, int64_t rows, int32_t cols, int64_t ldx, int64_t ldy,
+                      const float* acc, const float* g, float* dx, int64_t lddx, int32_t dcols, void* stream);
+/* mean cross-entropy over rows (reference dataset/code.py:39-45 per head, dataset/tud.py:25-27): target int64 with
+ * element stride tstride; lse fp32 [rows] saved for the backward; acc fp32 [3] zeroed by the caller. */
+int gt_ce_fwd(const float* x, const int64_t* target, int64_t tstride, int64_t rows, int32_t cols, int64_t ldx,
+              float* lse, float* acc, float* loss, void* stream);
+int gt_ce_bwd(const float* x, const int64_t* target, int64_t tstride, int64_t rows, int32_t cols, int64_t ldx,
+              const float* lse, const float* g, float* dx, int64_t lddx, int32_t dcols, void* stream);
 
 #ifdef __cplusplus
 }
