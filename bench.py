@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--distinct-batches", type=int, default=4)
     ap.add_argument("--no-wgrad-stream", action="store_true", help="keep weight gradients on the main stream")
+    ap.add_argument("--no-branch-stream", action="store_true", help="keep the virtual-node branch on the main stream")
     ap.add_argument("--eager", action="store_true", help="no CUDA-graph replay: launch every kernel from Python")
     return ap.parse_args()
 
@@ -332,12 +333,14 @@ def main_b200(ns):
 
     if not ns.no_wgrad_stream:
         ops.enable_wgrad_stream(True, dev)   # weight / bias / embedding gradients overlap the rest of the backward
+    if not ns.no_branch_stream:
+        ops.enable_branch_stream(True, dev)  # virtual-node update of a GNN layer runs next to its conv
 
     def eager_step(b):
         buckets.zero_grad()
         loss = lossf(model(b), b)
         loss.backward()
-        ops.join_wgrad_stream()
+        ops.join_side_streams()
         buckets.finish()
         return loss.detach()
 
@@ -428,7 +431,7 @@ def main_b200(ns):
                        "distinct_batches": len(dev_batches), "dropout": {"gnn": args.gnn_dropout,
                                                                          "transformer": args.transformer_dropout},
                        "step": "zero_grad+forward+loss+backward" + ("+NCCL gradient allreduce (4 buckets)" if world > 1 else ""),
-                       "wgrad_stream": not ns.no_wgrad_stream,
+                       "wgrad_stream": not ns.no_wgrad_stream, "branch_stream": not ns.no_branch_stream,
                        "launch": "eager (Python launches every kernel)" if graphed is None else
                                  "CUDA-graph replay per batch shape signature (captured in warm-up); inputs copied into static buffers inside the timed region",
                        "wall_ms_per_step_incl_flush": wall / K * 1e3},

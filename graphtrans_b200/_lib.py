@@ -36,7 +36,7 @@ SIGNATURES = {
     "gt_aggregate_bwd": [I, I, P, P, P, L, I32, I32, P, P, P, P, I, P, I32, P, P, P, P, I32, P, P, P, P, P, P, P, P, P],
     "gt_edge_slots": [P, P, P, P, L, L, P, P, I32, P, P, P, P],
     "gt_segment_sum": [I, P, P, L, I32, P, P],
-    "gt_segment_sum_sorted": [I, P, P, L, I32, P, P],
+    "gt_segment_sum_sorted": [I, P, P, L, I32, P, P, P],
     "gt_add_graph_vec": [I, P, P, P, L, I32, P, P],
     "gt_colstats": [I, P, L, I32, P, P],
     "gt_bn_finalize": [P, L, I32, I32, P, P, P, P, P, F, F, I, P, P],

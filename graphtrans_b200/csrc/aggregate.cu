@@ -30,9 +30,9 @@ struct EdgeEnc {
     const float* attr_slot;     // LINEAR: [E, kdim] attributes in slot order
 };
 
-template <int EK>
-struct EdgeRegs {  // per-lane edge-encoder parameters of the current 4-channel chunk
-    float w[MAX_KDIM][4];
+template <int EK, int KD = MAX_KDIM>
+struct EdgeRegs {  // per-lane edge-encoder parameters of the current 4-channel chunk (KD = compiled attribute width)
+    float w[KD][4];
     float b[4];
     __device__ __forceinline__ void load(const EdgeEnc& en, int c0, int d) {
         if (EK == GT_EDGE_LINEAR) {
@@ -41,12 +41,12 @@ struct EdgeRegs {  // per-lane edge-encoder parameters of the current 4-channel 
                 const bool ok = c0 + q < d;
                 b[q] = ok ? en.b[c0 + q] : 0.f;
 #pragma unroll
-                for (int k = 0; k < MAX_KDIM; ++k) w[k][q] = (ok && k < en.kdim) ? en.w[(c0 + q) * en.kdim + k] : 0.f;
+                for (int k = 0; k < KD; ++k) w[k][q] = (ok && k < en.kdim) ? en.w[(c0 + q) * en.kdim + k] : 0.f;
             }
         }
     }
     // same with the edge attributes / type already fetched (edge-batched kernels)
-    __device__ __forceinline__ void embed_pre(const EdgeEnc& en, const float (&a)[MAX_KDIM], int ty, int c0, int ld, float (&ee)[4]) const {
+    __device__ __forceinline__ void embed_pre(const EdgeEnc& en, const float (&a)[KD], int ty, int c0, int ld, float (&ee)[4]) const {
         if (EK == GT_EDGE_NONE) {
             ee[0] = ee[1] = ee[2] = ee[3] = 0.f;
         } else if (EK == GT_EDGE_LINEAR) {
@@ -54,7 +54,7 @@ struct EdgeRegs {  // per-lane edge-encoder parameters of the current 4-channel 
             for (int q = 0; q < 4; ++q) {
                 float v = b[q];
 #pragma unroll
-                for (int k = 0; k < MAX_KDIM; ++k) v = fmaf(a[k], w[k][q], v);
+                for (int k = 0; k < KD; ++k) v = fmaf(a[k], w[k][q], v);
                 ee[q] = v;
             }
         } else {
@@ -279,7 +279,7 @@ k_agg_bwd(const T* __restrict__ x, const T* __restrict__ dout, T* __restrict__ d
 // the 32 lanes first fetch up to 32 edges of the node IN PARALLEL (neighbour ids, GCN norms, edge attributes / types),
 // then the warp walks them with register shuffles, and every edge issues the loads of ALL channel chunks of the
 // neighbour row back to back (the whole 600-byte row per edge, several edges in flight through the unrolled loop).
-template <typename T, int CONV, int EK, int NCH>
+template <typename T, int CONV, int EK, int NCH, int KD>
 __global__ void __launch_bounds__(AGG_WARPS * 32)
 k_agg_fwd2(const T* __restrict__ x, T* __restrict__ out, int N, int d, int ld,
            const int32_t* __restrict__ rp_dst, const int32_t* __restrict__ src_by_dst,
@@ -293,7 +293,7 @@ k_agg_fwd2(const T* __restrict__ x, T* __restrict__ out, int N, int d, int ld,
     const int warp = gwarp / nch;
     const int nwarps = gridDim.x * AGG_WARPS / nch;
     const float eps1 = (CONV == GT_CONV_GIN) ? 1.f + self_param[0] : 0.f;
-    EdgeRegs<EK> er[NCH];
+    EdgeRegs<EK, KD> er[NCH];
     float root[NCH][4];
 #pragma unroll
     for (int k = 0; k < NCH; ++k) {
@@ -319,7 +319,7 @@ k_agg_fwd2(const T* __restrict__ x, T* __restrict__ out, int N, int d, int ld,
             const int p = base + lane;
             const bool have = p < e;
             const int j_l = have ? src_by_dst[p] : 0;
-            float nrm_l = 1.f, a_l[MAX_KDIM] = {0.f, 0.f, 0.f, 0.f};
+            float nrm_l = 1.f, a_l[KD] = {};
             int ty_l = 0;
             if (have) {
                 if (CONV == GT_CONV_GCN)
@@ -327,7 +327,7 @@ k_agg_fwd2(const T* __restrict__ x, T* __restrict__ out, int N, int d, int ld,
                 if (EK == GT_EDGE_LINEAR) {
                     const float* ap = en.attr_slot ? en.attr_slot + (int64_t)p * en.kdim : en.attr + (int64_t)eid_by_dst[p] * en.kdim;
 #pragma unroll
-                    for (int k = 0; k < MAX_KDIM; ++k)
+                    for (int k = 0; k < KD; ++k)
                         if (k < en.kdim) a_l[k] = ap[k];
                 } else if (EK == GT_EDGE_TABLE) {
                     ty_l = en.etype_slot ? en.etype_slot[p] : en.etype[eid_by_dst[p]];
@@ -338,11 +338,11 @@ k_agg_fwd2(const T* __restrict__ x, T* __restrict__ out, int N, int d, int ld,
             for (int t = 0; t < cnt; ++t) {
                 const int j = __shfl_sync(0xffffffffu, j_l, t);
                 const float nrm = CONV == GT_CONV_GCN ? __shfl_sync(0xffffffffu, nrm_l, t) : 1.f;
-                float a[MAX_KDIM] = {0.f, 0.f, 0.f, 0.f};
+                float a[KD] = {};
                 int ty = 0;
                 if (EK == GT_EDGE_LINEAR) {
 #pragma unroll
-                    for (int k = 0; k < MAX_KDIM; ++k) a[k] = __shfl_sync(0xffffffffu, a_l[k], t);
+                    for (int k = 0; k < KD; ++k) a[k] = __shfl_sync(0xffffffffu, a_l[k], t);
                 } else if (EK == GT_EDGE_TABLE) {
                     ty = __shfl_sync(0xffffffffu, ty_l, t);
                 }
@@ -379,14 +379,14 @@ k_agg_fwd2(const T* __restrict__ x, T* __restrict__ out, int N, int d, int ld,
 // adjoint, edge-batched: one warp per SOURCE node j, its out-edges fetched 32 at a time.  Edge-table gradients are
 // reduced per block in a dynamic shared-memory table [ntypes][ld] (lanes own distinct channels: conflict-free inside a
 // warp); Linear edge-encoder gradients in registers, then shared memory, then one global atomic per (block, element).
-template <typename T, int CONV, int EK, int NCH>
+template <typename T, int CONV, int EK, int NCH, int KD>
 __global__ void __launch_bounds__(AGG_WARPS * 32)
 k_agg_bwd2(const T* __restrict__ x, const T* __restrict__ dout, T* __restrict__ dx, int N, int d, int ld,
            const int32_t* __restrict__ rp_src, const int32_t* __restrict__ dst_by_src,
            const int32_t* __restrict__ eid_by_src, EdgeEnc en, const float* __restrict__ self_param,
            float* __restrict__ d_edge_w, float* __restrict__ d_edge_b, float* __restrict__ d_table,
            float* __restrict__ d_self, int nch) {
-    extern __shared__ float sh_dyn[];   // TABLE: [ntypes][ld];  LINEAR / GCN: [(2 + MAX_KDIM)][128 * nch]
+    extern __shared__ float sh_dyn[];   // TABLE: [ntypes][ld];  LINEAR / GCN: [(2 + KD)][128 * nch]
     const int lane = threadIdx.x & 31;
     const int gwarp = blockIdx.x * AGG_WARPS + (threadIdx.x >> 5);
     const int cbase = (gwarp % nch) * 128;   // this warp's 128-channel chunk (see k_agg_fwd2)
@@ -395,13 +395,13 @@ k_agg_bwd2(const T* __restrict__ x, const T* __restrict__ dout, T* __restrict__ 
     const int W = 128 * nch;
     float* sh_tab = sh_dyn;
     float* sh_par = sh_dyn + (EK == GT_EDGE_TABLE ? en.ntypes * ld : 0);   // [self | b | w0..w3][W]
-    const int n_par = (2 + MAX_KDIM) * W;
+    const int n_par = (2 + 4) * W;   // host-side layout: [self | b | w0..w3][W]
     for (int i = threadIdx.x; i < (EK == GT_EDGE_TABLE ? en.ntypes * ld : 0) + n_par; i += blockDim.x) sh_dyn[i] = 0.f;
     __syncthreads();
     const float eps1 = (CONV == GT_CONV_GIN) ? 1.f + self_param[0] : 0.f;
     float deps = 0.f;
-    EdgeRegs<EK> er[NCH];
-    float root[NCH][4], a_self[NCH][4], a_b[NCH][4], a_w[NCH][MAX_KDIM][4];
+    EdgeRegs<EK, KD> er[NCH];
+    float root[NCH][4], a_self[NCH][4], a_b[NCH][4], a_w[NCH][KD][4];
 #pragma unroll
     for (int k = 0; k < NCH; ++k) {
         const int c0 = cbase + k * 128 + lane * 4;
@@ -411,7 +411,7 @@ k_agg_bwd2(const T* __restrict__ x, const T* __restrict__ dout, T* __restrict__ 
             root[k][q] = (CONV == GT_CONV_GCN && c0 + q < d) ? self_param[c0 + q] : 0.f;
             a_self[k][q] = a_b[k][q] = 0.f;
 #pragma unroll
-            for (int kk = 0; kk < MAX_KDIM; ++kk) a_w[k][kk][q] = 0.f;
+            for (int kk = 0; kk < KD; ++kk) a_w[k][kk][q] = 0.f;
         }
     }
     for (int j = warp; j < N; j += nwarps) {
@@ -434,7 +434,7 @@ k_agg_bwd2(const T* __restrict__ x, const T* __restrict__ dout, T* __restrict__ 
             const int p = base + lane;
             const bool have = p < e;
             const int i_l = have ? dst_by_src[p] : 0;
-            float nrm_l = 1.f, a_l[MAX_KDIM] = {0.f, 0.f, 0.f, 0.f};
+            float nrm_l = 1.f, a_l[KD] = {};
             int ty_l = 0;
             if (have) {
                 if (CONV == GT_CONV_GCN)
@@ -442,7 +442,7 @@ k_agg_bwd2(const T* __restrict__ x, const T* __restrict__ dout, T* __restrict__ 
                 if (EK == GT_EDGE_LINEAR) {
                     const float* ap = en.attr_slot ? en.attr_slot + (int64_t)p * en.kdim : en.attr + (int64_t)eid_by_src[p] * en.kdim;
 #pragma unroll
-                    for (int k = 0; k < MAX_KDIM; ++k)
+                    for (int k = 0; k < KD; ++k)
                         if (k < en.kdim) a_l[k] = ap[k];
                 } else if (EK == GT_EDGE_TABLE) {
                     ty_l = en.etype_slot ? en.etype_slot[p] : en.etype[eid_by_src[p]];
@@ -453,11 +453,11 @@ k_agg_bwd2(const T* __restrict__ x, const T* __restrict__ dout, T* __restrict__ 
             for (int t = 0; t < cnt; ++t) {
                 const int i = __shfl_sync(0xffffffffu, i_l, t);
                 const float nrm = CONV == GT_CONV_GCN ? __shfl_sync(0xffffffffu, nrm_l, t) : 1.f;
-                float a[MAX_KDIM] = {0.f, 0.f, 0.f, 0.f};
+                float a[KD] = {};
                 int ty = 0;
                 if (EK == GT_EDGE_LINEAR) {
 #pragma unroll
-                    for (int k = 0; k < MAX_KDIM; ++k) a[k] = __shfl_sync(0xffffffffu, a_l[k], t);
+                    for (int k = 0; k < KD; ++k) a[k] = __shfl_sync(0xffffffffu, a_l[k], t);
                 } else if (EK == GT_EDGE_TABLE) {
                     ty = __shfl_sync(0xffffffffu, ty_l, t);
                 }
@@ -478,7 +478,7 @@ k_agg_bwd2(const T* __restrict__ x, const T* __restrict__ dout, T* __restrict__ 
                             for (int q = 0; q < 4; ++q) {
                                 a_b[k][q] += gm[q];
 #pragma unroll
-                                for (int kk = 0; kk < MAX_KDIM; ++kk) a_w[k][kk][q] = fmaf(a[kk], gm[q], a_w[k][kk][q]);
+                                for (int kk = 0; kk < KD; ++kk) a_w[k][kk][q] = fmaf(a[kk], gm[q], a_w[k][kk][q]);
                             }
                         } else if (EK == GT_EDGE_TABLE) {
                             float* row = sh_tab + ty * ld + c0;
@@ -521,7 +521,7 @@ k_agg_bwd2(const T* __restrict__ x, const T* __restrict__ dout, T* __restrict__ 
             if (EK == GT_EDGE_LINEAR) {
                 atomicAdd(&sh_par[W + cw + q], a_b[k][q]);
 #pragma unroll
-                for (int kk = 0; kk < MAX_KDIM; ++kk)
+                for (int kk = 0; kk < KD; ++kk)
                     if (kk < en.kdim) atomicAdd(&sh_par[(2 + kk) * W + cw + q], a_w[k][kk][q]);
             }
         }
@@ -552,7 +552,8 @@ static int launch_fwd(int ek, const T* x, T* out, int N, int d, int ld, const in
                       EdgeEnc en, const float* self_param, cudaStream_t st) {
     const int grid = blocks_for(N, AGG_WARPS, kNumSMs * 8);
     const int nch = (ld + 127) / 128;
-#define L2(EK, NCH) k_agg_fwd2<T, CONV, EK, NCH><<<grid2, AGG_WARPS * 32, 0, st>>>(x, out, N, d, ld, rp_dst, src_by_dst, eid_by_dst, rp_src, en, self_param, nch)
+#define L2K(EK, NCH, KD) k_agg_fwd2<T, CONV, EK, NCH, KD><<<grid2, AGG_WARPS * 32, 0, st>>>(x, out, N, d, ld, rp_dst, src_by_dst, eid_by_dst, rp_src, en, self_param, nch)
+#define L2(EK, NCH) do { if (EK == GT_EDGE_LINEAR && en.kdim > 2) L2K(EK, NCH, 4); else L2K(EK, NCH, 2); } while (0)
 #define L2N(EK) L2(EK, 1)
     // (node, 128-channel chunk) items: the global warp count must be a multiple of nch
     const int grid2 = (blocks_for((int64_t)N * nch, AGG_WARPS, kNumSMs * 8) + nch - 1) / nch * nch;
@@ -568,6 +569,7 @@ static int launch_fwd(int ek, const T* x, T* out, int N, int d, int ld, const in
 #undef L
 #undef L2N
 #undef L2
+#undef L2K
     return 0;
 }
 
@@ -579,11 +581,12 @@ static int launch_bwd(int ek, const T* x, const T* dout, T* dx, int N, int d, in
     int grid = blocks_for(N, AGG_WARPS, kNumSMs * 8);
     const int nch = (ld + 127) / 128;
     const size_t smem2 = sizeof(float) * ((size_t)(2 + MAX_KDIM) * 128 * nch + (ek == GT_EDGE_TABLE ? (size_t)en.ntypes * ld : 0));
-#define L2(EK, NCH) do { \
+#define L2K(EK, NCH, KD) do { \
         static bool attr = false; \
-        if (!attr) { cudaFuncSetAttribute(k_agg_bwd2<T, CONV, EK, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr = true; } \
-        k_agg_bwd2<T, CONV, EK, NCH><<<grid, AGG_WARPS * 32, smem2, st>>>(x, dout, dx, N, d, ld, rp_src, dst_by_src, eid_by_src, en, self_param, dw, db, dtab, dself, nch); \
+        if (!attr) { cudaFuncSetAttribute(k_agg_bwd2<T, CONV, EK, NCH, KD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr = true; } \
+        k_agg_bwd2<T, CONV, EK, NCH, KD><<<grid, AGG_WARPS * 32, smem2, st>>>(x, dout, dx, N, d, ld, rp_src, dst_by_src, eid_by_src, en, self_param, dw, db, dtab, dself, nch); \
     } while (0)
+#define L2(EK, NCH) do { if (EK == GT_EDGE_LINEAR && en.kdim > 2) L2K(EK, NCH, 4); else L2K(EK, NCH, 2); } while (0)
 #define L2N(EK) L2(EK, 1)
 #define L(EK) k_agg_bwd<T, CONV, EK><<<grid, AGG_WARPS * 32, 0, st>>>(x, dout, dx, N, d, ld, rp_src, dst_by_src, eid_by_src, en, self_param, dw, db, dtab, dself)
     static const int variant = getenv("GT_AGG_VARIANT") ? atoi(getenv("GT_AGG_VARIANT")) : 0;

@@ -39,11 +39,12 @@ __global__ void k_segment_sum(const T* __restrict__ x, const int32_t* __restrict
 }
 
 // sorted variant (graphs own contiguous row ranges [node_off[g], node_off[g+1])): one warp per (graph, 128-channel
-// chunk) sums its rows in registers and is the single writer of out[g, chunk] - no atomics, deterministic
+// chunk) sums its rows in registers and is the single writer of out[g, chunk] = init[g, chunk] + sum - no atomics,
+// deterministic, `out` needs no zero fill
 template <typename T>
 __global__ void __launch_bounds__(256)
 k_segment_sum_sorted(const T* __restrict__ x, const int32_t* __restrict__ node_off, int B, int ld, int nch,
-                     float* __restrict__ out) {
+                     const float* __restrict__ init, float* __restrict__ out) {
     const int lane = threadIdx.x & 31;
     const int item = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (item >= B * nch) return;
@@ -58,9 +59,9 @@ k_segment_sum_sorted(const T* __restrict__ x, const int32_t* __restrict__ node_o
 #pragma unroll
         for (int q = 0; q < 4; ++q) acc[q] += v[q];
     }
-    float* o = out + (int64_t)g * ld + c0;
-    float4 cur = *reinterpret_cast<float4*>(o);
-    *reinterpret_cast<float4*>(o) = make_float4(cur.x + acc[0], cur.y + acc[1], cur.z + acc[2], cur.w + acc[3]);
+    float4 cur = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (init) cur = *reinterpret_cast<const float4*>(init + (int64_t)g * ld + c0);
+    *reinterpret_cast<float4*>(out + (int64_t)g * ld + c0) = make_float4(cur.x + acc[0], cur.y + acc[1], cur.z + acc[2], cur.w + acc[3]);
 }
 
 template <typename T>
@@ -847,11 +848,11 @@ extern "C" int gt_segment_sum(int dt, const void* x, const int32_t* node_graph, 
     return 0;
 }
 
-extern "C" int gt_segment_sum_sorted(int dt, const void* x, const int32_t* node_off, int64_t B, int32_t ld, float* out,
-                                     void* stream) {
+extern "C" int gt_segment_sum_sorted(int dt, const void* x, const int32_t* node_off, int64_t B, int32_t ld,
+                                     const float* init, float* out, void* stream) {
     GT_CHECK_ARG(B > 0 && ld > 0 && ld % 4 == 0, "gt_segment_sum_sorted: bad shape");
     const int nch = (ld + 127) / 128;
-    GT_DISPATCH_DT(dt, (k_segment_sum_sorted<T><<<(unsigned)((B * nch + 7) / 8), 256, 0, ST>>>((const T*)x, node_off, (int)B, ld, nch, out)));
+    GT_DISPATCH_DT(dt, (k_segment_sum_sorted<T><<<(unsigned)((B * nch + 7) / 8), 256, 0, ST>>>((const T*)x, node_off, (int)B, ld, nch, init, out)));
     GT_LAUNCH_CHECK("gt_segment_sum_sorted");
     return 0;
 }
@@ -1046,7 +1047,7 @@ static void cast_pad_out(int dt_out, const TI* src, int64_t ri, int64_t ci, int6
 
 extern "C" int gt_cast_pad(int dt_in, const void* src, int64_t rows_in, int64_t cols_in, int64_t ld_in, int dt_out,
                            void* dst, int64_t rows_out, int64_t cols_out, int64_t ld_out, void* stream) {
-    GT_CHECK_ARG(rows_out >= rows_in && cols_out >= cols_in && ld_out >= cols_out && ld_in >= cols_in, "gt_cast_pad: bad shape");
+    GT_CHECK_ARG(rows_out >= rows_in && cols_out >= cols_in && ld_out >= cols_out && (ld_in >= cols_in || ld_in == 0), "gt_cast_pad: bad shape");
     GT_CHECK_ARG((dt_in == GT_F32 || dt_in == GT_BF16) && (dt_out == GT_F32 || dt_out == GT_BF16), "gt_cast_pad: bad dtype");
     if (rows_out * cols_out == 0) return 0;
     if (dt_in == GT_F32) cast_pad_out<float>(dt_out, (const float*)src, rows_in, cols_in, ld_in, dst, rows_out, cols_out, ld_out, ST);

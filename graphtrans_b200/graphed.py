@@ -51,7 +51,7 @@ class GraphedStep:
         self.buckets.zero_grad()
         loss = self.loss_fn(self.model(b), b)
         loss.backward()
-        ops.join_wgrad_stream()       # weight gradients issued on the side stream (ops.enable_wgrad_stream)
+        ops.join_side_streams()       # weight gradients / virtual-node branch issued on side streams (ops.enable_*)
         return loss.detach()
 
     def _capture(self, batch, sig):

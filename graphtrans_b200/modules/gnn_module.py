@@ -123,21 +123,27 @@ class GNN_node_Virtualnode(_GNNBase):
         d, ld = self.emb_dim, ops.ldp(self.emb_dim)
         h0 = self._input(batched_data, perturb)
         # per-graph virtual-node state, fp32 [B, ld]
-        vn = ops.pad_cols(self.virtualnode_embedding.weight, ld).expand(plan.B, ld)
+        vn = ops.broadcast_row(self.virtualnode_embedding.weight, plan.B, ld)
         h_list = [ops.add_graph_vec(h0, vn, plan)]              # h + vn[batch]  (gnn_module.py:199)
         drop = self.drop_ratio if self.training else 0.0
         for layer in range(self.num_layer):
             hv = h_list[layer]
             vn_next = None
+            br = None
             if layer < self.num_layer - 1:                       # gnn_module.py:217-229
                 mlp = self.mlp_virtualnode_list[layer]
-                t = ops.segment_sum(hv, plan, init=vn)            # global_add_pool(h_list[layer]) + vn
-                t = ops.cast_to(t, ops.act_dtype())               # the MLP runs in the activation dtype
-                t = ops.batch_norm(ops.linear(t, mlp[0].weight, mlp[0].bias), mlp[1], relu=True)
-                t = ops.batch_norm(ops.linear(t, mlp[3].weight, mlp[3].bias), mlp[4], relu=True, drop_p=drop)
-                t = ops.cast_to(t, torch.float32)                 # the virtual-node state itself stays fp32
-                vn_next = vn + t if self.residual else t
+                # independent of this layer's conv: runs as a parallel branch (ops.Branch) joined at the BN below
+                br = ops.Branch(hv, vn)
+                with br:
+                    t = ops.segment_sum(hv, plan, init=vn)        # global_add_pool(h_list[layer]) + vn
+                    t = ops.cast_to(t, ops.act_dtype())           # the MLP runs in the activation dtype
+                    t = ops.batch_norm(ops.linear(t, mlp[0].weight, mlp[0].bias), mlp[1], relu=True)
+                    t = ops.batch_norm(ops.linear(t, mlp[3].weight, mlp[3].bias), mlp[4], relu=True, drop_p=drop)
+                    t = ops.cast_to(t, torch.float32)             # the virtual-node state itself stays fp32
+                    vn_next = vn + t if self.residual else t
             h = self.convs[layer](hv, edge_index, edge_attr, plan=plan)
+            if br is not None:
+                br.join(vn_next)
             # BN -> ReLU (not last) -> dropout -> (+residual) -> (+ next layer's vn[batch]) in one kernel
             h = ops.batch_norm(h, self.batch_norms[layer], relu=layer != self.num_layer - 1,
                                resid=hv if self.residual else None, gvec=vn_next, plan=plan, drop_p=drop)

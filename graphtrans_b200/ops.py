@@ -130,7 +130,7 @@ def next_salt() -> int:
 # Weight / bias gradients are off the critical path of the backward pass (nothing upstream consumes them), so they
 # can run on a second stream next to the memory-bound kernels of the next layer (BN / LayerNorm backward, aggregation
 # adjoint ...), which co-reside on an SM with the one-CTA-per-SM persistent GEMM.  Opt-in: whoever enables it must
-# call join_wgrad_stream() after backward() and before reading gradients (GraphedStep and bench.py do).
+# call join_side_streams() after backward() and before reading gradients (GraphedStep and bench.py do).
 _wgrad = {"stream": None}
 
 
@@ -138,10 +138,15 @@ def enable_wgrad_stream(on=True, device="cuda"):
     _wgrad["stream"] = torch.cuda.Stream(device=device) if on else None
 
 
-def join_wgrad_stream():
-    st = _wgrad["stream"]
-    if st is not None:
-        torch.cuda.current_stream().wait_stream(st)
+def join_side_streams():
+    """make the current stream wait for the weight-gradient stream and the parallel-branch stream (call after
+    backward(), before anything reads the gradients)"""
+    for st in (_branch["stream"], _wgrad["stream"]):
+        if st is not None:
+            torch.cuda.current_stream().wait_stream(st)
+
+
+join_wgrad_stream = join_side_streams
 
 
 class _WgradCtx:
@@ -166,6 +171,53 @@ class _WgradCtx:
         if self.ctx is not None:
             self.ctx.__exit__(*exc)
         return False
+
+
+# ----------------------------------------------------------------------------- parallel branch stream
+# The virtual-node update of a GNN layer (global_add_pool -> 2-layer MLP on [B, d_g], reference gnn_module.py:217-229)
+# only needs the layer INPUT and is consumed at the very end of the layer, so it is independent of the conv of that
+# layer: a dozen kernels of a few CTAs each that can run next to the conv on a second stream (a parallel branch of
+# the captured CUDA graph).  autograd runs the backward of every node on the stream of its forward and inserts the
+# cross-stream waits itself, so the backward overlaps the same way.  Opt-in like the weight-gradient stream: whoever
+# enables it calls join_side_streams() after backward() (GraphedStep and bench.py do).
+_branch = {"stream": None}
+
+
+def enable_branch_stream(on=True, device="cuda"):
+    _branch["stream"] = torch.cuda.Stream(device=device) if on else None
+
+
+class Branch:
+    """`with Branch(inputs...) as br: ...` runs the enclosed ops on the branch stream (when enabled), ordered after
+    everything issued so far on the current stream; `br.join(outputs...)` makes the current stream wait for them."""
+
+    def __init__(self, *tensors):
+        self.st = _branch["stream"]
+        self.tensors = [t for t in tensors if t is not None]
+        self.ctx = None
+
+    def __enter__(self):
+        if self.st is not None:
+            self.st.wait_stream(torch.cuda.current_stream())
+            for t in self.tensors:
+                t.record_stream(self.st)
+            self.ctx = torch.cuda.stream(self.st)
+            self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+            self.ctx = None
+        return False
+
+    def join(self, *outputs):
+        if self.st is not None:
+            cur = torch.cuda.current_stream()
+            cur.wait_stream(self.st)
+            for t in outputs:
+                if t is not None:
+                    t.record_stream(cur)
 
 
 # ----------------------------------------------------------------------------- fused gradient delivery
@@ -595,8 +647,10 @@ class _SegmentSumFn(torch.autograd.Function):
     def forward(ctx, x, plan, init=None):
         x = x.contiguous()
         N, ld = x.shape
-        out = zeros_f32((plan.B, ld), x.device) if init is None else init.clone()
-        call("gt_segment_sum_sorted", dt_of(x), ptr(x), ptr(plan.node_off), plan.B, ld, ptr(out))
+        out = torch.empty(plan.B, ld, dtype=torch.float32, device=x.device)
+        if init is not None:
+            init = init.contiguous()
+        call("gt_segment_sum_sorted", dt_of(x), ptr(x), ptr(plan.node_off), plan.B, ld, ptr(init), ptr(out))
         ctx.meta = (plan, x.dtype, N, ld)
         return out
 
@@ -633,13 +687,40 @@ class _AddGraphVecFn(torch.autograd.Function):
         g = g.contiguous()
         dv = None
         if ctx.needs_input_grad[1]:
-            dv = zeros_f32((plan.B, ld), g.device)
-            call("gt_segment_sum_sorted", dt_of(g), ptr(g), ptr(plan.node_off), plan.B, ld, ptr(dv))
+            dv = torch.empty(plan.B, ld, dtype=torch.float32, device=g.device)
+            call("gt_segment_sum_sorted", dt_of(g), ptr(g), ptr(plan.node_off), plan.B, ld, None, ptr(dv))
         return g, dv, None
 
 
 def add_graph_vec(x, v, plan):
     return _AddGraphVecFn.apply(x, v, plan)
+
+
+class _BroadcastRowFn(torch.autograd.Function):
+    """fp32 [rows, ld] filled with the (zero-padded) single row of a [1, d] parameter (the initial virtual-node state,
+    reference modules/gnn_module.py:188-189); backward = column sum straight into the parameter gradient"""
+
+    @staticmethod
+    def forward(ctx, w, rows, ld):
+        d = w.shape[1]
+        wc = w.contiguous()
+        out = torch.empty(rows, ld, dtype=torch.float32, device=w.device)
+        call("gt_cast_pad", GT_F32, ptr(wc), rows, d, 0, GT_F32, ptr(out), rows, ld, ld)   # source row stride 0
+        ctx.param, ctx.meta = w, (rows, d, ld)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        rows, d, ld = ctx.meta
+        g = g.contiguous()
+        tgt, gw = _grad_target(ctx.param)
+        call("gt_colsum", dt_of(g), ptr(g), rows, d, ld, ptr(tgt))
+        _grad_done(ctx.param)
+        return gw, None, None
+
+
+def broadcast_row(w, rows, ld):
+    return _BroadcastRowFn.apply(w, rows, ld)
 
 
 # ----------------------------------------------------------------------------- BatchNorm1d
@@ -693,8 +774,8 @@ class _BatchNormFn(torch.autograd.Function):
         dres = g if has_resid else None
         dgv = None
         if has_gvec and ctx.needs_input_grad[11]:
-            dgv = zeros_f32((plan.B, ld), dev)
-            call("gt_segment_sum_sorted", dt_of(g), ptr(g), ptr(plan.node_off), plan.B, ld, ptr(dgv))
+            dgv = torch.empty(plan.B, ld, dtype=torch.float32, device=dev)
+            call("gt_segment_sum_sorted", dt_of(g), ptr(g), ptr(plan.node_off), plan.B, ld, None, ptr(dgv))
         return dx, dgamma, dbeta, None, None, None, None, None, None, None, dres, dgv, None, None, None
 
 

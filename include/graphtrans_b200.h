@@ -129,9 +129,10 @@ int gt_edge_slots(const int32_t* rowptr_slot, const int32_t* nbr_slot, const int
 int gt_segment_sum(int dt, const void* x, const int32_t* node_graph, int64_t N, int32_t ld,
                    float* out, void* stream);
 /* same for graphs that own contiguous row ranges [node_off[g], node_off[g+1]) (PyG batches are sorted): one warp per
- * (graph, 128-channel chunk), single writer, no atomics (deterministic); out [B, ld] fp32 is accumulated into */
-int gt_segment_sum_sorted(int dt, const void* x, const int32_t* node_off, int64_t B, int32_t ld, float* out,
-                          void* stream);
+ * (graph, 128-channel chunk), single writer, no atomics (deterministic);
+ * out[g,:] = (init ? init[g,:] : 0) + sum_{i in g} x[i,:]  (fp32 [B, ld]; out needs no zero fill, init may be NULL) */
+int gt_segment_sum_sorted(int dt, const void* x, const int32_t* node_off, int64_t B, int32_t ld,
+                          const float* init, float* out, void* stream);
 /* y[i,:] = x[i,:] + v[node_graph[i],:]   (v fp32 [B,ld]); x may be NULL (pure broadcast) */
 int gt_add_graph_vec(int dt, const void* x, const float* v, const int32_t* node_graph, int64_t N,
                      int32_t ld, void* y, void* stream);
@@ -187,7 +188,8 @@ int gt_gemm(int dt, const void* A, int a_mn, int64_t lda, const void* B, int b_m
 int gt_relu_bwd(int dt, const void* dy, const void* y, int64_t n, void* dz, float scale, void* stream);
 /* out[n] += sum_m X[m,n]  (bias gradients) ; out fp32 [N] is ACCUMULATED into (caller zeroes a fresh buffer) */
 int gt_colsum(int dt, const void* X, int64_t M, int64_t N, int64_t ld, float* out, void* stream);
-/* dst[r, 0:cols_out] = cast(src[r, 0:cols_in]) zero padded to cols_out; rows_out >= rows_in zero padded */
+/* dst[r, 0:cols_out] = cast(src[r, 0:cols_in]) zero padded to cols_out; rows_out >= rows_in zero padded;
+ * ld_in == 0 broadcasts the single source row to rows_in rows */
 int gt_cast_pad(int dt_in, const void* src, int64_t rows_in, int64_t cols_in, int64_t ld_in,
                 int dt_out, void* dst, int64_t rows_out, int64_t cols_out, int64_t ld_out, void* stream);
 

@@ -32,15 +32,23 @@ def _batch(args, B, seed):
     return b
 
 
-@pytest.mark.parametrize("cfg,precision", [("molpcba", "fp32"), ("code2", "bf16")])
-def test_replay_matches_eager(cfg, precision):
+@pytest.mark.parametrize("cfg,precision,side", [("molpcba", "fp32", False), ("molpcba", "fp32", True),
+                                                ("code2", "bf16", True)])
+def test_replay_matches_eager(cfg, precision, side):
+    """side=True: weight gradients and the virtual-node branch on their own streams (parallel graph branches), as
+    bench.py runs the step"""
     ops.set_precision(precision)
+    ops.enable_wgrad_stream(side)
+    ops.enable_branch_stream(side)
     try:
         args, model, lossf = _setup(cfg, drop=False)
         init = copy.deepcopy(model.state_dict())
         buckets = GradBuckets(model, n_buckets=2, overlap=False)
         step = GraphedStep(model, lossf, buckets)
-        b1 = _batch(args, 6, seed=1).to("cuda")
+        # molpcba: 32 graphs keep the train-mode BatchNorm of the virtual-node MLP (statistics over B rows) well
+        # conditioned; with a handful of graphs fp32 summation-order noise alone exceeds the tolerance
+        nb = 32 if cfg == "molpcba" else 6
+        b1 = _batch(args, nb, seed=1).to("cuda")
         l_cap = float(step(b1))                          # capture + first replay
         g_cap = buckets.flat.clone()
         # eager reference on a fresh copy of the model
@@ -50,8 +58,10 @@ def test_replay_matches_eager(cfg, precision):
         rb.zero_grad()
         loss = lossf(ref(b1), b1)
         loss.backward()
+        ops.join_side_streams()
+        loss = float(loss.detach())
         tol = 2e-3 if precision == "fp32" else 5e-2
-        assert abs(l_cap - float(loss)) < tol * max(1.0, abs(float(loss)))
+        assert abs(l_cap - loss) < tol * max(1.0, abs(loss))
         assert rel_l2(g_cap, rb.flat) < tol
         # same signature, different content: permute the graphs' labels and node features
         b2 = b1.clone()
@@ -73,14 +83,18 @@ def test_replay_matches_eager(cfg, precision):
         buckets.zero_grad()
         le = lossf(model(b2), b2)
         le.backward()
-        assert abs(l2 - float(le)) < tol * max(1.0, abs(float(le)))
+        ops.join_side_streams()
+        le = float(le.detach())                           # drop the autograd graph before the next capture
+        assert abs(l2 - le) < tol * max(1.0, abs(le))
         assert rel_l2(buckets.flat, g2) < tol
         # different signature -> new capture
-        b3 = _batch(args, 5, seed=7).to("cuda")
+        b3 = _batch(args, nb - 1, seed=7).to("cuda")
         step(b3)
         assert len(step.cache) == n_graphs + 1
     finally:
         ops.set_precision("fp32")
+        ops.enable_wgrad_stream(False)
+        ops.enable_branch_stream(False)
 
 
 def test_replay_advances_bn_buffers_and_dropout():

@@ -35,13 +35,15 @@ def run_product(args, batch, init_sd, precision="fp32", train=True, buckets=Fals
         model.zero_grad()
     if wgrad_stream:
         ops.enable_wgrad_stream(True)
+        ops.enable_branch_stream(True)
     try:
         pred = model(b)
         loss = factory.loss_fn(args)(pred, b)
         loss.backward()
-        ops.join_wgrad_stream()
+        ops.join_side_streams()
     finally:
         ops.enable_wgrad_stream(False)
+        ops.enable_branch_stream(False)
     torch.cuda.synchronize()
     grads = {k: (p.grad.detach().clone() if p.grad is not None else torch.zeros_like(p))
              for k, p in model.named_parameters()}
@@ -72,7 +74,8 @@ def test_golden_fwd_bwd_fp32(name):
 
 @pytest.mark.parametrize("name", GOLDEN_CASES)
 def test_golden_grads_with_wgrad_side_stream(name):
-    """weight / bias / embedding gradients issued on the second stream (ops.enable_wgrad_stream): same parity bar"""
+    """weight / bias / embedding gradients issued on the second stream (ops.enable_wgrad_stream) and the virtual-node
+    update on the parallel branch stream (ops.enable_branch_stream): same parity bar"""
     fx = load_golden(name)
     _, pred, loss, grads, _ = run_product(fx["args"], fx["batch"], fx["init_sd"], buckets=True, wgrad_stream=True)
     for a, b in zip(as_list(pred), as_list(fx["logits"])):
@@ -106,10 +109,12 @@ def test_golden_bf16_mode_is_close(name):
     assert glob < 0.5, (glob, worst, key)
 
 
-@pytest.mark.parametrize("cfg,B", [("nci1", 32), ("molpcba", 24), ("code2", 6), ("syn", 8), ("code2-pna", 6)])
+@pytest.mark.parametrize("cfg,B", [("nci1", 32), ("molpcba", 48), ("code2", 6), ("syn", 8), ("code2-pna", 6)])
 def test_oracle_parity_at_config_shapes(cfg, B):
     """BASELINE configs at their real widths (d_g=300/272/256, d=128/256, 5+4 layers) on a reduced
-    number of graphs so the fp64 CPU oracle finishes in seconds; dropout 0 (RNG cannot match)."""
+    number of graphs so the fp64 CPU oracle finishes in seconds; dropout 0 (RNG cannot match).
+    molpcba uses 48 graphs: with 24 the train-mode BatchNorm of the virtual-node MLP (statistics over B rows) is so
+    ill-conditioned that the fp32 ORACLE itself is 1.0e-3 away from its fp64 run (1.8e-4 at B=48)."""
     kw = dict(gnn_dropout=0.0, transformer_dropout=0.0)
     if cfg in ("code2", "code2-pna"):
         kw.update(num_tasks=500)         # 5 heads x 500 classes keep the oracle fast
