@@ -35,6 +35,8 @@ SIGNATURES = {
     "gt_aggregate_fwd": [I, I, P, P, L, I32, I32, P, P, P, P, I, P, I32, P, P, P, P, P, P, P, P, P],
     "gt_aggregate_bwd": [I, I, P, P, P, L, I32, I32, P, P, P, P, I, P, I32, P, P, P, P, I32, P, P, P, P, P, P, P, P, P],
     "gt_edge_slots": [P, P, P, P, L, L, P, P, I32, P, P, P, P],
+    "gt_edges_by_type": [P, P, L, I32, P, P, P, P, P, P],
+    "gt_aggregate_table_grad": [I, I, P, P, L, I32, I32, P, L, P, P, P, P, I32, P, P],
     "gt_segment_sum": [I, P, P, L, I32, P, P],
     "gt_segment_sum_sorted": [I, P, P, L, I32, P, P, P],
     "gt_add_graph_vec": [I, P, P, P, L, I32, P, P],
@@ -68,7 +70,7 @@ SIGNATURES = {
 
 # kernels launched per export (everything not listed launches exactly one); cudaMemsetAsync nodes
 # are not counted
-KERNELS_PER_CALL = {"gt_csr_build": 4, "gt_batch_plan": 3, "gt_mha_bwd": 2}
+KERNELS_PER_CALL = {"gt_csr_build": 4, "gt_batch_plan": 3, "gt_mha_bwd": 2, "gt_edges_by_type": 3}
 
 _lib = None
 launch_count = 0   # C-ABI calls issued

@@ -144,7 +144,8 @@ k_agg_bwd(const T* __restrict__ x, const T* __restrict__ dout, T* __restrict__ d
     // table-edge gradients: a handful of rows shared by every edge would serialise global atomics, so they are
     // reduced per block in shared memory (lanes own distinct channels: no intra-warp conflicts) and flushed once
     __shared__ float sh_tab[EK == GT_EDGE_TABLE ? AGG_TAB_ROWS * 128 : 1];
-    const bool tab_smem = EK == GT_EDGE_TABLE && en.ntypes <= AGG_TAB_ROWS;
+    const bool tab_grad = EK == GT_EDGE_TABLE && d_table != nullptr;   // null: gt_aggregate_table_grad computes it
+    const bool tab_smem = tab_grad && en.ntypes <= AGG_TAB_ROWS;
     const int lane = threadIdx.x & 31;
     const int warp = blockIdx.x * AGG_WARPS + (threadIdx.x >> 5);
     const int nwarps = gridDim.x * AGG_WARPS;
@@ -209,7 +210,7 @@ k_agg_bwd(const T* __restrict__ x, const T* __restrict__ dout, T* __restrict__ d
 #pragma unroll
                             for (int k = 0; k < MAX_KDIM; ++k) a_w[k][q] = fmaf(a[k], gm[q], a_w[k][q]);
                         }
-                    } else if (EK == GT_EDGE_TABLE) {
+                    } else if (EK == GT_EDGE_TABLE && tab_grad) {
                         const int ty = en.etype[eid];
                         float* row = tab_smem ? sh_tab + ty * 128 + lane * 4 : d_table + (int64_t)ty * ld + c0;
 #pragma unroll
@@ -393,10 +394,11 @@ k_agg_bwd2(const T* __restrict__ x, const T* __restrict__ dout, T* __restrict__ 
     const int warp = gwarp / nch;
     const int nwarps = gridDim.x * AGG_WARPS / nch;
     const int W = 128 * nch;
+    const bool tab_grad = EK == GT_EDGE_TABLE && d_table != nullptr;   // null: gt_aggregate_table_grad computes it
     float* sh_tab = sh_dyn;
-    float* sh_par = sh_dyn + (EK == GT_EDGE_TABLE ? en.ntypes * ld : 0);   // [self | b | w0..w3][W]
+    float* sh_par = sh_dyn + (tab_grad ? en.ntypes * ld : 0);   // [self | b | w0..w3][W]
     const int n_par = (2 + 4) * W;   // host-side layout: [self | b | w0..w3][W]
-    for (int i = threadIdx.x; i < (EK == GT_EDGE_TABLE ? en.ntypes * ld : 0) + n_par; i += blockDim.x) sh_dyn[i] = 0.f;
+    for (int i = threadIdx.x; i < (tab_grad ? en.ntypes * ld : 0) + n_par; i += blockDim.x) sh_dyn[i] = 0.f;
     __syncthreads();
     const float eps1 = (CONV == GT_CONV_GIN) ? 1.f + self_param[0] : 0.f;
     float deps = 0.f;
@@ -480,7 +482,7 @@ k_agg_bwd2(const T* __restrict__ x, const T* __restrict__ dout, T* __restrict__ 
 #pragma unroll
                                 for (int kk = 0; kk < KD; ++kk) a_w[k][kk][q] = fmaf(a[kk], gm[q], a_w[k][kk][q]);
                             }
-                        } else if (EK == GT_EDGE_TABLE) {
+                        } else if (EK == GT_EDGE_TABLE && tab_grad) {
                             float* row = sh_tab + ty * ld + c0;
 #pragma unroll
                             for (int q = 0; q < 4; ++q)
@@ -534,7 +536,7 @@ k_agg_bwd2(const T* __restrict__ x, const T* __restrict__ dout, T* __restrict__ 
             for (int kk = 0; kk < en.kdim; ++kk) atomicAdd(&d_edge_w[c * en.kdim + kk], sh_par[(2 + kk) * W + c]);
         }
     }
-    if (EK == GT_EDGE_TABLE) {
+    if (tab_grad) {
         for (int i = threadIdx.x; i < en.ntypes * ld; i += blockDim.x) {
             const float v = sh_tab[i];
             if (v != 0.f && (i % ld) < d) atomicAdd(d_table + i, v);
@@ -543,6 +545,75 @@ k_agg_bwd2(const T* __restrict__ x, const T* __restrict__ dout, T* __restrict__ 
     if (CONV == GT_CONV_GIN) {
         deps = warp_sum(deps);
         if (lane == 0 && deps != 0.f) atomicAdd(d_self, deps);
+    }
+}
+
+// Edge-table gradient, split off the adjoint (gt_aggregate_table_grad): d_table[ty] = sum over the edges of type ty
+// of norm_e * dout[dst_e] * 1[x[src_e] + table[ty] > 0].  Inside the adjoint it costs one shared-memory atomic per
+// (edge, channel) plus a block-private [ntypes][ld] table (3.5x the forward on the molpcba batch); it is a LEAF
+// gradient, so it runs here, off the critical path, over the edges SORTED BY TYPE (gt_edges_by_type, once per batch):
+// a warp owns (32 consecutive sorted slots, one 128-channel chunk), keeps the table row of the current type and the
+// running sum in registers, gathers TG_U edges' rows at a time (all loads issued before the first use) and issues
+// one global atomic per (type run, channel).
+constexpr int TG_U = 8;
+template <typename T, int CONV>
+__global__ void __launch_bounds__(256)
+k_agg_table_grad(const T* __restrict__ x, const T* __restrict__ dout, int d, int ld, int nch,
+                 const int32_t* __restrict__ rp_src, int64_t E, const int32_t* __restrict__ src_t,
+                 const int32_t* __restrict__ dst_t, const int32_t* __restrict__ type_t,
+                 const float* __restrict__ table, float* __restrict__ d_table) {
+    const int lane = threadIdx.x & 31;
+    const int64_t item = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int64_t p0 = (item / nch) * 32;
+    const int c0 = (int)(item % nch) * 128 + lane * 4;
+    if (p0 >= E) return;
+    const bool col_ok = c0 < ld;
+    const int cnt = (int)min((int64_t)32, E - p0);
+    const bool have = lane < cnt;
+    const int j_l = have ? src_t[p0 + lane] : 0, i_l = have ? dst_t[p0 + lane] : 0;
+    const int ty_l = have ? type_t[p0 + lane] : -1;
+    float nrm_l = 1.f;
+    if (CONV == GT_CONV_GCN && have)
+        nrm_l = rsqrtf((float)(rp_src[j_l + 1] - rp_src[j_l] + 1)) * rsqrtf((float)(rp_src[i_l + 1] - rp_src[i_l] + 1));
+    int cur = -1;
+    float tab[4] = {0.f, 0.f, 0.f, 0.f}, acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int t0 = 0; t0 < cnt; t0 += TG_U) {
+        int ty[TG_U];
+        float nrm[TG_U], xv[TG_U][4], g[TG_U][4];
+#pragma unroll
+        for (int u = 0; u < TG_U; ++u) {
+            const int t = min(t0 + u, cnt - 1);               // tail slots repeat the last edge with weight 0
+            const int j = __shfl_sync(0xffffffffu, j_l, t), i = __shfl_sync(0xffffffffu, i_l, t);
+            ty[u] = __shfl_sync(0xffffffffu, ty_l, t);
+            nrm[u] = CONV == GT_CONV_GCN ? __shfl_sync(0xffffffffu, nrm_l, t) : 1.f;
+            if (t0 + u >= cnt) nrm[u] = 0.f;
+            if (col_ok) {
+                ld4(x + (int64_t)j * ld + c0, xv[u]);
+                ld4(dout + (int64_t)i * ld + c0, g[u]);
+            }
+        }
+        if (!col_ok) continue;
+#pragma unroll
+        for (int u = 0; u < TG_U; ++u) {
+            if (ty[u] != cur) {                                // warp-uniform, rare: the slots are sorted by type
+                if (cur >= 0) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (c0 + q < d && acc[q] != 0.f) atomicAdd(d_table + (int64_t)cur * ld + c0 + q, acc[q]);
+                }
+                cur = ty[u];
+                ld4(table + (int64_t)cur * ld + c0, tab);
+                acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (xv[u][q] + tab[q] > 0.f) acc[q] = fmaf(nrm[u], g[u][q], acc[q]);
+        }
+    }
+    if (col_ok && cur >= 0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (c0 + q < d && acc[q] != 0.f) atomicAdd(d_table + (int64_t)cur * ld + c0 + q, acc[q]);
     }
 }
 
@@ -580,7 +651,8 @@ static int launch_bwd(int ek, const T* x, const T* dout, T* dx, int N, int d, in
                       cudaStream_t st) {
     int grid = blocks_for(N, AGG_WARPS, kNumSMs * 8);
     const int nch = (ld + 127) / 128;
-    const size_t smem2 = sizeof(float) * ((size_t)(2 + MAX_KDIM) * 128 * nch + (ek == GT_EDGE_TABLE ? (size_t)en.ntypes * ld : 0));
+    const bool tab_grad = ek == GT_EDGE_TABLE && dtab != nullptr;
+    const size_t smem2 = sizeof(float) * ((size_t)(2 + MAX_KDIM) * 128 * nch + (tab_grad ? (size_t)en.ntypes * ld : 0));
 #define L2K(EK, NCH, KD) do { \
         static bool attr = false; \
         if (!attr) { cudaFuncSetAttribute(k_agg_bwd2<T, CONV, EK, NCH, KD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr = true; } \
@@ -593,7 +665,8 @@ static int launch_bwd(int ek, const T* x, const T* dout, T* dx, int N, int d, in
     // measured (tools/agg_bench.py): with an edge-type table the block-private [ntypes][ld] shared-memory table of the
     // batched kernel costs too much occupancy (84 vs 53 us on the molpcba batch); the per-edge kernel keeps its
     // 32 KB per-chunk table.  Linear / no edge encoder: the batched kernel wins (62 vs 73 us on the code2 batch).
-    if (nch <= 4 && smem2 <= 100 * 1024 && variant != 1 && (ek != GT_EDGE_TABLE || variant == 2)) {
+    // Without the table gradient (d_table == NULL: gt_aggregate_table_grad computes it) the batched kernel is used.
+    if (nch <= 4 && smem2 <= 100 * 1024 && variant != 1 && (!tab_grad || variant == 2)) {
         // every block flushes its private gradient tables once: keep the block count near the resident capacity
         const int cap = kNumSMs * (smem2 > 48 * 1024 ? 2 : 8);
         grid = blocks_for((int64_t)N * nch, AGG_WARPS, cap);
@@ -661,6 +734,27 @@ extern "C" int gt_aggregate_bwd(int dt, int conv, const void* x, const void* dou
             launch_bwd<T, GT_CONV_GIN>(edge_kind, (const T*)x, (const T*)dout, (T*)dx, (int)N, d, ld, rowptr_src, dst_by_src, eid_by_src, en, self_param, d_edge_w, d_edge_b, d_table, d_self, st);
     });
     GT_LAUNCH_CHECK("gt_aggregate_bwd");
+    return 0;
+}
+
+extern "C" int gt_aggregate_table_grad(int dt, int conv, const void* x, const void* dout, int64_t N, int32_t d, int32_t ld,
+                                       const int32_t* rowptr_src, int64_t E, const int32_t* src_t, const int32_t* dst_t,
+                                       const int32_t* type_t, const float* table, int32_t ntypes, float* d_table,
+                                       void* stream) {
+    if (int r = check_common("gt_aggregate_table_grad", conv, N, d, ld, GT_EDGE_TABLE, 0)) return r;
+    GT_CHECK_ARG(ntypes > 0 && E >= 0 && E < (1ll << 31), "gt_aggregate_table_grad: bad ntypes / E");
+    if (E == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nch = (ld + 127) / 128;
+    const int64_t items = (E + 31) / 32 * nch;          // (32 sorted slots, 128-channel chunk) per warp
+    const unsigned grid = (unsigned)((items + 7) / 8);
+    GT_DISPATCH_DT(dt, {
+        if (conv == GT_CONV_GCN)
+            k_agg_table_grad<T, GT_CONV_GCN><<<grid, 256, 0, st>>>((const T*)x, (const T*)dout, d, ld, nch, rowptr_src, E, src_t, dst_t, type_t, table, d_table);
+        else
+            k_agg_table_grad<T, GT_CONV_GIN><<<grid, 256, 0, st>>>((const T*)x, (const T*)dout, d, ld, nch, rowptr_src, E, src_t, dst_t, type_t, table, d_table);
+    });
+    GT_LAUNCH_CHECK("gt_aggregate_table_grad");
     return 0;
 }
 

@@ -18,6 +18,8 @@
 // Both operands may be K-major (row = m or n, k contiguous) or MN-major (row = k, m or n contiguous); the
 // major-ness goes into the UMMA instruction descriptor and the TMA box shape, so forward (K,K), dX (K,MN) and
 // dW (MN,MN) all run here without transposes.  Ragged M/N/K edges are zero-filled by TMA.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace gt {
@@ -49,7 +51,10 @@ struct Params {
     int tma_store;                       // epilogue writes C through TMA bulk stores / reductions (fast path)
     int m_tiles, n_tiles, total_tiles;   // work list: tile t -> n = t % n_tiles, m = (t / n_tiles) % m_tiles, split = rest
     uint32_t idesc, tmem_cols, acc_stride;
+    unsigned long long* trace;           // debug (GT_GEMM_TRACE=1): clock64 stamps of CTA 0's phases, else NULL
 };
+
+#define GT_TRACE(slot) do { if (p.trace && blockIdx.x == 0) p.trace[slot] = (unsigned long long)clock64(); } while (0)
 
 template <bool A_MN, bool B_MN, bool OUT_BF16>
 __global__ void __launch_bounds__(THREADS)
@@ -60,12 +65,18 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUt
     __shared__ uint32_t tmem_base_s;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) GT_TRACE(0);
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     // B tile: K-major = BN rows of 128 B; MN-major = ceil(BN/64) TMA boxes of [64 k-rows x 64 columns] (8 KB each)
     const int b_boxes = (p.BN + 63) / 64;
     const uint32_t b_bytes = B_MN ? (uint32_t)b_boxes * 8192u : (uint32_t)p.BN * (BK * 2);
     const uint32_t stage_bytes = A_TILE_BYTES + b_bytes;
 
+    if (threadIdx.x == 32) {   // descriptor fetch overlaps barrier init / TMEM allocation instead of the first TMA issue
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_b)) : "memory");
+        if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_c)) : "memory");
+    }
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(&full_bar[s], 1);
@@ -86,6 +97,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUt
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
+    if (threadIdx.x == 0) GT_TRACE(1);
 
     if (warp == 0) {
         if (lane == 0) {  // ===== TMA producer =====
@@ -112,6 +124,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUt
                     } else {
                         for (int j = 0; j < b_boxes; ++j) tma_load_2d(b_dst + j * 8192, &tma_b, &full_bar[s], n0 + j * 64, k0);
                     }
+                    if (it == 0) GT_TRACE(2);
                 }
             }
         }
@@ -129,6 +142,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUt
                     const int s = it % p.stages;
                     const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
                     mbar_wait(&full_bar[s], ph);
+                    if (it == 0) GT_TRACE(3);
                     tc_fence_after();
                     const uint32_t a_addr = smem_base + (uint32_t)s * stage_bytes, b_addr = a_addr + A_TILE_BYTES;
 #pragma unroll
@@ -140,6 +154,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUt
                     umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
                 }
                 umma_commit(&tmem_full_bar[buf]);  // accumulator of this tile complete
+                if (ti == 0) GT_TRACE(4);
             }
         }
     } else {  // ===== epilogue warps 2..9: TMEM lane group = warp % 4, column-slab parity = (warp - 2) / 4 =====
@@ -163,6 +178,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUt
             const int buf = ti & 1;
             const uint32_t acc = tmem_base + (uint32_t)buf * p.acc_stride + ((uint32_t)(q * 32) << 16);
             mbar_wait(&tmem_full_bar[buf], (uint32_t)(ti >> 1) & 1u);
+            if (ti == 0 && warp == 2 && lane == 0) GT_TRACE(5);
             tc_fence_after();
             if (p.tma_store) {
                 // fast path: thread = accumulator row.  TMEM -> registers -> (bias, ReLU, convert) -> this warp's
@@ -170,12 +186,22 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUt
                 // per slab, double-buffered so the next slab is produced while the previous one drains.
                 constexpr int SLAB_COLS = OUT_BF16 ? 64 : 32;
                 uint8_t* sbase = reinterpret_cast<uint8_t*>(stg);          // 2 x 4 KB of this warp's region
+                float* bias_sm = reinterpret_cast<float*>(sbase + 8192);     // + 1 KB spare: bias of the current slab
                 const uint32_t s_u32 = smem_u32(sbase);
                 const uint32_t rsw = (uint32_t)lane & 7u;
                 for (int c0 = sub * SLAB_COLS; c0 < p.BN; c0 += 2 * SLAB_COLS) {   // BN % SLAB_COLS == 0 on this path
                     const int n_slab = n0 + c0;
                     if (n_slab >= ncols) break;   // warp-uniform
                     const uint32_t sb = s_u32 + (uint32_t)(slab_i & 1) * 4096u;
+                    // bias of this slab: two coalesced loads per lane into the warp-private spare KB of the staging
+                    // region, read back below as broadcast 16-byte shared loads.  (One scalar global load per
+                    // (thread, column) serialises on its destination registers: 2.6 us per slab, measured with
+                    // tools/gemm_trace.py - the whole kernel was epilogue bound.)
+                    const bool use_bias = first && p.bias;
+                    if (use_bias) {
+#pragma unroll
+                        for (int i = lane; i < SLAB_COLS; i += 32) bias_sm[i] = (n_slab + i < p.N) ? __ldg(p.bias + n_slab + i) : 0.f;
+                    }
                     if (lane == 0) tma_wait_group_read<1>();   // the store that last used this buffer has read it
                     __syncwarp();
 #pragma unroll
@@ -188,10 +214,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUt
                         float v[16];
 #pragma unroll
                         for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r32[cc + i]);
-                        if (first && p.bias) {
+                        if (use_bias) {
 #pragma unroll
-                            for (int i = 0; i < 16; ++i)
-                                if (n_slab + c + i < p.N) v[i] += __ldg(p.bias + n_slab + c + i);
+                            for (int i = 0; i < 16; i += 4) {
+                                const float4 b4 = *reinterpret_cast<const float4*>(bias_sm + c + i);
+                                v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+                            }
                         }
                         if (relu) {
 #pragma unroll
@@ -240,6 +268,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUt
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+                if (ti == 0 && warp == 2 && lane == 0) GT_TRACE(6);
                 continue;
             }
             bool released = false;
@@ -355,7 +384,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUt
                 if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
             }
         }
+        if (warp == 2 && lane == 0) GT_TRACE(7);
         if (p.tma_store && lane == 0) tma_wait_group_all();   // staged slabs must be drained before the CTA exits
+        if (warp == 2 && lane == 0) GT_TRACE(8);
     }
     tc_fence_before();
     __syncthreads();
@@ -363,6 +394,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUt
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
     }
+    if (threadIdx.x == 32) GT_TRACE(9);
 }
 
 // ---------------------------------------------------------------------------------------- host side
@@ -382,6 +414,8 @@ static cudaError_t launch(const CUtensorMap& ma, const CUtensorMap& mb, const CU
 }
 
 }  // namespace tc
+
+static unsigned long long* g_trace_buf = nullptr;
 
 // returns 0 ok, -2 = shape/layout/dtype not eligible (caller falls back to the CUDA-core kernel), >0 CUDA error
 int gemm_tc_launch(int dt, const void* A, int a_mn, int64_t lda, const void* B, int b_mn, int64_t ldb, void* C, int64_t ldc,
@@ -417,7 +451,7 @@ int gemm_tc_launch(int dt, const void* A, int a_mn, int64_t lda, const void* B, 
     int splits = 1;
     if (accum) {   // split-K: enough work items for ~2 per SM (weight gradients: few output tiles, very long K)
         const int64_t tiles = (int64_t)p.n_tiles * p.m_tiles;
-        splits = (int)((kNumSMs + tiles - 1) / tiles);   // one wave: every extra split adds a full fp32 reduction pass
+        splits = (int)(kNumSMs / tiles);   // ONE wave (<= 148 work items): an item more than the SM count doubles the duration
         if (splits > p.kb_total) splits = p.kb_total;
         if (splits < 1) splits = 1;
     }
@@ -450,6 +484,11 @@ int gemm_tc_launch(int dt, const void* A, int a_mn, int64_t lda, const void* B, 
     if (p.tma_store && !make_map(&mc, C, (uint64_t)ncols, (uint64_t)M, (uint64_t)ldc, out_bf16 ? 64 : 32, 32, 128, !out_bf16))
         p.tma_store = 0;
 
+    static unsigned long long* trace_buf = nullptr;
+    static const bool trace_on = getenv("GT_GEMM_TRACE") != nullptr;
+    if (trace_on && !trace_buf) { cudaMalloc(&trace_buf, 16 * sizeof(unsigned long long)); g_trace_buf = trace_buf; }
+    p.trace = trace_on ? trace_buf : nullptr;
+
     cudaError_t e;
     if (a_mn && b_mn) e = launch<true, true>(ma, mb, mc, p, grid, smem, out_bf16, st);
     else if (a_mn) e = launch<true, false>(ma, mb, mc, p, grid, smem, out_bf16, st);
@@ -460,3 +499,9 @@ int gemm_tc_launch(int dt, const void* A, int a_mn, int64_t lda, const void* B, 
 }
 
 }  // namespace gt
+
+// profiling hook (not part of the product ABI): phase stamps of CTA 0 of the last traced gt_gemm launch
+extern "C" int gtdbg_gemm_trace_read(unsigned long long* out16) {
+    if (!gt::g_trace_buf) return -1;
+    return (int)cudaMemcpy(out16, gt::g_trace_buf, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+}

@@ -113,6 +113,58 @@ __global__ void k_edge_type(const int64_t* __restrict__ attr, int64_t E, int nco
     }
 }
 
+// ---------------------------------------------------------------- edges sorted by type (counting sort)
+// ntypes is small (<= 1024): block-private shared-memory histograms, one global atomic per (block, type).
+constexpr int EBT_MAX_TYPES = 1024;
+__global__ void __launch_bounds__(256)
+k_ebt_hist(const int32_t* __restrict__ etype, int64_t E, int ntypes, int64_t chunk, int32_t* __restrict__ cnt) {
+    __shared__ int32_t sh[EBT_MAX_TYPES];
+    for (int i = threadIdx.x; i < ntypes; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const int64_t e0 = blockIdx.x * chunk, e1 = min(e0 + chunk, E);
+    for (int64_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) atomicAdd(&sh[etype[e]], 1);
+    __syncthreads();
+    for (int i = threadIdx.x; i < ntypes; i += blockDim.x)
+        if (sh[i]) atomicAdd(&cnt[i], sh[i]);
+}
+// single block: type_ptr = exclusive scan of cnt, cursor = copy of type_ptr
+__global__ void k_ebt_scan(const int32_t* __restrict__ cnt, int ntypes, int32_t* __restrict__ type_ptr,
+                           int32_t* __restrict__ cursor) {
+    if (threadIdx.x == 0) {
+        int32_t run = 0;
+        for (int i = 0; i < ntypes; ++i) {
+            type_ptr[i] = run;
+            cursor[i] = run;
+            run += cnt[i];
+        }
+        type_ptr[ntypes] = run;
+    }
+}
+__global__ void __launch_bounds__(256)
+k_ebt_fill(const int64_t* __restrict__ ei, const int32_t* __restrict__ etype, int64_t E, int ntypes, int64_t chunk,
+           int32_t* __restrict__ cursor, int32_t* __restrict__ src_t, int32_t* __restrict__ dst_t,
+           int32_t* __restrict__ type_t) {
+    __shared__ int32_t sh_cnt[EBT_MAX_TYPES];
+    __shared__ int32_t sh_base[EBT_MAX_TYPES];
+    for (int i = threadIdx.x; i < ntypes; i += blockDim.x) sh_cnt[i] = 0;
+    __syncthreads();
+    const int64_t e0 = blockIdx.x * chunk, e1 = min(e0 + chunk, E);
+    for (int64_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) atomicAdd(&sh_cnt[etype[e]], 1);
+    __syncthreads();
+    for (int i = threadIdx.x; i < ntypes; i += blockDim.x) {
+        sh_base[i] = sh_cnt[i] ? atomicAdd(&cursor[i], sh_cnt[i]) : 0;   // this block's slot range of type i
+        sh_cnt[i] = 0;
+    }
+    __syncthreads();
+    for (int64_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+        const int ty = etype[e];
+        const int32_t p = sh_base[ty] + atomicAdd(&sh_cnt[ty], 1);
+        src_t[p] = (int32_t)ei[e];
+        dst_t[p] = (int32_t)ei[E + e];
+        type_t[p] = ty;
+    }
+}
+
 // ---------------------------------------------------------------- batch plan
 __global__ void k_plan_bounds(const int64_t* __restrict__ batch, int64_t N, int64_t B, int32_t* node_off,
                               int32_t* node_graph) {
@@ -257,6 +309,25 @@ extern "C" int gt_edge_type(const int64_t* edge_attr, int64_t E, int32_t ncol, c
         k_edge_type<<<blocks_for(E, 256), 256, 0, (cudaStream_t)stream>>>(edge_attr, E, ncol, m[0], m[1], m[2],
                                                                           m[3], etype);
     GT_LAUNCH_CHECK("gt_edge_type");
+    return 0;
+}
+
+extern "C" int gt_edges_by_type(const int64_t* edge_index, const int32_t* etype, int64_t E, int32_t ntypes,
+                                int32_t* type_ptr, int32_t* src_t, int32_t* dst_t, int32_t* type_t, int32_t* work,
+                                void* stream) {
+    GT_CHECK_ARG(E >= 0 && E < (1ll << 31) && ntypes > 0 && ntypes <= EBT_MAX_TYPES, "gt_edges_by_type: ntypes=%d not in 1..%d", ntypes, EBT_MAX_TYPES);
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(work, 0, sizeof(int32_t) * 2 * (size_t)ntypes, st);
+    if (e != cudaSuccess) return cuda_fail(e, "gt_edges_by_type");
+    int32_t* cnt = work;
+    int32_t* cursor = work + ntypes;
+    int64_t chunk = (E + 4 * kNumSMs - 1) / (4 * kNumSMs);
+    if (chunk < 1024) chunk = 1024;
+    const unsigned grid = (unsigned)((E + chunk - 1) / chunk);
+    if (E > 0) k_ebt_hist<<<grid, 256, 0, st>>>(etype, E, ntypes, chunk, cnt);
+    k_ebt_scan<<<1, 32, 0, st>>>(cnt, ntypes, type_ptr, cursor);
+    if (E > 0) k_ebt_fill<<<grid, 256, 0, st>>>(edge_index, etype, E, ntypes, chunk, cursor, src_t, dst_t, type_t);
+    GT_LAUNCH_CHECK("gt_edges_by_type");
     return 0;
 }
 

@@ -150,15 +150,18 @@ join_wgrad_stream = join_side_streams
 
 
 class _WgradCtx:
-    """`with _WgradCtx(tensors...)`: run the enclosed launches on the side stream (if enabled), ordered after
-    everything issued so far on the current stream; the tensors are kept alive for that stream."""
+    """`with _WgradCtx(on, tensors...)`: if `on` and the side stream is enabled, run the enclosed launches on it,
+    ordered after everything issued so far on the current stream; the tensors are kept alive for that stream.
+    `on` must be False whenever a result of the enclosed launches is handed back to autograd (which assumes the
+    node's own stream)."""
 
-    def __init__(self, *tensors):
+    def __init__(self, on, *tensors):
+        self.on = bool(on)
         self.tensors = [t for t in tensors if t is not None]
         self.ctx = None
 
     def __enter__(self):
-        st = _wgrad["stream"]
+        st = _wgrad["stream"] if self.on else None
         if st is not None:
             st.wait_stream(torch.cuda.current_stream())
             for t in self.tensors:
@@ -382,6 +385,8 @@ class GraphPlan:
              ptr(self.cls_rows), ptr(self.scalars))
         self._etype = {}
         self._slots = {}
+        self._by_type = {}
+        self._edge_index = ei
         self._S = None
         # attention metadata of the packed layout (row key ranges, tile ranges): once per batch for all layers
         self.row_bounds = torch.empty(2 * self.n_rows, **i32)
@@ -427,6 +432,23 @@ class GraphPlan:
         self._slots[key] = tuple(res)
         return self._slots[key]
 
+    def edges_by_type(self, edge_index, etype, ntypes):
+        """edges counting-sorted by combined edge type (once per batch, reused by the table-gradient kernel of every
+        layer): (src_t, dst_t, type_t) int32 [E]"""
+        key = (etype.data_ptr(), int(ntypes))
+        hit = self._by_type.get(key)
+        if hit is None:
+            E, dev = max(self.E, 1), etype.device
+            i32 = dict(dtype=torch.int32, device=dev)
+            type_ptr = torch.empty(ntypes + 1, **i32)
+            src_t, dst_t, type_t = torch.empty(E, **i32), torch.empty(E, **i32), torch.empty(E, **i32)
+            work = torch.empty(2 * ntypes, **i32)
+            call("gt_edges_by_type", ptr(edge_index.contiguous()), ptr(etype), self.E, int(ntypes), ptr(type_ptr),
+                 ptr(src_t), ptr(dst_t), ptr(type_t), ptr(work))
+            hit = (src_t, dst_t, type_t, type_ptr)
+            self._by_type[key] = hit
+        return hit
+
     @property
     def S(self) -> int:
         """padded length min(max n_i, L) - needs one device->host read (public pad_batch API only)."""
@@ -462,7 +484,7 @@ class _EmbedSumFn(torch.autograd.Function):
         a_clp = (ctypes.c_int64 * n)(*clamps)
         a_tab = (ctypes.c_void_p * n)(*[t[0].data_ptr() for t in targets])
         side_ok = all(_main_grad(t) is not None for t in ctx.tables)   # leaf-only gradients: off the critical path
-        with (_WgradCtx(g) if side_ok else _WgradCtx()):
+        with _WgradCtx(side_ok, g):
             call("gt_embed_sum_bwd", dt_of(g), ptr(g), N, d, ld, n, a_idx, a_str, a_clp, a_tab)
             for t in ctx.tables:
                 _grad_done(t)
@@ -479,7 +501,11 @@ def embed_sum(index_cols, tables, clamps=None, dtype=None):
     strides = [c.stride(0) if c.dim() else 1 for c in index_cols]
     clamps = clamps or [t.shape[0] - 1 for t in tables]
     meta = (list(index_cols), strides, list(clamps), N, d, ldp(d), dtype or act_dtype())
-    return _EmbedSumFn.apply(meta, *tables)
+    out = _EmbedSumFn.apply(meta, *tables)
+    # every table delivers its gradient straight into the arena: the backward of this op runs on the weight-gradient
+    # stream, and so may whatever produces the gradient of `out` if `out` only feeds leaf gradients (edge tables)
+    out._gt_leaf_side = all(_main_grad(t) is not None for t in tables)
+    return out
 
 
 # ----------------------------------------------------------------------------- dense layers
@@ -561,7 +587,7 @@ class _LinearFn(torch.autograd.Function):
         weight, bias = ctx.params
         # parameter gradients accumulated in place need no ordering with the rest of the backward: side stream
         side_ok = _main_grad(weight) is not None and (not has_bias or _main_grad(bias) is not None)
-        with (_WgradCtx(gy, x) if side_ok else _WgradCtx()):
+        with _WgradCtx(side_ok, gy, x):
             if ctx.needs_input_grad[1]:
                 tgt, gw = _grad_target(weight)
                 # dW[n,k] = sum_m dY[m,n] X[m,k]: both operands MN-major, split-K over the rows, accumulated in place
@@ -587,7 +613,7 @@ def linear(x, weight, bias=None, relu=False, out_f32=False, resid=None, drop_p=0
 # ----------------------------------------------------------------------------- aggregation
 class _AggregateFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, plan, conv, d, edge_kind, edge_attr, edge_w, edge_b, etype, table, self_param):
+    def forward(ctx, x, plan, conv, d, edge_kind, edge_attr, edge_w, edge_b, etype, table, self_param, tab_side=False):
         x = x.contiguous()
         N, ld = x.shape
         out = torch.empty_like(x)
@@ -607,6 +633,10 @@ class _AggregateFn(torch.autograd.Function):
              ptr(edge_w), ptr(edge_b), ptr(etype), ptr(table), ptr(sp), ptr(slots[0][0]), ptr(slots[0][1]),
              ptr(slots[0][2]))
         ctx.slots = slots[1]
+        ctx.split = edge_kind == EDGE_TABLE and table.shape[0] <= 1024
+        ctx.tab_side = bool(tab_side)
+        if ctx.split:   # type-sorted edges for the table-gradient kernel (once per batch)
+            plan.edges_by_type(plan._edge_index, etype, table.shape[0])
         ctx.save_for_backward(x, edge_attr, edge_w, edge_b, etype, table, sp)
         ctx.params = (edge_w_param, edge_b, self_param)
         ctx.meta = (plan, conv, d, edge_kind, kdim, self_param.shape)
@@ -624,19 +654,31 @@ class _AggregateFn(torch.autograd.Function):
         if edge_kind == EDGE_LINEAR:
             tw, tb = _grad_target(pw), _grad_target(pb)
         dtab = zeros_f32(tuple(table.shape), x.device) if edge_kind == EDGE_TABLE else None
+        # the edge-table gradient is a leaf gradient: computed by its own kernel over the type-sorted edges, on the
+        # weight-gradient stream, instead of shared-memory atomics inside the adjoint (which then stays as cheap as
+        # the forward)
+        split = ctx.split
         tself = _grad_target(pself)
         call("gt_aggregate_bwd", dt_of(x), conv, ptr(x), ptr(g), ptr(dx), N, d, ld, ptr(plan.rowptr_dst),
              ptr(plan.rowptr_src), ptr(plan.dst_by_src), ptr(plan.eid_by_src), edge_kind, ptr(edge_attr), kdim,
              ptr(edge_w), ptr(edge_b), ptr(etype), ptr(table), table.shape[0] if edge_kind == EDGE_TABLE else 0, ptr(sp),
-             ptr(tw[0]), ptr(tb[0]), ptr(dtab), ptr(tself[0]), ptr(ctx.slots[0]), ptr(ctx.slots[1]), ptr(ctx.slots[2]))
+             ptr(tw[0]), ptr(tb[0]), None if split else ptr(dtab), ptr(tself[0]), ptr(ctx.slots[0]), ptr(ctx.slots[1]),
+             ptr(ctx.slots[2]))
+        if split:
+            src_t, dst_t, type_t, _ = plan.edges_by_type(plan._edge_index, etype, table.shape[0])
+            # on the side stream only when the consumer of dtab (the embed_sum backward of the table) runs there too
+            with _WgradCtx(ctx.tab_side, x, g, dtab):
+                call("gt_aggregate_table_grad", dt_of(x), conv, ptr(x), ptr(g), N, d, ld, ptr(plan.rowptr_src), plan.E,
+                     ptr(src_t), ptr(dst_t), ptr(type_t), ptr(table), table.shape[0], ptr(dtab))
         for prm in (pw, pb, pself):
             _grad_done(prm)
-        return dx, None, None, None, None, None, tw[1], tb[1], None, dtab, tself[1]
+        return dx, None, None, None, None, None, tw[1], tb[1], None, dtab, tself[1], None
 
 
 def aggregate(x, plan, conv, d, self_param, edge_kind=EDGE_NONE, edge_attr=None, edge_w=None, edge_b=None,
               etype=None, table=None):
-    return _AggregateFn.apply(x, plan, conv, d, edge_kind, edge_attr, edge_w, edge_b, etype, table, self_param)
+    tab_side = edge_kind == EDGE_TABLE and bool(getattr(table, "_gt_leaf_side", False))
+    return _AggregateFn.apply(x, plan, conv, d, edge_kind, edge_attr, edge_w, edge_b, etype, table, self_param, tab_side)
 
 
 # ----------------------------------------------------------------------------- segment ops

@@ -104,7 +104,8 @@ int gt_aggregate_fwd(int dt, int conv, const void* x, void* out, int64_t N, int3
                      const float* self_param, const float* norm_slot, const int32_t* etype_slot,
                      const float* attr_slot, void* stream);
 /* adjoint: dx (same dtype), and fp32 accumulators (must be zeroed by the caller):
- * d_edge_w [d,kdim], d_edge_b [d] (LINEAR) or d_table [ntypes, ld] (TABLE), d_self ([d] or [1]). */
+ * d_edge_w [d,kdim], d_edge_b [d] (LINEAR) or d_table [ntypes, ld] (TABLE; NULL = skipped here, see
+ * gt_aggregate_table_grad), d_self ([d] or [1]). */
 int gt_aggregate_bwd(int dt, int conv, const void* x, const void* dout, void* dx, int64_t N,
                      int32_t d, int32_t ld,
                      const int32_t* rowptr_dst, const int32_t* rowptr_src, const int32_t* dst_by_src,
@@ -122,6 +123,20 @@ int gt_edge_slots(const int32_t* rowptr_slot, const int32_t* nbr_slot, const int
                   const int32_t* rowptr_src, int64_t E, int64_t N, const int32_t* etype,
                   const float* edge_attr, int32_t kdim, float* norm_slot, int32_t* etype_slot,
                   float* attr_slot, void* stream);
+
+/* Edge-table gradient of gt_aggregate split off the adjoint (leaf gradient, off the critical path):
+ * d_table[ty,:] += sum over edges e of type ty of norm_e * dout[dst_e,:] * 1[x[src_e,:] + table[ty,:] > 0]
+ * (norm_e = 1 for GIN).  Pass d_table = NULL to gt_aggregate_bwd when this is used.  The edges come SORTED BY TYPE
+ * from gt_edges_by_type (once per batch): type_ptr[ntypes+1] (run boundaries), src_t / dst_t / type_t [E] = endpoints
+ * and type of the edge in sorted slot p (order inside a type run unspecified); work = int32[2*ntypes] scratch;
+ * every etype must lie in [0, ntypes), ntypes <= 1024. */
+int gt_edges_by_type(const int64_t* edge_index, const int32_t* etype, int64_t E, int32_t ntypes,
+                     int32_t* type_ptr, int32_t* src_t, int32_t* dst_t, int32_t* type_t, int32_t* work,
+                     void* stream);
+int gt_aggregate_table_grad(int dt, int conv, const void* x, const void* dout, int64_t N, int32_t d, int32_t ld,
+                            const int32_t* rowptr_src, int64_t E, const int32_t* src_t, const int32_t* dst_t,
+                            const int32_t* type_t, const float* table, int32_t ntypes, float* d_table,
+                            void* stream);
 
 /* ---- per-graph segment ops (PyG global_add_pool / vn[batch], reference
  *      modules/gnn_module.py:199,219) --------------------------------------------------------

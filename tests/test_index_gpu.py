@@ -113,3 +113,23 @@ def test_empty_edge_list_and_single_node_graphs():
     assert _np(plan.rowptr_dst).tolist() == [0, 0, 0, 0, 0]
     assert _np(plan.tok_off).tolist() == [0, 2, 5, 7]
     assert plan.S == 2
+
+
+@pytest.mark.parametrize("B,ntypes", [(64, 60), (7, 3), (300, 1000)])
+def test_edges_by_type_is_a_sorted_permutation(B, ntypes):
+    """gt_edges_by_type: counting sort of the edges by combined edge type - run boundaries equal the histogram scan,
+    types are sorted, and the (src, dst, type) multiset is preserved (order inside a run is unspecified)"""
+    batch = synth.gen_mol(B, seed=5)
+    ei = batch.edge_index.cuda()
+    E = ei.shape[1]
+    g = torch.Generator().manual_seed(1)
+    et = torch.randint(0, ntypes, (E,), generator=g, dtype=torch.int32)
+    plan = ops.GraphPlan(ei, batch.batch.cuda(), B)
+    src_t, dst_t, type_t, type_ptr = plan.edges_by_type(ei, et.cuda(), ntypes)
+    cnt = np.bincount(et.numpy(), minlength=ntypes)
+    assert np.array_equal(_np(type_ptr), np.concatenate([[0], np.cumsum(cnt)]).astype(np.int32))
+    ty = _np(type_t)[:E]
+    assert np.all(np.diff(ty) >= 0)
+    got = np.stack([ty, _np(src_t)[:E], _np(dst_t)[:E]], 1)
+    ref = np.stack([et.numpy(), ei[0].cpu().numpy().astype(np.int32), ei[1].cpu().numpy().astype(np.int32)], 1)
+    assert np.array_equal(got[np.lexsort(got.T[::-1])], ref[np.lexsort(ref.T[::-1])])

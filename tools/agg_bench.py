@@ -44,3 +44,13 @@ for cfg in ("molpcba", "code2", "syn"):
     byt = 2 * N * d * 2 + 16 * E + ea
     print(f"{cfg:8s} N={N} E={E} d={d}: fwd {t_f:7.1f} us ({byt / t_f / 1e3:7.1f} GB/s)   bwd(+grad bookkeeping) {t_b:7.1f} us ({byt / t_b / 1e3:7.1f} GB/s)"
           f"   variant={os.environ.get('GT_AGG_VARIANT', '0')}")
+    # per-export timing of the adjoint (CUDA events around every C-ABI call)
+    from graphtrans_b200 import _lib
+    import collections
+    _lib.start_profile()
+    for _ in range(10):
+        torch.autograd.grad(y, x, gy, retain_graph=True)
+    per = collections.defaultdict(list)
+    for name, ms, _ in _lib.stop_profile():
+        per[name].append(ms * 1e3)
+    print("          " + "  ".join(f"{k}: {sum(v) / len(v):.1f} us" for k, v in per.items()))
