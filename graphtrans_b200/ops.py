@@ -131,19 +131,23 @@ def next_salt() -> int:
 # can run on a second stream next to the memory-bound kernels of the next layer (BN / LayerNorm backward, aggregation
 # adjoint ...), which co-reside on an SM with the one-CTA-per-SM persistent GEMM.  Opt-in: whoever enables it must
 # call join_side_streams() after backward() and before reading gradients (GraphedStep and bench.py do).
-_wgrad = {"stream": None}
+_wgrad = {"stream": None, "used": False}
 
 
 def enable_wgrad_stream(on=True, device="cuda"):
     _wgrad["stream"] = torch.cuda.Stream(device=device) if on else None
+    _wgrad["used"] = False
 
 
 def join_side_streams():
     """make the current stream wait for the weight-gradient stream and the parallel-branch stream (call after
     backward(), before anything reads the gradients)"""
-    for st in (_branch["stream"], _wgrad["stream"]):
-        if st is not None:
-            torch.cuda.current_stream().wait_stream(st)
+    for side in (_branch, _wgrad):
+        # only a stream that forked since the last join: waiting on an untouched stream would make a capturing
+        # stream depend on uncaptured work (cudaErrorStreamCaptureIsolation)
+        if side["stream"] is not None and side["used"]:
+            torch.cuda.current_stream().wait_stream(side["stream"])
+            side["used"] = False
 
 
 join_wgrad_stream = join_side_streams
@@ -163,6 +167,7 @@ class _WgradCtx:
     def __enter__(self):
         st = _wgrad["stream"] if self.on else None
         if st is not None:
+            _wgrad["used"] = True
             st.wait_stream(torch.cuda.current_stream())
             for t in self.tensors:
                 t.record_stream(st)
@@ -183,11 +188,12 @@ class _WgradCtx:
 # the captured CUDA graph).  autograd runs the backward of every node on the stream of its forward and inserts the
 # cross-stream waits itself, so the backward overlaps the same way.  Opt-in like the weight-gradient stream: whoever
 # enables it calls join_side_streams() after backward() (GraphedStep and bench.py do).
-_branch = {"stream": None}
+_branch = {"stream": None, "used": False}
 
 
 def enable_branch_stream(on=True, device="cuda"):
     _branch["stream"] = torch.cuda.Stream(device=device) if on else None
+    _branch["used"] = False
 
 
 class Branch:
@@ -201,6 +207,7 @@ class Branch:
 
     def __enter__(self):
         if self.st is not None:
+            _branch["used"] = True
             self.st.wait_stream(torch.cuda.current_stream())
             for t in self.tensors:
                 t.record_stream(self.st)
@@ -945,7 +952,8 @@ def pad_batch_dense(h, plan, S):
 # ----------------------------------------------------------------------------- attention
 class _MHAFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, qkv, plan, nhead, key_start, drop_p, salt):
+    def forward(ctx, qkv, plan, nhead, key_start, drop_p, salt, impl=None):
+        impl = MHA_IMPL if impl is None else impl
         qkv = qkv.contiguous()
         n_rows, d3 = qkv.shape
         d = d3 // 3
@@ -957,15 +965,15 @@ class _MHAFn(torch.autograd.Function):
         call("gt_mha_fwd", dt_of(qkv), ptr(qkv), ptr(plan.tok_graph), ptr(plan.tok_off), ptr(key_start), ptr(meta[0]),
              ptr(meta[1]), n_rows,
              plan.B, nhead, dh, scale, ptr(out), ptr(lse), float(drop_p),
-             ptr(rng_state(qkv.device)) if drop_p else None, salt, MHA_IMPL)
+             ptr(rng_state(qkv.device)) if drop_p else None, salt, impl)
         ctx.save_for_backward(qkv, out, lse)
-        ctx.meta = (plan, nhead, dh, scale, key_start, float(drop_p), salt)
+        ctx.meta = (plan, nhead, dh, scale, key_start, float(drop_p), salt, impl)
         return out
 
     @staticmethod
     def backward(ctx, g):
         qkv, out, lse = ctx.saved_tensors
-        plan, nhead, dh, scale, key_start, drop_p, salt = ctx.meta
+        plan, nhead, dh, scale, key_start, drop_p, salt, impl = ctx.meta
         g = g.contiguous()
         n_rows = qkv.shape[0]
         dqkv = torch.empty_like(qkv)
@@ -973,13 +981,13 @@ class _MHAFn(torch.autograd.Function):
         meta = (getattr(plan, "row_bounds", None), getattr(plan, "tile_bounds", None)) if key_start is None else (None, None)
         call("gt_mha_bwd", dt_of(qkv), ptr(qkv), ptr(out), ptr(g), ptr(lse), ptr(plan.tok_graph), ptr(plan.tok_off),
              ptr(key_start), ptr(meta[0]), ptr(meta[1]), n_rows, plan.B, nhead, dh, scale, ptr(dqkv), ptr(delta), drop_p,
-             ptr(rng_state(qkv.device)) if drop_p else None, salt, MHA_IMPL)
-        return dqkv, None, None, None, None, None
+             ptr(rng_state(qkv.device)) if drop_p else None, salt, impl)
+        return dqkv, None, None, None, None, None, None
 
 
 def mha_packed(qkv, plan, nhead, key_start=None, drop_p=0.0):
     """`plan` needs .tok_graph, .tok_off and .B (GraphPlan or any object with those fields)."""
-    return _MHAFn.apply(qkv, plan, nhead, key_start, drop_p, next_salt() if drop_p else 0)
+    return _MHAFn.apply(qkv, plan, nhead, key_start, drop_p, next_salt() if drop_p else 0, None)
 
 
 # ----------------------------------------------------------------------------- PNA

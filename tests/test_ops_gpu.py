@@ -163,11 +163,11 @@ def test_mha_dropout_matches_masked_reference():
     probe = torch.zeros_like(qkv)
     probe[:, 2 * d:2 * d + n] = torch.eye(n, device="cuda")
     salt = 77
-    out = ops._MHAFn.apply(probe, plan, nhead, None, p, salt)
+    out = ops._MHAFn.apply(probe, plan, nhead, None, p, salt, None)
     mask = (out[:, :n] > 0).double()
     assert abs(mask.mean().item() - (1 - p)) < 0.05
     qkv.requires_grad_(True)
-    out = ops._MHAFn.apply(qkv, plan, nhead, None, p, salt)
+    out = ops._MHAFn.apply(qkv, plan, nhead, None, p, salt, None)
     w = torch.randn_like(out)
     (out * w).sum().backward()
     q64 = qkv.detach().double().requires_grad_(True)

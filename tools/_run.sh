@@ -1,4 +1,5 @@
-for m in 0 2 10 15 8 3; do
-GT_BN_SLAB=$m python bench.py --no-cpu-baseline --no-roofline --no-e2e > gpurun_out/bench25_slab$m.log 2>&1
-done
-python tools/gemm_bench.py > gpurun_out/gemm_bench6.log 2>&1
+python tools/mha_bench.py molpcba nci1 > gpurun_out/mha_bench2.log 2>&1
+python -m pytest tests -q -m gpu -x 2>&1 | tail -30 > gpurun_out/t34.log
+python bench.py --no-cpu-baseline > gpurun_out/bench27.log 2>&1
+python bench.py --no-cpu-baseline --config nci1 > gpurun_out/bench27_nci1.log 2>&1
+tail -5 gpurun_out/t34.log
