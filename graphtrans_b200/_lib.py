@@ -32,6 +32,8 @@ SIGNATURES = {
     "gt_batch_plan": [P, L, L, L, I32, P, P, P, P, P, P, P, P, P, P],
     "gt_embed_sum_fwd": [I, P, L, I32, I32, I32, P, P, P, P, P],
     "gt_embed_sum_bwd": [I, P, L, I32, I32, I32, P, P, P, P, P],
+    "gt_onehot": [L, I32, P, P, P, P, I32, P, P],
+    "gt_embed_unpack": [P, I32, I32, I32, I32, P, P, P, P],
     "gt_aggregate_fwd": [I, I, P, P, L, I32, I32, P, P, P, P, I, P, I32, P, P, P, P, P, P, P, P, P],
     "gt_aggregate_bwd": [I, I, P, P, P, L, I32, I32, P, P, P, P, I, P, I32, P, P, P, P, I32, P, P, P, P, P, P, P, P, P],
     "gt_edge_slots": [P, P, P, P, L, L, P, P, I32, P, P, P, P],
@@ -76,6 +78,7 @@ _lib = None
 launch_count = 0   # C-ABI calls issued
 kernel_count = 0   # kernels those calls launched (bench.py reports it as gpu_launches)
 _profile = None    # when a list: (name, start_event, end_event, info) per call (bench.py roofline pass)
+_stamps = None     # when a dict: device timestamp after every call (tools/graph_trace.py; survives graph capture)
 
 
 def load():
@@ -126,10 +129,32 @@ def call(name, *args):
         _profile.append((name, e0, e1, args))
     else:
         rc = getattr(lib, name)(*args, stream())
+    if _stamps is not None:
+        stamp(name, args)
     launch_count += 1
     kernel_count += KERNELS_PER_CALL.get(name, 1)
     if rc != 0:
         raise RuntimeError(f"{name} failed (rc={rc}): {lib.gt_last_error().decode()}")
+
+
+def start_stamps(capacity=8192, device="cuda"):
+    """record a %globaltimer stamp on the launching stream after every C-ABI call (and wherever stamp() is called)"""
+    global _stamps
+    _stamps = {"buf": torch.zeros(capacity, dtype=torch.int64, device=device), "rec": []}
+
+
+def stamp(name, args=()):
+    st = _stamps
+    idx = len(st["rec"])
+    load().gtdbg_stamp(ctypes.c_void_p(st["buf"].data_ptr()), idx, ctypes.c_void_p(stream()))
+    st["rec"].append((name, stream(), args))
+
+
+def stop_stamps():
+    """-> (records [(name, stream, args)], int64 tensor of ns stamps); the buffer keeps being rewritten by replays"""
+    global _stamps
+    st, _stamps = _stamps, None
+    return st["rec"], st["buf"]
 
 
 def start_profile():

@@ -42,30 +42,42 @@ __global__ void k_segment_sum(const T* __restrict__ x, const int32_t* __restrict
     }
 }
 
-// sorted variant (graphs own contiguous row ranges [node_off[g], node_off[g+1])): one warp per (graph, 128-channel
-// chunk) sums its rows in registers and is the single writer of out[g, chunk] = init[g, chunk] + sum - no atomics,
-// deterministic, `out` needs no zero fill
+// sorted variant (graphs own contiguous row ranges [node_off[g], node_off[g+1])): one BLOCK per (graph, 128-channel
+// chunk); its 8 warps take interleaved rows (a Code2 graph has up to 2000 rows: one warp walking them alone was the
+// critical path of the virtual-node branch), partial sums meet in shared memory and warp 0 is the single writer of
+// out[g, chunk] = init[g, chunk] + sum - no atomics, deterministic, `out` needs no zero fill
 template <typename T>
 __global__ void __launch_bounds__(256)
 k_segment_sum_sorted(const T* __restrict__ x, const int32_t* __restrict__ node_off, int B, int ld, int nch,
                      const float* __restrict__ init, float* __restrict__ out) {
-    const int lane = threadIdx.x & 31;
-    const int item = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (item >= B * nch) return;
+    __shared__ float4 part[8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int item = blockIdx.x;
     const int g = item / nch, c0 = (item - g * nch) * 128 + lane * 4;
-    if (c0 >= ld) return;
+    const bool col_ok = c0 < ld;
     const int r0 = node_off[g], r1 = node_off[g + 1];
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (col_ok) {
 #pragma unroll 4
-    for (int r = r0; r < r1; ++r) {
-        float v[4];
-        ld4(x + (int64_t)r * ld + c0, v);
+        for (int r = r0 + warp; r < r1; r += 8) {
+            float v[4];
+            ld4(x + (int64_t)r * ld + c0, v);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) acc[q] += v[q];
+            for (int q = 0; q < 4; ++q) acc[q] += v[q];
+        }
     }
-    float4 cur = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (init) cur = *reinterpret_cast<const float4*>(init + (int64_t)g * ld + c0);
-    *reinterpret_cast<float4*>(out + (int64_t)g * ld + c0) = make_float4(cur.x + acc[0], cur.y + acc[1], cur.z + acc[2], cur.w + acc[3]);
+    part[warp][lane] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    __syncthreads();
+    if (warp == 0 && col_ok) {
+        float4 cur = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (init) cur = *reinterpret_cast<const float4*>(init + (int64_t)g * ld + c0);
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const float4 p = part[w][lane];
+            cur.x += p.x; cur.y += p.y; cur.z += p.z; cur.w += p.w;
+        }
+        *reinterpret_cast<float4*>(out + (int64_t)g * ld + c0) = cur;
+    }
 }
 
 template <typename T>
@@ -1025,7 +1037,7 @@ extern "C" int gt_segment_sum_sorted(int dt, const void* x, const int32_t* node_
                                      const float* init, float* out, void* stream) {
     GT_CHECK_ARG(B > 0 && ld > 0 && ld % 4 == 0, "gt_segment_sum_sorted: bad shape");
     const int nch = (ld + 127) / 128;
-    GT_DISPATCH_DT(dt, (k_segment_sum_sorted<T><<<(unsigned)((B * nch + 7) / 8), 256, 0, ST>>>((const T*)x, node_off, (int)B, ld, nch, init, out)));
+    GT_DISPATCH_DT(dt, (k_segment_sum_sorted<T><<<(unsigned)(B * nch), 256, 0, ST>>>((const T*)x, node_off, (int)B, ld, nch, init, out)));
     GT_LAUNCH_CHECK("gt_segment_sum_sorted");
     return 0;
 }
@@ -1215,6 +1227,86 @@ extern "C" int gt_embed_sum_bwd(int dt, const void* dout, int64_t N, int32_t d, 
         k_embed_bwd<T><<<grid, 256, smem, ST>>>(c, N, d, ld, (const T*)dout);
     });
     GT_LAUNCH_CHECK("gt_embed_sum_bwd");
+    return 0;
+}
+
+// ---- embedding gradients of SMALL tables as a tensor-core contraction --------------------------------------------
+// d_table[v] = sum over the nodes whose index is v of dout[node] is OneHot^T [R x N] . dout [N x d]: the few-row
+// vocabularies (atom / node-type / depth tables) serialise atomics on a handful of rows, the contraction does not.
+// gt_onehot writes the bf16 one-hot operand [N, R_pad] (row i has a 1 at base_c + idx_c[i] for every column c with
+// base_c >= 0) once per batch; the backward is one gt_gemm (split-K over the nodes, fp32) + gt_embed_unpack.
+namespace gt {
+struct OneHotCols {
+    const int64_t* idx[EMB_MAXCOL];
+    int64_t stride[EMB_MAXCOL];
+    int64_t clamp[EMB_MAXCOL];
+    int32_t base[EMB_MAXCOL];
+    int32_t rows[EMB_MAXCOL];
+    float* dtable[EMB_MAXCOL];
+    int ncol;
+};
+__global__ void k_onehot(OneHotCols cols, int64_t N, int groups, bf16* __restrict__ out) {
+    const int64_t total = N * groups;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / groups;
+        const int g = (int)(i - r * groups);
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+        for (int c = 0; c < cols.ncol; ++c) {
+            if (cols.base[c] < 0) continue;
+            int64_t id = cols.idx[c][r * cols.stride[c]];
+            if (id > cols.clamp[c]) id = cols.clamp[c];
+            const int pos = cols.base[c] + (int)id;
+            if ((pos >> 3) == g) w[(pos & 7) >> 1] |= 0x3F80u << (16 * (pos & 1));   // bf16 1.0
+        }
+        *reinterpret_cast<uint4*>(out + (r * groups + g) * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+__global__ void k_embed_unpack(OneHotCols cols, const float* __restrict__ temp, int ld_t, int d, int R) {
+    const int vpr = d / 4;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < R * vpr; i += gridDim.x * blockDim.x) {
+        const int r = i / vpr, c0 = (i - r * vpr) * 4;
+        for (int c = 0; c < cols.ncol; ++c) {
+            if (cols.base[c] < 0 || r < cols.base[c] || r >= cols.base[c] + cols.rows[c]) continue;
+            const float4 v = *reinterpret_cast<const float4*>(temp + (int64_t)r * ld_t + c0);
+            float* dst = cols.dtable[c] + (int64_t)(r - cols.base[c]) * d + c0;
+            dst[0] += v.x; dst[1] += v.y; dst[2] += v.z; dst[3] += v.w;     // single writer per element
+        }
+    }
+}
+}  // namespace gt
+
+static int fill_onehot(OneHotCols& c, int32_t ncol, const int64_t* const* idx, const int64_t* stride, const int64_t* clamp,
+                       const int32_t* base, const int32_t* rows, float* const* dtable) {
+    GT_CHECK_ARG(ncol >= 1 && ncol <= EMB_MAXCOL, "onehot: ncol=%d not in 1..%d", ncol, EMB_MAXCOL);
+    c.ncol = ncol;
+    for (int i = 0; i < ncol; ++i) {
+        c.idx[i] = idx ? idx[i] : nullptr;
+        c.stride[i] = stride ? stride[i] : 0;
+        c.clamp[i] = clamp ? clamp[i] : 0;
+        c.base[i] = base[i];
+        c.rows[i] = rows ? rows[i] : 0;
+        c.dtable[i] = dtable ? dtable[i] : nullptr;
+    }
+    return 0;
+}
+
+extern "C" int gt_onehot(int64_t N, int32_t ncol, const int64_t* const* idx_host, const int64_t* stride_host,
+                         const int64_t* clamp_host, const int32_t* base_host, int32_t r_pad, void* out, void* stream) {
+    GT_CHECK_ARG(N > 0 && r_pad > 0 && r_pad % 8 == 0, "gt_onehot: bad shape");
+    OneHotCols c;
+    if (int r = fill_onehot(c, ncol, idx_host, stride_host, clamp_host, base_host, nullptr, nullptr)) return r;
+    k_onehot<<<blocks_for(N * (r_pad / 8), 256), 256, 0, ST>>>(c, N, r_pad / 8, (bf16*)out);
+    GT_LAUNCH_CHECK("gt_onehot");
+    return 0;
+}
+
+extern "C" int gt_embed_unpack(const float* temp, int32_t ld_t, int32_t d, int32_t R, int32_t ncol, const int32_t* base_host,
+                               const int32_t* rows_host, float* const* dtable_host, void* stream) {
+    GT_CHECK_ARG(R > 0 && d % 4 == 0 && ld_t >= d && ld_t % 4 == 0, "gt_embed_unpack: bad shape");
+    OneHotCols c;
+    if (int r = fill_onehot(c, ncol, nullptr, nullptr, nullptr, base_host, rows_host, dtable_host)) return r;
+    k_embed_unpack<<<blocks_for((int64_t)R * (d / 4), 256), 256, 0, ST>>>(c, temp, ld_t, d, R);
+    GT_LAUNCH_CHECK("gt_embed_unpack");
     return 0;
 }
 

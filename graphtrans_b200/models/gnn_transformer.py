@@ -58,7 +58,8 @@ class _GraphTransBase(BaseModel):
         else:
             for _ in range(args.max_seq_len):
                 self.graph_pred_linear_list.append(torch.nn.Linear(args.d_model, self.num_tasks))
-        ops.w16.register(self)   # bf16 operand copies of every Linear / in_proj weight, refreshed once per step
+        self._w16 = ops.W16Registry()
+        self._w16.register(self)   # bf16 operand copies of every Linear / in_proj weight, refreshed once per step
 
     def _gnn2transformer(self, parts):
         """Linear over the logical concatenation of the JK parts without materialising the concat:
@@ -72,11 +73,18 @@ class _GraphTransBase(BaseModel):
 
     def forward(self, batched_data, perturb=None):
         ops._lib.require_cuda(batched_data.batch, batched_data.edge_index)
+        dev = batched_data.batch.device
+        side = None
         if self.training:
-            ops.begin_step(batched_data.batch.device)
+            ops.begin_step(dev, cast_now=False, registry=self._w16)
+            if ops.precision() == "bf16":       # bf16 weight copies refreshed next to the plan build
+                side = lambda: self._w16.refresh(dev)  # noqa: E731
+        elif ops.precision() == "bf16":
+            ops.w16 = self._w16
+            side = lambda: self._w16.refresh(dev)  # noqa: E731
         enc = self.transformer_encoder
         plan = ops.GraphPlan(batched_data.edge_index, batched_data.batch, getattr(batched_data, "num_graphs", None),
-                             enc.max_input_len, cls=self.pooling == "cls")
+                             enc.max_input_len, cls=self.pooling == "cls", side_work=side)
         parts = self.gnn_node.forward_parts(batched_data, perturb, plan=plan)
         h_node = self._gnn2transformer(parts)                          # [N, d_model]
         h_graph = enc.forward_packed(h_node, plan)                       # [B, d_model] (pooled rows only)

@@ -105,15 +105,21 @@ class _W16Registry:
         return self.copies.get(id(w))
 
 
-w16 = _W16Registry()
+W16Registry = _W16Registry
+w16 = _W16Registry()   # registry of the model whose step is running (begin_step(registry=...)); default: a global one
 
 
-def begin_step(device):
+def begin_step(device, cast_now=True, registry=None):
     """advance the device-side dropout step counter (one launch; graph-capturable) and restart the
-    per-step call-site salts.  Called by the model at the top of every training forward."""
+    per-step call-site salts.  Called by the model at the top of every training forward.  cast_now=False leaves the
+    refresh of the bf16 weight copies to the caller (the model hands it to GraphPlan as `side_work`, so it runs on the
+    branch stream next to the CSR build)."""
+    global w16
+    if registry is not None:   # every model owns its operand copies: a captured step keeps valid pointers when
+        w16 = registry         # another model is built or stepped in the same process
     _salt[0] = 0
     call("gt_rng_advance", ptr(rng_state(device)))
-    if _PRECISION == "bf16":
+    if _PRECISION == "bf16" and cast_now:
         w16.refresh(device)
     a = _arena(device)
     if a["off"] or not a["armed"]:
@@ -358,7 +364,9 @@ class GraphPlan:
     gt_csr_build / gt_batch_plan without any host synchronisation (B comes from
     `batch.num_graphs` when present, otherwise one .item() like reference gnn_module.py:195)."""
 
-    def __init__(self, edge_index, batch, num_graphs=None, max_input_len=1000, cls=True):
+    def __init__(self, edge_index, batch, num_graphs=None, max_input_len=1000, cls=True, side_work=None):
+        """side_work: optional callable launched on the branch stream together with the token plan (the two CSR
+        sorts stay on the current stream): the integer prep of a batch is three independent chains."""
         _lib.require_cuda(edge_index, batch)
         dev = batch.device
         N = batch.numel()
@@ -374,8 +382,6 @@ class GraphPlan:
         self.dst_by_src = torch.empty(max(E, 1), **i32)
         self.eid_by_src = torch.empty(max(E, 1), **i32)
         work = torch.empty(2 * (N + 1), **i32)
-        call("gt_csr_build", ptr(ei), E, N, ptr(self.rowptr_dst), ptr(self.src_by_dst), ptr(self.eid_by_dst),
-             ptr(self.rowptr_src), ptr(self.dst_by_src), ptr(self.eid_by_src), ptr(work))
         self.node_off = torch.empty(B + 1, **i32)
         self.kept = torch.empty(B, **i32)
         self.tok_off = torch.empty(B + 1, **i32)
@@ -386,20 +392,29 @@ class GraphPlan:
         self.node2tok = torch.empty(N, **i32)
         self.cls_rows = torch.empty(B, **i32)
         self.scalars = torch.empty(4, **i32)
+        # attention metadata of the packed layout (row key ranges, tile ranges): once per batch for all layers
+        self.row_bounds = torch.empty(2 * self.n_rows, **i32)
+        self.tile_bounds = torch.empty(2 * ((self.n_rows + 127) // 128), **i32)
         b = batch.contiguous()
-        call("gt_batch_plan", ptr(b), N, B, self.L, int(self.cls), ptr(self.node_off), ptr(self.kept), ptr(self.tok_off),
-             ptr(self.tok2node), ptr(self.tok_graph), ptr(self.node_graph), ptr(self.node2tok),
-             ptr(self.cls_rows), ptr(self.scalars))
+        plan_out = (self.node_off, self.kept, self.tok_off, self.tok2node, self.tok_graph, self.node_graph, self.node2tok,
+                    self.cls_rows, self.scalars, self.row_bounds, self.tile_bounds)
+        br = Branch(b, *plan_out)
+        with br:    # token plan (+ the caller's side work) next to the CSR sorts
+            if side_work is not None:
+                side_work()
+            call("gt_batch_plan", ptr(b), N, B, self.L, int(self.cls), ptr(self.node_off), ptr(self.kept), ptr(self.tok_off),
+                 ptr(self.tok2node), ptr(self.tok_graph), ptr(self.node_graph), ptr(self.node2tok),
+                 ptr(self.cls_rows), ptr(self.scalars))
+            call("gt_mha_meta", ptr(self.tok_graph), ptr(self.tok_off), self.n_rows, B, ptr(self.row_bounds),
+                 ptr(self.tile_bounds))
+        call("gt_csr_build", ptr(ei), E, N, ptr(self.rowptr_dst), ptr(self.src_by_dst), ptr(self.eid_by_dst),
+             ptr(self.rowptr_src), ptr(self.dst_by_src), ptr(self.eid_by_src), ptr(work))
+        br.join()
         self._etype = {}
         self._slots = {}
         self._by_type = {}
         self._edge_index = ei
         self._S = None
-        # attention metadata of the packed layout (row key ranges, tile ranges): once per batch for all layers
-        self.row_bounds = torch.empty(2 * self.n_rows, **i32)
-        self.tile_bounds = torch.empty(2 * ((self.n_rows + 127) // 128), **i32)
-        call("gt_mha_meta", ptr(self.tok_graph), ptr(self.tok_off), self.n_rows, B, ptr(self.row_bounds),
-             ptr(self.tile_bounds))
 
     def edge_type(self, edge_attr: torch.Tensor, dims) -> torch.Tensor:
         """combined categorical edge id (mixed radix over `dims`) for table edge encoders."""
@@ -465,6 +480,11 @@ class GraphPlan:
 
 
 # ----------------------------------------------------------------------------- node encoders
+ONEHOT_MIN_ROWS = int(os.environ.get("GT_ONEHOT_MIN_ROWS", "2048"))      # below this many index rows the atomics kernel is cheap (edge-type digit tables)
+ONEHOT_MAX_TABLE = 256      # tables with more rows keep global atomics (little contention per row)
+ONEHOT_MAX_TOTAL = 1024
+
+
 class _EmbedSumFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, meta, *tables):
@@ -478,6 +498,26 @@ class _EmbedSumFn(torch.autograd.Function):
         call("gt_embed_sum_fwd", dt_of(out), ptr(out), N, d, ld, n, a_idx, a_str, a_clp, a_tab)
         ctx.meta = meta
         ctx.tables = tables
+        ctx.onehot = None
+        # few-row vocabularies: their gradient is the contraction OneHot^T . dout on the tensor cores (bf16 mode);
+        # the one-hot operand is written here, once per batch
+        if dtype == torch.bfloat16 and N >= ONEHOT_MIN_ROWS and any(t.requires_grad for t in tables):
+            base, rows, acc = [], [], 0
+            for c, t in enumerate(tables):
+                r = min(int(clamps[c]) + 1, t.shape[0])
+                if t.requires_grad and r <= ONEHOT_MAX_TABLE and acc + r <= ONEHOT_MAX_TOTAL:
+                    base.append(acc)
+                    rows.append(r)
+                    acc += r
+                else:
+                    base.append(-1)
+                    rows.append(0)
+            if acc:
+                r_pad = ldp(acc)
+                oh = torch.empty(N, r_pad, dtype=torch.bfloat16, device=out.device)
+                a_base = (ctypes.c_int32 * n)(*base)
+                call("gt_onehot", N, n, a_idx, a_str, a_clp, a_base, r_pad, ptr(oh))
+                ctx.onehot = (oh, base, rows, acc, r_pad)
         return out
 
     @staticmethod
@@ -486,13 +526,28 @@ class _EmbedSumFn(torch.autograd.Function):
         g = g.contiguous()
         n = len(idx)
         targets = [_grad_target(t) for t in ctx.tables]
-        a_idx = (ctypes.c_void_p * n)(*[t.data_ptr() for t in idx])
-        a_str = (ctypes.c_int64 * n)(*strides)
-        a_clp = (ctypes.c_int64 * n)(*clamps)
-        a_tab = (ctypes.c_void_p * n)(*[t[0].data_ptr() for t in targets])
         side_ok = all(_main_grad(t) is not None for t in ctx.tables)   # leaf-only gradients: off the critical path
         with _WgradCtx(side_ok, g):
-            call("gt_embed_sum_bwd", dt_of(g), ptr(g), N, d, ld, n, a_idx, a_str, a_clp, a_tab)
+            rest = list(range(n))
+            if ctx.onehot is not None:
+                oh, base, rows, R, r_pad = ctx.onehot
+                ldt = ldp(d)
+                temp = zeros_small(R * ldt, torch.float32, g.device)
+                # temp[R, d] += OneHot^T [R x N] . g [N x d]  (both operands MN-major, split-K over the nodes)
+                _gemm_raw(GT_BF16, oh.data_ptr(), 1, r_pad, g.data_ptr(), 1, ld, temp.data_ptr(), ldt, R, d, N, d, None,
+                          None, 0, EPI_ACCUM | EPI_OUT_F32)
+                a_base = (ctypes.c_int32 * n)(*base)
+                a_rows = (ctypes.c_int32 * n)(*rows)
+                a_tab = (ctypes.c_void_p * n)(*[t[0].data_ptr() for t in targets])
+                call("gt_embed_unpack", ptr(temp), ldt, d, R, n, a_base, a_rows, a_tab)
+                rest = [c for c in range(n) if base[c] < 0]
+            if rest:
+                m = len(rest)
+                a_idx = (ctypes.c_void_p * m)(*[idx[c].data_ptr() for c in rest])
+                a_str = (ctypes.c_int64 * m)(*[strides[c] for c in rest])
+                a_clp = (ctypes.c_int64 * m)(*[clamps[c] for c in rest])
+                a_tab = (ctypes.c_void_p * m)(*[targets[c][0].data_ptr() for c in rest])
+                call("gt_embed_sum_bwd", dt_of(g), ptr(g), N, d, ld, m, a_idx, a_str, a_clp, a_tab)
             for t in ctx.tables:
                 _grad_done(t)
         return (None, *[t[1] for t in targets])

@@ -90,6 +90,15 @@ int gt_embed_sum_bwd(int dt, const void* dout, int64_t N, int32_t d, int32_t ld,
                      const int64_t* const* idx_host, const int64_t* stride_host,
                      const int64_t* clamp_host, float* const* dtable_host, void* stream);
 
+/* Embedding gradients of small tables as a contraction (backward of dataset/utils.py:28-30 / ogb AtomEncoder):
+ * gt_onehot writes the bf16 one-hot operand [N, r_pad] (1 at base_c + min(idx_c[i], clamp_c) for every column with
+ * base_c >= 0); d_tables = OneHot^T . dout is then one gt_gemm (a_mn = b_mn = 1, GT_EPI_ACCUM | GT_EPI_OUT_F32) into
+ * an fp32 [R, ld_t] buffer that gt_embed_unpack adds to the per-table gradients (rows [base_c, base_c + rows_c)). */
+int gt_onehot(int64_t N, int32_t ncol, const int64_t* const* idx_host, const int64_t* stride_host,
+              const int64_t* clamp_host, const int32_t* base_host, int32_t r_pad, void* out, void* stream);
+int gt_embed_unpack(const float* temp, int32_t ld_t, int32_t d, int32_t R, int32_t ncol, const int32_t* base_host,
+                    const int32_t* rows_host, float* const* dtable_host, void* stream);
+
 /* ---- stage 1: message-passing aggregation (reference modules/conv.py:26-33, 50-68) ---------
  * GCN: out[i] = sum_{e:(j->i)} rsqrt(deg_j) rsqrt(deg_i) relu(x[j]+ee_e) + relu(x[i]+root)/deg_i,
  *      deg = out-degree + 1 (conv.py:57);   GIN: out[i] = (1+eps) x[i] + sum relu(x[j]+ee_e).

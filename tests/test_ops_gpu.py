@@ -453,3 +453,46 @@ def test_aggregate_table_gradient_split_kernel(conv, dtype, d):
     else:
         ref_dx += gd * ((xd + sp.detach().double()) > 0) / deg[:, None]
     assert (dx[:, :d].double() - ref_dx).norm() / ref_dx.norm() < (1e-5 if dtype == torch.float32 else 2e-2)
+
+
+@pytest.mark.parametrize("dtype,N", [(torch.bfloat16, 5000), (torch.bfloat16, 300), (torch.float32, 5000)])
+def test_embed_sum_gradient_onehot_contraction(dtype, N):
+    """embedding-sum backward: small tables go through gt_onehot + gt_gemm + gt_embed_unpack in bf16 mode (N >= 2048),
+    a big table (Code2 attribute vocabulary) and every other case through the atomics kernel; all against index_add_ in
+    fp64, bit-for-bit integer semantics (clamped indices, strided index columns)"""
+    torch.manual_seed(5)
+    d = 300
+    dims = [119, 4, 12, 3000, 21]
+    clamps = [118, 3, 11, 2999, 20]
+    xi = torch.stack([torch.randint(0, v + (5 if i == 4 else 0), (N,)) for i, v in enumerate(dims)], 1).cuda()  # col 4 exceeds its clamp
+    tabs = [torch.randn(v, d, device="cuda", requires_grad=True) for v in dims]
+    out = ops.embed_sum([xi[:, c] for c in range(len(dims))], tabs, clamps=clamps, dtype=dtype)
+    ref = sum(t.detach().double()[xi[:, c].clamp(max=clamps[c])] for c, t in enumerate(tabs))
+    assert rel_l2(out[:, :d].double(), ref) < (1e-6 if dtype == torch.float32 else 1e-2)
+    ld = out.shape[1]
+    g = torch.zeros(N, ld, device="cuda")
+    g[:, :d] = torch.randn(N, d, device="cuda")
+    g = g.to(dtype)
+    grads = torch.autograd.grad(out, tabs, g)
+    for c, (t, gt_) in enumerate(zip(tabs, grads)):
+        r = torch.zeros(dims[c], d, device="cuda", dtype=torch.float64).index_add_(0, xi[:, c].clamp(max=clamps[c]), g[:, :d].double())
+        assert gt_.shape == t.shape
+        assert rel_l2(gt_.double(), r) < 1e-5, (c, rel_l2(gt_.double(), r))
+
+
+def test_segment_sum_sorted_long_and_empty_graphs():
+    """global_add_pool over contiguous graph ranges: block-per-(graph, chunk) kernel with graphs of 0, 1 and 3000 rows"""
+    import types
+    sizes = [3, 0, 3000, 1, 0, 257]
+    off = torch.tensor([0] + list(torch.tensor(sizes).cumsum(0)), dtype=torch.int32, device="cuda")
+    N, ld = int(off[-1]), 304
+    torch.manual_seed(0)
+    for dtype in (torch.float32, torch.bfloat16):
+        x = torch.randn(N, ld, device="cuda").to(dtype)
+        init = torch.randn(len(sizes), ld, device="cuda")
+        plan = types.SimpleNamespace(node_off=off, B=len(sizes))
+        out = ops.segment_sum(x, plan, init=init)
+        ref = init.double().clone()
+        for g in range(len(sizes)):
+            ref[g] += x[int(off[g]):int(off[g + 1])].double().sum(0)
+        assert (out.double() - ref).abs().max() < (1e-3 if dtype == torch.float32 else 1e-3) * max(1.0, float(ref.abs().max()))

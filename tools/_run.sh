@@ -1,5 +1,5 @@
-python tools/mha_bench.py molpcba nci1 > gpurun_out/mha_bench2.log 2>&1
-python -m pytest tests -q -m gpu -x 2>&1 | tail -30 > gpurun_out/t34.log
-python bench.py --no-cpu-baseline > gpurun_out/bench27.log 2>&1
-python bench.py --no-cpu-baseline --config nci1 > gpurun_out/bench27_nci1.log 2>&1
-tail -5 gpurun_out/t34.log
+mkdir -p gpurun_out
+python -m pytest tests -q -m gpu -x 2>&1 | grep -v "^frame" | tail -40 > gpurun_out/s4_tests2.log
+python tools/graph_trace.py molpcba --raw > gpurun_out/s4_trace2_molpcba.log 2>&1
+python tools/graph_trace.py code2 --raw > gpurun_out/s4_trace2_code2.log 2>&1
+tail -4 gpurun_out/s4_tests2.log; head -2 gpurun_out/s4_trace2_molpcba.log; head -2 gpurun_out/s4_trace2_code2.log
