@@ -21,7 +21,11 @@ class GradBuckets:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.params = [p for p in model.parameters() if p.requires_grad]
         dev = self.params[0].device
-        total = sum(p.numel() for p in self.params)
+        # every gradient starts on a 128-byte boundary of the arena: the split-K weight-gradient GEMM accumulates through
+        # TMA bulk reductions / 16-byte vector atomics, which a 4-byte-aligned view (anything laid out after GIN's
+        # one-element eps or a [5002] head bias) would degrade to one scalar atomic per element
+        ALIGN = 32
+        total = sum((p.numel() + ALIGN - 1) // ALIGN * ALIGN for p in self.params)
         # one flat fp32 gradient arena; every p.grad is a view into it (no copies around the allreduce)
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
         # bucket boundaries: parameters() order is forward order, so the LAST bucket completes first
@@ -36,7 +40,7 @@ class GradBuckets:
             p._gt_main_grad = p.grad
             p._gt_uses = getattr(p, "_gt_uses", 1)
             p._gt_grad_ready = self._make_ready(i)
-            off += p.numel()
+            off += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
             cur += p.numel()
             idxs.append(i)
             if cur >= target and len(self.buckets) < n_buckets - 1:

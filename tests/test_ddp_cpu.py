@@ -36,10 +36,12 @@ def _worker(rank, world, port, n_buckets, out):
         model(x).square().sum().backward()
         buckets.finish()
     flat = buckets.flat.clone()
+    grads = torch.cat([p.grad.flatten() for p in buckets.params])      # the (128-byte aligned) views, without the padding
+    aligned = all((p.grad.data_ptr() - buckets.flat.data_ptr()) % 128 == 0 for p in buckets.params)
     gathered = [torch.zeros_like(flat) for _ in range(world)]
     dist.all_gather(gathered, flat)
     if rank == 0:
-        torch.save(dict(flat=flat, same=all(torch.equal(g, gathered[0]) for g in gathered),
+        torch.save(dict(flat=grads, aligned=aligned, same=all(torch.equal(g, gathered[0]) for g in gathered),
                         n_buckets=len(buckets.buckets), views=all(p.grad.data_ptr() >= buckets.flat.data_ptr()
                                                                   for p in buckets.params)), out)
     dist.destroy_process_group()
@@ -50,7 +52,7 @@ def test_bucketed_allreduce_gloo_world2(tmp_path, n_buckets):
     out = str(tmp_path / "r0.pt")
     mp.spawn(_worker, args=(2, _free_port(), n_buckets, out), nprocs=2, join=True)
     res = torch.load(out)
-    assert res["same"] and res["views"] and res["n_buckets"] <= n_buckets
+    assert res["same"] and res["views"] and res["aligned"] and res["n_buckets"] <= n_buckets
     # expected: mean over ranks of the per-rank gradient of the SECOND step
     exp = []
     for rank in range(2):
