@@ -115,6 +115,11 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
+inline int& g_last_map_result() {   // CUresult of the last cuTensorMapEncodeTiled of this thread (error messages)
+    static thread_local int r = 0;
+    return r;
+}
+
 // 2-D bf16 tensor map: dim0 = contiguous extent, dim1 = rows with `ld` elements pitch; 128B swizzle, zero OOB fill
 // swizzle_bytes: 128 or 64 (= box0 * 2)
 static bool make_map(CUtensorMap* map, const void* base, uint64_t dim0, uint64_t dim1, uint64_t ld, uint32_t box0, uint32_t box1,
@@ -125,8 +130,16 @@ static bool make_map(CUtensorMap* map, const void* base, uint64_t dim0, uint64_t
     cuuint64_t gstr[1] = {ld * (f32 ? 4 : 2)};
     cuuint32_t box[2] = {box0, box1};
     cuuint32_t estr[2] = {1, 1};
-    return fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-              swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    g_last_map_result() = (int)fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (g_last_map_result() == (int)CUDA_ERROR_INVALID_CONTEXT) {
+        // driver API on a thread that has made no runtime call yet (the autograd engine's worker thread when the first
+        // backward op of the process builds a tensor map): bind the primary context and retry
+        cudaFree(nullptr);
+        g_last_map_result() = (int)fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    return g_last_map_result() == (int)CUDA_SUCCESS;
 }
 
 

@@ -84,7 +84,8 @@ class _GraphTransBase(BaseModel):
             side = lambda: self._w16.refresh(dev)  # noqa: E731
         enc = self.transformer_encoder
         plan = ops.GraphPlan(batched_data.edge_index, batched_data.batch, getattr(batched_data, "num_graphs", None),
-                             enc.max_input_len, cls=self.pooling == "cls", side_work=side)
+                             enc.max_input_len, cls=self.pooling == "cls", side_work=side,
+                             max_nodes=getattr(batched_data, "max_nodes", None))
         parts = self.gnn_node.forward_parts(batched_data, perturb, plan=plan)
         h_node = self._gnn2transformer(parts)                          # [N, d_model]
         h_graph = enc.forward_packed(h_node, plan)                       # [B, d_model] (pooled rows only)

@@ -359,14 +359,31 @@ def cast_to(x: torch.Tensor, dtype) -> torch.Tensor:
 
 
 # ----------------------------------------------------------------------------- graph plan
+MHA_LOCAL = int(os.environ.get("GT_MHA_LOCAL", "1"))    # 0: always the streamed attention kernels
+
+
+def token_bucket(max_nodes, max_input_len=1000, cls=True):
+    """tokens-per-graph bound rounded up to {32, 64, 96, 128} (coarse, so that CUDA-graph signatures and launch
+    bounds do not change with every batch); None = unknown or some graph exceeds one 128-row tile"""
+    if max_nodes is None:
+        return None
+    t = min(int(max_nodes), int(max_input_len)) + 1     # + <CLS>; kept when there is none so that the bucket is a
+    for b in (32, 64, 96, 128):                         # function of ceil((max_nodes + 1) / 32) alone (graphed._signature)
+        if t <= b:
+            return b
+    return None
+
+
 class GraphPlan:
     """Integer metadata of one batch: both CSRs and the packed-token plan. Built on device by
     gt_csr_build / gt_batch_plan without any host synchronisation (B comes from
     `batch.num_graphs` when present, otherwise one .item() like reference gnn_module.py:195)."""
 
-    def __init__(self, edge_index, batch, num_graphs=None, max_input_len=1000, cls=True, side_work=None):
+    def __init__(self, edge_index, batch, num_graphs=None, max_input_len=1000, cls=True, side_work=None, max_nodes=None):
         """side_work: optional callable launched on the branch stream together with the token plan (the two CSR
         sorts stay on the current stream): the integer prep of a batch is three independent chains."""
+        # max_nodes: optional host-side upper bound of the nodes per graph (collate-time metadata, e.g.
+        # synth.GraphBatch.max_nodes).  When every graph fits one 128-row tile the tile-local attention kernels apply.
         _lib.require_cuda(edge_index, batch)
         dev = batch.device
         N = batch.numel()
@@ -398,6 +415,14 @@ class GraphPlan:
         b = batch.contiguous()
         plan_out = (self.node_off, self.kept, self.tok_off, self.tok2node, self.tok_graph, self.node_graph, self.node2tok,
                     self.cls_rows, self.scalars, self.row_bounds, self.tile_bounds)
+        self.loc_tiles = self.loc_count = None
+        self.loc_max_tiles = 0
+        bucket = token_bucket(max_nodes, self.L, self.cls)
+        if bucket is not None and MHA_LOCAL:
+            self.loc_max_tiles = max(1, min(B, -(-self.n_rows // (129 - bucket))))
+            self.loc_tiles = torch.empty(2 * self.loc_max_tiles, **i32)
+            self.loc_count = torch.empty(1, **i32)
+            plan_out = plan_out + (self.loc_tiles, self.loc_count)
         br = Branch(b, *plan_out)
         with br:    # token plan (+ the caller's side work) next to the CSR sorts
             if side_work is not None:
@@ -407,6 +432,8 @@ class GraphPlan:
                  ptr(self.cls_rows), ptr(self.scalars))
             call("gt_mha_meta", ptr(self.tok_graph), ptr(self.tok_off), self.n_rows, B, ptr(self.row_bounds),
                  ptr(self.tile_bounds))
+            if self.loc_tiles is not None:
+                call("gt_mha_local_tiles", ptr(self.tok_off), B, self.loc_max_tiles, ptr(self.loc_tiles), ptr(self.loc_count))
         call("gt_csr_build", ptr(ei), E, N, ptr(self.rowptr_dst), ptr(self.src_by_dst), ptr(self.eid_by_dst),
              ptr(self.rowptr_src), ptr(self.dst_by_src), ptr(self.eid_by_src), ptr(work))
         br.join()
@@ -644,8 +671,16 @@ class _LinearFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             gx = torch.empty(M, ld_in, dtype=x.dtype, device=x.device)
             # dX[m,k] = sum_n dY[m,n] W[n,k]: B operand = W read "MN-major" (k contiguous)
-            _gemm_raw(dt_of(x), gy.data_ptr(), 0, ld_out, wptr, 1, ldw, gx.data_ptr(), ld_in, M, K, N, ld_in, None,
-                      None, 0, 0)
+            if x.dtype == torch.bfloat16 and N >= 2048 and M * K <= 256 * 512:
+                # a handful of output tiles over a very long contraction (the 5002-class Code2 heads): split-K into a
+                # zeroed fp32 scratch (one CTA would otherwise walk ~80 k-blocks alone), then one cast
+                g32 = zeros_small(M * ld_in, torch.float32, x.device).view(M, ld_in)
+                _gemm_raw(dt_of(x), gy.data_ptr(), 0, ld_out, wptr, 1, ldw, g32.data_ptr(), ld_in, M, K, N, ld_in, None,
+                          None, 0, EPI_ACCUM | EPI_OUT_F32)
+                call("gt_cast_pad", GT_F32, ptr(g32), M, ld_in, ld_in, dt_of(gx), ptr(gx), M, ld_in, ld_in)
+            else:
+                _gemm_raw(dt_of(x), gy.data_ptr(), 0, ld_out, wptr, 1, ldw, gx.data_ptr(), ld_in, M, K, N, ld_in, None,
+                          None, 0, 0)
         weight, bias = ctx.params
         # parameter gradients accumulated in place need no ordering with the rest of the backward: side stream
         side_ok = _main_grad(weight) is not None and (not has_bias or _main_grad(bias) is not None)
@@ -1017,21 +1052,34 @@ class _MHAFn(torch.autograd.Function):
         out = torch.empty(n_rows, d, dtype=qkv.dtype, device=qkv.device)
         lse = torch.empty(nhead * n_rows, dtype=torch.float32, device=qkv.device)
         meta = (getattr(plan, "row_bounds", None), getattr(plan, "tile_bounds", None)) if key_start is None else (None, None)
-        call("gt_mha_fwd", dt_of(qkv), ptr(qkv), ptr(plan.tok_graph), ptr(plan.tok_off), ptr(key_start), ptr(meta[0]),
-             ptr(meta[1]), n_rows,
-             plan.B, nhead, dh, scale, ptr(out), ptr(lse), float(drop_p),
-             ptr(rng_state(qkv.device)) if drop_p else None, salt, impl)
+        # every graph inside one graph-aligned 128-row tile: loop-free tile-local kernels (attn_local.cu)
+        local = (impl == 0 and key_start is None and getattr(plan, "loc_tiles", None) is not None
+                 and qkv.dtype == torch.bfloat16 and dh in (32, 64))
+        if local:
+            call("gt_mha_local_fwd", dt_of(qkv), ptr(qkv), ptr(plan.row_bounds), ptr(plan.loc_tiles), plan.loc_max_tiles,
+                 n_rows, nhead, dh, scale, ptr(out), ptr(lse), float(drop_p),
+                 ptr(rng_state(qkv.device)) if drop_p else None, salt)
+        else:
+            call("gt_mha_fwd", dt_of(qkv), ptr(qkv), ptr(plan.tok_graph), ptr(plan.tok_off), ptr(key_start), ptr(meta[0]),
+                 ptr(meta[1]), n_rows,
+                 plan.B, nhead, dh, scale, ptr(out), ptr(lse), float(drop_p),
+                 ptr(rng_state(qkv.device)) if drop_p else None, salt, impl)
         ctx.save_for_backward(qkv, out, lse)
-        ctx.meta = (plan, nhead, dh, scale, key_start, float(drop_p), salt, impl)
+        ctx.meta = (plan, nhead, dh, scale, key_start, float(drop_p), salt, impl, local)
         return out
 
     @staticmethod
     def backward(ctx, g):
         qkv, out, lse = ctx.saved_tensors
-        plan, nhead, dh, scale, key_start, drop_p, salt, impl = ctx.meta
+        plan, nhead, dh, scale, key_start, drop_p, salt, impl, local = ctx.meta
         g = g.contiguous()
         n_rows = qkv.shape[0]
         dqkv = torch.empty_like(qkv)
+        if local:
+            call("gt_mha_local_bwd", dt_of(qkv), ptr(qkv), ptr(out), ptr(g), ptr(lse), ptr(plan.row_bounds),
+                 ptr(plan.loc_tiles), plan.loc_max_tiles, n_rows, nhead, dh, scale, ptr(dqkv), drop_p,
+                 ptr(rng_state(qkv.device)) if drop_p else None, salt)
+            return dqkv, None, None, None, None, None, None
         delta = torch.empty(nhead * n_rows, dtype=torch.float32, device=qkv.device)
         meta = (getattr(plan, "row_bounds", None), getattr(plan, "tile_bounds", None)) if key_start is None else (None, None)
         call("gt_mha_bwd", dt_of(qkv), ptr(qkv), ptr(out), ptr(g), ptr(lse), ptr(plan.tok_graph), ptr(plan.tok_off),

@@ -74,6 +74,9 @@ def _finish(n, **kw):
     batch = np.repeat(np.arange(B, dtype=np.int64), n)
     kw["batch"] = torch.from_numpy(batch)
     kw["num_graphs"] = B
+    # collate-time metadata (host ints, no device sync needed later): the largest graph decides whether the
+    # tile-local attention kernels apply (every graph within one 128-row tile)
+    kw["max_nodes"] = int(np.max(n)) if B else 0
     return GraphBatch(**kw)
 
 

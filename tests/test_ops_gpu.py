@@ -496,3 +496,50 @@ def test_segment_sum_sorted_long_and_empty_graphs():
         for g in range(len(sizes)):
             ref[g] += x[int(off[g]):int(off[g + 1])].double().sum(0)
         assert (out.double() - ref).abs().max() < (1e-3 if dtype == torch.float32 else 1e-3) * max(1.0, float(ref.abs().max()))
+
+
+def _small_graph_plan(lens, max_nodes):
+    import numpy as np
+    batch = torch.from_numpy(np.repeat(np.arange(len(lens)), lens)).cuda()
+    ei = torch.zeros(2, 0, dtype=torch.long, device="cuda")
+    return ops.GraphPlan(ei, batch, len(lens), 1000, cls=True, max_nodes=max_nodes)
+
+
+@pytest.mark.parametrize("nhead,dh", [(4, 32), (4, 64), (2, 64)])
+@pytest.mark.parametrize("drop_p", [0.0, 0.3])
+@pytest.mark.parametrize("lens", [[5, 60, 1, 33, 127, 2, 64, 64, 17], [26] * 40, [127, 127, 1, 1, 1, 126]])
+def test_mha_tile_local_matches_streamed_kernels(nhead, dh, drop_p, lens):
+    """graph-aligned single-tile attention (gt_mha_local_*) against the streamed tcgen05 kernels and the fp32 CUDA-core
+    kernels on the same packed tokens: forward, lse and all three input gradients, with the shared dropout hash"""
+    torch.manual_seed(11)
+    plan_loc = _small_graph_plan(lens, max(lens))
+    plan_gen = _small_graph_plan(lens, None)
+    assert plan_loc.loc_tiles is not None and plan_gen.loc_tiles is None
+    tiles = plan_loc.loc_tiles.view(-1, 2).cpu()
+    cnt = int(plan_loc.loc_count)
+    tok_off = plan_loc.tok_off.cpu()
+    # tiles partition the token rows at graph boundaries, each within 128 rows
+    assert cnt <= plan_loc.loc_max_tiles and int(tiles[:cnt, 1].sum()) == int(tok_off[-1])
+    assert int(tiles[:cnt, 1].max()) <= 128 and all(int(t) in set(tok_off.tolist()) for t in tiles[:cnt, 0])
+    assert bool((tiles[cnt:] == 0).all())
+    d = nhead * dh
+    n_rows = plan_loc.n_rows
+    qkv = (torch.randn(n_rows, 3 * d, device="cuda") * 0.7).bfloat16().requires_grad_(True)
+    go = torch.randn(n_rows, d, device="cuda").bfloat16()
+    ops.manual_seed(77)
+    ops.begin_step("cuda")
+    res = []
+    for plan, impl in ((plan_loc, None), (plan_gen, None)):
+        ops._salt[0] = 0
+        o = ops._MHAFn.apply(qkv, plan, nhead, None, drop_p, 5 if drop_p else 0, impl)
+        (g,) = torch.autograd.grad(o, qkv, go)
+        res.append((o.float(), g.float()))
+    n_tok = int(tok_off[-1])
+    assert rel_l2(res[0][0][:n_tok], res[1][0][:n_tok]) < 1e-2
+    assert rel_l2(res[0][1][:n_tok], res[1][1][:n_tok]) < 2e-2
+    # and against the exact fp32 CUDA-core kernels
+    q32 = qkv.detach().float().requires_grad_(True)
+    o32 = ops._MHAFn.apply(q32, plan_gen, nhead, None, drop_p, 5 if drop_p else 0, 1)
+    (g32,) = torch.autograd.grad(o32, q32, go.float())
+    assert rel_l2(res[0][0][:n_tok], o32[:n_tok]) < 1.5e-2
+    assert rel_l2(res[0][1][:n_tok], g32[:n_tok]) < 3e-2

@@ -1,5 +1,8 @@
 mkdir -p gpurun_out
-python -m pytest tests -q -m gpu -x 2>&1 | grep -v "^frame" | tail -40 > gpurun_out/s4_tests3.log
-python tools/graph_trace.py molpcba --raw > gpurun_out/s4_trace3_molpcba.log 2>&1
-python tools/graph_trace.py code2 --raw > gpurun_out/s4_trace3_code2.log 2>&1
-tail -2 gpurun_out/s4_tests3.log; head -2 gpurun_out/s4_trace3_molpcba.log; head -2 gpurun_out/s4_trace3_code2.log
+timeout 600 python -m pytest tests -q -m gpu -x 2>&1 | grep -v "^frame" | tail -30 > gpurun_out/s4_tests5.log
+tail -3 gpurun_out/s4_tests5.log
+timeout 120 python tools/graph_trace.py molpcba --raw > gpurun_out/s4_trace5_molpcba.log 2>&1
+timeout 120 python tools/graph_trace.py code2 --raw > gpurun_out/s4_trace5_code2.log 2>&1
+head -2 gpurun_out/s4_trace5_molpcba.log; head -2 gpurun_out/s4_trace5_code2.log
+python bench.py --no-cpu-baseline > gpurun_out/s4_bench5_molpcba.log 2>&1
+tail -c 1500 gpurun_out/s4_bench5_molpcba.log
