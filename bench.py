@@ -224,7 +224,8 @@ def hot_kernel_roofline(args, model, b, hb, ns, step_ms):
     es = 2 if ns.precision == "bf16" else 4
     alg = algorithmic(args, hb, es)
     act = ops.act_dtype()
-    plan = ops.GraphPlan(b.edge_index, b.batch, b.num_graphs, int(args.max_input_len), cls=args.graph_pooling == "cls")
+    plan = ops.GraphPlan(b.edge_index, b.batch, b.num_graphs, int(args.max_input_len), cls=args.graph_pooling == "cls",
+                         max_nodes=getattr(hb, "max_nodes", None))     # same attention path as the model takes
     N, d_g, ld = alg["N"], args.gnn_emb_dim, ops.ldp(args.gnn_emb_dim)
     out = []
     torch.manual_seed(0)
@@ -273,9 +274,14 @@ def hot_kernel_roofline(args, model, b, hb, ns, step_ms):
     ms = _timed(mha)
     fl = alg["mha_fwd_flops"] + alg["mha_bwd_flops"]
     ach = fl / (ms * 1e-3) / 1e12
-    out.append({"kernel": "gt_mha_fwd + gt_mha_bwd (k_mha_tc_fwd, k_mha_tc_bwd<dQ>, k_mha_tc_bwd<dKV>, k_mha_delta)", "bound": "tensor",
+    local = plan.loc_tiles is not None and act == torch.bfloat16
+    mha_name = ("gt_mha_local_fwd + gt_mha_local_bwd (k_mha_loc_fwd, k_mha_loc_bwd: graph-aligned 128-row tiles)" if local else
+                "gt_mha_fwd + gt_mha_bwd (k_mha_tc_fwd, k_mha_tc_bwd<dQ>, k_mha_tc_bwd<dKV>, k_mha_delta)")
+    n_launch = 2 if local else 4
+    out.append({"kernel": mha_name, "bound": "tensor",
                 "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": ach / pk["tensor"],
-                "traffic": traffic.get("mha"), "avg_launch_us": ms / 4 * 1e3, "share_of_step": ms * args.num_encoder_layers / step_ms,
+                "traffic": traffic.get("mha_local" if local else "mha"), "avg_launch_us": ms / n_launch * 1e3,
+                "share_of_step": ms * args.num_encoder_layers / step_ms,
                 "useful_flops_fwd_bwd": fl, "peak_source": pk["source"],
                 "note": "useful (unpadded, block-diagonal) flops only; recompute flops of the backward are not counted"})
     # dense: the largest contraction of the model (fwd + dX + dW)

@@ -622,52 +622,85 @@ __global__ void k_layernorm_bwd(const T* __restrict__ dy, const T* __restrict__ 
     for (int k = 0; k < MAXV; ++k)
 #pragma unroll
         for (int q = 0; q < 4; ++q) ag[k][q] = ab[k][q] = 0.f;
-    for (int64_t row = blockIdx.x * (int64_t)nw + wid; row < M; row += (int64_t)gridDim.x * nw) {
-        const float mean = mean_rstd[2 * row], rstd = mean_rstd[2 * row + 1];
-        float xh[MAXV][4], gy[MAXV][4];
-        float s1 = 0.f, s2 = 0.f;
+    // a warp takes LN_BR consecutive rows per iteration: the loads of all of them are in flight before the first shuffle
+    // reduction (one row at a time is a load -> reduce -> store latency chain; rows per warp, not bytes, set the time)
+    constexpr int R = MAXV == 1 ? 4 : (MAXV == 2 ? 2 : 1);
+    float gmm[MAXV][4];
 #pragma unroll
-        for (int k = 0; k < MAXV; ++k) {
-            const int vi = lane + k * 32;
-            if (vi < nv) {
-                float g[4], t[4], u[4];
-                ld4(gamma + vi * 4, g);
-                ld4(dy + row * d + vi * 4, t);
-                ld4(presum + row * d + vi * 4, u);
+    for (int k = 0; k < MAXV; ++k) {
+        const int vi = lane + k * 32;
+        if (vi < nv) ld4(gamma + vi * 4, gmm[k]);
+    }
+    for (int64_t row0 = (blockIdx.x * (int64_t)nw + wid) * R; row0 < M; row0 += (int64_t)gridDim.x * nw * R) {
+        float xh[R][MAXV][4], gy[R][MAXV][4], mean[R], rstd[R], s1[R], s2[R];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    xh[k][q] = (u[q] - mean) * rstd;
-                    ab[k][q] += t[q];
-                    ag[k][q] = fmaf(t[q], xh[k][q], ag[k][q]);
-                    gy[k][q] = t[q] * g[q];
-                    s1 += gy[k][q];
-                    s2 = fmaf(gy[k][q], xh[k][q], s2);
+        for (int rr = 0; rr < R; ++rr) {
+            const int64_t row = row0 + rr;
+            const bool ok = row < M;
+            mean[rr] = ok ? mean_rstd[2 * row] : 0.f;
+            rstd[rr] = ok ? mean_rstd[2 * row + 1] : 0.f;
+#pragma unroll
+            for (int k = 0; k < MAXV; ++k) {
+                const int vi = lane + k * 32;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) xh[rr][k][q] = gy[rr][k][q] = 0.f;
+                if (ok && vi < nv) {
+                    ld4(dy + row * d + vi * 4, gy[rr][k]);
+                    ld4(presum + row * d + vi * 4, xh[rr][k]);
                 }
             }
         }
-        s1 = warp_sum(s1) / (float)d;
-        s2 = warp_sum(s2) / (float)d;
-        int64_t dst = row;
-        if (out_rows) dst = out_rows[row];
 #pragma unroll
-        for (int k = 0; k < MAXV; ++k) {
-            const int vi = lane + k * 32;
-            if (vi < nv) {
-                float o[4];
+        for (int rr = 0; rr < R; ++rr) {
+            s1[rr] = s2[rr] = 0.f;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) o[q] = rstd * (gy[k][q] - s1 - xh[k][q] * s2);
-                if (dst >= 0) {
-                    st4(dx + dst * d + vi * 4, o);
-                    if (dx_drop) {   // gradient of the dropped operand: same mask as the forward
-                        float ds[4];
-                        drop4(dr, (uint64_t)(row * nv + vi), ds);
+            for (int k = 0; k < MAXV; ++k) {
+                const int vi = lane + k * 32;
+                if (vi < nv && row0 + rr < M) {
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) o[q] *= ds[q];
-                        st4(dx_drop + dst * d + vi * 4, o);
+                    for (int q = 0; q < 4; ++q) {
+                        const float t = gy[rr][k][q];
+                        xh[rr][k][q] = (xh[rr][k][q] - mean[rr]) * rstd[rr];
+                        ab[k][q] += t;
+                        ag[k][q] = fmaf(t, xh[rr][k][q], ag[k][q]);
+                        gy[rr][k][q] = t * gmm[k][q];
+                        s1[rr] += gy[rr][k][q];
+                        s2[rr] = fmaf(gy[rr][k][q], xh[rr][k][q], s2[rr]);
                     }
-                } else if (dst == -1 && dcls) {
+                }
+            }
+        }
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) atomicAdd(dcls + vi * 4 + q, o[q]);
+        for (int rr = 0; rr < R; ++rr) {
+            s1[rr] = warp_sum(s1[rr]) / (float)d;
+            s2[rr] = warp_sum(s2[rr]) / (float)d;
+        }
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) {
+            const int64_t row = row0 + rr;
+            if (row >= M) break;
+            int64_t dst = row;
+            if (out_rows) dst = out_rows[row];
+#pragma unroll
+            for (int k = 0; k < MAXV; ++k) {
+                const int vi = lane + k * 32;
+                if (vi < nv) {
+                    float o[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) o[q] = rstd[rr] * (gy[rr][k][q] - s1[rr] - xh[rr][k][q] * s2[rr]);
+                    if (dst >= 0) {
+                        st4(dx + dst * d + vi * 4, o);
+                        if (dx_drop) {   // gradient of the dropped operand: same mask as the forward
+                            float ds[4];
+                            drop4(dr, (uint64_t)(row * nv + vi), ds);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) o[q] *= ds[q];
+                            st4(dx_drop + dst * d + vi * 4, o);
+                        }
+                    } else if (dst == -1 && dcls) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) atomicAdd(dcls + vi * 4 + q, o[q]);
+                    }
                 }
             }
         }
@@ -1147,9 +1180,11 @@ extern "C" int gt_layernorm_bwd(int dt, const void* dy, const void* presum, cons
     // every block ends with 2*d global atomics for dgamma / dbeta (<= 444 serialised L2 atomics per address); three
     // 8-warp blocks per SM keep a warp at <= ~3 sequential rows (each row is a load -> 2 shuffle reductions -> store
     // latency chain, so rows per warp, not bytes, set the duration at these sizes)
-    const int grid = blocks_for(M, 8, 3 * kNumSMs);   // ~80 registers: three blocks per SM are resident
+    const int br = d <= 128 ? 4 : (d <= 256 ? 2 : 1);                  // rows per warp iteration (kernel's R)
+    const int grid = blocks_for((M + br - 1) / br, 8, 3 * kNumSMs);
     GT_DISPATCH_DT(dt, {
-        if (d <= 256) k_layernorm_bwd<T, 2><<<grid, 256, 2 * d * sizeof(float), ST>>>((const T*)dy, (const T*)presum, mean_rstd, out_rows, M, d, gamma, (T*)dx, dgamma, dbeta, dcls, (T*)dx_drop, drop_p, rng_state, salt);
+        if (d <= 128) k_layernorm_bwd<T, 1><<<grid, 256, 2 * d * sizeof(float), ST>>>((const T*)dy, (const T*)presum, mean_rstd, out_rows, M, d, gamma, (T*)dx, dgamma, dbeta, dcls, (T*)dx_drop, drop_p, rng_state, salt);
+        else if (d <= 256) k_layernorm_bwd<T, 2><<<grid, 256, 2 * d * sizeof(float), ST>>>((const T*)dy, (const T*)presum, mean_rstd, out_rows, M, d, gamma, (T*)dx, dgamma, dbeta, dcls, (T*)dx_drop, drop_p, rng_state, salt);
         else k_layernorm_bwd<T, LN_MAXV><<<grid, 256, 2 * d * sizeof(float), ST>>>((const T*)dy, (const T*)presum, mean_rstd, out_rows, M, d, gamma, (T*)dx, dgamma, dbeta, dcls, (T*)dx_drop, drop_p, rng_state, salt);
     });
     GT_LAUNCH_CHECK("gt_layernorm_bwd");
