@@ -940,7 +940,8 @@ k_cast_multi(const int64_t* __restrict__ desc, int n) {
     const int64_t* dsc = desc + lo * 6;
     const float* src = reinterpret_cast<const float*>(dsc[0]);
     bf16* dst = reinterpret_cast<bf16*>(dsc[1]);
-    const int64_t rows = dsc[2], cols = dsc[3], ld = dsc[4];
+    const bool keep_f32 = dsc[4] < 0;                       // ld < 0: fp32 destination (stacked bias vectors)
+    const int64_t rows = dsc[2], cols = dsc[3], ld = keep_f32 ? -dsc[4] : dsc[4];
     const int64_t base = ((int64_t)blockIdx.x - dsc[5]) * CASTM_PER_BLOCK;
     const int64_t total = rows * ld;
 #pragma unroll
@@ -948,7 +949,9 @@ k_cast_multi(const int64_t* __restrict__ desc, int n) {
         const int64_t i = base + k * 256 + threadIdx.x;
         if (i < total) {
             const int64_t r = i / ld, c = i - r * ld;
-            dst[i] = __float2bfloat16_rn(c < cols ? src[r * cols + c] : 0.f);
+            const float v = c < cols ? src[r * cols + c] : 0.f;
+            if (keep_f32) reinterpret_cast<float*>(dst)[i] = v;
+            else dst[i] = __float2bfloat16_rn(v);
         }
     }
 }

@@ -42,6 +42,11 @@ def loss_fn(args):
     ds = args.dataset
     if ds == "code2":
         def calc_loss(pred_list, batch, m=1.0):
+            st = getattr(pred_list, "stacked", None)
+            if st is not None and batch.y_arr.is_contiguous() and batch.y_arr.shape[1] == len(pred_list):
+                # heads stacked as [B, H, Np]: mean CE over the B * H rows == (1/H) sum_h mean_b CE_h, one launch
+                y, rp, n_cls = st
+                return ops.cross_entropy_mean(y.view(-1, rp), batch.y_arr.view(-1), n_cols=n_cls) / m
             loss = 0
             for i in range(len(pred_list)):
                 if pred_list[i].is_cuda:

@@ -59,6 +59,8 @@ class _GraphTransBase(BaseModel):
             for _ in range(args.max_seq_len):
                 self.graph_pred_linear_list.append(torch.nn.Linear(args.d_model, self.num_tasks))
         self._w16 = ops.W16Registry()
+        if len(self.graph_pred_linear_list) > 1:      # the 5 x 5002-class Code2 heads: one stacked operand
+            self._w16.register_heads(self.graph_pred_linear_list)
         self._w16.register(self)   # bf16 operand copies of every Linear / in_proj weight, refreshed once per step
 
     def _gnn2transformer(self, parts):
@@ -92,6 +94,13 @@ class _GraphTransBase(BaseModel):
         if self.max_seq_len is None:
             w, b = self.graph_pred_linear.weight, self.graph_pred_linear.bias
             return ops.linear(h_graph, w, b, out_f32=True)[:, :self.num_tasks]
+        st = ops.stacked_heads(h_graph, self.graph_pred_linear_list)
+        if st is not None:     # all heads in one contraction; per-head views for the caller, stacked buffer for the loss
+            y, rp = st
+            v = y.view(y.shape[0], len(self.graph_pred_linear_list), rp)
+            preds = ops.PredList(v[:, h, :self.num_tasks] for h in range(v.shape[1]))
+            preds.stacked = (y, rp, self.num_tasks)
+            return preds
         return [ops.linear(h_graph, l.weight, l.bias, out_f32=True)[:, :self.num_tasks]
                 for l in self.graph_pred_linear_list]
 

@@ -58,13 +58,25 @@ def manual_seed(seed: int, device="cuda"):
 # ----------------------------------------------------------------------------- bf16 operand copies of the weights
 class _W16Registry:
     """All registered fp32 master weights get a zero-padded bf16 operand copy ([rows, ldp(cols)]) that ONE kernel
-    (gt_cast_multi) refreshes at the top of every forward, instead of one cast kernel per nn.Linear call."""
+    (gt_cast_multi) refreshes at the top of every forward, instead of one cast kernel per nn.Linear call.
+    `register_heads` additionally STACKS the copies of a list of equally shaped Linear heads (Code2: 5 x [5002, d]) as
+    one [H * ldp(N), ldp(K)] operand (+ one fp32 [H * ldp(N)] bias vector), so that all heads are one contraction."""
 
     def __init__(self):
         self.params, self.copies, self.desc, self.ptrs, self.blocks = [], {}, None, None, 0
+        self.stacks, self.stack_copies, self._stacked_ids = [], {}, set()
+
+    def register_heads(self, linears):
+        linears = list(linears)
+        if len(linears) < 2 or any(l.bias is None or l.weight.shape != linears[0].weight.shape for l in linears):
+            return
+        self.stacks.append([(l.weight, l.bias) for l in linears])
+        self._stacked_ids.update(id(l.weight) for l in linears)
+        self.params = [w for w in self.params if id(w) not in self._stacked_ids]
+        self.desc = None
 
     def register(self, module: torch.nn.Module):
-        seen = {id(p) for p in self.params}
+        seen = {id(p) for p in self.params} | self._stacked_ids
         for m in module.modules():
             cand = []
             if isinstance(m, torch.nn.Linear):
@@ -77,9 +89,12 @@ class _W16Registry:
                     self.params.append(w)
         self.desc = None
 
+    def _all_ptrs(self):
+        return tuple(w.data_ptr() for w in self.params) + tuple(t.data_ptr() for st in self.stacks for wb in st for t in wb)
+
     def _build(self, device):
         recs, blk = [], 0
-        self.copies = {}
+        self.copies, self.stack_copies = {}, {}
         for w in self.params:
             if not w.is_cuda or w.dtype != torch.float32 or not w.is_contiguous():
                 continue
@@ -89,20 +104,37 @@ class _W16Registry:
             self.copies[id(w)] = (c, ld)
             recs.append([w.data_ptr(), c.data_ptr(), rows, cols, ld, blk])
             blk += (rows * ld + 2047) // 2048
+        for st in self.stacks:
+            w0 = st[0][0]
+            if not all(t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() for wb in st for t in wb):
+                continue
+            rows, cols = w0.shape
+            ld, rp = ldp(cols), ldp(rows)
+            wst = torch.zeros(len(st) * rp, ld, dtype=torch.bfloat16, device=w0.device)   # pad rows stay zero
+            bst = torch.zeros(len(st) * rp, dtype=torch.float32, device=w0.device)
+            for h, (w, b) in enumerate(st):
+                recs.append([w.data_ptr(), wst.data_ptr() + h * rp * ld * 2, rows, cols, ld, blk])
+                blk += (rows * ld + 2047) // 2048
+                recs.append([b.data_ptr(), bst.data_ptr() + h * rp * 4, 1, rows, -rp, blk])   # ld < 0: fp32 copy
+                blk += (rp + 2047) // 2048
+            self.stack_copies[id(w0)] = (wst, bst, rp, ld)
         self.blocks = blk
-        self.ptrs = tuple(w.data_ptr() for w in self.params)
+        self.ptrs = self._all_ptrs()
         self.desc = torch.tensor(recs, dtype=torch.int64, device=device) if recs else None
 
     def refresh(self, device):
-        if not self.params:
+        if not self.params and not self.stacks:
             return
-        if self.desc is None or self.ptrs != tuple(w.data_ptr() for w in self.params):
+        if self.desc is None or self.ptrs != self._all_ptrs():
             self._build(device)
         if self.desc is not None:
             call("gt_cast_multi", ptr(self.desc), self.desc.shape[0], self.blocks)
 
     def lookup(self, w):
         return self.copies.get(id(w))
+
+    def stack_lookup(self, w0):
+        return self.stack_copies.get(id(w0))
 
 
 W16Registry = _W16Registry
@@ -707,6 +739,78 @@ def linear(x, weight, bias=None, relu=False, out_f32=False, resid=None, drop_p=0
     return dropout(y, drop_p) if (drop_p and not fused) else y
 
 
+class _StackedHeadsFn(torch.autograd.Function):
+    """All H equally shaped Linear heads as ONE contraction over the stacked bf16 operand copy of the registry:
+    y [M, H * Np] fp32 (Np = ldp(N); head h owns columns [h * Np, h * Np + N), pad columns are zero).  Replaces the
+    per-head loop of reference models/gnn_transformer.py:121-128.  Backward: one split-K dX over the H * Np contraction,
+    per-head dW / db on the weight-gradient stream."""
+
+    @staticmethod
+    def forward(ctx, x, H, *wb):
+        ws, bs = wb[:H], wb[H:]
+        wst, bst, rp, ldw = w16.stack_lookup(ws[0])
+        x = x.contiguous()
+        M, ld_in = x.shape
+        N, K = ws[0].shape
+        y = torch.empty(M, H * rp, dtype=torch.float32, device=x.device)
+        _gemm_raw(dt_of(x), x.data_ptr(), 0, ld_in, wst.data_ptr(), 0, ldw, y.data_ptr(), H * rp, M, H * rp, K, H * rp, bst,
+                  None, 0, EPI_OUT_F32)
+        ctx.save_for_backward(x, wst)
+        ctx.params = (ws, bs)
+        ctx.meta = (H, M, N, K, rp, ld_in, ldw)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, wst = ctx.saved_tensors
+        ws, bs = ctx.params
+        H, M, N, K, rp, ld_in, ldw = ctx.meta
+        gy = gy.contiguous()
+        if gy.dtype != x.dtype:
+            g2 = torch.empty(M, H * rp, dtype=x.dtype, device=x.device)
+            call("gt_cast_pad", dt_of(gy), ptr(gy), M, H * rp, H * rp, dt_of(g2), ptr(g2), M, H * rp, H * rp)
+            gy = g2
+        gx = None
+        if ctx.needs_input_grad[0]:
+            # dX[m, k] = sum over (head, class) of dY W: a single output tile over a 25 k-long contraction -> split-K
+            g32 = zeros_small(M * ld_in, torch.float32, x.device).view(M, ld_in)
+            _gemm_raw(dt_of(x), gy.data_ptr(), 0, H * rp, wst.data_ptr(), 1, ldw, g32.data_ptr(), ld_in, M, K, H * rp, ld_in,
+                      None, None, 0, EPI_ACCUM | EPI_OUT_F32)
+            gx = torch.empty(M, ld_in, dtype=x.dtype, device=x.device)
+            call("gt_cast_pad", GT_F32, ptr(g32), M, ld_in, ld_in, dt_of(gx), ptr(gx), M, ld_in, ld_in)
+        es = gy.element_size()
+        side_ok = all(_main_grad(t) is not None for t in (*ws, *bs))
+        gws, gbs = [], []
+        with _WgradCtx(side_ok, gy, x):
+            for h in range(H):
+                tgt, gw = _grad_target(ws[h])
+                _gemm_raw(dt_of(x), gy.data_ptr() + h * rp * es, 1, H * rp, x.data_ptr(), 1, ld_in, tgt.data_ptr(), K, N, K, M, K,
+                          None, None, 0, EPI_ACCUM | EPI_OUT_F32)
+                _grad_done(ws[h])
+                gws.append(gw)
+                tgt, gb = _grad_target(bs[h])
+                lib_call_colsum(gy, h * rp, M, N, H * rp, tgt)
+                _grad_done(bs[h])
+                gbs.append(gb)
+        return (gx, None, *gws, *gbs)
+
+
+def stacked_heads(x, linears):
+    """-> ([M, H * Np] fp32 logits of all heads, Np) or None when the stacked operand copy is not available (fp32 parity
+    mode, heads not registered with the current step's registry)"""
+    linears = list(linears)
+    if x.dtype != torch.bfloat16 or w16.stack_lookup(linears[0].weight) is None:
+        return None
+    rp = w16.stack_lookup(linears[0].weight)[2]
+    y = _StackedHeadsFn.apply(x, len(linears), *[l.weight for l in linears], *[l.bias for l in linears])
+    return y, rp
+
+
+class PredList(list):
+    """list of per-head logits views that remembers the stacked [M, H * Np] buffer they live in (fused loss)"""
+    stacked = None
+
+
 # ----------------------------------------------------------------------------- aggregation
 class _AggregateFn(torch.autograd.Function):
     @staticmethod
@@ -1235,30 +1339,34 @@ def bce_with_logits_masked_mean(pred, y):
 
 
 class _CEFn(torch.autograd.Function):
-    """mean cross-entropy over rows (reference dataset/code.py:39-45 per head, dataset/tud.py:25-27)"""
+    """mean cross-entropy over rows (reference dataset/code.py:39-45 per head, dataset/tud.py:25-27); n_cols: the first
+    n_cols columns of every row are the classes, the rest is layout padding (its gradient is written as zeros)"""
 
     @staticmethod
-    def forward(ctx, x, target):
+    def forward(ctx, x, target, n_cols):
         if x.dtype != torch.float32 or x.stride(-1) != 1:
             x = x.float().contiguous()
-        rows, cols = x.shape
+        rows, width = x.shape
+        cols = width if n_cols is None else int(n_cols)
         acc = torch.zeros(3, dtype=torch.float32, device=x.device)
         lse = torch.empty(rows, dtype=torch.float32, device=x.device)
         loss = torch.empty((), dtype=torch.float32, device=x.device)
         call("gt_ce_fwd", ptr(x), ptr(target), target.stride(0), rows, cols, x.stride(0), ptr(lse), ptr(acc), ptr(loss))
         ctx.save_for_backward(x, target, lse)
+        ctx.cols = cols
         return loss
 
     @staticmethod
     def backward(ctx, g):
         x, target, lse = ctx.saved_tensors
-        rows, cols = x.shape
-        dx = torch.empty(rows, cols, dtype=torch.float32, device=x.device)
+        rows, width = x.shape
+        dx = torch.empty(rows, width, dtype=torch.float32, device=x.device)
         g = g.contiguous()
-        call("gt_ce_bwd", ptr(x), ptr(target), target.stride(0), rows, cols, x.stride(0), ptr(lse), ptr(g), ptr(dx), cols, cols)
-        return dx, None
+        call("gt_ce_bwd", ptr(x), ptr(target), target.stride(0), rows, ctx.cols, x.stride(0), ptr(lse), ptr(g), ptr(dx), width, width)
+        return dx, None, None
 
 
-def cross_entropy_mean(pred, target):
-    """pred [rows, classes] fp32 (row-strided views are fine), target int64 [rows] (any stride)"""
-    return _CEFn.apply(pred, target)
+def cross_entropy_mean(pred, target, n_cols=None):
+    """pred [rows, classes] fp32 (row-strided views are fine), target int64 [rows] (any stride); n_cols < pred.shape[1]
+    marks trailing padding columns"""
+    return _CEFn.apply(pred, target, n_cols)

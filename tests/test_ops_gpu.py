@@ -543,3 +543,52 @@ def test_mha_tile_local_matches_streamed_kernels(nhead, dh, drop_p, lens):
     (g32,) = torch.autograd.grad(o32, q32, go.float())
     assert rel_l2(res[0][0][:n_tok], o32[:n_tok]) < 1.5e-2
     assert rel_l2(res[0][1][:n_tok], g32[:n_tok]) < 3e-2
+
+
+@pytest.mark.parametrize("H,N,K,M", [(5, 5002, 256, 128), (3, 50, 64, 7)])
+def test_stacked_heads_match_per_head_linears(H, N, K, M):
+    """all prediction heads as one contraction over the stacked operand copy (+ fused CE over the stacked logits) against
+    H separate torch Linears + F.cross_entropy: logits, loss and the gradients of x, every weight and every bias"""
+    import torch.nn.functional as F
+    from graphtrans_b200 import factory
+    torch.manual_seed(2)
+    heads = torch.nn.ModuleList(torch.nn.Linear(K, N) for _ in range(H)).cuda()
+    ops.set_precision("bf16")
+    try:
+        reg = ops.W16Registry()
+        reg.register_heads(heads)
+        reg.register(heads)
+        assert not reg.params                                   # stacked weights are not copied twice
+        ops.begin_step("cuda", registry=reg)
+        x = torch.randn(M, K, device="cuda").bfloat16().requires_grad_(True)
+        y_arr = torch.randint(0, N, (M, H), device="cuda")
+        st = ops.stacked_heads(x, heads)
+        assert st is not None
+        y, rp = st
+        v = y.view(M, H, rp)
+        preds = ops.PredList(v[:, h, :N] for h in range(H))
+        preds.stacked = (y, rp, N)
+        import types
+        args = types.SimpleNamespace(dataset="code2")
+        loss = factory.loss_fn(args)(preds, types.SimpleNamespace(y_arr=y_arr))
+        params = [p for l in heads for p in (l.weight, l.bias)]
+        grads = torch.autograd.grad(loss, [x] + params)
+        ops.join_side_streams()
+        # reference in fp32 on the bf16-rounded operands
+        xr = x.detach().float().requires_grad_(True)
+        ref_loss = 0
+        for h, l in enumerate(heads):
+            wq = l.weight.detach().bfloat16().float().requires_grad_(True)
+            bq = l.bias.detach().clone().requires_grad_(True)
+            lg = xr @ wq.t() + bq
+            assert rel_l2(preds[h].float(), lg.detach()) < 1e-2
+            ref_loss = ref_loss + F.cross_entropy(lg, y_arr[:, h])
+            l._ref = (wq, bq)
+        ref_loss = ref_loss / H
+        assert abs(float(loss) - float(ref_loss)) < 2e-2 * max(1.0, abs(float(ref_loss)))
+        rg = torch.autograd.grad(ref_loss, [xr] + [t for l in heads for t in l._ref])
+        assert float(y.view(M, H, rp)[:, :, N:].abs().max()) == 0.0 if rp > N else True
+        for a, b in zip(grads, rg):
+            assert rel_l2(a.float(), b) < 3e-2, (a.shape, rel_l2(a.float(), b))
+    finally:
+        ops.set_precision("fp32")
