@@ -11,7 +11,7 @@ __device__ __forceinline__ uint64_t att_row_id_tc(int h, int64_t q, int64_t n_ro
 
 namespace tc {
 
-constexpr int ATT_THREADS = 192;          // backward kernels: TMA warp, MMA warp, 4 math warps
+constexpr int ATT_THREADS = 320;          // backward kernels: TMA warp, MMA warp, 8 math warps (2 per TMEM lane group)
 constexpr int ATT_FWD_THREADS = 320;      // forward: TMA warp, MMA warp, 8 softmax warps (2 per TMEM lane group)
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
@@ -44,6 +44,14 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // as two 64-column SWIZZLE_128B blocks of 16 KB
 __device__ __forceinline__ uint32_t p_chunk_off(int r, int c) {
     return (uint32_t)(c >> 6) * 16384u + (uint32_t)r * 128u + ((((uint32_t)(c & 63) >> 3) ^ ((uint32_t)r & 7u)) << 4);
+}
+
+// bit i set <=> lo <= c + i < hi   (validity of the 32 columns [c, c + 32) for a row with the index range [lo, hi))
+__device__ __forceinline__ uint32_t range_mask32(int lo, int hi, int c) {
+    const int a = min(max(lo - c, 0), 32), b = min(max(hi - c, 0), 32);
+    const uint32_t below_b = b >= 32 ? 0xffffffffu : ((1u << b) - 1u);
+    const uint32_t below_a = a >= 32 ? 0xffffffffu : ((1u << a) - 1u);
+    return below_b & ~below_a;
 }
 
 }  // namespace tc

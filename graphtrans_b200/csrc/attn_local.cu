@@ -21,14 +21,6 @@ namespace tc {
 // four-way split accumulators below) buys issue slots that one warp per row leaves idle (IPC 0.26 measured with one).
 constexpr int LOC_THREADS = 320;
 
-// bit i set <=> lo <= c + i < hi   (validity of the 32 key columns [c, c + 32) for a row with key range [lo, hi))
-__device__ __forceinline__ uint32_t range_mask32(int lo, int hi, int c) {
-    const int a = min(max(lo - c, 0), 32), b = min(max(hi - c, 0), 32);
-    const uint32_t below_b = b >= 32 ? 0xffffffffu : ((1u << b) - 1u);
-    const uint32_t below_a = a >= 32 ? 0xffffffffu : ((1u << a) - 1u);
-    return below_b & ~below_a;
-}
-
 struct LocParams {
     const int2* row_bounds;    // [lo, hi) token rows of the graph of every row
     const int2* tiles;         // (first row, rows) of every graph-aligned tile; rows == 0: unused slot

@@ -409,7 +409,7 @@ struct ColMeta {     // DKV mode: per streamed QUERY column
     uint32_t rk[64];
 };
 
-template <int DH, bool DKV>
+template <int DH, bool DKV, bool DROP>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 k_mha_tc_bwd(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant__ CUtensorMap tma_do,
              const __grid_constant__ CUtensorMap tma_qkv64, const __grid_constant__ CUtensorMap tma_do64, const AttnBwdParams p) {
@@ -436,8 +436,8 @@ k_mha_tc_bwd(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant_
         mbar_init(&own_full, 1);
         for (int s = 0; s < STG; ++s) mbar_init(&st_full[s], 1), mbar_init(&st_empty[s], 1);
         mbar_init(&sdp_full, 1);
-        mbar_init(&sdp_free, 128);
-        mbar_init(&pds_full, 128);
+        mbar_init(&sdp_free, 256);
+        mbar_init(&pds_full, 256);
         mbar_init(&acc_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_async_smem();
@@ -530,9 +530,14 @@ k_mha_tc_bwd(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant_
                 umma_commit(&acc_done);
             }
         }
-    } else {  // ===== math warps: thread = owned row =====
-        const int qd = warp & 3;
+    } else {  // ===== math warps 2..9: thread = (owned row, 32 of the 64 streamed columns of every tile) =====
+        // Two warps share a TMEM lane group and split the streamed columns: per row the math is a chain of tcgen05.ld ->
+        // MUFU -> FMUL with little ILP, so the second warp per row (8 instead of 4 math warps per CTA, 2 CTAs per SM)
+        // fills issue slots that were idle; masking is branch-free (bit mask of the row's index range), dropout is a
+        // template flag.
+        const int qd = warp & 3, half = (warp - 2) >> 2;
         const int r = qd * 32 + lane;
+        const int c = half * 32;                  // this warp's columns of every streamed tile: [c, c + 32)
         const int64_t orow = (int64_t)t0 + r;
         const uint32_t t_lane = tmem + ((uint32_t)(qd * 32) << 16);
         const Drop dr = make_drop(p.rng, p.salt, p.drop_p);
@@ -556,7 +561,8 @@ k_mha_tc_bwd(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant_
         }
         const int wlo = __reduce_min_sync(0xffffffffu, hi > lo ? lo : 0x7fffffff);
         const int whi = __reduce_max_sync(0xffffffffu, hi > lo ? hi : 0);
-        const int tid = threadIdx.x - 64;     // 0..127 among the math warps
+        const int tid = threadIdx.x - 64;     // 0..255 among the math warps
+        const float sl2 = p.scale_log2;
         for (int t = 0; t < nst; ++t) {
             const int c0 = st_lo + t * 64;    // first streamed row of this tile
             if (DKV) {                         // per-column query metadata of this tile
@@ -572,63 +578,50 @@ k_mha_tc_bwd(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant_
                     }
                     cm.lse2[tid] = a, cm.delta[tid] = b, cm.rk[tid] = k;
                 }
-                named_bar_sync(1, 128);
+                named_bar_sync(1, 256);
             }
             mbar_wait(&sdp_full, (uint32_t)t & 1u);
             tc_fence_after();
             if (t > 0) mbar_wait(&acc_done, (uint32_t)(t - 1) & 1u);   // previous dS / P tiles have been consumed
-#pragma unroll 1
-            for (int c = 0; c < 64; c += 32) {
-                const bool last = c == 32;
-                if (c0 + c + 32 <= wlo || c0 + c >= whi) {   // fully masked for this warp (warp-uniform): dS = P = 0
+            const int s0 = c0 + c;            // streamed index of this warp's first column
+            if (s0 + 32 <= wlo || s0 >= whi) {   // fully masked for this warp (warp-uniform): dS = P = 0
 #pragma unroll
-                    for (int i = 0; i < 32; i += 8) {
-                        const uint32_t off = p_chunk_off(r, c + i);
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(ds_s + off), "r"(0u) : "memory");
-                        if (DKV) asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(pp_s + off), "r"(0u) : "memory");
-                    }
-                    if (last) {
-                        tc_fence_before();
-                        mbar_arrive(&sdp_free);
-                    }
-                    continue;
+                for (int i = 0; i < 32; i += 8) {
+                    const uint32_t off = p_chunk_off(r, c + i);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(ds_s + off), "r"(0u) : "memory");
+                    if (DKV) asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(pp_s + off), "r"(0u) : "memory");
                 }
+                tc_fence_before();
+                mbar_arrive(&sdp_free);
+            } else {
                 uint32_t rs[32], rp[32];
                 tmem_ld32(t_lane + c, rs);
                 tmem_ld32(t_lane + 64 + c, rp);
-                if (last) {
-                    tc_fence_before();
-                    mbar_arrive(&sdp_free);
-                }
+                tc_fence_before();
+                mbar_arrive(&sdp_free);
+                const uint32_t vm = range_mask32(lo, hi, s0);
 #pragma unroll
                 for (int i0 = 0; i0 < 32; i0 += 8) {
                     float pv[8], dsv[8];
-                    const int s0 = c0 + c + i0;          // streamed index of the first element of this group
-                    const bool all_in = s0 >= lo && s0 + 8 <= hi;
-                    if (!all_in && (s0 + 8 <= lo || s0 >= hi)) {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) pv[i] = dsv[i] = 0.f;
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int sidx = s0 + i;
-                            const bool valid = all_in || (sidx >= lo && sidx < hi);
-                            const float l2 = DKV ? cmeta[t & 1].lse2[c + i0 + i] : lse2;
-                            const float de = DKV ? cmeta[t & 1].delta[c + i0 + i] : dl;
-                            float pr = valid ? ex2_approx(fmaf(__uint_as_float(rs[i0 + i]), p.scale_log2, -l2)) : 0.f;
-                            float dp = __uint_as_float(rp[i0 + i]);
-                            if (dr.on) {
-                                // mask element (query, key): dQ mode query = owned row, key = streamed; dKV the reverse
-                                const float mk = DKV ? drop_elem(dr, cmeta[t & 1].rk[c + i0 + i], (uint32_t)orow)
-                                                     : drop_elem(dr, rk, (uint32_t)sidx);
-                                dp *= mk;
-                                dsv[i] = pr * (dp - de);
-                                pr *= mk;
-                            } else {
-                                dsv[i] = pr * (dp - de);
-                            }
-                            pv[i] = pr;
+                    for (int i = 0; i < 8; ++i) {
+                        const float l2 = DKV ? cmeta[t & 1].lse2[c + i0 + i] : lse2;
+                        const float de = DKV ? cmeta[t & 1].delta[c + i0 + i] : dl;
+                        // every column's exponential is formed (an overflow on a masked column is discarded by the select)
+                        float pr = ex2_approx(fmaf(__uint_as_float(rs[i0 + i]), sl2, -l2));
+                        pr = (vm & (1u << (i0 + i))) ? pr : 0.f;
+                        float dp = __uint_as_float(rp[i0 + i]);
+                        if (DROP) {
+                            // mask element (query, key): dQ mode query = owned row, key = streamed; dKV the reverse
+                            const float mk = DKV ? drop_elem(dr, cmeta[t & 1].rk[c + i0 + i], (uint32_t)orow)
+                                                 : drop_elem(dr, rk, (uint32_t)(s0 + i0 + i));
+                            dp *= mk;
+                            dsv[i] = pr * (dp - de);
+                            pr *= mk;
+                        } else {
+                            dsv[i] = pr * (dp - de);
                         }
+                        pv[i] = pr;
                     }
                     const uint32_t off = p_chunk_off(r, c + i0);
                     __nv_bfloat162 h0 = __floats2bfloat162_rn(dsv[0], dsv[1]), h1 = __floats2bfloat162_rn(dsv[2], dsv[3]);
@@ -648,33 +641,40 @@ k_mha_tc_bwd(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant_
             fence_async_smem();
             mbar_arrive(&pds_full);
         }
-        // epilogue: the accumulators' TMEM lanes are the owned rows
+        // epilogue: the accumulators' TMEM lanes are the owned rows; the two warps of a lane group split the columns
         if (nst > 0) {
             mbar_wait(&acc_done, (uint32_t)(nst - 1) & 1u);
             tc_fence_after();
         }
         bf16* gp = (bf16*)p.dqkv + orow * (int64_t)(3 * p.d);
+        constexpr int OC = DH / 2;
 #pragma unroll
         for (int a = 0; a < (DKV ? 2 : 1); ++a) {
-            const int col = !DKV ? colQ : (a == 0 ? colK : colV);
+            const int col = (!DKV ? colQ : (a == 0 ? colK : colV)) + half * OC;
             const float mul = (DKV && a == 1) ? 1.f : p.scale;
+            uint32_t rr[32];
+            if (nst > 0) {
+                if (OC == 32) {
+                    tmem_ld32(t_lane + 128 + a * 64 + half * OC, rr);
+                } else {
+                    uint32_t r16[16];
+                    tmem_ld16(t_lane + 128 + a * 64 + half * OC, r16);
 #pragma unroll
-            for (int c = 0; c < DH; c += 32) {
-                uint32_t rr[32];
-                if (nst > 0) tmem_ld32(t_lane + 128 + a * 64 + c, rr);
-                if (orow < p.n_rows) {
+                    for (int i = 0; i < 16; ++i) rr[i] = r16[i];
+                }
+            }
+            if (orow < p.n_rows) {
 #pragma unroll
-                    for (int i = 0; i < 32; i += 8) {
-                        float v[8];
+                for (int i = 0; i < OC; i += 8) {
+                    float v[8];
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) v[e] = nst > 0 ? __uint_as_float(rr[i + e]) * mul : 0.f;
-                        uint4 pk;
-                        __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
-                        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
-                        pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
-                        pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                        *reinterpret_cast<uint4*>(gp + col + c + i) = pk;
-                    }
+                    for (int e = 0; e < 8; ++e) v[e] = nst > 0 ? __uint_as_float(rr[i + e]) * mul : 0.f;
+                    uint4 pk;
+                    __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+                    __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
+                    pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                    pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                    *reinterpret_cast<uint4*>(gp + col + i) = pk;
                 }
             }
         }
@@ -687,19 +687,24 @@ k_mha_tc_bwd(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant_
     }
 }
 
-template <int DH, bool DKV>
-static cudaError_t launch_bwd(const CUtensorMap& mq, const CUtensorMap& md, const CUtensorMap& mq64, const CUtensorMap& md64,
-                              const AttnBwdParams& p, cudaStream_t st) {
+template <int DH, bool DKV, bool DROP>
+static cudaError_t launch_bwd2(const CUtensorMap& mq, const CUtensorMap& md, const CUtensorMap& mq64, const CUtensorMap& md64,
+                               const AttnBwdParams& p, cudaStream_t st) {
     constexpr int TILE = 128 * DH * 2, STILE = 64 * DH * 2;
     const size_t smem = (size_t)2 * TILE + (size_t)4 * STILE + 16384 * (DKV ? 2 : 1) + 1024;
     static bool attr = false;
     if (!attr) {
-        cudaFuncSetAttribute(k_mha_tc_bwd<DH, DKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_mha_tc_bwd<DH, DKV, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr = true;
     }
     dim3 grid((unsigned)((p.n_rows + 127) / 128), (unsigned)p.nhead);
-    k_mha_tc_bwd<DH, DKV><<<grid, ATT_THREADS, smem, st>>>(mq, md, mq64, md64, p);
+    k_mha_tc_bwd<DH, DKV, DROP><<<grid, ATT_THREADS, smem, st>>>(mq, md, mq64, md64, p);
     return cudaGetLastError();
+}
+template <int DH, bool DKV>
+static cudaError_t launch_bwd(const CUtensorMap& mq, const CUtensorMap& md, const CUtensorMap& mq64, const CUtensorMap& md64,
+                              const AttnBwdParams& p, cudaStream_t st) {
+    return p.drop_p > 0.f ? launch_bwd2<DH, DKV, true>(mq, md, mq64, md64, p, st) : launch_bwd2<DH, DKV, false>(mq, md, mq64, md64, p, st);
 }
 
 }  // namespace tc
