@@ -39,7 +39,7 @@ struct AttnParams {
 // accumulator never leaves TMEM until the end, the softmax threads never wait for the P V MMA, and S is released as
 // soon as it sits in registers so that the next Q K^T overlaps the exponentials.  The extra Q K^T costs tensor-core
 // time that is idle anyway (this kernel is bound by the softmax threads, not by the MMAs).
-template <int DH>
+template <int DH, bool DROP>
 __global__ void __launch_bounds__(ATT_FWD_THREADS, 2)
 k_mha_tc_fwd(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p) {
     constexpr int PITCH = DH * 2;                 // bytes per operand row
@@ -179,7 +179,7 @@ k_mha_tc_fwd(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p) {
         const int wlo = __reduce_min_sync(0xffffffffu, hi > lo ? lo : 0x7fffffff);
         const int whi = __reduce_max_sync(0xffffffffu, hi > lo ? hi : 0);
         // ---- phase 1: row maxima
-        float m = -INFINITY;
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
         for (int j = 0; j < nkv; ++j) {
             const int kv0 = kv_lo + j * BKV;
             mbar_wait(&s_full, (uint32_t)j & 1u);
@@ -189,26 +189,23 @@ k_mha_tc_fwd(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p) {
                 if (kv0 + c + 32 <= wlo || kv0 + c >= whi) continue;   // warp-uniform
                 uint32_t rr[32];
                 tmem_ld32(t_lane + c, rr);
-                const int k0 = kv0 + c;
-                if (k0 >= lo && k0 + 32 <= hi) {                        // whole group valid for this row
+                const uint32_t vm = range_mask32(lo, hi, kv0 + c);     // branch-free: predicated maxima, 4 chains
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(rr[i]));
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (k0 + i >= lo && k0 + i < hi) m = fmaxf(m, __uint_as_float(rr[i]));
-                }
+                for (int i = 0; i < 32; ++i)
+                    if (vm & (1u << i)) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(rr[i]));
             }
             tc_fence_before();
             mbar_arrive(&s_free);
         }
+        float m = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
         xchg[half][r] = m;
         named_bar_sync(1, 256);
         m = fmaxf(xchg[0][r], xchg[1][r]);
         const float m_use = (m == -INFINITY) ? 0.f : m * p.scale_log2;
         named_bar_sync(1, 256);                     // xchg is reused for the row sums
         // ---- phase 2: probabilities with the final maximum; O accumulates in TMEM
-        float l = 0.f;
+        float ls[4] = {0.f, 0.f, 0.f, 0.f};
+        const float sl2 = p.scale_log2;
         for (int j = 0; j < nkv; ++j) {
             const int kv0 = kv_lo + j * BKV;
             mbar_wait(&s_full, (uint32_t)(nkv + j) & 1u);
@@ -233,31 +230,19 @@ k_mha_tc_fwd(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p) {
                     tc_fence_before();
                     mbar_arrive(&s_free);
                 }
+                const uint32_t vm = range_mask32(lo, hi, kv0 + c);
 #pragma unroll
                 for (int i0 = 0; i0 < 32; i0 += 8) {
                     float pv[8];
-                    const int k0 = kv0 + c + i0;
-                    if (k0 >= lo && k0 + 8 <= hi) {                    // 8 valid keys: no per-element masking
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            float e = ex2_approx(fmaf(__uint_as_float(rr[i0 + i]), p.scale_log2, -m_use));
-                            l += e;
-                            if (dr.on) e *= drop_elem(dr, rk, (uint32_t)(k0 + i));
-                            pv[i] = e;
-                        }
-                    } else if (k0 + 8 <= lo || k0 >= hi) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) pv[i] = 0.f;
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int key = k0 + i;
-                            const bool valid = key >= lo && key < hi;
-                            float e = valid ? ex2_approx(fmaf(__uint_as_float(rr[i0 + i]), p.scale_log2, -m_use)) : 0.f;
-                            l += e;
-                            if (dr.on && valid) e *= drop_elem(dr, rk, (uint32_t)key);
-                            pv[i] = e;
-                        }
+                    for (int i = 0; i < 8; ++i) {
+                        // every column's exponential is formed; masked columns (finite scores of other graphs, possibly
+                        // overflowing to +inf) are discarded by the select
+                        float e = ex2_approx(fmaf(__uint_as_float(rr[i0 + i]), sl2, -m_use));
+                        e = (vm & (1u << (i0 + i))) ? e : 0.f;
+                        ls[i & 3] += e;
+                        if (DROP) e *= drop_elem(dr, rk, (uint32_t)(kv0 + c + i0 + i));
+                        pv[i] = e;
                     }
                     __nv_bfloat162 h0 = __floats2bfloat162_rn(pv[0], pv[1]), h1 = __floats2bfloat162_rn(pv[2], pv[3]);
                     __nv_bfloat162 h2 = __floats2bfloat162_rn(pv[4], pv[5]), h3 = __floats2bfloat162_rn(pv[6], pv[7]);
@@ -269,6 +254,7 @@ k_mha_tc_fwd(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p) {
             fence_async_smem();      // generic-proxy smem writes -> visible to the tensor core (async proxy)
             mbar_arrive(&p_full);
         }
+        float l = (ls[0] + ls[1]) + (ls[2] + ls[3]);
         xchg[half][r] = l;
         named_bar_sync(1, 256);
         l = xchg[0][r] + xchg[1][r];
@@ -317,19 +303,23 @@ k_mha_tc_fwd(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p) {
     }
 }
 
-template <int DH>
-static cudaError_t launch_fwd(const CUtensorMap& map, const AttnParams& p, cudaStream_t st) {
+template <int DH, bool DROP>
+static cudaError_t launch_fwd2(const CUtensorMap& map, const AttnParams& p, cudaStream_t st) {
     constexpr int TILE = 128 * DH * 2;
     constexpr int KST = 2, VST = (DH == 64 ? 1 : 2);
     const size_t smem = (size_t)(1 + KST + VST) * TILE + 32768 + 1024;
     static bool attr = false;
     if (!attr) {
-        cudaFuncSetAttribute(k_mha_tc_fwd<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_mha_tc_fwd<DH, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr = true;
     }
     dim3 grid((unsigned)((p.n_rows + BQ - 1) / BQ), (unsigned)p.nhead);
-    k_mha_tc_fwd<DH><<<grid, ATT_FWD_THREADS, smem, st>>>(map, p);
+    k_mha_tc_fwd<DH, DROP><<<grid, ATT_FWD_THREADS, smem, st>>>(map, p);
     return cudaGetLastError();
+}
+template <int DH>
+static cudaError_t launch_fwd(const CUtensorMap& map, const AttnParams& p, cudaStream_t st) {
+    return p.drop_p > 0.f ? launch_fwd2<DH, true>(map, p, st) : launch_fwd2<DH, false>(map, p, st);
 }
 
 
