@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-optimizer", action="store_true", help="skip the second figure (step + fused AdamW update)")
     ap.add_argument("--distinct-batches", type=int, default=4)
     ap.add_argument("--no-wgrad-stream", action="store_true", help="keep weight gradients on the main stream")
     ap.add_argument("--no-branch-stream", action="store_true", help="keep the virtual-node branch on the main stream")
@@ -422,6 +423,32 @@ def main_b200(ns):
         roof_all = hot_kernel_roofline(args, model, dev_batches[0], host_batches[0], ns, t_dev / K * 1e3)
         roof = dict(roof_all[0]) if roof_all else None
 
+    # ---- second figure: the same step followed by the fused AdamW update (+ allreduce when N > 1);
+    # measured last because it moves the weights
+    with_opt = None
+    if not ns.no_optimizer and graphed is not None:
+        from graphtrans_b200.optim import FusedAdamW
+        opt = FusedAdamW(buckets, lr=1e-4, weight_decay=1e-5)
+        gstep = GraphedStep(model, lossf, buckets, max_graphs=2 * ns.distinct_batches + 2, optimizer=opt)
+        for i in range(max(3, len(dev_batches))):
+            gstep(dev_batches[i % len(dev_batches)])
+        barrier()
+        evs2 = []
+        for i in range(K):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            loss_t = gstep(dev_batches[i % len(dev_batches)])
+            e1.record()
+            evs2.append((e0, e1))
+        barrier()
+        t2 = torch.tensor([sum(a.elapsed_time(b) for a, b in evs2) * 1e-3], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        with_opt = {"value": B * world * K / float(t2), "unit": UNIT, "ms_per_step": float(t2) / K * 1e3,
+                    "step": "zero_grad+forward+loss+backward" + ("+allreduce" if world > 1 else "") + "+fused AdamW (gt_adamw_multi)",
+                    "finite_loss": bool(torch.isfinite(loss_t).item())}
+
     cpu = None
     if not ns.no_cpu_baseline and rank == 0:
         gps, ms, desc = cpu_reference_run(ns, 3, 1)
@@ -441,7 +468,8 @@ def main_b200(ns):
                        "launch": "eager (Python launches every kernel)" if graphed is None else
                                  "CUDA-graph replay per batch shape signature (captured in warm-up); inputs copied into static buffers inside the timed region",
                        "wall_ms_per_step_incl_flush": wall / K * 1e3},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "roofline_kernels": roof_all,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "with_optimizer": with_opt, "roofline": roof,
+            "roofline_kernels": roof_all,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)

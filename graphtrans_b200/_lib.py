@@ -69,13 +69,14 @@ SIGNATURES = {
     "gt_bce_masked_bwd": [P, P, L, I32, L, L, P, P, P, L, I32, P],
     "gt_ce_fwd": [P, P, L, L, I32, L, P, P, P, P],
     "gt_ce_bwd": [P, P, L, L, I32, L, P, P, P, L, I32, P],
+    "gt_adamw_multi": [P, I32, L, P, P, P, P, P, P],
     "gt_pna_reduce_fwd": [I, P, P, P, L, I32, I32, I32, P, P, F, P, I32, P, P, P],
     "gt_pna_reduce_bwd": [I, P, P, P, L, I32, I32, I32, I32, P, P, F, P, P, P, P, P, P],
 }
 
 # kernels launched per export (everything not listed launches exactly one); cudaMemsetAsync nodes
 # are not counted
-KERNELS_PER_CALL = {"gt_csr_build": 4, "gt_batch_plan": 3, "gt_mha_bwd": 2, "gt_edges_by_type": 3}
+KERNELS_PER_CALL = {"gt_csr_build": 4, "gt_batch_plan": 3, "gt_mha_bwd": 3, "gt_edges_by_type": 3, "gt_adamw_multi": 2}
 
 _lib = None
 launch_count = 0   # C-ABI calls issued

@@ -34,7 +34,9 @@ class GradBuckets:
         lo, cur, idxs = 0, 0, []
         off = 0
         self._bucket_of = {}
+        self.offsets = []          # arena offset (elements) of every parameter's gradient view
         for i, p in enumerate(self.params):
+            self.offsets.append(off)
             p.grad = self.flat[off:off + p.numel()].view_as(p)
             # fused gradient delivery (ops._grad_target): the backward kernels accumulate straight into the arena
             p._gt_main_grad = p.grad

@@ -39,8 +39,12 @@ class _Entry:
 
 
 class GraphedStep:
-    def __init__(self, model, loss_fn, buckets, max_graphs=16, warmup_iters=2):
+    def __init__(self, model, loss_fn, buckets, max_graphs=16, warmup_iters=2, optimizer=None):
+        """optimizer: optional graphtrans_b200.optim.FusedAdamW; on one GPU its step is part of the captured graph, with
+        several ranks it runs after the gradient allreduce (which stays outside the graph)"""
         self.model, self.loss_fn, self.buckets = model, loss_fn, buckets
+        self.optimizer = optimizer
+        self.opt_in_graph = optimizer is not None and getattr(buckets, "world", 1) == 1
         if getattr(buckets, "overlap", False):
             raise ValueError("GraphedStep needs GradBuckets(overlap=False): collectives stay outside the graph")
         self.max_graphs, self.warmup_iters = max_graphs, warmup_iters
@@ -54,6 +58,8 @@ class GraphedStep:
         loss = self.loss_fn(self.model(b), b)
         loss.backward()
         ops.join_side_streams()       # weight gradients / virtual-node branch issued on side streams (ops.enable_*)
+        if self.opt_in_graph:
+            self.optimizer.step()
         return loss.detach()
 
     def _capture(self, batch, sig):
@@ -61,9 +67,15 @@ class GraphedStep:
         ent.static_batch = batch.to(self.device).clone()       # static input buffers of this signature
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream())
+        if self.optimizer is not None:
+            self.optimizer.enabled = False                      # warm-up must not move the weights
         with torch.cuda.stream(side):                           # warm-up off the capture (cudaFuncSetAttribute,
             for _ in range(self.warmup_iters):                  # allocator warm-up, lazy module state)
                 self._eager(ent.static_batch)
+        if self.optimizer is not None:
+            self.optimizer.enabled = True
+            if self.optimizer._desc is None:
+                self.optimizer._build()                          # descriptor table allocated outside the capture
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize(self.device)
         ent.graph = torch.cuda.CUDAGraph()
@@ -94,4 +106,6 @@ class GraphedStep:
         ent.graph.replay()
         self.last_kernels = ent.kernels
         self.buckets.finish()
+        if self.optimizer is not None and not self.opt_in_graph:
+            self.optimizer.step()
         return ent.loss

@@ -294,6 +294,14 @@ int gt_mha_local_bwd(int dt, const void* qkv, const void* out, const void* dout,
                      int32_t dh, float scale, void* dqkv, float drop_p, const uint64_t* rng_state, uint64_t salt,
                      void* stream);
 
+/* ---- fused AdamW (reference main.py:178 optim.AdamW; trainers/base_trainer.py:36 optimizer.step()) ----------
+ * One launch for all parameters.  desc_dev int64 [n][4] = {parameter pointer (fp32), offset of its gradient / moments in
+ * the flat arenas (elements), numel, first block}; a block updates 2048 elements; total_blocks = sum ceil(numel/2048).
+ * hyper_dev fp32 [5] = {lr, beta1, beta2, eps, weight_decay} and step_dev int64 [1] are DEVICE memory (graph replay sees
+ * host updates); the call increments *step_dev first.  p = p (1 - lr wd) - lr/(1-b1^t) m / (sqrt(v)/sqrt(1-b2^t) + eps). */
+int gt_adamw_multi(const int64_t* desc_dev, int32_t n, int64_t total_blocks, const float* grad_flat, float* m_flat,
+                   float* v_flat, const float* hyper_dev, int64_t* step_dev, void* stream);
+
 /* ---- PNA multi-aggregator reduce (reference modules/pna_layer.py:131-167 via
  *      modules/pna/pna_module.py:43-51; aggregators.py:11-34; scalers.py:10-31) ---------------
  * x [N, ld]: layer input viewed as `towers` towers of F channels (d = towers*F <= ld, F % 4 == 0);

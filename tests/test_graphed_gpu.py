@@ -114,3 +114,43 @@ def test_replay_advances_bn_buffers_and_dropout():
         assert torch.isfinite(buckets.flat).all()
     finally:
         ops.set_precision("fp32")
+
+
+def test_fused_adamw_matches_torch_adamw_and_replays():
+    """gt_adamw_multi over the flat arena against torch.optim.AdamW on the same gradients (3 steps, fp32), then as part
+    of a captured step: the weights move on every replay and stay finite"""
+    from graphtrans_b200.optim import FusedAdamW
+    ops.set_precision("fp32")
+    try:
+        args, model, lossf = _setup("molpcba", drop=False)
+        ref = factory.build_model(args).cuda().train()
+        ref.load_state_dict(copy.deepcopy(model.state_dict()))
+        buckets = GradBuckets(model, n_buckets=2, overlap=False)
+        opt = FusedAdamW(buckets, lr=3e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=0.05)
+        topt = torch.optim.AdamW(ref.parameters(), lr=3e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=0.05)
+        b = _batch(args, 16, seed=4).to("cuda")
+        for _ in range(3):
+            buckets.zero_grad()
+            lossf(model(b), b).backward()
+            ops.join_side_streams()
+            # same gradients for both optimizers: copy ours into the reference model
+            for p, q in zip(model.parameters(), ref.parameters()):
+                q.grad = p.grad.detach().clone()
+            opt.step()
+            topt.step()
+        for (k, p), q in zip(model.named_parameters(), ref.parameters()):
+            assert torch.allclose(p, q, rtol=2e-5, atol=2e-6), k
+        assert int(opt.step_count) == 3
+        # inside the captured step
+        step = GraphedStep(model, lossf, buckets, optimizer=opt)
+        w0 = [p.detach().clone() for p in model.parameters()]
+        step(b)
+        assert int(opt.step_count) == 4                     # warm-up iterations of the capture did not step
+        w1 = [p.detach().clone() for p in model.parameters()]
+        step(b)
+        moved = sum(float((a - c).abs().sum()) for a, c in zip(w0, w1))
+        moved2 = sum(float((a - p.detach()).abs().sum()) for a, p in zip(w1, model.parameters()))
+        assert moved > 0 and moved2 > 0 and int(opt.step_count) == 5
+        assert all(torch.isfinite(p).all() for p in model.parameters())
+    finally:
+        ops.set_precision("fp32")
