@@ -627,6 +627,306 @@ k_agg_table_grad(const T* __restrict__ x, const T* __restrict__ dout, int d, int
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// v3: THREAD per (node, 8-channel vector).  blockDim = (ld / 8, nodes per block): the threads of a node read one
+// feature row with consecutive 16-byte loads (a fully coalesced 512-608 byte row), every thread walks the CSR slots of
+// its node itself (the neighbour ids / norms / edge types are the same address for all threads of the node: one
+// broadcast transaction), gathers AGG_U neighbour rows per batch with all loads issued before the first use, and keeps
+// the segmented sum of its 8 channels in registers.  Against the warp-per-(node, 128-channel chunk) kernels above this
+// removes the shuffle traffic and the per-chunk repetition of the index work (4x fewer instructions per channel on
+// the 2-edge-per-node molecule batches, where the per-node overhead dominates) and keeps every lane busy at
+// ld = 304 (three 128-channel chunks left 62 % of the last chunk's lanes idle).
+constexpr int AGG_U = 4;
+
+__device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void ld8(const bf16* p, float (&v)[8]) {
+    const uint4 t = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        v[2 * i] = __uint_as_float(w[i] << 16);
+        v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+}
+__device__ __forceinline__ void st8(float* p, const float (&v)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void st8(bf16* p, const float (&v)[8]) {
+    uint4 t;
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
+    t.x = *reinterpret_cast<uint32_t*>(&h0); t.y = *reinterpret_cast<uint32_t*>(&h1);
+    t.z = *reinterpret_cast<uint32_t*>(&h2); t.w = *reinterpret_cast<uint32_t*>(&h3);
+    *reinterpret_cast<uint4*>(p) = t;
+}
+
+template <int EK, int KD>
+struct EdgeVec {   // edge-encoder parameters of this thread's 8 channels
+    float w[KD][8], b[8];
+    __device__ __forceinline__ void load(const EdgeEnc& en, int c0, int d) {
+        if (EK == GT_EDGE_LINEAR) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const bool ok = c0 + q < d;
+                b[q] = ok ? en.b[c0 + q] : 0.f;
+#pragma unroll
+                for (int k = 0; k < KD; ++k) w[k][q] = (ok && k < en.kdim) ? en.w[(c0 + q) * en.kdim + k] : 0.f;
+            }
+        }
+    }
+    __device__ __forceinline__ void embed(const EdgeEnc& en, const float (&a)[KD], int ty, int c0, int ld, float (&ee)[8]) const {
+        if (EK == GT_EDGE_NONE) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) ee[q] = 0.f;
+        } else if (EK == GT_EDGE_LINEAR) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                float v = b[q];
+#pragma unroll
+                for (int k = 0; k < KD; ++k) v = fmaf(a[k], w[k][q], v);
+                ee[q] = v;
+            }
+        } else {
+            ld8(en.table + (int64_t)ty * ld + c0, ee);
+        }
+    }
+};
+
+// per-slot edge data of slot p (slot order = the CSR being walked)
+template <int CONV, int EK, int KD>
+__device__ __forceinline__ void slot_data(const EdgeEnc& en, const int32_t* __restrict__ nbr, const int32_t* __restrict__ eid_slot,
+                                          const int32_t* __restrict__ rp_src, int p, int owner, float dis_owner, int& other,
+                                          float& nrm, float (&a)[KD], int& ty) {
+    other = nbr[p];
+    nrm = 1.f;
+    ty = 0;
+    if (CONV == GT_CONV_GCN)
+        nrm = en.norm_slot ? en.norm_slot[p] : dis_owner * rsqrtf((float)(rp_src[other + 1] - rp_src[other] + 1));
+    if (EK == GT_EDGE_LINEAR) {
+        const float* ap = en.attr_slot ? en.attr_slot + (int64_t)p * en.kdim : en.attr + (int64_t)eid_slot[p] * en.kdim;
+#pragma unroll
+        for (int k = 0; k < KD; ++k) a[k] = k < en.kdim ? ap[k] : 0.f;
+    } else if (EK == GT_EDGE_TABLE) {
+        ty = en.etype_slot ? en.etype_slot[p] : en.etype[eid_slot[p]];
+    }
+    (void)owner;
+}
+
+// first AGG_U CSR slots of a node (slots [b, e); tail slots repeat a valid slot with weight 0)
+template <int KD>
+struct SlotBatch {
+    int other[AGG_U], ty[AGG_U];
+    float nrm[AGG_U], a[AGG_U][KD];
+};
+template <int CONV, int EK, int KD>
+__device__ __forceinline__ void load_slots(SlotBatch<KD>& sb, const EdgeEnc& en, const int32_t* __restrict__ nbr,
+                                           const int32_t* __restrict__ eid_slot, const int32_t* __restrict__ rp_src, int p0, int e,
+                                           int owner, float dis_owner) {
+#pragma unroll
+    for (int u = 0; u < AGG_U; ++u) {
+        const int p = max(min(p0 + u, e - 1), 0);
+        slot_data<CONV, EK, KD>(en, nbr, eid_slot, rp_src, p, owner, dis_owner, sb.other[u], sb.nrm[u], sb.a[u], sb.ty[u]);
+        if (p0 + u >= e) sb.nrm[u] = 0.f;
+    }
+}
+
+template <typename T, int CONV, int EK, int KD>
+__global__ void __launch_bounds__(256)
+k_agg_fwd3(const T* __restrict__ x, T* __restrict__ out, int N, int d, int ld,
+           const int32_t* __restrict__ rp_dst, const int32_t* __restrict__ src_by_dst,
+           const int32_t* __restrict__ eid_by_dst, const int32_t* __restrict__ rp_src, EdgeEnc en,
+           const float* __restrict__ self_param) {
+    const int c0 = threadIdx.x * 8;
+    EdgeVec<EK, KD> ev;
+    ev.load(en, c0, d);
+    float root[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) root[q] = (CONV == GT_CONV_GCN && c0 + q < d) ? self_param[c0 + q] : 0.f;
+    const float eps1 = (CONV == GT_CONV_GIN) ? 1.f + self_param[0] : 0.f;
+    // Software pipeline over the nodes of a thread (grid-stride): the row pointers are fetched two nodes ahead and the
+    // first AGG_U slots (neighbour id, norm, edge type / attributes) one node ahead, so the only exposed latency per
+    // node is the feature-row gather itself instead of the chain rowptr -> slot -> row.
+    const int stride = gridDim.x * blockDim.y;
+    int i = blockIdx.x * blockDim.y + threadIdx.y;
+    int b0 = 0, e0 = 0, b1 = 0, e1 = 0;
+    if (i < N) b0 = rp_dst[i], e0 = rp_dst[i + 1];
+    if (i + stride < N) b1 = rp_dst[i + stride], e1 = rp_dst[i + stride + 1];
+    SlotBatch<KD> cur;
+    if (i < N) load_slots<CONV, EK, KD>(cur, en, src_by_dst, eid_by_dst, rp_src, b0, e0, i, 1.f);
+    for (; i < N; i += stride) {
+        float xi[8], xv[AGG_U][8];
+        ld8(x + (int64_t)i * ld + c0, xi);
+#pragma unroll
+        for (int u = 0; u < AGG_U; ++u) ld8(x + (int64_t)cur.other[u] * ld + c0, xv[u]);
+        // prefetch for the next two nodes while the gathers are in flight
+        SlotBatch<KD> nxt;
+        const int inext = i + stride;
+        if (inext < N) load_slots<CONV, EK, KD>(nxt, en, src_by_dst, eid_by_dst, rp_src, b1, e1, inext, 1.f);
+        int b2 = 0, e2 = 0;
+        if (inext + stride < N) b2 = rp_dst[inext + stride], e2 = rp_dst[inext + stride + 1];
+        float inv_deg_i = 1.f;
+        if (CONV == GT_CONV_GCN) inv_deg_i = 1.f / (float)(rp_src[i + 1] - rp_src[i] + 1);
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int u = 0; u < AGG_U; ++u) {
+            float ee[8];
+            ev.embed(en, cur.a[u], cur.ty[u], c0, ld, ee);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[q] = fmaf(cur.nrm[u], fmaxf(xv[u][q] + ee[q], 0.f), acc[q]);
+        }
+        for (int p0 = b0 + AGG_U; p0 < e0; p0 += AGG_U) {         // nodes with more than AGG_U in-edges
+            SlotBatch<KD> sb;
+            load_slots<CONV, EK, KD>(sb, en, src_by_dst, eid_by_dst, rp_src, p0, e0, i, 1.f);
+#pragma unroll
+            for (int u = 0; u < AGG_U; ++u) ld8(x + (int64_t)sb.other[u] * ld + c0, xv[u]);
+#pragma unroll
+            for (int u = 0; u < AGG_U; ++u) {
+                float ee[8];
+                ev.embed(en, sb.a[u], sb.ty[u], c0, ld, ee);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) acc[q] = fmaf(sb.nrm[u], fmaxf(xv[u][q] + ee[q], 0.f), acc[q]);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            if (CONV == GT_CONV_GCN) acc[q] = fmaf(fmaxf(xi[q] + root[q], 0.f), inv_deg_i, acc[q]);
+            else acc[q] = fmaf(eps1, xi[q], acc[q]);
+        }
+        st8(out + (int64_t)i * ld + c0, acc);
+        cur = nxt;
+        b0 = b1, e0 = e1, b1 = b2, e1 = e2;
+    }
+}
+
+// adjoint, thread per (source node j, 8-channel vector): dx[j] = sum over out-edges of mask * norm * dout[dst] + self
+// term.  Parameter gradients (GCN root, Linear edge encoder, GIN eps) accumulate in registers over the nodes a thread
+// visits (its channel vector is fixed), meet in shared memory once per block and leave as one global atomic per
+// (block, element).  The edge-TABLE gradient is the separate type-sorted kernel (gt_aggregate_table_grad).
+template <typename T, int CONV, int EK, int KD>
+__global__ void __launch_bounds__(256)
+k_agg_bwd3(const T* __restrict__ x, const T* __restrict__ dout, T* __restrict__ dx, int N, int d, int ld,
+           const int32_t* __restrict__ rp_src, const int32_t* __restrict__ dst_by_src,
+           const int32_t* __restrict__ eid_by_src, EdgeEnc en, const float* __restrict__ self_param,
+           float* __restrict__ d_edge_w, float* __restrict__ d_edge_b, float* __restrict__ d_self) {
+    extern __shared__ float sh_par[];    // [self | b | w0..w(KD-1)][ld], then one eps slot per warp
+    const int c0 = threadIdx.x * 8;
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
+    constexpr bool PAR = CONV == GT_CONV_GCN || EK == GT_EDGE_LINEAR;
+    if (PAR) {
+        for (int i = tid; i < (2 + KD) * ld; i += nthr) sh_par[i] = 0.f;
+        __syncthreads();
+    }
+    EdgeVec<EK, KD> ev;
+    ev.load(en, c0, d);
+    float root[8], a_self[8], a_b[8], a_w[KD][8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        root[q] = (CONV == GT_CONV_GCN && c0 + q < d) ? self_param[c0 + q] : 0.f;
+        a_self[q] = a_b[q] = 0.f;
+#pragma unroll
+        for (int k = 0; k < KD; ++k) a_w[k][q] = 0.f;
+    }
+    const float eps1 = (CONV == GT_CONV_GIN) ? 1.f + self_param[0] : 0.f;
+    float deps = 0.f;
+    // software pipeline as in the forward: row pointers two nodes ahead, the first AGG_U out-edge slots one node ahead
+    const int stride = gridDim.x * blockDim.y;
+    int j = blockIdx.x * blockDim.y + threadIdx.y;
+    int b0 = 0, e0 = 0, b1 = 0, e1 = 0;
+    if (j < N) b0 = rp_src[j], e0 = rp_src[j + 1];
+    if (j + stride < N) b1 = rp_src[j + stride], e1 = rp_src[j + stride + 1];
+    SlotBatch<KD> cur;
+    if (j < N) load_slots<CONV, EK, KD>(cur, en, dst_by_src, eid_by_src, rp_src, b0, e0, j, 1.f);
+    for (; j < N; j += stride) {
+        float xj[8], gj[8], g[AGG_U][8];
+        ld8(x + (int64_t)j * ld + c0, xj);
+        ld8(dout + (int64_t)j * ld + c0, gj);
+#pragma unroll
+        for (int u = 0; u < AGG_U; ++u) ld8(dout + (int64_t)cur.other[u] * ld + c0, g[u]);
+        SlotBatch<KD> nxt;
+        const int jnext = j + stride;
+        if (jnext < N) load_slots<CONV, EK, KD>(nxt, en, dst_by_src, eid_by_src, rp_src, b1, e1, jnext, 1.f);
+        int b2 = 0, e2 = 0;
+        if (jnext + stride < N) b2 = rp_src[jnext + stride], e2 = rp_src[jnext + stride + 1];
+        const float inv_deg_j = CONV == GT_CONV_GCN ? 1.f / (float)(e0 - b0 + 1) : 1.f;
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        auto consume = [&](const SlotBatch<KD>& sb) {
+#pragma unroll
+            for (int u = 0; u < AGG_U; ++u) {
+                float ee[8];
+                ev.embed(en, sb.a[u], sb.ty[u], c0, ld, ee);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float gm = (xj[q] + ee[q] > 0.f) ? sb.nrm[u] * g[u][q] : 0.f;
+                    acc[q] += gm;
+                    if (EK == GT_EDGE_LINEAR) {
+                        a_b[q] += gm;
+#pragma unroll
+                        for (int k = 0; k < KD; ++k) a_w[k][q] = fmaf(sb.a[u][k], gm, a_w[k][q]);
+                    }
+                }
+            }
+        };
+        consume(cur);
+        for (int p0 = b0 + AGG_U; p0 < e0; p0 += AGG_U) {         // nodes with more than AGG_U out-edges
+            SlotBatch<KD> sb;
+            load_slots<CONV, EK, KD>(sb, en, dst_by_src, eid_by_src, rp_src, p0, e0, j, 1.f);
+#pragma unroll
+            for (int u = 0; u < AGG_U; ++u) ld8(dout + (int64_t)sb.other[u] * ld + c0, g[u]);
+            consume(sb);
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            if (CONV == GT_CONV_GCN) {
+                const float gs = (xj[q] + root[q] > 0.f) ? gj[q] * inv_deg_j : 0.f;
+                acc[q] += gs;
+                a_self[q] += gs;
+            } else {
+                acc[q] = fmaf(eps1, gj[q], acc[q]);
+                deps = fmaf(xj[q], gj[q], deps);
+            }
+        }
+        st8(dx + (int64_t)j * ld + c0, acc);
+        cur = nxt;
+        b0 = b1, e0 = e1, b1 = b2, e1 = e2;
+    }
+    if (PAR) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            if (CONV == GT_CONV_GCN) atomicAdd(&sh_par[c0 + q], a_self[q]);
+            if (EK == GT_EDGE_LINEAR) {
+                atomicAdd(&sh_par[ld + c0 + q], a_b[q]);
+#pragma unroll
+                for (int k = 0; k < KD; ++k)
+                    if (k < en.kdim) atomicAdd(&sh_par[(2 + k) * ld + c0 + q], a_w[k][q]);
+            }
+        }
+        __syncthreads();
+        for (int c = tid; c < d; c += nthr) {
+            if (CONV == GT_CONV_GCN) atomicAdd(&d_self[c], sh_par[c]);
+            if (EK == GT_EDGE_LINEAR) {
+                atomicAdd(&d_edge_b[c], sh_par[ld + c]);
+                for (int k = 0; k < en.kdim; ++k) atomicAdd(&d_edge_w[c * en.kdim + k], sh_par[(2 + k) * ld + c]);
+            }
+        }
+    }
+    if (CONV == GT_CONV_GIN) {   // d eps: one global atomic per block
+        float* sh_eps = sh_par + (PAR ? (2 + KD) * ld : 0);
+        deps = warp_sum(deps);
+        const int nw = (nthr + 31) >> 5;
+        if ((tid & 31) == 0) sh_eps[tid >> 5] = deps;
+        __syncthreads();
+        if (tid == 0) {
+            float t = 0.f;
+            for (int w = 0; w < nw; ++w) t += sh_eps[w];
+            if (t != 0.f) atomicAdd(d_self, t);
+        }
+    }
+}
+
 template <typename T, int CONV>
 static int launch_fwd(int ek, const T* x, T* out, int N, int d, int ld, const int32_t* rp_dst,
                       const int32_t* src_by_dst, const int32_t* eid_by_dst, const int32_t* rp_src,
@@ -639,8 +939,19 @@ static int launch_fwd(int ek, const T* x, T* out, int N, int d, int ld, const in
     // (node, 128-channel chunk) items: the global warp count must be a multiple of nch
     const int grid2 = (blocks_for((int64_t)N * nch, AGG_WARPS, kNumSMs * 8) + nch - 1) / nch * nch;
 #define L(EK) k_agg_fwd<T, CONV, EK><<<grid, AGG_WARPS * 32, 0, st>>>(x, out, N, d, ld, rp_dst, src_by_dst, eid_by_dst, rp_src, en, self_param)
-    static const int variant = getenv("GT_AGG_VARIANT") ? atoi(getenv("GT_AGG_VARIANT")) : 0;   // tuning knob: 1 = per-edge kernels
-    if (nch <= 4 && variant != 1) {
+    static const int variant = getenv("GT_AGG_VARIANT") ? atoi(getenv("GT_AGG_VARIANT")) : 0;   // tuning knob: 1 = per-edge kernels, 2 = warp-per-chunk
+    // measured (tools/agg_bench.py): v3 wins with table / no edge encoders (58-64 registers); with the Linear edge encoder
+    // its per-thread weight registers (104-128 per thread) cost too much occupancy and the warp-per-chunk kernel stays
+    const bool slots_ok = CONV != GT_CONV_GCN || en.norm_slot != nullptr;   // v3 reads the GCN norm per slot
+    if (ld % 8 == 0 && ld <= 512 && slots_ok && (variant == 3 || (variant == 0 && ek != GT_EDGE_LINEAR))) {   // v3: thread per (node, 8-channel vector)
+        const dim3 blk((unsigned)(ld / 8), (unsigned)max(1, 256 / (ld / 8)));
+        const int grid3 = blocks_for(N, (int)blk.y, kNumSMs * 3);    // ~one resident wave (74-80 registers); threads pipeline over their nodes
+#define L3K(EK, KD) k_agg_fwd3<T, CONV, EK, KD><<<grid3, blk, 0, st>>>(x, out, N, d, ld, rp_dst, src_by_dst, eid_by_dst, rp_src, en, self_param)
+        if (ek == GT_EDGE_NONE) L3K(GT_EDGE_NONE, 1);
+        else if (ek == GT_EDGE_LINEAR) { if (en.kdim > 2) L3K(GT_EDGE_LINEAR, 4); else L3K(GT_EDGE_LINEAR, 2); }
+        else L3K(GT_EDGE_TABLE, 1);
+#undef L3K
+    } else if (nch <= 4 && variant != 1) {
         if (ek == GT_EDGE_NONE) L2N(GT_EDGE_NONE);
         else if (ek == GT_EDGE_LINEAR) L2N(GT_EDGE_LINEAR);
         else L2N(GT_EDGE_TABLE);
@@ -676,7 +987,19 @@ static int launch_bwd(int ek, const T* x, const T* dout, T* dx, int N, int d, in
     // batched kernel costs too much occupancy (84 vs 53 us on the molpcba batch); the per-edge kernel keeps its
     // 32 KB per-chunk table.  Linear / no edge encoder: the batched kernel wins (62 vs 73 us on the code2 batch).
     // Without the table gradient (d_table == NULL: gt_aggregate_table_grad computes it) the batched kernel is used.
-    if (nch <= 4 && smem2 <= 100 * 1024 && variant != 1 && (!tab_grad || variant == 2)) {
+    const bool slots_ok = CONV != GT_CONV_GCN || en.norm_slot != nullptr;
+    if (ld % 8 == 0 && ld <= 512 && slots_ok && (variant == 3 || (variant == 0 && ek != GT_EDGE_LINEAR)) && !tab_grad) {   // v3
+        const dim3 blk((unsigned)(ld / 8), (unsigned)max(1, 256 / (ld / 8)));
+        // ~one resident wave (threads pipeline over their nodes; every block ends with one global atomic per
+        // parameter-gradient element)
+        const int grid3 = blocks_for(N, (int)blk.y, kNumSMs * 3);
+        const size_t smem3 = sizeof(float) * ((size_t)(2 + MAX_KDIM) * ld + 32);
+#define L3K(EK, KD) k_agg_bwd3<T, CONV, EK, KD><<<grid3, blk, smem3, st>>>(x, dout, dx, N, d, ld, rp_src, dst_by_src, eid_by_src, en, self_param, dw, db, dself)
+        if (ek == GT_EDGE_NONE) L3K(GT_EDGE_NONE, 1);
+        else if (ek == GT_EDGE_LINEAR) { if (en.kdim > 2) L3K(GT_EDGE_LINEAR, 4); else L3K(GT_EDGE_LINEAR, 2); }
+        else L3K(GT_EDGE_TABLE, 1);
+#undef L3K
+    } else if (nch <= 4 && smem2 <= 100 * 1024 && variant != 1 && (!tab_grad || variant == 2)) {
         // every block flushes its private gradient tables once: keep the block count near the resident capacity
         const int cap = kNumSMs * (smem2 > 48 * 1024 ? 2 : 8);
         grid = blocks_for((int64_t)N * nch, AGG_WARPS, cap);
