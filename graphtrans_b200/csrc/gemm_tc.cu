@@ -52,6 +52,7 @@ struct Params {
     int m_tiles, n_tiles, total_tiles;   // work list: tile t -> n = t % n_tiles, m = (t / n_tiles) % m_tiles, split = rest
     uint32_t idesc, tmem_cols, acc_stride;
     unsigned long long* trace;           // debug (GT_GEMM_TRACE=1): clock64 stamps of CTA 0's phases, else NULL
+    double* col_stats;                   // optional [2][ldc]: += column sums / sums of squares of the stored C (BatchNorm)
 };
 
 #define GT_TRACE(slot) do { if (p.trace && blockIdx.x == 0) p.trace[slot] = (unsigned long long)clock64(); } while (0)
@@ -63,9 +64,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUt
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tmem_full_bar[2], tmem_empty_bar[2];
     __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(16) float stat_sm[2][2][128];   // [column-slab parity][slab buffer][64 columns x (sum, sumsq)]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) GT_TRACE(0);
+    for (int i = threadIdx.x; i < 2 * 2 * 128; i += blockDim.x) (&stat_sm[0][0][0])[i] = 0.f;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     // B tile: K-major = BN rows of 128 B; MN-major = ceil(BN/64) TMA boxes of [64 k-rows x 64 columns] (8 KB each)
     const int b_boxes = (p.BN + 63) / 64;
@@ -257,6 +260,44 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUt
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
+                    if (OUT_BF16 && p.col_stats) {
+                        // BatchNorm statistics of the tile while it sits in shared memory: lane = 2 adjacent columns of
+                        // the [32 rows x 64 columns] bf16 slab (one conflict-free 128-byte row per shared load), fp32
+                        // partials over the 32 rows; the four lane-group warps of a slab (128 rows) meet in shared
+                        // memory and ONE warp issues the fp64 atomics (one per (tile, column) instead of four: the
+                        // L2 atomics on ~1200 addresses are what this costs) - replaces the separate gt_colstats
+                        // pass over C.  Rows beyond M hold bias-only garbage and are skipped.
+                        const int rows_valid = min(32, p.M - (m0 + q * 32));        // warp-uniform
+                        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+                        for (int rr = 0; rr < rows_valid; ++rr) {
+                            uint32_t u;
+                            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u) : "r"(sb + (uint32_t)rr * 128u + ((((uint32_t)lane >> 2) ^ ((uint32_t)rr & 7u)) << 4) + ((uint32_t)lane & 3u) * 4u));
+                            const float lo = __uint_as_float(u << 16), hi = __uint_as_float(u & 0xffff0000u);
+                            s0 += lo; q0 = fmaf(lo, lo, q0);
+                            s1 += hi; q1 = fmaf(hi, hi, q1);
+                        }
+                        float* sm = &stat_sm[sub][slab_i & 1][0];
+                        if (rows_valid > 0) {
+                            atomicAdd(sm + 4 * lane, s0);
+                            atomicAdd(sm + 4 * lane + 1, q0);
+                            atomicAdd(sm + 4 * lane + 2, s1);
+                            atomicAdd(sm + 4 * lane + 3, q1);
+                        }
+                        asm volatile("bar.sync %0, 128;" ::"r"(2 + sub) : "memory");   // the 4 warps of this column-slab parity
+                        if (q == 0) {
+                            const float4 t = *reinterpret_cast<const float4*>(sm + 4 * lane);
+                            *reinterpret_cast<float4*>(sm + 4 * lane) = make_float4(0.f, 0.f, 0.f, 0.f);
+                            const int col = n_slab + 2 * lane;
+                            if (col < p.N) {
+                                atomicAdd(p.col_stats + col, (double)t.x);
+                                atomicAdd(p.col_stats + p.ldc + col, (double)t.y);
+                                if (col + 1 < p.N) {
+                                    atomicAdd(p.col_stats + col + 1, (double)t.z);
+                                    atomicAdd(p.col_stats + p.ldc + col + 1, (double)t.w);
+                                }
+                            }
+                        }
+                    }
                     if (lane == 0) {
                         if (accum) tma_reduce_add_2d(&tma_c, sb, n_slab, m0 + q * 32);
                         else tma_store_2d(&tma_c, sb, n_slab, m0 + q * 32);
@@ -403,11 +444,11 @@ static cudaError_t launch(const CUtensorMap& ma, const CUtensorMap& mb, const CU
                           bool out_bf16, cudaStream_t st) {
     if (out_bf16) {
         static bool attr = false;
-        if (!attr) { cudaFuncSetAttribute(k_gemm_tc<A_MN, B_MN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); attr = true; }
+        if (!attr) { cudaFuncSetAttribute(k_gemm_tc<A_MN, B_MN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 223 * 1024); attr = true; }
         k_gemm_tc<A_MN, B_MN, true><<<grid, THREADS, smem, st>>>(ma, mb, mc, p);
     } else {
         static bool attr = false;
-        if (!attr) { cudaFuncSetAttribute(k_gemm_tc<A_MN, B_MN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); attr = true; }
+        if (!attr) { cudaFuncSetAttribute(k_gemm_tc<A_MN, B_MN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 223 * 1024); attr = true; }
         k_gemm_tc<A_MN, B_MN, false><<<grid, THREADS, smem, st>>>(ma, mb, mc, p);
     }
     return cudaGetLastError();
@@ -420,7 +461,8 @@ static unsigned long long* g_trace_buf = nullptr;
 // returns 0 ok, -2 = shape/layout/dtype not eligible (caller falls back to the CUDA-core kernel), >0 CUDA error
 int gemm_tc_launch(int dt, const void* A, int a_mn, int64_t lda, const void* B, int b_mn, int64_t ldb, void* C, int64_t ldc,
                    int64_t M, int64_t N, int64_t K, int64_t n_fill, const float* bias, const void* resid, int64_t ldr, int flags,
-                   float drop_p, const uint64_t* rng, uint64_t salt, cudaStream_t st) {
+                   float drop_p, const uint64_t* rng, uint64_t salt, double* col_stats, int* stats_fused, cudaStream_t st) {
+    if (stats_fused) *stats_fused = 0;
     using namespace tc;
     if (dt != GT_BF16) { set_error("tcgen05 GEMM takes bf16 operands"); return -2; }
     if (((uintptr_t)A | (uintptr_t)B) & 15 || lda % 8 || ldb % 8) { set_error("operands need 16-byte aligned rows"); return -2; }
@@ -463,7 +505,7 @@ int gemm_tc_launch(int dt, const void* A, int a_mn, int64_t lda, const void* B, 
     dim3 grid((unsigned)(total < kNumSMs ? total : kNumSMs), 1, 1);   // persistent: one CTA per SM
     p.BN = BN;
     const size_t stage_bytes = A_TILE_BYTES + (b_mn ? (size_t)((BN + 63) / 64) * 8192 : (size_t)BN * BK * 2);
-    p.stages = (int)((226 * 1024 - 1024 - STG_BYTES) / stage_bytes);   // ring + epilogue staging + alignment slack
+    p.stages = (int)((223 * 1024 - 1024 - STG_BYTES) / stage_bytes);   // ring + epilogue staging + alignment slack
     if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
     const size_t smem = p.stages * stage_bytes + STG_BYTES + 1024;
     p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
@@ -488,6 +530,9 @@ int gemm_tc_launch(int dt, const void* A, int a_mn, int64_t lda, const void* B, 
     static const bool trace_on = getenv("GT_GEMM_TRACE") != nullptr;
     if (trace_on && !trace_buf) { cudaMalloc(&trace_buf, 16 * sizeof(unsigned long long)); g_trace_buf = trace_buf; }
     p.trace = trace_on ? trace_buf : nullptr;
+    // column statistics ride in the TMA-store epilogue of a bf16, non-accumulating output
+    p.col_stats = (col_stats && p.tma_store && out_bf16 && !accum) ? col_stats : nullptr;
+    if (stats_fused) *stats_fused = p.col_stats != nullptr;
 
     cudaError_t e;
     if (a_mn && b_mn) e = launch<true, true>(ma, mb, mc, p, grid, smem, out_bf16, st);

@@ -79,9 +79,11 @@ class GINConv(_ConvBase):
         x, plan, d, ld, logical = self._prep(x, edge_index, plan)
         enc = _edge_encoder_args(self.edge_encoder, edge_attr, plan, d, ld)
         z = ops.aggregate(x, plan, CONV_GIN, d, self.eps, **enc)          # (1+eps) x + sum relu(x_j + e)
-        z = ops.linear(z, self.mlp[0].weight, self.mlp[0].bias)
+        # both Linears feed a train-mode BatchNorm (mlp[1] here, batch_norms[layer] in the caller): their column
+        # statistics are taken in the GEMM epilogue
+        z = ops.linear(z, self.mlp[0].weight, self.mlp[0].bias, col_stats=self.training)
         z = ops.batch_norm(z, self.mlp[1], relu=True)
-        out = ops.linear(z, self.mlp[3].weight, self.mlp[3].bias)
+        out = ops.linear(z, self.mlp[3].weight, self.mlp[3].bias, col_stats=self.training)
         return out[:, :d].float() if logical else out
 
 

@@ -137,8 +137,9 @@ class GNN_node_Virtualnode(_GNNBase):
                 with br:
                     t = ops.segment_sum(hv, plan, init=vn)        # global_add_pool(h_list[layer]) + vn
                     t = ops.cast_to(t, ops.act_dtype())           # the MLP runs in the activation dtype
-                    t = ops.batch_norm(ops.linear(t, mlp[0].weight, mlp[0].bias), mlp[1], relu=True)
-                    t = ops.batch_norm(ops.linear(t, mlp[3].weight, mlp[3].bias), mlp[4], relu=True, drop_p=drop)
+                    cs = self.training
+                    t = ops.batch_norm(ops.linear(t, mlp[0].weight, mlp[0].bias, col_stats=cs), mlp[1], relu=True)
+                    t = ops.batch_norm(ops.linear(t, mlp[3].weight, mlp[3].bias, col_stats=cs), mlp[4], relu=True, drop_p=drop)
                     t = ops.cast_to(t, torch.float32)             # the virtual-node state itself stays fp32
                     vn_next = vn + t if self.residual else t
             h = self.convs[layer](hv, edge_index, edge_attr, plan=plan)

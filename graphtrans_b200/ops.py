@@ -631,8 +631,13 @@ def embed_sum(index_cols, tables, clamps=None, dtype=None):
 
 # ----------------------------------------------------------------------------- dense layers
 def _gemm_raw(dt, A, a_mn, lda, Bm, b_mn, ldb, C, ldc, M, N, K, n_fill, bias, resid, ldr, flags, impl=None,
-              drop_p=0.0, rng=None, salt=0):
-    """raw-pointer gt_gemm (A, Bm, C are device addresses so strided sub-blocks need no copies)"""
+              drop_p=0.0, rng=None, salt=0, col_stats=None):
+    """raw-pointer gt_gemm (A, Bm, C are device addresses so strided sub-blocks need no copies); col_stats: fp64
+    [2 * ldc] that receives the BatchNorm column statistics of C in the same pass (gt_gemm_stats)"""
+    if col_stats is not None:
+        call("gt_gemm_stats", dt, A, int(a_mn), lda, Bm, int(b_mn), ldb, C, ldc, M, N, K, n_fill, ptr(bias), ptr(resid), ldr,
+             flags, float(drop_p), rng, salt, GEMM_IMPL if impl is None else impl, ptr(col_stats))
+        return
     call("gt_gemm", dt, A, int(a_mn), lda, Bm, int(b_mn), ldb, C, ldc, M, N, K, n_fill, ptr(bias), ptr(resid), ldr,
          flags, float(drop_p), rng, salt, GEMM_IMPL if impl is None else impl)
 
@@ -643,7 +648,7 @@ class _LinearFn(torch.autograd.Function):
     block of the weight (JK=cat: gnn2transformer applied to the parts without concatenating)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, relu, out_f32, resid, off, K, drop_p, salt):
+    def forward(ctx, x, weight, bias, relu, out_f32, resid, off, K, drop_p, salt, want_stats=False):
         x = x.contiguous()
         M, ld_in = x.shape
         N, Kw = weight.shape
@@ -672,17 +677,22 @@ class _LinearFn(torch.autograd.Function):
                 raise RuntimeError("linear: resid must match the output")
             if out_dtype == torch.float32 and x.dtype != torch.float32:
                 flags |= _lib.EPI_RESID_F32
+        stats = zeros_small(2 * ld_out, torch.float64, x.device) if want_stats else None
         _gemm_raw(dt_of(x), x.data_ptr(), 0, ld_in, wptr, 0, ldw, y.data_ptr(), ld_out, M, N, K, ld_out, bias, resid,
-                  ld_out, flags, drop_p=drop_p, rng=ptr(rng_state(x.device)) if drop_p else None, salt=salt)
+                  ld_out, flags, drop_p=drop_p, rng=ptr(rng_state(x.device)) if drop_p else None, salt=salt,
+                  col_stats=stats)
         ctx.drop_p = drop_p
         ctx.save_for_backward(x, w, y if relu else None)
         ctx.params = (weight, bias)
         ctx.woff = wptr - w.data_ptr()      # byte offset of the operand block inside the saved weight tensor
         ctx.meta = (M, N, K, Kw, off, ld_in, ldw, ld_out, relu, bias is not None, resid is not None)
+        if want_stats:
+            ctx.mark_non_differentiable(stats)
+            return y, stats
         return y
 
     @staticmethod
-    def backward(ctx, gy):
+    def backward(ctx, gy, _gstats=None):
         x, w, y = ctx.saved_tensors
         M, N, K, Kw, off, ld_in, ldw, ld_out, relu, has_bias, has_resid = ctx.meta
         gy = gy.contiguous()
@@ -727,13 +737,19 @@ class _LinearFn(torch.autograd.Function):
                 tgt, gb = _grad_target(bias)
                 call("gt_colsum", dt_of(gy), ptr(gy), M, N, ld_out, ptr(tgt))
                 _grad_done(bias)
-        return gx, gw, gb, None, None, g_res, None, None, None, None
+        return gx, gw, gb, None, None, g_res, None, None, None, None, None
 
 
-def linear(x, weight, bias=None, relu=False, out_f32=False, resid=None, drop_p=0.0, w_col_off=0, K=None):
+def linear(x, weight, bias=None, relu=False, out_f32=False, resid=None, drop_p=0.0, w_col_off=0, K=None, col_stats=False):
     """drop(act(x W[:, off:off+K]^T + b)) [+ resid]; drop(relu(.)) runs in the GEMM epilogue (the FFN pattern of
-    nn.TransformerEncoderLayer); dropout without ReLU / together with resid is not a reference pattern"""
+    nn.TransformerEncoderLayer); dropout without ReLU / together with resid is not a reference pattern.
+    col_stats=True: the output carries its BatchNorm column statistics (taken in the GEMM epilogue), which
+    ops.batch_norm picks up instead of a separate gt_colstats pass."""
     fused = bool(drop_p) and relu and resid is None
+    if col_stats and not drop_p and not out_f32:
+        y, stats = _LinearFn.apply(x, weight, bias, relu, out_f32, resid, w_col_off, K, 0.0, 0, True)
+        y._gt_colstats = stats
+        return y
     y = _LinearFn.apply(x, weight, bias, relu, out_f32, resid, w_col_off, K, float(drop_p) if fused else 0.0,
                         next_salt() if fused else 0)
     return dropout(y, drop_p) if (drop_p and not fused) else y
@@ -973,7 +989,7 @@ class _BatchNormFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, gamma, beta, running_mean, running_var, nbt, training, momentum, eps, relu, resid,
-                gvec, plan, drop_p, salt):
+                gvec, plan, drop_p, salt, pre_stats=None):
         x = x.contiguous()
         M, ld = x.shape
         d = gamma.shape[0]
@@ -981,8 +997,11 @@ class _BatchNormFn(torch.autograd.Function):
         ssmr = torch.empty(4 * ld, dtype=torch.float32, device=dev)
         stats = None
         if training:
-            stats = zeros_small(2 * ld, torch.float64, dev)
-            call("gt_colstats", dt_of(x), ptr(x), M, ld, ptr(stats))
+            if pre_stats is not None and pre_stats.numel() == 2 * ld:   # taken in the producing GEMM's epilogue
+                stats = pre_stats
+            else:
+                stats = zeros_small(2 * ld, torch.float64, dev)
+                call("gt_colstats", dt_of(x), ptr(x), M, ld, ptr(stats))
         y = torch.empty_like(x)
         if resid is not None:
             resid = resid.contiguous()
@@ -1019,15 +1038,17 @@ class _BatchNormFn(torch.autograd.Function):
         if has_gvec and ctx.needs_input_grad[11]:
             dgv = torch.empty(plan.B, ld, dtype=torch.float32, device=dev)
             call("gt_segment_sum_sorted", dt_of(g), ptr(g), ptr(plan.node_off), plan.B, ld, None, ptr(dgv))
-        return dx, dgamma, dbeta, None, None, None, None, None, None, None, dres, dgv, None, None, None
+        return dx, dgamma, dbeta, None, None, None, None, None, None, None, dres, dgv, None, None, None, None
 
 
 def batch_norm(x, bn: torch.nn.BatchNorm1d, relu=False, resid=None, gvec=None, plan=None, drop_p=0.0):
-    """drop(act(BN(x))) [+ resid] [+ gvec[graph]] in one kernel"""
+    """drop(act(BN(x))) [+ resid] [+ gvec[graph]] in one kernel; an input produced by ops.linear(col_stats=True) brings
+    its column statistics along"""
     training = bn.training or bn.running_mean is None
+    pre = getattr(x, "_gt_colstats", None) if (training and x.is_contiguous()) else None
     return _BatchNormFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked,
                               training, bn.momentum, bn.eps, relu, resid, gvec, plan, drop_p,
-                              next_salt() if drop_p else 0)
+                              next_salt() if drop_p else 0, pre)
 
 
 # ----------------------------------------------------------------------------- LayerNorm / tokens

@@ -207,6 +207,14 @@ int gt_gemm(int dt, const void* A, int a_mn, int64_t lda, const void* B, int b_m
             void* C, int64_t ldc, int64_t M, int64_t N, int64_t K, int64_t n_fill,
             const float* bias, const void* resid, int64_t ldr, int flags, float drop_p,
             const uint64_t* rng_state, uint64_t salt, int impl, void* stream);
+/* gt_gemm + the BatchNorm column statistics of the stored C in one pass: col_stats fp64 [2][ldc] (pre-zeroed) receives
+ * += sum_m C[m, c] and += sum_m C[m, c]^2 exactly as gt_colstats(C) would (of the ROUNDED stored values).  In the tcgen05
+ * kernel the sums are taken from the shared-memory slab of the TMA-store epilogue; other paths run gt_colstats after
+ * the contraction.  Needs a non-accumulating C with n_fill >= ldc (every column written). */
+int gt_gemm_stats(int dt, const void* A, int a_mn, int64_t lda, const void* B, int b_mn, int64_t ldb,
+                  void* C, int64_t ldc, int64_t M, int64_t N, int64_t K, int64_t n_fill,
+                  const float* bias, const void* resid, int64_t ldr, int flags, float drop_p,
+                  const uint64_t* rng_state, uint64_t salt, int impl, double* col_stats, void* stream);
 /* dz = dy * (y > 0) * scale: backward of a ReLU (+ dropout: a dropped element has y == 0, scale = 1/(1-p)) that
  * was fused into a GEMM epilogue; n % 4 == 0 */
 int gt_relu_bwd(int dt, const void* dy, const void* y, int64_t n, void* dz, float scale, void* stream);

@@ -592,3 +592,36 @@ def test_stacked_heads_match_per_head_linears(H, N, K, M):
             assert rel_l2(a.float(), b) < 3e-2, (a.shape, rel_l2(a.float(), b))
     finally:
         ops.set_precision("fp32")
+
+
+@pytest.mark.parametrize("M,N,K", [(13233, 600, 300), (512, 300, 600), (129, 72, 64), (70, 36, 40)])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_linear_with_fused_column_statistics(M, N, K, dtype):
+    """ops.linear(col_stats=True): the BatchNorm column sums / sums of squares taken in the GEMM epilogue (tcgen05 TMA-store
+    path; other paths run gt_colstats inside gt_gemm_stats) equal fp64 sums over the STORED output, and batch_norm on
+    that output matches batch_norm with its own statistics pass"""
+    torch.manual_seed(1)
+    ops.set_precision("bf16" if dtype == torch.bfloat16 else "fp32")
+    try:
+        ops.begin_step("cuda")
+        lin = torch.nn.Linear(K, N).cuda()
+        ld_in = ops.ldp(K)
+        x = torch.zeros(M, ld_in, device="cuda")
+        x[:, :K] = torch.randn(M, K, device="cuda")
+        x = x.to(dtype)
+        y = ops.linear(x, lin.weight, lin.bias, col_stats=True)
+        st = y._gt_colstats.clone()
+        ld = y.shape[1]
+        yd = y.detach().double()
+        assert torch.allclose(st[:ld], yd.sum(0), rtol=1e-6, atol=1e-3 * max(1.0, float(yd.abs().max())))
+        assert torch.allclose(st[ld:], (yd * yd).sum(0), rtol=1e-6, atol=1e-3 * max(1.0, float((yd * yd).max())))
+        y0 = ops.linear(x, lin.weight, lin.bias)
+        assert torch.equal(y0, y.detach())
+        bn = torch.nn.BatchNorm1d(N).cuda().train()
+        bn2 = torch.nn.BatchNorm1d(N).cuda().train()
+        a = ops.batch_norm(y, bn, relu=True)
+        b = ops.batch_norm(y0, bn2, relu=True)
+        assert rel_l2(a.float(), b.float()) < 1e-5
+        assert torch.allclose(bn.running_var, bn2.running_var, rtol=1e-5, atol=1e-7)
+    finally:
+        ops.set_precision("fp32")
