@@ -18,6 +18,8 @@ from ._lib import (CONV_GCN, CONV_GIN, EDGE_LINEAR, EDGE_NONE, EDGE_TABLE, EPI_A
 
 _PRECISION = os.environ.get("GT_PRECISION", "fp32")
 GEMM_IMPL = int(os.environ.get("GT_GEMM_IMPL", "0"))   # 0 auto, 1 CUDA-core, 2 tcgen05 only
+FUSE_COLSTATS = int(os.environ.get("GT_FUSE_COLSTATS", "1"))         # BatchNorm statistics in the producing GEMM's epilogue
+SKIP_ZERO_BIAS_GRAD = int(os.environ.get("GT_SKIP_ZERO_BIAS_GRAD", "1"))   # bias of a Linear feeding train-mode BN: gradient == 0
 MHA_IMPL = int(os.environ.get("GT_MHA_IMPL", "0"))
 
 
@@ -686,6 +688,9 @@ class _LinearFn(torch.autograd.Function):
         ctx.params = (weight, bias)
         ctx.woff = wptr - w.data_ptr()      # byte offset of the operand block inside the saved weight tensor
         ctx.meta = (M, N, K, Kw, off, ld_in, ldw, ld_out, relu, bias is not None, resid is not None)
+        # want_stats <=> the output feeds a train-mode BatchNorm directly: the BN backward returns a gradient whose
+        # column sums vanish identically, i.e. the bias gradient of this Linear is exactly zero - no gt_colsum launch
+        ctx.bias_grad_zero = bool(want_stats) and SKIP_ZERO_BIAS_GRAD
         if want_stats:
             ctx.mark_non_differentiable(stats)
             return y, stats
@@ -734,8 +739,9 @@ class _LinearFn(torch.autograd.Function):
                           M, K, None, None, 0, EPI_ACCUM | EPI_OUT_F32)
                 _grad_done(weight)
             if has_bias and ctx.needs_input_grad[2]:
-                tgt, gb = _grad_target(bias)
-                call("gt_colsum", dt_of(gy), ptr(gy), M, N, ld_out, ptr(tgt))
+                tgt, gb = _grad_target(bias)           # (a fresh zero tensor when there is no arena)
+                if not ctx.bias_grad_zero:
+                    call("gt_colsum", dt_of(gy), ptr(gy), M, N, ld_out, ptr(tgt))
                 _grad_done(bias)
         return gx, gw, gb, None, None, g_res, None, None, None, None, None
 
@@ -746,7 +752,7 @@ def linear(x, weight, bias=None, relu=False, out_f32=False, resid=None, drop_p=0
     col_stats=True: the output carries its BatchNorm column statistics (taken in the GEMM epilogue), which
     ops.batch_norm picks up instead of a separate gt_colstats pass."""
     fused = bool(drop_p) and relu and resid is None
-    if col_stats and not drop_p and not out_f32:
+    if col_stats and FUSE_COLSTATS and not drop_p and not out_f32:
         y, stats = _LinearFn.apply(x, weight, bias, relu, out_f32, resid, w_col_off, K, 0.0, 0, True)
         y._gt_colstats = stats
         return y
