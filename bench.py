@@ -244,7 +244,8 @@ def hot_kernel_roofline(args, model, b, hb, ns, step_ms):
         def agg():
             y = ops.aggregate(x, plan, kind, d_g, sp, **enc)
             torch.autograd.grad(y, x, gy)      # no .grad accumulation kernels inside the timed launches
-        name = "gt_aggregate_fwd + gt_aggregate_bwd (k_agg_fwd2 / k_agg_bwd2)"
+        kname = "k_agg_fwd2 / k_agg_bwd2" if enc.get("edge_kind") == conv_mod.EDGE_LINEAR else "k_agg_fwd3 / k_agg_bwd3"
+        name = f"gt_aggregate_fwd + gt_aggregate_bwd ({kname})"
     else:
         layer = model.gnn_node.layers[0]
         x = (torch.randn(N, ld, device=b.batch.device) * 0.5).to(act).requires_grad_(True)
