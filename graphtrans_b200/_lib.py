@@ -64,7 +64,7 @@ SIGNATURES = {
     "gt_mha_fwd": [I, P, P, P, P, P, P, L, L, I32, I32, F, P, P, F, P, U64, I, P],
     "gt_mha_bwd": [I, P, P, P, P, P, P, P, P, P, L, L, I32, I32, F, P, P, F, P, U64, I, P],
     "gt_mha_local_tiles": [P, L, L, P, P, P],
-    "gt_mha_local_fwd": [I, P, P, P, L, L, I32, I32, F, P, P, F, P, U64, P],
+    "gt_mha_local_fwd": [I, P, P, P, P, L, L, I32, I32, F, P, P, F, P, U64, P],
     "gt_mha_local_bwd": [I, P, P, P, P, P, P, L, L, I32, I32, F, P, F, P, U64, P],
     "gt_bce_masked_fwd": [P, P, L, I32, L, L, P, P, P],
     "gt_bce_masked_bwd": [P, P, L, I32, L, L, P, P, P, L, I32, P],

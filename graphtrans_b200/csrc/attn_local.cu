@@ -24,6 +24,7 @@ constexpr int LOC_THREADS = 320;
 struct LocParams {
     const int2* row_bounds;    // [lo, hi) token rows of the graph of every row
     const int2* tiles;         // (first row, rows) of every graph-aligned tile; rows == 0: unused slot
+    const int32_t* count;      // tiles used; < 0: the batch violated the host's bound (a graph > 128 tokens / too many tiles)
     void* out;                 // forward: written; backward: read (delta)
     const void* dout;
     float* lse;
@@ -78,6 +79,11 @@ k_mha_loc_fwd(const __grid_constant__ CUtensorMap tma_qkv, const LocParams p) {
     __shared__ uint32_t tmem_base_s;
     __shared__ float xchg[2][128];                             // row max / row sum exchange between the two column halves
     if (threadIdx.x == 0) LOC_TRACE(0);
+    if (p.count && p.count[0] < 0) {   // fail loudly: a NaN row poisons the loss instead of silently skipping graphs
+        if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < p.d)
+            reinterpret_cast<bf16*>(p.out)[threadIdx.x] = __float2bfloat16_rn(__int_as_float(0x7fc00000));
+        return;
+    }
     const int2 tile = p.tiles[blockIdx.x];
     const int row0 = tile.x, nrows = tile.y;
     if (nrows <= 0) return;                                   // unused slot of the (host-side) upper bound
@@ -400,9 +406,9 @@ __global__ void __launch_bounds__(256)
 k_mha_local_tiles(const int32_t* __restrict__ tok_off, int B, int max_tiles, int2* __restrict__ tiles, int32_t* __restrict__ count) {
     constexpr int CH = 2048;
     __shared__ int32_t off[CH + 1];
-    __shared__ int s_start, s_n;
+    __shared__ int s_start, s_n, s_bad;
     for (int i = threadIdx.x; i < max_tiles; i += blockDim.x) tiles[i] = make_int2(0, 0);
-    if (threadIdx.x == 0) s_start = tok_off[0], s_n = 0;
+    if (threadIdx.x == 0) s_start = tok_off[0], s_n = 0, s_bad = 0;
     __syncthreads();
     for (int g0 = 0; g0 < B; g0 += CH) {
         const int n = min(CH, B - g0);
@@ -411,6 +417,7 @@ k_mha_local_tiles(const int32_t* __restrict__ tok_off, int B, int max_tiles, int
         if (threadIdx.x == 0) {
             int start = s_start, cnt = s_n;
             for (int i = 0; i < n; ++i) {                      // graph g0 + i owns rows [off[i], off[i + 1])
+                if (off[i + 1] - off[i] > 128) s_bad = 1;      // a graph that does not fit one tile: host bound violated
                 if (off[i + 1] - start > 128 && off[i] > start) {
                     if (cnt < max_tiles) tiles[cnt] = make_int2(start, min(off[i] - start, 128));
                     ++cnt;
@@ -428,7 +435,7 @@ k_mha_local_tiles(const int32_t* __restrict__ tok_off, int B, int max_tiles, int
             if (cnt < max_tiles) tiles[cnt] = make_int2(s_start, min(end - s_start, 128));
             ++cnt;
         }
-        *count = cnt;
+        *count = (s_bad || cnt > max_tiles) ? -1 : cnt;        // < 0: gt_mha_local_fwd poisons its output with NaN
     }
 }
 
@@ -485,8 +492,8 @@ extern "C" int gt_mha_local_tiles(const int32_t* tok_off, int64_t B, int64_t max
     return 0;
 }
 
-extern "C" int gt_mha_local_fwd(int dt, const void* qkv, const int32_t* row_bounds, const int32_t* tiles, int64_t max_tiles,
-                                int64_t n_rows, int32_t nhead, int32_t dh, float scale, void* out, float* lse, float drop_p,
+extern "C" int gt_mha_local_fwd(int dt, const void* qkv, const int32_t* row_bounds, const int32_t* tiles, const int32_t* count,
+                                int64_t max_tiles, int64_t n_rows, int32_t nhead, int32_t dh, float scale, void* out, float* lse, float drop_p,
                                 const uint64_t* rng_state, uint64_t salt, void* stream) {
     if (int r = loc_check("gt_mha_local_fwd", dt, qkv, out, n_rows, nhead, dh, max_tiles)) return r;
     const int d = nhead * dh;
@@ -496,7 +503,7 @@ extern "C" int gt_mha_local_fwd(int dt, const void* qkv, const int32_t* row_boun
         return -1;
     }
     LocParams p{};
-    p.row_bounds = (const int2*)row_bounds; p.tiles = (const int2*)tiles; p.out = out; p.lse = lse; p.rng = rng_state; p.salt = salt;
+    p.row_bounds = (const int2*)row_bounds; p.tiles = (const int2*)tiles; p.count = count; p.out = out; p.lse = lse; p.rng = rng_state; p.salt = salt;
     p.n_rows = n_rows; p.nhead = nhead; p.d = d; p.scale = scale; p.scale_log2 = scale * LOG2E; p.drop_p = drop_p;
     p.trace = loc_trace_buf();
     const cudaError_t e = dh == 64 ? launch_loc_fwd<64>(map, p, (int)max_tiles, (cudaStream_t)stream)

@@ -1187,7 +1187,8 @@ class _MHAFn(torch.autograd.Function):
         local = (impl == 0 and key_start is None and getattr(plan, "loc_tiles", None) is not None
                  and qkv.dtype == torch.bfloat16 and dh in (32, 64))
         if local:
-            call("gt_mha_local_fwd", dt_of(qkv), ptr(qkv), ptr(plan.row_bounds), ptr(plan.loc_tiles), plan.loc_max_tiles,
+            call("gt_mha_local_fwd", dt_of(qkv), ptr(qkv), ptr(plan.row_bounds), ptr(plan.loc_tiles), ptr(plan.loc_count),
+                 plan.loc_max_tiles,
                  n_rows, nhead, dh, scale, ptr(out), ptr(lse), float(drop_p),
                  ptr(rng_state(qkv.device)) if drop_p else None, salt)
         else:

@@ -289,13 +289,15 @@ int gt_mha_bwd(int dt, const void* qkv, const void* out, const void* dout, const
 
 /* Tile-local attention for batches of SMALL graphs (every graph <= 128 tokens incl. <CLS>; same math, dropout hash and
  * lse as gt_mha_fwd/bwd).  gt_mha_local_tiles packs consecutive graphs greedily into graph-aligned tiles of <= 128
- * packed rows: tiles int32 [max_tiles][2] = (first row, rows), unused slots (0, 0); *count = tiles used.  max_tiles is a
+ * packed rows: tiles int32 [max_tiles][2] = (first row, rows), unused slots (0, 0); *count = tiles used, or -1 when the
+ * batch violates the bound (a graph longer than 128 rows, more tiles than max_tiles): gt_mha_local_fwd (count may be
+ * NULL) then writes a NaN row so that the loss fails loudly instead of silently skipping graphs.  max_tiles is a
  * host-side upper bound, e.g. min(B, ceil(n_rows / (129 - max_tokens_per_graph))).  A CTA = (tile, head) keeps Q, K, V
  * (and dO) of the tile in shared memory: forward = 2 tcgen05 MMA groups, backward = 5 (dQ, dK, dV in ONE launch, no
  * atomics, delta computed in-kernel).  bf16 only, dh in {32, 64}. */
 int gt_mha_local_tiles(const int32_t* tok_off, int64_t B, int64_t max_tiles, int32_t* tiles, int32_t* count, void* stream);
-int gt_mha_local_fwd(int dt, const void* qkv, const int32_t* row_bounds, const int32_t* tiles, int64_t max_tiles,
-                     int64_t n_rows, int32_t nhead, int32_t dh, float scale, void* out, float* lse, float drop_p,
+int gt_mha_local_fwd(int dt, const void* qkv, const int32_t* row_bounds, const int32_t* tiles, const int32_t* count,
+                     int64_t max_tiles, int64_t n_rows, int32_t nhead, int32_t dh, float scale, void* out, float* lse, float drop_p,
                      const uint64_t* rng_state, uint64_t salt, void* stream);
 int gt_mha_local_bwd(int dt, const void* qkv, const void* out, const void* dout, const float* lse,
                      const int32_t* row_bounds, const int32_t* tiles, int64_t max_tiles, int64_t n_rows, int32_t nhead,

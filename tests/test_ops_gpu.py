@@ -625,3 +625,14 @@ def test_linear_with_fused_column_statistics(M, N, K, dtype):
         assert torch.allclose(bn.running_var, bn2.running_var, rtol=1e-5, atol=1e-7)
     finally:
         ops.set_precision("fp32")
+
+
+def test_mha_tile_local_fails_loudly_on_a_wrong_size_hint():
+    """a batch whose largest graph exceeds the host-side max_nodes bound must not silently skip graphs: the tile builder
+    flags it on the device and the forward writes NaN"""
+    lens = [20, 200, 30]
+    plan = _small_graph_plan(lens, 30)          # lie: the second graph has 200 nodes
+    assert plan.loc_tiles is not None and int(plan.loc_count) < 0
+    qkv = torch.randn(plan.n_rows, 3 * 128, device="cuda").bfloat16()
+    o = ops.mha_packed(qkv, plan, 4)
+    assert torch.isnan(o.float()).any()

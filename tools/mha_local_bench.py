@@ -28,8 +28,8 @@ if __name__ == "__main__":
         print(f"{cfg}: rows={n} tiles used {int(plan.loc_count)} of {plan.loc_max_tiles} slots, dh={dh}")
         for p in (0.0, 0.3):
             def lf():
-                call("gt_mha_local_fwd", dt_of(qkv), ptr(qkv), ptr(plan.row_bounds), ptr(plan.loc_tiles), plan.loc_max_tiles, n, nhead,
-                     dh, dh ** -0.5, ptr(out), ptr(lse), p, ptr(rng) if p else None, 5)
+                call("gt_mha_local_fwd", dt_of(qkv), ptr(qkv), ptr(plan.row_bounds), ptr(plan.loc_tiles), ptr(plan.loc_count), plan.loc_max_tiles, n,
+                     nhead, dh, dh ** -0.5, ptr(out), ptr(lse), p, ptr(rng) if p else None, 5)
 
             def lb():
                 call("gt_mha_local_bwd", dt_of(qkv), ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(plan.row_bounds), ptr(plan.loc_tiles),
