@@ -1,4 +1,8 @@
-mkdir -p gpurun_out
-timeout 600 python -m pytest tests -q -m gpu -x 2>&1 | grep -v "^frame" | tail -40 | grep -E "passed|failed|Error|assert|^E " > gpurun_out/s4_tests14.log
-cat gpurun_out/s4_tests14.log
-python tools/graph_trace.py molpcba 2>&1 | head -1
+for i in 1 2; do
+for kb in 16 32 64; do
+echo "min_kb=$kb $(GT_SPLITK_MIN_KB=$kb python tools/graph_trace.py molpcba 2>&1 | head -1 | cut -c1-60)"
+done
+done
+for kb in 16 32 64; do
+echo "code2 min_kb=$kb $(GT_SPLITK_MIN_KB=$kb python tools/graph_trace.py code2 2>&1 | head -1 | cut -c1-60)"
+done
