@@ -257,13 +257,31 @@ def hot_kernel_roofline(args, model, b, hb, ns, step_ms):
             y = ops.pna_reduce(x, pj, pi, plan, 4, d_g // 4, layer.avg_deg["log"])
             torch.autograd.grad(y, (x, pj, pi), gy)
         name = "gt_pna_reduce_fwd + gt_pna_reduce_bwd"
-    ms = _timed(agg)
+    ms = _timed(agg)                       # the edge table is a constant here: exactly the two named kernels run
     ach = 2 * alg["agg_bytes_per_launch"] / (ms * 1e-3) / 1e9
     out.append({"kernel": name, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
                 "traffic": traffic.get("aggregate"), "avg_launch_us": ms / 2 * 1e3,
                 "share_of_step": ms * args.gnn_num_layer / step_ms,
                 "algorithmic_bytes_per_launch": alg["agg_bytes_per_launch"], "peak_source": pk["source"],
                 "note": "the [N, d_g] matrix of these configs is L2-resident (8-10 MB << 126 MB L2)"})
+    if args.model_type == "gnn-transformer" and enc.get("edge_kind") == conv_mod.EDGE_TABLE:
+        # the edge-table gradient of the same layer (weight-gradient stream): gathers x[src] and dout[dst] of every edge
+        from graphtrans_b200._lib import call as _call, dt_of as _dt, ptr as _p
+        table, etype = enc["table"], enc["etype"]
+        src_t, dst_t, type_t, _ = plan.edges_by_type(plan._edge_index, etype, table.shape[0])
+        dtab = torch.zeros_like(table)
+        xc = x.detach()
+
+        def tab_grad():
+            _call("gt_aggregate_table_grad", _dt(xc), kind, _p(xc), _p(gy), N, d_g, ld, _p(plan.rowptr_src), plan.E, _p(src_t),
+                  _p(dst_t), _p(type_t), _p(table), table.shape[0], _p(dtab))
+        ms_t = _timed(tab_grad)
+        tg_bytes = 2 * plan.E * d_g * es + 12 * plan.E
+        ach_t = tg_bytes / (ms_t * 1e-3) / 1e9
+        out.append({"kernel": "gt_aggregate_table_grad (k_agg_table_grad, weight-gradient stream)", "bound": "hbm", "achieved": ach_t,
+                    "peak": pk["hbm"], "unit": "GB/s", "frac": ach_t / pk["hbm"], "traffic": None, "avg_launch_us": ms_t * 1e3,
+                    "share_of_step": None, "algorithmic_bytes_per_launch": tg_bytes, "peak_source": pk["source"],
+                    "note": "gather formulation: 2 E d_g s + 12 E bytes (x[src], dout[dst], sorted edge triples); L2-resident rows"})
     # stage 2: masked MHA fwd + bwd over the packed tokens (one encoder layer)
     d, nh = args.d_model, args.nhead
     qkv = torch.randn(plan.n_rows, 3 * d, device=b.batch.device).to(act).requires_grad_(True)

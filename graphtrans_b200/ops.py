@@ -876,16 +876,17 @@ class _AggregateFn(torch.autograd.Function):
         tw = tb = (None, None)
         if edge_kind == EDGE_LINEAR:
             tw, tb = _grad_target(pw), _grad_target(pb)
-        dtab = zeros_f32(tuple(table.shape), x.device) if edge_kind == EDGE_TABLE else None
+        need_tab = edge_kind == EDGE_TABLE and ctx.needs_input_grad[9]     # a constant table has no gradient kernel
+        dtab = zeros_f32(tuple(table.shape), x.device) if need_tab else None
         # the edge-table gradient is a leaf gradient: computed by its own kernel over the type-sorted edges, on the
         # weight-gradient stream, instead of shared-memory atomics inside the adjoint (which then stays as cheap as
         # the forward)
-        split = ctx.split
+        split = ctx.split and need_tab
         tself = _grad_target(pself)
         call("gt_aggregate_bwd", dt_of(x), conv, ptr(x), ptr(g), ptr(dx), N, d, ld, ptr(plan.rowptr_dst),
              ptr(plan.rowptr_src), ptr(plan.dst_by_src), ptr(plan.eid_by_src), edge_kind, ptr(edge_attr), kdim,
              ptr(edge_w), ptr(edge_b), ptr(etype), ptr(table), table.shape[0] if edge_kind == EDGE_TABLE else 0, ptr(sp),
-             ptr(tw[0]), ptr(tb[0]), None if split else ptr(dtab), ptr(tself[0]), ptr(ctx.slots[0]), ptr(ctx.slots[1]),
+             ptr(tw[0]), ptr(tb[0]), None if (split or not need_tab) else ptr(dtab), ptr(tself[0]), ptr(ctx.slots[0]), ptr(ctx.slots[1]),
              ptr(ctx.slots[2]))
         if split:
             src_t, dst_t, type_t, _ = plan.edges_by_type(plan._edge_index, etype, table.shape[0])
