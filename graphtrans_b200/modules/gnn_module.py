@@ -1,7 +1,8 @@
 """GNN stacks with the reference's API (reference modules/gnn_module.py:18-248): node encoder ->
 L x (conv -> BatchNorm1d -> ReLU -> dropout [-> residual]) -> JK, optional virtual node.  The
 layer loop is re-expressed over physical [N, ld] matrices; BN-apply, ReLU, residual and the
-next layer's virtual-node broadcast are one kernel (gt_bn_apply_fwd)."""
+next layer's virtual-node broadcast are one kernel (gt_bn_norm_fwd); the statistics of a BatchNorm that follows a
+Linear come out of that GEMM's epilogue (gt_gemm_stats)."""
 import torch
 
 from .. import ops
