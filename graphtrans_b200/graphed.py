@@ -14,6 +14,7 @@ Replaces the Python-level orchestration of reference trainers/base_trainer.py:28
 """
 from __future__ import annotations
 
+import os
 from collections import OrderedDict
 
 import torch
@@ -52,6 +53,12 @@ class GraphedStep:
         self.pool = None
         self.device = buckets.flat.device
         self.last_kernels = 0
+        # the step is captured on a HIGH-priority stream: its kernels are the critical path, the weight-gradient and
+        # virtual-node branches (default = lowest priority) only fill the SMs it leaves free.  Captured kernel nodes
+        # inherit the priority of the stream they were issued on.
+        self.capture_stream = None
+        if self.device.type == "cuda" and os.environ.get("GT_MAIN_PRIORITY", "1") == "1":
+            self.capture_stream = torch.cuda.Stream(device=self.device, priority=-1)
 
     def _eager(self, b):
         self.buckets.zero_grad()
@@ -80,7 +87,7 @@ class GraphedStep:
         torch.cuda.synchronize(self.device)
         ent.graph = torch.cuda.CUDAGraph()
         k0 = _lib.kernel_count
-        with torch.cuda.graph(ent.graph, pool=self.pool):
+        with torch.cuda.graph(ent.graph, pool=self.pool, stream=self.capture_stream):
             ent.loss = self._eager(ent.static_batch)
         ent.kernels = _lib.kernel_count - k0
         if self.pool is None:
