@@ -232,7 +232,10 @@ _branch = {"stream": None, "used": False}
 
 
 def enable_branch_stream(on=True, device="cuda"):
-    _branch["stream"] = torch.cuda.Stream(device=device) if on else None
+    # the virtual-node update joins the main stream at the end of every GNN layer, i.e. it is on the critical path
+    # (unlike the weight gradients): high priority, like the stream GraphedStep captures the step on
+    prio = -1 if os.environ.get("GT_BRANCH_PRIORITY", "1") == "1" else 0
+    _branch["stream"] = torch.cuda.Stream(device=device, priority=prio) if on else None
     _branch["used"] = False
 
 

@@ -1,4 +1,7 @@
+# scratch command file for `gpurun -- 'bash tools/_run.sh'` (what the last GPU call of the session ran): full GPU test suite,
+# smoke, the headline bench; outputs under gpurun_out/ (copy what should be kept into profiles/)
 mkdir -p gpurun_out
-python bench.py > gpurun_out/r01_bench_molpcba_v8.log 2>&1
-python bench.py --config code2-pna --no-cpu-baseline --no-optimizer > gpurun_out/r01_bench_code2-pna_v8.log 2>&1
-python bench.py --config code2 --no-cpu-baseline > gpurun_out/r01_bench_code2_v8.log 2>&1
+timeout 600 python -m pytest tests -q -m gpu -x 2>&1 | grep -v "^frame" | tail -40 | grep -E "passed|failed|Error|assert|^E " > gpurun_out/tests_gpu.log
+cat gpurun_out/tests_gpu.log
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -3 gpurun_out/smoke.log
+python bench.py > gpurun_out/bench_molpcba.log 2>&1
