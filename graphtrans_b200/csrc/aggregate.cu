@@ -811,7 +811,9 @@ __global__ void __launch_bounds__(256)
 k_agg_bwd3(const T* __restrict__ x, const T* __restrict__ dout, T* __restrict__ dx, int N, int d, int ld,
            const int32_t* __restrict__ rp_src, const int32_t* __restrict__ dst_by_src,
            const int32_t* __restrict__ eid_by_src, EdgeEnc en, const float* __restrict__ self_param,
-           float* __restrict__ d_edge_w, float* __restrict__ d_edge_b, float* __restrict__ d_self) {
+           float* __restrict__ d_edge_w, float* __restrict__ d_edge_b, float* __restrict__ d_self, T* __restrict__ gm_out) {
+    // gm_out (optional, [E, ld] in source-sorted slot order): the per-edge masked message gradient norm * dout[dst] *
+    // 1[x[src] + e > 0], written for the edge-table gradient as a contraction (OneHot(type)^T . gm on the tensor cores)
     extern __shared__ float sh_par[];    // [self | b | w0..w(KD-1)][ld], then one eps slot per warp
     const int c0 = threadIdx.x * 8;
     const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
@@ -853,14 +855,15 @@ k_agg_bwd3(const T* __restrict__ x, const T* __restrict__ dout, T* __restrict__ 
         if (jnext + stride < N) b2 = rp_src[jnext + stride], e2 = rp_src[jnext + stride + 1];
         const float inv_deg_j = CONV == GT_CONV_GCN ? 1.f / (float)(e0 - b0 + 1) : 1.f;
         float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        auto consume = [&](const SlotBatch<KD>& sb) {
+        auto consume = [&](const SlotBatch<KD>& sb, int pbase) {
 #pragma unroll
             for (int u = 0; u < AGG_U; ++u) {
-                float ee[8];
+                float ee[8], gmv[8];
                 ev.embed(en, sb.a[u], sb.ty[u], c0, ld, ee);
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     const float gm = (xj[q] + ee[q] > 0.f) ? sb.nrm[u] * g[u][q] : 0.f;
+                    gmv[q] = gm;
                     acc[q] += gm;
                     if (EK == GT_EDGE_LINEAR) {
                         a_b[q] += gm;
@@ -868,15 +871,16 @@ k_agg_bwd3(const T* __restrict__ x, const T* __restrict__ dout, T* __restrict__ 
                         for (int k = 0; k < KD; ++k) a_w[k][q] = fmaf(sb.a[u][k], gm, a_w[k][q]);
                     }
                 }
+                if (gm_out && pbase + u < e0) st8(gm_out + (int64_t)(pbase + u) * ld + c0, gmv);
             }
         };
-        consume(cur);
+        consume(cur, b0);
         for (int p0 = b0 + AGG_U; p0 < e0; p0 += AGG_U) {         // nodes with more than AGG_U out-edges
             SlotBatch<KD> sb;
             load_slots<CONV, EK, KD>(sb, en, dst_by_src, eid_by_src, rp_src, p0, e0, j, 1.f);
 #pragma unroll
             for (int u = 0; u < AGG_U; ++u) ld8(dout + (int64_t)sb.other[u] * ld + c0, g[u]);
-            consume(sb);
+            consume(sb, p0);
         }
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -968,7 +972,7 @@ static int launch_fwd(int ek, const T* x, T* out, int N, int d, int ld, const in
 template <typename T, int CONV>
 static int launch_bwd(int ek, const T* x, const T* dout, T* dx, int N, int d, int ld, const int32_t* rp_src,
                       const int32_t* dst_by_src, const int32_t* eid_by_src, EdgeEnc en,
-                      const float* self_param, float* dw, float* db, float* dtab, float* dself,
+                      const float* self_param, float* dw, float* db, float* dtab, float* dself, T* gm_out,
                       cudaStream_t st) {
     int grid = blocks_for(N, AGG_WARPS, kNumSMs * 8);
     const int nch = (ld + 127) / 128;
@@ -994,11 +998,14 @@ static int launch_bwd(int ek, const T* x, const T* dout, T* dx, int N, int d, in
         // parameter-gradient element)
         const int grid3 = blocks_for(N, (int)blk.y, kNumSMs * 3);
         const size_t smem3 = sizeof(float) * ((size_t)(2 + MAX_KDIM) * ld + 32);
-#define L3K(EK, KD) k_agg_bwd3<T, CONV, EK, KD><<<grid3, blk, smem3, st>>>(x, dout, dx, N, d, ld, rp_src, dst_by_src, eid_by_src, en, self_param, dw, db, dself)
+#define L3K(EK, KD) k_agg_bwd3<T, CONV, EK, KD><<<grid3, blk, smem3, st>>>(x, dout, dx, N, d, ld, rp_src, dst_by_src, eid_by_src, en, self_param, dw, db, dself, gm_out)
         if (ek == GT_EDGE_NONE) L3K(GT_EDGE_NONE, 1);
         else if (ek == GT_EDGE_LINEAR) { if (en.kdim > 2) L3K(GT_EDGE_LINEAR, 4); else L3K(GT_EDGE_LINEAR, 2); }
         else L3K(GT_EDGE_TABLE, 1);
 #undef L3K
+    } else if (gm_out) {
+        set_error("gt_aggregate_bwd: gm_out needs the vector kernel (ld %% 8 == 0, ld <= 512, table / no edge encoder, d_table == NULL)");
+        return -1;
     } else if (nch <= 4 && smem2 <= 100 * 1024 && variant != 1 && (!tab_grad || variant == 2)) {
         // every block flushes its private gradient tables once: keep the block count near the resident capacity
         const int cap = kNumSMs * (smem2 > 48 * 1024 ? 2 : 8);
@@ -1054,18 +1061,20 @@ extern "C" int gt_aggregate_bwd(int dt, int conv, const void* x, const void* dou
                                 const float* edge_attr, int32_t kdim, const float* edge_w, const float* edge_b,
                                 const int32_t* etype, const float* table, int32_t ntypes, const float* self_param,
                                 float* d_edge_w, float* d_edge_b, float* d_table, float* d_self, const float* norm_slot,
-                                const int32_t* etype_slot, const float* attr_slot, void* stream) {
+                                const int32_t* etype_slot, const float* attr_slot, void* gm_out, void* stream) {
     (void)rowptr_dst;
     if (int r = check_common("gt_aggregate_bwd", conv, N, d, ld, edge_kind, kdim)) return r;
     GT_CHECK_ARG(edge_kind != GT_EDGE_TABLE || ntypes > 0, "gt_aggregate_bwd: ntypes must be the row count of the edge table");
     EdgeEnc en{edge_attr, edge_w, edge_b, etype, table, kdim, ntypes, norm_slot, etype_slot, attr_slot};
     cudaStream_t st = (cudaStream_t)stream;
+    int rc = 0;
     GT_DISPATCH_DT(dt, {
         if (conv == GT_CONV_GCN)
-            launch_bwd<T, GT_CONV_GCN>(edge_kind, (const T*)x, (const T*)dout, (T*)dx, (int)N, d, ld, rowptr_src, dst_by_src, eid_by_src, en, self_param, d_edge_w, d_edge_b, d_table, d_self, st);
+            rc = launch_bwd<T, GT_CONV_GCN>(edge_kind, (const T*)x, (const T*)dout, (T*)dx, (int)N, d, ld, rowptr_src, dst_by_src, eid_by_src, en, self_param, d_edge_w, d_edge_b, d_table, d_self, (T*)gm_out, st);
         else
-            launch_bwd<T, GT_CONV_GIN>(edge_kind, (const T*)x, (const T*)dout, (T*)dx, (int)N, d, ld, rowptr_src, dst_by_src, eid_by_src, en, self_param, d_edge_w, d_edge_b, d_table, d_self, st);
+            rc = launch_bwd<T, GT_CONV_GIN>(edge_kind, (const T*)x, (const T*)dout, (T*)dx, (int)N, d, ld, rowptr_src, dst_by_src, eid_by_src, en, self_param, d_edge_w, d_edge_b, d_table, d_self, (T*)gm_out, st);
     });
+    if (rc) return rc;
     GT_LAUNCH_CHECK("gt_aggregate_bwd");
     return 0;
 }

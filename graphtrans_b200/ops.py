@@ -20,6 +20,7 @@ _PRECISION = os.environ.get("GT_PRECISION", "fp32")
 GEMM_IMPL = int(os.environ.get("GT_GEMM_IMPL", "0"))   # 0 auto, 1 CUDA-core, 2 tcgen05 only
 FUSE_COLSTATS = int(os.environ.get("GT_FUSE_COLSTATS", "1"))         # BatchNorm statistics in the producing GEMM's epilogue
 SKIP_ZERO_BIAS_GRAD = int(os.environ.get("GT_SKIP_ZERO_BIAS_GRAD", "1"))   # bias of a Linear feeding train-mode BN: gradient == 0
+TABLE_GRAD_GEMM = int(os.environ.get("GT_TABLE_GRAD_GEMM", "1"))           # edge-table gradient as a one-hot contraction (bf16)
 MHA_IMPL = int(os.environ.get("GT_MHA_IMPL", "0"))
 
 
@@ -535,6 +536,25 @@ class GraphPlan:
             self._by_type[key] = hit
         return hit
 
+    def type_onehot(self, etype_slot, ntypes):
+        """bf16 one-hot [E, ldp(ntypes)] of the per-slot edge types (once per batch, reused by every layer's
+        edge-table gradient contraction)"""
+        key = (etype_slot.data_ptr(), int(ntypes))
+        hit = self._by_type.get(("onehot",) + key)
+        if hit is None:
+            E = max(self.E, 1)
+            idx = etype_slot.long()
+            r_pad = ldp(int(ntypes))
+            oh = torch.empty(E, r_pad, dtype=torch.bfloat16, device=etype_slot.device)
+            a_idx = (ctypes.c_void_p * 1)(idx.data_ptr())
+            a_str = (ctypes.c_int64 * 1)(1)
+            a_clp = (ctypes.c_int64 * 1)(int(ntypes) - 1)
+            a_base = (ctypes.c_int32 * 1)(0)
+            call("gt_onehot", E, 1, a_idx, a_str, a_clp, a_base, r_pad, ptr(oh))
+            hit = (oh, r_pad, idx)
+            self._by_type[("onehot",) + key] = hit
+        return hit
+
     @property
     def S(self) -> int:
         """padded length min(max n_i, L) - needs one device->host read (public pad_batch API only)."""
@@ -861,7 +881,12 @@ class _AggregateFn(torch.autograd.Function):
         ctx.slots = slots[1]
         ctx.split = edge_kind == EDGE_TABLE and table.shape[0] <= 1024
         ctx.tab_side = bool(tab_side)
-        if ctx.split:   # type-sorted edges for the table-gradient kernel (once per batch)
+        # bf16: the table gradient is the contraction OneHot(type)^T . gm over the per-edge gradients the adjoint writes
+        ctx.tab_gemm = bool(ctx.split and TABLE_GRAD_GEMM and x.dtype == torch.bfloat16 and plan.E >= 1024 and ld % 8 == 0
+                            and ld <= 512 and slots[1][1] is not None)
+        if ctx.tab_gemm:
+            plan.type_onehot(slots[1][1], table.shape[0])
+        elif ctx.split:   # type-sorted edges for the table-gradient kernel (once per batch)
             plan.edges_by_type(plan._edge_index, etype, table.shape[0])
         ctx.save_for_backward(x, edge_attr, edge_w, edge_b, etype, table, sp)
         ctx.params = (edge_w_param, edge_b, self_param)
@@ -885,13 +910,20 @@ class _AggregateFn(torch.autograd.Function):
         # weight-gradient stream, instead of shared-memory atomics inside the adjoint (which then stays as cheap as
         # the forward)
         split = ctx.split and need_tab
+        gm = torch.empty(max(plan.E, 1), ld, dtype=x.dtype, device=x.device) if (split and ctx.tab_gemm) else None
         tself = _grad_target(pself)
         call("gt_aggregate_bwd", dt_of(x), conv, ptr(x), ptr(g), ptr(dx), N, d, ld, ptr(plan.rowptr_dst),
              ptr(plan.rowptr_src), ptr(plan.dst_by_src), ptr(plan.eid_by_src), edge_kind, ptr(edge_attr), kdim,
              ptr(edge_w), ptr(edge_b), ptr(etype), ptr(table), table.shape[0] if edge_kind == EDGE_TABLE else 0, ptr(sp),
              ptr(tw[0]), ptr(tb[0]), None if (split or not need_tab) else ptr(dtab), ptr(tself[0]), ptr(ctx.slots[0]), ptr(ctx.slots[1]),
-             ptr(ctx.slots[2]))
-        if split:
+             ptr(ctx.slots[2]), ptr(gm))
+        if split and gm is not None:
+            oh, r_pad, _ = plan.type_onehot(ctx.slots[1], table.shape[0])
+            with _WgradCtx(ctx.tab_side, gm, dtab):
+                # d_table[t, :] += sum over the slots of type t of gm[slot, :]   (split-K over the edges)
+                _gemm_raw(GT_BF16, oh.data_ptr(), 1, r_pad, gm.data_ptr(), 1, ld, dtab.data_ptr(), ld, table.shape[0], d, plan.E, d,
+                          None, None, 0, EPI_ACCUM | EPI_OUT_F32)
+        elif split:
             src_t, dst_t, type_t, _ = plan.edges_by_type(plan._edge_index, etype, table.shape[0])
             # on the side stream only when the consumer of dtab (the embed_sum backward of the table) runs there too
             with _WgradCtx(ctx.tab_side, x, g, dtab):

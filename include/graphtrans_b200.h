@@ -123,7 +123,10 @@ int gt_aggregate_bwd(int dt, int conv, const void* x, const void* dout, void* dx
                      const float* edge_b, const int32_t* etype, const float* table, int32_t ntypes,
                      const float* self_param,
                      float* d_edge_w, float* d_edge_b, float* d_table, float* d_self, const float* norm_slot,
-                     const int32_t* etype_slot, const float* attr_slot, void* stream);
+                     const int32_t* etype_slot, const float* attr_slot, void* gm_out, void* stream);
+/* gm_out (optional, activation dtype [E, ld], source-sorted slot order = dst_by_src order): per-edge masked message
+ * gradient norm_e * dout[dst_e] * 1[x[src_e] + ee_e > 0].  With it the edge-TABLE gradient is the contraction
+ * d_table = OneHot(etype_slot)^T . gm (gt_onehot + gt_gemm) instead of gt_aggregate_table_grad's second gather pass. */
 /* per-CSR-slot copies of the per-edge data, computed once per batch and reused by every layer (optional; NULL
  * arguments to gt_aggregate_* mean "follow the indirection in-kernel").  For the CSR given by (rowptr_slot, nbr_slot,
  * eid_slot) - target-sorted for the forward, source-sorted for the adjoint: norm_slot[p] = GCN norm of the edge in
