@@ -281,7 +281,9 @@ def hot_kernel_roofline(args, model, b, hb, ns, step_ms):
         out.append({"kernel": "gt_aggregate_table_grad (k_agg_table_grad, weight-gradient stream)", "bound": "hbm", "achieved": ach_t,
                     "peak": pk["hbm"], "unit": "GB/s", "frac": ach_t / pk["hbm"], "traffic": None, "avg_launch_us": ms_t * 1e3,
                     "share_of_step": None, "algorithmic_bytes_per_launch": tg_bytes, "peak_source": pk["source"],
-                    "note": "gather formulation: 2 E d_g s + 12 E bytes (x[src], dout[dst], sorted edge triples); L2-resident rows"})
+                    "note": "gather formulation: 2 E d_g s + 12 E bytes (x[src], dout[dst], sorted edge triples); L2-resident rows. "
+                            "The bf16 step no longer launches it (the adjoint writes the per-edge gradient and the table "
+                            "gradient is a one-hot contraction, GT_TABLE_GRAD_GEMM=1); it remains the fp32 / small-batch path"})
     # stage 2: masked MHA fwd + bwd over the packed tokens (one encoder layer)
     d, nh = args.d_model, args.nhead
     qkv = torch.randn(plan.n_rows, 3 * d, device=b.batch.device).to(act).requires_grad_(True)

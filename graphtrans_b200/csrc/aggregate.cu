@@ -807,7 +807,7 @@ k_agg_fwd3(const T* __restrict__ x, T* __restrict__ out, int N, int d, int ld,
 // visits (its channel vector is fixed), meet in shared memory once per block and leave as one global atomic per
 // (block, element).  The edge-TABLE gradient is the separate type-sorted kernel (gt_aggregate_table_grad).
 template <typename T, int CONV, int EK, int KD>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, EK == GT_EDGE_LINEAR ? 1 : 3)     // table / no encoder: three blocks per SM
 k_agg_bwd3(const T* __restrict__ x, const T* __restrict__ dout, T* __restrict__ dx, int N, int d, int ld,
            const int32_t* __restrict__ rp_src, const int32_t* __restrict__ dst_by_src,
            const int32_t* __restrict__ eid_by_src, EdgeEnc en, const float* __restrict__ self_param,

@@ -1,5 +1,5 @@
+# scratch command file for `gpurun -- 'bash tools/_run.sh'` (what the last GPU call of the session ran)
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -q -m gpu -x 2>&1 | grep -v "^frame" | tail -40 | grep -E "passed|failed|Error|assert|^E " > gpurun_out/tests_gpu.log
-cat gpurun_out/tests_gpu.log
-for v in 1 0; do echo "tabgemm=$v $(GT_TABLE_GRAD_GEMM=$v python tools/graph_trace.py molpcba 2>&1 | head -1 | cut -c1-60)"; done
-for v in 1 0; do echo "syn tabgemm=$v $(GT_TABLE_GRAD_GEMM=$v python bench.py --config syn --steps 6 --warmup 3 --no-cpu-baseline --no-roofline --no-e2e --no-optimizer 2>&1 | grep -o '"ms_per_step": [0-9.]*')"; done
+timeout 300 python -m pytest tests -q -m gpu -x 2>&1 | grep -E "passed|failed|Error|^E " | tail -3
+python bench.py > gpurun_out/r01_bench_molpcba_v9.log 2>&1
+python bench.py --config syn --steps 8 --warmup 3 --no-cpu-baseline --no-e2e --no-optimizer > gpurun_out/r01_bench_syn_v9b.log 2>&1
