@@ -476,7 +476,7 @@ def main_b200(ns):
                     "finite_loss": bool(torch.isfinite(loss_t).item())}
 
     cpu = None
-    if not ns.no_cpu_baseline and rank == 0:
+    if not ns.no_cpu_baseline and rank == 0 and world == 1:      # reported at N = 1 only (the other ranks would idle)
         gps, ms, desc = cpu_reference_run(ns, 3, 1)
         cpu = {"value": gps, "unit": UNIT, "cores": desc["cores"], "kind": desc["kind"], "sample": desc["sample"],
                "ms_per_step": ms}
