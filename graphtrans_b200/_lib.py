@@ -42,17 +42,18 @@ SIGNATURES = {
     "gt_segment_sum": [I, P, P, L, I32, P, P],
     "gt_segment_sum_sorted": [I, P, P, L, I32, P, P, P],
     "gt_add_graph_vec": [I, P, P, P, L, I32, P, P],
-    "gt_colstats": [I, P, L, I32, P, P],
+    "gt_colstats": [I, P, L, I32, P, P, P],
     "gt_bn_finalize": [P, L, I32, I32, P, P, P, P, P, F, F, I, P, P],
     "gt_bn_apply_fwd": [I, P, L, I32, I32, P, I, P, P, P, P, F, P, U64, P],
-    "gt_bn_norm_fwd": [I, P, L, I32, I32, P, P, P, P, P, P, F, F, I, I, P, P, P, P, P, F, P, U64, P],
-    "gt_bn_bwd_reduce": [I, P, P, L, I32, I32, P, I, P, F, P, U64, P],
-    "gt_bn_bwd_apply": [I, P, P, L, I32, I32, P, P, I, I, P, P, P, P, F, P, U64, P],
+    "gt_bn_norm_fwd": [I, P, L, I32, I32, P, P, P, P, P, P, F, F, I, I, P, P, P, P, P, F, P, U64, P, P],
+    "gt_bn_bwd_reduce": [I, P, P, L, I32, I32, P, I, P, F, P, U64, P, P],
+    "gt_bn_bwd_apply": [I, P, P, L, I32, I32, P, P, I, I, P, P, P, P, F, P, U64, P, P],
     "gt_gemm": [I, P, I, L, P, I, L, P, L, L, L, L, L, P, P, L, I, F, P, U64, I, P],
-    "gt_gemm_stats": [I, P, I, L, P, I, L, P, L, L, L, L, L, P, P, L, I, F, P, U64, I, P, P],
+    "gt_gemm_stats": [I, P, I, L, P, I, L, P, L, L, L, L, L, P, P, L, I, F, P, U64, I, P, P, P],
     "gt_relu_bwd": [I, P, P, L, P, F, P],
     "gt_colsum": [I, P, L, L, L, P, P],
     "gt_cast_multi": [P, I32, L, P],
+    "gt_add_blocks": [P, I32, I32, P, P, P, P, P, P, P],
     "gt_cast_pad": [I, P, L, L, L, I, P, L, L, L, P],
     "gt_layernorm_fwd": [I, P, P, P, P, L, I32, P, P, F, P, P, P, F, P, U64, P],
     "gt_layernorm_bwd": [I, P, P, P, P, L, I32, P, P, P, P, P, P, F, P, U64, P],
@@ -70,7 +71,13 @@ SIGNATURES = {
     "gt_bce_masked_bwd": [P, P, L, I32, L, L, P, P, P, L, I32, P],
     "gt_ce_fwd": [P, P, L, L, I32, L, P, P, P, P],
     "gt_ce_bwd": [P, P, L, L, I32, L, P, P, P, L, I32, P],
-    "gt_adamw_multi": [P, I32, L, P, P, P, P, P, P],
+    "gt_mha_cls_fwd": [I, P, P, P, P, L, L, I32, I32, F, P, P, F, P, U64, P],
+    "gt_mha_cls_bwd": [I, P, P, P, P, P, P, P, L, L, I32, I32, F, P, P, F, P, U64, P],
+    "gt_adamw_multi": [P, I32, L, P, P, P, P, P, P, P],
+    "gt_sumsq": [P, L, P, P],
+    "gt_segment_pool_fwd": [I, I, P, P, L, I32, P, P, P],
+    "gt_segment_pool_bwd": [I, I, P, P, P, P, L, I32, P, P],
+    "gt_argmax_rows": [P, L, I32, L, P, P],
     "gt_pna_reduce_fwd": [I, P, P, P, L, I32, I32, I32, P, P, F, P, I32, P, P, P],
     "gt_pna_reduce_bwd": [I, P, P, P, L, I32, I32, I32, I32, P, P, F, P, P, P, P, P, P],
 }

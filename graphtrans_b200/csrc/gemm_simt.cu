@@ -11,7 +11,7 @@ namespace gt {
 int gemm_tc_launch(int dt, const void* A, int a_mn, int64_t lda, const void* B, int b_mn, int64_t ldb, void* C,
                    int64_t ldc, int64_t M, int64_t N, int64_t K, int64_t n_fill, const float* bias,
                    const void* resid, int64_t ldr, int flags, float drop_p, const uint64_t* rng, uint64_t salt,
-                   double* col_stats, int* stats_fused, cudaStream_t st);  // gemm_tc.cu; -2 = not eligible
+                   double* col_stats, const int32_t* m_valid, int* stats_fused, cudaStream_t st);  // gemm_tc.cu; -2 = not eligible
 
 constexpr int SBM = 64, SBN = 64, SBK = 16;
 
@@ -141,12 +141,12 @@ static int launch_simt(const T* A, int a_mn, int64_t lda, const T* B, int b_mn, 
 
 using namespace gt;
 
-extern "C" int gt_colstats(int dt, const void* x, int64_t M, int32_t ld, double* stats, void* stream);
+extern "C" int gt_colstats(int dt, const void* x, int64_t M, int32_t ld, double* stats, const int32_t* m_valid, void* stream);
 
 static int gemm_dispatch(int dt, const void* A, int a_mn, int64_t lda, const void* B, int b_mn, int64_t ldb, void* C,
                          int64_t ldc, int64_t M, int64_t N, int64_t K, int64_t n_fill, const float* bias,
                          const void* resid, int64_t ldr, int flags, float drop_p, const uint64_t* rng_state, uint64_t salt,
-                         int impl, double* col_stats, void* stream) {
+                         int impl, double* col_stats, const int32_t* m_valid, void* stream) {
     GT_CHECK_ARG(M > 0 && N > 0 && K > 0, "gt_gemm: bad shape M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
     GT_CHECK_ARG(!(flags & GT_EPI_ACCUM) || (flags & GT_EPI_OUT_F32) || dt == GT_F32, "gt_gemm: ACCUM needs an fp32 C");
     GT_CHECK_ARG(!((flags & GT_EPI_ACCUM) && (flags & GT_EPI_RELU)), "gt_gemm: ACCUM and RELU are exclusive");
@@ -156,14 +156,14 @@ static int gemm_dispatch(int dt, const void* A, int a_mn, int64_t lda, const voi
     const int dt_out = (flags & GT_EPI_OUT_F32) ? GT_F32 : dt;
     if (impl != 1) {
         int fused = 0;
-        const int r = gemm_tc_launch(dt, A, a_mn, lda, B, b_mn, ldb, C, ldc, M, N, K, n_fill, bias, resid, ldr, flags, drop_p, rng_state, salt, col_stats, &fused, st);
-        if (r == 0 && col_stats && !fused) return gt_colstats(dt_out, C, M, (int32_t)ldc, col_stats, stream);
+        const int r = gemm_tc_launch(dt, A, a_mn, lda, B, b_mn, ldb, C, ldc, M, N, K, n_fill, bias, resid, ldr, flags, drop_p, rng_state, salt, col_stats, m_valid, &fused, st);
+        if (r == 0 && col_stats && !fused) return gt_colstats(dt_out, C, M, (int32_t)ldc, col_stats, m_valid, stream);
         if (r != -2) return r;
         GT_CHECK_ARG(impl != 2, "gt_gemm: shape/layout not eligible for the tcgen05 kernel (%s)", gt_last_error());
     }
     GT_DISPATCH_DT(dt, launch_simt<T>((const T*)A, a_mn, lda, (const T*)B, b_mn, ldb, C, ldc, M, N, K, n_fill, bias, resid, ldr, flags, drop_p, rng_state, salt, st));
     GT_LAUNCH_CHECK("gt_gemm(simt)");
-    if (col_stats) return gt_colstats(dt_out, C, M, (int32_t)ldc, col_stats, stream);
+    if (col_stats) return gt_colstats(dt_out, C, M, (int32_t)ldc, col_stats, m_valid, stream);
     return 0;
 }
 
@@ -172,14 +172,14 @@ extern "C" int gt_gemm(int dt, const void* A, int a_mn, int64_t lda, const void*
                        const void* resid, int64_t ldr, int flags, float drop_p, const uint64_t* rng_state, uint64_t salt,
                        int impl, void* stream) {
     return gemm_dispatch(dt, A, a_mn, lda, B, b_mn, ldb, C, ldc, M, N, K, n_fill, bias, resid, ldr, flags, drop_p, rng_state, salt,
-                         impl, nullptr, stream);
+                         impl, nullptr, nullptr, stream);
 }
 
 extern "C" int gt_gemm_stats(int dt, const void* A, int a_mn, int64_t lda, const void* B, int b_mn, int64_t ldb, void* C,
                              int64_t ldc, int64_t M, int64_t N, int64_t K, int64_t n_fill, const float* bias,
                              const void* resid, int64_t ldr, int flags, float drop_p, const uint64_t* rng_state, uint64_t salt,
-                             int impl, double* col_stats, void* stream) {
+                             int impl, double* col_stats, const int32_t* m_valid, void* stream) {
     GT_CHECK_ARG(col_stats != nullptr, "gt_gemm_stats: col_stats is NULL");
     return gemm_dispatch(dt, A, a_mn, lda, B, b_mn, ldb, C, ldc, M, N, K, n_fill, bias, resid, ldr, flags, drop_p, rng_state, salt,
-                         impl, col_stats, stream);
+                         impl, col_stats, m_valid, stream);
 }

@@ -53,6 +53,7 @@ struct Params {
     uint32_t idesc, tmem_cols, acc_stride;
     unsigned long long* trace;           // debug (GT_GEMM_TRACE=1): clock64 stamps of CTA 0's phases, else NULL
     double* col_stats;                   // optional [2][ldc]: += column sums / sums of squares of the stored C (BatchNorm)
+    const int32_t* m_valid;              // optional: only rows < m_valid[0] enter col_stats (shape-bucket slack rows)
 };
 
 #define GT_TRACE(slot) do { if (p.trace && blockIdx.x == 0) p.trace[slot] = (unsigned long long)clock64(); } while (0)
@@ -267,7 +268,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUt
                         // memory and ONE warp issues the fp64 atomics (one per (tile, column) instead of four: the
                         // L2 atomics on ~1200 addresses are what this costs) - replaces the separate gt_colstats
                         // pass over C.  Rows beyond M hold bias-only garbage and are skipped.
-                        const int rows_valid = min(32, p.M - (m0 + q * 32));        // warp-uniform
+                        const int m_lim = p.m_valid ? min(p.M, max(__ldg(p.m_valid), 1)) : p.M;
+                        const int rows_valid = min(32, m_lim - (m0 + q * 32));      // warp-uniform
                         float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
                         for (int rr = 0; rr < rows_valid; ++rr) {
                             uint32_t u;
@@ -461,7 +463,7 @@ static unsigned long long* g_trace_buf = nullptr;
 // returns 0 ok, -2 = shape/layout/dtype not eligible (caller falls back to the CUDA-core kernel), >0 CUDA error
 int gemm_tc_launch(int dt, const void* A, int a_mn, int64_t lda, const void* B, int b_mn, int64_t ldb, void* C, int64_t ldc,
                    int64_t M, int64_t N, int64_t K, int64_t n_fill, const float* bias, const void* resid, int64_t ldr, int flags,
-                   float drop_p, const uint64_t* rng, uint64_t salt, double* col_stats, int* stats_fused, cudaStream_t st) {
+                   float drop_p, const uint64_t* rng, uint64_t salt, double* col_stats, const int32_t* m_valid, int* stats_fused, cudaStream_t st) {
     if (stats_fused) *stats_fused = 0;
     using namespace tc;
     if (dt != GT_BF16) { set_error("tcgen05 GEMM takes bf16 operands"); return -2; }
@@ -537,6 +539,7 @@ int gemm_tc_launch(int dt, const void* A, int a_mn, int64_t lda, const void* B, 
     p.trace = trace_on ? trace_buf : nullptr;
     // column statistics ride in the TMA-store epilogue of a bf16, non-accumulating output
     p.col_stats = (col_stats && p.tma_store && out_bf16 && !accum) ? col_stats : nullptr;
+    p.m_valid = m_valid;
     if (stats_fused) *stats_fused = p.col_stats != nullptr;
 
     cudaError_t e;

@@ -169,9 +169,13 @@ k_ebt_fill(const int64_t* __restrict__ ei, const int32_t* __restrict__ etype, in
 __global__ void k_plan_bounds(const int64_t* __restrict__ batch, int64_t N, int64_t B, int32_t* node_off,
                               int32_t* node_graph) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t g = batch[i];
-        node_graph[i] = (int32_t)g;
-        if (i == 0 || batch[i - 1] != g) node_off[g] = (int32_t)i;
+        // ids >= B mark trailing shape-bucket slack nodes (graphtrans_b200.loader.pad_to_bucket): they belong to no
+        // graph (node_graph = -1, no tokens); node_off[B] = first slack node = number of real nodes
+        const int64_t g = batch[i] < B ? batch[i] : B;
+        node_graph[i] = g < B ? (int32_t)g : -1;
+        if (i == 0 || batch[i - 1] != batch[i]) {
+            if (g < B || i == 0 || batch[i - 1] < B) node_off[g] = (int32_t)i;
+        }
     }
 }
 
@@ -182,7 +186,7 @@ __global__ void k_plan_scan(int64_t N, int64_t B, int64_t L, int cls, int32_t* n
     __shared__ int32_t carry_s, max_s;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) {
-        node_off[B] = (int32_t)N;
+        if (node_off[B] < 0) node_off[B] = (int32_t)N;
         for (int64_t g = B - 1; g >= 0; --g)
             if (node_off[g] < 0) node_off[g] = node_off[g + 1];
         carry_s = 0;
@@ -265,9 +269,13 @@ __global__ void k_plan_maps(int64_t N, int64_t B, int cls, const int32_t* __rest
         }
         if (t < N) {
             const int32_t g = node_graph[t];
-            const int32_t n = node_off[g + 1] - node_off[g], k = kept[g];
-            const int32_t local = (int32_t)t - node_off[g], skip = n - k;
-            node2tok[t] = local >= skip ? tok_off[g] + local - skip : -1;
+            if (g < 0) {
+                node2tok[t] = -1;
+            } else {
+                const int32_t n = node_off[g + 1] - node_off[g], k = kept[g];
+                const int32_t local = (int32_t)t - node_off[g], skip = n - k;
+                node2tok[t] = local >= skip ? tok_off[g] + local - skip : -1;
+            }
         }
     }
 }

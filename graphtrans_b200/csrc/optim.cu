@@ -14,7 +14,7 @@ __global__ void k_adamw_advance(int64_t* step) { step[0] += 1; }
 // desc[i] = {param pointer, arena offset (elements), numel, first block}
 __global__ void __launch_bounds__(256)
 k_adamw_multi(const int64_t* __restrict__ desc, int n, const float* __restrict__ grad, float* __restrict__ m, float* __restrict__ v,
-              const float* __restrict__ hyper, const int64_t* __restrict__ step) {
+              const float* __restrict__ hyper, const int64_t* __restrict__ step, const float* __restrict__ clip) {
     int lo = 0, hi = n;   // largest i with desc[i].first_block <= blockIdx.x
     while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
@@ -28,11 +28,15 @@ k_adamw_multi(const int64_t* __restrict__ desc, int n, const float* __restrict__
     const float t = (float)step[0];
     const float bc1 = 1.f - powf(b1, t), bc2_sqrt = sqrtf(1.f - powf(b2, t));
     const float step_size = lr / bc1, decay = 1.f - lr * wd;
+    // clip_grad_norm_(parameters, max_norm) of reference trainers/base_trainer.py:34-35 folded into the gradient read:
+    // clip = {max_norm, sum of squares of the whole arena (gt_sumsq)}; coefficient = min(1, max_norm / (norm + 1e-6))
+    float gscale = 1.f;
+    if (clip && clip[0] > 0.f) gscale = fminf(1.f, clip[0] / (sqrtf(clip[1]) + 1e-6f));
 #pragma unroll
     for (int k = 0; k < ADAM_PER_BLOCK / 256; ++k) {
         const int64_t i = base + k * 256 + threadIdx.x;
         if (i < numel) {
-            const float g = grad[off + i];
+            const float g = grad[off + i] * gscale;
             const float mi = b1 * m[off + i] + (1.f - b1) * g;
             const float vi = b2 * v[off + i] + (1.f - b2) * g * g;
             m[off + i] = mi;
@@ -48,12 +52,12 @@ k_adamw_multi(const int64_t* __restrict__ desc, int n, const float* __restrict__
 using namespace gt;
 
 extern "C" int gt_adamw_multi(const int64_t* desc_dev, int32_t n, int64_t total_blocks, const float* grad_flat, float* m_flat,
-                              float* v_flat, const float* hyper_dev, int64_t* step_dev, void* stream) {
+                              float* v_flat, const float* hyper_dev, int64_t* step_dev, const float* clip_dev, void* stream) {
     GT_CHECK_ARG(desc_dev && n > 0 && total_blocks > 0 && total_blocks < (1ll << 31) && grad_flat && m_flat && v_flat && hyper_dev && step_dev,
                  "gt_adamw_multi: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     k_adamw_advance<<<1, 1, 0, st>>>(step_dev);
-    k_adamw_multi<<<(unsigned)total_blocks, 256, 0, st>>>(desc_dev, n, grad_flat, m_flat, v_flat, hyper_dev, step_dev);
+    k_adamw_multi<<<(unsigned)total_blocks, 256, 0, st>>>(desc_dev, n, grad_flat, m_flat, v_flat, hyper_dev, step_dev, clip_dev);
     GT_LAUNCH_CHECK("gt_adamw_multi");
     return 0;
 }

@@ -90,9 +90,12 @@ __global__ void k_add_graph_vec(const T* __restrict__ x, const float* __restrict
         const int c0 = (int)(i - r * vpr) * 4;
         float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4];
         if (x) ld4(x + r * ld + c0, a);
-        ld4(v + (int64_t)node_graph[r] * ld + c0, b);
+        const int g = node_graph[r];
+        if (g >= 0) {      // g < 0: shape-bucket slack node (belongs to no graph)
+            ld4(v + (int64_t)g * ld + c0, b);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) a[q] += b[q];
+            for (int q = 0; q < 4; ++q) a[q] += b[q];
+        }
         st4(y + r * ld + c0, a);
     }
 }
@@ -105,6 +108,13 @@ __global__ void k_add_graph_vec(const T* __restrict__ x, const float* __restrict
 // shared-memory tree over the 8 row lanes, then ONE fp64 atomic per (block, channel) - deterministic enough for
 // statistics and ~300 blocks keep every SM busy.
 constexpr int STAT_TY = 8;
+// rows [m_valid[0], M) of a matrix may be shape-bucket slack (graphtrans_b200.graphed: batches padded up to a bucket so
+// that CUDA-graph signatures repeat): they take no part in the batch statistics and receive a zero gradient
+__device__ __forceinline__ int64_t valid_rows(const int32_t* __restrict__ m_valid, int64_t M) {
+    if (!m_valid) return M;
+    const int64_t v = (int64_t)m_valid[0];
+    return v < M ? (v > 0 ? v : 1) : M;
+}
 __device__ __forceinline__ void stat_flush(float (&s)[4], float (&s2)[4], int tx, int ty, int c0, int ld,
                                            double* __restrict__ out) {
     __shared__ float sh[2][STAT_TY][128 + 4];
@@ -125,11 +135,12 @@ __device__ __forceinline__ void stat_flush(float (&s)[4], float (&s2)[4], int tx
 
 template <typename T, bool SQ>
 __global__ void __launch_bounds__(256)
-k_colstats(const T* __restrict__ x, int64_t M, int ld, int64_t rows_per_block, double* __restrict__ stats) {
+k_colstats(const T* __restrict__ x, int64_t M, int ld, int64_t rows_per_block, double* __restrict__ stats,
+           const int32_t* __restrict__ m_valid) {
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int c0 = blockIdx.x * 128 + tx * 4;
     const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
-    const int64_t r1 = min(r0 + rows_per_block, M);
+    const int64_t r1 = min(r0 + rows_per_block, valid_rows(m_valid, M));
     float s[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
     if (c0 < ld) {
         for (int64_t r = r0 + ty; r < r1; r += STAT_TY) {
@@ -210,7 +221,7 @@ __global__ void k_bn_apply(const T* __restrict__ x, int64_t M, int ld, const flo
 #pragma unroll
             for (int q = 0; q < 4; ++q) v[q] += t[q];
         }
-        if (gvec) {
+        if (gvec && node_graph[r] >= 0) {
             float t[4];
             ld4(gvec + (int64_t)node_graph[r] * ld + c0, t);
 #pragma unroll
@@ -229,11 +240,13 @@ k_bn_norm_fwd(const T* __restrict__ x, int64_t M, int d, int ld, int64_t rows_pe
               const float* __restrict__ gamma, const float* __restrict__ beta, float* running_mean, float* running_var,
               int64_t* nbt, float momentum, float eps, int training, int relu, const T* __restrict__ resid,
               const float* __restrict__ gvec, const int32_t* __restrict__ node_graph, T* __restrict__ y,
-              float* __restrict__ ssmr, float drop_p, const uint64_t* __restrict__ rng, uint64_t salt) {
+              float* __restrict__ ssmr, float drop_p, const uint64_t* __restrict__ rng, uint64_t salt,
+              const int32_t* __restrict__ m_valid) {
     const Drop dr = make_drop(rng, salt, drop_p);
     const int vpr = ld / 4;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int c0 = blockIdx.x * 128 + tx * 4;
+    const int64_t Mv = valid_rows(m_valid, M);
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && training && nbt) *nbt += 1;
     if (c0 >= ld) return;
     float sc[4], sh[4];
@@ -244,13 +257,13 @@ k_bn_norm_fwd(const T* __restrict__ x, int64_t M, int d, int ld, int64_t rows_pe
         float scale = 0.f, shift = 0.f, mean = 0.f, rstd = 0.f;
         if (c < d) {
             if (training) {
-                const double mu = stats[c] / (double)M;
-                double var = stats[ld + c] / (double)M - mu * mu;
+                const double mu = stats[c] / (double)Mv;
+                double var = stats[ld + c] / (double)Mv - mu * mu;
                 if (var < 0) var = 0;
                 mean = (float)mu;
                 rstd = (float)(1.0 / sqrt(var + (double)eps));
                 if (writer && running_mean) {
-                    const double unb = M > 1 ? var * ((double)M / (double)(M - 1)) : var;
+                    const double unb = Mv > 1 ? var * ((double)Mv / (double)(Mv - 1)) : var;
                     running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
                     running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
                 }
@@ -290,7 +303,7 @@ k_bn_norm_fwd(const T* __restrict__ x, int64_t M, int d, int ld, int64_t rows_pe
 #pragma unroll
             for (int q = 0; q < 4; ++q) v[q] += t[q];
         }
-        if (gvec) {
+        if (gvec && node_graph[r] >= 0) {
             float t[4];
             ld4(gvec + (int64_t)node_graph[r] * ld + c0, t);
 #pragma unroll
@@ -304,13 +317,13 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 k_bn_bwd_reduce(const T* __restrict__ x, const T* __restrict__ dy, int64_t M, int ld, int64_t rows_per_block,
                 const float* __restrict__ ssmr, int relu, double* __restrict__ red, float drop_p,
-                const uint64_t* __restrict__ rng, uint64_t salt) {
+                const uint64_t* __restrict__ rng, uint64_t salt, const int32_t* __restrict__ m_valid) {
     const Drop dr = make_drop(rng, salt, drop_p);
     const int vpr = ld / 4;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int c0 = blockIdx.x * 128 + tx * 4;
     const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
-    const int64_t r1 = min(r0 + rows_per_block, M);
+    const int64_t r1 = min(r0 + rows_per_block, valid_rows(m_valid, M));
     float s[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
     if (c0 < ld) {
         float sc[4], sh[4], mu[4], rs[4];
@@ -342,14 +355,16 @@ __global__ void __launch_bounds__(256)
 k_bn_bwd_apply(const T* __restrict__ x, const T* __restrict__ dy, int64_t M, int d, int ld, int64_t rows_per_block,
                const float* __restrict__ ssmr, const float* __restrict__ gamma, int relu, int training,
                const double* __restrict__ red, T* __restrict__ dx, float* __restrict__ dgamma,
-               float* __restrict__ dbeta, float drop_p, const uint64_t* __restrict__ rng, uint64_t salt) {
+               float* __restrict__ dbeta, float drop_p, const uint64_t* __restrict__ rng, uint64_t salt,
+               const int32_t* __restrict__ m_valid) {
     const Drop dr = make_drop(rng, salt, drop_p);
     const int vpr = ld / 4;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int c0 = blockIdx.x * 128 + tx * 4;
     if (c0 >= ld) return;
     const int64_t r0 = (int64_t)blockIdx.y * rows_per_block, r1 = min(r0 + rows_per_block, M);
-    const float invM = 1.f / (float)M;
+    const int64_t Mv = valid_rows(m_valid, M);
+    const float invM = 1.f / (float)Mv;
     float sc[4], sh[4], mu[4], rs[4], m0[4], m1[4];
     ld4(ssmr + c0, sc);
     ld4(ssmr + ld + c0, sh);
@@ -362,6 +377,11 @@ k_bn_bwd_apply(const T* __restrict__ x, const T* __restrict__ dy, int64_t M, int
     }
     for (int64_t r = r0 + ty; r < r1; r += STAT_TY) {
         float v[4], g[4], o[4], ds[4];
+        if (r >= Mv) {      // bucket slack rows: no gradient
+            o[0] = o[1] = o[2] = o[3] = 0.f;
+            st4(dx + r * ld + c0, o);
+            continue;
+        }
         ld4(x + r * ld + c0, v);
         ld4(dy + r * ld + c0, g);
         drop4(dr, (uint64_t)(r * vpr + c0 / 4), ds);
@@ -483,9 +503,15 @@ k_bn_norm_fwd_slab(const T* __restrict__ x, int64_t M, int d, int ld, int tpr, i
                    const float* __restrict__ beta, float* running_mean, float* running_var, int64_t* nbt,
                    float momentum, float eps, int training, int relu, const T* __restrict__ resid,
                    const float* __restrict__ gvec, const int32_t* __restrict__ node_graph, T* __restrict__ y,
-                   float* __restrict__ ssmr, float drop_p, const uint64_t* __restrict__ rng, uint64_t salt) {
+                   float* __restrict__ ssmr, float drop_p, const uint64_t* __restrict__ rng, uint64_t salt,
+                   const int32_t* __restrict__ m_valid) {
     constexpr int V = VecW<T>::V;
     const Drop dr = make_drop(rng, salt, drop_p);
+    if (m_valid) {
+        const int64_t Mv = valid_rows(m_valid, M);
+        invM = 1.0 / (double)Mv;
+        unbias = Mv > 1 ? (double)Mv / (double)(Mv - 1) : 1.0;
+    }
     const int rr = threadIdx.x / tpr, c0 = (threadIdx.x - rr * tpr) * V;
     if (blockIdx.x == 0 && threadIdx.x == 0 && training && nbt) *nbt += 1;
     if (rr >= rpi) return;
@@ -518,7 +544,7 @@ k_bn_norm_fwd_slab(const T* __restrict__ x, int64_t M, int d, int ld, int tpr, i
 #pragma unroll
             for (int q = 0; q < V; ++q) v[q] += t[q];
         }
-        if (gvec) {
+        if (gvec && node_graph[r] >= 0) {
             const float* gp = gvec + (int64_t)node_graph[r] * ld + c0;
 #pragma unroll
             for (int h = 0; h < V / 4; ++h) {
@@ -927,32 +953,52 @@ __global__ void k_dropout(const T* __restrict__ x, int64_t n4, T* __restrict__ y
 
 __global__ void k_rng_advance(uint64_t* rng) { rng[1] += 1; }
 
-// one launch casting MANY fp32 parameter matrices to zero-padded bf16 operand copies.  desc (device, int64[6] per
-// tensor): src, dst, rows, cols, ld_dst, first block; a block converts 2048 consecutive destination elements.
+// one launch casting MANY fp32 parameter matrices to zero-padded bf16 operand copies.  desc (device, int64[8] per
+// tensor): src, dst, rows, cols, ld_dst, first block, ld_src (0 = cols: contiguous source), width (0 = ld_dst: columns
+// written per destination row; width < ld_dst writes a sub-block of a larger matrix, e.g. one diagonal block of the
+// PNA tower operands); a block converts 2048 consecutive (row, column < width) elements.
 constexpr int CASTM_PER_BLOCK = 2048;
+constexpr int CASTM_FIELDS = 8;
 __global__ void __launch_bounds__(256)
 k_cast_multi(const int64_t* __restrict__ desc, int n) {
     int lo = 0, hi = n;   // largest i with desc[i].first_block <= blockIdx.x
     while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
-        if (desc[mid * 6 + 5] <= (int64_t)blockIdx.x) lo = mid; else hi = mid;
+        if (desc[mid * CASTM_FIELDS + 5] <= (int64_t)blockIdx.x) lo = mid; else hi = mid;
     }
-    const int64_t* dsc = desc + lo * 6;
+    const int64_t* dsc = desc + lo * CASTM_FIELDS;
     const float* src = reinterpret_cast<const float*>(dsc[0]);
     bf16* dst = reinterpret_cast<bf16*>(dsc[1]);
     const bool keep_f32 = dsc[4] < 0;                       // ld < 0: fp32 destination (stacked bias vectors)
     const int64_t rows = dsc[2], cols = dsc[3], ld = keep_f32 ? -dsc[4] : dsc[4];
+    const int64_t ld_src = dsc[6] ? dsc[6] : cols, width = dsc[7] ? dsc[7] : ld;
     const int64_t base = ((int64_t)blockIdx.x - dsc[5]) * CASTM_PER_BLOCK;
-    const int64_t total = rows * ld;
+    const int64_t total = rows * width;
 #pragma unroll
     for (int k = 0; k < CASTM_PER_BLOCK / 256; ++k) {
         const int64_t i = base + k * 256 + threadIdx.x;
         if (i < total) {
-            const int64_t r = i / ld, c = i - r * ld;
-            const float v = c < cols ? src[r * cols + c] : 0.f;
-            if (keep_f32) reinterpret_cast<float*>(dst)[i] = v;
-            else dst[i] = __float2bfloat16_rn(v);
+            const int64_t r = i / width, c = i - r * width;
+            const float v = c < cols ? src[r * ld_src + c] : 0.f;
+            if (keep_f32) reinterpret_cast<float*>(dst)[r * ld + c] = v;
+            else dst[r * ld + c] = __float2bfloat16_rn(v);
         }
+    }
+}
+
+// dst_b[r, c] += src[r0_b + r, c0_b + c] for up to 16 rectangular blocks of one fp32 matrix (gradients of the diagonal
+// blocks of a block-diagonal operand, added into the per-tower parameter gradients)
+struct AddBlocks {
+    float* dst[16];
+    int ld_dst[16], r0[16], c0[16], rows[16], cols[16];
+    int n;
+};
+__global__ void k_add_blocks(AddBlocks ab, const float* __restrict__ src, int ld_src) {
+    const int b = blockIdx.y;
+    const int total = ab.rows[b] * ab.cols[b];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int r = i / ab.cols[b], c = i - r * ab.cols[b];
+        ab.dst[b][(int64_t)r * ab.ld_dst[b] + c] += src[(int64_t)(ab.r0[b] + r) * ld_src + ab.c0[b] + c];
     }
 }
 
@@ -1086,11 +1132,11 @@ extern "C" int gt_add_graph_vec(int dt, const void* x, const float* v, const int
     return 0;
 }
 
-extern "C" int gt_colstats(int dt, const void* x, int64_t M, int32_t ld, double* stats, void* stream) {
+extern "C" int gt_colstats(int dt, const void* x, int64_t M, int32_t ld, double* stats, const int32_t* m_valid, void* stream) {
     GT_CHECK_ARG(M > 0 && ld > 0 && ld % 4 == 0, "gt_colstats: bad shape");
     int64_t rpb;
     const dim3 grid = stat_grid(M, ld, &rpb);
-    GT_DISPATCH_DT(dt, (k_colstats<T, true><<<grid, 256, 0, ST>>>((const T*)x, M, ld, rpb, stats)));
+    GT_DISPATCH_DT(dt, (k_colstats<T, true><<<grid, 256, 0, ST>>>((const T*)x, M, ld, rpb, stats, m_valid)));
     GT_LAUNCH_CHECK("gt_colstats");
     return 0;
 }
@@ -1120,31 +1166,31 @@ extern "C" int gt_bn_norm_fwd(int dt, const void* x, int64_t M, int32_t d, int32
                               const float* gamma, const float* beta, float* running_mean, float* running_var,
                               int64_t* nbt, float momentum, float eps, int training, int relu, const void* resid,
                               const float* gvec, const int32_t* node_graph, void* y, float* ssmr, float drop_p,
-                              const uint64_t* rng_state, uint64_t salt, void* stream) {
+                              const uint64_t* rng_state, uint64_t salt, const int32_t* m_valid, void* stream) {
     GT_CHECK_ARG(M > 0 && d > 0 && ld >= d && ld % 4 == 0, "gt_bn_norm_fwd: bad shape");
     GT_CHECK_ARG(training ? stats != nullptr : (running_mean && running_var), "gt_bn_norm_fwd: missing statistics");
     GT_CHECK_ARG(!gvec || node_graph, "gt_bn_norm_fwd: gvec needs node_graph");
     Slab sl;
     if (slab_cfg(dt, M, ld, {x, y, resid, gvec, ssmr}, &sl)) {
         const double invM = 1.0 / (double)M, unbias = M > 1 ? (double)M / (double)(M - 1) : 1.0;
-        GT_DISPATCH_DT(dt, (k_bn_norm_fwd_slab<T><<<sl.grid, SLAB_THREADS, 0, ST>>>((const T*)x, M, d, ld, sl.tpr, sl.rpi, sl.rows_per_block, invM, unbias, stats, gamma, beta, running_mean, running_var, nbt, momentum, eps, training, relu, (const T*)resid, gvec, node_graph, (T*)y, ssmr, drop_p, rng_state, salt)));
+        GT_DISPATCH_DT(dt, (k_bn_norm_fwd_slab<T><<<sl.grid, SLAB_THREADS, 0, ST>>>((const T*)x, M, d, ld, sl.tpr, sl.rpi, sl.rows_per_block, invM, unbias, stats, gamma, beta, running_mean, running_var, nbt, momentum, eps, training, relu, (const T*)resid, gvec, node_graph, (T*)y, ssmr, drop_p, rng_state, salt, m_valid)));
         GT_LAUNCH_CHECK("gt_bn_norm_fwd");
         return 0;
     }
     int64_t rpb;
     const dim3 grid = stat_grid(M, ld, &rpb);
-    GT_DISPATCH_DT(dt, (k_bn_norm_fwd<T><<<grid, 256, 0, ST>>>((const T*)x, M, d, ld, rpb, stats, gamma, beta, running_mean, running_var, nbt, momentum, eps, training, relu, (const T*)resid, gvec, node_graph, (T*)y, ssmr, drop_p, rng_state, salt)));
+    GT_DISPATCH_DT(dt, (k_bn_norm_fwd<T><<<grid, 256, 0, ST>>>((const T*)x, M, d, ld, rpb, stats, gamma, beta, running_mean, running_var, nbt, momentum, eps, training, relu, (const T*)resid, gvec, node_graph, (T*)y, ssmr, drop_p, rng_state, salt, m_valid)));
     GT_LAUNCH_CHECK("gt_bn_norm_fwd");
     return 0;
 }
 
 extern "C" int gt_bn_bwd_reduce(int dt, const void* x, const void* dy, int64_t M, int32_t d, int32_t ld,
                                 const float* ssmr, int relu, double* red, float drop_p,
-                                const uint64_t* rng_state, uint64_t salt, void* stream) {
+                                const uint64_t* rng_state, uint64_t salt, const int32_t* m_valid, void* stream) {
     GT_CHECK_ARG(M > 0 && ld >= d && ld % 4 == 0, "gt_bn_bwd_reduce: bad shape");
     int64_t rpb;
     const dim3 grid = stat_grid(M, ld, &rpb);
-    GT_DISPATCH_DT(dt, (k_bn_bwd_reduce<T><<<grid, 256, 0, ST>>>((const T*)x, (const T*)dy, M, ld, rpb, ssmr, relu, red, drop_p, rng_state, salt)));
+    GT_DISPATCH_DT(dt, (k_bn_bwd_reduce<T><<<grid, 256, 0, ST>>>((const T*)x, (const T*)dy, M, ld, rpb, ssmr, relu, red, drop_p, rng_state, salt, m_valid)));
     GT_LAUNCH_CHECK("gt_bn_bwd_reduce");
     return 0;
 }
@@ -1152,11 +1198,11 @@ extern "C" int gt_bn_bwd_reduce(int dt, const void* x, const void* dy, int64_t M
 extern "C" int gt_bn_bwd_apply(int dt, const void* x, const void* dy, int64_t M, int32_t d, int32_t ld,
                                const float* ssmr, const float* gamma, int relu, int training, const double* red,
                                void* dx, float* dgamma, float* dbeta, float drop_p, const uint64_t* rng_state,
-                               uint64_t salt, void* stream) {
+                               uint64_t salt, const int32_t* m_valid, void* stream) {
     GT_CHECK_ARG(M > 0 && ld >= d && ld % 4 == 0, "gt_bn_bwd_apply: bad shape");
     int64_t rpb;
     const dim3 grid = stat_grid(M, ld, &rpb);
-    GT_DISPATCH_DT(dt, (k_bn_bwd_apply<T><<<grid, 256, 0, ST>>>((const T*)x, (const T*)dy, M, d, ld, rpb, ssmr, gamma, relu, training, red, (T*)dx, dgamma, dbeta, drop_p, rng_state, salt)));
+    GT_DISPATCH_DT(dt, (k_bn_bwd_apply<T><<<grid, 256, 0, ST>>>((const T*)x, (const T*)dy, M, d, ld, rpb, ssmr, gamma, relu, training, red, (T*)dx, dgamma, dbeta, drop_p, rng_state, salt, m_valid)));
     GT_LAUNCH_CHECK("gt_bn_bwd_apply");
     return 0;
 }
@@ -1364,6 +1410,25 @@ extern "C" int gt_cast_pad(int dt_in, const void* src, int64_t rows_in, int64_t 
     if (dt_in == GT_F32) cast_pad_out<float>(dt_out, (const float*)src, rows_in, cols_in, ld_in, dst, rows_out, cols_out, ld_out, ST);
     else cast_pad_out<bf16>(dt_out, (const bf16*)src, rows_in, cols_in, ld_in, dst, rows_out, cols_out, ld_out, ST);
     GT_LAUNCH_CHECK("gt_cast_pad");
+    return 0;
+}
+
+extern "C" int gt_add_blocks(const float* src, int32_t ld_src, int32_t n, float* const* dst_host, const int32_t* ld_dst_host,
+                             const int32_t* r0_host, const int32_t* c0_host, const int32_t* rows_host, const int32_t* cols_host,
+                             void* stream) {
+    GT_CHECK_ARG(src && n > 0 && n <= 16, "gt_add_blocks: 1..16 blocks");
+    AddBlocks ab;
+    ab.n = n;
+    int maxel = 1;
+    for (int b = 0; b < n; ++b) {
+        ab.dst[b] = dst_host[b]; ab.ld_dst[b] = ld_dst_host[b]; ab.r0[b] = r0_host[b]; ab.c0[b] = c0_host[b];
+        ab.rows[b] = rows_host[b]; ab.cols[b] = cols_host[b];
+        GT_CHECK_ARG(ab.dst[b] && ab.rows[b] >= 0 && ab.cols[b] >= 0, "gt_add_blocks: bad block %d", b);
+        if (ab.rows[b] * ab.cols[b] > maxel) maxel = ab.rows[b] * ab.cols[b];
+    }
+    dim3 grid((unsigned)blocks_for(maxel, 256, 64), (unsigned)n, 1);
+    k_add_blocks<<<grid, 256, 0, ST>>>(ab, src, ld_src);
+    GT_LAUNCH_CHECK("gt_add_blocks");
     return 0;
 }
 

@@ -7,7 +7,14 @@ rank's shard, BatchNorm statistics stay local (plain DistributedDataParallel beh
 SURVEY §8e.  There is no data-path collective: graphs are independent units.
 
 Works with any torch.distributed backend ('nccl' on GPUs; 'gloo' in the CPU tests of the bucket
-logic, where AVG is emulated by SUM + scale).
+logic, where AVG is emulated by SUM + scale).  With `direct=True` (CUDA ranks) the reductions are issued through
+graphtrans_b200.nccl on the comm stream, which makes them capturable: GraphedStep records one ncclAllReduce node per
+bucket inside the CUDA graph of the step, forked off the backward at the point where the bucket's last gradient has
+been produced, so the transfer overlaps the rest of the backward on every replay.
+
+Constraints of overlap=True (documented in INTEGRATION.md): exactly ONE backward per zero_grad() - with gradient
+accumulation or FLAG's m > 1 ascent steps (reference trainers/flag_trainer.py) wrap all but the last backward in
+`no_sync()`, which keeps the buckets un-armed.
 """
 from __future__ import annotations
 
@@ -16,8 +23,9 @@ import torch.distributed as dist
 
 
 class GradBuckets:
-    def __init__(self, model: torch.nn.Module, n_buckets: int = 4, overlap: bool = True, group=None):
+    def __init__(self, model: torch.nn.Module, n_buckets: int = 4, overlap: bool = True, group=None, direct: bool = False):
         self.group = group
+        self._sync_enabled = True
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.params = [p for p in model.parameters() if p.requires_grad]
         dev = self.params[0].device
@@ -55,6 +63,11 @@ class GradBuckets:
                 self._bucket_of[i] = b
         self.overlap = overlap and self.world > 1 and dev.type == "cuda"
         self.comm_stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
+        # direct NCCL communicator (capturable collectives on an explicit stream)
+        self.nccl = None
+        if direct and self.world > 1 and dev.type == "cuda":
+            from . import nccl
+            self.nccl = nccl.Communicator(group)
         self._pending = [0] * len(self.buckets)
         self._work = []
         self._launched = [False] * len(self.buckets)
@@ -66,6 +79,8 @@ class GradBuckets:
     # ------------------------------------------------------------------
     def _make_ready(self, i):
         def ready():
+            if not self._sync_enabled:
+                return
             self._uses_left[i] -= 1
             if self._uses_left[i] == 0 and self.overlap:
                 b = self._bucket_of[i]
@@ -87,6 +102,8 @@ class GradBuckets:
 
     def _make_hook(self, i):
         def hook(_p):
+            if not self._sync_enabled:
+                return
             b = self._bucket_of[i]
             self._pending[b] -= 1
             if self._pending[b] == 0:
@@ -101,13 +118,35 @@ class GradBuckets:
         chunk = self.flat[lo:hi]
         if self.comm_stream is not None:
             self.comm_stream.wait_stream(torch.cuda.current_stream())
+            # gradients of this bucket may still be queued on the weight-gradient / virtual-node streams (the main
+            # stream only joins them after backward()): the reduction has to wait for those as well
+            from . import ops
+            for side in (ops._wgrad, ops._branch):
+                if side["stream"] is not None and side["used"]:
+                    self.comm_stream.wait_stream(side["stream"])
             with torch.cuda.stream(self.comm_stream):
                 self._allreduce(chunk)
         else:
             self._allreduce(chunk)
 
+    def no_sync(self):
+        """context manager: backward passes inside it do not arm / launch the bucket reductions (gradient accumulation,
+        FLAG ascent steps); the last backward outside it reduces the accumulated gradients"""
+        outer = self
+
+        class _NoSync:
+            def __enter__(self):
+                self.prev, outer._sync_enabled = outer._sync_enabled, False
+
+            def __exit__(self, *exc):
+                outer._sync_enabled = self.prev
+                return False
+        return _NoSync()
+
     def _allreduce(self, chunk):
-        if dist.get_backend(self.group) == "nccl":
+        if self.nccl is not None:
+            self.nccl.all_reduce(chunk, avg=True)        # on torch's current stream (= comm stream here); capturable
+        elif dist.get_backend(self.group) == "nccl":
             self._work.append(dist.all_reduce(chunk, op=dist.ReduceOp.AVG, group=self.group, async_op=True))
         else:
             dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group)

@@ -14,16 +14,18 @@ from .models import MODELS
 
 def build_model(args):
     ds = args.dataset
+    model_cls = MODELS[args.model_type]
+    emb = model_cls.get_emb_dim(args)        # reference dataset/mol.py:83: the node encoder takes the MODEL's width
     if ds == "code2":
-        node_encoder = ASTNodeEncoder(args.gnn_emb_dim, num_nodetypes=getattr(args, "num_nodetypes", synth.CODE2_NUM_NODETYPES),
+        node_encoder = ASTNodeEncoder(emb, num_nodetypes=getattr(args, "num_nodetypes", synth.CODE2_NUM_NODETYPES),
                                       num_nodeattributes=getattr(args, "num_nodeattrs", synth.CODE2_NUM_NODEATTRS),
                                       max_depth=synth.CODE2_MAX_DEPTH)
         edge_encoder_cls = lambda emb_dim: nn.Linear(2, emb_dim)  # noqa: E731
     elif ds in ("mol", "syn"):
-        node_encoder = AtomEncoder(args.gnn_emb_dim)
+        node_encoder = AtomEncoder(emb)
         edge_encoder_cls = lambda emb_dim: BondEncoder(emb_dim=emb_dim)  # noqa: E731
     elif ds == "nci1":
-        node_encoder = nn.Linear(37, args.gnn_emb_dim)
+        node_encoder = nn.Linear(37, emb)
 
         def edge_encoder_cls(_):
             def zero(_):
@@ -31,8 +33,26 @@ def build_model(args):
             return zero
     else:
         raise ValueError(ds)
-    return MODELS[args.model_type](num_tasks=args.num_tasks, args=args, node_encoder=node_encoder,
-                                   edge_encoder_cls=edge_encoder_cls)
+    return model_cls(num_tasks=args.num_tasks, args=args, node_encoder=node_encoder, edge_encoder_cls=edge_encoder_cls)
+
+
+def predict_fn(args):
+    """eval read-out of the reference's dataset adapters on the logits the model returns: Code2 -> int64 [B, max_seq_len]
+    token ids (reference dataset/code.py:62-66: argmax per head, ONE launch over the stacked logits here); TU -> argmax
+    class (dataset/tud.py:37); mol -> the logits themselves (dataset/mol.py:47-49 hands them to the OGB evaluator)"""
+    from . import ops
+    ds = args.dataset
+    if ds == "code2":
+        def predict(pred_list):
+            st = getattr(pred_list, "stacked", None)
+            if st is not None:
+                y, rp, n_cls = st
+                return ops.argmax_rows(y.view(-1, rp), n_cols=n_cls).view(y.shape[0], -1)
+            return torch.stack([ops.argmax_rows(p) for p in pred_list], dim=1)
+        return predict
+    if ds == "nci1":
+        return lambda pred: ops.argmax_rows(pred)
+    return lambda pred: pred
 
 
 def loss_fn(args):

@@ -1,16 +1,26 @@
-"""CUDA-graph replay of one training step (zero_grad -> forward -> loss -> backward).
+"""CUDA-graph replay of one training step (zero_grad -> forward -> loss -> backward [-> allreduce] [-> AdamW]).
 
 The hot path launches a few hundred small kernels per step (ideal step times are fractions of a
 millisecond), so in eager mode the Python host - not the GPU - sets the pace.  Every
 C-ABI export is asynchronous on the caller's stream, allocation-free and sync-free, the dropout RNG
 state and the batch plan live on the device, and parameter gradients are accumulated by the kernels
 straight into the flat arena of `ddp.GradBuckets`: the whole step is capturable.  `GraphedStep`
-captures it once per batch *shape signature* (N, E, B, feature shapes) into a `torch.cuda.CUDAGraph`
-with static input buffers and replays it afterwards; a new signature is captured on first use (LRU
-cache).  The gradient allreduce stays outside the graph (`buckets.finish()` after the replay).
+captures it once per batch *shape signature* into a `torch.cuda.CUDAGraph` with static input buffers
+and replays it afterwards.
 
-Replaces the Python-level orchestration of reference trainers/base_trainer.py:28-33
-(`optimizer.zero_grad(); pred = model(batch); loss = calc_loss(pred, batch); loss.backward()`).
+Real loaders yield a different (N, E) almost every step, so with `bucket=True` a batch is first padded
+up to a shape bucket (`loader.pad_to_bucket`: slack nodes / edges that belong to no graph and provably
+do not change logits, loss or gradients), gets its int32 CSR built at collate time and travels as one
+pinned blob (`loader.prepare`): a handful of signatures then covers an epoch, and a replay refreshes
+its static inputs with a single H2D copy.
+
+With several ranks and `GradBuckets(direct=True, overlap=True)` the bucketed `ncclAllReduce`s are part
+of the captured graph (forked off the backward where each bucket completes), and the fused AdamW update
+follows inside the same graph.
+
+Replaces the Python-level orchestration of reference trainers/base_trainer.py:28-39
+(`optimizer.zero_grad(); pred = model(batch); loss = calc_loss(pred, batch); loss.backward();
+optimizer.step()`).
 """
 from __future__ import annotations
 
@@ -25,13 +35,15 @@ from . import _lib, ops
 def _signature(batch):
     sig = []
     for k in sorted(batch.__dict__):
+        if k.startswith("_"):
+            continue
         v = getattr(batch, k)
         if torch.is_tensor(v):
             sig.append((k, tuple(v.shape), str(v.dtype)))
         elif k == "max_nodes":   # only its coarse bucket shapes the launches (ops.token_bucket)
             sig.append((k, None if v is None else -(-(int(v) + 1) // 32)))
         else:
-            sig.append((k, v if isinstance(v, (int, float, str, type(None))) else None))
+            sig.append((k, v if isinstance(v, (int, float, str, bool, type(None))) else None))
     return tuple(sig)
 
 
@@ -40,19 +52,25 @@ class _Entry:
 
 
 class GraphedStep:
-    def __init__(self, model, loss_fn, buckets, max_graphs=16, warmup_iters=2, optimizer=None):
-        """optimizer: optional graphtrans_b200.optim.FusedAdamW; on one GPU its step is part of the captured graph, with
-        several ranks it runs after the gradient allreduce (which stays outside the graph)"""
+    def __init__(self, model, loss_fn, buckets, max_graphs=16, warmup_iters=2, optimizer=None, bucket=False):
+        """optimizer: optional graphtrans_b200.optim.FusedAdamW; its step is part of the captured graph whenever the
+        gradient reduction is (one GPU, or GradBuckets(direct=True)); otherwise it runs after the host-issued allreduce.
+        bucket: pad HOST batches to shape buckets + collate-time CSR + one pinned blob (loader.prepare) before use."""
         self.model, self.loss_fn, self.buckets = model, loss_fn, buckets
         self.optimizer = optimizer
-        self.opt_in_graph = optimizer is not None and getattr(buckets, "world", 1) == 1
-        if getattr(buckets, "overlap", False):
-            raise ValueError("GraphedStep needs GradBuckets(overlap=False): collectives stay outside the graph")
+        self.world = getattr(buckets, "world", 1)
+        self.comm_in_graph = self.world > 1 and getattr(buckets, "nccl", None) is not None
+        self.opt_in_graph = optimizer is not None and (self.world == 1 or self.comm_in_graph)
+        if getattr(buckets, "overlap", False) and not self.comm_in_graph:
+            raise ValueError("GraphedStep with overlap needs GradBuckets(direct=True): only the direct NCCL binding is "
+                             "captured into the graph; torch.distributed collectives stay outside (overlap=False)")
         self.max_graphs, self.warmup_iters = max_graphs, warmup_iters
+        self.bucket = bool(bucket)
         self.cache: "OrderedDict[tuple, _Entry]" = OrderedDict()
         self.pool = None
         self.device = buckets.flat.device
         self.last_kernels = 0
+        self.captures = 0
         # the step is captured on a HIGH-priority stream: its kernels are the critical path, the weight-gradient and
         # virtual-node branches (default = lowest priority) only fill the SMs it leaves free.  Captured kernel nodes
         # inherit the priority of the stream they were issued on.
@@ -65,9 +83,24 @@ class GraphedStep:
         loss = self.loss_fn(self.model(b), b)
         loss.backward()
         ops.join_side_streams()       # weight gradients / virtual-node branch issued on side streams (ops.enable_*)
+        if self.comm_in_graph:
+            self.buckets.finish()     # captured: joins the comm stream (buckets the hooks did not launch go last)
         if self.opt_in_graph:
             self.optimizer.step()
         return loss.detach()
+
+    def _snapshot(self):
+        """state the warm-up iterations must not move: BatchNorm running statistics / num_batches_tracked and the
+        dropout step counter (the optimizer is disabled separately)"""
+        bufs = [b for b in self.model.buffers()]
+        return [b.clone() for b in bufs], ops.rng_state(self.device).clone()
+
+    def _restore(self, snap):
+        saved, rng = snap
+        with torch.no_grad():
+            for b, s in zip(self.model.buffers(), saved):
+                b.copy_(s)
+            ops.rng_state(self.device).copy_(rng)
 
     def _capture(self, batch, sig):
         ent = _Entry()
@@ -76,14 +109,24 @@ class GraphedStep:
         side.wait_stream(torch.cuda.current_stream())
         if self.optimizer is not None:
             self.optimizer.enabled = False                      # warm-up must not move the weights
+        snap = self._snapshot()
+        sync_prev = getattr(self.buckets, "_sync_enabled", True)
+        if self.comm_in_graph:
+            self.buckets._sync_enabled = False                  # warm-up: local only (no collective outside the graph)
         with torch.cuda.stream(side):                           # warm-up off the capture (cudaFuncSetAttribute,
             for _ in range(self.warmup_iters):                  # allocator warm-up, lazy module state)
-                self._eager(ent.static_batch)
+                self.buckets.zero_grad()
+                loss = self.loss_fn(self.model(ent.static_batch), ent.static_batch)
+                loss.backward()
+                ops.join_side_streams()
+        if self.comm_in_graph:
+            self.buckets._sync_enabled = sync_prev
+        torch.cuda.current_stream().wait_stream(side)
+        self._restore(snap)                                     # running stats / dropout counter as before the warm-up
         if self.optimizer is not None:
             self.optimizer.enabled = True
             if self.optimizer._desc is None:
                 self.optimizer._build()                          # descriptor table allocated outside the capture
-        torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize(self.device)
         ent.graph = torch.cuda.CUDAGraph()
         k0 = _lib.kernel_count
@@ -93,13 +136,24 @@ class GraphedStep:
         if self.pool is None:
             self.pool = ent.graph.pool()
         self.cache[sig] = ent
+        self.captures += 1
         while len(self.cache) > self.max_graphs:
             self.cache.popitem(last=False)
         return ent
 
+    def prepare(self, batch):
+        """host batch -> bucket-padded, CSR-carrying, single-blob batch (idempotent)"""
+        if not self.bucket or getattr(batch, "_blob", None) is not None:
+            return batch
+        if batch.batch.is_cuda:
+            return batch
+        from . import loader
+        return loader.prepare(batch)
+
     def __call__(self, batch):
         """batch: GraphBatch on the host (pinned) or on the device.  Returns the (static) loss tensor; the
         gradients are in `buckets.flat` / p.grad after the call."""
+        batch = self.prepare(batch)
         sig = _signature(batch)
         ent = self.cache.get(sig)
         if ent is None:
@@ -107,12 +161,18 @@ class GraphedStep:
         else:
             self.cache.move_to_end(sig)
         sb = ent.static_batch
-        for k, v in batch.__dict__.items():
-            if torch.is_tensor(v):
+        blob = getattr(batch, "_blob", None)
+        if blob is not None and getattr(sb, "_blob", None) is not None:
+            sb._blob.copy_(blob, non_blocking=True)              # ONE copy refreshes every static input
+        else:
+            for k, v in batch.tensors():
                 getattr(sb, k).copy_(v, non_blocking=True)
         ent.graph.replay()
         self.last_kernels = ent.kernels
-        self.buckets.finish()
+        if self.world > 1 and not self.comm_in_graph:
+            self.buckets.finish()
+        elif self.comm_in_graph:
+            self.buckets.reset()      # host-side bookkeeping only (the reductions ran inside the graph)
         if self.optimizer is not None and not self.opt_in_graph:
             self.optimizer.step()
         return ent.loss

@@ -11,6 +11,7 @@ from __future__ import annotations
 
 from typing import Iterable, Iterator, List, Sequence
 
+import numpy as np
 import torch
 
 from .synth import GraphBatch
@@ -132,3 +133,105 @@ class DevicePrefetcher:
             except StopIteration:
                 nxt = None
             yield cur
+
+
+# ----------------------------------------------------------------------------- collate-time integer work
+_CSR_FIELDS = ("csr_rowptr_dst", "csr_src_by_dst", "csr_eid_by_dst", "csr_rowptr_src", "csr_dst_by_src", "csr_eid_by_src")
+
+
+def attach_csr(batch: GraphBatch) -> GraphBatch:
+    """Build both int32 CSRs of `edge_index` on the HOST (loader worker time, numpy stable counting sort) and attach them
+    as `csr_*` fields: bit-identical to what gt_csr_build produces on the device (rows in edge-id order), so the model
+    skips the per-step device sort (ops.plan_for).  Returns the same batch object."""
+    ei = batch.edge_index.cpu().numpy()
+    N = int(batch.batch.numel())
+    src, dst = ei[0], ei[1]
+
+    def one(key, other):
+        order = np.argsort(key, kind="stable").astype(np.int32)
+        rowptr = np.zeros(N + 1, np.int32)
+        np.cumsum(np.bincount(key, minlength=N), out=rowptr[1:])
+        nbr = other[order].astype(np.int32)
+        if order.size == 0:                                   # kernels expect at least one element to point at
+            order, nbr = np.zeros(1, np.int32), np.zeros(1, np.int32)
+        return torch.from_numpy(rowptr), torch.from_numpy(nbr), torch.from_numpy(order)
+
+    rp_d, s_by_d, e_by_d = one(dst, src)
+    rp_s, d_by_s, e_by_s = one(src, dst)
+    for k, v in zip(_CSR_FIELDS, (rp_d, s_by_d, e_by_d, rp_s, d_by_s, e_by_s)):
+        setattr(batch, k, v)
+    return batch
+
+
+def bucket_size(n: int) -> int:
+    """smallest bucket > n on a grid whose step is 1/32 .. 1/16 of the size: a few buckets cover the batches of an epoch
+    (N and E of a batch of B iid graphs vary by a few percent), so CUDA-graph signatures repeat"""
+    n = int(n) + 1
+    q = 1 << max(int(n).bit_length() - 5, 3)
+    return (n + q - 1) // q * q
+
+
+def pad_to_bucket(batch: GraphBatch, n_nodes: int = None, n_edges: int = None) -> GraphBatch:
+    """Append slack nodes / edges so that the batch has exactly `n_nodes` nodes and `n_edges` edges (default: the next
+    buckets, `bucket_size`).  Slack nodes carry batch id == num_graphs, i.e. they belong to NO graph: they get no token
+    row, no virtual-node state, stay out of the BatchNorm statistics (GraphPlan.m_valid) and receive exactly zero
+    gradients, so logits, loss and parameter gradients equal those of the unpadded batch.  Slack edges are self loops
+    spread over the slack nodes.  Host-side (collate time); any `csr_*` fields are rebuilt."""
+    if getattr(batch, "slack", False):
+        raise ValueError("pad_to_bucket: batch is already padded")
+    N, E, B = int(batch.batch.numel()), int(batch.edge_index.shape[1]), int(batch.num_graphs)
+    n_nodes = bucket_size(N) if n_nodes is None else int(n_nodes)
+    n_edges = bucket_size(E) if n_edges is None else int(n_edges)
+    if n_nodes <= N or n_edges < E:
+        raise ValueError(f"pad_to_bucket: bucket ({n_nodes}, {n_edges}) does not exceed the batch ({N}, {E})")
+    dn, de = n_nodes - N, n_edges - E
+    out = {k: v for k, v in batch.__dict__.items() if not k.startswith("csr_") and not k.startswith("_")}
+
+    def grow(t, extra, fill=0):
+        return torch.cat([t, t.new_full((extra,) + tuple(t.shape[1:]), fill)], dim=0)
+
+    for k in _NODE_FIELDS:
+        v = out.get(k)
+        if v is not None:
+            out[k] = grow(v, dn)
+    out["batch"] = grow(batch.batch, dn, B)
+    loops = N + (torch.arange(de, dtype=batch.edge_index.dtype) % dn)
+    out["edge_index"] = torch.cat([batch.edge_index, torch.stack([loops, loops])], dim=1)
+    if out.get("edge_attr") is not None:
+        out["edge_attr"] = grow(batch.edge_attr, de)
+    out["slack"] = True
+    padded = GraphBatch(**out)
+    if getattr(batch, _CSR_FIELDS[0], None) is not None:
+        attach_csr(padded)
+    return padded
+
+
+def pack(batch: GraphBatch, pin: bool = True) -> GraphBatch:
+    """Lay every tensor of a host batch out in ONE (pinned) byte blob, 256-byte aligned: `packed.to(device)` is then a
+    single H2D copy instead of one per field (trainers/base_trainer.py:23 `batch.to(device)` issues 7-9), and a captured
+    step refreshes its static inputs with one copy."""
+    layout, off = [], 0
+    for name, t in batch.tensors():
+        t = t.contiguous()
+        nbytes = t.numel() * t.element_size()
+        layout.append((name, t.dtype, tuple(t.shape), off, nbytes, t))
+        off += (nbytes + 255) // 256 * 256
+    blob = torch.empty(max(off, 256), dtype=torch.uint8)
+    if pin and torch.cuda.is_available():
+        blob = blob.pin_memory()
+    out = GraphBatch(**{k: v for k, v in batch.__dict__.items() if not torch.is_tensor(v)})
+    for name, dtype, shape, o, nbytes, t in layout:
+        blob[o:o + nbytes].copy_(t.view(-1).view(torch.uint8))
+        setattr(out, name, blob[o:o + nbytes].view(dtype).view(shape))
+    out._blob = blob
+    out._layout = [(name, dtype, shape, o, nbytes) for name, dtype, shape, o, nbytes, _ in layout]
+    return out
+
+
+def prepare(batch: GraphBatch, bucket: bool = True, csr: bool = True, blob: bool = True) -> GraphBatch:
+    """collate-time pipeline of a host batch: shape-bucket padding -> int32 CSR -> one pinned blob"""
+    if bucket and not getattr(batch, "slack", False):
+        batch = pad_to_bucket(batch)
+    if csr and getattr(batch, _CSR_FIELDS[0], None) is None:
+        attach_csr(batch)
+    return pack(batch) if blob else batch

@@ -62,6 +62,9 @@ class _GraphTransBase(BaseModel):
         if len(self.graph_pred_linear_list) > 1:      # the 5 x 5002-class Code2 heads: one stacked operand
             self._w16.register_heads(self.graph_pred_linear_list)
         self._w16.register(self)   # bf16 operand copies of every Linear / in_proj weight, refreshed once per step
+        for m in self.modules():
+            if hasattr(m, "register_operands"):
+                m.register_operands(self._w16)
 
     def _gnn2transformer(self, parts):
         """Linear over the logical concatenation of the JK parts without materialising the concat:
@@ -85,9 +88,7 @@ class _GraphTransBase(BaseModel):
             ops.w16 = self._w16
             side = lambda: self._w16.refresh(dev)  # noqa: E731
         enc = self.transformer_encoder
-        plan = ops.GraphPlan(batched_data.edge_index, batched_data.batch, getattr(batched_data, "num_graphs", None),
-                             enc.max_input_len, cls=self.pooling == "cls", side_work=side,
-                             max_nodes=getattr(batched_data, "max_nodes", None))
+        plan = ops.plan_for(batched_data, enc.max_input_len, cls=self.pooling == "cls", side_work=side)
         parts = self.gnn_node.forward_parts(batched_data, perturb, plan=plan)
         h_node = self._gnn2transformer(parts)                          # [N, d_model]
         h_graph = enc.forward_packed(h_node, plan)                       # [B, d_model] (pooled rows only)

@@ -75,15 +75,28 @@ class GINConv(_ConvBase):
         self.eps = torch.nn.Parameter(torch.Tensor([0]))
         self.edge_encoder = edge_encoder_cls(emb_dim)
 
-    def forward(self, x, edge_index, edge_attr, plan=None):
+    def forward(self, x, edge_index, edge_attr, plan=None, out_bn=None, out_relu=False):
+        """out_bn / out_relu: the BatchNorm (+ ReLU) the caller applies right after this conv; in eval mode it is
+        folded into mlp[3] and the result carries `_gt_bn_folded = True`"""
         x, plan, d, ld, logical = self._prep(x, edge_index, plan)
         enc = _edge_encoder_args(self.edge_encoder, edge_attr, plan, d, ld)
         z = ops.aggregate(x, plan, CONV_GIN, d, self.eps, **enc)          # (1+eps) x + sum relu(x_j + e)
         # both Linears feed a train-mode BatchNorm (mlp[1] here, batch_norms[layer] in the caller): their column
         # statistics are taken in the GEMM epilogue
-        z = ops.linear(z, self.mlp[0].weight, self.mlp[0].bias, col_stats=self.training)
-        z = ops.batch_norm(z, self.mlp[1], relu=True)
-        out = ops.linear(z, self.mlp[3].weight, self.mlp[3].bias, col_stats=self.training)
+        mv = plan.m_valid
+        folded = ops.fold_bn(self.mlp[0], self.mlp[1])
+        if folded is not None:      # eval: Linear + BatchNorm(running stats) + ReLU as one contraction
+            z = ops.linear(z, folded[0], folded[1], relu=True)
+        else:
+            z = ops.linear(z, self.mlp[0].weight, self.mlp[0].bias, col_stats=self.training, m_valid=mv)
+            z = ops.batch_norm(z, self.mlp[1], relu=True, m_valid=mv)
+        if out_bn is not None:      # eval, caller's BatchNorm (no residual / virtual-node add on top) folded as well
+            f2 = ops.fold_bn(self.mlp[3], out_bn)
+            if f2 is not None:
+                out = ops.linear(z, f2[0], f2[1], relu=out_relu)
+                out._gt_bn_folded = True
+                return out
+        out = ops.linear(z, self.mlp[3].weight, self.mlp[3].bias, col_stats=self.training, m_valid=mv)
         return out[:, :d].float() if logical else out
 
 

@@ -20,8 +20,7 @@ def _encode(node_encoder, batched_data):
 def _plan_of(batched_data, max_input_len=1000):
     plan = getattr(batched_data, "_gt_plan", None)
     if plan is None or plan.L != int(max_input_len):
-        plan = ops.GraphPlan(batched_data.edge_index, batched_data.batch, getattr(batched_data, "num_graphs", None),
-                             max_input_len)
+        plan = ops.plan_for(batched_data, max_input_len)
     return plan
 
 
@@ -94,10 +93,15 @@ class GNN_node(_GNNBase):
         edge_index, edge_attr = batched_data.edge_index, batched_data.edge_attr
         h_list = [self._input(batched_data, perturb)]
         for layer in range(self.num_layer):
-            h = self.convs[layer](h_list[layer], edge_index, edge_attr, plan=plan)
-            h = ops.batch_norm(h, self.batch_norms[layer], relu=layer != self.num_layer - 1,
-                               resid=h_list[layer] if self.residual else None,
-                               drop_p=self.drop_ratio if self.training else 0.0)
+            relu = layer != self.num_layer - 1
+            kw = {}
+            if isinstance(self.convs[layer], GINConv) and not self.residual:   # eval: BatchNorm folded into mlp[3]
+                kw = dict(out_bn=self.batch_norms[layer], out_relu=relu)
+            h = self.convs[layer](h_list[layer], edge_index, edge_attr, plan=plan, **kw)
+            if not getattr(h, "_gt_bn_folded", False):
+                h = ops.batch_norm(h, self.batch_norms[layer], relu=relu,
+                                   resid=h_list[layer] if self.residual else None,
+                                   drop_p=self.drop_ratio if self.training else 0.0, m_valid=plan.m_valid)
             h_list.append(h)
         return self._jk(h_list)
 
@@ -139,8 +143,12 @@ class GNN_node_Virtualnode(_GNNBase):
                     t = ops.segment_sum(hv, plan, init=vn)        # global_add_pool(h_list[layer]) + vn
                     t = ops.cast_to(t, ops.act_dtype())           # the MLP runs in the activation dtype
                     cs = self.training
-                    t = ops.batch_norm(ops.linear(t, mlp[0].weight, mlp[0].bias, col_stats=cs), mlp[1], relu=True)
-                    t = ops.batch_norm(ops.linear(t, mlp[3].weight, mlp[3].bias, col_stats=cs), mlp[4], relu=True, drop_p=drop)
+                    f0, f3 = ops.fold_bn(mlp[0], mlp[1]), ops.fold_bn(mlp[3], mlp[4])
+                    if f0 is not None and f3 is not None:          # eval: both Linear + BatchNorm + ReLU pairs folded
+                        t = ops.linear(ops.linear(t, f0[0], f0[1], relu=True), f3[0], f3[1], relu=True)
+                    else:
+                        t = ops.batch_norm(ops.linear(t, mlp[0].weight, mlp[0].bias, col_stats=cs), mlp[1], relu=True)
+                        t = ops.batch_norm(ops.linear(t, mlp[3].weight, mlp[3].bias, col_stats=cs), mlp[4], relu=True, drop_p=drop)
                     t = ops.cast_to(t, torch.float32)             # the virtual-node state itself stays fp32
                     vn_next = vn + t if self.residual else t
             h = self.convs[layer](hv, edge_index, edge_attr, plan=plan)
@@ -148,7 +156,8 @@ class GNN_node_Virtualnode(_GNNBase):
                 br.join(vn_next)
             # BN -> ReLU (not last) -> dropout -> (+residual) -> (+ next layer's vn[batch]) in one kernel
             h = ops.batch_norm(h, self.batch_norms[layer], relu=layer != self.num_layer - 1,
-                               resid=hv if self.residual else None, gvec=vn_next, plan=plan, drop_p=drop)
+                               resid=hv if self.residual else None, gvec=vn_next, plan=plan, drop_p=drop,
+                               m_valid=plan.m_valid)
             h_list.append(h)
             vn = vn_next
         return self._jk(h_list)

@@ -36,6 +36,17 @@ class PNAConv(nn.Module):
         for m in self.pre_nns:          # W_i and W_j halves are applied separately: two gradient contributions
             m[0].weight._gt_uses = 2
 
+    def register_operands(self, registry):
+        """block-diagonal bf16 tower operands (W_i | W_j halves of pre_nns, post_nns) in the model's registry: built once,
+        refreshed with every other weight copy by the one gt_cast_multi launch of the step"""
+        F = self.F_in
+        pre_w, pre_b = [m[0].weight for m in self.pre_nns], [m[0].bias for m in self.pre_nns]
+        post_w, post_b = [m[0].weight for m in self.post_nns], [m[0].bias for m in self.post_nns]
+        self._bd_keys = (("pna_wi", id(self)), ("pna_wj", id(self)), ("pna_post", id(self)))
+        registry.register_blockdiag(self._bd_keys[0], pre_w, pre_b, col_lo=0, K=F)
+        registry.register_blockdiag(self._bd_keys[1], pre_w, None, col_lo=F, K=F)
+        registry.register_blockdiag(self._bd_keys[2], post_w, post_b, col_lo=0, K=13 * F)
+
     def forward(self, x, edge_index=None, plan=None):
         """x: physical [N, ldp(d)] activation matrix; returns the same layout."""
         F, T = self.F_in, self.towers
@@ -44,15 +55,16 @@ class PNAConv(nn.Module):
         post_w = [m[0].weight for m in self.post_nns]
         post_b = [m[0].bias for m in self.post_nns]
         # W_pre [x_i || x_j] = W_i x_i + W_j x_j: project per NODE, then reduce over in-edges
-        if ops.precision() == "bf16" and (T * F) % 8 == 0 and (13 * F * T) % 8 == 0:
-            # tensor-core path: the four towers as ONE block-diagonal contraction per stage (tower slices of width F
-            # are not 16-byte aligned for F = 68, whole matrices are); the off-diagonal zero blocks only cost MMA slots
-            w_i = torch.block_diag(*[w[:, :F] for w in pre_w])             # [T*F, T*F]
-            w_j = torch.block_diag(*[w[:, F:] for w in pre_w])
-            pi = ops.linear(x, w_i, torch.cat(pre_b))
-            pj = ops.linear(x, w_j)
+        keys = getattr(self, "_bd_keys", None)
+        pi = None
+        if keys is not None and ops.precision() == "bf16" and (T * F) % 8 == 0 and (13 * F * T) % 8 == 0:
+            # tensor-core path: the four towers as ONE block-diagonal contraction per stage over operand copies the
+            # registry keeps (tower slices of width F are not 16-byte aligned for F = 68, whole matrices are)
+            pi = ops.blockdiag_linear(x, keys[0], pre_w, pre_b, 0, F)
+        if pi is not None:
+            pj = ops.blockdiag_linear(x, keys[1], pre_w, None, F, F)
             agg = ops.pna_reduce(x, pj, pi, plan, T, F, self.avg_deg["log"])  # [N, T*13F]
-            y = ops.linear(agg, torch.block_diag(*post_w), torch.cat(post_b))
+            y = ops.blockdiag_linear(agg, keys[2], post_w, post_b, 0, 13 * F)
         else:
             pi = ops.tower_linear(x, pre_w, pre_b, F, F, w_col_off=0)
             pj = ops.tower_linear(x, pre_w, None, F, F, w_col_off=F)
@@ -111,7 +123,7 @@ class PNANodeEmbedding(nn.Module):
         for conv, bn in zip(self.layers, self.batch_norms):
             h = conv(x, plan=plan)
             if self.residual:      # x = dropout(relu(BN(h)) + x)   (pna_module.py:73-76)
-                x = ops.dropout(ops.batch_norm(h, bn.module, relu=True, resid=x), drop)
+                x = ops.dropout(ops.batch_norm(h, bn.module, relu=True, resid=x, m_valid=plan.m_valid), drop)
             else:                  # reference keeps x (h is discarded); dropout still applies
                 x = ops.dropout(x, drop)
         return [x]

@@ -2,12 +2,17 @@
 modules/transformer_encoder.py:9-61).  The nn.TransformerEncoder it owns is used as a PARAMETER
 CONTAINER only (identical keys / init as the reference); the math runs on packed tokens through
 gt_gemm / gt_mha_* / gt_layernorm_* (post-norm layers, ReLU FFN, final LayerNorm)."""
+import os
 import types
 
 import torch
 import torch.nn as nn
 
 from .. import ops
+
+# last encoder layer: compute only the pooled query row of every graph (exactly what the model reads, reference
+# models/gnn_transformer.py:114-115); GT_POOLED_LAST=0 runs the full layer (A/B switch for the parity tests)
+POOLED_LAST = int(os.environ.get("GT_POOLED_LAST", "1"))
 
 
 class TransformerNodeEncoder(nn.Module):
@@ -45,12 +50,38 @@ class TransformerNodeEncoder(nn.Module):
         self.cls_embedding = None
         if args.graph_pooling == "cls":
             self.cls_embedding = nn.Parameter(torch.randn([1, 1, args.d_model], requires_grad=True))
+        # the pooled last layer applies in_proj in two row blocks (q | k,v): two gradient contributions per step
+        at = self.transformer.layers[-1].self_attn
+        at.in_proj_weight._gt_uses = at.in_proj_bias._gt_uses = 2
 
     # ------------------------------------------------------------------ packed path (model)
-    def encode_layers(self, x, plan, key_start=None):
+    def _ffn_block(self, layer, a, x, drop):
+        """out-projection .. norm2 of one post-norm encoder layer on the rows of `a` (residual stream `x`)"""
+        at = layer.self_attn
+        a = ops.linear(a, at.out_proj.weight, at.out_proj.bias)
+        x1 = ops.layer_norm(a, layer.norm1, resid=x, drop_p=drop)                           # norm1(x + drop(a))
+        f = ops.linear(x1, layer.linear1.weight, layer.linear1.bias, relu=True, drop_p=drop)
+        f = ops.linear(f, layer.linear2.weight, layer.linear2.bias)
+        return ops.layer_norm(f, layer.norm2, resid=x1, drop_p=drop)                         # norm2(x + drop(f))
+
+    def encode_pooled_last(self, x, plan):
+        """LAST layer for the pooled rows only: k | v of every token, q / out-proj / norms / FFN of the B pooled rows
+        (plan.cls_rows: <CLS>, or the last node with pooling == 'last').  x: [n_rows, d] -> [B, d]."""
+        drop = self.dropout if self.training else 0.0
+        layer = self.transformer.layers[-1]
+        at = layer.self_attn
+        d = self.d_model
+        xq = ops.gather_rows(x, plan.cls_rows, n_rows=plan.B)                                 # [B, d] residual stream
+        kv = ops.linear(x, at.in_proj_weight, at.in_proj_bias, w_row_off=d, n_out=2 * d)     # [n_rows, 2d]
+        q = ops.linear(xq, at.in_proj_weight, at.in_proj_bias, w_row_off=0, n_out=d)         # [B, d]
+        a = ops.mha_pooled_query(q, kv, plan, self.nhead, drop_p=drop)
+        return self._ffn_block(layer, a, xq, drop)
+
+    def encode_layers(self, x, plan, key_start=None, skip_last=False):
         """x: [n_rows, d] packed tokens -> last layer output (before the final norm)."""
         drop = self.dropout if self.training else 0.0
-        for layer in self.transformer.layers:
+        layers = list(self.transformer.layers)
+        for layer in (layers[:-1] if skip_last else layers):
             at = layer.self_attn
             qkv = ops.linear(x, at.in_proj_weight, at.in_proj_bias)
             a = ops.mha_packed(qkv, plan, self.nhead, key_start, drop_p=drop)
@@ -61,17 +92,27 @@ class TransformerNodeEncoder(nn.Module):
             x = ops.layer_norm(f, layer.norm2, resid=x1, drop_p=drop)                       # norm2(x + drop(f))
         return x
 
-    def forward_packed(self, h_node, plan):
-        """h_node: [N, d] node states (gnn2transformer output) -> [B, d] encoder output at the pooled
-        position (<CLS> row, or the last node when pooling == 'last')."""
+    def _tokens(self, h_node, plan):
         cls = self.cls_embedding
         if plan.cls != (cls is not None):
             raise RuntimeError("GraphPlan was built with a different <CLS> setting than the encoder")
-        rows = plan.tok2node
         if self.norm_input is not None:
-            x = ops.layer_norm(h_node, self.norm_input, in_rows=rows, cls=cls, n_rows=plan.n_rows)
-        else:
-            x = ops.gather_rows(h_node, rows, cls=cls, n_rows=plan.n_rows)
+            return ops.layer_norm(h_node, self.norm_input, in_rows=plan.tok2node, cls=cls, n_rows=plan.n_rows)
+        return ops.gather_rows(h_node, plan.tok2node, cls=cls, n_rows=plan.n_rows)
+
+    def forward_tokens(self, h_node, plan):
+        """h_node [N, d] -> encoder output of EVERY packed token row [n_rows, d] (final norm applied): the callers that
+        pool over nodes afterwards (reference models/transformer.py:105-106)"""
+        x = self.encode_layers(self._tokens(h_node, plan), plan)
+        return ops.layer_norm(x, self.transformer.norm)
+
+    def forward_packed(self, h_node, plan):
+        """h_node: [N, d] node states (gnn2transformer output) -> [B, d] encoder output at the pooled
+        position (<CLS> row, or the last node when pooling == 'last')."""
+        x = self._tokens(h_node, plan)
+        if POOLED_LAST:
+            x = self.encode_layers(x, plan, skip_last=True)
+            return ops.layer_norm(self.encode_pooled_last(x, plan), self.transformer.norm)
         x = self.encode_layers(x, plan)
         return ops.layer_norm(x, self.transformer.norm, in_rows=plan.cls_rows, n_rows=plan.B)
 

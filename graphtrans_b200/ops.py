@@ -68,6 +68,8 @@ class _W16Registry:
     def __init__(self):
         self.params, self.copies, self.desc, self.ptrs, self.blocks = [], {}, None, None, 0
         self.stacks, self.stack_copies, self._stacked_ids = [], {}, set()
+        self.extra = {}
+        self.blockdiags, self.bd_copies = [], {}
 
     def register_heads(self, linears):
         linears = list(linears)
@@ -77,6 +79,18 @@ class _W16Registry:
         self._stacked_ids.update(id(l.weight) for l in linears)
         self.params = [w for w in self.params if id(w) not in self._stacked_ids]
         self.desc = None
+
+    def register_blockdiag(self, key, weights, biases=None, col_lo=0, K=None):
+        """block-diagonal operand of equally shaped tower Linears (PNA pre / post MLPs, reference modules/pna_layer.py:
+        102-118): diag_t = weights[t][:, col_lo:col_lo+K] -> ONE bf16 [T*Fo, ldp(T*K)] operand (+ fp32 bias [T*Fo]),
+        refreshed with the other operand copies; `bd_lookup(key)` -> (operand, ld, bias or None)"""
+        weights = list(weights)
+        K = weights[0].shape[1] - col_lo if K is None else K
+        self.blockdiags.append((key, weights, list(biases) if biases is not None else None, int(col_lo), int(K)))
+        self.desc = None
+
+    def bd_lookup(self, key):
+        return self.bd_copies.get(key)
 
     def register(self, module: torch.nn.Module):
         seen = {id(p) for p in self.params} | self._stacked_ids
@@ -93,7 +107,8 @@ class _W16Registry:
         self.desc = None
 
     def _all_ptrs(self):
-        return tuple(w.data_ptr() for w in self.params) + tuple(t.data_ptr() for st in self.stacks for wb in st for t in wb)
+        return (tuple(w.data_ptr() for w in self.params) + tuple(t.data_ptr() for st in self.stacks for wb in st for t in wb)
+                + tuple(w.data_ptr() for bd in self.blockdiags for w in bd[1]))
 
     def _build(self, device):
         recs, blk = [], 0
@@ -105,7 +120,7 @@ class _W16Registry:
             ld = ldp(cols)
             c = torch.empty(rows, ld, dtype=torch.bfloat16, device=w.device)
             self.copies[id(w)] = (c, ld)
-            recs.append([w.data_ptr(), c.data_ptr(), rows, cols, ld, blk])
+            recs.append([w.data_ptr(), c.data_ptr(), rows, cols, ld, blk, 0, 0])
             blk += (rows * ld + 2047) // 2048
         for st in self.stacks:
             w0 = st[0][0]
@@ -116,17 +131,32 @@ class _W16Registry:
             wst = torch.zeros(len(st) * rp, ld, dtype=torch.bfloat16, device=w0.device)   # pad rows stay zero
             bst = torch.zeros(len(st) * rp, dtype=torch.float32, device=w0.device)
             for h, (w, b) in enumerate(st):
-                recs.append([w.data_ptr(), wst.data_ptr() + h * rp * ld * 2, rows, cols, ld, blk])
+                recs.append([w.data_ptr(), wst.data_ptr() + h * rp * ld * 2, rows, cols, ld, blk, 0, 0])
                 blk += (rows * ld + 2047) // 2048
-                recs.append([b.data_ptr(), bst.data_ptr() + h * rp * 4, 1, rows, -rp, blk])   # ld < 0: fp32 copy
+                recs.append([b.data_ptr(), bst.data_ptr() + h * rp * 4, 1, rows, -rp, blk, 0, 0])   # ld < 0: fp32 copy
                 blk += (rp + 2047) // 2048
             self.stack_copies[id(w0)] = (wst, bst, rp, ld)
+        self.bd_copies = {}
+        for key, ws, bs, col_lo, K in self.blockdiags:
+            if not all(w.is_cuda and w.dtype == torch.float32 and w.is_contiguous() for w in ws):
+                continue
+            T, Fo, Kw = len(ws), ws[0].shape[0], ws[0].shape[1]
+            ld = ldp(T * K)
+            op = torch.zeros(T * Fo, ld, dtype=torch.bfloat16, device=ws[0].device)     # off-diagonal blocks stay zero
+            bias = torch.zeros(T * Fo, dtype=torch.float32, device=ws[0].device) if bs is not None else None
+            for t, w in enumerate(ws):
+                recs.append([w.data_ptr() + col_lo * 4, op.data_ptr() + (t * Fo * ld + t * K) * 2, Fo, K, ld, blk, Kw, K])
+                blk += (Fo * K + 2047) // 2048
+                if bs is not None:
+                    recs.append([bs[t].data_ptr(), bias.data_ptr() + t * Fo * 4, 1, Fo, -Fo, blk, 0, 0])
+                    blk += (Fo + 2047) // 2048
+            self.bd_copies[key] = (op, ld, bias)
         self.blocks = blk
         self.ptrs = self._all_ptrs()
         self.desc = torch.tensor(recs, dtype=torch.int64, device=device) if recs else None
 
     def refresh(self, device):
-        if not self.params and not self.stacks:
+        if not self.params and not self.stacks and not self.blockdiags:
             return
         if self.desc is None or self.ptrs != self._all_ptrs():
             self._build(device)
@@ -134,7 +164,12 @@ class _W16Registry:
             call("gt_cast_multi", ptr(self.desc), self.desc.shape[0], self.blocks)
 
     def lookup(self, w):
-        return self.copies.get(id(w))
+        ent = self.copies.get(id(w))
+        return ent if ent is not None else self.extra.get(id(w))
+
+    def put(self, w, copy, ld):
+        """operand copy of a derived (non-parameter) fp32 matrix, e.g. an eval-time BatchNorm-folded weight"""
+        self.extra[id(w)] = (copy, ld)
 
     def stack_lookup(self, w0):
         return self.stack_copies.get(id(w0))
@@ -142,6 +177,9 @@ class _W16Registry:
 
 W16Registry = _W16Registry
 w16 = _W16Registry()   # registry of the model whose step is running (begin_step(registry=...)); default: a global one
+
+
+_train_steps = [0]      # bumped by every training forward: eval-time derived weights (fold_bn) are recomputed after it
 
 
 def begin_step(device, cast_now=True, registry=None):
@@ -153,6 +191,7 @@ def begin_step(device, cast_now=True, registry=None):
     if registry is not None:   # every model owns its operand copies: a captured step keeps valid pointers when
         w16 = registry         # another model is built or stepped in the same process
     _salt[0] = 0
+    _train_steps[0] += 1
     call("gt_rng_advance", ptr(rng_state(device)))
     if _PRECISION == "bf16" and cast_now:
         w16.refresh(device)
@@ -417,26 +456,45 @@ class GraphPlan:
     gt_csr_build / gt_batch_plan without any host synchronisation (B comes from
     `batch.num_graphs` when present, otherwise one .item() like reference gnn_module.py:195)."""
 
-    def __init__(self, edge_index, batch, num_graphs=None, max_input_len=1000, cls=True, side_work=None, max_nodes=None):
+    def __init__(self, edge_index, batch, num_graphs=None, max_input_len=1000, cls=True, side_work=None, max_nodes=None,
+                 prebuilt=None, slack=False):
         """side_work: optional callable launched on the branch stream together with the token plan (the two CSR
-        sorts stay on the current stream): the integer prep of a batch is three independent chains."""
+        sorts stay on the current stream): the integer prep of a batch is three independent chains.
+        prebuilt: the six int32 CSR arrays (rowptr_dst, src_by_dst, eid_by_dst, rowptr_src, dst_by_src, eid_by_src) when
+        the loader built them at collate time (loader.attach_csr): gt_csr_build is skipped.
+        slack: the batch ends with shape-bucket slack nodes (batch id == num_graphs, loader.pad_to_bucket): they belong
+        to no graph; `m_valid` (device int32[1] = number of real nodes) keeps them out of the BatchNorm statistics."""
         # max_nodes: optional host-side upper bound of the nodes per graph (collate-time metadata, e.g.
         # synth.GraphBatch.max_nodes).  When every graph fits one 128-row tile the tile-local attention kernels apply.
         _lib.require_cuda(edge_index, batch)
         dev = batch.device
         N = batch.numel()
         E = edge_index.shape[1]
-        B = int(num_graphs) if num_graphs is not None else int(batch[-1].item()) + 1
+        if num_graphs is None:
+            if slack:
+                raise RuntimeError("GraphPlan: a batch with slack nodes needs num_graphs")
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("GraphPlan: batch.num_graphs is required under CUDA-graph capture (batch[-1].item() would sync)")
+            B = int(batch[-1].item()) + 1       # one device->host read, like reference modules/gnn_module.py:195
+        else:
+            B = int(num_graphs)
         self.N, self.E, self.B, self.L, self.cls = N, E, B, int(max_input_len), bool(cls)
         i32 = dict(dtype=torch.int32, device=dev)
         ei = edge_index.contiguous()
-        self.rowptr_dst = torch.empty(N + 1, **i32)
-        self.rowptr_src = torch.empty(N + 1, **i32)
-        self.src_by_dst = torch.empty(max(E, 1), **i32)
-        self.eid_by_dst = torch.empty(max(E, 1), **i32)
-        self.dst_by_src = torch.empty(max(E, 1), **i32)
-        self.eid_by_src = torch.empty(max(E, 1), **i32)
-        work = torch.empty(2 * (N + 1), **i32)
+        if prebuilt is not None:
+            (self.rowptr_dst, self.src_by_dst, self.eid_by_dst, self.rowptr_src, self.dst_by_src, self.eid_by_src) = prebuilt
+            for t, n in zip(prebuilt, (N + 1, E, E, N + 1, E, E)):
+                if t.dtype != torch.int32 or not t.is_cuda or t.numel() < max(n, 1) or not t.is_contiguous():
+                    raise RuntimeError("GraphPlan: prebuilt CSR arrays must be contiguous int32 CUDA tensors of the batch's sizes")
+            work = None
+        else:
+            self.rowptr_dst = torch.empty(N + 1, **i32)
+            self.rowptr_src = torch.empty(N + 1, **i32)
+            self.src_by_dst = torch.empty(max(E, 1), **i32)
+            self.eid_by_dst = torch.empty(max(E, 1), **i32)
+            self.dst_by_src = torch.empty(max(E, 1), **i32)
+            self.eid_by_src = torch.empty(max(E, 1), **i32)
+            work = torch.empty(2 * (N + 1), **i32)
         self.node_off = torch.empty(B + 1, **i32)
         self.kept = torch.empty(B, **i32)
         self.tok_off = torch.empty(B + 1, **i32)
@@ -472,9 +530,11 @@ class GraphPlan:
                  ptr(self.tile_bounds))
             if self.loc_tiles is not None:
                 call("gt_mha_local_tiles", ptr(self.tok_off), B, self.loc_max_tiles, ptr(self.loc_tiles), ptr(self.loc_count))
-        call("gt_csr_build", ptr(ei), E, N, ptr(self.rowptr_dst), ptr(self.src_by_dst), ptr(self.eid_by_dst),
-             ptr(self.rowptr_src), ptr(self.dst_by_src), ptr(self.eid_by_src), ptr(work))
+        if prebuilt is None:
+            call("gt_csr_build", ptr(ei), E, N, ptr(self.rowptr_dst), ptr(self.src_by_dst), ptr(self.eid_by_dst),
+                 ptr(self.rowptr_src), ptr(self.dst_by_src), ptr(self.eid_by_src), ptr(work))
         br.join()
+        self.m_valid = self.node_off[B:B + 1] if slack else None
         self._etype = {}
         self._slots = {}
         self._by_type = {}
@@ -561,6 +621,20 @@ class GraphPlan:
         if self._S is None:
             self._S = int(self.scalars[0].item())
         return self._S
+
+
+_CSR_FIELDS = ("csr_rowptr_dst", "csr_src_by_dst", "csr_eid_by_dst", "csr_rowptr_src", "csr_dst_by_src", "csr_eid_by_src")
+
+
+def plan_for(batched_data, max_input_len=1000, cls=True, side_work=None):
+    """GraphPlan of a batch object, honouring the optional collate-time metadata the loader attaches: `num_graphs`,
+    `max_nodes`, the int32 CSR (`csr_*`, loader.attach_csr) and `slack` (loader.pad_to_bucket)"""
+    pre = None
+    if getattr(batched_data, _CSR_FIELDS[0], None) is not None:
+        pre = tuple(getattr(batched_data, k) for k in _CSR_FIELDS)
+    return GraphPlan(batched_data.edge_index, batched_data.batch, getattr(batched_data, "num_graphs", None), max_input_len,
+                     cls=cls, side_work=side_work, max_nodes=getattr(batched_data, "max_nodes", None), prebuilt=pre,
+                     slack=bool(getattr(batched_data, "slack", False)))
 
 
 # ----------------------------------------------------------------------------- node encoders
@@ -656,12 +730,13 @@ def embed_sum(index_cols, tables, clamps=None, dtype=None):
 
 # ----------------------------------------------------------------------------- dense layers
 def _gemm_raw(dt, A, a_mn, lda, Bm, b_mn, ldb, C, ldc, M, N, K, n_fill, bias, resid, ldr, flags, impl=None,
-              drop_p=0.0, rng=None, salt=0, col_stats=None):
+              drop_p=0.0, rng=None, salt=0, col_stats=None, m_valid=None):
     """raw-pointer gt_gemm (A, Bm, C are device addresses so strided sub-blocks need no copies); col_stats: fp64
-    [2 * ldc] that receives the BatchNorm column statistics of C in the same pass (gt_gemm_stats)"""
+    [2 * ldc] that receives the BatchNorm column statistics of C in the same pass (gt_gemm_stats; m_valid: device
+    int32[1] = number of leading real rows when the matrix carries shape-bucket slack rows)"""
     if col_stats is not None:
         call("gt_gemm_stats", dt, A, int(a_mn), lda, Bm, int(b_mn), ldb, C, ldc, M, N, K, n_fill, ptr(bias), ptr(resid), ldr,
-             flags, float(drop_p), rng, salt, GEMM_IMPL if impl is None else impl, ptr(col_stats))
+             flags, float(drop_p), rng, salt, GEMM_IMPL if impl is None else impl, ptr(col_stats), ptr(m_valid))
         return
     call("gt_gemm", dt, A, int(a_mn), lda, Bm, int(b_mn), ldb, C, ldc, M, N, K, n_fill, ptr(bias), ptr(resid), ldr,
          flags, float(drop_p), rng, salt, GEMM_IMPL if impl is None else impl)
@@ -673,24 +748,30 @@ class _LinearFn(torch.autograd.Function):
     block of the weight (JK=cat: gnn2transformer applied to the parts without concatenating)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, relu, out_f32, resid, off, K, drop_p, salt, want_stats=False):
+    def forward(ctx, x, weight, bias, relu, out_f32, resid, off, K, drop_p, salt, want_stats=False, m_valid=None,
+                row_off=0, n_out=None):
         x = x.contiguous()
         M, ld_in = x.shape
         N, Kw = weight.shape
+        if n_out is not None:       # row block [row_off, row_off + n_out) of the weight / bias (q or k|v part of in_proj)
+            N = int(n_out)
         K = Kw - off if K is None else K
         if K > ld_in:
             raise RuntimeError(f"linear: input width {ld_in} < in_features {K}")
         wf = weight.contiguous()
+        bias_param = bias
+        if bias is not None and (row_off or N != bias.shape[0]):
+            bias = bias[row_off:row_off + N]
         if x.dtype == torch.float32:
-            w, ldw, wptr = wf, Kw, wf.data_ptr() + off * 4
+            w, ldw, wptr = wf, Kw, wf.data_ptr() + (row_off * Kw + off) * 4
         else:
             ent = w16.lookup(weight) if off % 8 == 0 else None
             if ent is not None:   # operand copy refreshed once per step by gt_cast_multi (begin_step)
                 w, ldw = ent
-                wptr = w.data_ptr() + off * 2
+                wptr = w.data_ptr() + (row_off * ldw + off) * 2
             else:  # bf16 operand copy of the fp32 master weight block, K padded so rows stay 16-B aligned
                 w = torch.empty(N, ld_in, dtype=x.dtype, device=x.device)
-                call("gt_cast_pad", GT_F32, wf.data_ptr() + off * 4, N, K, Kw, dt_of(w), ptr(w), N, ld_in, ld_in)
+                call("gt_cast_pad", GT_F32, wf.data_ptr() + (row_off * Kw + off) * 4, N, K, Kw, dt_of(w), ptr(w), N, ld_in, ld_in)
                 ldw, wptr = ld_in, w.data_ptr()
         ld_out = ldp(N)
         out_dtype = torch.float32 if out_f32 else x.dtype
@@ -705,15 +786,17 @@ class _LinearFn(torch.autograd.Function):
         stats = zeros_small(2 * ld_out, torch.float64, x.device) if want_stats else None
         _gemm_raw(dt_of(x), x.data_ptr(), 0, ld_in, wptr, 0, ldw, y.data_ptr(), ld_out, M, N, K, ld_out, bias, resid,
                   ld_out, flags, drop_p=drop_p, rng=ptr(rng_state(x.device)) if drop_p else None, salt=salt,
-                  col_stats=stats)
+                  col_stats=stats, m_valid=m_valid)
         ctx.drop_p = drop_p
         ctx.save_for_backward(x, w, y if relu else None)
-        ctx.params = (weight, bias)
+        ctx.params = (weight, bias_param)
         ctx.woff = wptr - w.data_ptr()      # byte offset of the operand block inside the saved weight tensor
         ctx.meta = (M, N, K, Kw, off, ld_in, ldw, ld_out, relu, bias is not None, resid is not None)
-        # want_stats <=> the output feeds a train-mode BatchNorm directly: the BN backward returns a gradient whose
-        # column sums vanish identically, i.e. the bias gradient of this Linear is exactly zero - no gt_colsum launch
-        ctx.bias_grad_zero = bool(want_stats) and SKIP_ZERO_BIAS_GRAD
+        ctx.row_off = int(row_off)
+        # set by ops.batch_norm when a TRAIN-mode BatchNorm actually consumes this output: its backward returns a gradient
+        # whose column sums vanish identically, i.e. the bias gradient of this Linear is exactly zero - no gt_colsum launch.
+        # The consumer opts in (a frozen BN, a standalone conv or any other reader keeps the real column sum).
+        ctx.bias_grad_zero = False
         if want_stats:
             ctx.mark_non_differentiable(stats)
             return y, stats
@@ -758,29 +841,30 @@ class _LinearFn(torch.autograd.Function):
             if ctx.needs_input_grad[1]:
                 tgt, gw = _grad_target(weight)
                 # dW[n,k] = sum_m dY[m,n] X[m,k]: both operands MN-major, split-K over the rows, accumulated in place
-                _gemm_raw(dt_of(x), gy.data_ptr(), 1, ld_out, x.data_ptr(), 1, ld_in, tgt.data_ptr() + off * 4, Kw, N, K,
-                          M, K, None, None, 0, EPI_ACCUM | EPI_OUT_F32)
+                _gemm_raw(dt_of(x), gy.data_ptr(), 1, ld_out, x.data_ptr(), 1, ld_in,
+                          tgt.data_ptr() + (ctx.row_off * Kw + off) * 4, Kw, N, K, M, K, None, None, 0, EPI_ACCUM | EPI_OUT_F32)
                 _grad_done(weight)
             if has_bias and ctx.needs_input_grad[2]:
                 tgt, gb = _grad_target(bias)           # (a fresh zero tensor when there is no arena)
                 if not ctx.bias_grad_zero:
-                    call("gt_colsum", dt_of(gy), ptr(gy), M, N, ld_out, ptr(tgt))
+                    call("gt_colsum", dt_of(gy), ptr(gy), M, N, ld_out, tgt.data_ptr() + ctx.row_off * 4)
                 _grad_done(bias)
-        return gx, gw, gb, None, None, g_res, None, None, None, None, None
+        return gx, gw, gb, None, None, g_res, None, None, None, None, None, None, None, None
 
 
-def linear(x, weight, bias=None, relu=False, out_f32=False, resid=None, drop_p=0.0, w_col_off=0, K=None, col_stats=False):
+def linear(x, weight, bias=None, relu=False, out_f32=False, resid=None, drop_p=0.0, w_col_off=0, K=None, col_stats=False,
+           m_valid=None, w_row_off=0, n_out=None):
     """drop(act(x W[:, off:off+K]^T + b)) [+ resid]; drop(relu(.)) runs in the GEMM epilogue (the FFN pattern of
     nn.TransformerEncoderLayer); dropout without ReLU / together with resid is not a reference pattern.
     col_stats=True: the output carries its BatchNorm column statistics (taken in the GEMM epilogue), which
     ops.batch_norm picks up instead of a separate gt_colstats pass."""
     fused = bool(drop_p) and relu and resid is None
     if col_stats and FUSE_COLSTATS and not drop_p and not out_f32:
-        y, stats = _LinearFn.apply(x, weight, bias, relu, out_f32, resid, w_col_off, K, 0.0, 0, True)
+        y, stats = _LinearFn.apply(x, weight, bias, relu, out_f32, resid, w_col_off, K, 0.0, 0, True, m_valid)
         y._gt_colstats = stats
         return y
     y = _LinearFn.apply(x, weight, bias, relu, out_f32, resid, w_col_off, K, float(drop_p) if fused else 0.0,
-                        next_salt() if fused else 0)
+                        next_salt() if fused else 0, False, None, w_row_off, n_out)
     return dropout(y, drop_p) if (drop_p and not fused) else y
 
 
@@ -1031,7 +1115,7 @@ class _BatchNormFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, gamma, beta, running_mean, running_var, nbt, training, momentum, eps, relu, resid,
-                gvec, plan, drop_p, salt, pre_stats=None):
+                gvec, plan, drop_p, salt, pre_stats=None, m_valid=None):
         x = x.contiguous()
         M, ld = x.shape
         d = gamma.shape[0]
@@ -1043,7 +1127,7 @@ class _BatchNormFn(torch.autograd.Function):
                 stats = pre_stats
             else:
                 stats = zeros_small(2 * ld, torch.float64, dev)
-                call("gt_colstats", dt_of(x), ptr(x), M, ld, ptr(stats))
+                call("gt_colstats", dt_of(x), ptr(x), M, ld, ptr(stats), ptr(m_valid))
         y = torch.empty_like(x)
         if resid is not None:
             resid = resid.contiguous()
@@ -1052,7 +1136,8 @@ class _BatchNormFn(torch.autograd.Function):
         rng = ptr(rng_state(dev)) if drop_p else None
         call("gt_bn_norm_fwd", dt_of(x), ptr(x), M, d, ld, ptr(stats), ptr(gamma), ptr(beta), ptr(running_mean),
              ptr(running_var), ptr(nbt), float(momentum), float(eps), int(training), int(relu), ptr(resid), ptr(gvec),
-             ptr(plan.node_graph) if gvec is not None else None, ptr(y), ptr(ssmr), float(drop_p), rng, salt)
+             ptr(plan.node_graph) if gvec is not None else None, ptr(y), ptr(ssmr), float(drop_p), rng, salt, ptr(m_valid))
+        ctx.m_valid = m_valid
         ctx.save_for_backward(x, ssmr, gamma)
         ctx.params = (gamma, beta)
         ctx.meta = (M, d, ld, relu, training, plan, resid is not None, gvec is not None, float(drop_p), salt)
@@ -1066,13 +1151,14 @@ class _BatchNormFn(torch.autograd.Function):
         dev = x.device
         rng = ptr(rng_state(dev)) if drop_p else None
         red = zeros_small(2 * ld, torch.float64, dev)
+        mv = ptr(ctx.m_valid)
         call("gt_bn_bwd_reduce", dt_of(x), ptr(x), ptr(g), M, d, ld, ptr(ssmr), int(relu), ptr(red), drop_p, rng,
-             salt)
+             salt, mv)
         dx = torch.empty_like(x)
         pg, pb = ctx.params
         (tg, dgamma), (tb, dbeta) = _grad_target(pg), _grad_target(pb)
         call("gt_bn_bwd_apply", dt_of(x), ptr(x), ptr(g), M, d, ld, ptr(ssmr), ptr(gamma), int(relu),
-             int(training), ptr(red), ptr(dx), ptr(tg), ptr(tb), drop_p, rng, salt)
+             int(training), ptr(red), ptr(dx), ptr(tg), ptr(tb), drop_p, rng, salt, mv)
         _grad_done(pg)
         _grad_done(pb)
         dres = g if has_resid else None
@@ -1080,17 +1166,60 @@ class _BatchNormFn(torch.autograd.Function):
         if has_gvec and ctx.needs_input_grad[11]:
             dgv = torch.empty(plan.B, ld, dtype=torch.float32, device=dev)
             call("gt_segment_sum_sorted", dt_of(g), ptr(g), ptr(plan.node_off), plan.B, ld, None, ptr(dgv))
-        return dx, dgamma, dbeta, None, None, None, None, None, None, None, dres, dgv, None, None, None, None
+        return dx, dgamma, dbeta, None, None, None, None, None, None, None, dres, dgv, None, None, None, None, None
 
 
-def batch_norm(x, bn: torch.nn.BatchNorm1d, relu=False, resid=None, gvec=None, plan=None, drop_p=0.0):
+def batch_norm(x, bn: torch.nn.BatchNorm1d, relu=False, resid=None, gvec=None, plan=None, drop_p=0.0, m_valid=None):
     """drop(act(BN(x))) [+ resid] [+ gvec[graph]] in one kernel; an input produced by ops.linear(col_stats=True) brings
     its column statistics along"""
     training = bn.training or bn.running_mean is None
     pre = getattr(x, "_gt_colstats", None) if (training and x.is_contiguous()) else None
+    if pre is not None and SKIP_ZERO_BIAS_GRAD and hasattr(x.grad_fn, "bias_grad_zero"):
+        x.grad_fn.bias_grad_zero = True      # producer = _LinearFn whose output goes straight into this train-mode BN
     return _BatchNormFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked,
                               training, bn.momentum, bn.eps, relu, resid, gvec, plan, drop_p,
-                              next_salt() if drop_p else 0, pre)
+                              next_salt() if drop_p else 0, pre, m_valid)
+
+
+# eval path (SURVEY §8f rank 3): a BatchNorm that directly follows a Linear is, with running statistics, an affine map
+# of the Linear's output - folded into the weight / bias once per evaluation phase, the layer is ONE contraction with
+# a ReLU epilogue instead of contraction + normalise pass.  y = s * (x W^T + b) + t, s = gamma * rsqrt(var + eps),
+# t = beta - mean * s  ->  W' = diag(s) W, b' = s * b + t.
+EVAL_FOLD_BN = int(os.environ.get("GT_EVAL_FOLD_BN", "1"))
+
+
+def fold_bn(lin: torch.nn.Linear, bn: torch.nn.BatchNorm1d):
+    """-> (W', b') of Linear followed by eval-mode BatchNorm, or None when folding does not apply (training, autograd on,
+    no running statistics).  Cached until the next training forward; bf16 mode keeps an operand copy in the registry."""
+    if not EVAL_FOLD_BN or bn.training or torch.is_grad_enabled() or bn.running_mean is None or not lin.weight.is_cuda:
+        return None
+    ent = lin.__dict__.get("_gt_fold")        # lives (and dies) with the module
+    # stale after any training forward (the fused optimizer writes through raw pointers) or any in-place update torch
+    # tracks (load_state_dict of best_model.pt before the final eval, reference main.py:262-267)
+    stamp = (_train_steps[0],) + tuple(t._version for t in (lin.weight, lin.bias, bn.weight, bn.bias, bn.running_mean,
+                                                              bn.running_var) if t is not None)
+    if ent is None or ent[0] != stamp or ent[3] is not bn or ent[1].device != lin.weight.device:
+        with torch.no_grad():
+            s = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
+            w = (lin.weight * s[:, None]).contiguous()
+            b0 = lin.bias if lin.bias is not None else torch.zeros_like(s)
+            b = ((b0 - bn.running_mean) * s + bn.bias).contiguous()
+        ent = (stamp, w, b, bn)
+        lin.__dict__["_gt_fold"] = ent
+        if _PRECISION == "bf16":
+            rows, cols = w.shape
+            ld = ldp(cols)
+            c = torch.empty(rows, ld, dtype=torch.bfloat16, device=w.device)
+            call("gt_cast_pad", GT_F32, ptr(w), rows, cols, cols, GT_BF16, ptr(c), rows, ld, ld)
+            w16.put(w, c, ld)
+    elif _PRECISION == "bf16" and w16.lookup(ent[1]) is None:     # another registry became current since the fold
+        w = ent[1]
+        rows, cols = w.shape
+        ld = ldp(cols)
+        c = torch.empty(rows, ld, dtype=torch.bfloat16, device=w.device)
+        call("gt_cast_pad", GT_F32, ptr(w), rows, cols, cols, GT_BF16, ptr(c), rows, ld, ld)
+        w16.put(w, c, ld)
+    return ent[1], ent[2]
 
 
 # ----------------------------------------------------------------------------- LayerNorm / tokens
@@ -1261,6 +1390,84 @@ def mha_packed(qkv, plan, nhead, key_start=None, drop_p=0.0):
     return _MHAFn.apply(qkv, plan, nhead, key_start, drop_p, next_salt() if drop_p else 0, None)
 
 
+class _MHAClsFn(torch.autograd.Function):
+    """attention of ONE query per graph (the pooled row) over all token rows of the graph: q [B, d], kv [n_rows, 2d]"""
+
+    @staticmethod
+    def forward(ctx, q, kv, plan, nhead, drop_p, salt):
+        q, kv = q.contiguous(), kv.contiguous()
+        B, d = q.shape
+        n_rows = kv.shape[0]
+        dh = d // nhead
+        scale = float(dh) ** -0.5
+        out = torch.empty(B, d, dtype=q.dtype, device=q.device)
+        lse = torch.empty(B * nhead, dtype=torch.float32, device=q.device)
+        call("gt_mha_cls_fwd", dt_of(q), ptr(q), ptr(kv), ptr(plan.tok_off), ptr(plan.cls_rows), n_rows, B, nhead, dh, scale,
+             ptr(out), ptr(lse), float(drop_p), ptr(rng_state(q.device)) if drop_p else None, salt)
+        ctx.save_for_backward(q, kv, out, lse)
+        ctx.meta = (plan, nhead, dh, scale, float(drop_p), salt)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        q, kv, out, lse = ctx.saved_tensors
+        plan, nhead, dh, scale, drop_p, salt = ctx.meta
+        g = g.contiguous()
+        dq, dkv = torch.empty_like(q), torch.empty_like(kv)
+        call("gt_mha_cls_bwd", dt_of(q), ptr(q), ptr(kv), ptr(out), ptr(g), ptr(lse), ptr(plan.tok_off), ptr(plan.cls_rows),
+             kv.shape[0], q.shape[0], nhead, dh, scale, ptr(dq), ptr(dkv), drop_p,
+             ptr(rng_state(q.device)) if drop_p else None, salt)
+        return dq, dkv, None, None, None, None
+
+
+def mha_pooled_query(q, kv, plan, nhead, drop_p=0.0):
+    """last encoder layer: only the pooled row of every graph is a query (reference models/gnn_transformer.py:114-115
+    reads `transformer_out[-1]` only); keys / values are all token rows of the graph"""
+    return _MHAClsFn.apply(q, kv, plan, nhead, drop_p, next_salt() if drop_p else 0)
+
+
+# ----------------------------------------------------------------------------- graph read-outs (baseline models)
+class _SegmentPoolFn(torch.autograd.Function):
+    """global_mean_pool / global_max_pool: [N, ld] -> fp32 [B, ld]"""
+
+    @staticmethod
+    def forward(ctx, x, plan, mode):
+        x = x.contiguous()
+        N, ld = x.shape
+        out = torch.empty(plan.B, ld, dtype=torch.float32, device=x.device)
+        arg = torch.empty(plan.B, ld, dtype=torch.int32, device=x.device) if mode == 2 else None
+        call("gt_segment_pool_fwd", dt_of(x), mode, ptr(x), ptr(plan.node_off), plan.B, ld, ptr(out), ptr(arg))
+        ctx.meta = (plan, mode, N, ld, x.dtype)
+        ctx.arg = arg
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        plan, mode, N, ld, dtype = ctx.meta
+        g = g.contiguous().float()
+        dx = torch.empty(N, ld, dtype=dtype, device=g.device)
+        call("gt_segment_pool_bwd", dt_of(dx), mode, ptr(g), ptr(plan.node_off), ptr(plan.node_graph), ptr(ctx.arg), N, ld,
+             ptr(dx))
+        return dx, None, None
+
+
+def segment_pool(x, plan, kind):
+    """kind in ('sum', 'mean', 'max'): PyG global_add_pool / global_mean_pool / global_max_pool over physical [N, ld]"""
+    if kind == "sum":
+        return segment_sum(x, plan)
+    return _SegmentPoolFn.apply(x, plan, {"mean": 1, "max": 2}[kind])
+
+
+def argmax_rows(x, n_cols=None):
+    """eval read-out: int64 [rows] index of the first maximum of the first n_cols columns of fp32 x"""
+    if x.dtype != torch.float32 or x.stride(-1) != 1:
+        x = x.float().contiguous()
+    rows, width = x.shape
+    out = torch.empty(rows, dtype=torch.int64, device=x.device)
+    call("gt_argmax_rows", ptr(x), rows, int(n_cols or width), x.stride(0), ptr(out))
+    return out
+
+
 # ----------------------------------------------------------------------------- PNA
 class _TowerLinearFn(torch.autograd.Function):
     """Block-diagonal ("tower") linear: y[:, t*Fo:(t+1)*Fo] = x[:, xo_t : xo_t+K] W_t[:, wo:wo+K]^T (+ b_t),
@@ -1324,6 +1531,82 @@ class _TowerLinearFn(torch.autograd.Function):
             else:
                 gbs.append(None)
         return (gx, None, None, None, None, None, *gws, *gbs)
+
+
+class _BlockDiagLinearFn(torch.autograd.Function):
+    """y = x . BD^T (+ b): the T towers of a PNA stage as ONE tensor-core contraction over the block-diagonal bf16 operand
+    the registry keeps (W16Registry.register_blockdiag; off-diagonal zero blocks only cost MMA slots - a tower slice
+    of width F = 68 is not 16-byte aligned, the whole matrix is).  Backward: dX = dY . BD (one contraction), the
+    operand gradient dBD = dY^T X is taken whole into a zeroed fp32 scratch (split-K) and its diagonal blocks are
+    added to the per-tower weight gradients by gt_add_blocks; bias gradients are column sums of dY."""
+
+    @staticmethod
+    def forward(ctx, x, key, col_lo, K, T, use_bias, *wb):
+        ws, bs = wb[:T], wb[T:]
+        op, ldk, bias = w16.bd_lookup(key)
+        x = x.contiguous()
+        M, ldx = x.shape
+        Fo = ws[0].shape[0]
+        N = T * Fo
+        ld_out = ldp(N)
+        y = torch.empty(M, ld_out, dtype=x.dtype, device=x.device)
+        _gemm_raw(dt_of(x), x.data_ptr(), 0, ldx, op.data_ptr(), 0, ldk, y.data_ptr(), ld_out, M, N, T * K, ld_out,
+                  bias if use_bias else None, None, 0, 0)
+        ctx.save_for_backward(x, op)
+        ctx.params = (ws, bs)
+        ctx.meta = (col_lo, K, T, Fo, use_bias, ldk, ld_out)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, op = ctx.saved_tensors
+        ws, bs = ctx.params
+        col_lo, K, T, Fo, use_bias, ldk, ld_out = ctx.meta
+        gy = gy.contiguous()
+        M, ldx = x.shape
+        N = T * Fo
+        gx = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty(M, ldx, dtype=x.dtype, device=x.device)
+            _gemm_raw(dt_of(x), gy.data_ptr(), 0, ld_out, op.data_ptr(), 1, ldk, gx.data_ptr(), ldx, M, T * K, N, ldx, None,
+                      None, 0, 0)
+        side_ok = all(_main_grad(t) is not None for t in ws) and (not use_bias or all(_main_grad(t) is not None for t in bs))
+        gws, gbs = [], []
+        with _WgradCtx(side_ok, gy, x):
+            ldt = ldp(T * K)
+            temp = zeros_small(N * ldt, torch.float32, x.device)
+            _gemm_raw(dt_of(x), gy.data_ptr(), 1, ld_out, x.data_ptr(), 1, ldx, temp.data_ptr(), ldt, N, T * K, M, T * K, None,
+                      None, 0, EPI_ACCUM | EPI_OUT_F32)
+            tg = [_grad_target(w) for w in ws]
+            a_dst = (ctypes.c_void_p * T)(*[t[0].data_ptr() + col_lo * 4 for t in tg])
+            a_ld = (ctypes.c_int32 * T)(*[w.shape[1] for w in ws])
+            a_r0 = (ctypes.c_int32 * T)(*[t * Fo for t in range(T)])
+            a_c0 = (ctypes.c_int32 * T)(*[t * K for t in range(T)])
+            a_rows = (ctypes.c_int32 * T)(*[Fo] * T)
+            a_cols = (ctypes.c_int32 * T)(*[K] * T)
+            call("gt_add_blocks", ptr(temp), ldt, T, a_dst, a_ld, a_r0, a_c0, a_rows, a_cols)
+            for t in range(T):
+                _grad_done(ws[t])
+                gws.append(tg[t][1])
+            if use_bias:
+                for t in range(T):
+                    tgt, gb = _grad_target(bs[t])
+                    lib_call_colsum(gy, t * Fo, M, Fo, ld_out, tgt)
+                    _grad_done(bs[t])
+                    gbs.append(gb)
+            else:
+                gbs = [None] * T
+        return (gx, None, None, None, None, None, *gws, *gbs)
+
+
+def blockdiag_linear(x, key, weights, biases, col_lo, K):
+    """tower Linears through the registry's block-diagonal operand `key`; None when it is not available (fp32 parity
+    mode, registry of another model current)"""
+    if x.dtype != torch.bfloat16 or w16.bd_lookup(key) is None:
+        return None
+    use_bias = biases is not None
+    bs = list(biases) if use_bias else [None] * len(weights)
+    return _BlockDiagLinearFn.apply(x, key, col_lo, K, len(weights), use_bias, *weights, *bs)
 
 
 def lib_call_colsum(g, col_off, M, n, ld, out):

@@ -1,7 +1,9 @@
 """Fused AdamW over the flat gradient arena of `ddp.GradBuckets` (one launch for all parameters; device-resident
 hyper-parameters and step counter, so the update is CUDA-graph capturable).  Same update rule as
 torch.optim.AdamW (reference main.py:178: AdamW(model.parameters(), lr, weight_decay); step at
-trainers/base_trainer.py:36).  The reference's optional clip_grad_norm_ (base_trainer.py:34-35) is not built."""
+trainers/base_trainer.py:36).  The reference's optional `clip_grad_norm_(model.parameters(), args.grad_clip)`
+(base_trainer.py:34-35) is `max_grad_norm`: one gt_sumsq launch over the arena, the clip coefficient is applied inside the
+optimizer's gradient read (the arena itself stays unscaled)."""
 from __future__ import annotations
 
 import torch
@@ -10,7 +12,7 @@ from ._lib import call, ptr
 
 
 class FusedAdamW:
-    def __init__(self, buckets, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
+    def __init__(self, buckets, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, max_grad_norm=None):
         self.buckets = buckets
         flat = buckets.flat
         if not flat.is_cuda:
@@ -20,6 +22,10 @@ class FusedAdamW:
         self.hyper = torch.tensor([lr, betas[0], betas[1], eps, weight_decay], dtype=torch.float32, device=flat.device)
         self.step_count = torch.zeros(1, dtype=torch.int64, device=flat.device)
         self.enabled = True
+        # {max_norm, sum of squares}: device-resident so that a captured step sees set_max_grad_norm() updates
+        self.clip = None
+        if max_grad_norm is not None and max_grad_norm > 0:
+            self.clip = torch.tensor([float(max_grad_norm), 0.0], dtype=torch.float32, device=flat.device)
         self._desc = self._ptrs = None
         self._blocks = 0
 
@@ -44,8 +50,15 @@ class FusedAdamW:
             return
         if self._desc is None or self._ptrs != tuple(p.data_ptr() for p in self.buckets.params):
             self._build()
+        if self.clip is not None:
+            self.clip[1:2].zero_()
+            call("gt_sumsq", ptr(self.buckets.flat), self.buckets.flat.numel(), self.clip.data_ptr() + 4)
         call("gt_adamw_multi", ptr(self._desc), self._desc.shape[0], self._blocks, ptr(self.buckets.flat), ptr(self.m),
-             ptr(self.v), ptr(self.hyper), ptr(self.step_count))
+             ptr(self.v), ptr(self.hyper), ptr(self.step_count), ptr(self.clip))
+
+    def grad_norm(self):
+        """total gradient norm of the last step (device scalar; only tracked with max_grad_norm)"""
+        return None if self.clip is None else self.clip[1].sqrt()
 
     def zero_grad(self):
         self.buckets.zero_grad()

@@ -24,7 +24,10 @@ CODE2_NUM_CLASSES = 5002
 
 
 class GraphBatch:
-    """Attribute bag standing in for torch_geometric.data.Batch."""
+    """Attribute bag standing in for torch_geometric.data.Batch.
+
+    A *packed* batch (graphtrans_b200.loader.pack) keeps every tensor as a view into ONE byte blob (`_blob`, layout in
+    `_layout`): moving it to the device is a single copy of the blob, after which the views are rebuilt."""
 
     _TENSOR_FIELDS = ("x", "edge_index", "edge_attr", "batch", "node_depth", "y", "y_arr")
 
@@ -32,8 +35,22 @@ class GraphBatch:
         for k, v in kw.items():
             setattr(self, k, v)
 
+    def tensors(self):
+        """(name, tensor) of the public tensor fields (the blob of a packed batch is not one of them)"""
+        return [(k, v) for k, v in self.__dict__.items() if torch.is_tensor(v) and not k.startswith("_")]
+
     def _map(self, fn):
+        blob = self.__dict__.get("_blob")
         out = GraphBatch()
+        if blob is not None:
+            new_blob = fn(blob)
+            for k, v in self.__dict__.items():
+                if not torch.is_tensor(v):
+                    setattr(out, k, v)
+            out._blob = new_blob
+            for name, dtype, shape, off, nbytes in self._layout:
+                setattr(out, name, new_blob[off:off + nbytes].view(dtype).view(shape))
+            return out
         for k, v in self.__dict__.items():
             setattr(out, k, fn(v) if torch.is_tensor(v) else v)
         return out
@@ -48,7 +65,10 @@ class GraphBatch:
         return self._map(lambda t: t.clone())
 
     def nbytes(self):
-        return sum(v.numel() * v.element_size() for v in self.__dict__.values() if torch.is_tensor(v))
+        blob = self.__dict__.get("_blob")
+        if blob is not None:
+            return blob.numel()
+        return sum(v.numel() * v.element_size() for _, v in self.tensors())
 
 
 def _undirected_pairs(rng, n_per_graph, pairs_per_graph, offsets, allow_self=True):

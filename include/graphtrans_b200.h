@@ -165,8 +165,11 @@ int gt_add_graph_vec(int dt, const void* x, const float* v, const int32_t* node_
                      int32_t ld, void* y, void* stream);
 
 /* ---- BatchNorm1d, train/eval (reference modules/gnn_module.py:58,84,164,167; conv.py:19) ---
- * colstats: stats[0:ld] += sum_rows x, stats[ld:2ld] += sum_rows x^2 (fp64, pre-zeroed). */
-int gt_colstats(int dt, const void* x, int64_t M, int32_t ld, double* stats, void* stream);
+ * colstats: stats[0:ld] += sum_rows x, stats[ld:2ld] += sum_rows x^2 (fp64, pre-zeroed).
+ * m_valid (optional DEVICE int32[1], all BatchNorm entry points): only the leading m_valid[0] rows are real; the rest is
+ * shape-bucket slack (batches padded up to a bucket so that CUDA-graph signatures repeat, graphtrans_b200/graphed.py):
+ * slack rows stay out of the batch statistics (divisor m_valid[0]) and receive a zero gradient.  NULL = all M rows. */
+int gt_colstats(int dt, const void* x, int64_t M, int32_t ld, double* stats, const int32_t* m_valid, void* stream);
 /* finalize: from stats (train) or running stats (eval) produce scale/shift (y = x*scale+shift)
  * and mean/rstd; in train mode update running_mean/var (momentum, unbiased var) and ++nbt. */
 int gt_bn_finalize(const double* stats, int64_t M, int32_t d, int32_t ld, const float* gamma,
@@ -184,18 +187,18 @@ int gt_bn_norm_fwd(int dt, const void* x, int64_t M, int32_t d, int32_t ld, cons
                    const float* gamma, const float* beta, float* running_mean, float* running_var,
                    int64_t* nbt, float momentum, float eps, int training, int relu, const void* resid,
                    const float* gvec, const int32_t* node_graph, void* y, float* ssmr, float drop_p,
-                   const uint64_t* rng_state, uint64_t salt, void* stream);
+                   const uint64_t* rng_state, uint64_t salt, const int32_t* m_valid, void* stream);
 /* backward pass 1: g = dy * keep/(1-p) * relu'(x*scale+shift); red[0:ld] += sum g,
  * red[ld:2ld] += sum g*xhat */
 int gt_bn_bwd_reduce(int dt, const void* x, const void* dy, int64_t M, int32_t d, int32_t ld,
                      const float* ssmr, int relu, double* red, float drop_p, const uint64_t* rng_state,
-                     uint64_t salt, void* stream);
+                     uint64_t salt, const int32_t* m_valid, void* stream);
 /* backward pass 2: dx = gamma*rstd*(g - red0/M - xhat*red1/M) (train) or g*scale (eval);
  * dgamma += red1, dbeta += red0 (fp32 [d], accumulated so that gradients can be summed in place) */
 int gt_bn_bwd_apply(int dt, const void* x, const void* dy, int64_t M, int32_t d, int32_t ld,
                     const float* ssmr, const float* gamma, int relu, int training, const double* red,
                     void* dx, float* dgamma, float* dbeta, float drop_p, const uint64_t* rng_state,
-                    uint64_t salt, void* stream);
+                    uint64_t salt, const int32_t* m_valid, void* stream);
 
 /* ---- dense contraction (replaces nn.Linear -> cuBLAS, reference modules/conv.py:18-20,44;
  *      modules/gnn_module.py:161-170; models/gnn_transformer.py:70,85-88; the in/out
@@ -217,7 +220,8 @@ int gt_gemm(int dt, const void* A, int a_mn, int64_t lda, const void* B, int b_m
 int gt_gemm_stats(int dt, const void* A, int a_mn, int64_t lda, const void* B, int b_mn, int64_t ldb,
                   void* C, int64_t ldc, int64_t M, int64_t N, int64_t K, int64_t n_fill,
                   const float* bias, const void* resid, int64_t ldr, int flags, float drop_p,
-                  const uint64_t* rng_state, uint64_t salt, int impl, double* col_stats, void* stream);
+                  const uint64_t* rng_state, uint64_t salt, int impl, double* col_stats, const int32_t* m_valid,
+                  void* stream);
 /* dz = dy * (y > 0) * scale: backward of a ReLU (+ dropout: a dropped element has y == 0, scale = 1/(1-p)) that
  * was fused into a GEMM epilogue; n % 4 == 0 */
 int gt_relu_bwd(int dt, const void* dy, const void* y, int64_t n, void* dz, float scale, void* stream);
@@ -229,10 +233,17 @@ int gt_cast_pad(int dt_in, const void* src, int64_t rows_in, int64_t cols_in, in
                 int dt_out, void* dst, int64_t rows_out, int64_t cols_out, int64_t ld_out, void* stream);
 
 /* every fp32 master weight of the model -> its zero-padded bf16 operand copy in ONE launch (once per step; replaces
- * what torch autocast does per nn.Linear call).  desc_dev: DEVICE int64[n][6] = {src fp32 [rows, cols] contiguous,
- * dst bf16 [rows, ld_dst], rows, cols, ld_dst, first block}; a block covers 2048 destination elements and
- * total_blocks = sum over tensors of ceil(rows*ld_dst / 2048). */
+ * what torch autocast does per nn.Linear call).  desc_dev: DEVICE int64[n][8] = {src fp32 [rows, cols], dst bf16
+ * [rows, ld_dst] (ld_dst < 0: fp32 destination with row pitch -ld_dst), rows, cols, ld_dst, first block, ld_src (0 =
+ * cols), width (0 = |ld_dst|: destination columns written per row; columns cols..width-1 := 0)}; a block covers 2048
+ * (row, column < width) elements and total_blocks = sum over tensors of ceil(rows*width / 2048).  width < ld_dst
+ * writes a sub-block of a larger matrix (the diagonal blocks of the PNA tower operands, modules/pna_layer.py:102-118). */
 int gt_cast_multi(const int64_t* desc_dev, int32_t n, int64_t total_blocks, void* stream);
+/* dst_b[r, c] += src[r0_b + r, c0_b + c] for n <= 16 rectangular blocks of the fp32 matrix src [*, ld_src]: gradients of
+ * the diagonal blocks of a block-diagonal operand added into the per-tower parameter gradients (all arrays HOST). */
+int gt_add_blocks(const float* src, int32_t ld_src, int32_t n, float* const* dst_host, const int32_t* ld_dst_host,
+                  const int32_t* r0_host, const int32_t* c0_host, const int32_t* rows_host, const int32_t* cols_host,
+                  void* stream);
 
 /* ---- token packing + LayerNorm (reference modules/utils.py:5-29 pad_batch,
  *      modules/transformer_encoder.py:50-57 CLS append + norm_input) --------------------------
@@ -307,13 +318,44 @@ int gt_mha_local_bwd(int dt, const void* qkv, const void* out, const void* dout,
                      int32_t dh, float scale, void* dqkv, float drop_p, const uint64_t* rng_state, uint64_t salt,
                      void* stream);
 
+/* Pooled-query attention of the LAST encoder layer: the model reads only the pooled row of the encoder output
+ * (reference models/gnn_transformer.py:114-115 `transformer_out[-1]`), so that layer needs ONE query per graph.
+ * q [B, d] (unscaled query rows), kv [n_rows, 2d] (k | v of every packed token), q_rows int32 [B] = packed row of each
+ * query (dropout row id: the same probabilities are dropped as in a full-layer run), out [B, d], lse fp32 [B, nhead].
+ * Backward: dq [B, d], dkv [n_rows, 2d] fully overwritten (rows beyond tok_off[B] := 0).  dh % 4 == 0, dh <= 64. */
+int gt_mha_cls_fwd(int dt, const void* q, const void* kv, const int32_t* tok_off, const int32_t* q_rows,
+                   int64_t n_rows, int64_t B, int32_t nhead, int32_t dh, float scale, void* out, float* lse,
+                   float drop_p, const uint64_t* rng_state, uint64_t salt, void* stream);
+int gt_mha_cls_bwd(int dt, const void* q, const void* kv, const void* out, const void* dout, const float* lse,
+                   const int32_t* tok_off, const int32_t* q_rows, int64_t n_rows, int64_t B, int32_t nhead,
+                   int32_t dh, float scale, void* dq, void* dkv, float drop_p, const uint64_t* rng_state,
+                   uint64_t salt, void* stream);
+
 /* ---- fused AdamW (reference main.py:178 optim.AdamW; trainers/base_trainer.py:36 optimizer.step()) ----------
  * One launch for all parameters.  desc_dev int64 [n][4] = {parameter pointer (fp32), offset of its gradient / moments in
  * the flat arenas (elements), numel, first block}; a block updates 2048 elements; total_blocks = sum ceil(numel/2048).
  * hyper_dev fp32 [5] = {lr, beta1, beta2, eps, weight_decay} and step_dev int64 [1] are DEVICE memory (graph replay sees
  * host updates); the call increments *step_dev first.  p = p (1 - lr wd) - lr/(1-b1^t) m / (sqrt(v)/sqrt(1-b2^t) + eps). */
 int gt_adamw_multi(const int64_t* desc_dev, int32_t n, int64_t total_blocks, const float* grad_flat, float* m_flat,
-                   float* v_flat, const float* hyper_dev, int64_t* step_dev, void* stream);
+                   float* v_flat, const float* hyper_dev, int64_t* step_dev, const float* clip_dev, void* stream);
+/* clip_dev (optional DEVICE fp32[2] = {max_norm, sum of squares of the gradient arena}): torch.nn.utils.clip_grad_norm_
+ * (reference trainers/base_trainer.py:34-35) folded into the optimizer's gradient read - every gradient is scaled by
+ * min(1, max_norm / (sqrt(sumsq) + 1e-6)); the arena itself is left unscaled.  gt_sumsq accumulates sum x^2 of a
+ * 16-byte aligned fp32 buffer into out[0] (pre-zeroed by the caller; with several ranks run it after the allreduce). */
+int gt_sumsq(const float* x, int64_t n, float* out, void* stream);
+
+/* ---- graph-level read-outs of the reference's baseline models (PyG global_mean_pool / global_max_pool, reference
+ *      models/gnn.py:64-69, models/pna.py:74-79, models/transformer.py:49-54; global_add_pool = gt_segment_sum_sorted) --
+ * mode 1 = mean, 2 = max over the rows [node_off[g], node_off[g+1]) of x [N, ld]; out fp32 [B, ld]; an empty graph gives
+ * 0.  arg int32 [B, ld] (max only): row index of the first maximum, used by the backward (gradient to one winner per
+ * (graph, channel), torch_scatter semantics).  Backward: dx [N, ld] (activation dtype) fully overwritten; node_graph < 0
+ * (shape-bucket slack nodes) -> 0. */
+int gt_segment_pool_fwd(int dt, int mode, const void* x, const int32_t* node_off, int64_t B, int32_t ld,
+                        float* out, int32_t* arg, void* stream);
+int gt_segment_pool_bwd(int dt, int mode, const float* dout, const int32_t* node_off, const int32_t* node_graph,
+                        const int32_t* arg, int64_t N, int32_t ld, void* dx, void* stream);
+/* eval read-out: out[r] = index of the first maximum of x[r, :cols] (reference dataset/code.py:64 torch.argmax) */
+int gt_argmax_rows(const float* x, int64_t rows, int32_t cols, int64_t ldx, int64_t* out, void* stream);
 
 /* ---- PNA multi-aggregator reduce (reference modules/pna_layer.py:131-167 via
  *      modules/pna/pna_module.py:43-51; aggregators.py:11-34; scalers.py:10-31) ---------------

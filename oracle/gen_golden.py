@@ -48,6 +48,9 @@ def reference_model(args):
                 return 0
             return zero
     model_cls = MODELS[args.model_type]
+    if ds != "code2" and model_cls.get_emb_dim(args) != args.gnn_emb_dim:     # reference dataset/mol.py:83, tud.py:65
+        emb = model_cls.get_emb_dim(args)
+        node_encoder = AtomEncoder(emb) if ds in ("mol", "syn") else nn.Linear(37, emb)
     return model_cls(num_tasks=args.num_tasks, args=args, node_encoder=node_encoder,
                      edge_encoder_cls=edge_encoder_cls)
 
@@ -147,6 +150,19 @@ def cases():
     a = small_args("code2-pna", gnn_emb_dim=40, gnn_num_layer=2, num_tasks=50, max_seq_len=3,
                    deg=synth.in_degree_histogram(b, 800))
     out["pna_code2"] = (a, b)
+    # baseline model families on the same kernels
+    a = small_args("molpcba", model_type="gnn", gnn_emb_dim=36, num_tasks=12, gnn_JK="last", graph_pooling="mean")
+    out["zgnn_gin_virtual_mean_mol"] = (a, synth.gen_mol(7, seed=8, num_tasks=12))
+    a = small_args("nci1", model_type="gnn", gnn_JK="sum", graph_pooling="max")
+    out["zgnn_gcn_max_nci1"] = (a, synth.gen_nci1(6, seed=9))
+    b = synth.gen_mol(6, seed=10, num_tasks=12)
+    a = small_args("molpcba", model_type="pna", gnn_emb_dim=40, gnn_num_layer=2, num_tasks=12, gnn_residual=True,
+                   graph_pooling="sum", deg=synth.in_degree_histogram(b, 10))
+    out["zpna_sum_mol"] = (a, b)
+    a = small_args("molpcba", model_type="transformer", num_tasks=12, graph_pooling="cls")
+    out["ztransformer_cls_mol"] = (a, synth.gen_mol(6, seed=11, num_tasks=12))
+    a = small_args("nci1", model_type="transformer", graph_pooling="mean", max_input_len=9)
+    out["ztransformer_mean_trunc_nci1"] = (a, synth.gen_nci1(5, seed=12))
     return out
 
 

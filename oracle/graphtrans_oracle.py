@@ -236,10 +236,10 @@ def pna_conv(ctx, prefix, args, x, edge_index, towers=4):
     return linear(sd, prefix + ".lin", torch.cat(outs, dim=1))
 
 
-def pna_node(ctx, args, batch, perturb=None, prefix="gnn_node"):
+def pna_node(ctx, args, batch, perturb=None, prefix="gnn_node", enc_prefix=None):
     """PNANodeEmbedding.forward, reference modules/pna/pna_module.py:57-78."""
     sd = ctx.sd
-    x = encode_nodes(sd, prefix + ".node_encoder", args.dataset, batch)
+    x = encode_nodes(sd, enc_prefix or (prefix + ".node_encoder"), args.dataset, batch)
     if perturb is not None:
         x = x + perturb
     for layer in range(args.gnn_num_layer):
@@ -312,12 +312,79 @@ def transformer_encoder(sd, args, padded, mask, prefix="transformer_encoder"):
     return x, mask
 
 
+# ------------------------------------------------------------------ baseline models
+def global_pool(h, bidx, B, kind):
+    """PyG global_add_pool / global_mean_pool / global_max_pool = torch_scatter.scatter over `batch` (Appendix A.3:
+    mean divides by clamp(count, 1); an empty segment of max gives 0)."""
+    if kind == "sum":
+        return scatter_sum(h, bidx, B)
+    if kind == "mean":
+        cnt = degree(bidx, B, h.dtype).clamp(min=1).view(-1, 1)
+        return scatter_sum(h, bidx, B) / cnt
+    if kind == "max":
+        init = torch.zeros((B, h.shape[1]), dtype=h.dtype)
+        return init.scatter_reduce(0, bidx.view(-1, 1).expand_as(h), h, "amax", include_self=False)
+    raise NotImplementedError(kind)
+
+
+def heads(sd, args, hg):
+    if args.max_seq_len is None:
+        return linear(sd, "graph_pred_linear", hg)
+    return [linear(sd, f"graph_pred_linear_list.{i}", hg) for i in range(args.max_seq_len)]
+
+
+def unpad_batch(out, prev, batch_idx, max_input_len):
+    """reference modules/utils.py:32-53: the last k_i = min(n_i, S) nodes of graph i take padded rows [S - k_i, S) of
+    `out` [S, B, d]; nodes truncated away keep `prev`."""
+    n, off, k, S = pad_plan(batch_idx, max_input_len)
+    N = prev.shape[0]
+    g = batch_idx
+    pos = torch.arange(N) - off[g] - n[g] + S
+    valid = pos >= 0
+    src = out[pos.clamp(min=0), g]
+    return torch.where(valid.view(-1, 1), src, prev)
+
+
+def forward_baseline(ctx, sd, args, batch, perturb):
+    """GNN.forward (reference models/gnn.py:100-115), PNANet.forward (models/pna.py:96-108) and Transformer.forward
+    (models/transformer.py:86-115)."""
+    bidx = batch.batch
+    B = int(bidx[-1]) + 1
+    if args.model_type == "gnn":
+        hg = global_pool(gnn_node(ctx, args, batch, perturb), bidx, B, args.graph_pooling)
+        return heads(sd, args, hg)
+    if args.model_type == "pna":
+        # PNANet registers the node encoder twice (models/pna.py:49,51): named_parameters() reports it as `node_encoder.*`
+        hg = global_pool(pna_node(ctx, args, batch, perturb, prefix="pna_module", enc_prefix="node_encoder"), bidx, B,
+                         args.graph_pooling)
+        if args.max_seq_len is None:
+            h = F.relu(linear(sd, "mlp.0", hg))
+            h = F.relu(linear(sd, "mlp.2", h))
+            return linear(sd, "mlp.4", h)
+        return [linear(sd, f"graph_pred_linear_list.{i}.2", F.relu(linear(sd, f"graph_pred_linear_list.{i}.0", hg)))
+                for i in range(args.max_seq_len)]
+    if args.model_type == "transformer":
+        tmp = encode_nodes(sd, "node_encoder", args.dataset, batch)
+        if perturb is not None:
+            tmp = tmp + perturb
+        padded, mask = pad_batch(tmp, bidx, int(args.max_input_len))
+        out, _ = transformer_encoder(sd, args, padded, mask, prefix="transformer")
+        if args.graph_pooling == "cls":
+            hg = out[-1]
+        else:
+            hg = global_pool(unpad_batch(out, tmp, bidx, int(args.max_input_len)), bidx, B, args.graph_pooling)
+        return heads(sd, args, hg)
+    raise ValueError(args.model_type)
+
+
 # ------------------------------------------------------------------ model (a1, a7, a11, a12)
 def forward(sd, args, batch, training=True, perturb=None):
     """GNNTransformer.forward (reference models/gnn_transformer.py:90-128) and
     PNATransformer.forward (reference models/pna_transformer.py:78-100).
     Returns (logits or list of logits, dict of updated BN buffers)."""
     ctx = _Ctx(sd, training)
+    if args.model_type in ("gnn", "pna", "transformer"):
+        return forward_baseline(ctx, sd, args, batch, perturb), ctx.new_buffers
     if args.model_type == "pna-transformer":
         h = pna_node(ctx, args, batch, perturb)
     else:
