@@ -1,17 +1,25 @@
 #!/usr/bin/env python
 """graphs/sec forward+backward of the GraphTrans hot path on N B200s (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--config molpcba|code2|syn|code2-pna|nci1]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config syn|molpcba|code2|code2-pna|nci1]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
     python bench.py --impl reference ...      # the reference's CPU path (oracle port) on the host cores
+    python bench.py --impl torch-gpu ...      # the same restatement on the B200 through stock torch kernels (comparator)
 
-One "step" = zero_grad -> forward -> loss -> backward (+ bucketed NCCL gradient allreduce when
-N > 1) over one synthetic batch of the named config.  Rank 0 prints ONE JSON line.
+Headline workload = BASELINE.json configs[3] (the one its scaling sweep is defined on): synthetic graphs n~U{64..192},
+4 GIN + 4 Tx layers, d = 256, GLOBAL batch 4096, STRONG scaling over N GPUs (4096 / N graphs per rank).  Configs 2, 3 and
+5 (molpcba B=512, Code2 B=128, Code2-PNA B=128 per GPU) are timed in the same run and carried under `configs`.
+
+One "step" = zero_grad -> forward -> loss -> backward (+ bucketed NCCL gradient allreduce, captured inside the CUDA graph
+of the step, when N > 1) over one synthetic batch.  Rank 0 prints ONE JSON line.
   value : whole-job graphs/s with the batches already resident in HBM (CUDA events, max over ranks)
-  e2e   : same metric through the public model API with HOST (pinned) batches: H2D copy of the
-          step's batch and a D2H read of the loss inside the timed region
-  roofline     : dominant hot-stage kernel class, achieved = algorithmic bytes|flops (SURVEY §8d,
-                 DESIGN.md) / CUDA-event time of those launches, peak from MEASURED_PEAKS.json
+  e2e   : same metric through the public API (GraphedStep over loader.prepare'd HOST batches) on batches the step has
+          NEVER seen: the H2D copy of each batch (one pinned blob, prefetched on a copy stream while the previous step
+          runs) and a D2H read of the loss inside the timed region
+  roofline     : the hot-stage kernel BASELINE.json quotes the config on, timed IN the captured step (device timestamps
+                 after every kernel of the replayed graph, graphtrans_b200/trace.py): achieved = algorithmic bytes|flops
+                  / in-step time; peak from MEASURED_PEAKS.json.  `alone` = the same kernels replayed back
+                 to back outside the step.
   cpu_baseline : the CPU oracle (port of the reference's PyTorch path) timed on the host cores
 """
 import argparse
@@ -32,8 +40,10 @@ from graphtrans_b200 import synth  # noqa: E402
 
 METRIC = "graphs/sec fwd+bwd"
 UNIT = "graphs/s"
-# CPU sample sizes (graphs per step) keeping the reference arm / cpu_baseline to ~10-30 s of CPU work
-CPU_SAMPLE_B = {"molpcba": 128, "code2": 8, "syn": 32, "code2-pna": 8, "nci1": 32}
+HEADLINE = "syn"
+EXTRA_CONFIGS = ("molpcba", "code2", "code2-pna")
+# graphs per CPU step: the full batch where a step costs ~1 s of CPU time, a bounded sample otherwise
+CPU_SAMPLE_B = {"molpcba": 512, "code2": 8, "syn": 32, "code2-pna": 8, "nci1": 32}
 
 
 def parse():
@@ -41,20 +51,26 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default="molpcba", choices=list(synth.CONFIGS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "torch-gpu"])
+    ap.add_argument("--config", default=HEADLINE, choices=list(synth.CONFIGS))
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--batch", type=int, default=None, help="graphs per GPU per step (default: the config's)")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--batch", type=int, default=None, help="graphs per step (global with --scaling strong, per GPU with weak)")
+    ap.add_argument("--scaling", default=None, choices=["weak", "strong"], help="default: strong for syn (BASELINE's sweep), weak otherwise")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-optimizer", action="store_true", help="skip the second figure (step + fused AdamW update)")
+    ap.add_argument("--no-extra-configs", action="store_true", help="only the headline workload (no `configs` entries)")
     ap.add_argument("--distinct-batches", type=int, default=4)
     ap.add_argument("--no-wgrad-stream", action="store_true", help="keep weight gradients on the main stream")
     ap.add_argument("--no-branch-stream", action="store_true", help="keep the virtual-node branch on the main stream")
     ap.add_argument("--eager", action="store_true", help="no CUDA-graph replay: launch every kernel from Python")
-    return ap.parse_args()
+    ap.add_argument("--comm", default="graph", choices=["graph", "host"],
+                    help="N > 1: gradient allreduce captured inside the step's CUDA graph (default) or issued from the host after the replay")
+    ns = ap.parse_args()
+    if ns.scaling is None:
+        ns.scaling = "strong" if ns.config == "syn" else "weak"
+    return ns
 
 
 def peaks():
@@ -65,12 +81,21 @@ def peaks():
     return dict(hbm=6650.0, tensor=1590.0, source="fallback")
 
 
-def config_args(ns):
-    args = synth.make_args(ns.config)
-    if ns.config == "code2-pna":
+def config_args(cfg):
+    args = synth.make_args(cfg)
+    if cfg == "code2-pna":
         probe = synth.make_batch(args, B=args.batch_size, seed=1234)
         args.deg = synth.in_degree_histogram(probe, 800)
     return args
+
+
+def workload_name(cfg, args, B_global, scaling, world):
+    arch = f"{args.gnn_type.upper() if args.model_type == 'gnn-transformer' else 'PNA'}{'-Virtual' if args.gnn_virtual_node else ''}"
+    base = (f"{cfg}: GraphTrans {arch} JK={args.gnn_JK} d_g={args.gnn_emb_dim} L_g={args.gnn_num_layer} d={args.d_model} "
+            f"L_t={args.num_encoder_layers}")
+    if scaling == "strong":
+        return base + f" global B={B_global} (strong scaling: B/N graphs per GPU)"
+    return base + f" B={B_global // max(world, 1)}/GPU"
 
 
 # ----------------------------------------------------------------------------------- clocks
@@ -122,62 +147,102 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-# ----------------------------------------------------------------------------------- CPU arm
-def cpu_reference_run(ns, steps, warmup):
-    """Times the CPU oracle (restatement of the reference's PyTorch/PyG path, fp32, all host
-    threads) on a bounded sample of the workload. -> (graphs/s, ms/step, description dict)"""
+# ----------------------------------------------------------------------------------- CPU arm / torch-gpu arm
+def oracle_run(cfg, B_full, steps, warmup, device="cpu", autocast=False):
+    """Times the oracle (restatement of the reference's PyTorch/PyG path) on a bounded sample of the workload, on the
+    host cores (device='cpu', fp32, all threads) or on the GPU through stock torch kernels (device='cuda').
+    -> (graphs/s, ms/step, description dict)"""
     from graphtrans_b200 import factory
     from oracle import graphtrans_oracle as O
-    args = config_args(ns)
+    args = config_args(cfg)
     args.gnn_dropout = 0.0           # the oracle has no dropout (identity); the product runs the configured p
     args.transformer_dropout = 0.0
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    Bs = min(CPU_SAMPLE_B[ns.config], ns.batch or args.batch_size)
+    Bs = min(CPU_SAMPLE_B[cfg], B_full) if device == "cpu" else B_full
     batch = synth.make_batch(args, B=Bs, seed=0)
     torch.manual_seed(0)
     sd = factory.build_model(args).state_dict()
+    if device != "cpu":
+        sd = {k: v.to(device) for k, v in sd.items()}
+        batch = batch.to(device)
+
+    def one():
+        if autocast:
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                O.fwd_bwd(sd, args, batch, dtype=torch.float32)
+        else:
+            O.fwd_bwd(sd, args, batch, dtype=torch.float32)
+        if device != "cpu":
+            torch.cuda.synchronize()
+
     for _ in range(warmup):
-        O.fwd_bwd(sd, args, batch, dtype=torch.float32)
+        one()
     t0 = time.perf_counter()
     for _ in range(steps):
-        O.fwd_bwd(sd, args, batch, dtype=torch.float32)
+        one()
     dt = (time.perf_counter() - t0) / steps
-    return Bs / dt, dt * 1e3, dict(cores=cores, threads=torch.get_num_threads(), kind="port",
-                                   sample=f"{Bs} of {ns.batch or args.batch_size} graphs/step ({ns.config} shape, seed 0), "
-                                          f"fp32, dropout 0, {warmup} warm-up + {steps} timed fwd+bwd steps of "
-                                          f"oracle/graphtrans_oracle.py")
+    sample = (f"{Bs} of {B_full} graphs/step ({cfg} shape, seed 0), fp32, dropout 0, {warmup} warm-up + {steps} timed "
+              f"fwd+bwd steps of oracle/graphtrans_oracle.py")
+    return Bs / dt, dt * 1e3, dict(cores=cores, threads=torch.get_num_threads(), kind="port", sample=sample, graphs=Bs)
 
 
 def main_reference(ns):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warmup = ns.steps, ns.warmup
-    # bound the arm to a few minutes whatever K the driver passes: cap total CPU steps
-    est_steps = min(steps, 10)
-    gps, ms, desc = cpu_reference_run(ns, est_steps, min(warmup, 2))
-    args = synth.make_args(ns.config)
+    args = config_args(ns.config)
+    B_global = ns.batch or args.batch_size * (1 if ns.scaling == "strong" else max(ns.gpus, 1))
+    # bound the arm to a few minutes whatever K the driver passes: cap the timed CPU steps
+    est_steps = min(ns.steps, 5 if CPU_SAMPLE_B[ns.config] >= 256 else 10)
+    gps, ms, desc = oracle_run(ns.config, B_global, est_steps, min(ns.warmup, 1))
     line = {
-        "impl": "reference", "metric": METRIC, "value": gps, "unit": UNIT, "n_gpus": ns.gpus, "steps": steps,
-        "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": ns.scaling, "vs_baseline": None,
+        "impl": "reference", "metric": METRIC, "value": gps, "unit": UNIT, "n_gpus": ns.gpus, "steps": ns.steps,
+        "warmup": ns.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": ns.scaling, "vs_baseline": None,
         "dtype": "fp32", "data": "synthetic",
-        "config": {"workload": workload_name(ns, args), "timed_steps": est_steps,
-                   "note": "CPU path of the reference (oracle port; the reference is pure Python and its "
-                           "third-party deps are not installable here, so there is no oracle/_ref)"},
-        "cpu_baseline": {"value": gps, "unit": UNIT, "cores": desc["cores"], "kind": desc["kind"],
-                         "sample": desc["sample"]},
+        "config": {"workload": workload_name(ns.config, args, B_global, ns.scaling, ns.gpus), "timed_steps": est_steps,
+                   "note": "CPU path of the reference (oracle port; the reference is pure Python and its third-party deps are "
+                           "not installable here, so there is no oracle/_ref); each step = a bounded sample of the workload, "
+                           "graphs/s = sample graphs / step time"},
+        "cpu_baseline": {"value": gps, "unit": UNIT, "cores": desc["cores"], "kind": desc["kind"], "sample": desc["sample"]},
         "e2e": {"value": gps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-def workload_name(ns, args):
-    B = ns.batch or args.batch_size
-    return (f"{ns.config}: GraphTrans {args.gnn_type.upper() if args.model_type == 'gnn-transformer' else 'PNA'}"
-            f"{'-Virtual' if args.gnn_virtual_node else ''} JK={args.gnn_JK} d_g={args.gnn_emb_dim} "
-            f"L_g={args.gnn_num_layer} d={args.d_model} L_t={args.num_encoder_layers} B={B}/GPU")
+def main_torch_gpu(ns):
+    """the GPU comparator: the same restatement of the reference's path executed on the B200 by stock
+    torch kernels (cuBLAS GEMMs, ATen scatter / softmax / norms), fp32 and under bf16 autocast"""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    assert torch.cuda.is_available()
+    out = {}
+    for cfg in ([ns.config] if ns.no_extra_configs else [ns.config] + [c for c in EXTRA_CONFIGS if c != ns.config]):
+        args = config_args(cfg)
+        B = ns.batch if (ns.batch and cfg == ns.config) else args.batch_size
+        if cfg == "syn":
+            B = min(B, 1024)          # the padded [T, B, d] attention of the restatement materialises B*h*T*T scores
+        res = {}
+        for name, ac in (("fp32", False), ("bf16_autocast", True)):
+            try:
+                gps, ms, desc = oracle_run(cfg, B, min(ns.steps, 10), 2, device="cuda", autocast=ac)
+                res[name] = {"value": gps, "ms_per_step": ms, "graphs_per_step": desc["graphs"]}
+            except Exception as e:  # noqa: BLE001
+                res[name] = {"error": repr(e)[:200]}
+            torch.cuda.empty_cache()
+        out[cfg] = res
+    head = out[ns.config].get("bf16_autocast", {})
+    args = config_args(ns.config)
+    line = {"impl": "torch-gpu", "metric": METRIC, "value": head.get("value"), "unit": UNIT, "n_gpus": 1, "steps": ns.steps,
+            "warmup": ns.warmup, "ms_per_step": head.get("ms_per_step"), "higher_is_better": True, "scaling": ns.scaling,
+            "vs_baseline": None, "dtype": "bf16 autocast (fp32 beside it)", "data": "synthetic",
+            "config": {"workload": workload_name(ns.config, args, ns.batch or args.batch_size, ns.scaling, 1),
+                       "note": "oracle port (plain torch ops) on the B200: stock cuBLAS / ATen kernels, eager launches, dropout 0; "
+                               "syn runs 1024 graphs per step (memory of the materialised attention scores)"},
+            "configs": out, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
 
 
 # ----------------------------------------------------------------------------------- GPU arm
@@ -189,13 +254,14 @@ def algorithmic(args, batch, es):
     d_g = args.gnn_emb_dim
     n = torch.bincount(batch.batch)
     t = n.clamp(max=int(args.max_input_len)) + (1 if args.graph_pooling == "cls" else 0)
-    sum_t2 = float((t.double() ** 2).sum())
+    sum_t2, sum_t = float((t.double() ** 2).sum()), float(t.sum())
     if args.model_type == "pna-transformer":
         agg_bytes = N * d_g * es * 3 + 13 * N * d_g * es + 16 * E      # x, pi, pj read; 13F x towers written
     else:
         agg_bytes = 2 * N * d_g * es + 16 * E + ea
-    return dict(N=N, E=E, agg_bytes_per_launch=agg_bytes, mha_fwd_flops=4.0 * args.d_model * sum_t2,
-                mha_bwd_flops=8.0 * args.d_model * sum_t2, tokens=int(t.sum()))
+    d = args.d_model
+    return dict(N=N, E=E, agg_bytes_per_launch=agg_bytes, mha_fwd_flops=4.0 * d * sum_t2, mha_bwd_flops=8.0 * d * sum_t2,
+                mha_pooled_fwd_flops=4.0 * d * sum_t, mha_pooled_bwd_flops=8.0 * d * sum_t, tokens=int(sum_t))
 
 
 def _timed(fn, reps=20):
@@ -213,163 +279,171 @@ def _timed(fn, reps=20):
     return e0.elapsed_time(e1) / reps
 
 
-def hot_kernel_roofline(args, model, b, hb, ns, step_ms):
+def alone_replays(args, model, b, hb, precision):
+    """the hot-stage kernels replayed back to back OUTSIDE the step, on this batch's real plan, running the SAME variants
+    the step runs (trainable edge table: the adjoint writes the per-edge gradient `gm`; the one-hot table-gradient
+    contraction is timed separately).  -> {name: ms per (fwd + bwd) pair}"""
     from graphtrans_b200 import ops
     from graphtrans_b200._lib import CONV_GCN, CONV_GIN
     from graphtrans_b200.modules import conv as conv_mod
-    pk = peaks()
-    traffic = {}
-    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(ns.config, {})
-    es = 2 if ns.precision == "bf16" else 4
-    alg = algorithmic(args, hb, es)
     act = ops.act_dtype()
-    plan = ops.GraphPlan(b.edge_index, b.batch, b.num_graphs, int(args.max_input_len), cls=args.graph_pooling == "cls",
-                         max_nodes=getattr(hb, "max_nodes", None))     # same attention path as the model takes
-    N, d_g, ld = alg["N"], args.gnn_emb_dim, ops.ldp(args.gnn_emb_dim)
-    out = []
+    plan = ops.plan_for(b, int(args.max_input_len), cls=args.graph_pooling == "cls")
+    N, d_g, ld = b.batch.numel(), args.gnn_emb_dim, ops.ldp(args.gnn_emb_dim)
+    dev = b.batch.device
+    out = {}
     torch.manual_seed(0)
-    # stage 1: message-passing aggregation fwd + adjoint (one GNN layer)
     if args.model_type == "gnn-transformer":
         conv = model.gnn_node.convs[1]
-        x = (torch.randn(N, ld, device=b.batch.device) * 0.5).to(act)
+        x = (torch.randn(N, ld, device=dev) * 0.5).to(act)
         x[:, d_g:] = 0
         x.requires_grad_(True)
-        gy = torch.randn(N, ld, device=b.batch.device).to(act)
-        enc = conv_mod._edge_encoder_args(conv.edge_encoder, b.edge_attr, plan, d_g, ld)
-        enc = {k: (v.detach() if torch.is_tensor(v) and v.dtype.is_floating_point and k == "table" else v) for k, v in enc.items()}
+        gy = torch.randn(N, ld, device=dev).to(act)
         kind, sp = (CONV_GCN, conv.root_emb.weight) if args.gnn_type == "gcn" else (CONV_GIN, conv.eps)
+
+        enc = conv_mod._edge_encoder_args(conv.edge_encoder, b.edge_attr, plan, d_g, ld)         # trainable table / weights
 
         def agg():
             y = ops.aggregate(x, plan, kind, d_g, sp, **enc)
-            torch.autograd.grad(y, x, gy)      # no .grad accumulation kernels inside the timed launches
-        kname = "k_agg_fwd2 / k_agg_bwd2" if enc.get("edge_kind") == conv_mod.EDGE_LINEAR else "k_agg_fwd3 / k_agg_bwd3"
-        name = f"gt_aggregate_fwd + gt_aggregate_bwd ({kname})"
+            torch.autograd.grad(y, x, gy)
+        out["aggregate"] = _timed(agg)
     else:
         layer = model.gnn_node.layers[0]
-        x = (torch.randn(N, ld, device=b.batch.device) * 0.5).to(act).requires_grad_(True)
-        pj = torch.randn(N, ld, device=b.batch.device).to(act).requires_grad_(True)
-        pi = torch.randn(N, ld, device=b.batch.device).to(act).requires_grad_(True)
-        gy = torch.randn(N, 4 * 13 * (d_g // 4), device=b.batch.device).to(act)
+        x = (torch.randn(N, ld, device=dev) * 0.5).to(act).requires_grad_(True)
+        pj = torch.randn(N, ld, device=dev).to(act).requires_grad_(True)
+        pi = torch.randn(N, ld, device=dev).to(act).requires_grad_(True)
+        gy = torch.randn(N, 4 * 13 * (d_g // 4), device=dev).to(act)
 
         def agg():
             y = ops.pna_reduce(x, pj, pi, plan, 4, d_g // 4, layer.avg_deg["log"])
             torch.autograd.grad(y, (x, pj, pi), gy)
-        name = "gt_pna_reduce_fwd + gt_pna_reduce_bwd"
-    ms = _timed(agg)                       # the edge table is a constant here: exactly the two named kernels run
-    ach = 2 * alg["agg_bytes_per_launch"] / (ms * 1e-3) / 1e9
-    out.append({"kernel": name, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
-                "traffic": traffic.get("aggregate"), "avg_launch_us": ms / 2 * 1e3,
-                "share_of_step": ms * args.gnn_num_layer / step_ms,
-                "algorithmic_bytes_per_launch": alg["agg_bytes_per_launch"], "peak_source": pk["source"],
-                "note": "the [N, d_g] matrix of these configs is L2-resident (8-10 MB << 126 MB L2)"})
-    if args.model_type == "gnn-transformer" and enc.get("edge_kind") == conv_mod.EDGE_TABLE:
-        # the edge-table gradient of the same layer (weight-gradient stream): gathers x[src] and dout[dst] of every edge
-        from graphtrans_b200._lib import call as _call, dt_of as _dt, ptr as _p
-        table, etype = enc["table"], enc["etype"]
-        src_t, dst_t, type_t, _ = plan.edges_by_type(plan._edge_index, etype, table.shape[0])
-        dtab = torch.zeros_like(table)
-        xc = x.detach()
-
-        def tab_grad():
-            _call("gt_aggregate_table_grad", _dt(xc), kind, _p(xc), _p(gy), N, d_g, ld, _p(plan.rowptr_src), plan.E, _p(src_t),
-                  _p(dst_t), _p(type_t), _p(table), table.shape[0], _p(dtab))
-        ms_t = _timed(tab_grad)
-        tg_bytes = 2 * plan.E * d_g * es + 12 * plan.E
-        ach_t = tg_bytes / (ms_t * 1e-3) / 1e9
-        out.append({"kernel": "gt_aggregate_table_grad (k_agg_table_grad, weight-gradient stream)", "bound": "hbm", "achieved": ach_t,
-                    "peak": pk["hbm"], "unit": "GB/s", "frac": ach_t / pk["hbm"], "traffic": None, "avg_launch_us": ms_t * 1e3,
-                    "share_of_step": None, "algorithmic_bytes_per_launch": tg_bytes, "peak_source": pk["source"],
-                    "note": "gather formulation: 2 E d_g s + 12 E bytes (x[src], dout[dst], sorted edge triples); L2-resident rows. "
-                            "The bf16 step no longer launches it (the adjoint writes the per-edge gradient and the table "
-                            "gradient is a one-hot contraction, GT_TABLE_GRAD_GEMM=1); it remains the fp32 / small-batch path"})
-    # stage 2: masked MHA fwd + bwd over the packed tokens (one encoder layer)
+        out["aggregate"] = _timed(agg)
     d, nh = args.d_model, args.nhead
-    qkv = torch.randn(plan.n_rows, 3 * d, device=b.batch.device).to(act).requires_grad_(True)
-    go = torch.randn(plan.n_rows, d, device=b.batch.device).to(act)
+    qkv = torch.randn(plan.n_rows, 3 * d, device=dev).to(act).requires_grad_(True)
+    go = torch.randn(plan.n_rows, d, device=dev).to(act)
     drop = float(args.transformer_dropout)
 
     def mha():
         o = ops.mha_packed(qkv, plan, nh, drop_p=drop)
         torch.autograd.grad(o, qkv, go)
-    ms = _timed(mha)
-    fl = alg["mha_fwd_flops"] + alg["mha_bwd_flops"]
-    ach = fl / (ms * 1e-3) / 1e12
-    local = plan.loc_tiles is not None and act == torch.bfloat16
-    mha_name = ("gt_mha_local_fwd + gt_mha_local_bwd (k_mha_loc_fwd, k_mha_loc_bwd: graph-aligned 128-row tiles)" if local else
-                "gt_mha_fwd + gt_mha_bwd (k_mha_tc_fwd, k_mha_tc_bwd<dQ>, k_mha_tc_bwd<dKV>, k_mha_delta)")
-    n_launch = 2 if local else 4
-    out.append({"kernel": mha_name, "bound": "tensor",
-                "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": ach / pk["tensor"],
-                "traffic": traffic.get("mha_local" if local else "mha"), "avg_launch_us": ms / n_launch * 1e3,
-                "share_of_step": ms * args.num_encoder_layers / step_ms,
-                "useful_flops_fwd_bwd": fl, "peak_source": pk["source"],
-                "note": "useful (unpadded, block-diagonal) flops only; recompute flops of the backward are not counted"})
-    # dense: the largest contraction of the model (fwd + dX + dW)
-    M, Nn, Kk = alg["tokens"], args.dim_feedforward, d
-    w = torch.randn(Nn, Kk, device=b.batch.device, requires_grad=True)
-    bias = torch.zeros(Nn, device=b.batch.device, requires_grad=True)
-    xx = torch.randn(plan.n_rows, Kk, device=b.batch.device).to(act).requires_grad_(True)
-    gg = torch.randn(plan.n_rows, ops.ldp(Nn), device=b.batch.device).to(act)
-
-    def ffn1():
-        y = ops.linear(xx, w, bias, relu=True)
-        torch.autograd.grad(y, (xx, w, bias), gg)
-    ms = _timed(ffn1)
-    fl = 3 * 2.0 * plan.n_rows * Nn * Kk
-    ach = fl / (ms * 1e-3) / 1e12
-    out.append({"kernel": "gt_gemm fwd + dX + dW of the FFN up-projection [tokens x dim_feedforward x d_model] (k_gemm_tc)",
-                "bound": "tensor", "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": ach / pk["tensor"],
-                "traffic": traffic.get("gemm"), "avg_launch_us": ms / 5 * 1e3, "share_of_step": None, "peak_source": pk["source"],
-                "note": "includes relu_bwd and colsum launches of the linear backward"})
-    out.sort(key=lambda r: -(r["share_of_step"] or 0))
-    # the headline `roofline` object is the hot stage BASELINE.json quotes the config on ("HBM GB/s (conv) + tensor-pipe %
-    # (MHA)"): configs 2 / 4 / 5 / 1 are the scatter-bound ones -> stage-1 aggregation (HBM roofline); config 3 (long padded
-    # sequences) stresses the masked-MHA tcgen05 path -> tensor roofline.  Every measured kernel stays in roofline_kernels.
-    primary = "gt_mha" if ns.config == "code2" else ("gt_pna_reduce" if args.model_type == "pna-transformer" else "gt_aggregate_fwd")
-    out.sort(key=lambda r: 0 if r["kernel"].startswith(primary) else 1)
+    out["mha"] = _timed(mha)
+    ops.join_side_streams()
     return out
 
 
-def main_b200(ns):
-    from graphtrans_b200 import _lib, factory, ops
-    from graphtrans_b200.ddp import GradBuckets
+def in_step_roofline(cfg, args, model, lossf, buckets, b, hb, ns, step_ms, rank):
+    """roofline objects of the hot-stage kernels from the IN-STEP timeline (every rank runs the stamped replay, rank 0
+    builds the objects)"""
+    from graphtrans_b200 import ops, trace
+    pk = peaks()
+    prof = trace.stamped_profile(model, lossf, buckets, b, reps=5)
+    if rank != 0:
+        return None
+    tr = {}
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        tr = json.load(open(tpath)).get(cfg, {})
+    es = 2 if ns.precision == "bf16" else 4
+    alg = algorithmic(args, hb, es)
+    alone = {}
+    try:
+        alone = alone_replays(args, model, b, hb, ns.precision)
+    except Exception as e:  # noqa: BLE001
+        alone = {"error": repr(e)[:160]}
+    step_us = step_ms * 1e3
+    out = []
+    pna = args.model_type == "pna-transformer"
+    names = ("gt_pna_reduce_fwd", "gt_pna_reduce_bwd") if pna else ("gt_aggregate_fwd", "gt_aggregate_bwd")
+    n, us = trace.kernel_time(prof, names)
+    if n:
+        ach = n * alg["agg_bytes_per_launch"] / (us * 1e-6) / 1e9
+        o = {"kernel": " + ".join(names) + (" (k_pna_fwd / k_pna_bwd)" if pna else " (k_agg_fwd* / k_agg_bwd*)"),
+             "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
+             "traffic": tr.get("aggregate"), "avg_launch_us": us / n, "launches_per_step": n, "share_of_step": us / step_us,
+             "algorithmic_bytes_per_launch": alg["agg_bytes_per_launch"], "peak_source": pk["source"],
+             "timing": "in-step: device timestamps after every kernel of the replayed CUDA graph (trace.stamped_profile), "
+                       "minus the stamp kernel's own %.2f us per interval" % prof["cal_us"]}
+        if isinstance(alone.get("aggregate"), float):
+            a = 2 * alg["agg_bytes_per_launch"] / (alone["aggregate"] * 1e-3) / 1e9
+            o["alone"] = {"achieved": a, "frac": a / pk["hbm"], "avg_launch_us": alone["aggregate"] / 2 * 1e3,
+                          "note": "fwd + adjoint replayed back to back outside the step (same variants: trainable edge "
+                                  "table, per-edge gradient store)"}
+        out.append(o)
+    full = ("gt_mha_fwd", "gt_mha_bwd", "gt_mha_local_fwd", "gt_mha_local_bwd")
+    n, us = trace.kernel_time(prof, full)
+    if n:
+        n_layers = sum(1 for r in prof["records"] if r[0] in ("gt_mha_fwd", "gt_mha_local_fwd"))
+        fl = n_layers * (alg["mha_fwd_flops"] + alg["mha_bwd_flops"])
+        ach = fl / (us * 1e-6) / 1e12
+        local = any(r[0] == "gt_mha_local_fwd" for r in prof["records"])
+        o = {"kernel": ("gt_mha_local_fwd + gt_mha_local_bwd (tile-local tcgen05 attention)" if local else
+                        "gt_mha_fwd + gt_mha_bwd (streamed tcgen05 attention: fwd, delta, dQ, dK/dV)"),
+             "bound": "tensor", "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": ach / pk["tensor"],
+             "traffic": tr.get("mha_local" if local else "mha"), "avg_launch_us": us / n, "launches_per_step": n,
+             "share_of_step": us / step_us, "useful_flops_per_step": fl, "peak_source": pk["source"],
+             "note": "useful (unpadded, block-diagonal) flops only, %d full layers (the last layer runs the pooled-query kernel); "
+                     "recompute flops of the backward are not counted; in-step timing" % n_layers}
+        if isinstance(alone.get("mha"), float):
+            a = (alg["mha_fwd_flops"] + alg["mha_bwd_flops"]) / (alone["mha"] * 1e-3) / 1e12
+            o["alone"] = {"achieved": a, "frac": a / pk["tensor"], "ms_fwd_bwd": alone["mha"]}
+        out.append(o)
+    n, us = trace.kernel_time(prof, ("gt_mha_cls_fwd", "gt_mha_cls_bwd"))
+    if n:
+        kvb = 2 * alg["tokens"] * 2 * args.d_model * es          # fwd reads k|v once; bwd reads them and writes dk|dv
+        ach = (kvb + 2 * kvb) / (us * 1e-6) / 1e9
+        out.append({"kernel": "gt_mha_cls_fwd + gt_mha_cls_bwd (pooled-query last layer)", "bound": "hbm", "achieved": ach,
+                    "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": None, "avg_launch_us": us / n,
+                    "launches_per_step": n, "share_of_step": us / step_us, "peak_source": pk["source"]})
+    # dense contractions: every gt_gemm / gt_gemm_stats of the step (forward, dX, split-K dW) with its own M, N, K
+    fl = us = 0.0
+    n = 0
+    cal = prof["cal_us"]
+    for name, _s, dur, a in prof["records"]:
+        if name in ("gt_gemm", "gt_gemm_stats"):
+            fl += 2.0 * a[9] * a[10] * a[11]
+            us += max(dur - cal, 0.2)
+            n += 1
+    if n:
+        ach = fl / (us * 1e-6) / 1e12
+        out.append({"kernel": "gt_gemm + gt_gemm_stats (k_gemm_tc: all %d contractions of the step)" % n, "bound": "tensor",
+                    "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": ach / pk["tensor"], "traffic": tr.get("gemm"),
+                    "avg_launch_us": us / n, "launches_per_step": n, "share_of_step_stream_time": us / step_us,
+                    "flops_per_step": fl, "peak_source": pk["source"],
+                    "note": "summed over three streams (weight gradients overlap the main stream), so the share can exceed the critical path's"})
+    primary = "gt_mha_fwd" if cfg == "code2" else ("gt_pna_reduce" if pna else "gt_aggregate_fwd")
+    out.sort(key=lambda r: 0 if r["kernel"].startswith(primary) or (cfg == "code2" and r["kernel"].startswith("gt_mha_local")) else 1)
+    meta = {"stamped_step_us": prof["span_us"], "calls": prof["n_calls"], "streams": prof["streams"], "stamp_us": prof["cal_us"]}
+    return out, meta
 
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if world != ns.gpus:
-        if world == 1 and ns.gpus > 1:
-            raise SystemExit("launch with torchrun for --gpus > 1")
-    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm"
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    _lib.load()
-    ops.set_precision(ns.precision)
-    args = config_args(ns)
-    B = ns.batch or args.batch_size
-    if ns.scaling == "strong" and world > 1:
-        B = max(2, B // world)
+
+def run_workload(ns, cfg, scaling, B_arg, rank, world, dev, K, W, full):
+    """one workload end to end -> result dict (on rank 0; None elsewhere)"""
+    from graphtrans_b200 import _lib, factory, loader, ops
+    from graphtrans_b200.ddp import GradBuckets
+    from graphtrans_b200.graphed import GraphedStep
+    args = config_args(cfg)
+    if scaling == "strong":
+        B_global = B_arg or args.batch_size
+        B = max(2, B_global // world)
+        B_global = B * world
+    else:
+        B = B_arg or args.batch_size
+        B_global = B * world
     lossf = factory.loss_fn(args)
     torch.manual_seed(0)
     model = factory.build_model(args).to(dev).train()
-    from graphtrans_b200.graphed import GraphedStep
-    buckets = GradBuckets(model, n_buckets=4, overlap=ns.eager)
-    graphed = None if ns.eager else GraphedStep(model, lossf, buckets, max_graphs=2 * ns.distinct_batches + 2)
-    host_batches = [synth.make_batch(args, B=B, seed=1000 * rank + i).pin_memory() for i in range(ns.distinct_batches)]
-    dev_batches = [b.to(dev) for b in host_batches]
+    in_graph = world > 1 and ns.comm == "graph" and not ns.eager
+    buckets = GradBuckets(model, n_buckets=4, overlap=ns.eager or in_graph, direct=in_graph)
+    graphed = None if ns.eager else GraphedStep(model, lossf, buckets, max_graphs=24, bucket=True)
+    nd = ns.distinct_batches
+    # every batch goes through the collate-time pipeline (shape bucket + int32 CSR + one pinned blob)
+    host = [loader.prepare(synth.make_batch(args, B=B, seed=1000 * rank + i)) for i in range(nd)]
+    dev_batches = [b.to(dev) for b in host]
     ops.manual_seed(1234 + rank, dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)    # > 126 MB L2
 
-    if not ns.no_wgrad_stream:
-        ops.enable_wgrad_stream(True, dev)   # weight / bias / embedding gradients overlap the rest of the backward
-    if not ns.no_branch_stream:
-        ops.enable_branch_stream(True, dev)  # virtual-node update of a GNN layer runs next to its conv
-
     def eager_step(b):
+        if not b.batch.is_cuda:
+            b = b.to(dev, non_blocking=True)
         buckets.zero_grad()
         loss = lossf(model(b), b)
         loss.backward()
@@ -377,7 +451,6 @@ def main_b200(ns):
         buckets.finish()
         return loss.detach()
 
-    # product step: CUDA-graph replay per batch shape (captured during warm-up), eager with --eager
     step = eager_step if graphed is None else graphed
 
     def barrier():
@@ -385,14 +458,10 @@ def main_b200(ns):
             dist.barrier()
         torch.cuda.synchronize()
 
-    K, W = ns.steps, ns.warmup
-    for i in range(max(W, 3, len(dev_batches))):
-        step(dev_batches[i % len(dev_batches)])
-    if graphed is not None and not ns.no_e2e:
-        for hb in host_batches:          # host-resident batches share the signatures captured above
-            step(hb)
+    for i in range(max(W, 3, nd)):
+        step(dev_batches[i % nd])
     barrier()
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(dev.index or 0)
     sampler.start()
     k0 = _lib.kernel_count
     graph_kernels = 0
@@ -403,7 +472,7 @@ def main_b200(ns):
         flush.zero_()                                  # L2 flush between timed iterations (outside the events)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        step(dev_batches[i % len(dev_batches)])
+        step(dev_batches[i % nd])
         e1.record()
         if graphed is not None:
             graph_kernels += graphed.last_kernels
@@ -417,87 +486,149 @@ def main_b200(ns):
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     t_dev = float(tt)
-    value = B * world * K / t_dev
+    value = B_global * K / t_dev
+    step_ms = t_dev / K * 1e3
 
-    # ---- end to end: host (pinned) batches through the public API, H2D + loss D2H inside the timed region
+    # ---- end to end on NEVER-SEEN host batches: collate-time prepare outside, H2D (prefetched blob) + step + loss D2H inside
     e2e = None
     if not ns.no_e2e:
-        def e2e_step(hb):
-            # public API call with a HOST batch: H2D copy of every input tensor, step, D2H read of the loss
-            return float(step(hb) if graphed is not None else step(hb.to(dev, non_blocking=True)))
-
-        for i in range(2):
-            e2e_step(host_batches[i % len(host_batches)])
+        n_warm = 4 if cfg == "syn" else 16             # batches that warm the bucket grid before the timed, never-seen ones
+        fresh = [loader.prepare(synth.make_batch(args, B=B, seed=50000 + 1000 * rank + i)) for i in range(K + n_warm)]
+        cap0 = graphed.captures if graphed is not None else 0
+        for hb in fresh[:n_warm]:                      # warm the bucket grid (captures of signatures not met so far)
+            float(step(hb))
+        cap1 = graphed.captures if graphed is not None else 0
+        timed = fresh[n_warm:]
         barrier()
         t0 = time.perf_counter()
+        if graphed is not None:
+            graphed.prefetch(timed[0])
         for i in range(K):
-            e2e_step(host_batches[i % len(host_batches)])
+            if graphed is not None and i + 1 < K:
+                graphed.prefetch(timed[i + 1])         # H2D of the next batch overlaps this step (copy stream)
+            float(step(timed[i]))                      # D2H read of the loss
         barrier()
         te = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = {"value": B * world * K / float(te), "unit": UNIT,
-               "h2d_bytes_per_step": int(statistics.mean(b.nbytes() for b in host_batches)),
-               "d2h_bytes_per_step": 4}
+        cap2 = graphed.captures if graphed is not None else 0
+        e2e = {"value": B_global * K / float(te), "unit": UNIT,
+               "h2d_bytes_per_step": int(statistics.mean(b.nbytes() for b in timed)), "d2h_bytes_per_step": 4,
+               "fresh_batches": True, "graph_captures_before_timing": cap1, "graph_captures_while_warming_buckets": cap1 - cap0,
+               "graph_captures_inside_timed_region": cap2 - cap1,
+               "distinct_raw_shapes": len({(int(b.batch.numel()), int(b.edge_index.shape[1])) for b in timed}),
+               "pipeline": "loader.prepare (shape bucket + int32 CSR + one pinned blob, collate time, untimed) -> prefetched H2D of "
+                           "the blob -> CUDA-graph replay -> loss.item()"}
+        del fresh, timed
 
-    # ---- roofline (rank 0, right after the timed region, same process): the two hot-stage kernels and the largest
-    # dense contraction are replayed on this batch's real plan / shapes, back to back behind a GPU-side head start
-    # (so Python launch latency is outside the CUDA events), and timed with CUDA events on the launching stream.
-    # achieved = algorithmic bytes|flops per launch / measured launch time.
-    roof, roof_all = None, None
-    if not ns.no_roofline and rank == 0:
-        roof_all = hot_kernel_roofline(args, model, dev_batches[0], host_batches[0], ns, t_dev / K * 1e3)
-        roof = dict(roof_all[0]) if roof_all else None
+    roof = None
+    if full and not ns.no_roofline and graphed is not None:
+        try:
+            roof = in_step_roofline(cfg, args, model, lossf, buckets, dev_batches[0], host[0], ns, step_ms, rank)
+        except Exception as e:  # noqa: BLE001
+            roof = ([{"kernel": "in-step roofline failed", "error": repr(e)[:300]}], {}) if rank == 0 else None
 
-    # ---- second figure: the same step followed by the fused AdamW update (+ allreduce when N > 1);
-    # measured last because it moves the weights
     with_opt = None
-    if not ns.no_optimizer and graphed is not None:
+    if full and not ns.no_optimizer and graphed is not None:
         from graphtrans_b200.optim import FusedAdamW
         opt = FusedAdamW(buckets, lr=1e-4, weight_decay=1e-5)
-        gstep = GraphedStep(model, lossf, buckets, max_graphs=2 * ns.distinct_batches + 2, optimizer=opt)
-        for i in range(max(3, len(dev_batches))):
-            gstep(dev_batches[i % len(dev_batches)])
+        gstep = GraphedStep(model, lossf, buckets, max_graphs=24, optimizer=opt)
+        for i in range(max(3, nd)):
+            gstep(dev_batches[i % nd])
         barrier()
         evs2 = []
         for i in range(K):
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            loss_t = gstep(dev_batches[i % len(dev_batches)])
+            loss_t = gstep(dev_batches[i % nd])
             e1.record()
             evs2.append((e0, e1))
         barrier()
         t2 = torch.tensor([sum(a.elapsed_time(b) for a, b in evs2) * 1e-3], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-        with_opt = {"value": B * world * K / float(t2), "unit": UNIT, "ms_per_step": float(t2) / K * 1e3,
-                    "step": "zero_grad+forward+loss+backward" + ("+allreduce" if world > 1 else "") + "+fused AdamW (gt_adamw_multi)",
+        with_opt = {"value": B_global * K / float(t2), "unit": UNIT, "ms_per_step": float(t2) / K * 1e3,
+                    "step": "zero_grad+forward+loss+backward" + ("+allreduce" if world > 1 else "") + "+fused AdamW (gt_adamw_multi), "
+                            + ("all inside one CUDA graph" if gstep.opt_in_graph else "optimizer after the host-issued allreduce"),
                     "finite_loss": bool(torch.isfinite(loss_t).item())}
 
+    if rank != 0:
+        return None
+    res = {
+        "value": value, "unit": UNIT, "ms_per_step": step_ms, "scaling": scaling, "graphs_per_gpu": B, "global_batch": B_global,
+        "config": {"workload": workload_name(cfg, args, B_global, scaling, world),
+                   "l2": "256 MiB buffer written between timed steps", "distinct_batches": nd,
+                   "dropout": {"gnn": args.gnn_dropout, "transformer": args.transformer_dropout},
+                   "step": "zero_grad+forward+loss+backward" + (
+                       "+NCCL gradient allreduce (4 buckets, " + ("captured inside the step's CUDA graph, overlapped with the backward)"
+                                                                   if in_graph else "issued from the host after the replay)") if world > 1 else ""),
+                   "wgrad_stream": not ns.no_wgrad_stream, "branch_stream": not ns.no_branch_stream,
+                   "batches": "shape-bucket padded (slack nodes / edges), int32 CSR built at collate time, one blob per batch",
+                   "launch": "eager (Python launches every kernel)" if graphed is None else
+                             "CUDA-graph replay per bucketed shape signature; inputs copied into static buffers inside the timed region",
+                   "wall_ms_per_step_incl_flush": wall / K * 1e3},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "with_optimizer": with_opt,
+    }
+    if roof is not None:
+        res["roofline"] = dict(roof[0][0]) if roof[0] else None
+        res["roofline_kernels"] = roof[0]
+        res["in_step_trace"] = roof[1]
+    return res
+
+
+def main_b200(ns):
+    from graphtrans_b200 import _lib, ops
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != ns.gpus and world == 1 and ns.gpus > 1:
+        raise SystemExit("launch with torchrun for --gpus > 1")
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+    ops.set_precision(ns.precision)
+    if not ns.no_wgrad_stream:
+        ops.enable_wgrad_stream(True, dev)   # weight / bias / embedding gradients overlap the rest of the backward
+    if not ns.no_branch_stream:
+        ops.enable_branch_stream(True, dev)  # virtual-node update of a GNN layer runs next to its conv
+    K, W = ns.steps, max(ns.warmup, 3)
+    head = run_workload(ns, ns.config, ns.scaling, ns.batch, rank, world, dev, K, W, full=True)
+    extras = {}
+    if not ns.no_extra_configs:
+        for cfg in EXTRA_CONFIGS:
+            if cfg == ns.config:
+                continue
+            torch.cuda.empty_cache()
+            try:
+                r = run_workload(ns, cfg, "weak", None, rank, world, dev, min(K, 20), 3, full=True)
+            except Exception as e:  # noqa: BLE001
+                r = {"error": repr(e)[:300]}
+            if rank == 0:
+                if r is not None:
+                    r.pop("clocks", None)
+                extras[cfg] = r
     cpu = None
     if not ns.no_cpu_baseline and rank == 0 and world == 1:      # reported at N = 1 only (the other ranks would idle)
-        gps, ms, desc = cpu_reference_run(ns, 3, 1)
-        cpu = {"value": gps, "unit": UNIT, "cores": desc["cores"], "kind": desc["kind"], "sample": desc["sample"],
-               "ms_per_step": ms}
-
+        args = config_args(ns.config)
+        gps, ms, desc = oracle_run(ns.config, head["global_batch"], 2, 1)
+        cpu = {"value": gps, "unit": UNIT, "cores": desc["cores"], "kind": desc["kind"], "sample": desc["sample"], "ms_per_step": ms}
+        if "molpcba" in extras and isinstance(extras["molpcba"], dict) and "value" in extras["molpcba"]:
+            g2, m2, d2 = oracle_run("molpcba", 512, 2, 1)
+            extras["molpcba"]["cpu_baseline"] = {"value": g2, "unit": UNIT, "cores": d2["cores"], "kind": d2["kind"],
+                                                 "sample": d2["sample"], "ms_per_step": m2}
     if rank == 0:
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(W, 3),
-            "ms_per_step": t_dev / K * 1e3, "higher_is_better": True, "scaling": ns.scaling, "vs_baseline": None,
-            "dtype": ns.precision, "data": "synthetic",
-            "config": {"workload": workload_name(ns, args), "l2": "256 MiB buffer written between timed steps",
-                       "distinct_batches": len(dev_batches), "dropout": {"gnn": args.gnn_dropout,
-                                                                         "transformer": args.transformer_dropout},
-                       "step": "zero_grad+forward+loss+backward" + ("+NCCL gradient allreduce (4 buckets)" if world > 1 else ""),
-                       "wgrad_stream": not ns.no_wgrad_stream, "branch_stream": not ns.no_branch_stream,
-                       "launch": "eager (Python launches every kernel)" if graphed is None else
-                                 "CUDA-graph replay per batch shape signature (captured in warm-up); inputs copied into static buffers inside the timed region",
-                       "wall_ms_per_step_incl_flush": wall / K * 1e3},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "with_optimizer": with_opt, "roofline": roof,
-            "roofline_kernels": roof_all,
-            "cpu_baseline": cpu,
-        }
+        line = {"metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": head["scaling"], "vs_baseline": None,
+                "dtype": ns.precision, "data": "synthetic", "config": head["config"], "clocks": head["clocks"], "e2e": head["e2e"],
+                "gpu_launches": head["gpu_launches"], "with_optimizer": head["with_optimizer"],
+                "roofline": head.get("roofline"), "roofline_kernels": head.get("roofline_kernels"),
+                "in_step_trace": head.get("in_step_trace"), "cpu_baseline": cpu,
+                "graphs_per_gpu": head["graphs_per_gpu"], "global_batch": head["global_batch"],
+                "configs": extras}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -507,5 +638,7 @@ if __name__ == "__main__":
     ns = parse()
     if ns.impl == "reference":
         main_reference(ns)
+    elif ns.impl == "torch-gpu":
+        main_torch_gpu(ns)
     else:
         main_b200(ns)

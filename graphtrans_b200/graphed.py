@@ -77,6 +77,8 @@ class GraphedStep:
         self.capture_stream = None
         if self.device.type == "cuda" and os.environ.get("GT_MAIN_PRIORITY", "1") == "1":
             self.capture_stream = torch.cuda.Stream(device=self.device, priority=-1)
+        self.copy_stream = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
+        self._staged = {}
 
     def _eager(self, b):
         self.buckets.zero_grad()
@@ -150,10 +152,30 @@ class GraphedStep:
         from . import loader
         return loader.prepare(batch)
 
+    def prefetch(self, batch):
+        """start the H2D copy of a HOST batch on the copy stream (overlaps the step that is running); the next
+        `step(batch)` with the same object consumes the staged device copy.  The double-buffered loader of SURVEY §8f
+        rank 1: replaces the synchronous `batch.to(device)` of reference trainers/base_trainer.py:23."""
+        prepared = self.prepare(batch)
+        if prepared.batch.is_cuda:
+            return
+        with torch.cuda.stream(self.copy_stream):
+            dev = prepared.to(self.device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+        self._staged[id(batch)] = (prepared, dev, ev)
+
     def __call__(self, batch):
         """batch: GraphBatch on the host (pinned) or on the device.  Returns the (static) loss tensor; the
         gradients are in `buckets.flat` / p.grad after the call."""
-        batch = self.prepare(batch)
+        staged = self._staged.pop(id(batch), None)
+        if staged is not None:
+            _, batch, ev = staged                                 # device copy issued earlier on the copy stream
+            torch.cuda.current_stream().wait_event(ev)
+            for _, v in ([("_blob", batch._blob)] if getattr(batch, "_blob", None) is not None else batch.tensors()):
+                v.record_stream(torch.cuda.current_stream())
+        else:
+            batch = self.prepare(batch)
         sig = _signature(batch)
         ent = self.cache.get(sig)
         if ent is None:

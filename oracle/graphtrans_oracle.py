@@ -153,7 +153,7 @@ def gnn_node(ctx, args, batch, perturb=None, prefix="gnn_node"):
     B = int(bidx[-1]) + 1
     virtual = args.gnn_virtual_node
     if virtual:
-        vn = sd[prefix + ".virtualnode_embedding.weight"][torch.zeros(B, dtype=torch.long)]
+        vn = sd[prefix + ".virtualnode_embedding.weight"][torch.zeros(B, dtype=torch.long, device=bidx.device)]
     for layer in range(L):
         if virtual:
             h_list[layer] = h_list[layer] + vn[bidx]  # mutation seen by JK (gnn_module.py:199)
@@ -206,7 +206,7 @@ def pna_conv(ctx, prefix, args, x, edge_index, towers=4):
         if name == "mean":
             aggs.append(scatter_sum(m, dst, n) / cdiv)
         elif name in ("max", "min"):
-            init = torch.zeros((n, towers, Fd), dtype=x.dtype)
+            init = torch.zeros((n, towers, Fd), dtype=x.dtype, device=x.device)
             idx = dst.view(-1, 1, 1).expand_as(m)
             aggs.append(init.scatter_reduce(0, idx, m, "amax" if name == "max" else "amin", include_self=False))
         elif name == "std":
@@ -264,10 +264,10 @@ def pad_plan(batch_idx, max_input_len):
 def pad_batch(h, batch_idx, max_input_len):
     n, off, k, S = pad_plan(batch_idx, max_input_len)
     B, d = n.numel(), h.shape[-1]
-    pos = torch.arange(S).view(S, 1)                      # [S,1]
+    pos = torch.arange(S, device=h.device).view(S, 1)     # [S,1]
     valid = pos >= (S - k).view(1, B)                     # [S,B]
     src = (off + n - S).view(1, B) + pos                  # node index feeding padded[p, i]
-    padded = torch.zeros(S, B, d, dtype=h.dtype)
+    padded = torch.zeros(S, B, d, dtype=h.dtype, device=h.device)
     padded[valid] = h[src[valid]]
     mask = ~valid.t()                                     # [B,S] True = PAD
     return padded, mask.contiguous()
@@ -298,7 +298,7 @@ def transformer_encoder(sd, args, padded, mask, prefix="transformer_encoder"):
     if args.graph_pooling == "cls":
         cls = sd[prefix + ".cls_embedding"].expand(1, B, -1)
         padded = torch.cat([padded, cls], dim=0)
-        mask = torch.cat([mask, torch.zeros(B, 1, dtype=torch.bool)], dim=1)
+        mask = torch.cat([mask, torch.zeros(B, 1, dtype=torch.bool, device=mask.device)], dim=1)
     x = padded
     if args.transformer_norm_input:
         x = layernorm(x, sd[prefix + ".norm_input.weight"], sd[prefix + ".norm_input.bias"])
@@ -322,7 +322,7 @@ def global_pool(h, bidx, B, kind):
         cnt = degree(bidx, B, h.dtype).clamp(min=1).view(-1, 1)
         return scatter_sum(h, bidx, B) / cnt
     if kind == "max":
-        init = torch.zeros((B, h.shape[1]), dtype=h.dtype)
+        init = torch.zeros((B, h.shape[1]), dtype=h.dtype, device=h.device)
         return init.scatter_reduce(0, bidx.view(-1, 1).expand_as(h), h, "amax", include_self=False)
     raise NotImplementedError(kind)
 
@@ -339,7 +339,7 @@ def unpad_batch(out, prev, batch_idx, max_input_len):
     n, off, k, S = pad_plan(batch_idx, max_input_len)
     N = prev.shape[0]
     g = batch_idx
-    pos = torch.arange(N) - off[g] - n[g] + S
+    pos = torch.arange(N, device=prev.device) - off[g] - n[g] + S
     valid = pos >= 0
     src = out[pos.clamp(min=0), g]
     return torch.where(valid.view(-1, 1), src, prev)

@@ -1,0 +1,320 @@
+"""GPU tests of the round-2 additions, all through the C ABI:
+  * pooled-query last encoder layer == full last layer on everything the loss depends on (incl. dropout masks)
+  * shape-bucket padding (slack nodes / edges) leaves logits, loss and every gradient unchanged
+  * collate-time CSR == device CSR (bit-exact); single-blob batches; bucketed CUDA-graph capture covers many batches
+  * global mean / max pooling, row argmax, gradient clipping inside the fused AdamW
+  * eval path: BatchNorm folding on / off agree, argmax read-out
+"""
+import copy
+
+import pytest
+import torch
+
+from graphtrans_b200 import factory, loader, ops, synth
+from graphtrans_b200.ddp import GradBuckets
+from graphtrans_b200.graphed import GraphedStep
+from graphtrans_b200.modules import transformer_encoder as te
+from tests.helpers import as_list, grad_report, load_golden, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _small(cfg, **kw):
+    base = dict(gnn_dropout=0.0, transformer_dropout=0.0)
+    if cfg in ("code2", "code2-pna"):
+        base["num_tasks"] = 300
+    base.update(kw)
+    args = synth.make_args(cfg, **base)
+    return args
+
+
+def _batch(args, B, seed):
+    b = synth.make_batch(args, B=B, seed=seed)
+    if args.dataset == "code2":
+        b.y_arr = b.y_arr % args.num_tasks
+    if args.model_type in ("pna-transformer", "pna") and args.deg is None:
+        args.deg = synth.in_degree_histogram(b, 800)
+    return b
+
+
+def _run(model, lossf, b):
+    model.zero_grad(set_to_none=True)
+    pred = model(b)
+    loss = lossf(pred, b)
+    loss.backward()
+    ops.join_side_streams()
+    torch.cuda.synchronize()
+    grads = {k: (p.grad.detach().clone() if p.grad is not None else torch.zeros_like(p)) for k, p in model.named_parameters()}
+    return [t.detach().clone() for t in as_list(pred)], float(loss.detach()), grads
+
+
+# ----------------------------------------------------------------------------- pooled-query last layer
+@pytest.mark.parametrize("nhead,dh", [(4, 32), (4, 64)])
+@pytest.mark.parametrize("drop_p", [0.0, 0.3])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_pooled_query_attention_matches_full_attention_rows(nhead, dh, drop_p, dtype):
+    """gt_mha_cls_* against the CUDA-core full attention restricted to the pooled rows: output, dq, dk, dv - with the
+    SAME dropout mask (row id = packed row of the query, column = key row)"""
+    import numpy as np
+    torch.manual_seed(5)
+    lens = [5, 60, 1, 33, 200, 2, 64, 17]
+    batch = torch.from_numpy(np.repeat(np.arange(len(lens)), lens)).cuda()
+    plan = ops.GraphPlan(torch.zeros(2, 0, dtype=torch.long, device="cuda"), batch, len(lens), 1000, cls=True)
+    d, n_rows, B = nhead * dh, plan.n_rows, len(lens)
+    qkv32 = (torch.randn(n_rows, 3 * d, device="cuda") * 0.7)
+    go_full = torch.zeros(n_rows, d, device="cuda")
+    rows = plan.cls_rows.long()
+    go_cls = torch.randn(B, d, device="cuda")
+    go_full[rows] = go_cls
+    ops.manual_seed(9)
+    ops.begin_step("cuda")
+    ref_in = qkv32.clone().requires_grad_(True)
+    o_full = ops._MHAFn.apply(ref_in, plan, nhead, None, drop_p, 7 if drop_p else 0, 1)      # exact fp32 kernels
+    (g_full,) = torch.autograd.grad(o_full, ref_in, go_full)
+    x = qkv32.to(dtype)
+    q = x[rows, :d].contiguous().requires_grad_(True)
+    kv = x[:, d:].contiguous().requires_grad_(True)
+    o = ops._MHAClsFn.apply(q, kv, plan, nhead, drop_p, 7 if drop_p else 0)
+    dq, dkv = torch.autograd.grad(o, (q, kv), go_cls.to(dtype))
+    tol = 2e-5 if dtype == torch.float32 else 2e-2
+    n_tok = int(plan.tok_off[-1])
+    assert rel_l2(o.float(), o_full[rows]) < tol
+    assert rel_l2(dq.float(), g_full[rows, :d]) < tol
+    assert rel_l2(dkv.float()[:n_tok], g_full[:n_tok, d:]) < tol
+    assert float(dkv.float()[n_tok:].abs().max()) == 0.0        # unused tail rows are cleared
+
+
+@pytest.mark.parametrize("name", ["gcn_virtual_cat_code2", "gin_virtual_cat_mol", "gcn_plain_nci1", "pna_code2"])
+def test_pooled_last_layer_equals_full_last_layer(name):
+    fx = load_golden(name)
+    ops.set_precision("fp32")
+    res = []
+    for flag in (1, 0):
+        te.POOLED_LAST = flag
+        try:
+            model = factory.build_model(fx["args"]).cuda().train()
+            model.load_state_dict(fx["init_sd"])
+            res.append(_run(model, factory.loss_fn(fx["args"]), fx["batch"].clone().to("cuda")))
+        finally:
+            te.POOLED_LAST = 1
+    for a, b in zip(res[0][0], res[1][0]):
+        assert rel_l2(a, b) < 1e-5
+    glob, worst, key = grad_report(res[0][2], res[1][2])
+    assert glob < 1e-4 and worst < 1e-3, (glob, worst, key)
+
+
+# ----------------------------------------------------------------------------- shape buckets / collate-time work
+def test_collate_time_csr_is_bit_exact():
+    args = _small("code2")
+    hb = _batch(args, 12, seed=4)
+    loader.attach_csr(hb)
+    db = hb.to("cuda")
+    plan_dev = ops.GraphPlan(db.edge_index, db.batch, db.num_graphs)
+    plan_pre = ops.plan_for(db)
+    for k in ("rowptr_dst", "src_by_dst", "eid_by_dst", "rowptr_src", "dst_by_src", "eid_by_src"):
+        assert torch.equal(getattr(plan_dev, k), getattr(plan_pre, k)), k
+    assert plan_pre.rowptr_dst.data_ptr() == db.csr_rowptr_dst.data_ptr()       # no rebuild, no copy
+
+
+def test_packed_batch_is_one_blob():
+    args = _small("molpcba")
+    hb = loader.prepare(_batch(args, 16, seed=2))
+    assert hb._blob.is_pinned()
+    db = hb.to("cuda", non_blocking=True)
+    lo, hi = db._blob.data_ptr(), db._blob.data_ptr() + db._blob.numel()
+    for k, v in db.tensors():
+        assert lo <= v.data_ptr() < hi, k
+        assert torch.equal(v.cpu(), getattr(hb, k)), k
+    assert db.slack and db.num_graphs == 16 and int(db.batch.max()) == 16
+
+
+@pytest.mark.parametrize("cfg,B", [("molpcba", 24), ("code2", 5), ("syn", 6), ("code2-pna", 5), ("nci1", 16)])
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_bucket_padding_changes_nothing(cfg, B, precision):
+    """slack nodes / edges belong to no graph: logits, loss and every parameter gradient of the padded batch equal those
+    of the original batch (train-mode BatchNorm statistics included)"""
+    ops.set_precision(precision)
+    try:
+        args = _small(cfg)
+        hb = _batch(args, B, seed=3)
+        torch.manual_seed(0)
+        model = factory.build_model(args).cuda().train()
+        lossf = factory.loss_fn(args)
+        init = copy.deepcopy(model.state_dict())
+        p0, l0, g0 = _run(model, lossf, hb.clone().to("cuda"))
+        bufs0 = {k: v.clone() for k, v in model.named_buffers()}
+        model.load_state_dict(init)
+        pb = loader.prepare(hb.clone())
+        assert pb.batch.numel() > hb.batch.numel() and pb.edge_index.shape[1] >= hb.edge_index.shape[1]
+        p1, l1, g1 = _run(model, lossf, pb.to("cuda"))
+        tol = 2e-5 if precision == "fp32" else 2e-2
+        for a, b in zip(p1, p0):
+            assert a.shape == b.shape and rel_l2(a, b) < tol
+        assert abs(l1 - l0) < tol * max(1.0, abs(l0))
+        glob, worst, key = grad_report(g1, g0)
+        assert glob < (1e-4 if precision == "fp32" else 5e-2), (glob, worst, key)
+        for k, v in model.named_buffers():       # running statistics see the real rows only
+            assert rel_l2(v.double(), bufs0[k].double()) < (1e-5 if precision == "fp32" else 1e-2), k
+    finally:
+        ops.set_precision("fp32")
+
+
+def test_bucketed_capture_covers_many_batches():
+    """200 molpcba-shaped batches with fresh sizes every step: shape buckets make the captured graphs repeat (the
+    reference loop trainers/base_trainer.py:22-33 yields a new (N, E) almost every step), and every replay returns the
+    loss of the eager step on the same batch"""
+    ops.set_precision("fp32")
+    args = _small("molpcba")
+    torch.manual_seed(0)
+    model = factory.build_model(args).cuda().train()
+    lossf = factory.loss_fn(args)
+    buckets = GradBuckets(model, n_buckets=2, overlap=False)
+    step = GraphedStep(model, lossf, buckets, max_graphs=16, bucket=True)
+    ref = factory.build_model(args).cuda().train()
+    rb = GradBuckets(ref, n_buckets=1, overlap=False)
+    sigs = set()
+    for i in range(200):
+        hb = _batch(args, 256, seed=100 + i)
+        sigs.add((hb.batch.numel(), hb.edge_index.shape[1]))
+        loss = float(step(hb))
+        if i % 20 == 0:                      # eager check on a model with the same weights and buffers
+            ref.load_state_dict(model.state_dict())
+            rb.zero_grad()
+            le = lossf(ref(hb.to("cuda")), hb.to("cuda"))
+            le.backward()
+            assert abs(loss - float(le.detach())) < 2e-4 * max(1.0, abs(float(le.detach()))), i
+            assert rel_l2(buckets.flat, rb.flat) < 2e-3, i
+    assert len(sigs) > 100                   # the raw shapes almost never repeat ...
+    assert step.captures <= 16, step.captures     # ... the bucketed ones do
+
+
+def test_capture_warmup_does_not_move_bn_buffers_or_rng():
+    ops.set_precision("fp32")
+    args = synth.make_args("molpcba")
+    torch.manual_seed(0)
+    model = factory.build_model(args).cuda().train()
+    buckets = GradBuckets(model, n_buckets=2, overlap=False)
+    step = GraphedStep(model, factory.loss_fn(args), buckets, warmup_iters=2)
+    bn = model.gnn_node.batch_norms[0]
+    rng0 = ops.rng_state("cuda").clone()
+    step(_batch(args, 8, seed=1).to("cuda"))            # 2 warm-ups + capture + ONE replay
+    assert int(bn.num_batches_tracked) == 1
+    assert int(ops.rng_state("cuda")[1]) == int(rng0[1]) + 1
+
+
+# ----------------------------------------------------------------------------- read-outs / optimizer
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("kind", ["mean", "max", "sum"])
+def test_segment_pool_matches_torch(kind, dtype):
+    import numpy as np
+    torch.manual_seed(1)
+    lens = [3, 1, 40, 7, 300, 2]
+    batch = torch.from_numpy(np.repeat(np.arange(len(lens)), lens)).cuda()
+    plan = ops.GraphPlan(torch.zeros(2, 0, dtype=torch.long, device="cuda"), batch, len(lens))
+    x = torch.randn(sum(lens), 136, device="cuda").to(dtype).requires_grad_(True)
+    go = torch.randn(len(lens), 136, device="cuda")
+    out = ops.segment_pool(x, plan, kind)
+    (gx,) = torch.autograd.grad(out, x, go)
+    xr = x.detach().double().requires_grad_(True)
+    parts = torch.split(xr, lens)
+    ref = torch.stack([p.sum(0) if kind == "sum" else p.mean(0) if kind == "mean" else p.max(0).values for p in parts])
+    (gr,) = torch.autograd.grad(ref, xr, go.double())
+    assert rel_l2(out, ref) < (1e-6 if dtype == torch.float32 else 1e-5)
+    assert rel_l2(gx.float(), gr) < (1e-6 if dtype == torch.float32 else 5e-3)
+
+
+def test_argmax_rows_first_maximum():
+    torch.manual_seed(3)
+    x = torch.randn(37, 5008, device="cuda")
+    x[5, 100] = x[5, 4000] = 50.0            # tie: first index wins (torch.argmax on CUDA returns the first as well)
+    got = ops.argmax_rows(x, n_cols=5002)
+    assert torch.equal(got, x[:, :5002].argmax(1))
+    assert int(got[5]) == 100
+
+
+def test_grad_clip_inside_fused_adamw():
+    """clip_grad_norm_(max_norm) + AdamW of reference trainers/base_trainer.py:34-36 against gt_sumsq + gt_adamw_multi"""
+    from graphtrans_b200.optim import FusedAdamW
+    ops.set_precision("fp32")
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(40, 64), torch.nn.ReLU(), torch.nn.Linear(64, 7)).cuda()
+    ref = copy.deepcopy(net)
+    buckets = GradBuckets(net, n_buckets=2, overlap=False)
+    opt = FusedAdamW(buckets, lr=1e-2, weight_decay=1e-2, max_grad_norm=0.05)
+    ropt = torch.optim.AdamW(ref.parameters(), lr=1e-2, weight_decay=1e-2)
+    for it in range(3):
+        x = torch.randn(32, 40, device="cuda")
+        buckets.zero_grad()
+        net(x).pow(2).mean().backward()       # plain autograd accumulation into the arena views
+        opt.step()
+        ropt.zero_grad()
+        ref(x).pow(2).mean().backward()
+        total = torch.nn.utils.clip_grad_norm_(ref.parameters(), 0.05)
+        ropt.step()
+        assert abs(float(opt.grad_norm()) - float(total)) < 1e-4 * float(total)
+        assert float(total) > 0.05            # the clip is active
+    for a, b in zip(net.parameters(), ref.parameters()):
+        assert rel_l2(a, b) < 1e-5
+
+
+# ----------------------------------------------------------------------------- eval path
+@pytest.mark.parametrize("name", ["gin_virtual_cat_mol", "gin_plain_sum_syn", "zgnn_gin_virtual_mean_mol"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_eval_bn_folding_matches_unfolded(name, precision):
+    fx = load_golden(name)
+    ops.set_precision(precision)
+    try:
+        model = factory.build_model(fx["args"]).cuda()
+        sd = dict(fx["init_sd"])
+        sd.update(fx["buffers"])
+        model.load_state_dict(sd)
+        model.eval()
+        b = fx["batch"].clone().to("cuda")
+        outs = []
+        for flag in (1, 0):
+            ops.EVAL_FOLD_BN = flag
+            k0 = ops._lib.kernel_count
+            with torch.no_grad():
+                outs.append(([t.clone() for t in as_list(model(b))], ops._lib.kernel_count - k0))
+        ops.EVAL_FOLD_BN = 1
+        for a, c in zip(outs[0][0], outs[1][0]):
+            assert rel_l2(a, c) < (1e-5 if precision == "fp32" else 2e-2)
+        assert outs[0][1] < outs[1][1]                       # fewer launches with the BatchNorms folded away
+        if precision == "fp32":
+            for a, c in zip(outs[0][0], as_list(fx["logits_eval"])):
+                assert rel_l2(a, c) < 1e-3
+        # a training step in between invalidates the folded weights
+        model.train()
+        loss = factory.loss_fn(fx["args"])(model(b), b)
+        loss.backward()
+        with torch.no_grad():
+            for p in model.parameters():
+                p.add_(0.01 * torch.randn_like(p))
+        model.eval()
+        with torch.no_grad():
+            a1 = [t.clone() for t in as_list(model(b))]
+            ops.EVAL_FOLD_BN = 0
+            a0 = [t.clone() for t in as_list(model(b))]
+            ops.EVAL_FOLD_BN = 1
+        for a, c in zip(a1, a0):
+            assert rel_l2(a, c) < (1e-5 if precision == "fp32" else 2e-2)
+    finally:
+        ops.EVAL_FOLD_BN = 1
+        ops.set_precision("fp32")
+
+
+def test_eval_argmax_readout_code2():
+    fx = load_golden("gcn_virtual_cat_code2")
+    ops.set_precision("bf16")
+    try:
+        model = factory.build_model(fx["args"]).cuda().eval()
+        model.load_state_dict(fx["init_sd"])
+        b = fx["batch"].clone().to("cuda")
+        with torch.no_grad():
+            pred = model(b)
+            ids = factory.predict_fn(fx["args"])(pred)
+        assert ids.shape == (b.num_graphs, fx["args"].max_seq_len) and ids.dtype == torch.int64
+        for h, p in enumerate(pred):
+            assert torch.equal(ids[:, h], p.argmax(1))
+    finally:
+        ops.set_precision("fp32")
