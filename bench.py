@@ -435,8 +435,17 @@ def run_workload(ns, cfg, scaling, B_arg, rank, world, dev, K, W, full):
     buckets = GradBuckets(model, n_buckets=4, overlap=ns.eager or in_graph, direct=in_graph)
     graphed = None if ns.eager else GraphedStep(model, lossf, buckets, max_graphs=24, bucket=True)
     nd = ns.distinct_batches
-    # every batch goes through the collate-time pipeline (shape bucket + int32 CSR + one pinned blob)
-    host = [loader.prepare(synth.make_batch(args, B=B, seed=1000 * rank + i)) for i in range(nd)]
+    # every batch goes through the collate-time pipeline (shape bucket + int32 CSR + one pinned blob); the bucket grid is
+    # fitted to the shape spread of a sample of batches (what a loader knows after its first pass over the dataset)
+    if cfg == "syn":
+        grid = loader.Bucketer()
+    else:
+        sample = [synth.make_batch(args, B=B, seed=90000 + i) for i in range(48)]
+        grid = loader.Bucketer().fit([(int(s.batch.numel()), int(s.edge_index.shape[1])) for s in sample])
+        del sample
+    if graphed is not None:
+        graphed.bucket = grid
+    host = [loader.prepare(synth.make_batch(args, B=B, seed=1000 * rank + i), bucket=grid) for i in range(nd)]
     dev_batches = [b.to(dev) for b in host]
     ops.manual_seed(1234 + rank, dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)    # > 126 MB L2
@@ -493,7 +502,7 @@ def run_workload(ns, cfg, scaling, B_arg, rank, world, dev, K, W, full):
     e2e = None
     if not ns.no_e2e:
         n_warm = 4 if cfg == "syn" else 16             # batches that warm the bucket grid before the timed, never-seen ones
-        fresh = [loader.prepare(synth.make_batch(args, B=B, seed=50000 + 1000 * rank + i)) for i in range(K + n_warm)]
+        fresh = [loader.prepare(synth.make_batch(args, B=B, seed=50000 + 1000 * rank + i), bucket=grid) for i in range(K + n_warm)]
         cap0 = graphed.captures if graphed is not None else 0
         for hb in fresh[:n_warm]:                      # warm the bucket grid (captures of signatures not met so far)
             float(step(hb))
@@ -516,7 +525,8 @@ def run_workload(ns, cfg, scaling, B_arg, rank, world, dev, K, W, full):
                "h2d_bytes_per_step": int(statistics.mean(b.nbytes() for b in timed)), "d2h_bytes_per_step": 4,
                "fresh_batches": True, "graph_captures_before_timing": cap1, "graph_captures_while_warming_buckets": cap1 - cap0,
                "graph_captures_inside_timed_region": cap2 - cap1,
-               "distinct_raw_shapes": len({(int(b.batch.numel()), int(b.edge_index.shape[1])) for b in timed}),
+               "distinct_bucketed_shapes": len({(int(b.batch.numel()), int(b.edge_index.shape[1])) for b in timed}),
+               "bucket_grid_step": "1/%d .. 1/%d of the size" % (1 << grid.log2_steps, 1 << (grid.log2_steps - 1)),
                "pipeline": "loader.prepare (shape bucket + int32 CSR + one pinned blob, collate time, untimed) -> prefetched H2D of "
                            "the blob -> CUDA-graph replay -> loss.item()"}
         del fresh, timed

@@ -65,7 +65,7 @@ class GraphedStep:
             raise ValueError("GraphedStep with overlap needs GradBuckets(direct=True): only the direct NCCL binding is "
                              "captured into the graph; torch.distributed collectives stay outside (overlap=False)")
         self.max_graphs, self.warmup_iters = max_graphs, warmup_iters
-        self.bucket = bool(bucket)
+        self.bucket = bucket                  # False | True (default grid) | loader.Bucketer fitted to the dataset
         self.cache: "OrderedDict[tuple, _Entry]" = OrderedDict()
         self.pool = None
         self.device = buckets.flat.device
@@ -111,7 +111,7 @@ class GraphedStep:
         side.wait_stream(torch.cuda.current_stream())
         if self.optimizer is not None:
             self.optimizer.enabled = False                      # warm-up must not move the weights
-        snap = self._snapshot()
+        snap = self._snapshot() if os.environ.get("GT_DBG_NO_SNAPSHOT") != "1" else None
         sync_prev = getattr(self.buckets, "_sync_enabled", True)
         if self.comm_in_graph:
             self.buckets._sync_enabled = False                  # warm-up: local only (no collective outside the graph)
@@ -121,10 +121,15 @@ class GraphedStep:
                 loss = self.loss_fn(self.model(ent.static_batch), ent.static_batch)
                 loss.backward()
                 ops.join_side_streams()
+                # drop the autograd graph NOW: a live graph keeps the parameters' AccumulateGrad nodes (created here, on
+                # the warm-up stream) alive, the capture would reuse them and the engine's end-of-backward sync with
+                # that uncaptured stream invalidates the capture (cudaErrorStreamCaptureIsolation)
+                del loss
         if self.comm_in_graph:
             self.buckets._sync_enabled = sync_prev
         torch.cuda.current_stream().wait_stream(side)
-        self._restore(snap)                                     # running stats / dropout counter as before the warm-up
+        if snap is not None:
+            self._restore(snap)                                 # running stats / dropout counter as before the warm-up
         if self.optimizer is not None:
             self.optimizer.enabled = True
             if self.optimizer._desc is None:
@@ -150,7 +155,7 @@ class GraphedStep:
         if batch.batch.is_cuda:
             return batch
         from . import loader
-        return loader.prepare(batch)
+        return loader.prepare(batch, bucket=self.bucket)
 
     def prefetch(self, batch):
         """start the H2D copy of a HOST batch on the copy stream (overlaps the step that is running); the next

@@ -64,9 +64,10 @@ class Transformer(BaseModel):
             max_nodes = getattr(batched_data, "max_nodes", None)
             rows = plan.node2tok
             if max_nodes is None or int(max_nodes) > enc.max_input_len:
-                # truncated-away nodes keep the encoder input (unpad_batch)
+                # truncated-away nodes (node2tok = -1) keep the encoder input (unpad_batch); -2 = "no source row" for
+                # the gather / its scatter adjoint (-1 would mean the <CLS> vector)
                 kept = (rows >= 0).unsqueeze(-1)
-                h_node = torch.where(kept, ops.gather_rows(h_tok, rows.clamp(min=0)), tmp)
+                h_node = torch.where(kept, ops.gather_rows(h_tok, torch.where(rows < 0, torch.full_like(rows, -2), rows)), tmp)
             else:
                 h_node = ops.gather_rows(h_tok, rows)
             h_graph = _readout.pool_nodes(h_node, plan, self.graph_pooling)

@@ -211,12 +211,13 @@ def next_salt() -> int:
 # can run on a second stream next to the memory-bound kernels of the next layer (BN / LayerNorm backward, aggregation
 # adjoint ...), which co-reside on an SM with the one-CTA-per-SM persistent GEMM.  Opt-in: whoever enables it must
 # call join_side_streams() after backward() and before reading gradients (GraphedStep and bench.py do).
-_wgrad = {"stream": None, "used": False}
+_wgrad = {"stream": None, "used": False, "keep": []}
 
 
 def enable_wgrad_stream(on=True, device="cuda"):
     _wgrad["stream"] = torch.cuda.Stream(device=device) if on else None
     _wgrad["used"] = False
+    _wgrad["keep"] = []
 
 
 def join_side_streams():
@@ -228,6 +229,7 @@ def join_side_streams():
         if side["stream"] is not None and side["used"]:
             torch.cuda.current_stream().wait_stream(side["stream"])
             side["used"] = False
+    _wgrad["keep"].clear()
 
 
 join_wgrad_stream = join_side_streams
@@ -249,6 +251,11 @@ class _WgradCtx:
         if st is not None:
             _wgrad["used"] = True
             st.wait_stream(torch.cuda.current_stream())
+            # the operands stay referenced until join_side_streams(): the autograd engine accumulates gradients IN PLACE
+            # into a tensor it holds the only reference to (e.g. the residual branch of a LayerNorm backward hands the
+            # same tensor to two consumers) - a write the side stream's reads are not ordered against.  A second reference
+            # makes the engine add out of place.  (record_stream only guards against reuse after free.)
+            _wgrad["keep"].extend(self.tensors)
             for t in self.tensors:
                 t.record_stream(st)
             self.ctx = torch.cuda.stream(st)
@@ -535,6 +542,9 @@ class GraphPlan:
                  ptr(self.rowptr_src), ptr(self.dst_by_src), ptr(self.eid_by_src), ptr(work))
         br.join()
         self.m_valid = self.node_off[B:B + 1] if slack else None
+        # the static row bound n_rows = N + B can exceed the token count (slack nodes, truncated graphs): kernels that
+        # only write the rows of real tokens then leave a tail that must not hold garbage (it enters later contractions)
+        self.has_tail = bool(slack) or max_nodes is None or int(max_nodes) > self.L
         self._etype = {}
         self._slots = {}
         self._by_type = {}
@@ -685,7 +695,9 @@ class _EmbedSumFn(torch.autograd.Function):
         n = len(idx)
         targets = [_grad_target(t) for t in ctx.tables]
         side_ok = all(_main_grad(t) is not None for t in ctx.tables)   # leaf-only gradients: off the critical path
-        with _WgradCtx(side_ok, g):
+        # every tensor the side-stream kernels READ is listed: it must neither be reused by the allocator nor modified in
+        # place by the autograd engine before join_side_streams()
+        with _WgradCtx(side_ok, g, ctx.onehot[0] if ctx.onehot is not None else None, *idx):
             rest = list(range(n))
             if ctx.onehot is not None:
                 oh, base, rows, R, r_pad = ctx.onehot
@@ -1003,14 +1015,14 @@ class _AggregateFn(torch.autograd.Function):
              ptr(ctx.slots[2]), ptr(gm))
         if split and gm is not None:
             oh, r_pad, _ = plan.type_onehot(ctx.slots[1], table.shape[0])
-            with _WgradCtx(ctx.tab_side, gm, dtab):
+            with _WgradCtx(ctx.tab_side, gm, dtab, oh):
                 # d_table[t, :] += sum over the slots of type t of gm[slot, :]   (split-K over the edges)
                 _gemm_raw(GT_BF16, oh.data_ptr(), 1, r_pad, gm.data_ptr(), 1, ld, dtab.data_ptr(), ld, table.shape[0], d, plan.E, d,
                           None, None, 0, EPI_ACCUM | EPI_OUT_F32)
         elif split:
             src_t, dst_t, type_t, _ = plan.edges_by_type(plan._edge_index, etype, table.shape[0])
             # on the side stream only when the consumer of dtab (the embed_sum backward of the table) runs there too
-            with _WgradCtx(ctx.tab_side, x, g, dtab):
+            with _WgradCtx(ctx.tab_side, x, g, dtab, table, src_t, dst_t, type_t, plan.rowptr_src):
                 call("gt_aggregate_table_grad", dt_of(x), conv, ptr(x), ptr(g), N, d, ld, ptr(plan.rowptr_src), plan.E,
                      ptr(src_t), ptr(dst_t), ptr(type_t), ptr(table), table.shape[0], ptr(dtab))
         for prm in (pw, pb, pself):
@@ -1037,6 +1049,7 @@ class _SegmentSumFn(torch.autograd.Function):
             init = init.contiguous()
         call("gt_segment_sum_sorted", dt_of(x), ptr(x), ptr(plan.node_off), plan.B, ld, ptr(init), ptr(out))
         ctx.meta = (plan, x.dtype, N, ld)
+        ctx.has_init = init is not None
         return out
 
     @staticmethod
@@ -1045,7 +1058,7 @@ class _SegmentSumFn(torch.autograd.Function):
         g = g.contiguous()
         dx = torch.empty(N, ld, dtype=dtype, device=g.device)
         call("gt_add_graph_vec", dt_of(dx), None, ptr(g), ptr(plan.node_graph), N, ld, ptr(dx))
-        return dx, None, g
+        return dx, None, (g if ctx.has_init else None)
 
 
 def segment_sum(x, plan, init=None):
@@ -1345,12 +1358,14 @@ class _MHAFn(torch.autograd.Function):
         d = d3 // 3
         dh = d // nhead
         scale = float(dh) ** -0.5
-        out = torch.empty(n_rows, d, dtype=qkv.dtype, device=qkv.device)
         lse = torch.empty(nhead * n_rows, dtype=torch.float32, device=qkv.device)
         meta = (getattr(plan, "row_bounds", None), getattr(plan, "tile_bounds", None)) if key_start is None else (None, None)
         # every graph inside one graph-aligned 128-row tile: loop-free tile-local kernels (attn_local.cu)
         local = (impl == 0 and key_start is None and getattr(plan, "loc_tiles", None) is not None
                  and qkv.dtype == torch.bfloat16 and dh in (32, 64))
+        # the tile-local kernels write the rows of their tiles only: rows past the last token are cleared up front
+        tail = local and getattr(plan, "has_tail", True)
+        out = (torch.zeros if tail else torch.empty)(n_rows, d, dtype=qkv.dtype, device=qkv.device)
         if local:
             call("gt_mha_local_fwd", dt_of(qkv), ptr(qkv), ptr(plan.row_bounds), ptr(plan.loc_tiles), ptr(plan.loc_count),
                  plan.loc_max_tiles,
@@ -1371,7 +1386,7 @@ class _MHAFn(torch.autograd.Function):
         plan, nhead, dh, scale, key_start, drop_p, salt, impl, local = ctx.meta
         g = g.contiguous()
         n_rows = qkv.shape[0]
-        dqkv = torch.empty_like(qkv)
+        dqkv = torch.zeros_like(qkv) if (local and getattr(plan, "has_tail", True)) else torch.empty_like(qkv)
         if local:
             call("gt_mha_local_bwd", dt_of(qkv), ptr(qkv), ptr(out), ptr(g), ptr(lse), ptr(plan.row_bounds),
                  ptr(plan.loc_tiles), plan.loc_max_tiles, n_rows, nhead, dh, scale, ptr(dqkv), drop_p,
