@@ -40,8 +40,8 @@ def _signature(batch):
         v = getattr(batch, k)
         if torch.is_tensor(v):
             sig.append((k, tuple(v.shape), str(v.dtype)))
-        elif k == "max_nodes":   # only its coarse bucket shapes the launches (ops.token_bucket)
-            sig.append((k, None if v is None else -(-(int(v) + 1) // 32)))
+        elif k == "max_nodes":   # only its coarse bucket shapes the launches (ops.token_bucket: 32 / 64 / 96 / 128 / none)
+            sig.append((k, None if v is None else min(-(-(int(v) + 1) // 32), 5)))
         else:
             sig.append((k, v if isinstance(v, (int, float, str, bool, type(None))) else None))
     return tuple(sig)
