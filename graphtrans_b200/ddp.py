@@ -71,6 +71,7 @@ class GradBuckets:
         self._pending = [0] * len(self.buckets)
         self._work = []
         self._launched = [False] * len(self.buckets)
+        self._fused_seen = [False] * len(self.params)     # parameters whose gradients the backward kernels deliver themselves
         if self.overlap:
             for i, p in enumerate(self.params):
                 p.register_post_accumulate_grad_hook(self._make_hook(i))
@@ -81,18 +82,29 @@ class GradBuckets:
         def ready():
             if not self._sync_enabled:
                 return
+            self._fused_seen[i] = True
             self._uses_left[i] -= 1
             if self._uses_left[i] == 0 and self.overlap:
-                b = self._bucket_of[i]
-                self._pending[b] -= 1
-                if self._pending[b] == 0:
-                    self._launch(b)
+                self._count(i)
         return ready
+
+    def _count(self, i):
+        """parameter i has its complete gradient: counted ONCE per step, whichever notification comes first (the fused
+        delivery's `_gt_grad_ready` or autograd's post-accumulate hook - the engine runs the AccumulateGrad node, and with
+        it the hook, even when the backward kernels delivered the gradient themselves and returned None)"""
+        if self._counted[i]:
+            return
+        self._counted[i] = True
+        b = self._bucket_of[i]
+        self._pending[b] -= 1
+        if self._pending[b] == 0:
+            self._launch(b)
 
     def reset(self):
         self._uses_left = [getattr(p, "_gt_uses", 1) for p in self.params]
         self._pending = [len(ids) for _, _, ids in self.buckets]
         self._launched = [False] * len(self.buckets)
+        self._counted = [False] * len(self.params)
         self._work = []
 
     def zero_grad(self):
@@ -104,16 +116,20 @@ class GradBuckets:
         def hook(_p):
             if not self._sync_enabled:
                 return
-            b = self._bucket_of[i]
-            self._pending[b] -= 1
-            if self._pending[b] == 0:
-                self._launch(b)
+            if self._uses_left[i] > 0 and getattr(self.params[i], "_gt_main_grad", None) is not None and self._fused_seen[i]:
+                return      # fused delivery in progress for this parameter: its own notifications decide
+            self._count(i)
         return hook
 
     def _launch(self, b):
         if self._launched[b] or self.world == 1:
             return
         self._launched[b] = True
+        if __import__("os").environ.get("GT_DDP_DEBUG"):
+            import threading
+            print(f"[ddp] launch bucket {b} thread={threading.current_thread().name} stream={torch.cuda.current_stream().cuda_stream:#x} "
+                  f"capturing={torch.cuda.is_current_stream_capturing()} pending={self._pending} "
+                  f"undone={[i for i, u in enumerate(self._uses_left) if u > 0][:8]}", flush=True)
         lo, hi, _ = self.buckets[b]
         chunk = self.flat[lo:hi]
         if self.comm_stream is not None:
