@@ -375,13 +375,13 @@ k_bn_bwd_apply(const T* __restrict__ x, const T* __restrict__ dy, int64_t M, int
         m0[q] = (float)red[c0 + q] * invM;
         m1[q] = (float)red[ld + c0 + q] * invM;
     }
-    for (int64_t r = r0 + ty; r < r1; r += STAT_TY) {
+    const int64_t r1v = min(r1, Mv);
+    for (int64_t r = max(r0, Mv) + ty; r < r1; r += STAT_TY) {      // bucket slack rows: no gradient
+        const float z[4] = {0.f, 0.f, 0.f, 0.f};
+        st4(dx + r * ld + c0, z);
+    }
+    for (int64_t r = r0 + ty; r < r1v; r += STAT_TY) {
         float v[4], g[4], o[4], ds[4];
-        if (r >= Mv) {      // bucket slack rows: no gradient
-            o[0] = o[1] = o[2] = o[3] = 0.f;
-            st4(dx + r * ld + c0, o);
-            continue;
-        }
         ld4(x + r * ld + c0, v);
         ld4(dy + r * ld + c0, g);
         drop4(dr, (uint64_t)(r * vpr + c0 / 4), ds);
@@ -558,10 +558,92 @@ k_bn_norm_fwd_slab(const T* __restrict__ x, int64_t M, int d, int ld, int tpr, i
     }
 }
 
+// backward apply on the row-slab mapping (no reduction in this pass: per-channel constants in registers, 16-byte
+// accesses, four rows of the thread in flight): dx = scale * (g - mean(g) - xhat * mean(g * xhat)) (train) or scale * g
+template <typename T>
+__global__ void __launch_bounds__(SLAB_THREADS)
+k_bn_bwd_apply_slab(const T* __restrict__ x, const T* __restrict__ dy, int64_t M, int d, int ld, int tpr, int rpi,
+                    int rows_per_block, const float* __restrict__ ssmr, int relu, int training,
+                    const double* __restrict__ red, T* __restrict__ dx, float* __restrict__ dgamma,
+                    float* __restrict__ dbeta, float drop_p, const uint64_t* __restrict__ rng, uint64_t salt,
+                    const int32_t* __restrict__ m_valid) {
+    constexpr int V = VecW<T>::V;
+    const Drop dr = make_drop(rng, salt, drop_p);
+    const int rr = threadIdx.x / tpr, c0 = (threadIdx.x - rr * tpr) * V;
+    if (rr >= rpi) return;
+    const int64_t Mv = valid_rows(m_valid, M);
+    const float invM = 1.f / (float)Mv;
+    float sc[V], sh[V], mu[V], rs[V], m0[V], m1[V];
+#pragma unroll
+    for (int q = 0; q < V; ++q) {
+        sc[q] = ssmr[c0 + q];
+        sh[q] = ssmr[ld + c0 + q];
+        mu[q] = ssmr[2 * ld + c0 + q];
+        rs[q] = ssmr[3 * ld + c0 + q];
+        m0[q] = (float)red[c0 + q] * invM;
+        m1[q] = (float)red[ld + c0 + q] * invM;
+    }
+    if (blockIdx.x == 0 && rr == 0) {
+#pragma unroll
+        for (int q = 0; q < V; ++q)
+            if (c0 + q < d) {
+                dgamma[c0 + q] += (float)red[ld + c0 + q];   // accumulate semantics (single writer per channel)
+                dbeta[c0 + q] += (float)red[c0 + q];
+            }
+    }
+    const int vpr4 = ld / 4;
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = min(r0 + (int64_t)rows_per_block, M);
+    const int64_t r1v = min(r1, Mv);
+    for (int64_t r = max(r0, Mv) + rr; r < r1; r += rpi) {       // bucket slack rows: no gradient
+        float z[V];
+#pragma unroll
+        for (int q = 0; q < V; ++q) z[q] = 0.f;
+        stw(dx + r * ld + c0, z);
+    }
+#pragma unroll 4
+    for (int64_t r = r0 + rr; r < r1v; r += rpi) {
+        float v[V], g[V], o[V];
+        ldw(x + r * ld + c0, v);
+        ldw(dy + r * ld + c0, g);
+        if (dr.on) {
+            float ds[V];
+            dropw<V>(dr, (uint64_t)(r * vpr4 + c0 / 4), ds);
+#pragma unroll
+            for (int q = 0; q < V; ++q) g[q] *= ds[q];
+        }
+#pragma unroll
+        for (int q = 0; q < V; ++q) {
+            if (relu && fmaf(v[q], sc[q], sh[q]) <= 0.f) g[q] = 0.f;
+            if (training) {
+                const float xh = (v[q] - mu[q]) * rs[q];
+                o[q] = sc[q] * (g[q] - m0[q] - xh * m1[q]);      // sc = gamma * rstd
+            } else {
+                o[q] = sc[q] * g[q];
+            }
+        }
+        stw(dx + r * ld + c0, o);
+    }
+}
+
 // ------------------------------------------------------------------ LayerNorm (+resid, +gather)
-// one warp per row, d <= 1024, d % 4 == 0; lane owns vectors lane, lane+32, ...
-constexpr int LN_MAXV = 8;  // d <= 1024
-template <typename T, int MAXV>
+// one warp per row, d <= 1024; lane owns the VW-element vectors lane, lane+32, ...  VW = 8 (16-byte accesses) for bf16
+// rows of d % 8 == 0 wider than one 4-element pass, VW = 4 otherwise.
+constexpr int LN_MAXV = 8;  // d <= 1024 with VW = 4
+template <int VW, typename T> __device__ __forceinline__ void ldx(const T* p, float (&v)[VW]) {
+    if constexpr (VW == 8) ldw<T, 8>(p, v); else ld4(p, v);
+}
+template <int VW, typename T> __device__ __forceinline__ void stx(T* p, const float (&v)[VW]) {
+    if constexpr (VW == 8) stw<T, 8>(p, v); else st4(p, v);
+}
+template <int VW> __device__ __forceinline__ void ldxf(const float* p, float (&v)[VW]) {
+#pragma unroll
+    for (int h = 0; h < VW / 4; ++h) {
+        const float4 t = *reinterpret_cast<const float4*>(p + 4 * h);
+        v[4 * h] = t.x; v[4 * h + 1] = t.y; v[4 * h + 2] = t.z; v[4 * h + 3] = t.w;
+    }
+}
+
+template <typename T, int MAXV, int VW>
 __global__ void k_layernorm_fwd(const T* __restrict__ x, const T* __restrict__ resid,
                                 const int32_t* __restrict__ in_rows, const float* __restrict__ cls, int64_t M,
                                 int d, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
@@ -571,33 +653,36 @@ __global__ void k_layernorm_fwd(const T* __restrict__ x, const T* __restrict__ r
     const int lane = threadIdx.x & 31;
     const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= M) return;
-    const int nv = d / 4;
+    const int nv = d / VW, nv4 = d / 4;
     int64_t src = row;
     if (in_rows) src = in_rows[row];
-    float v[MAXV][4];
+    float v[MAXV][VW];
     float s = 0.f;
 #pragma unroll
     for (int k = 0; k < MAXV; ++k) {
         const int vi = lane + k * 32;
         if (vi < nv) {
-            if (src >= 0) ld4(x + src * d + vi * 4, v[k]);
-            else if (src == -1 && cls) ld4(cls + vi * 4, v[k]);
-            else v[k][0] = v[k][1] = v[k][2] = v[k][3] = 0.f;
-            if (dr.on) {   // LN(drop(x) + resid): dropout on the sub-layer output before the residual add
-                float ds[4];
-                drop4(dr, (uint64_t)(row * nv + vi), ds);
+            if (src >= 0) ldx<VW>(x + src * d + vi * VW, v[k]);
+            else if (src == -1 && cls) ldxf<VW>(cls + vi * VW, v[k]);
+            else {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) v[k][q] *= ds[q];
+                for (int q = 0; q < VW; ++q) v[k][q] = 0.f;
+            }
+            if (dr.on) {   // LN(drop(x) + resid): dropout on the sub-layer output before the residual add
+                float ds[VW];
+                dropw<VW>(dr, (uint64_t)(row * nv4 + vi * (VW / 4)), ds);
+#pragma unroll
+                for (int q = 0; q < VW; ++q) v[k][q] *= ds[q];
             }
             if (resid) {
-                float t[4];
-                ld4(resid + row * d + vi * 4, t);
+                float t[VW];
+                ldx<VW>(resid + row * d + vi * VW, t);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) v[k][q] += t[q];
+                for (int q = 0; q < VW; ++q) v[k][q] += t[q];
             }
-            if (presum) st4(presum + row * d + vi * 4, v[k]);
+            if (presum) stx<VW>(presum + row * d + vi * VW, v[k]);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) s += v[k][q];
+            for (int q = 0; q < VW; ++q) s += v[k][q];
         }
     }
     const float mean = warp_sum(s) / (float)d;
@@ -606,7 +691,7 @@ __global__ void k_layernorm_fwd(const T* __restrict__ x, const T* __restrict__ r
     for (int k = 0; k < MAXV; ++k)
         if (lane + k * 32 < nv)
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < VW; ++q) {
                 const float t = v[k][q] - mean;
                 s2 = fmaf(t, t, s2);
             }
@@ -615,12 +700,12 @@ __global__ void k_layernorm_fwd(const T* __restrict__ x, const T* __restrict__ r
     for (int k = 0; k < MAXV; ++k) {
         const int vi = lane + k * 32;
         if (vi < nv) {
-            float g[4], b[4], o[4];
-            ld4(gamma + vi * 4, g);
-            ld4(beta + vi * 4, b);
+            float g[VW], b[VW], o[VW];
+            ldxf<VW>(gamma + vi * VW, g);
+            ldxf<VW>(beta + vi * VW, b);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) o[q] = fmaf((v[k][q] - mean) * rstd, g[q], b[q]);
-            st4(y + row * d + vi * 4, o);
+            for (int q = 0; q < VW; ++q) o[q] = fmaf((v[k][q] - mean) * rstd, g[q], b[q]);
+            stx<VW>(y + row * d + vi * VW, o);
         }
     }
     if (lane == 0 && mean_rstd) {
@@ -629,10 +714,13 @@ __global__ void k_layernorm_fwd(const T* __restrict__ x, const T* __restrict__ r
     }
 }
 
-// block = 8 warps; each warp loops over rows (grid-stride); per-lane dgamma/dbeta partials kept in
-// registers and flushed once per block through shared memory + atomics.
-template <typename T, int MAXV>
-__global__ void k_layernorm_bwd(const T* __restrict__ dy, const T* __restrict__ presum,
+// block = 8 warps; each warp loops over rows (grid-stride), R rows per iteration with all their loads in flight before
+// the first shuffle reduction (one row at a time is a load -> reduce -> store latency chain; rows per warp, not bytes,
+// set the time); per-lane dgamma/dbeta partials kept in registers and flushed once per block through shared memory +
+// atomics.
+template <typename T, int MAXV, int VW, int R>
+__global__ void __launch_bounds__(256, (MAXV * VW <= 16) ? 2 : 1)
+k_layernorm_bwd(const T* __restrict__ dy, const T* __restrict__ presum,
                                 const float* __restrict__ mean_rstd, const int32_t* __restrict__ out_rows,
                                 int64_t M, int d, const float* __restrict__ gamma, T* __restrict__ dx,
                                 float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dcls,
@@ -640,25 +728,22 @@ __global__ void k_layernorm_bwd(const T* __restrict__ dy, const T* __restrict__ 
     const Drop dr = make_drop(rng, salt, drop_p);
     extern __shared__ float sh[];  // [2*d]
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const int nv = d / 4;
+    const int nv = d / VW, nv4 = d / 4;
     for (int i = threadIdx.x; i < 2 * d; i += blockDim.x) sh[i] = 0.f;
     __syncthreads();
-    float ag[MAXV][4], ab[MAXV][4];
+    float ag[MAXV][VW], ab[MAXV][VW];
 #pragma unroll
     for (int k = 0; k < MAXV; ++k)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) ag[k][q] = ab[k][q] = 0.f;
-    // a warp takes LN_BR consecutive rows per iteration: the loads of all of them are in flight before the first shuffle
-    // reduction (one row at a time is a load -> reduce -> store latency chain; rows per warp, not bytes, set the time)
-    constexpr int R = MAXV == 1 ? 4 : (MAXV == 2 ? 2 : 1);
-    float gmm[MAXV][4];
+        for (int q = 0; q < VW; ++q) ag[k][q] = ab[k][q] = 0.f;
+    float gmm[MAXV][VW];
 #pragma unroll
     for (int k = 0; k < MAXV; ++k) {
         const int vi = lane + k * 32;
-        if (vi < nv) ld4(gamma + vi * 4, gmm[k]);
+        if (vi < nv) ldxf<VW>(gamma + vi * VW, gmm[k]);
     }
     for (int64_t row0 = (blockIdx.x * (int64_t)nw + wid) * R; row0 < M; row0 += (int64_t)gridDim.x * nw * R) {
-        float xh[R][MAXV][4], gy[R][MAXV][4], mean[R], rstd[R], s1[R], s2[R];
+        float xh[R][MAXV][VW], gy[R][MAXV][VW], mean[R], rstd[R], s1[R], s2[R];
 #pragma unroll
         for (int rr = 0; rr < R; ++rr) {
             const int64_t row = row0 + rr;
@@ -669,10 +754,10 @@ __global__ void k_layernorm_bwd(const T* __restrict__ dy, const T* __restrict__ 
             for (int k = 0; k < MAXV; ++k) {
                 const int vi = lane + k * 32;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) xh[rr][k][q] = gy[rr][k][q] = 0.f;
+                for (int q = 0; q < VW; ++q) xh[rr][k][q] = gy[rr][k][q] = 0.f;
                 if (ok && vi < nv) {
-                    ld4(dy + row * d + vi * 4, gy[rr][k]);
-                    ld4(presum + row * d + vi * 4, xh[rr][k]);
+                    ldx<VW>(dy + row * d + vi * VW, gy[rr][k]);
+                    ldx<VW>(presum + row * d + vi * VW, xh[rr][k]);
                 }
             }
         }
@@ -684,7 +769,7 @@ __global__ void k_layernorm_bwd(const T* __restrict__ dy, const T* __restrict__ 
                 const int vi = lane + k * 32;
                 if (vi < nv && row0 + rr < M) {
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
+                    for (int q = 0; q < VW; ++q) {
                         const float t = gy[rr][k][q];
                         xh[rr][k][q] = (xh[rr][k][q] - mean[rr]) * rstd[rr];
                         ab[k][q] += t;
@@ -711,21 +796,21 @@ __global__ void k_layernorm_bwd(const T* __restrict__ dy, const T* __restrict__ 
             for (int k = 0; k < MAXV; ++k) {
                 const int vi = lane + k * 32;
                 if (vi < nv) {
-                    float o[4];
+                    float o[VW];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) o[q] = rstd[rr] * (gy[rr][k][q] - s1[rr] - xh[rr][k][q] * s2[rr]);
+                    for (int q = 0; q < VW; ++q) o[q] = rstd[rr] * (gy[rr][k][q] - s1[rr] - xh[rr][k][q] * s2[rr]);
                     if (dst >= 0) {
-                        st4(dx + dst * d + vi * 4, o);
+                        stx<VW>(dx + dst * d + vi * VW, o);
                         if (dx_drop) {   // gradient of the dropped operand: same mask as the forward
-                            float ds[4];
-                            drop4(dr, (uint64_t)(row * nv + vi), ds);
+                            float ds[VW];
+                            dropw<VW>(dr, (uint64_t)(row * nv4 + vi * (VW / 4)), ds);
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) o[q] *= ds[q];
-                            st4(dx_drop + dst * d + vi * 4, o);
+                            for (int q = 0; q < VW; ++q) o[q] *= ds[q];
+                            stx<VW>(dx_drop + dst * d + vi * VW, o);
                         }
                     } else if (dst == -1 && dcls) {
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) atomicAdd(dcls + vi * 4 + q, o[q]);
+                        for (int q = 0; q < VW; ++q) atomicAdd(dcls + vi * VW + q, o[q]);
                     }
                 }
             }
@@ -736,9 +821,9 @@ __global__ void k_layernorm_bwd(const T* __restrict__ dy, const T* __restrict__ 
         const int vi = lane + k * 32;
         if (vi < nv)
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                atomicAdd(&sh[vi * 4 + q], ag[k][q]);
-                atomicAdd(&sh[d + vi * 4 + q], ab[k][q]);
+            for (int q = 0; q < VW; ++q) {
+                atomicAdd(&sh[vi * VW + q], ag[k][q]);
+                atomicAdd(&sh[d + vi * VW + q], ab[k][q]);
             }
     }
     __syncthreads();
@@ -1200,6 +1285,12 @@ extern "C" int gt_bn_bwd_apply(int dt, const void* x, const void* dy, int64_t M,
                                void* dx, float* dgamma, float* dbeta, float drop_p, const uint64_t* rng_state,
                                uint64_t salt, const int32_t* m_valid, void* stream) {
     GT_CHECK_ARG(M > 0 && ld >= d && ld % 4 == 0, "gt_bn_bwd_apply: bad shape");
+    Slab sl;
+    if (slab_cfg(dt, M, ld, {x, dy, dx, ssmr}, &sl)) {
+        GT_DISPATCH_DT(dt, (k_bn_bwd_apply_slab<T><<<sl.grid, SLAB_THREADS, 0, ST>>>((const T*)x, (const T*)dy, M, d, ld, sl.tpr, sl.rpi, sl.rows_per_block, ssmr, relu, training, red, (T*)dx, dgamma, dbeta, drop_p, rng_state, salt, m_valid)));
+        GT_LAUNCH_CHECK("gt_bn_bwd_apply");
+        return 0;
+    }
     int64_t rpb;
     const dim3 grid = stat_grid(M, ld, &rpb);
     GT_DISPATCH_DT(dt, (k_bn_bwd_apply<T><<<grid, 256, 0, ST>>>((const T*)x, (const T*)dy, M, d, ld, rpb, ssmr, gamma, relu, training, red, (T*)dx, dgamma, dbeta, drop_p, rng_state, salt, m_valid)));
@@ -1212,10 +1303,22 @@ extern "C" int gt_layernorm_fwd(int dt, const void* x, const void* resid, const 
                                 void* presum, float* mean_rstd, float drop_p, const uint64_t* rng_state, uint64_t salt,
                                 void* stream) {
     GT_CHECK_ARG(M > 0 && d > 0 && d % 4 == 0 && d <= LN_MAXV * 128, "gt_layernorm_fwd: d=%d must be a multiple of 4 and <= %d", d, LN_MAXV * 128);
-    GT_DISPATCH_DT(dt, {
-        if (d <= 256) k_layernorm_fwd<T, 2><<<(int)((M + 7) / 8), 256, 0, ST>>>((const T*)x, (const T*)resid, in_rows, cls, M, d, gamma, beta, eps, (T*)y, (T*)presum, mean_rstd, drop_p, rng_state, salt);
-        else k_layernorm_fwd<T, LN_MAXV><<<(int)((M + 7) / 8), 256, 0, ST>>>((const T*)x, (const T*)resid, in_rows, cls, M, d, gamma, beta, eps, (T*)y, (T*)presum, mean_rstd, drop_p, rng_state, salt);
-    });
+    const int grid_f = (int)((M + 7) / 8);
+#define LNF(MAXV, VW) k_layernorm_fwd<T, MAXV, VW><<<grid_f, 256, 0, ST>>>((const T*)x, (const T*)resid, in_rows, cls, M, d, gamma, beta, eps, (T*)y, (T*)presum, mean_rstd, drop_p, rng_state, salt)
+    // bf16 rows wider than one 4-element pass: 16-byte accesses (8 channels per lane and vector)
+    const bool wide = dt == GT_BF16 && d % 8 == 0 && d > 128 && ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0) &&
+                      (!resid || (uintptr_t)resid % 16 == 0) && (!presum || (uintptr_t)presum % 16 == 0);
+    if (wide) {
+        if (d <= 256) k_layernorm_fwd<bf16, 1, 8><<<grid_f, 256, 0, ST>>>((const bf16*)x, (const bf16*)resid, in_rows, cls, M, d, gamma, beta, eps, (bf16*)y, (bf16*)presum, mean_rstd, drop_p, rng_state, salt);
+        else if (d <= 512) k_layernorm_fwd<bf16, 2, 8><<<grid_f, 256, 0, ST>>>((const bf16*)x, (const bf16*)resid, in_rows, cls, M, d, gamma, beta, eps, (bf16*)y, (bf16*)presum, mean_rstd, drop_p, rng_state, salt);
+        else k_layernorm_fwd<bf16, 4, 8><<<grid_f, 256, 0, ST>>>((const bf16*)x, (const bf16*)resid, in_rows, cls, M, d, gamma, beta, eps, (bf16*)y, (bf16*)presum, mean_rstd, drop_p, rng_state, salt);
+    } else {
+        GT_DISPATCH_DT(dt, {
+            if (d <= 256) LNF(2, 4);
+            else LNF(LN_MAXV, 4);
+        });
+    }
+#undef LNF
     GT_LAUNCH_CHECK("gt_layernorm_fwd");
     return 0;
 }
@@ -1231,11 +1334,21 @@ extern "C" int gt_layernorm_bwd(int dt, const void* dy, const void* presum, cons
     // latency chain, so rows per warp, not bytes, set the duration at these sizes)
     const int br = d <= 128 ? 4 : (d <= 256 ? 2 : 1);                  // rows per warp iteration (kernel's R)
     const int grid = blocks_for((M + br - 1) / br, 8, 3 * kNumSMs);
-    GT_DISPATCH_DT(dt, {
-        if (d <= 128) k_layernorm_bwd<T, 1><<<grid, 256, 2 * d * sizeof(float), ST>>>((const T*)dy, (const T*)presum, mean_rstd, out_rows, M, d, gamma, (T*)dx, dgamma, dbeta, dcls, (T*)dx_drop, drop_p, rng_state, salt);
-        else if (d <= 256) k_layernorm_bwd<T, 2><<<grid, 256, 2 * d * sizeof(float), ST>>>((const T*)dy, (const T*)presum, mean_rstd, out_rows, M, d, gamma, (T*)dx, dgamma, dbeta, dcls, (T*)dx_drop, drop_p, rng_state, salt);
-        else k_layernorm_bwd<T, LN_MAXV><<<grid, 256, 2 * d * sizeof(float), ST>>>((const T*)dy, (const T*)presum, mean_rstd, out_rows, M, d, gamma, (T*)dx, dgamma, dbeta, dcls, (T*)dx_drop, drop_p, rng_state, salt);
-    });
+    const bool wide = dt == GT_BF16 && d % 8 == 0 && d > 128 && ((uintptr_t)dy % 16 == 0) && ((uintptr_t)presum % 16 == 0) &&
+                      ((uintptr_t)dx % 16 == 0) && (!dx_drop || (uintptr_t)dx_drop % 16 == 0);
+#define LNB(TT, MAXV, VW, RR, G) k_layernorm_bwd<TT, MAXV, VW, RR><<<G, 256, 2 * d * sizeof(float), ST>>>((const TT*)dy, (const TT*)presum, mean_rstd, out_rows, M, d, gamma, (TT*)dx, dgamma, dbeta, dcls, (TT*)dx_drop, drop_p, rng_state, salt)
+    if (wide) {      // 16-byte accesses, four (d <= 256) / two (d <= 512) / one row(s) of a warp in flight
+        if (d <= 256) LNB(bf16, 1, 8, 4, blocks_for((M + 3) / 4, 8, 3 * kNumSMs));
+        else if (d <= 512) LNB(bf16, 2, 8, 2, blocks_for((M + 1) / 2, 8, 3 * kNumSMs));
+        else LNB(bf16, 4, 8, 1, blocks_for(M, 8, 3 * kNumSMs));
+    } else {
+        GT_DISPATCH_DT(dt, {
+            if (d <= 128) LNB(T, 1, 4, 4, grid);
+            else if (d <= 256) LNB(T, 2, 4, 2, grid);
+            else LNB(T, LN_MAXV, 4, 1, grid);
+        });
+    }
+#undef LNB
     GT_LAUNCH_CHECK("gt_layernorm_bwd");
     return 0;
 }
