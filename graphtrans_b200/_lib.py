@@ -50,6 +50,7 @@ SIGNATURES = {
     "gt_bn_bwd_apply": [I, P, P, L, I32, I32, P, P, I, I, P, P, P, P, F, P, U64, P, P],
     "gt_gemm": [I, P, I, L, P, I, L, P, L, L, L, L, L, P, P, L, I, F, P, U64, I, P],
     "gt_gemm_stats": [I, P, I, L, P, I, L, P, L, L, L, L, L, P, P, L, I, F, P, U64, I, P, P, P],
+    "gt_split3": [P, L, L, L, P, L, P],
     "gt_relu_bwd": [I, P, P, L, P, F, P],
     "gt_colsum": [I, P, L, L, L, P, P],
     "gt_cast_multi": [P, I32, L, P],

@@ -347,24 +347,43 @@ __global__ void k_mha_meta(const int32_t* __restrict__ tok_graph, const int32_t*
 }
 
 // ------------------------------------------------------------------------------------------ backward
-// delta[h, row] = sum_c dO[row, h*dh + c] * O[row, h*dh + c]   (one warp per (row, head))
+// delta[h, row] = sum_c dO[row, h*dh + c] * O[row, h*dh + c].  A thread owns one 16-byte vector (8 channels) of a row,
+// the dh / 8 lanes of a (row, head) meet with xor shuffles: the two [n_rows, d] matrices are streamed once with fully
+// coalesced 16-byte loads, two vectors per thread in flight (dh in {32, 64}: 4 or 8 lanes per head).
 __global__ void __launch_bounds__(256)
 k_mha_delta(const bf16* __restrict__ out, const bf16* __restrict__ dout, int64_t n_rows, int nhead, int dh,
             float* __restrict__ delta) {
-    const int lane = threadIdx.x & 31;
-    const int64_t item = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (item >= n_rows * nhead) return;
-    const int64_t row = item / nhead;
-    const int h = (int)(item - row * nhead);
-    const int64_t off = row * (int64_t)(nhead * dh) + h * dh;
-    float s = 0.f;
-    for (int c = lane * 2; c < dh; c += 64) {
-        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(out + off + c));
-        const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dout + off + c));
-        s = fmaf(a.x, b.x, fmaf(a.y, b.y, s));
+    const int d = nhead * dh, gl = dh >> 3;          // lanes per (row, head)
+    const int64_t nvec = n_rows * (int64_t)(d >> 3);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t v0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v0 - threadIdx.x % 32 < nvec; v0 += 2 * stride) {
+        float s[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int64_t v = v0 + u * stride;
+            s[u] = 0.f;
+            if (v < nvec) {
+                const uint4 a = *reinterpret_cast<const uint4*>(out + v * 8);
+                const uint4 b = *reinterpret_cast<const uint4*>(dout + v * 8);
+                const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    s[u] = fmaf(__uint_as_float(aw[i] << 16), __uint_as_float(bw[i] << 16), s[u]);
+                    s[u] = fmaf(__uint_as_float(aw[i] & 0xffff0000u), __uint_as_float(bw[i] & 0xffff0000u), s[u]);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            for (int o = gl >> 1; o > 0; o >>= 1) s[u] += __shfl_xor_sync(0xffffffffu, s[u], o);
+            const int64_t v = v0 + u * stride;
+            if (v < nvec && (v & (gl - 1)) == 0) {
+                const int64_t e = v * 8, row = e / d;
+                const int h = (int)(e - row * d) / dh;
+                delta[(int64_t)h * n_rows + row] = s[u];
+            }
+        }
     }
-    s = warp_sum(s);
-    if (lane == 0) delta[(int64_t)h * n_rows + row] = s;
 }
 
 struct AttnBwdParams {
@@ -750,8 +769,11 @@ int mha_tc_bwd_launch(int dt, const void* qkv, const void* out, const void* dout
         set_error("cuTensorMapEncodeTiled failed or unavailable");
         return -2;
     }
-    const int64_t items = n_rows * nhead;
-    k_mha_delta<<<(unsigned)((items + 7) / 8), 256, 0, st>>>((const bf16*)out, (const bf16*)dout, n_rows, nhead, dh, delta);
+    {
+        const int64_t nvec = n_rows * (int64_t)(d >> 3);
+        const int blocks = blocks_for((nvec + 1) / 2, 256, kNumSMs * 8);
+        k_mha_delta<<<blocks, 256, 0, st>>>((const bf16*)out, (const bf16*)dout, n_rows, nhead, dh, delta);
+    }
     AttnBwdParams p;
     p.tok_graph = tok_graph; p.tok_off = tok_off; p.lse = lse; p.delta = delta; p.dqkv = dqkv; p.rng = rng; p.salt = salt;
     p.row_bounds = (const int2*)row_bounds; p.tile_bounds = (const int2*)tile_bounds;

@@ -1148,6 +1148,49 @@ k_colsum_v(const T* __restrict__ X, int64_t M, int N, int64_t ld, int64_t rows_p
     }
 }
 
+// wide variant: 16-byte accesses (8 bf16 / 4 fp32 channels per lane), 16 row lanes x 16 column lanes, four rows of a
+// thread in flight; one fp32 atomic per (block, channel)
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_colsum_w(const T* __restrict__ X, int64_t M, int N, int64_t ld, int64_t rows_per_block, float* __restrict__ out) {
+    constexpr int V = VecW<T>::V, TX = 16, TY = 16;
+    __shared__ float sh[TY][TX * V + 1];
+    const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+    const int c0 = (blockIdx.x * TX + tx) * V;
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_block, r1 = min(r0 + rows_per_block, M);
+    float s[V];
+#pragma unroll
+    for (int q = 0; q < V; ++q) s[q] = 0.f;
+    if (c0 < N) {
+        int64_t r = r0 + ty;
+        for (; r + 3 * TY < r1; r += 4 * TY) {
+            float v[4][V];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) ldw(X + (r + u * TY) * ld + c0, v[u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int q = 0; q < V; ++q) s[q] += v[u][q];
+        }
+        for (; r < r1; r += TY) {
+            float v[V];
+            ldw(X + r * ld + c0, v);
+#pragma unroll
+            for (int q = 0; q < V; ++q) s[q] += v[q];
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < V; ++q) sh[ty][tx * V + q] = s[q];
+    __syncthreads();
+    if (threadIdx.x < TX * V) {
+        float a = 0.f;
+#pragma unroll
+        for (int k = 0; k < TY; ++k) a += sh[k][threadIdx.x];
+        const int c = blockIdx.x * TX * V + threadIdx.x;
+        if (c < N) atomicAdd(out + c, a);
+    }
+}
+
 }  // namespace gt
 
 using namespace gt;
@@ -1334,8 +1377,8 @@ extern "C" int gt_layernorm_bwd(int dt, const void* dy, const void* presum, cons
     // latency chain, so rows per warp, not bytes, set the duration at these sizes)
     const int br = d <= 128 ? 4 : (d <= 256 ? 2 : 1);                  // rows per warp iteration (kernel's R)
     const int grid = blocks_for((M + br - 1) / br, 8, 3 * kNumSMs);
-    const bool wide = dt == GT_BF16 && d % 8 == 0 && d > 128 && ((uintptr_t)dy % 16 == 0) && ((uintptr_t)presum % 16 == 0) &&
-                      ((uintptr_t)dx % 16 == 0) && (!dx_drop || (uintptr_t)dx_drop % 16 == 0);
+    const bool wide = env_int("GT_LN_WIDE", 1) && dt == GT_BF16 && d % 8 == 0 && d > 128 && ((uintptr_t)dy % 16 == 0) &&
+                      ((uintptr_t)presum % 16 == 0) && ((uintptr_t)dx % 16 == 0) && (!dx_drop || (uintptr_t)dx_drop % 16 == 0);
 #define LNB(TT, MAXV, VW, RR, G) k_layernorm_bwd<TT, MAXV, VW, RR><<<G, 256, 2 * d * sizeof(float), ST>>>((const TT*)dy, (const TT*)presum, mean_rstd, out_rows, M, d, gamma, (TT*)dx, dgamma, dbeta, dcls, (TT*)dx_drop, drop_p, rng_state, salt)
     if (wide) {      // 16-byte accesses, four (d <= 256) / two (d <= 512) / one row(s) of a warp in flight
         if (d <= 256) LNB(bf16, 1, 8, 4, blocks_for((M + 3) / 4, 8, 3 * kNumSMs));
@@ -1545,6 +1588,31 @@ extern "C" int gt_add_blocks(const float* src, int32_t ld_src, int32_t n, float*
     return 0;
 }
 
+// fp32 -> three bf16 terms (x = p0 + p1 + p2 up to 2^-24 |x|): p0 = bf16(x), p1 = bf16(x - p0), p2 = bf16(x - p0 - p1)
+namespace gt {
+__global__ void k_split3(const float* __restrict__ src, int64_t rows, int64_t cols, int64_t ld_src, bf16* __restrict__ dst,
+                         int64_t ld_dst) {
+    const int64_t total = rows * ld_dst, plane = rows * ld_dst;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / ld_dst, c = i - r * ld_dst;
+        float x = c < cols ? src[r * ld_src + c] : 0.f;
+        const bf16 p0 = __float2bfloat16_rn(x);
+        x -= __bfloat162float(p0);
+        const bf16 p1 = __float2bfloat16_rn(x);
+        x -= __bfloat162float(p1);
+        dst[i] = p0;
+        dst[plane + i] = p1;
+        dst[2 * plane + i] = __float2bfloat16_rn(x);
+    }
+}
+}  // namespace gt
+extern "C" int gt_split3(const float* src, int64_t rows, int64_t cols, int64_t ld_src, void* dst, int64_t ld_dst, void* stream) {
+    GT_CHECK_ARG(rows > 0 && cols > 0 && ld_src >= cols && ld_dst >= cols, "gt_split3: bad shape");
+    gt::k_split3<<<blocks_for(rows * ld_dst, 256), 256, 0, ST>>>(src, rows, cols, ld_src, (gt::bf16*)dst, ld_dst);
+    GT_LAUNCH_CHECK("gt_split3");
+    return 0;
+}
+
 extern "C" int gt_cast_multi(const int64_t* desc_dev, int32_t n, int64_t total_blocks, void* stream) {
     GT_CHECK_ARG(desc_dev && n > 0 && total_blocks > 0 && total_blocks < (1ll << 31), "gt_cast_multi: bad arguments");
     k_cast_multi<<<(unsigned)total_blocks, 256, 0, ST>>>(desc_dev, n);
@@ -1578,6 +1646,17 @@ extern "C" int gt_rng_advance(uint64_t* rng_state, void* stream) {
 extern "C" int gt_colsum(int dt, const void* X, int64_t M, int64_t N, int64_t ld, float* out, void* stream) {
     GT_CHECK_ARG(M > 0 && N > 0 && ld >= N, "gt_colsum: bad shape");
     const int esz = dt == GT_BF16 ? 2 : 4;
+    const int Vw = 16 / esz;
+    if (M >= 4096 && ld % Vw == 0 && (uintptr_t)X % 16 == 0 && (N + Vw - 1) / Vw * Vw <= ld) {   // tall matrices: 16-byte accesses
+        const int gx = (int)((N + 16 * Vw - 1) / (16 * Vw));
+        int64_t gy = (4 * kNumSMs + gx - 1) / gx;
+        if (gy > (M + 255) / 256) gy = (M + 255) / 256;
+        const int64_t rpb = (M + gy - 1) / gy;
+        gy = (M + rpb - 1) / rpb;
+        GT_DISPATCH_DT(dt, (k_colsum_w<T><<<dim3((unsigned)gx, (unsigned)gy), 256, 0, ST>>>((const T*)X, M, (int)N, ld, rpb, out)));
+        GT_LAUNCH_CHECK("gt_colsum");
+        return 0;
+    }
     if (ld % 4 == 0 && (uintptr_t)X % (4 * esz) == 0 && (N + 3) / 4 * 4 <= ld) {
         int64_t rpb;
         const dim3 grid = stat_grid(M, (int)((N + 3) / 4 * 4), &rpb);

@@ -22,6 +22,9 @@ FUSE_COLSTATS = int(os.environ.get("GT_FUSE_COLSTATS", "1"))         # BatchNorm
 SKIP_ZERO_BIAS_GRAD = int(os.environ.get("GT_SKIP_ZERO_BIAS_GRAD", "1"))   # bias of a Linear feeding train-mode BN: gradient == 0
 TABLE_GRAD_GEMM = int(os.environ.get("GT_TABLE_GRAD_GEMM", "1"))           # edge-table gradient as a one-hot contraction (bf16)
 MHA_IMPL = int(os.environ.get("GT_MHA_IMPL", "0"))
+# fp32 parity mode with every contraction ON the tcgen05 kernel: operands split into three bf16 terms, six products
+# accumulated in fp32 (SURVEY §7 "fp32 parity on tensor cores"); 0 = exact CUDA-core contractions (default parity path)
+GEMM_TC_PARITY = int(os.environ.get("GT_GEMM_TC_PARITY", "0"))
 
 
 def set_precision(p: str):
@@ -746,12 +749,57 @@ def _gemm_raw(dt, A, a_mn, lda, Bm, b_mn, ldb, C, ldc, M, N, K, n_fill, bias, re
     """raw-pointer gt_gemm (A, Bm, C are device addresses so strided sub-blocks need no copies); col_stats: fp64
     [2 * ldc] that receives the BatchNorm column statistics of C in the same pass (gt_gemm_stats; m_valid: device
     int32[1] = number of leading real rows when the matrix carries shape-bucket slack rows)"""
+    if dt == GT_F32 and GEMM_TC_PARITY and (impl is None or impl == 2):
+        return _gemm_split3(A, a_mn, lda, Bm, b_mn, ldb, C, ldc, M, N, K, n_fill, bias, resid, ldr, flags, drop_p, rng, salt,
+                            col_stats, m_valid)
     if col_stats is not None:
         call("gt_gemm_stats", dt, A, int(a_mn), lda, Bm, int(b_mn), ldb, C, ldc, M, N, K, n_fill, ptr(bias), ptr(resid), ldr,
              flags, float(drop_p), rng, salt, GEMM_IMPL if impl is None else impl, ptr(col_stats), ptr(m_valid))
         return
     call("gt_gemm", dt, A, int(a_mn), lda, Bm, int(b_mn), ldb, C, ldc, M, N, K, n_fill, ptr(bias), ptr(resid), ldr,
          flags, float(drop_p), rng, salt, GEMM_IMPL if impl is None else impl)
+
+
+def _gemm_split3(A, a_mn, lda, Bm, b_mn, ldb, C, ldc, M, N, K, n_fill, bias, resid, ldr, flags, drop_p, rng, salt, col_stats,
+                 m_valid):
+    """fp32 contraction on the tcgen05 kernel: A = a0 + a1 + a2, B = b0 + b1 + b2 (bf16 terms, gt_split3), C = sum of the
+    six products a_i . b_j with i + j <= 2 (what is dropped is below 2^-22 of |A||B|), accumulated in fp32.  The five
+    small terms are accumulated first into an fp32 scratch, the leading term a0 . b0 is the last call and takes the scratch
+    as its residual operand, so bias / ReLU / dropout / column fill / BatchNorm statistics are the normal epilogue."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    ra, ca = (K, M) if a_mn else (M, K)           # stored rows x contiguous columns of each operand
+    rb, cb = (K, N) if b_mn else (N, K)
+    la, lb = ldp(ca), ldp(cb)
+    sa = torch.empty(3, ra, la, dtype=torch.bfloat16, device=dev)
+    sb = torch.empty(3, rb, lb, dtype=torch.bfloat16, device=dev)
+    call("gt_split3", A, ra, ca, lda, ptr(sa), la)
+    call("gt_split3", Bm, rb, cb, ldb, ptr(sb), lb)
+    pa = [sa[i].data_ptr() for i in range(3)]
+    pb = [sb[i].data_ptr() for i in range(3)]
+    small = ((0, 1), (1, 0), (0, 2), (2, 0), (1, 1))
+    if flags & EPI_ACCUM:                          # weight gradients: every term accumulates straight into C
+        for i, j in ((0, 0),) + small:
+            call("gt_gemm", GT_BF16, pa[i], int(a_mn), la, pb[j], int(b_mn), lb, C, ldc, M, N, K, n_fill, None, None, 0,
+                 EPI_ACCUM | EPI_OUT_F32, 0.0, None, 0, 2)
+        return
+    if resid is not None:
+        if ldr != ldc:
+            raise RuntimeError("tensor-core parity mode: the residual operand must share the output's row pitch")
+        part = resid.to(torch.float32).clone().contiguous()
+        if part.stride(0) != ldc:
+            raise RuntimeError("tensor-core parity mode: unexpected residual layout")
+    else:
+        part = torch.zeros(M, ldc, dtype=torch.float32, device=dev)
+    for i, j in small:
+        call("gt_gemm", GT_BF16, pa[i], int(a_mn), la, pb[j], int(b_mn), lb, ptr(part), ldc, M, N, K, N, None, None, 0,
+             EPI_ACCUM | EPI_OUT_F32, 0.0, None, 0, 2)
+    fl = (flags & EPI_RELU) | EPI_OUT_F32 | _lib.EPI_RESID_F32
+    if col_stats is not None:
+        call("gt_gemm_stats", GT_BF16, pa[0], int(a_mn), la, pb[0], int(b_mn), lb, C, ldc, M, N, K, n_fill, ptr(bias), ptr(part), ldc,
+             fl, float(drop_p), rng, salt, 2, ptr(col_stats), ptr(m_valid))
+    else:
+        call("gt_gemm", GT_BF16, pa[0], int(a_mn), la, pb[0], int(b_mn), lb, C, ldc, M, N, K, n_fill, ptr(bias), ptr(part), ldc,
+             fl, float(drop_p), rng, salt, 2)
 
 
 class _LinearFn(torch.autograd.Function):

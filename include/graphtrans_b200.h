@@ -225,6 +225,10 @@ int gt_gemm_stats(int dt, const void* A, int a_mn, int64_t lda, const void* B, i
 /* dz = dy * (y > 0) * scale: backward of a ReLU (+ dropout: a dropped element has y == 0, scale = 1/(1-p)) that
  * was fused into a GEMM epilogue; n % 4 == 0 */
 int gt_relu_bwd(int dt, const void* dy, const void* y, int64_t n, void* dz, float scale, void* stream);
+/* fp32 parity mode ON the tensor cores: dst bf16 [3][rows][ld_dst] = the three-term split x = p0 + p1 + p2 of src fp32
+ * [rows, cols] (row pitch ld_src; columns cols..ld_dst-1 := 0).  The host sums the six products p_i . q_j with i + j <= 2
+ * through gt_gemm (fp32 accumulation in TMEM), which reproduces an fp32 contraction to ~2^-22 (ops._gemm_raw, GT_GEMM_TC_PARITY). */
+int gt_split3(const float* src, int64_t rows, int64_t cols, int64_t ld_src, void* dst, int64_t ld_dst, void* stream);
 /* out[n] += sum_m X[m,n]  (bias gradients) ; out fp32 [N] is ACCUMULATED into (caller zeroes a fresh buffer) */
 int gt_colsum(int dt, const void* X, int64_t M, int64_t N, int64_t ld, float* out, void* stream);
 /* dst[r, 0:cols_out] = cast(src[r, 0:cols_in]) zero padded to cols_out; rows_out >= rows_in zero padded;

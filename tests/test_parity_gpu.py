@@ -73,6 +73,26 @@ def test_golden_fwd_bwd_fp32(name):
 
 
 @pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_golden_fwd_bwd_fp32_on_tensor_cores(name):
+    """the fp32 contract with EVERY contraction on the tcgen05 kernel (ops.GEMM_TC_PARITY: three-term bf16 split, six
+    products accumulated in fp32 in TMEM) - the tensor-core GEMM itself meets the <= 1e-3 bar (SURVEY 7 'fp32 parity on
+    tensor cores'), not only its CUDA-core twin"""
+    fx = load_golden(name)
+    ops.GEMM_TC_PARITY = 1
+    try:
+        k0 = ops._lib.kernel_count
+        model, pred, loss, grads, bufs = run_product(fx["args"], fx["batch"], fx["init_sd"])
+        assert ops._lib.kernel_count > k0
+    finally:
+        ops.GEMM_TC_PARITY = 0
+    for a, b in zip(as_list(pred), as_list(fx["logits"])):
+        assert rel_l2(a.detach(), b) < LOGIT_TOL
+    assert abs(float(loss) - float(fx["loss"])) < 1e-4 * max(1.0, abs(float(fx["loss"])))
+    glob, worst, key = grad_report(grads, fx["grads"])
+    assert glob < GRAD_TOL and worst < WORST_TOL, (glob, worst, key)
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
 def test_golden_grads_with_wgrad_side_stream(name):
     """weight / bias / embedding gradients issued on the second stream (ops.enable_wgrad_stream) and the virtual-node
     update on the parallel branch stream (ops.enable_branch_stream): same parity bar"""
