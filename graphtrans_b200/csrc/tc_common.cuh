@@ -126,6 +126,13 @@ static bool make_map(CUtensorMap* map, const void* base, uint64_t dim0, uint64_t
                      int swizzle_bytes = 128, bool f32 = false) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
+    // the driver-API encode needs a current context: a thread that has made no runtime call yet (the autograd engine's
+    // worker thread when the first backward op of the process builds a tensor map) binds the primary context first
+    static thread_local bool ctx_bound = false;
+    if (!ctx_bound) {
+        cudaFree(nullptr);
+        ctx_bound = true;
+    }
     cuuint64_t gdim[2] = {dim0, dim1};
     cuuint64_t gstr[1] = {ld * (f32 ? 4 : 2)};
     cuuint32_t box[2] = {box0, box1};

@@ -52,6 +52,18 @@ def _mixed_radix_digits(dims, device):
     return _DIGITS[key]
 
 
+def edge_encoder_operands(convs, edge_attr, plan, d):
+    """the edge-encoder operands of ALL conv layers up front, on the parallel branch stream (when enabled): the combined
+    bond tables (<= 60 rows each) depend on the weights only, so their five tiny launches leave the critical path of the
+    layer loop.  -> list of kwargs for ops.aggregate, one per layer"""
+    ld = ops.ldp(d)
+    br = ops.Branch(edge_attr)
+    with br:
+        encs = [_edge_encoder_args(c.edge_encoder, edge_attr, plan, d, ld) for c in convs]
+    br.join(*[e.get("table") for e in encs], *[e.get("etype") for e in encs])
+    return encs
+
+
 class _ConvBase(torch.nn.Module):
     def _prep(self, x, edge_index, plan):
         d = self.emb_dim
@@ -75,11 +87,13 @@ class GINConv(_ConvBase):
         self.eps = torch.nn.Parameter(torch.Tensor([0]))
         self.edge_encoder = edge_encoder_cls(emb_dim)
 
-    def forward(self, x, edge_index, edge_attr, plan=None, out_bn=None, out_relu=False):
+    def forward(self, x, edge_index, edge_attr, plan=None, out_bn=None, out_relu=False, enc=None):
         """out_bn / out_relu: the BatchNorm (+ ReLU) the caller applies right after this conv; in eval mode it is
-        folded into mlp[3] and the result carries `_gt_bn_folded = True`"""
+        folded into mlp[3] and the result carries `_gt_bn_folded = True`.  enc: edge-encoder operands prepared by the
+        caller (`edge_encoder_operands`), None = built here"""
         x, plan, d, ld, logical = self._prep(x, edge_index, plan)
-        enc = _edge_encoder_args(self.edge_encoder, edge_attr, plan, d, ld)
+        if enc is None:
+            enc = _edge_encoder_args(self.edge_encoder, edge_attr, plan, d, ld)
         z = ops.aggregate(x, plan, CONV_GIN, d, self.eps, **enc)          # (1+eps) x + sum relu(x_j + e)
         # both Linears feed a train-mode BatchNorm (mlp[1] here, batch_norms[layer] in the caller): their column
         # statistics are taken in the GEMM epilogue
@@ -109,9 +123,10 @@ class GCNConv(_ConvBase):
         self.root_emb = torch.nn.Embedding(1, emb_dim)
         self.edge_encoder = edge_encoder_cls(emb_dim)
 
-    def forward(self, x, edge_index, edge_attr, plan=None):
+    def forward(self, x, edge_index, edge_attr, plan=None, enc=None):
         x, plan, d, ld, logical = self._prep(x, edge_index, plan)
-        enc = _edge_encoder_args(self.edge_encoder, edge_attr, plan, d, ld)
+        if enc is None:
+            enc = _edge_encoder_args(self.edge_encoder, edge_attr, plan, d, ld)
         xl = ops.linear(x, self.linear.weight, self.linear.bias)
         out = ops.aggregate(xl, plan, CONV_GCN, d, self.root_emb.weight, **enc)
         return out[:, :d].float() if logical else out

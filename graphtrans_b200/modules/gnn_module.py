@@ -6,7 +6,7 @@ Linear come out of that GEMM's epilogue (gt_gemm_stats)."""
 import torch
 
 from .. import ops
-from .conv import GCNConv, GINConv
+from .conv import GCNConv, GINConv, edge_encoder_operands
 
 
 def _encode(node_encoder, batched_data):
@@ -92,11 +92,12 @@ class GNN_node(_GNNBase):
         plan = plan or _plan_of(batched_data)
         edge_index, edge_attr = batched_data.edge_index, batched_data.edge_attr
         h_list = [self._input(batched_data, perturb)]
+        encs = edge_encoder_operands(self.convs, edge_attr, plan, self.emb_dim)
         for layer in range(self.num_layer):
             relu = layer != self.num_layer - 1
-            kw = {}
+            kw = dict(enc=encs[layer])
             if isinstance(self.convs[layer], GINConv) and not self.residual:   # eval: BatchNorm folded into mlp[3]
-                kw = dict(out_bn=self.batch_norms[layer], out_relu=relu)
+                kw.update(out_bn=self.batch_norms[layer], out_relu=relu)
             h = self.convs[layer](h_list[layer], edge_index, edge_attr, plan=plan, **kw)
             if not getattr(h, "_gt_bn_folded", False):
                 h = ops.batch_norm(h, self.batch_norms[layer], relu=relu,
@@ -130,6 +131,7 @@ class GNN_node_Virtualnode(_GNNBase):
         # per-graph virtual-node state, fp32 [B, ld]
         vn = ops.broadcast_row(self.virtualnode_embedding.weight, plan.B, ld)
         h_list = [ops.add_graph_vec(h0, vn, plan)]              # h + vn[batch]  (gnn_module.py:199)
+        encs = edge_encoder_operands(self.convs, edge_attr, plan, self.emb_dim)
         drop = self.drop_ratio if self.training else 0.0
         for layer in range(self.num_layer):
             hv = h_list[layer]
@@ -151,7 +153,7 @@ class GNN_node_Virtualnode(_GNNBase):
                         t = ops.batch_norm(ops.linear(t, mlp[3].weight, mlp[3].bias, col_stats=cs), mlp[4], relu=True, drop_p=drop)
                     t = ops.cast_to(t, torch.float32)             # the virtual-node state itself stays fp32
                     vn_next = vn + t if self.residual else t
-            h = self.convs[layer](hv, edge_index, edge_attr, plan=plan)
+            h = self.convs[layer](hv, edge_index, edge_attr, plan=plan, enc=encs[layer])
             if br is not None:
                 br.join(vn_next)
             # BN -> ReLU (not last) -> dropout -> (+residual) -> (+ next layer's vn[batch]) in one kernel
