@@ -75,7 +75,7 @@ SIGNATURES = {
     "gt_mha_cls_fwd": [I, P, P, P, P, L, L, I32, I32, F, P, P, F, P, U64, P],
     "gt_mha_cls_bwd": [I, P, P, P, P, P, P, P, L, L, I32, I32, F, P, P, F, P, U64, P],
     "gt_adamw_multi": [P, I32, L, P, P, P, P, P, P, P],
-    "gt_sumsq": [P, L, P, P],
+    "gt_sumsq": [P, L, P, P, I32, P],
     "gt_segment_pool_fwd": [I, I, P, P, L, I32, P, P, P],
     "gt_segment_pool_bwd": [I, I, P, P, P, P, L, I32, P, P],
     "gt_argmax_rows": [P, L, I32, L, P, P],

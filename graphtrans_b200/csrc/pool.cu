@@ -123,8 +123,11 @@ k_argmax_rows(const float* __restrict__ x, int64_t rows, int cols, int64_t ldx, 
     if (lane == 0) out[r] = bi == 0x7fffffff ? 0 : bi;
 }
 
+// deterministic: every block writes its partial sum to scratch[blockIdx.x]; the last block to finish (ticket in
+// scratch[gridDim.x]) adds the partials in index order - the same bits on every rank of a data-parallel job (the clip
+// coefficient derived from it must not differ between ranks) and on every replay
 __global__ void __launch_bounds__(256)
-k_sumsq(const float* __restrict__ x, int64_t n, float* __restrict__ out) {
+k_sumsq(const float* __restrict__ x, int64_t n, float* __restrict__ out, float* __restrict__ scratch) {
     float s = 0.f;
     const int64_t n4 = n / 4;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -137,10 +140,25 @@ k_sumsq(const float* __restrict__ x, int64_t n, float* __restrict__ out) {
     __shared__ float sh[8];
     if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
     __syncthreads();
+    __shared__ bool last;
     if (threadIdx.x == 0) {
         float t = 0.f;
         for (int k = 0; k < 8; ++k) t += sh[k];
-        atomicAdd(out, t);
+        scratch[blockIdx.x] = t;
+        __threadfence();
+        unsigned int* ticket = reinterpret_cast<unsigned int*>(scratch + gridDim.x);
+        last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last && threadIdx.x < 32) {
+        __threadfence();
+        float t = 0.f;                              // fixed order: lane l takes partials l, l + 32, ...; then a fixed shuffle tree
+        for (unsigned int i = threadIdx.x; i < gridDim.x; i += 32) t += __ldcg(scratch + i);
+        t = warp_sum(t);
+        if (threadIdx.x == 0) {
+            out[0] = t;
+            *reinterpret_cast<unsigned int*>(scratch + gridDim.x) = 0u;     // re-armed for the next launch / replay
+        }
     }
 }
 
@@ -185,9 +203,12 @@ extern "C" int gt_argmax_rows(const float* x, int64_t rows, int32_t cols, int64_
     return 0;
 }
 
-extern "C" int gt_sumsq(const float* x, int64_t n, float* out, void* stream) {
+extern "C" int gt_sumsq(const float* x, int64_t n, float* out, float* scratch, int32_t n_scratch, void* stream) {
     GT_CHECK_ARG(n > 0 && ((uintptr_t)x % 16) == 0, "gt_sumsq: needs a 16-byte aligned buffer");
-    k_sumsq<<<blocks_for(n / 4 + 1, 256, kNumSMs * 4), 256, 0, (cudaStream_t)stream>>>(x, n, out);
+    GT_CHECK_ARG(scratch && n_scratch >= 2, "gt_sumsq: needs a zero-initialised scratch of >= 2 floats");
+    int blocks = blocks_for(n / 4 + 1, 256, kNumSMs * 4);
+    if (blocks > n_scratch - 1) blocks = n_scratch - 1;
+    k_sumsq<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, n, out, scratch);
     GT_LAUNCH_CHECK("gt_sumsq");
     return 0;
 }

@@ -26,6 +26,7 @@ class FusedAdamW:
         self.clip = None
         if max_grad_norm is not None and max_grad_norm > 0:
             self.clip = torch.tensor([float(max_grad_norm), 0.0], dtype=torch.float32, device=flat.device)
+            self._clip_scratch = torch.zeros(4 * 148 + 1, dtype=torch.float32, device=flat.device)
         self._desc = self._ptrs = None
         self._blocks = 0
 
@@ -51,8 +52,8 @@ class FusedAdamW:
         if self._desc is None or self._ptrs != tuple(p.data_ptr() for p in self.buckets.params):
             self._build()
         if self.clip is not None:
-            self.clip[1:2].zero_()
-            call("gt_sumsq", ptr(self.buckets.flat), self.buckets.flat.numel(), self.clip.data_ptr() + 4)
+            call("gt_sumsq", ptr(self.buckets.flat), self.buckets.flat.numel(), self.clip.data_ptr() + 4,
+                 ptr(self._clip_scratch), self._clip_scratch.numel())
         call("gt_adamw_multi", ptr(self._desc), self._desc.shape[0], self._blocks, ptr(self.buckets.flat), ptr(self.m),
              ptr(self.v), ptr(self.hyper), ptr(self.step_count), ptr(self.clip))
 

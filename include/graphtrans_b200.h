@@ -344,9 +344,12 @@ int gt_adamw_multi(const int64_t* desc_dev, int32_t n, int64_t total_blocks, con
                    float* v_flat, const float* hyper_dev, int64_t* step_dev, const float* clip_dev, void* stream);
 /* clip_dev (optional DEVICE fp32[2] = {max_norm, sum of squares of the gradient arena}): torch.nn.utils.clip_grad_norm_
  * (reference trainers/base_trainer.py:34-35) folded into the optimizer's gradient read - every gradient is scaled by
- * min(1, max_norm / (sqrt(sumsq) + 1e-6)); the arena itself is left unscaled.  gt_sumsq accumulates sum x^2 of a
- * 16-byte aligned fp32 buffer into out[0] (pre-zeroed by the caller; with several ranks run it after the allreduce). */
-int gt_sumsq(const float* x, int64_t n, float* out, void* stream);
+ * min(1, max_norm / (sqrt(sumsq) + 1e-6)); the arena itself is left unscaled.  gt_sumsq writes out[0] = sum x^2 of a
+ * 16-byte aligned fp32 buffer DETERMINISTICALLY (per-block partials in scratch, added in index order by the last block):
+ * every rank of a data-parallel job derives the same clip coefficient from the same averaged gradients.  scratch: fp32
+ * [n_scratch >= 2], zero-initialised once by the caller (the last element is a ticket the kernel re-arms itself);
+ * with several ranks run it after the allreduce. */
+int gt_sumsq(const float* x, int64_t n, float* out, float* scratch, int32_t n_scratch, void* stream);
 
 /* ---- graph-level read-outs of the reference's baseline models (PyG global_mean_pool / global_max_pool, reference
  *      models/gnn.py:64-69, models/pna.py:74-79, models/transformer.py:49-54; global_add_pool = gt_segment_sum_sorted) --
