@@ -51,6 +51,18 @@ class _Entry:
     __slots__ = ("graph", "static_batch", "loss", "kernels", "staging", "stage_idx", "consumed", "sig")
 
 
+class LossHandle:
+    """loss of one step on its way to the host: `item()` waits for that step's device->host copy only"""
+    __slots__ = ("buf", "ev")
+
+    def __init__(self, buf, ev):
+        self.buf, self.ev = buf, ev
+
+    def item(self) -> float:
+        self.ev.synchronize()
+        return float(self.buf)
+
+
 class GraphedStep:
     def __init__(self, model, loss_fn, buckets, max_graphs=16, warmup_iters=2, optimizer=None, bucket=False):
         """optimizer: optional graphtrans_b200.optim.FusedAdamW; its step is part of the captured graph whenever the
@@ -79,6 +91,7 @@ class GraphedStep:
             self.capture_stream = torch.cuda.Stream(device=self.device, priority=-1)
         self.copy_stream = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
         self._staged = {}
+        self._loss_ring, self._ring_i = None, 0
 
     def _eager(self, b):
         self.buckets.zero_grad()
@@ -223,6 +236,20 @@ class GraphedStep:
                 getattr(sb, k).copy_(v, non_blocking=True)
         ent.graph.replay()
         return self._after_replay(ent)
+
+    def step_async(self, batch) -> LossHandle:
+        """one step whose loss is copied to pinned host memory asynchronously: the caller reads it (`handle.item()`) after
+        launching the NEXT step, so the device never idles on the host round trip that `loss.item()` per step
+        (reference trainers/base_trainer.py:41-44) costs; every step's loss still reaches the host"""
+        loss = self(batch)
+        if self._loss_ring is None:
+            self._loss_ring = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(8)]
+        buf = self._loss_ring[self._ring_i % len(self._loss_ring)]
+        self._ring_i += 1
+        buf.copy_(loss.detach().reshape(()).float(), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        return LossHandle(buf, ev)
 
     def _after_replay(self, ent):
         self.last_kernels = ent.kernels

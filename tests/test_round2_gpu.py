@@ -327,3 +327,34 @@ def test_eval_argmax_readout_code2():
             assert torch.equal(ids[:, h], p.argmax(1))
     finally:
         ops.set_precision("fp32")
+
+
+def test_prefetch_and_async_loss_match_plain_steps():
+    """the pipelined loop (H2D of batch i+1 under step i into persistent staging blobs, loss read one step late) returns
+    exactly the losses / gradients of plain synchronous steps on the same batches"""
+    ops.set_precision("fp32")
+    args = _small("molpcba")
+    torch.manual_seed(0)
+    model = factory.build_model(args).cuda().train()
+    lossf = factory.loss_fn(args)
+    buckets = GradBuckets(model, n_buckets=2, overlap=False)
+    step = GraphedStep(model, lossf, buckets, bucket=True)
+    batches = [_batch(args, 48, seed=300 + i) for i in range(10)]
+    plain, grads = [], []
+    for hb in batches:
+        plain.append(float(step(hb)))
+        grads.append(buckets.flat.clone())
+    got, pending = [], None
+    step.prefetch(batches[0])
+    for i, hb in enumerate(batches):
+        if i + 1 < len(batches):
+            step.prefetch(batches[i + 1])
+        h = step.step_async(hb)
+        if i == 4:
+            torch.cuda.synchronize()
+            assert torch.equal(buckets.flat, grads[4])          # same captured graph, same inputs: bit-identical
+        if pending is not None:
+            got.append(pending.item())
+        pending = h
+    got.append(pending.item())
+    assert got == plain
