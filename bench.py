@@ -518,7 +518,7 @@ def run_workload(ns, cfg, scaling, B_arg, rank, world, dev, K, W, full):
                    {(int(b.batch.numel()), int(b.edge_index.shape[1])) for b in host}
             for shp in sorted({(int(b.batch.numel()), int(b.edge_index.shape[1])) for b in timed} - have):
                 src = next((r for r in raw_warm if r.batch.numel() < shp[0] and r.edge_index.shape[1] <= shp[1]), None)
-                for t in range(24):                    # no warm batch fits under this bucket: draw more until one does
+                for t in range(64):                    # no warm batch fits under this bucket: draw more until one does
                     if src is not None:
                         break
                     r = synth.make_batch(args, B=B, seed=70000 + 1000 * rank + t)
