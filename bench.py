@@ -437,12 +437,9 @@ def run_workload(ns, cfg, scaling, B_arg, rank, world, dev, K, W, full):
     nd = ns.distinct_batches
     # every batch goes through the collate-time pipeline (shape bucket + int32 CSR + one pinned blob); the bucket grid is
     # fitted to the shape spread of a sample of batches (what a loader knows after its first pass over the dataset)
-    if cfg == "syn":
-        grid = loader.Bucketer()
-    else:
-        sample = [synth.make_batch(args, B=B, seed=90000 + i) for i in range(48)]
-        grid = loader.Bucketer().fit([(int(s.batch.numel()), int(s.edge_index.shape[1])) for s in sample])
-        del sample
+    sample = [synth.make_batch(args, B=B, seed=90000 + i) for i in range(12 if cfg == "syn" else 48)]
+    grid = loader.Bucketer().fit([(int(s.batch.numel()), int(s.edge_index.shape[1])) for s in sample])
+    del sample
     if graphed is not None:
         graphed.bucket = grid
     host = [loader.prepare(synth.make_batch(args, B=B, seed=1000 * rank + i), bucket=grid) for i in range(nd)]
@@ -561,7 +558,8 @@ def run_workload(ns, cfg, scaling, B_arg, rank, world, dev, K, W, full):
                "fresh_batches": True, "graph_captures_before_timing": cap1, "graph_captures_while_warming_buckets": cap1 - cap0,
                "graph_captures_inside_timed_region": int(capt),
                "distinct_bucketed_shapes": len({(int(b.batch.numel()), int(b.edge_index.shape[1])) for b in timed}),
-               "bucket_grid_step": "1/%d .. 1/%d of the size" % (1 << grid.log2_steps, 1 << (grid.log2_steps - 1)),
+               "bucket_grid": ("one bucket %s fitted to a sample of batches (spread <= 6 %%)" % (grid.fixed,) if grid.fixed else
+                               "steps of 1/%d .. 1/%d of the size" % (1 << grid.log2_steps, 1 << (grid.log2_steps - 1))),
                "pipeline": "loader.prepare (shape bucket + int32 CSR + one pinned blob, collate time, untimed) -> prefetched H2D of "
                            "the blob into a persistent staging buffer -> CUDA-graph replay -> asynchronous D2H copy of the loss, "
                            "read by the host one step later (every step's loss is read inside the timed region)"}

@@ -180,10 +180,21 @@ class Bucketer:
 
     def __init__(self, log2_steps: int = 6):
         self.log2_steps = int(log2_steps)
+        self.fixed = None
 
-    def fit(self, shapes, target: int = 6):
-        """shapes: iterable of (n_nodes, n_edges) of sample batches (collate-time ints)"""
+    def fit(self, shapes, target: int = 6, single_bucket_spread: float = 0.06):
+        """shapes: iterable of (n_nodes, n_edges) of sample batches (collate-time ints).  When the sample's spread is
+        small (max / min - 1 <= single_bucket_spread: large batches of iid graphs) ONE bucket just above the largest
+        sample serves (nearly) every batch - a few percent of slack rows, no recapture; batches beyond it fall back to
+        the grid."""
         shapes = list(shapes)
+        n_lo, n_hi = min(s[0] for s in shapes), max(s[0] for s in shapes)
+        e_lo, e_hi = min(s[1] for s in shapes), max(s[1] for s in shapes)
+        self.fixed = None
+        if n_hi <= (1 + single_bucket_spread) * n_lo and e_hi <= (1 + single_bucket_spread) * max(e_lo, 1):
+            margin = 1 + single_bucket_spread / 4
+            self.fixed = (bucket_size(int(n_hi * margin), 7), bucket_size(int(e_hi * margin), 7))
+            return self
         for k in (6, 5, 4, 3):
             self.log2_steps = k
             if len({self.bucket(n, e) for n, e in shapes}) <= target:
@@ -191,6 +202,8 @@ class Bucketer:
         return self
 
     def bucket(self, n_nodes, n_edges):
+        if self.fixed is not None and n_nodes < self.fixed[0] and n_edges <= self.fixed[1]:
+            return self.fixed
         return bucket_size(n_nodes, self.log2_steps), bucket_size(n_edges, self.log2_steps)
 
     def pad(self, batch: "GraphBatch") -> "GraphBatch":
