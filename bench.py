@@ -43,7 +43,7 @@ UNIT = "graphs/s"
 HEADLINE = "syn"
 EXTRA_CONFIGS = ("molpcba", "code2", "code2-pna")
 # graphs per CPU step: the full batch where a step costs ~1 s of CPU time, a bounded sample otherwise
-CPU_SAMPLE_B = {"molpcba": 512, "code2": 8, "syn": 32, "code2-pna": 8, "nci1": 32}
+CPU_SAMPLE_B = {"molpcba": 512, "code2": 16, "syn": 256, "code2-pna": 16, "nci1": 32}
 
 
 def parse():
