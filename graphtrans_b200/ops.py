@@ -215,6 +215,7 @@ def next_salt() -> int:
 # adjoint ...), which co-reside on an SM with the one-CTA-per-SM persistent GEMM.  Opt-in: whoever enables it must
 # call join_side_streams() after backward() and before reading gradients (GraphedStep and bench.py do).
 _wgrad = {"stream": None, "used": False, "keep": []}
+WGRAD_SIDE_MAX_ELEMS = int(os.environ.get("GT_WGRAD_SIDE_MAX_ELEMS", str(16 << 20)))
 
 
 def enable_wgrad_stream(on=True, device="cuda"):
@@ -245,8 +246,12 @@ class _WgradCtx:
     node's own stream)."""
 
     def __init__(self, on, *tensors):
-        self.on = bool(on)
         self.tensors = [t for t in tensors if t is not None]
+        # Large operands (config 4: [5e5, 512] gradients) make the weight-gradient kernels HBM-bound device-filling
+        # launches of their own: run next to the equally HBM-bound main stream they only thrash (measured: 39.2 ms with,
+        # 38.3 ms without the side stream on config 4; the small configs gain 3-4 % from it) - those stay on the main stream.
+        big = max((t.numel() for t in self.tensors), default=0) > WGRAD_SIDE_MAX_ELEMS
+        self.on = bool(on) and not big
         self.ctx = None
 
     def __enter__(self):
