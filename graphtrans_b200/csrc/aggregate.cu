@@ -7,7 +7,7 @@
 // registers in CSR order (deterministic, no atomics on the feature path).
 #include <stdlib.h>
 
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace gt {
 
@@ -928,6 +928,227 @@ k_agg_bwd3(const T* __restrict__ x, const T* __restrict__ dout, T* __restrict__ 
             for (int w = 0; w < nw; ++w) t += sh_eps[w];
             if (t != 0.f) atomicAdd(d_self, t);
         }
+    }
+}
+
+// Adjoint with the edge-TABLE gradient fused in (bf16, table edge encoder, <= 64 edge types, ld = 128 or 256).
+// The table gradient is the contraction d_table[t, c] = sum over edges e of type t of gm[e, c] with gm[e, :] =
+// norm * dout[dst(e), :] * 1[x[src(e), :] + table[t, :] > 0] - exactly the per-edge vector the adjoint already holds in
+// registers.  k_agg_bwd3 wrote gm ([E, ld] bf16, 1.08 GB per layer at config 4) for a separate OneHot^T . gm GEMM that read
+// it back; here gm never leaves the SM:
+//   worker warps 0..6 : thread = (source node j, 8-channel vector) as in k_agg_bwd3, over a CONTIGUOUS node range per
+//                       block, so the block's out-edges are the contiguous CSR slots [P0, P1): slot p is row (p-P0) % 32
+//                       of staging tile (p-P0) / 32.  A worker stores its 8 gm values (bf16) into the tile as the
+//                       MN-major A operand (k = row, m = channel; 128B swizzle) and its share of the row's one-hot type
+//                       column into the K-major B operand (n = type, k = row), then the node's lane 0 arrives on the
+//                       tile's mbarrier (32 arrivals = 32 rows complete).
+//   warp 7            : one lane issues tcgen05.mma (M = 128 channels, N = 64 types, K = 16 rows; ld / 128 channel groups
+//                       x 2 k-steps per tile) accumulating D[channel, type] in TMEM over all tiles of the block;
+//                       tcgen05.commit hands the (double-buffered) tile back to the workers.
+//   epilogue          : TMEM -> registers -> one fp32 global atomic per (block, type, channel).
+// Rows past the block's last edge are written as zero rows / zero one-hot columns, so a tile is always complete.
+constexpr int BW4_WORKERS = 7 * 32, BW4_THREADS = 8 * 32, BW4_ROWS = 32, BW4_TYPES = 64;
+
+template <int CONV>
+__global__ void __launch_bounds__(BW4_THREADS, 3)
+k_agg_bwd4(const bf16* __restrict__ x, const bf16* __restrict__ dout, bf16* __restrict__ dx, int N, int d, int ld,
+           const int32_t* __restrict__ rp_src, const int32_t* __restrict__ dst_by_src,
+           const int32_t* __restrict__ eid_by_src, EdgeEnc en, const float* __restrict__ self_param,
+           float* __restrict__ d_self, float* __restrict__ d_table, int nodes_per_block) {
+    using namespace tc;
+    constexpr int EK = GT_EDGE_TABLE, KD = 1;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t full_bar[2], empty_bar[2], done_bar;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float sh_eps[8];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int L = ld >> 3;                    // lanes per node: 16 or 32
+    const int nb = BW4_WORKERS / L;           // nodes in flight per block iteration
+    const int groups = ld >> 7;               // 128-channel accumulator groups (1 or 2)
+    const uint32_t a_bytes = (uint32_t)(ld >> 6) * 4096u;           // A tile: ld/64 chunks of [32 rows x 128 B]
+    const uint32_t tile_bytes = a_bytes + 8192u;                    // + B tile: [64 types x 128 B] (k = 0..31 used)
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int n_begin = min(blockIdx.x * nodes_per_block, N), n_end = min(n_begin + nodes_per_block, N);
+    const int P0 = rp_src[n_begin], P1 = rp_src[n_end];
+    const int ntiles = (P1 - P0 + BW4_ROWS - 1) / BW4_ROWS;
+    const uint32_t tmem_cols = groups == 1 ? 64u : 128u;
+
+    if (tid == 0) {
+        for (int b = 0; b < 2; ++b) mbar_init(&full_bar[b], BW4_ROWS), mbar_init(&empty_bar[b], 1);
+        mbar_init(&done_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 7) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    float deps = 0.f;
+
+    if (warp == 7) {
+        if (lane == 0 && ntiles > 0) {   // ===== MMA issuer =====
+            // D[m = channel, n = type] += A[m, k] B[n, k]: A MN-major (a_mn = 1), B K-major, M = 128, N = 64
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | ((uint32_t)(BW4_TYPES >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            for (int t = 0; t < ntiles; ++t) {
+                const int b = t & 1;
+                const uint32_t a_addr = base + (uint32_t)b * tile_bytes, b_addr = a_addr + a_bytes;
+                mbar_wait(&full_bar[b], (uint32_t)(t >> 1) & 1u);
+                tc_fence_after();
+                for (int g = 0; g < groups; ++g) {
+#pragma unroll
+                    for (int ks = 0; ks < BW4_ROWS / 16; ++ks)
+                        umma_f16(tmem + (uint32_t)g * BW4_TYPES, desc_mnmajor(a_addr + (uint32_t)g * 8192u + (uint32_t)ks * 2048u, 4096u),
+                                 desc_kmajor(b_addr + (uint32_t)ks * 32u), idesc, (t > 0 || ks > 0) ? 1u : 0u);
+                }
+                umma_commit(&empty_bar[b]);     // the tile may be rewritten once these MMAs have read it
+            }
+            umma_commit(&done_bar);
+        }
+    } else {                             // ===== workers =====
+        const int tx = tid % L, ty = tid / L;
+        const int c0 = tx * 8;
+        const uint32_t gmask = L == 32 ? 0xffffffffu : (0xffffu << (lane & 16));
+        EdgeVec<EK, KD> ev;
+        ev.load(en, c0, d);
+        float root[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) root[q] = (CONV == GT_CONV_GCN && c0 + q < d) ? self_param[c0 + q] : 0.f;
+        float a_self[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        const float eps1 = (CONV == GT_CONV_GIN) ? 1.f + self_param[0] : 0.f;
+        int t_ok = 1;                     // tiles <= t_ok are known to be writable (the first use of either buffer is free)
+        // one staged row: 8 gm values of this thread's channels + this thread's share of the one-hot type column
+        auto stage_row = [&](int q, const float (&gmv)[8], int ty_e) {
+            const int t = q >> 5;
+            const uint32_t r = (uint32_t)q & 31u;
+            if (t > t_ok) {
+                mbar_wait(&empty_bar[t & 1], (((uint32_t)t >> 1) & 1u) ^ 1u);   // MMAs of tile t - 2 have read the buffer
+                t_ok = t;
+            }
+            const uint32_t a_addr = base + (uint32_t)(t & 1) * tile_bytes, b_addr = a_addr + a_bytes;
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(gmv[0], gmv[1]), h1 = __floats2bfloat162_rn(gmv[2], gmv[3]);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(gmv[4], gmv[5]), h3 = __floats2bfloat162_rn(gmv[6], gmv[7]);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                         ::"r"(a_addr + (uint32_t)(tx >> 3) * 4096u + r * 128u + ((((uint32_t)tx & 7u) ^ (r & 7u)) << 4)),
+                           "r"(*reinterpret_cast<uint32_t*>(&h0)), "r"(*reinterpret_cast<uint32_t*>(&h1)),
+                           "r"(*reinterpret_cast<uint32_t*>(&h2)), "r"(*reinterpret_cast<uint32_t*>(&h3)) : "memory");
+            for (int n = tx; n < BW4_TYPES; n += L) {
+                const unsigned short one = (n == ty_e) ? (unsigned short)0x3F80 : (unsigned short)0;
+                asm volatile("st.shared.u16 [%0], %1;"
+                             ::"r"(b_addr + (uint32_t)n * 128u + ((((r >> 3) ^ ((uint32_t)n & 7u))) << 4) + (r & 7u) * 2u), "h"(one) : "memory");
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp(gmask);
+            if (tx == 0) mbar_arrive(&full_bar[t & 1]);
+        };
+        const int stride = nb;
+        int j = n_begin + ty;
+        int b0 = 0, e0 = 0, b1 = 0, e1 = 0;
+        const bool active = ty < nb;      // L = 16: 14 node slots, no idle threads; kept for safety
+        if (active && j < n_end) b0 = rp_src[j], e0 = rp_src[j + 1];
+        if (active && j + stride < n_end) b1 = rp_src[j + stride], e1 = rp_src[j + stride + 1];
+        SlotBatch<KD> cur;
+        if (active && j < n_end) load_slots<CONV, EK, KD>(cur, en, dst_by_src, eid_by_src, rp_src, b0, e0, j, 1.f);
+        for (; active && j < n_end; j += stride) {
+            float xj[8], gj[8], g[AGG_U][8];
+            ld8(x + (int64_t)j * ld + c0, xj);
+            ld8(dout + (int64_t)j * ld + c0, gj);
+#pragma unroll
+            for (int u = 0; u < AGG_U; ++u) ld8(dout + (int64_t)cur.other[u] * ld + c0, g[u]);
+            SlotBatch<KD> nxt;
+            const int jnext = j + stride;
+            if (jnext < n_end) load_slots<CONV, EK, KD>(nxt, en, dst_by_src, eid_by_src, rp_src, b1, e1, jnext, 1.f);
+            int b2 = 0, e2 = 0;
+            if (jnext + stride < n_end) b2 = rp_src[jnext + stride], e2 = rp_src[jnext + stride + 1];
+            const float inv_deg_j = CONV == GT_CONV_GCN ? 1.f / (float)(e0 - b0 + 1) : 1.f;
+            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            auto consume = [&](const SlotBatch<KD>& sb, int pbase) {
+#pragma unroll
+                for (int u = 0; u < AGG_U; ++u) {
+                    float ee[8], gmv[8];
+                    ev.embed(en, sb.a[u], sb.ty[u], c0, ld, ee);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float gm = (xj[q] + ee[q] > 0.f) ? sb.nrm[u] * g[u][q] : 0.f;
+                        gmv[q] = gm;
+                        acc[q] += gm;
+                    }
+                    if (pbase + u < e0) stage_row(pbase + u - P0, gmv, sb.ty[u]);     // node-uniform condition
+                }
+            };
+            consume(cur, b0);
+            for (int p0 = b0 + AGG_U; p0 < e0; p0 += AGG_U) {
+                SlotBatch<KD> sb;
+                load_slots<CONV, EK, KD>(sb, en, dst_by_src, eid_by_src, rp_src, p0, e0, j, 1.f);
+#pragma unroll
+                for (int u = 0; u < AGG_U; ++u) ld8(dout + (int64_t)sb.other[u] * ld + c0, g[u]);
+                consume(sb, p0);
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                if (CONV == GT_CONV_GCN) {
+                    const float gs = (xj[q] + root[q] > 0.f) ? gj[q] * inv_deg_j : 0.f;
+                    acc[q] += gs;
+                    a_self[q] += gs;
+                } else {
+                    acc[q] = fmaf(eps1, gj[q], acc[q]);
+                    deps = fmaf(xj[q], gj[q], deps);
+                }
+            }
+            st8(dx + (int64_t)j * ld + c0, acc);
+            cur = nxt;
+            b0 = b1, e0 = e1, b1 = b2, e1 = e2;
+        }
+        // rows between the block's last edge and the end of its last tile: zero rows, zero one-hot columns
+        if (active) {
+            const float zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            for (int q = P1 - P0 + ty; q < ntiles * BW4_ROWS; q += nb) stage_row(q, zero, -1);
+        }
+        if (CONV == GT_CONV_GCN) {          // d root: one global atomic per (thread, channel)
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (c0 + q < d && a_self[q] != 0.f) atomicAdd(&d_self[c0 + q], a_self[q]);
+        }
+        // ---- table-gradient epilogue: warps 0..3 own TMEM lanes 32 w .. 32 w + 31 = channels of every group
+        if (ntiles > 0 && warp < 4) {
+            mbar_wait(&done_bar, 0);
+            tc_fence_after();
+            for (int g = 0; g < groups; ++g) {
+                const int ch = g * 128 + warp * 32 + lane;
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    uint32_t rr[32];
+                    tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(g * BW4_TYPES + hf * 32), rr);
+                    if (ch < d) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const int ty_e = hf * 32 + i;
+                            const float v = __uint_as_float(rr[i]);
+                            if (ty_e < en.ntypes && v != 0.f) atomicAdd(d_table + (int64_t)ty_e * ld + ch, v);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+        }
+    }
+    if (CONV == GT_CONV_GIN) {   // d eps: one global atomic per block
+        deps = warp_sum(deps);
+        if (lane == 0) sh_eps[warp] = deps;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (CONV == GT_CONV_GIN && tid == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 7; ++w) t += sh_eps[w];
+        if (t != 0.f) atomicAdd(d_self, t);
+    }
+    if (warp == 7) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols) : "memory");
     }
 }
 

@@ -72,7 +72,7 @@ k_mha_tc_fwd(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p) {
         int lo = 0, n = 0;
         if (p.tile_bounds) {
             const int2 tb = p.tile_bounds[blockIdx.x];
-            lo = tb.x, n = tb.y;
+            lo = tb.x, n = (tb.y + BKV - 1) / BKV;
         } else if (q0 < p.tok_off[p.B]) {
             const int n_tok = p.tok_off[p.B];
             const int g0 = p.tok_graph[q0];
@@ -325,7 +325,8 @@ static cudaError_t launch_fwd(const CUtensorMap& map, const AttnParams& p, cudaS
 
 // per-step attention metadata (once per batch instead of three dependent loads in every CTA of every layer):
 // row_bounds[row] = [lo, hi) token rows of the row's graph (0,0 for tail rows); tile_bounds[t] = (first row, number
-// of 128-row tiles) of the contiguous row range that interacts with rows [128 t, 128 t + 128)
+// of rows) of the contiguous row range that interacts with rows [128 t, 128 t + 128): the forward streams it in
+// ceil(n / 128) key tiles, the backward in ceil(n / 64) tiles
 __global__ void k_mha_meta(const int32_t* __restrict__ tok_graph, const int32_t* __restrict__ tok_off, int64_t n_rows, int B,
                            int2* __restrict__ row_bounds, int2* __restrict__ tile_bounds) {
     const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -340,7 +341,7 @@ __global__ void k_mha_meta(const int32_t* __restrict__ tok_graph, const int32_t*
         if (row < n_tok) {
             const int g1 = tok_graph[min((int64_t)row + 127, (int64_t)n_tok - 1)];
             tb.x = rb.x;
-            tb.y = (tok_off[g1 + 1] - rb.x + 127) / 128;
+            tb.y = tok_off[g1 + 1] - rb.x;
         }
         tile_bounds[row >> 7] = tb;
     }
@@ -460,10 +461,10 @@ k_mha_tc_bwd(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant_
             const int g0 = p.tok_graph[t0];
             const int g1 = p.tok_graph[min(t0 + 127, n_tok - 1)];
             lo = p.tok_off[g0];
-            n = (p.tok_off[g1 + 1] - lo + 127) / 128;
+            n = p.tok_off[g1 + 1] - lo;
         }
         st_lo_s = lo;
-        nst_s = 2 * n;      // 64-row streamed tiles
+        nst_s = (n + 63) / 64;      // 64-row streamed tiles covering the n interacting rows
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(TMEM_COLS) : "memory");

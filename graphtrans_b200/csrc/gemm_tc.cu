@@ -202,12 +202,35 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUt
                     // (thread, column) serialises on its destination registers: 2.6 us per slab, measured with
                     // tools/gemm_trace.py - the whole kernel was epilogue bound.)
                     const bool use_bias = first && p.bias;
+                    // bf16 residual operand: the [32 rows x 128 B] box of this slab is fetched with coalesced 16-byte loads
+                    // (8 lanes per row), parked in the staging slab in the store's swizzled layout and picked up below by
+                    // the thread that owns the row (in place: a chunk is read by its owner right before it is rewritten)
+                    const bool use_res = OUT_BF16 && first && p.resid != nullptr;
+                    uint4 rv[8];
+                    if (use_res) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int row = i * 4 + (lane >> 3), m = m0 + q * 32 + row, n = n_slab + (lane & 7) * 8;
+                            rv[i] = make_uint4(0u, 0u, 0u, 0u);
+                            if (m < p.M && n + 8 <= p.N)
+                                rv[i] = __ldg(reinterpret_cast<const uint4*>((const bf16*)p.resid + (int64_t)m * p.ldr + n));
+                        }
+                    }
                     if (use_bias) {
 #pragma unroll
                         for (int i = lane; i < SLAB_COLS; i += 32) bias_sm[i] = (n_slab + i < p.N) ? __ldg(p.bias + n_slab + i) : 0.f;
                     }
                     if (lane == 0) tma_wait_group_read<1>();   // the store that last used this buffer has read it
                     __syncwarp();
+                    if (use_res) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const uint32_t row = (uint32_t)(i * 4 + (lane >> 3)), ch = (uint32_t)lane & 7u;
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sb + row * 128u + ((ch ^ (row & 7u)) << 4)),
+                                         "r"(rv[i].x), "r"(rv[i].y), "r"(rv[i].z), "r"(rv[i].w) : "memory");
+                        }
+                        __syncwarp();
+                    }
 #pragma unroll
                     for (int c32 = 0; c32 < SLAB_COLS; c32 += 32) {
                       uint32_t r32[32];
@@ -223,6 +246,21 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUt
                             for (int i = 0; i < 16; i += 4) {
                                 const float4 b4 = *reinterpret_cast<const float4*>(bias_sm + c + i);
                                 v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+                            }
+                        }
+                        if (use_res) {
+#pragma unroll
+                            for (int i = 0; i < 16; i += 8) {
+                                const uint32_t ch = (uint32_t)(c + i) >> 3;
+                                uint32_t w0, w1, w2, w3;
+                                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                                             : "r"(sb + (uint32_t)lane * 128u + ((ch ^ rsw) << 4)) : "memory");
+                                const uint32_t w[4] = {w0, w1, w2, w3};
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    v[i + 2 * k] += __uint_as_float(w[k] << 16);
+                                    v[i + 2 * k + 1] += __uint_as_float(w[k] & 0xffff0000u);
+                                }
                             }
                         }
                         if (relu) {
@@ -474,10 +512,13 @@ int gemm_tc_launch(int dt, const void* A, int a_mn, int64_t lda, const void* B, 
     const int64_t ncols = n_fill > N ? n_fill : N;
     // output tile width: the fewest tiles of <= 256 columns, rounded to the UMMA N granularity of 16 (wide tiles keep
     // the operand re-read factor, i.e. L2 traffic, low; an MN-major B tile is loaded as ceil(BN/64) TMA boxes)
-    // The TMA-store epilogue (rows 16-byte aligned, no residual operand) moves whole [32 x 128 B] boxes, so there BN
+    // The TMA-store epilogue (rows 16-byte aligned, no fp32 residual operand) moves whole [32 x 128 B] boxes, so there BN
     // is a multiple of the slab width (64 bf16 / 32 fp32 columns); padded columns only cost MMA issue slots.
     const int csz0 = out_bf16 ? 2 : 4;
-    const bool tma_ok = ((uintptr_t)C % 16 == 0) && ((ldc * csz0) % 16 == 0) && !resid;
+    // a bf16 residual operand with 16-byte aligned rows rides in the TMA-store epilogue too (staged through the slab)
+    const bool res_fast = resid && out_bf16 && !(flags & GT_EPI_RESID_F32) && !accum && ((uintptr_t)resid % 16 == 0) &&
+                          ((ldr * 2) % 16 == 0) && N % 8 == 0;
+    const bool tma_ok = ((uintptr_t)C % 16 == 0) && ((ldc * csz0) % 16 == 0) && (!resid || res_fast);
     const int gran = tma_ok ? (out_bf16 ? 64 : 32) : 16;
     const int64_t nt = (ncols + 255) / 256;
     const int BN = (int)(((ncols + nt - 1) / nt + gran - 1) / gran * gran);
@@ -526,7 +567,7 @@ int gemm_tc_launch(int dt, const void* A, int a_mn, int64_t lda, const void* B, 
     ok = ok && (b_mn ? make_map(&mb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, 64)
                      : make_map(&mb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64, (uint32_t)BN));
     if (!ok) { set_error("cuTensorMapEncodeTiled failed or unavailable"); return -2; }
-    // output through TMA when rows are 16-byte aligned and there is no residual operand; [32 x 128 B] boxes per warp.
+    // output through TMA when rows are 16-byte aligned (residual operand: bf16 only); [32 x 128 B] boxes per warp.
     // The map's column extent is max(N, n_fill): columns N..n_fill-1 receive the (zero) accumulators of B's OOB rows.
     CUtensorMap mc = ma;
     p.tma_store = tma_ok;

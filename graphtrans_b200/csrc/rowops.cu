@@ -1379,11 +1379,22 @@ extern "C" int gt_layernorm_bwd(int dt, const void* dy, const void* presum, cons
     const int grid = blocks_for((M + br - 1) / br, 8, 3 * kNumSMs);
     const bool wide = env_int("GT_LN_WIDE", 1) && dt == GT_BF16 && d % 8 == 0 && d > 128 && ((uintptr_t)dy % 16 == 0) &&
                       ((uintptr_t)presum % 16 == 0) && ((uintptr_t)dx % 16 == 0) && (!dx_drop || (uintptr_t)dx_drop % 16 == 0);
-#define LNB(TT, MAXV, VW, RR, G) k_layernorm_bwd<TT, MAXV, VW, RR><<<G, 256, 2 * d * sizeof(float), ST>>>((const TT*)dy, (const TT*)presum, mean_rstd, out_rows, M, d, gamma, (TT*)dx, dgamma, dbeta, dcls, (TT*)dx_drop, drop_p, rng_state, salt)
+    // grid = exactly the blocks that are resident at once (the kernels loop grid-stride; a partial second wave costs a
+    // full block duration: 444 blocks on 2 x 148 slots ran 1.5 waves)
+#define LNB(TT, MAXV, VW, RR, G) do { \
+        static int occ = 0; \
+        if (!occ) { \
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_layernorm_bwd<TT, MAXV, VW, RR>, 256, 2 * d * sizeof(float)); \
+            if (occ < 1) occ = 1; \
+        } \
+        int g_ = (G); \
+        if (g_ > occ * kNumSMs) g_ = occ * kNumSMs; \
+        k_layernorm_bwd<TT, MAXV, VW, RR><<<g_, 256, 2 * d * sizeof(float), ST>>>((const TT*)dy, (const TT*)presum, mean_rstd, out_rows, M, d, gamma, (TT*)dx, dgamma, dbeta, dcls, (TT*)dx_drop, drop_p, rng_state, salt); \
+    } while (0)
     if (wide) {      // 16-byte accesses, four (d <= 256) / two (d <= 512) / one row(s) of a warp in flight
-        if (d <= 256) LNB(bf16, 1, 8, 4, blocks_for((M + 3) / 4, 8, 3 * kNumSMs));
-        else if (d <= 512) LNB(bf16, 2, 8, 2, blocks_for((M + 1) / 2, 8, 3 * kNumSMs));
-        else LNB(bf16, 4, 8, 1, blocks_for(M, 8, 3 * kNumSMs));
+        if (d <= 256) LNB(bf16, 1, 8, 4, blocks_for((M + 3) / 4, 8, 4 * kNumSMs));
+        else if (d <= 512) LNB(bf16, 2, 8, 2, blocks_for((M + 1) / 2, 8, 4 * kNumSMs));
+        else LNB(bf16, 4, 8, 1, blocks_for(M, 8, 4 * kNumSMs));
     } else {
         GT_DISPATCH_DT(dt, {
             if (d <= 128) LNB(T, 1, 4, 4, grid);

@@ -60,7 +60,7 @@ class TransformerNodeEncoder(nn.Module):
         at = layer.self_attn
         a = ops.linear(a, at.out_proj.weight, at.out_proj.bias)
         x1 = ops.layer_norm(a, layer.norm1, resid=x, drop_p=drop)                           # norm1(x + drop(a))
-        f = ops.linear(x1, layer.linear1.weight, layer.linear1.bias, relu=True, drop_p=drop)
+        f, x1 = ops.linear(x1, layer.linear1.weight, layer.linear1.bias, relu=True, drop_p=drop, passthrough=True)
         f = ops.linear(f, layer.linear2.weight, layer.linear2.bias)
         return ops.layer_norm(f, layer.norm2, resid=x1, drop_p=drop)                         # norm2(x + drop(f))
 
@@ -71,8 +71,8 @@ class TransformerNodeEncoder(nn.Module):
         layer = self.transformer.layers[-1]
         at = layer.self_attn
         d = self.d_model
+        kv, x = ops.linear(x, at.in_proj_weight, at.in_proj_bias, w_row_off=d, n_out=2 * d, passthrough=True)   # [n_rows, 2d]
         xq = ops.gather_rows(x, plan.cls_rows, n_rows=plan.B)                                 # [B, d] residual stream
-        kv = ops.linear(x, at.in_proj_weight, at.in_proj_bias, w_row_off=d, n_out=2 * d)     # [n_rows, 2d]
         q = ops.linear(xq, at.in_proj_weight, at.in_proj_bias, w_row_off=0, n_out=d)         # [B, d]
         a = ops.mha_pooled_query(q, kv, plan, self.nhead, drop_p=drop)
         return self._ffn_block(layer, a, xq, drop)
@@ -83,11 +83,13 @@ class TransformerNodeEncoder(nn.Module):
         layers = list(self.transformer.layers)
         for layer in (layers[:-1] if skip_last else layers):
             at = layer.self_attn
-            qkv = ops.linear(x, at.in_proj_weight, at.in_proj_bias)
+            # passthrough: the residual stream is handed on by the Linear that also reads it, so the residual path's
+            # gradient is added in that Linear's dX epilogue (no autograd accumulation kernel per sublayer)
+            qkv, x = ops.linear(x, at.in_proj_weight, at.in_proj_bias, passthrough=True)
             a = ops.mha_packed(qkv, plan, self.nhead, key_start, drop_p=drop)
             a = ops.linear(a, at.out_proj.weight, at.out_proj.bias)
             x1 = ops.layer_norm(a, layer.norm1, resid=x, drop_p=drop)                       # norm1(x + drop(a))
-            f = ops.linear(x1, layer.linear1.weight, layer.linear1.bias, relu=True, drop_p=drop)
+            f, x1 = ops.linear(x1, layer.linear1.weight, layer.linear1.bias, relu=True, drop_p=drop, passthrough=True)
             f = ops.linear(f, layer.linear2.weight, layer.linear2.bias)
             x = ops.layer_norm(f, layer.norm2, resid=x1, drop_p=drop)                       # norm2(x + drop(f))
         return x

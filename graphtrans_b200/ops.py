@@ -814,7 +814,8 @@ class _LinearFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias, relu, out_f32, resid, off, K, drop_p, salt, want_stats=False, m_valid=None,
-                row_off=0, n_out=None):
+                row_off=0, n_out=None, passthrough=False):
+        x_in = x
         x = x.contiguous()
         M, ld_in = x.shape
         N, Kw = weight.shape
@@ -862,15 +863,24 @@ class _LinearFn(torch.autograd.Function):
         # whose column sums vanish identically, i.e. the bias gradient of this Linear is exactly zero - no gt_colsum launch.
         # The consumer opts in (a frozen BN, a standalone conv or any other reader keeps the real column sum).
         ctx.bias_grad_zero = False
+        ctx.passthrough = bool(passthrough)
         if want_stats:
             ctx.mark_non_differentiable(stats)
             return y, stats
+        if passthrough:
+            # second output = the input itself, for the caller's residual connection: its gradient comes back HERE and is
+            # added in the dX GEMM's epilogue (fp32 accumulator + g_pass, one rounding) instead of by an autograd
+            # accumulation kernel over [M, ld_in]
+            return y, x_in.view_as(x_in)
         return y
 
     @staticmethod
     def backward(ctx, gy, _gstats=None):
         x, w, y = ctx.saved_tensors
         M, N, K, Kw, off, ld_in, ldw, ld_out, relu, has_bias, has_resid = ctx.meta
+        g_pass = _gstats if ctx.passthrough else None
+        if gy is None:      # only the pass-through output was used
+            gy = torch.zeros(M, ld_out, dtype=y.dtype if y is not None else x.dtype, device=x.device)
         gy = gy.contiguous()
         g_res = gy if has_resid else None
         if gy.dtype != x.dtype:  # fp32 head logits: bring the gradient to the operand dtype
@@ -888,8 +898,12 @@ class _LinearFn(torch.autograd.Function):
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
             gx = torch.empty(M, ld_in, dtype=x.dtype, device=x.device)
+            if g_pass is not None:
+                g_pass = g_pass.contiguous()
+                if g_pass.dtype != x.dtype or g_pass.shape != gx.shape:
+                    raise RuntimeError("linear: pass-through gradient must match the input")
             # dX[m,k] = sum_n dY[m,n] W[n,k]: B operand = W read "MN-major" (k contiguous)
-            if x.dtype == torch.bfloat16 and N >= 2048 and M * K <= 256 * 512:
+            if g_pass is None and x.dtype == torch.bfloat16 and N >= 2048 and M * K <= 256 * 512:
                 # a handful of output tiles over a very long contraction (the 5002-class Code2 heads): split-K into a
                 # zeroed fp32 scratch (one CTA would otherwise walk ~80 k-blocks alone), then one cast
                 g32 = zeros_small(M * ld_in, torch.float32, x.device).view(M, ld_in)
@@ -898,7 +912,7 @@ class _LinearFn(torch.autograd.Function):
                 call("gt_cast_pad", GT_F32, ptr(g32), M, ld_in, ld_in, dt_of(gx), ptr(gx), M, ld_in, ld_in)
             else:
                 _gemm_raw(dt_of(x), gy.data_ptr(), 0, ld_out, wptr, 1, ldw, gx.data_ptr(), ld_in, M, K, N, ld_in, None,
-                          None, 0, 0)
+                          g_pass, ld_in, 0)
         weight, bias = ctx.params
         # parameter gradients accumulated in place need no ordering with the rest of the backward: side stream
         side_ok = _main_grad(weight) is not None and (not has_bias or _main_grad(bias) is not None)
@@ -914,11 +928,11 @@ class _LinearFn(torch.autograd.Function):
                 if not ctx.bias_grad_zero:
                     call("gt_colsum", dt_of(gy), ptr(gy), M, N, ld_out, tgt.data_ptr() + ctx.row_off * 4)
                 _grad_done(bias)
-        return gx, gw, gb, None, None, g_res, None, None, None, None, None, None, None, None
+        return gx, gw, gb, None, None, g_res, None, None, None, None, None, None, None, None, None
 
 
 def linear(x, weight, bias=None, relu=False, out_f32=False, resid=None, drop_p=0.0, w_col_off=0, K=None, col_stats=False,
-           m_valid=None, w_row_off=0, n_out=None):
+           m_valid=None, w_row_off=0, n_out=None, passthrough=False):
     """drop(act(x W[:, off:off+K]^T + b)) [+ resid]; drop(relu(.)) runs in the GEMM epilogue (the FFN pattern of
     nn.TransformerEncoderLayer); dropout without ReLU / together with resid is not a reference pattern.
     col_stats=True: the output carries its BatchNorm column statistics (taken in the GEMM epilogue), which
@@ -928,6 +942,13 @@ def linear(x, weight, bias=None, relu=False, out_f32=False, resid=None, drop_p=0
         y, stats = _LinearFn.apply(x, weight, bias, relu, out_f32, resid, w_col_off, K, 0.0, 0, True, m_valid)
         y._gt_colstats = stats
         return y
+    if passthrough:
+        # -> (y, x'): x' is x for the residual connection of the caller, routed through this op so that the gradient of
+        # the residual path joins dX inside the GEMM epilogue
+        if (drop_p and not fused) or not x.requires_grad:
+            return linear(x, weight, bias, relu, out_f32, resid, drop_p, w_col_off, K, False, m_valid, w_row_off, n_out), x
+        return _LinearFn.apply(x, weight, bias, relu, out_f32, resid, w_col_off, K, float(drop_p) if fused else 0.0,
+                               next_salt() if fused else 0, False, None, w_row_off, n_out, True)
     y = _LinearFn.apply(x, weight, bias, relu, out_f32, resid, w_col_off, K, float(drop_p) if fused else 0.0,
                         next_salt() if fused else 0, False, None, w_row_off, n_out)
     return dropout(y, drop_p) if (drop_p and not fused) else y

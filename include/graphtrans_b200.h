@@ -291,7 +291,7 @@ int gt_pad_batch_bwd(int dt, const void* dpadded, const int32_t* node_off, const
  * impl: 0 auto, 1 CUDA-core, 2 tcgen05. */
 /* optional per-batch metadata for the tcgen05 kernels (computed once per step, reused by every layer and head):
  * row_bounds int32 [n_rows][2] = key-row range [lo, hi) of every token row; tile_bounds int32 [ceil(n_rows/128)][2]
- * = (first row, number of 128-row tiles) of the row range interacting with each 128-row tile.  NULL = derive in-kernel. */
+ * = (first row, number of rows) of the row range interacting with each 128-row tile.  NULL = derive in-kernel. */
 int gt_mha_meta(const int32_t* tok_graph, const int32_t* tok_off, int64_t n_rows, int64_t B,
                 int32_t* row_bounds, int32_t* tile_bounds, void* stream);
 int gt_mha_fwd(int dt, const void* qkv, const int32_t* tok_graph, const int32_t* tok_off,
