@@ -52,6 +52,7 @@ SIGNATURES = {
     "gt_gemm_stats": [I, P, I, L, P, I, L, P, L, L, L, L, L, P, P, L, I, F, P, U64, I, P, P, P],
     "gt_split3": [P, L, L, L, P, L, P],
     "gt_relu_bwd": [I, P, P, L, P, F, P],
+    "gt_relu_bwd_colsum": [I, P, P, L, L, L, P, F, P, P],
     "gt_colsum": [I, P, L, L, L, P, P],
     "gt_cast_multi": [P, I32, L, P],
     "gt_add_blocks": [P, I32, I32, P, P, P, P, P, P, P],

@@ -7,6 +7,8 @@
 // registers in CSR order (deterministic, no atomics on the feature path).
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "tc_common.cuh"
 
 namespace gt {
@@ -939,15 +941,47 @@ k_agg_bwd3(const T* __restrict__ x, const T* __restrict__ dout, T* __restrict__ 
 //   worker warps 0..6 : thread = (source node j, 8-channel vector) as in k_agg_bwd3, over a CONTIGUOUS node range per
 //                       block, so the block's out-edges are the contiguous CSR slots [P0, P1): slot p is row (p-P0) % 32
 //                       of staging tile (p-P0) / 32.  A worker stores its 8 gm values (bf16) into the tile as the
-//                       MN-major A operand (k = row, m = channel; 128B swizzle) and its share of the row's one-hot type
-//                       column into the K-major B operand (n = type, k = row), then the node's lane 0 arrives on the
-//                       tile's mbarrier (32 arrivals = 32 rows complete).
+//                       MN-major A operand (k = row, m = channel; 128B swizzle), eight lanes store the row's one-hot type
+//                       vector into the MN-major B operand (k = row, n = type), then the node's lane 0 arrives on the
+//                       tile's mbarrier once per row (32 arrivals = 32 rows complete).
 //   warp 7            : one lane issues tcgen05.mma (M = 128 channels, N = 64 types, K = 16 rows; ld / 128 channel groups
 //                       x 2 k-steps per tile) accumulating D[channel, type] in TMEM over all tiles of the block;
-//                       tcgen05.commit hands the (double-buffered) tile back to the workers.
+//                       the completion of a tile's MMAs (tcgen05.commit) hands the tile (ring of three) back to the workers.
 //   epilogue          : TMEM -> registers -> one fp32 global atomic per (block, type, channel).
 // Rows past the block's last edge are written as zero rows / zero one-hot columns, so a tile is always complete.
-constexpr int BW4_WORKERS = 7 * 32, BW4_THREADS = 8 * 32, BW4_ROWS = 32, BW4_TYPES = 64;
+constexpr int BW4_WORKERS = 7 * 32, BW4_THREADS = 8 * 32, BW4_ROWS = 32, BW4_TYPES = 64, BW4_NBUF = 3;
+
+__device__ __forceinline__ bool bw4_try(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(tc::smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// mbarrier wait that turns a protocol error into a launch failure (message + trap) instead of a hung GPU
+__device__ __forceinline__ void bw4_wait(uint64_t* bar, uint32_t parity, int tag, int t, int ntiles) {
+    const uint32_t addr = tc::smem_u32(bar);
+    uint32_t ok = 0;
+    for (uint32_t spin = 0; !ok; ++spin) {
+        asm volatile(
+            "{\n.reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (!ok) __nanosleep(64);
+        if (!ok && spin > (1u << 23)) {
+            printf("k_agg_bwd4: stuck wait tag=%d tile=%d/%d block=%d thread=%d parity=%u\n", tag, t, ntiles, (int)blockIdx.x,
+                   (int)threadIdx.x, parity);
+            __trap();
+        }
+    }
+}
 
 template <int CONV>
 __global__ void __launch_bounds__(BW4_THREADS, 3)
@@ -958,15 +992,16 @@ k_agg_bwd4(const bf16* __restrict__ x, const bf16* __restrict__ dout, bf16* __re
     using namespace tc;
     constexpr int EK = GT_EDGE_TABLE, KD = 1;
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t full_bar[2], empty_bar[2], done_bar;
+    __shared__ uint64_t full_bar[BW4_NBUF], mma_bar;
     __shared__ uint32_t tmem_base_s;
+    __shared__ int tiles_done;            // tiles whose MMAs have completed (monotonic; published by the MMA issuer)
     __shared__ float sh_eps[8];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int L = ld >> 3;                    // lanes per node: 16 or 32
     const int nb = BW4_WORKERS / L;           // nodes in flight per block iteration
     const int groups = ld >> 7;               // 128-channel accumulator groups (1 or 2)
     const uint32_t a_bytes = (uint32_t)(ld >> 6) * 4096u;           // A tile: ld/64 chunks of [32 rows x 128 B]
-    const uint32_t tile_bytes = a_bytes + 8192u;                    // + B tile: [64 types x 128 B] (k = 0..31 used)
+    const uint32_t tile_bytes = a_bytes + 4096u;                    // + B tile: [32 rows x 64 types] one-hot, MN-major
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int n_begin = min(blockIdx.x * nodes_per_block, N), n_end = min(n_begin + nodes_per_block, N);
     const int P0 = rp_src[n_begin], P1 = rp_src[n_end];
@@ -974,8 +1009,9 @@ k_agg_bwd4(const bf16* __restrict__ x, const bf16* __restrict__ dout, bf16* __re
     const uint32_t tmem_cols = groups == 1 ? 64u : 128u;
 
     if (tid == 0) {
-        for (int b = 0; b < 2; ++b) mbar_init(&full_bar[b], BW4_ROWS), mbar_init(&empty_bar[b], 1);
-        mbar_init(&done_bar, 1);
+        for (int b = 0; b < BW4_NBUF; ++b) mbar_init(&full_bar[b], BW4_ROWS);
+        mbar_init(&mma_bar, 1);
+        tiles_done = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -991,22 +1027,45 @@ k_agg_bwd4(const bf16* __restrict__ x, const bf16* __restrict__ dout, bf16* __re
 
     if (warp == 7) {
         if (lane == 0 && ntiles > 0) {   // ===== MMA issuer =====
-            // D[m = channel, n = type] += A[m, k] B[n, k]: A MN-major (a_mn = 1), B K-major, M = 128, N = 64
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | ((uint32_t)(BW4_TYPES >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            // D[m = channel, n = type] += A[m, k] B[n, k]: both operands MN-major (rows = k), M = 128, N = 64
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(BW4_TYPES >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            // Progress is published as a monotonic tile count, not as an mbarrier phase: a worker whose consecutive rows
+            // lie many tiles apart (a node with hundreds of out-edges in between, e.g. the self loops of a shape-bucket
+            // slack node) would alias a parity wait on a barrier that has moved on by an even number of phases.  At most
+            // one commit is outstanding, so this thread itself never lags mma_bar by more than one phase.
+            int pub = 0;                  // tiles published (= MMAs complete, buffer reusable)
+            auto publish = [&]() {
+                ++pub;
+                asm volatile("st.release.cta.shared::cta.s32 [%0], %1;" ::"r"(smem_u32(&tiles_done)), "r"(pub) : "memory");
+            };
             for (int t = 0; t < ntiles; ++t) {
-                const int b = t & 1;
+                const int b = t % BW4_NBUF;
                 const uint32_t a_addr = base + (uint32_t)b * tile_bytes, b_addr = a_addr + a_bytes;
-                mbar_wait(&full_bar[b], (uint32_t)(t >> 1) & 1u);
+                // wait for tile t; the previous tile is handed back as soon as its MMAs are seen complete
+                for (uint32_t spin = 0;; ++spin) {
+                    if (pub < t && bw4_try(&mma_bar, (uint32_t)pub & 1u)) publish();
+                    if (bw4_try(&full_bar[b], (uint32_t)(t / BW4_NBUF) & 1u)) break;
+                    __nanosleep(128);     // a spinning issuer takes issue slots from the workers of three resident blocks
+                    if (spin > (1u << 23)) {
+                        printf("k_agg_bwd4: tile %d/%d of block %d never filled\n", t, ntiles, (int)blockIdx.x);
+                        __trap();
+                    }
+                }
+                if (pub < t) {
+                    bw4_wait(&mma_bar, (uint32_t)pub & 1u, 3, t, ntiles);
+                    publish();
+                }
                 tc_fence_after();
                 for (int g = 0; g < groups; ++g) {
 #pragma unroll
                     for (int ks = 0; ks < BW4_ROWS / 16; ++ks)
                         umma_f16(tmem + (uint32_t)g * BW4_TYPES, desc_mnmajor(a_addr + (uint32_t)g * 8192u + (uint32_t)ks * 2048u, 4096u),
-                                 desc_kmajor(b_addr + (uint32_t)ks * 32u), idesc, (t > 0 || ks > 0) ? 1u : 0u);
+                                 desc_mnmajor(b_addr + (uint32_t)ks * 2048u, 4096u), idesc, (t > 0 || ks > 0) ? 1u : 0u);
                 }
-                umma_commit(&empty_bar[b]);     // the tile may be rewritten once these MMAs have read it
+                umma_commit(&mma_bar);
             }
-            umma_commit(&done_bar);
+            bw4_wait(&mma_bar, (uint32_t)pub & 1u, 3, ntiles, ntiles);
+            publish();
         }
     } else {                             // ===== workers =====
         const int tx = tid % L, ty = tid / L;
@@ -1019,30 +1078,50 @@ k_agg_bwd4(const bf16* __restrict__ x, const bf16* __restrict__ dout, bf16* __re
         for (int q = 0; q < 8; ++q) root[q] = (CONV == GT_CONV_GCN && c0 + q < d) ? self_param[c0 + q] : 0.f;
         float a_self[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         const float eps1 = (CONV == GT_CONV_GIN) ? 1.f + self_param[0] : 0.f;
-        int t_ok = 1;                     // tiles <= t_ok are known to be writable (the first use of either buffer is free)
-        // one staged row: 8 gm values of this thread's channels + this thread's share of the one-hot type column
-        auto stage_row = [&](int q, const float (&gmv)[8], int ty_e) {
+        int t_ok = BW4_NBUF - 1;          // tiles <= t_ok are known to be writable (the first use of a buffer is free)
+        // one staged row: 8 gm values of this thread's channels into the A tile; lanes 0..7 of the node write the row's
+        // one-hot type vector (64 types = 128 B) into the B tile
+        auto write_row = [&](int q, const float (&gmv)[8], int ty_e) {
             const int t = q >> 5;
             const uint32_t r = (uint32_t)q & 31u;
-            if (t > t_ok) {
-                mbar_wait(&empty_bar[t & 1], (((uint32_t)t >> 1) & 1u) ^ 1u);   // MMAs of tile t - 2 have read the buffer
-                t_ok = t;
+            if (t > t_ok) {               // MMAs of tile t - NBUF must have read the buffer
+                int done = 0;
+                for (uint32_t spin = 0;; ++spin) {
+                    asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(done) : "r"(smem_u32(&tiles_done)) : "memory");
+                    if (done >= t - (BW4_NBUF - 1)) break;
+                    __nanosleep(64);
+                    if (spin > (1u << 24)) __trap();
+                }
+                t_ok = done + BW4_NBUF - 1;
             }
-            const uint32_t a_addr = base + (uint32_t)(t & 1) * tile_bytes, b_addr = a_addr + a_bytes;
+            const uint32_t a_addr = base + (uint32_t)(t % BW4_NBUF) * tile_bytes, b_addr = a_addr + a_bytes;
+            const uint32_t sw = (r & 7u);
             __nv_bfloat162 h0 = __floats2bfloat162_rn(gmv[0], gmv[1]), h1 = __floats2bfloat162_rn(gmv[2], gmv[3]);
             __nv_bfloat162 h2 = __floats2bfloat162_rn(gmv[4], gmv[5]), h3 = __floats2bfloat162_rn(gmv[6], gmv[7]);
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
-                         ::"r"(a_addr + (uint32_t)(tx >> 3) * 4096u + r * 128u + ((((uint32_t)tx & 7u) ^ (r & 7u)) << 4)),
+                         ::"r"(a_addr + (uint32_t)(tx >> 3) * 4096u + r * 128u + ((((uint32_t)tx & 7u) ^ sw) << 4)),
                            "r"(*reinterpret_cast<uint32_t*>(&h0)), "r"(*reinterpret_cast<uint32_t*>(&h1)),
                            "r"(*reinterpret_cast<uint32_t*>(&h2)), "r"(*reinterpret_cast<uint32_t*>(&h3)) : "memory");
-            for (int n = tx; n < BW4_TYPES; n += L) {
-                const unsigned short one = (n == ty_e) ? (unsigned short)0x3F80 : (unsigned short)0;
-                asm volatile("st.shared.u16 [%0], %1;"
-                             ::"r"(b_addr + (uint32_t)n * 128u + ((((r >> 3) ^ ((uint32_t)n & 7u))) << 4) + (r & 7u) * 2u), "h"(one) : "memory");
+            if (tx < 8) {                 // types 8 tx .. 8 tx + 7 of the row
+                const int idx = ty_e - tx * 8;
+                const uint32_t one = (idx & 1) ? 0x3F800000u : 0x00003F80u;
+                const uint32_t w0 = (idx >> 1) == 0 ? one : 0u, w1 = (idx >> 1) == 1 ? one : 0u;
+                const uint32_t w2 = (idx >> 1) == 2 ? one : 0u, w3 = (idx >> 1) == 3 ? one : 0u;
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                             ::"r"(b_addr + r * 128u + ((((uint32_t)tx) ^ sw) << 4)), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
             }
+        };
+        // rows [q0, q0 + n) of this node are in shared memory: make them visible to the tensor core, one arrival per row
+        auto publish_rows = [&](int q0, int n) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp(gmask);
-            if (tx == 0) mbar_arrive(&full_bar[t & 1]);
+            if (tx == 0) {
+                const int ta = q0 >> 5, tb = (q0 + n - 1) >> 5;
+                const int na = ta == tb ? n : BW4_ROWS - (q0 & 31);
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&full_bar[ta % BW4_NBUF])), "r"(na) : "memory");
+                if (tb != ta)
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&full_bar[tb % BW4_NBUF])), "r"(n - na) : "memory");
+            }
         };
         const int stride = nb;
         int j = n_begin + ty;
@@ -1076,8 +1155,9 @@ k_agg_bwd4(const bf16* __restrict__ x, const bf16* __restrict__ dout, bf16* __re
                         gmv[q] = gm;
                         acc[q] += gm;
                     }
-                    if (pbase + u < e0) stage_row(pbase + u - P0, gmv, sb.ty[u]);     // node-uniform condition
+                    if (pbase + u < e0) write_row(pbase + u - P0, gmv, sb.ty[u]);     // node-uniform condition
                 }
+                if (pbase < e0) publish_rows(pbase - P0, min(AGG_U, e0 - pbase));
             };
             consume(cur, b0);
             for (int p0 = b0 + AGG_U; p0 < e0; p0 += AGG_U) {
@@ -1105,7 +1185,10 @@ k_agg_bwd4(const bf16* __restrict__ x, const bf16* __restrict__ dout, bf16* __re
         // rows between the block's last edge and the end of its last tile: zero rows, zero one-hot columns
         if (active) {
             const float zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            for (int q = P1 - P0 + ty; q < ntiles * BW4_ROWS; q += nb) stage_row(q, zero, -1);
+            for (int q = P1 - P0 + ty; q < ntiles * BW4_ROWS; q += nb) {
+                write_row(q, zero, -1);
+                publish_rows(q, 1);
+            }
         }
         if (CONV == GT_CONV_GCN) {          // d root: one global atomic per (thread, channel)
 #pragma unroll
@@ -1114,7 +1197,13 @@ k_agg_bwd4(const bf16* __restrict__ x, const bf16* __restrict__ dout, bf16* __re
         }
         // ---- table-gradient epilogue: warps 0..3 own TMEM lanes 32 w .. 32 w + 31 = channels of every group
         if (ntiles > 0 && warp < 4) {
-            mbar_wait(&done_bar, 0);
+            for (uint32_t spin = 0;; ++spin) {
+                int done;
+                asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(done) : "r"(smem_u32(&tiles_done)) : "memory");
+                if (done >= ntiles) break;
+                __nanosleep(128);
+                if (spin > (1u << 24)) __trap();
+            }
             tc_fence_after();
             for (int g = 0; g < groups; ++g) {
                 const int ch = g * 128 + warp * 32 + lane;
@@ -1213,6 +1302,25 @@ static int launch_bwd(int ek, const T* x, const T* dout, T* dx, int N, int d, in
     // 32 KB per-chunk table.  Linear / no edge encoder: the batched kernel wins (62 vs 73 us on the code2 batch).
     // Without the table gradient (d_table == NULL: gt_aggregate_table_grad computes it) the batched kernel is used.
     const bool slots_ok = CONV != GT_CONV_GCN || en.norm_slot != nullptr;
+    // opt-in (GT_AGG_TABLE_FUSED=1 / ops.TABLE_GRAD_FUSED): measured at config 4 the fused kernel takes 757 us against
+    // 522 (k_agg_bwd3) + 203 (one-hot GEMM) + 71 (one-hot) = 796 us - both variants are issue bound at ~2.1 IPC per SM
+    // (446 M vs 265 M warp instructions, profiles/r02_ncu_agg4_syn_v1.txt), so the 2.2 GB per layer it keeps out of HBM buy
+    // 5 %; the default stays with the separate contraction.  fused_tab: -1 = not forced by the environment
+    static const int fused_env = getenv("GT_AGG_TABLE_FUSED") ? atoi(getenv("GT_AGG_TABLE_FUSED")) : -1;
+    const int fused_tab = fused_env != 0;   // the caller asks for it by passing d_table without gm_out
+    if (std::is_same<T, bf16>::value && tab_grad && fused_tab && !gm_out && slots_ok && (ld == 128 || ld == 256) &&
+        en.ntypes <= BW4_TYPES && variant == 0) {
+        // adjoint + edge-table gradient in one kernel (tcgen05 contraction of the per-edge gradients with the one-hot types)
+        int grid4 = blocks_for(N, BW4_WORKERS / (ld / 8), kNumSMs * 3);
+        const int npb = (N + grid4 - 1) / grid4;
+        grid4 = (N + npb - 1) / npb;
+        const size_t smem4 = BW4_NBUF * ((size_t)(ld / 64) * 4096 + 4096) + 1024;
+        static bool attr = false;
+        if (!attr) { cudaFuncSetAttribute(k_agg_bwd4<CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); attr = true; }
+        k_agg_bwd4<CONV><<<grid4, BW4_THREADS, smem4, st>>>((const bf16*)x, (const bf16*)dout, (bf16*)dx, N, d, ld, rp_src, dst_by_src,
+                                                            eid_by_src, en, self_param, dself, dtab, npb);
+        return 0;
+    }
     if (ld % 8 == 0 && ld <= 512 && slots_ok && (variant == 3 || (variant == 0 && ek != GT_EDGE_LINEAR)) && !tab_grad) {   // v3
         const dim3 blk((unsigned)(ld / 8), (unsigned)max(1, 256 / (ld / 8)));
         // ~one resident wave (threads pipeline over their nodes; every block ends with one global atomic per

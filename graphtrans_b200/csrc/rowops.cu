@@ -742,7 +742,19 @@ k_layernorm_bwd(const T* __restrict__ dy, const T* __restrict__ presum,
         const int vi = lane + k * 32;
         if (vi < nv) ldxf<VW>(gamma + vi * VW, gmm[k]);
     }
+    const bool pf_ok = ((size_t)d * sizeof(T)) % 16 == 0 && ((uintptr_t)dy % 16 == 0) && ((uintptr_t)presum % 16 == 0);
     for (int64_t row0 = (blockIdx.x * (int64_t)nw + wid) * R; row0 < M; row0 += (int64_t)gridDim.x * nw * R) {
+        // the rows of this warp's NEXT iteration start moving towards L2 now (one bulk prefetch per operand): with 16
+        // warps per SM and R rows each, the bytes in flight of the demand loads alone sit at the edge of what hides the HBM
+        // latency, and the load phase is only part of an iteration
+        if (pf_ok && lane == 0) {
+            const int64_t nrow = row0 + (int64_t)gridDim.x * nw * R;
+            if (nrow < M) {
+                const uint32_t bytes = (uint32_t)(min((int64_t)R, M - nrow) * d * sizeof(T));
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(dy + nrow * d), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(presum + nrow * d), "r"(bytes) : "memory");
+            }
+        }
         float xh[R][MAXV][VW], gy[R][MAXV][VW], mean[R], rstd[R], s1[R], s2[R];
 #pragma unroll
         for (int rr = 0; rr < R; ++rr) {
@@ -1177,6 +1189,64 @@ k_colsum_w(const T* __restrict__ X, int64_t M, int N, int64_t ld, int64_t rows_p
             ldw(X + r * ld + c0, v);
 #pragma unroll
             for (int q = 0; q < V; ++q) s[q] += v[q];
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < V; ++q) sh[ty][tx * V + q] = s[q];
+    __syncthreads();
+    if (threadIdx.x < TX * V) {
+        float a = 0.f;
+#pragma unroll
+        for (int k = 0; k < TY; ++k) a += sh[k][threadIdx.x];
+        const int c = blockIdx.x * TX * V + threadIdx.x;
+        if (c < N) atomicAdd(out + c, a);
+    }
+}
+
+// dz = dy * (y > 0) * scale and out[c] += sum over the rows of dz[:, c] in the same pass (the bias gradient of the Linear
+// whose epilogue applied the ReLU): k_colsum_w's mapping (16 row lanes x 16 column lanes of 16 bytes, four rows of a
+// thread in flight), one fp32 atomic per (block, channel)
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_relu_bwd_colsum(const T* __restrict__ dy, const T* __restrict__ y, int64_t M, int N, int64_t ld, int64_t rows_per_block,
+                  T* __restrict__ dz, float scale, float* __restrict__ out) {
+    constexpr int V = VecW<T>::V, TX = 16, TY = 16;
+    __shared__ float sh[TY][TX * V + 1];
+    const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+    const int c0 = (blockIdx.x * TX + tx) * V;
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_block, r1 = min(r0 + rows_per_block, M);
+    float s[V];
+#pragma unroll
+    for (int q = 0; q < V; ++q) s[q] = 0.f;
+    if (c0 < ld) {
+        int64_t r = r0 + ty;
+        for (; r + 3 * TY < r1; r += 4 * TY) {
+            float g[4][V], v[4][V];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                ldw(dy + (r + u * TY) * ld + c0, g[u]);
+                ldw(y + (r + u * TY) * ld + c0, v[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+#pragma unroll
+                for (int q = 0; q < V; ++q) {
+                    g[u][q] = v[u][q] > 0.f ? g[u][q] * scale : 0.f;
+                    s[q] += g[u][q];
+                }
+                stw(dz + (r + u * TY) * ld + c0, g[u]);
+            }
+        }
+        for (; r < r1; r += TY) {
+            float g[V], v[V];
+            ldw(dy + r * ld + c0, g);
+            ldw(y + r * ld + c0, v);
+#pragma unroll
+            for (int q = 0; q < V; ++q) {
+                g[q] = v[q] > 0.f ? g[q] * scale : 0.f;
+                s[q] += g[q];
+            }
+            stw(dz + r * ld + c0, g);
         }
     }
 #pragma unroll
@@ -1635,6 +1705,23 @@ extern "C" int gt_relu_bwd(int dt, const void* dy, const void* y, int64_t n, voi
     GT_CHECK_ARG(n > 0 && n % 4 == 0, "gt_relu_bwd: element count must be a positive multiple of 4");
     GT_DISPATCH_DT(dt, (k_relu_bwd<T><<<blocks_for(n / 4, 256), 256, 0, ST>>>((const T*)dy, (const T*)y, n / 4, (T*)dz, scale)));
     GT_LAUNCH_CHECK("gt_relu_bwd");
+    return 0;
+}
+
+extern "C" int gt_relu_bwd_colsum(int dt, const void* dy, const void* y, int64_t M, int64_t N, int64_t ld, void* dz,
+                                  float scale, float* colsum, void* stream) {
+    GT_CHECK_ARG(M > 0 && N > 0 && ld >= N && colsum, "gt_relu_bwd_colsum: bad shape");
+    const int esz = dt == GT_BF16 ? 2 : 4;
+    const int Vw = 16 / esz;
+    GT_CHECK_ARG(ld % Vw == 0 && (((uintptr_t)dy | (uintptr_t)y | (uintptr_t)dz) % 16 == 0),
+                 "gt_relu_bwd_colsum: rows must be 16-byte aligned (ld %% %d == 0)", Vw);
+    const int gx = (int)((ld + 16 * Vw - 1) / (16 * Vw));
+    int64_t gy = (4 * kNumSMs + gx - 1) / gx;
+    if (gy > (M + 63) / 64) gy = (M + 63) / 64;
+    const int64_t rpb = (M + gy - 1) / gy;
+    gy = (M + rpb - 1) / rpb;
+    GT_DISPATCH_DT(dt, (k_relu_bwd_colsum<T><<<dim3((unsigned)gx, (unsigned)gy), 256, 0, ST>>>((const T*)dy, (const T*)y, M, (int)N, ld, rpb, (T*)dz, scale, colsum)));
+    GT_LAUNCH_CHECK("gt_relu_bwd_colsum");
     return 0;
 }
 

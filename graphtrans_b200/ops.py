@@ -21,6 +21,10 @@ GEMM_IMPL = int(os.environ.get("GT_GEMM_IMPL", "0"))   # 0 auto, 1 CUDA-core, 2 
 FUSE_COLSTATS = int(os.environ.get("GT_FUSE_COLSTATS", "1"))         # BatchNorm statistics in the producing GEMM's epilogue
 SKIP_ZERO_BIAS_GRAD = int(os.environ.get("GT_SKIP_ZERO_BIAS_GRAD", "1"))   # bias of a Linear feeding train-mode BN: gradient == 0
 TABLE_GRAD_GEMM = int(os.environ.get("GT_TABLE_GRAD_GEMM", "1"))           # edge-table gradient as a one-hot contraction (bf16)
+# ... formed INSIDE the adjoint kernel (k_agg_bwd4: the per-edge gradients go straight from registers into a tcgen05
+# contraction with the one-hot edge types; no [E, ld] tensor); same eligibility rule as csrc/aggregate.cu launch_bwd
+# Opt-in: at config 4 it measures 757 us against 796 us for adjoint + one-hot GEMM (both issue bound), see DESIGN.md
+TABLE_GRAD_FUSED = int(os.environ.get("GT_AGG_TABLE_FUSED", "0"))
 MHA_IMPL = int(os.environ.get("GT_MHA_IMPL", "0"))
 # fp32 parity mode with every contraction ON the tcgen05 kernel: operands split into three bf16 terms, six products
 # accumulated in fp32 (SURVEY §7 "fp32 parity on tensor cores"); 0 = exact CUDA-core contractions (default parity path)
@@ -887,12 +891,23 @@ class _LinearFn(torch.autograd.Function):
             g2 = torch.empty(M, ld_out, dtype=x.dtype, device=x.device)
             call("gt_cast_pad", dt_of(gy), ptr(gy), M, ld_out, ld_out, dt_of(g2), ptr(g2), M, ld_out, ld_out)
             gy = g2
+        weight, bias = ctx.params
+        bias_done = False
         if relu:
             if y.dtype != gy.dtype:
                 raise RuntimeError("linear: relu with a widened output is not supported")
             gz = torch.empty_like(gy)
+            vw = 16 // gy.element_size()
             # a dropped element has y == 0, so the ReLU test also applies the keep mask; only the 1/(1-p) scale is left
-            call("gt_relu_bwd", dt_of(gy), ptr(gy), ptr(y), gy.numel(), ptr(gz), 1.0 / (1.0 - ctx.drop_p))
+            if (has_bias and ctx.needs_input_grad[2] and not ctx.bias_grad_zero and ld_out % vw == 0 and M >= 4096
+                    and _main_grad(bias) is not None):
+                # bias gradient = column sums of the masked gradient: taken in the same pass (no separate gt_colsum read)
+                tgt, _ = _grad_target(bias)
+                call("gt_relu_bwd_colsum", dt_of(gy), ptr(gy), ptr(y), M, N, ld_out, ptr(gz), 1.0 / (1.0 - ctx.drop_p),
+                     tgt.data_ptr() + ctx.row_off * 4)
+                bias_done = True
+            else:
+                call("gt_relu_bwd", dt_of(gy), ptr(gy), ptr(y), gy.numel(), ptr(gz), 1.0 / (1.0 - ctx.drop_p))
             gy = gz
         wptr = w.data_ptr() + ctx.woff
         gx = gw = gb = None
@@ -913,7 +928,6 @@ class _LinearFn(torch.autograd.Function):
             else:
                 _gemm_raw(dt_of(x), gy.data_ptr(), 0, ld_out, wptr, 1, ldw, gx.data_ptr(), ld_in, M, K, N, ld_in, None,
                           g_pass, ld_in, 0)
-        weight, bias = ctx.params
         # parameter gradients accumulated in place need no ordering with the rest of the backward: side stream
         side_ok = _main_grad(weight) is not None and (not has_bias or _main_grad(bias) is not None)
         with _WgradCtx(side_ok, gy, x):
@@ -925,7 +939,7 @@ class _LinearFn(torch.autograd.Function):
                 _grad_done(weight)
             if has_bias and ctx.needs_input_grad[2]:
                 tgt, gb = _grad_target(bias)           # (a fresh zero tensor when there is no arena)
-                if not ctx.bias_grad_zero:
+                if not ctx.bias_grad_zero and not bias_done:
                     call("gt_colsum", dt_of(gy), ptr(gy), M, N, ld_out, tgt.data_ptr() + ctx.row_off * 4)
                 _grad_done(bias)
         return gx, gw, gb, None, None, g_res, None, None, None, None, None, None, None, None, None
@@ -1052,9 +1066,14 @@ class _AggregateFn(torch.autograd.Function):
         ctx.split = edge_kind == EDGE_TABLE and table.shape[0] <= 1024
         ctx.tab_side = bool(tab_side)
         # bf16: the table gradient is the contraction OneHot(type)^T . gm over the per-edge gradients the adjoint writes
+        ctx.tab_fused = bool(ctx.split and TABLE_GRAD_FUSED and x.dtype == torch.bfloat16 and ld in (128, 256)
+                             and table.shape[0] <= 64 and (conv != CONV_GCN or slots[1][0] is not None)
+                             and not os.environ.get("GT_AGG_VARIANT"))
         ctx.tab_gemm = bool(ctx.split and TABLE_GRAD_GEMM and x.dtype == torch.bfloat16 and plan.E >= 1024 and ld % 8 == 0
-                            and ld <= 512 and slots[1][1] is not None)
-        if ctx.tab_gemm:
+                            and ld <= 512 and slots[1][1] is not None and not ctx.tab_fused)
+        if ctx.tab_fused:
+            pass
+        elif ctx.tab_gemm:
             plan.type_onehot(slots[1][1], table.shape[0])
         elif ctx.split:   # type-sorted edges for the table-gradient kernel (once per batch)
             plan.edges_by_type(plan._edge_index, etype, table.shape[0])
@@ -1079,7 +1098,8 @@ class _AggregateFn(torch.autograd.Function):
         # the edge-table gradient is a leaf gradient: computed by its own kernel over the type-sorted edges, on the
         # weight-gradient stream, instead of shared-memory atomics inside the adjoint (which then stays as cheap as
         # the forward)
-        split = ctx.split and need_tab
+        fused = ctx.tab_fused and need_tab      # table gradient accumulated by the adjoint kernel itself (d_table given)
+        split = ctx.split and need_tab and not fused
         gm = torch.empty(max(plan.E, 1), ld, dtype=x.dtype, device=x.device) if (split and ctx.tab_gemm) else None
         tself = _grad_target(pself)
         call("gt_aggregate_bwd", dt_of(x), conv, ptr(x), ptr(g), ptr(dx), N, d, ld, ptr(plan.rowptr_dst),

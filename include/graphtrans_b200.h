@@ -225,6 +225,11 @@ int gt_gemm_stats(int dt, const void* A, int a_mn, int64_t lda, const void* B, i
 /* dz = dy * (y > 0) * scale: backward of a ReLU (+ dropout: a dropped element has y == 0, scale = 1/(1-p)) that
  * was fused into a GEMM epilogue; n % 4 == 0 */
 int gt_relu_bwd(int dt, const void* dy, const void* y, int64_t n, void* dz, float scale, void* stream);
+/* the same over a [M, ld] matrix together with the column sums of dz: colsum fp32 [N] += sum_m dz[m, 0:N] (the bias
+ * gradient of the Linear whose epilogue applied the ReLU, reference nn.TransformerEncoderLayer linear1 built at
+ * modules/transformer_encoder.py:28-32); rows 16-byte aligned */
+int gt_relu_bwd_colsum(int dt, const void* dy, const void* y, int64_t M, int64_t N, int64_t ld, void* dz, float scale,
+                       float* colsum, void* stream);
 /* fp32 parity mode ON the tensor cores: dst bf16 [3][rows][ld_dst] = the three-term split x = p0 + p1 + p2 of src fp32
  * [rows, cols] (row pitch ld_src; columns cols..ld_dst-1 := 0).  The host sums the six products p_i . q_j with i + j <= 2
  * through gt_gemm (fp32 accumulation in TMEM), which reproduces an fp32 contraction to ~2^-22 (ops._gemm_raw, GT_GEMM_TC_PARITY). */

@@ -10,7 +10,7 @@ import copy
 import pytest
 import torch
 
-from graphtrans_b200 import factory, loader, ops, synth
+from graphtrans_b200 import _lib, factory, loader, ops, synth
 from graphtrans_b200.ddp import GradBuckets
 from graphtrans_b200.graphed import GraphedStep
 from graphtrans_b200.modules import transformer_encoder as te
@@ -358,3 +358,89 @@ def test_prefetch_and_async_loss_match_plain_steps():
         pending = h
     got.append(pending.item())
     assert len(got) == len(plain) and all(abs(a - b) < 1e-5 * max(1.0, abs(b)) for a, b in zip(got, plain)), (got, plain)
+
+
+@pytest.mark.parametrize("conv", ["gin", "gcn"])
+@pytest.mark.parametrize("d,n_graphs", [(256, 300), (250, 40), (128, 40), (256, 1), (256, -512), (256, -65)])
+def test_aggregate_table_gradient_fused_in_adjoint(conv, d, n_graphs):
+    """k_agg_bwd4: the edge-table gradient is contracted on the tensor cores inside the adjoint (per-edge gradients staged in
+    shared memory, one-hot edge types as the second operand).  Checked against the fp64 dense formula
+    d_table[t] = sum_{e: type t} norm_e * dout[dst_e] * 1[x[src_e] + table[t] > 0] and against the separate-GEMM path
+    (GT_AGG_TABLE_FUSED=0 semantics via ops.TABLE_GRAD_FUSED); dx and the self-parameter gradient ride along."""
+    from graphtrans_b200 import synth
+    from graphtrans_b200._lib import CONV_GCN, CONV_GIN, EDGE_TABLE
+    if n_graphs < 0:            # config-4 graphs: ~150 nodes and ~20 staging tiles per block (buffer reuse)
+        n_graphs = -n_graphs
+        batch = synth.gen_syn(n_graphs, seed=11)
+        if n_graphs % 2:        # hubs: three nodes with ~1000 self loops each (what the slack nodes of a shape bucket look
+            n_all = batch.batch.numel()    # like): the other workers' consecutive rows lie dozens of staging tiles apart
+            hubs = torch.tensor([n_all // 3, n_all // 2, n_all - 1]).repeat_interleave(1000)
+            batch.edge_index = torch.cat([batch.edge_index, torch.stack([hubs, hubs])], dim=1)
+    else:
+        batch = synth.gen_mol(n_graphs, seed=11)
+    ei = batch.edge_index.cuda()
+    N, E, ntypes = batch.batch.numel(), ei.shape[1], 60
+    ld = ops.ldp(d)
+    torch.manual_seed(5)
+    x0 = torch.zeros(N, ld, device="cuda")
+    x0[:, :d] = torch.randn(N, d, device="cuda")
+    table0 = torch.zeros(ntypes, ld, device="cuda")
+    table0[:, :d] = torch.randn(ntypes, d, device="cuda") * 0.5
+    etype = torch.randint(0, ntypes, (E,), device="cuda", dtype=torch.int32)
+    kind = CONV_GIN if conv == "gin" else CONV_GCN
+    sp0 = torch.full((1,), 0.25, device="cuda") if conv == "gin" else torch.randn(d, device="cuda")
+    gy = torch.zeros(N, ld, device="cuda")
+    gy[:, :d] = torch.randn(N, d, device="cuda")
+    gy = gy.bfloat16()
+
+    def run(fused):
+        prev = ops.TABLE_GRAD_FUSED
+        ops.TABLE_GRAD_FUSED = fused
+        try:
+            plan = ops.GraphPlan(ei, batch.batch.cuda(), n_graphs)
+            x = x0.bfloat16().requires_grad_(True)
+            table = table0.clone().requires_grad_(True)
+            sp = sp0.clone().requires_grad_(True)
+            y = ops.aggregate(x, plan, kind, d, sp, edge_kind=EDGE_TABLE, etype=etype, table=table)
+            return torch.autograd.grad(y, (x, table, sp), gy)
+        finally:
+            ops.TABLE_GRAD_FUSED = prev
+
+    k0 = _lib.kernel_count
+    dx, dtab, dsp = run(1)
+    n_fused = _lib.kernel_count - k0
+    k0 = _lib.kernel_count
+    dx_g, dtab_g, dsp_g = run(0)
+    assert n_fused < _lib.kernel_count - k0          # no one-hot / GEMM launches on the fused path
+    src, dst = ei[0], ei[1]
+    xd, gd, td = x0.bfloat16().double()[:, :d], gy.double()[:, :d], table0.double()[:, :d]
+    nrm = torch.ones(E, device="cuda", dtype=torch.float64)
+    if conv == "gcn":
+        deg = torch.bincount(src, minlength=N).double() + 1
+        nrm = deg[src].rsqrt() * deg[dst].rsqrt()
+    gm = nrm[:, None] * gd[dst] * ((xd[src] + td[etype.long()]) > 0)
+    ref_tab = torch.zeros(ntypes, d, device="cuda", dtype=torch.float64).index_add_(0, etype.long(), gm)
+    assert (dtab[:, :d].double() - ref_tab).norm() / ref_tab.norm() < 1e-2
+    assert (dtab.double() - dtab_g.double()).norm() / dtab_g.double().norm() < 2e-3
+    if ld > d:
+        assert float(dtab[:, d:].abs().max()) == 0.0
+    assert torch.equal(dx, dx_g)                     # same per-edge arithmetic and summation order
+    assert (dsp.double() - dsp_g.double()).norm() <= 1e-3 * dsp_g.double().norm() + 1e-6
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("M,N,ld", [(5000, 512, 512), (4097, 300, 304), (70, 8, 8)])
+def test_relu_bwd_colsum(dtype, M, N, ld):
+    """gt_relu_bwd_colsum == gt_relu_bwd followed by gt_colsum (bias gradient of a Linear with a fused ReLU epilogue)"""
+    torch.manual_seed(2)
+    dy = torch.randn(M, ld, device="cuda").to(dtype)
+    y = torch.relu(torch.randn(M, ld, device="cuda")).to(dtype)
+    y[:, N:] = 0
+    dz = torch.empty_like(dy)
+    cs = torch.full((N,), 0.5, device="cuda")
+    ops.call("gt_relu_bwd_colsum", ops.dt_of(dy), ops.ptr(dy), ops.ptr(y), M, N, ld, ops.ptr(dz), 1.25, ops.ptr(cs))
+    ref32 = torch.where(y > 0, dy.float() * 1.25, torch.zeros((), device="cuda"))
+    assert torch.equal(dz, ref32.to(dtype))
+    want = ref32.double()[:, :N].sum(0) + 0.5                     # fp32 products summed before the store rounds them;
+                                                                  # accumulates into the target
+    assert (cs.double() - want).abs().max() <= 1e-4 * max(1.0, float(want.abs().max()))
