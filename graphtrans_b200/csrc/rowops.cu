@@ -331,10 +331,7 @@ k_bn_bwd_reduce(const T* __restrict__ x, const T* __restrict__ dy, int64_t M, in
         ld4(ssmr + ld + c0, sh);
         ld4(ssmr + 2 * ld + c0, mu);
         ld4(ssmr + 3 * ld + c0, rs);
-        for (int64_t r = r0 + ty; r < r1; r += STAT_TY) {
-            float v[4], g[4];
-            ld4(x + r * ld + c0, v);
-            ld4(dy + r * ld + c0, g);
+        auto acc_row = [&](int64_t r, float (&v)[4], float (&g)[4]) {
             float ds[4];
             drop4(dr, (uint64_t)(r * vpr + c0 / 4), ds);
 #pragma unroll
@@ -344,6 +341,23 @@ k_bn_bwd_reduce(const T* __restrict__ x, const T* __restrict__ dy, int64_t M, in
                 s[q] += g[q];
                 s2[q] = fmaf(g[q], (v[q] - mu[q]) * rs[q], s2[q]);
             }
+        };
+        int64_t r = r0 + ty;
+        for (; r + 3 * STAT_TY < r1; r += 4 * STAT_TY) {       // four rows of a thread in flight (8-byte loads: the bytes
+            float v[4][4], g[4][4];                             // in flight per SM, not the arithmetic, bound this pass)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                ld4(x + (r + u * STAT_TY) * ld + c0, v[u]);
+                ld4(dy + (r + u * STAT_TY) * ld + c0, g[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc_row(r + u * STAT_TY, v[u], g[u]);
+        }
+        for (; r < r1; r += STAT_TY) {
+            float v[4], g[4];
+            ld4(x + r * ld + c0, v);
+            ld4(dy + r * ld + c0, g);
+            acc_row(r, v, g);
         }
     }
     stat_flush(s, s2, tx, ty, c0, ld, red);
