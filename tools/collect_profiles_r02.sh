@@ -14,8 +14,7 @@ cap() {  # cfg name regex skip count
   $NCU --set full --import-source on -k regex:$3 -s $4 -c $5 -f -o gpurun_out/r02_prof_$2_$1_${TAG} $B --config $1 > /dev/null 2>&1
 }
 cap syn agg "k_agg_(fwd|bwd)3" 12 2
-cap syn rowops "k_layernorm_bwd|k_layernorm_fwd|k_bn_bwd_apply|k_bn_bwd_reduce|k_bn_norm_fwd|k_colsum" 60 8
-GT_LN_WIDE=0 cap syn rowops_ln4 "k_layernorm_bwd" 8 3
+cap syn rowops "k_layernorm_bwd|k_layernorm_fwd|k_bn_bwd_apply|k_bn_bwd_reduce|k_bn_norm_fwd|k_colsum|k_relu_bwd" 60 8
 cap syn mha "k_mha_" 20 6
 cap syn gemm "k_gemm_tc" 60 8
 cap code2-pna pna "k_pna_" 12 2
