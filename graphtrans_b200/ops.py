@@ -220,6 +220,7 @@ def next_salt() -> int:
 # call join_side_streams() after backward() and before reading gradients (GraphedStep and bench.py do).
 _wgrad = {"stream": None, "used": False, "keep": []}
 WGRAD_SIDE_MAX_ELEMS = int(os.environ.get("GT_WGRAD_SIDE_MAX_ELEMS", str(16 << 20)))
+WGRAD_SIDE_MAX_ROWS = int(os.environ.get("GT_WGRAD_SIDE_MAX_ROWS", str(32 << 10)))
 
 
 def enable_wgrad_stream(on=True, device="cuda"):
@@ -254,7 +255,10 @@ class _WgradCtx:
         # Large operands (config 4: [5e5, 512] gradients) make the weight-gradient kernels HBM-bound device-filling
         # launches of their own: run next to the equally HBM-bound main stream they only thrash (measured: 39.2 ms with,
         # 38.3 ms without the side stream on config 4; the small configs gain 3-4 % from it) - those stay on the main stream.
-        big = max((t.numel() for t in self.tensors), default=0) > WGRAD_SIDE_MAX_ELEMS
+        # "Large" = many ROWS (the contraction length of a weight gradient) as well as many elements: a wide but short
+        # operand (config 5's [14 k, 3328] tower inputs) is a brief launch inside a latency-bound step and keeps the overlap
+        big = (max((t.numel() for t in self.tensors), default=0) > WGRAD_SIDE_MAX_ELEMS and
+               max((t.shape[0] for t in self.tensors if t.dim() > 1), default=0) > WGRAD_SIDE_MAX_ROWS)
         self.on = bool(on) and not big
         self.ctx = None
 

@@ -1,5 +1,7 @@
 #!/bin/bash
-timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
-for c in syn molpcba; do
-timeout 200 python tools/graph_trace.py $c > gpurun_out/r02_graph_trace_${c}_l.txt 2>&1; grep -E "us/step|bn_bwd_reduce" gpurun_out/r02_graph_trace_${c}_l.txt | cut -c1-140
+F="--steps 30 --warmup 5 --no-cpu-baseline --no-roofline --no-e2e --no-optimizer --no-extra-configs"
+for r in 32768 1; do
+  for c in code2-pna; do
+  echo "=== rows>$r $c"; GT_WGRAD_SIDE_MAX_ROWS=$r timeout 100 python bench.py $F --config $c 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['clocks'])"
+  done
 done
