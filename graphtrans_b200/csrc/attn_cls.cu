@@ -8,6 +8,8 @@
 // dQ accumulations (coalesced row reads).  fp32 math on fp32 or bf16 storage; memory-bound: K and V of every token
 // are read exactly once (n_rows * 2d * s bytes).  Same dropout hash as the full kernels (row id = head * n_rows +
 // query row, column = key row), so a full-layer run with the same salt drops the same probabilities.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace gt {
@@ -148,6 +150,164 @@ k_mha_cls_bwd(const T* __restrict__ q, const T* __restrict__ kv, const T* __rest
     if (lane + 32 < dh) dqr[lane + 32] = from_f<T>(a1);
 }
 
+// ---- d = 256, bf16: one warp per GRAPH (all heads).  A token row's k (or v) part is 512 contiguous bytes = one 16-byte
+// vector per lane, so every load of the pass is a fully coalesced row read, four rows of a warp in flight; the lanes of a
+// head (DH / 8 of them) meet with xor shuffles for the score, then run the online softmax redundantly.  The kernels above
+// read 8 bytes per lane from 32 different rows per instruction and walk V two bytes per lane (2 TB/s measured at config
+// 4); same arithmetic, same dropout hash.
+constexpr int CLSW_D = 256;
+
+__device__ __forceinline__ void clsw_unpack(const uint4& t, float (&v)[8]) {
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        v[2 * i] = __uint_as_float(w[i] << 16);
+        v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+}
+__device__ __forceinline__ uint4 clsw_pack(const float (&v)[8]) {
+    uint4 t;
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
+    t.x = *reinterpret_cast<uint32_t*>(&h0); t.y = *reinterpret_cast<uint32_t*>(&h1);
+    t.z = *reinterpret_cast<uint32_t*>(&h2); t.w = *reinterpret_cast<uint32_t*>(&h3);
+    return t;
+}
+template <int LPH>
+__device__ __forceinline__ float clsw_head_sum(float v) {      // sum over the LPH lanes of a head
+#pragma unroll
+    for (int o = LPH / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int DH>
+__global__ void __launch_bounds__(CLS_WARPS * 32)
+k_mha_cls_fwd_w(const bf16* __restrict__ q, const bf16* __restrict__ kv, const int32_t* __restrict__ tok_off,
+                const int32_t* __restrict__ q_rows, int64_t n_rows, int B, float scale, bf16* __restrict__ out,
+                float* __restrict__ lse, float drop_p, const uint64_t* __restrict__ rng, uint64_t salt) {
+    constexpr int D = CLSW_D, LPH = DH / 8, NH = D / DH, U = 4;
+    const Drop dr = make_drop(rng, salt, drop_p);
+    const int lane = threadIdx.x & 31, g = blockIdx.x * CLS_WARPS + (threadIdx.x >> 5);
+    if (g >= B) return;
+    const int h = lane / LPH;
+    const int ks = tok_off[g], ke = tok_off[g + 1];
+    float qv[8];
+    clsw_unpack(*reinterpret_cast<const uint4*>(q + (int64_t)g * D + lane * 8), qv);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) qv[c] *= scale;
+    const uint32_t rk = drop_row_key(dr, (uint64_t)h * (uint64_t)n_rows + (uint64_t)q_rows[g]);
+    float m = -INFINITY, l = 0.f, o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int j0 = ks; j0 < ke; j0 += U) {
+        uint4 kr[U], vr[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const bf16* row = kv + (int64_t)min(j0 + u, ke - 1) * (2 * D) + lane * 8;
+            kr[u] = *reinterpret_cast<const uint4*>(row);
+            vr[u] = *reinterpret_cast<const uint4*>(row + D);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (j0 + u >= ke) break;          // warp-uniform
+            float kf[8], vf[8];
+            clsw_unpack(kr[u], kf);
+            clsw_unpack(vr[u], vf);
+            float s = 0.f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) s = fmaf(qv[c], kf[c], s);
+            s = clsw_head_sum<LPH>(s);
+            const float mnew = fmaxf(m, s);
+            const float corr = __expf(m - mnew), p = __expf(s - mnew);
+            l = fmaf(l, corr, p);
+            const float pd = dr.on ? p * drop_elem(dr, rk, (uint32_t)(j0 + u)) : p;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) o[c] = fmaf(o[c], corr, pd * vf[c]);
+            m = mnew;
+        }
+    }
+    const float inv = l > 0.f ? 1.f / l : 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) o[c] *= inv;
+    *reinterpret_cast<uint4*>(out + (int64_t)g * D + lane * 8) = clsw_pack(o);
+    if (lane % LPH == 0) lse[(int64_t)g * NH + h] = m + __logf(l);
+}
+
+template <int DH>
+__global__ void __launch_bounds__(CLS_WARPS * 32)
+k_mha_cls_bwd_w(const bf16* __restrict__ q, const bf16* __restrict__ kv, const bf16* __restrict__ out,
+                const bf16* __restrict__ dout, const float* __restrict__ lse, const int32_t* __restrict__ tok_off,
+                const int32_t* __restrict__ q_rows, int64_t n_rows, int B, float scale, bf16* __restrict__ dq,
+                bf16* __restrict__ dkv, float drop_p, const uint64_t* __restrict__ rng, uint64_t salt) {
+    constexpr int D = CLSW_D, LPH = DH / 8, NH = D / DH, U = 4;
+    const Drop dr = make_drop(rng, salt, drop_p);
+    const int lane = threadIdx.x & 31, g = blockIdx.x * CLS_WARPS + (threadIdx.x >> 5);
+    if (g >= B) {   // tail rows [tok_off[B], n_rows): zero gradient (the trailing blocks)
+        const int64_t first = tok_off[B];
+        const int64_t n16 = (n_rows - first) * (2 * D / 8);
+        const int64_t t0 = (int64_t)(g - B) * 32 + lane;
+        const int64_t stride = ((int64_t)gridDim.x * CLS_WARPS - (int64_t)B) * 32;
+        for (int64_t i = t0; i < n16; i += stride)
+            *reinterpret_cast<uint4*>(dkv + first * (2 * D) + i * 8) = make_uint4(0u, 0u, 0u, 0u);
+        return;
+    }
+    const int h = lane / LPH;
+    const int ks = tok_off[g], ke = tok_off[g + 1];
+    float qv[8], gv[8], ov[8];
+    clsw_unpack(*reinterpret_cast<const uint4*>(q + (int64_t)g * D + lane * 8), qv);
+    clsw_unpack(*reinterpret_cast<const uint4*>(dout + (int64_t)g * D + lane * 8), gv);
+    clsw_unpack(*reinterpret_cast<const uint4*>(out + (int64_t)g * D + lane * 8), ov);
+    float dl = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) dl = fmaf(gv[c], ov[c], dl);
+    dl = clsw_head_sum<LPH>(dl);
+    const float L = lse[(int64_t)g * NH + h];
+    const uint32_t rk = drop_row_key(dr, (uint64_t)h * (uint64_t)n_rows + (uint64_t)q_rows[g]);
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int j0 = ks; j0 < ke; j0 += U) {
+        uint4 kr[U], vr[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const bf16* row = kv + (int64_t)min(j0 + u, ke - 1) * (2 * D) + lane * 8;
+            kr[u] = *reinterpret_cast<const uint4*>(row);
+            vr[u] = *reinterpret_cast<const uint4*>(row + D);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (j0 + u >= ke) break;          // warp-uniform
+            float kf[8], vf[8];
+            clsw_unpack(kr[u], kf);
+            clsw_unpack(vr[u], vf);
+            float s = 0.f, dp = 0.f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                s = fmaf(qv[c], kf[c], s);
+                dp = fmaf(gv[c], vf[c], dp);
+            }
+            s = clsw_head_sum<LPH>(s) * scale;
+            dp = clsw_head_sum<LPH>(dp);
+            const float p = __expf(s - L);
+            const float keep = dr.on ? drop_elem(dr, rk, (uint32_t)(j0 + u)) : 1.f;
+            const float ds = p * (dp * keep - dl) * scale, pd = p * keep;
+            float dk[8], dv[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                a[c] = fmaf(ds, kf[c], a[c]);
+                dk[c] = ds * qv[c];
+                dv[c] = pd * gv[c];
+            }
+            bf16* drow = dkv + (int64_t)(j0 + u) * (2 * D) + lane * 8;
+            *reinterpret_cast<uint4*>(drow) = clsw_pack(dk);
+            *reinterpret_cast<uint4*>(drow + D) = clsw_pack(dv);
+        }
+    }
+    *reinterpret_cast<uint4*>(dq + (int64_t)g * D + lane * 8) = clsw_pack(a);
+}
+
+static bool clsw_ok(int dt, int32_t nhead, int32_t dh, const void* a, const void* b, const void* c, const void* d4) {
+    static const int on = getenv("GT_CLS_WIDE") ? atoi(getenv("GT_CLS_WIDE")) : 1;
+    return on && dt == GT_BF16 && nhead * dh == CLSW_D && (dh == 32 || dh == 64) &&
+           (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c | (uintptr_t)d4) % 16 == 0);
+}
+
 }  // namespace gt
 
 using namespace gt;
@@ -157,6 +317,15 @@ extern "C" int gt_mha_cls_fwd(int dt, const void* q, const void* kv, const int32
                               float drop_p, const uint64_t* rng_state, uint64_t salt, void* stream) {
     GT_CHECK_ARG(B > 0 && n_rows > 0 && nhead > 0 && dh > 0 && dh <= CLS_MAXDH && dh % 4 == 0,
                  "gt_mha_cls_fwd: needs head dim %% 4 == 0 and <= %d (got %d)", CLS_MAXDH, dh);
+    if (clsw_ok(dt, nhead, dh, q, kv, out, nullptr)) {
+        const unsigned blocks = (unsigned)((B + CLS_WARPS - 1) / CLS_WARPS);
+        if (dh == 64)
+            k_mha_cls_fwd_w<64><<<blocks, CLS_WARPS * 32, 0, (cudaStream_t)stream>>>((const bf16*)q, (const bf16*)kv, tok_off, q_rows, n_rows, (int)B, scale, (bf16*)out, lse, drop_p, rng_state, salt);
+        else
+            k_mha_cls_fwd_w<32><<<blocks, CLS_WARPS * 32, 0, (cudaStream_t)stream>>>((const bf16*)q, (const bf16*)kv, tok_off, q_rows, n_rows, (int)B, scale, (bf16*)out, lse, drop_p, rng_state, salt);
+        GT_LAUNCH_CHECK("gt_mha_cls_fwd");
+        return 0;
+    }
     const int64_t items = B * nhead;
     GT_DISPATCH_DT(dt, (k_mha_cls_fwd<T><<<(unsigned)((items + CLS_WARPS - 1) / CLS_WARPS), CLS_WARPS * 32, 0, (cudaStream_t)stream>>>(
                            (const T*)q, (const T*)kv, tok_off, q_rows, n_rows, (int)B, nhead, dh, scale, (T*)out, lse, drop_p, rng_state, salt)));
@@ -170,6 +339,15 @@ extern "C" int gt_mha_cls_bwd(int dt, const void* q, const void* kv, const void*
                               uint64_t salt, void* stream) {
     GT_CHECK_ARG(B > 0 && n_rows > 0 && nhead > 0 && dh > 0 && dh <= CLS_MAXDH && dh % 4 == 0,
                  "gt_mha_cls_bwd: needs head dim %% 4 == 0 and <= %d (got %d)", CLS_MAXDH, dh);
+    if (clsw_ok(dt, nhead, dh, q, kv, dout, dkv) && ((uintptr_t)out | (uintptr_t)dq) % 16 == 0) {
+        const unsigned blocks = (unsigned)((B + CLS_WARPS - 1) / CLS_WARPS + 64);     // + 64 blocks for the tail rows
+        if (dh == 64)
+            k_mha_cls_bwd_w<64><<<blocks, CLS_WARPS * 32, 0, (cudaStream_t)stream>>>((const bf16*)q, (const bf16*)kv, (const bf16*)out, (const bf16*)dout, lse, tok_off, q_rows, n_rows, (int)B, scale, (bf16*)dq, (bf16*)dkv, drop_p, rng_state, salt);
+        else
+            k_mha_cls_bwd_w<32><<<blocks, CLS_WARPS * 32, 0, (cudaStream_t)stream>>>((const bf16*)q, (const bf16*)kv, (const bf16*)out, (const bf16*)dout, lse, tok_off, q_rows, n_rows, (int)B, scale, (bf16*)dq, (bf16*)dkv, drop_p, rng_state, salt);
+        GT_LAUNCH_CHECK("gt_mha_cls_bwd");
+        return 0;
+    }
     const int64_t items = B * nhead;
     const int64_t blocks = (items + CLS_WARPS - 1) / CLS_WARPS + 64;     // + 64 blocks that clear the unused tail rows
     GT_DISPATCH_DT(dt, (k_mha_cls_bwd<T><<<(unsigned)blocks, CLS_WARPS * 32, 0, (cudaStream_t)stream>>>(

@@ -49,7 +49,7 @@ def _run(model, lossf, b):
 
 
 # ----------------------------------------------------------------------------- pooled-query last layer
-@pytest.mark.parametrize("nhead,dh", [(4, 32), (4, 64)])
+@pytest.mark.parametrize("nhead,dh", [(4, 32), (4, 64), (8, 32)])      # d = 256 in bf16: the warp-per-graph kernels
 @pytest.mark.parametrize("drop_p", [0.0, 0.3])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_pooled_query_attention_matches_full_attention_rows(nhead, dh, drop_p, dtype):

@@ -1,7 +1,3 @@
 #!/bin/bash
-F="--steps 30 --warmup 5 --no-cpu-baseline --no-roofline --no-e2e --no-optimizer --no-extra-configs"
-for r in 32768 1; do
-  for c in code2-pna; do
-  echo "=== rows>$r $c"; GT_WGRAD_SIDE_MAX_ROWS=$r timeout 100 python bench.py $F --config $c 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['clocks'])"
-  done
-done
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+timeout 200 python tools/graph_trace.py syn > gpurun_out/r02_graph_trace_syn_m.txt 2>&1; grep -E "us/step|mha_cls" gpurun_out/r02_graph_trace_syn_m.txt | cut -c1-140
