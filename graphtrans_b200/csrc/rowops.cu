@@ -614,8 +614,19 @@ k_bn_bwd_apply_slab(const T* __restrict__ x, const T* __restrict__ dy, int64_t M
         for (int q = 0; q < V; ++q) z[q] = 0.f;
         stw(dx + r * ld + c0, z);
     }
+    // the block's rows are one contiguous byte range of x and dy: thread 0 keeps a window of them moving towards L2
+    // (bulk prefetch of the rows 8 iterations ahead), the demand loads then mostly hit L2
+    const bool pf = threadIdx.x == 0 && ((size_t)ld * sizeof(T)) % 16 == 0 && ((uintptr_t)x % 16 == 0) && ((uintptr_t)dy % 16 == 0);
 #pragma unroll 4
     for (int64_t r = r0 + rr; r < r1v; r += rpi) {
+        if (pf) {
+            const int64_t rp = r + 8 * (int64_t)rpi;
+            if (rp < r1v) {
+                const uint32_t bytes = (uint32_t)(min((int64_t)rpi, r1v - rp) * ld * sizeof(T));
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(x + rp * ld), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(dy + rp * ld), "r"(bytes) : "memory");
+            }
+        }
         float v[V], g[V], o[V];
         ldw(x + r * ld + c0, v);
         ldw(dy + r * ld + c0, g);
@@ -1581,19 +1592,36 @@ struct OneHotCols {
     int ncol;
 };
 __global__ void k_onehot(OneHotCols cols, int64_t N, int groups, bf16* __restrict__ out) {
-    const int64_t total = N * groups;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = i / groups;
-        const int g = (int)(i - r * groups);
-        uint32_t w[4] = {0u, 0u, 0u, 0u};
+    // thread = (row, 16-byte group); four rows of a thread in flight (index loads first, then the stores): the pass is a
+    // pure write stream whose only latency is the index fetch
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t rows_per_pass = stride / groups;       // host sizes the grid so that groups divides the thread count
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int g = (int)(t % groups);
+    for (int64_t r0 = t / groups; r0 < N; r0 += 4 * rows_per_pass) {
+        uint32_t w[4][4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) w[u][0] = w[u][1] = w[u][2] = w[u][3] = 0u;
         for (int c = 0; c < cols.ncol; ++c) {
             if (cols.base[c] < 0) continue;
-            int64_t id = cols.idx[c][r * cols.stride[c]];
-            if (id > cols.clamp[c]) id = cols.clamp[c];
-            const int pos = cols.base[c] + (int)id;
-            if ((pos >> 3) == g) w[(pos & 7) >> 1] |= 0x3F80u << (16 * (pos & 1));   // bf16 1.0
+            int64_t id[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t r = r0 + u * rows_per_pass;
+                id[u] = r < N ? cols.idx[c][r * cols.stride[c]] : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t v = id[u] > cols.clamp[c] ? cols.clamp[c] : id[u];
+                const int pos = cols.base[c] + (int)v;
+                if ((pos >> 3) == g) w[u][(pos & 7) >> 1] |= 0x3F80u << (16 * (pos & 1));   // bf16 1.0
+            }
         }
-        *reinterpret_cast<uint4*>(out + (r * groups + g) * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t r = r0 + u * rows_per_pass;
+            if (r < N) *reinterpret_cast<uint4*>(out + (r * groups + g) * 8) = make_uint4(w[u][0], w[u][1], w[u][2], w[u][3]);
+        }
     }
 }
 __global__ void k_embed_unpack(OneHotCols cols, const float* __restrict__ temp, int ld_t, int d, int R) {
@@ -1630,7 +1658,11 @@ extern "C" int gt_onehot(int64_t N, int32_t ncol, const int64_t* const* idx_host
     GT_CHECK_ARG(N > 0 && r_pad > 0 && r_pad % 8 == 0, "gt_onehot: bad shape");
     OneHotCols c;
     if (int r = fill_onehot(c, ncol, idx_host, stride_host, clamp_host, base_host, nullptr, nullptr)) return r;
-    k_onehot<<<blocks_for(N * (r_pad / 8), 256), 256, 0, ST>>>(c, N, r_pad / 8, (bf16*)out);
+    const int groups = r_pad / 8;
+    // every thread keeps its 16-byte group for all its rows: the block size is a multiple of the groups per row
+    const int bs = (256 / groups) * groups > 0 ? (256 / groups) * groups : groups;
+    GT_CHECK_ARG(bs <= 1024, "gt_onehot: r_pad=%d too wide", r_pad);
+    k_onehot<<<blocks_for((N * groups + 3) / 4, bs), bs, 0, ST>>>(c, N, groups, (bf16*)out);
     GT_LAUNCH_CHECK("gt_onehot");
     return 0;
 }
