@@ -388,7 +388,7 @@ def in_step_roofline(cfg, args, model, lossf, buckets, b, hb, ns, step_ms, rank)
         out.append(o)
     n, us = trace.kernel_time(prof, ("gt_mha_cls_fwd", "gt_mha_cls_bwd"))
     if n:
-        kvb = 2 * alg["tokens"] * 2 * args.d_model * es          # fwd reads k|v once; bwd reads them and writes dk|dv
+        kvb = alg["tokens"] * 2 * args.d_model * es              # k|v of every token: fwd reads them once; bwd reads them and writes dk|dv
         ach = (kvb + 2 * kvb) / (us * 1e-6) / 1e9
         out.append({"kernel": "gt_mha_cls_fwd + gt_mha_cls_bwd (pooled-query last layer)", "bound": "hbm", "achieved": ach,
                     "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": None, "avg_launch_us": us / n,
