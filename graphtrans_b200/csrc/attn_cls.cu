@@ -302,9 +302,14 @@ k_mha_cls_bwd_w(const bf16* __restrict__ q, const bf16* __restrict__ kv, const b
     *reinterpret_cast<uint4*>(dq + (int64_t)g * D + lane * 8) = clsw_pack(a);
 }
 
-static bool clsw_ok(int dt, int32_t nhead, int32_t dh, const void* a, const void* b, const void* c, const void* d4) {
+// One warp walks ALL token rows of its graph, four at a time: that needs enough graphs to fill the machine (>= 4 warps
+// per SM) and short graphs (config 4: 129 rows on average).  Few long graphs (Code2: 128 graphs of up to 1001 rows) keep
+// the warp-per-(graph, head) kernels with 32 keys in flight per warp (measured: 2.80 vs 2.91 ms per config-3 step).
+static bool clsw_ok(int dt, int32_t nhead, int32_t dh, int64_t B, int64_t n_rows, const void* a, const void* b, const void* c,
+                    const void* d4) {
     static const int on = getenv("GT_CLS_WIDE") ? atoi(getenv("GT_CLS_WIDE")) : 1;
-    return on && dt == GT_BF16 && nhead * dh == CLSW_D && (dh == 32 || dh == 64) &&
+    const bool shape = on == 2 || (B >= 4 * kNumSMs && n_rows <= 256 * B);
+    return on && shape && dt == GT_BF16 && nhead * dh == CLSW_D && (dh == 32 || dh == 64) &&
            (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c | (uintptr_t)d4) % 16 == 0);
 }
 
@@ -317,7 +322,7 @@ extern "C" int gt_mha_cls_fwd(int dt, const void* q, const void* kv, const int32
                               float drop_p, const uint64_t* rng_state, uint64_t salt, void* stream) {
     GT_CHECK_ARG(B > 0 && n_rows > 0 && nhead > 0 && dh > 0 && dh <= CLS_MAXDH && dh % 4 == 0,
                  "gt_mha_cls_fwd: needs head dim %% 4 == 0 and <= %d (got %d)", CLS_MAXDH, dh);
-    if (clsw_ok(dt, nhead, dh, q, kv, out, nullptr)) {
+    if (clsw_ok(dt, nhead, dh, B, n_rows, q, kv, out, nullptr)) {
         const unsigned blocks = (unsigned)((B + CLS_WARPS - 1) / CLS_WARPS);
         if (dh == 64)
             k_mha_cls_fwd_w<64><<<blocks, CLS_WARPS * 32, 0, (cudaStream_t)stream>>>((const bf16*)q, (const bf16*)kv, tok_off, q_rows, n_rows, (int)B, scale, (bf16*)out, lse, drop_p, rng_state, salt);
@@ -339,7 +344,7 @@ extern "C" int gt_mha_cls_bwd(int dt, const void* q, const void* kv, const void*
                               uint64_t salt, void* stream) {
     GT_CHECK_ARG(B > 0 && n_rows > 0 && nhead > 0 && dh > 0 && dh <= CLS_MAXDH && dh % 4 == 0,
                  "gt_mha_cls_bwd: needs head dim %% 4 == 0 and <= %d (got %d)", CLS_MAXDH, dh);
-    if (clsw_ok(dt, nhead, dh, q, kv, dout, dkv) && ((uintptr_t)out | (uintptr_t)dq) % 16 == 0) {
+    if (clsw_ok(dt, nhead, dh, B, n_rows, q, kv, dout, dkv) && ((uintptr_t)out | (uintptr_t)dq) % 16 == 0) {
         const unsigned blocks = (unsigned)((B + CLS_WARPS - 1) / CLS_WARPS + 64);     // + 64 blocks for the tail rows
         if (dh == 64)
             k_mha_cls_bwd_w<64><<<blocks, CLS_WARPS * 32, 0, (cudaStream_t)stream>>>((const bf16*)q, (const bf16*)kv, (const bf16*)out, (const bf16*)dout, lse, tok_off, q_rows, n_rows, (int)B, scale, (bf16*)dq, (bf16*)dkv, drop_p, rng_state, salt);
