@@ -23,6 +23,7 @@ of the step, when N > 1) over one synthetic batch.  Rank 0 prints ONE JSON line.
   cpu_baseline : the CPU oracle (port of the reference's PyTorch path) timed on the host cores
 """
 import argparse
+import gc
 import json
 import os
 import statistics
@@ -529,6 +530,10 @@ def run_workload(ns, cfg, scaling, B_arg, rank, world, dev, K, W, full):
         for j in range(int(n_extra)):
             float(step(extra[j] if j < len(extra) else fresh[0]))
         cap1 = graphed.captures if graphed is not None else 0
+        # a generational collection inside a 40 ms window (20 steps of 2 ms) would be the measurement: collect now, keep
+        # the collector off while the host loop is timed (as a training loop that cares about step jitter does)
+        gc.collect()
+        gc.disable()
         barrier()
         t0 = time.perf_counter()
         if graphed is not None:
@@ -547,6 +552,7 @@ def run_workload(ns, cfg, scaling, B_arg, rank, world, dev, K, W, full):
                 float(step(timed[i]))                  # D2H read of the loss
         barrier()
         te = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        gc.enable()
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         cap2 = graphed.captures if graphed is not None else 0
