@@ -35,7 +35,7 @@ SIGNATURES = {
     "gt_onehot": [L, I32, P, P, P, P, I32, P, P],
     "gt_embed_unpack": [P, I32, I32, I32, I32, P, P, P, P],
     "gt_aggregate_fwd": [I, I, P, P, L, I32, I32, P, P, P, P, I, P, I32, P, P, P, P, P, P, P, P, P],
-    "gt_aggregate_bwd": [I, I, P, P, P, L, I32, I32, P, P, P, P, I, P, I32, P, P, P, P, I32, P, P, P, P, P, P, P, P, P, P],
+    "gt_aggregate_bwd": [I, I, P, P, P, L, I32, I32, P, P, P, P, I, P, I32, P, P, P, P, I32, P, P, P, P, P, P, P, P, P, P, P],
     "gt_edge_slots": [P, P, P, P, L, L, P, P, I32, P, P, P, P],
     "gt_edges_by_type": [P, P, L, I32, P, P, P, P, P, P],
     "gt_aggregate_table_grad": [I, I, P, P, L, I32, I32, P, L, P, P, P, P, I32, P, P],

@@ -933,6 +933,114 @@ k_agg_bwd3(const T* __restrict__ x, const T* __restrict__ dout, T* __restrict__ 
     }
 }
 
+// GIN adjoint, bf16, edge-table encoder, PACKED mask arithmetic.  k_agg_bwd3 is issue-bound (~125 warp instructions per
+// edge at ~2.1 IPC per SM), and most of them form the ReLU mask and the masked gradient one channel at a time in fp32:
+//   gm = (x_j + e_t > 0) ? g : 0.
+// The mask is exact in bf16: x_j is a bf16 value, so  x_j + e_t > 0  <=>  x_j > -e_t  <=>  x_j > rd(-e_t)  with rd = round
+// DOWN to bf16 (no bf16 value lies in (rd(v), v]).  `th` [ntypes + 1, ld] holds rd(-table) (gt_edge_table_thresholds, once
+// per layer; row ntypes = +inf for the tail slots of a 4-slot batch), so a slot costs per channel PAIR one packed compare
+// (mask 0xFFFF / 0) and one AND with the packed gradient - which IS the bf16 per-edge gradient that gets stored - plus the
+// fp32 accumulation of dx.  One 16-byte table load per slot instead of two.
+__global__ void __launch_bounds__(256, 3)
+k_agg_bwd3p(const bf16* __restrict__ x, const bf16* __restrict__ dout, bf16* __restrict__ dx, int N, int d, int ld,
+            const int32_t* __restrict__ rp_src, const int32_t* __restrict__ dst_by_src,
+            const int32_t* __restrict__ eid_by_src, EdgeEnc en, const bf16* __restrict__ th,
+            const float* __restrict__ self_param, float* __restrict__ d_self, bf16* __restrict__ gm_out) {
+    constexpr int CONV = GT_CONV_GIN, EK = GT_EDGE_TABLE, KD = 1;
+    extern __shared__ float sh_par[];    // one eps slot per warp
+    const int c0 = threadIdx.x * 8;
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
+    const float eps1 = 1.f + self_param[0];
+    float deps = 0.f;
+    const int stride = gridDim.x * blockDim.y;
+    int j = blockIdx.x * blockDim.y + threadIdx.y;
+    int b0 = 0, e0 = 0, b1 = 0, e1 = 0;
+    if (j < N) b0 = rp_src[j], e0 = rp_src[j + 1];
+    if (j + stride < N) b1 = rp_src[j + stride], e1 = rp_src[j + stride + 1];
+    SlotBatch<KD> cur;
+    if (j < N) load_slots<CONV, EK, KD>(cur, en, dst_by_src, eid_by_src, rp_src, b0, e0, j, 1.f);
+    auto unpack_add = [](const uint32_t (&w)[4], float (&acc)[8]) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            acc[2 * k] += __uint_as_float(w[k] << 16);
+            acc[2 * k + 1] += __uint_as_float(w[k] & 0xffff0000u);
+        }
+    };
+    for (; j < N; j += stride) {
+        const uint4 xp = *reinterpret_cast<const uint4*>(x + (int64_t)j * ld + c0);
+        const uint4 gjp = *reinterpret_cast<const uint4*>(dout + (int64_t)j * ld + c0);
+        uint4 g[AGG_U];
+#pragma unroll
+        for (int u = 0; u < AGG_U; ++u) g[u] = *reinterpret_cast<const uint4*>(dout + (int64_t)cur.other[u] * ld + c0);
+        SlotBatch<KD> nxt;
+        const int jnext = j + stride;
+        if (jnext < N) load_slots<CONV, EK, KD>(nxt, en, dst_by_src, eid_by_src, rp_src, b1, e1, jnext, 1.f);
+        int b2 = 0, e2 = 0;
+        if (jnext + stride < N) b2 = rp_src[jnext + stride], e2 = rp_src[jnext + stride + 1];
+        const uint32_t xw[4] = {xp.x, xp.y, xp.z, xp.w};
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        auto consume = [&](const SlotBatch<KD>& sb, int pbase) {
+#pragma unroll
+            for (int u = 0; u < AGG_U; ++u) {
+                const int tyu = sb.nrm[u] != 0.f ? sb.ty[u] : en.ntypes;      // tail slot: the +inf row masks everything
+                const uint4 tp = *reinterpret_cast<const uint4*>(th + (int64_t)tyu * ld + c0);
+                const uint32_t tw[4] = {tp.x, tp.y, tp.z, tp.w}, gw[4] = {g[u].x, g[u].y, g[u].z, g[u].w};
+                uint32_t m[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    m[k] = gw[k] & __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&xw[k]), *reinterpret_cast<const __nv_bfloat162*>(&tw[k]));
+                unpack_add(m, acc);
+                if (gm_out && pbase + u < e0)
+                    *reinterpret_cast<uint4*>(gm_out + (int64_t)(pbase + u) * ld + c0) = make_uint4(m[0], m[1], m[2], m[3]);
+            }
+        };
+        consume(cur, b0);
+        for (int p0 = b0 + AGG_U; p0 < e0; p0 += AGG_U) {         // nodes with more than AGG_U out-edges
+            SlotBatch<KD> sb;
+            load_slots<CONV, EK, KD>(sb, en, dst_by_src, eid_by_src, rp_src, p0, e0, j, 1.f);
+#pragma unroll
+            for (int u = 0; u < AGG_U; ++u) g[u] = *reinterpret_cast<const uint4*>(dout + (int64_t)sb.other[u] * ld + c0);
+            consume(sb, p0);
+        }
+        const uint32_t gjw[4] = {gjp.x, gjp.y, gjp.z, gjp.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float g0 = __uint_as_float(gjw[k] << 16), g1 = __uint_as_float(gjw[k] & 0xffff0000u);
+            const float x0 = __uint_as_float(xw[k] << 16), x1 = __uint_as_float(xw[k] & 0xffff0000u);
+            acc[2 * k] = fmaf(eps1, g0, acc[2 * k]);
+            acc[2 * k + 1] = fmaf(eps1, g1, acc[2 * k + 1]);
+            deps = fmaf(x0, g0, deps);
+            deps = fmaf(x1, g1, deps);
+        }
+        st8(dx + (int64_t)j * ld + c0, acc);
+        cur = nxt;
+        b0 = b1, e0 = e1, b1 = b2, e1 = e2;
+    }
+    deps = warp_sum(deps);                  // d eps: one global atomic per block
+    const int nw = (nthr + 31) >> 5;
+    if ((tid & 31) == 0) sh_par[tid >> 5] = deps;
+    __syncthreads();
+    if (tid == 0) {
+        float t = 0.f;
+        for (int w = 0; w < nw; ++w) t += sh_par[w];
+        if (t != 0.f) atomicAdd(d_self, t);
+    }
+}
+
+// th[t, c] = round-down-to-bf16(-table[t, c]) for t < ntypes, +inf for t == ntypes (see k_agg_bwd3p)
+__global__ void k_edge_table_thresholds(const float* __restrict__ table, int ntypes, int ld, bf16* __restrict__ th) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (ntypes + 1) * ld) return;
+    uint16_t b = 0x7F80;                    // +inf
+    if (i < ntypes * ld) {
+        const uint32_t v = __float_as_uint(-table[i]);
+        b = (uint16_t)(v >> 16);
+        if ((v & 0xFFFFu) && (v >> 31)) b += 1;      // negative and inexact: truncation rounds towards zero, i.e. up
+        if ((v & 0x7FFFFFFFu) > 0x7F800000u) b = 0x7F80;   // NaN table entry: x + NaN > 0 is false
+    }
+    reinterpret_cast<uint16_t*>(th)[i] = b;
+}
+
 // Adjoint with the edge-TABLE gradient fused in (bf16, table edge encoder, <= 64 edge types, ld = 128 or 256).
 // The table gradient is the contraction d_table[t, c] = sum over edges e of type t of gm[e, c] with gm[e, :] =
 // norm * dout[dst(e), :] * 1[x[src(e), :] + table[t, :] > 0] - exactly the per-edge vector the adjoint already holds in
@@ -1283,7 +1391,7 @@ template <typename T, int CONV>
 static int launch_bwd(int ek, const T* x, const T* dout, T* dx, int N, int d, int ld, const int32_t* rp_src,
                       const int32_t* dst_by_src, const int32_t* eid_by_src, EdgeEnc en,
                       const float* self_param, float* dw, float* db, float* dtab, float* dself, T* gm_out,
-                      cudaStream_t st) {
+                      void* th_scratch, cudaStream_t st) {
     int grid = blocks_for(N, AGG_WARPS, kNumSMs * 8);
     const int nch = (ld + 127) / 128;
     const bool tab_grad = ek == GT_EDGE_TABLE && dtab != nullptr;
@@ -1327,6 +1435,16 @@ static int launch_bwd(int ek, const T* x, const T* dout, T* dx, int N, int d, in
         // parameter-gradient element)
         const int grid3 = blocks_for(N, (int)blk.y, kNumSMs * 3);
         const size_t smem3 = sizeof(float) * ((size_t)(2 + MAX_KDIM) * ld + 32);
+        static const int packed = getenv("GT_AGG_PACKED") ? atoi(getenv("GT_AGG_PACKED")) : 1;
+        if (packed && th_scratch && std::is_same<T, bf16>::value && CONV == GT_CONV_GIN && ek == GT_EDGE_TABLE &&
+            ((uintptr_t)x | (uintptr_t)dout | (uintptr_t)dx | (uintptr_t)th_scratch | (uintptr_t)gm_out) % 16 == 0) {
+            // packed-mask adjoint: thresholds of this layer's table first (61 x ld elements), then the walk
+            const int nth = (en.ntypes + 1) * ld;
+            k_edge_table_thresholds<<<(nth + 255) / 256, 256, 0, st>>>(en.table, en.ntypes, ld, (bf16*)th_scratch);
+            k_agg_bwd3p<<<grid3, blk, sizeof(float) * 32, st>>>((const bf16*)x, (const bf16*)dout, (bf16*)dx, N, d, ld, rp_src, dst_by_src,
+                                                              eid_by_src, en, (const bf16*)th_scratch, self_param, dself, (bf16*)gm_out);
+            return 0;
+        }
 #define L3K(EK, KD) k_agg_bwd3<T, CONV, EK, KD><<<grid3, blk, smem3, st>>>(x, dout, dx, N, d, ld, rp_src, dst_by_src, eid_by_src, en, self_param, dw, db, dself, gm_out)
         if (ek == GT_EDGE_NONE) L3K(GT_EDGE_NONE, 1);
         else if (ek == GT_EDGE_LINEAR) { if (en.kdim > 2) L3K(GT_EDGE_LINEAR, 4); else L3K(GT_EDGE_LINEAR, 2); }
@@ -1390,7 +1508,8 @@ extern "C" int gt_aggregate_bwd(int dt, int conv, const void* x, const void* dou
                                 const float* edge_attr, int32_t kdim, const float* edge_w, const float* edge_b,
                                 const int32_t* etype, const float* table, int32_t ntypes, const float* self_param,
                                 float* d_edge_w, float* d_edge_b, float* d_table, float* d_self, const float* norm_slot,
-                                const int32_t* etype_slot, const float* attr_slot, void* gm_out, void* stream) {
+                                const int32_t* etype_slot, const float* attr_slot, void* gm_out, void* th_scratch,
+                                void* stream) {
     (void)rowptr_dst;
     if (int r = check_common("gt_aggregate_bwd", conv, N, d, ld, edge_kind, kdim)) return r;
     GT_CHECK_ARG(edge_kind != GT_EDGE_TABLE || ntypes > 0, "gt_aggregate_bwd: ntypes must be the row count of the edge table");
@@ -1399,9 +1518,9 @@ extern "C" int gt_aggregate_bwd(int dt, int conv, const void* x, const void* dou
     int rc = 0;
     GT_DISPATCH_DT(dt, {
         if (conv == GT_CONV_GCN)
-            rc = launch_bwd<T, GT_CONV_GCN>(edge_kind, (const T*)x, (const T*)dout, (T*)dx, (int)N, d, ld, rowptr_src, dst_by_src, eid_by_src, en, self_param, d_edge_w, d_edge_b, d_table, d_self, (T*)gm_out, st);
+            rc = launch_bwd<T, GT_CONV_GCN>(edge_kind, (const T*)x, (const T*)dout, (T*)dx, (int)N, d, ld, rowptr_src, dst_by_src, eid_by_src, en, self_param, d_edge_w, d_edge_b, d_table, d_self, (T*)gm_out, th_scratch, st);
         else
-            rc = launch_bwd<T, GT_CONV_GIN>(edge_kind, (const T*)x, (const T*)dout, (T*)dx, (int)N, d, ld, rowptr_src, dst_by_src, eid_by_src, en, self_param, d_edge_w, d_edge_b, d_table, d_self, (T*)gm_out, st);
+            rc = launch_bwd<T, GT_CONV_GIN>(edge_kind, (const T*)x, (const T*)dout, (T*)dx, (int)N, d, ld, rowptr_src, dst_by_src, eid_by_src, en, self_param, d_edge_w, d_edge_b, d_table, d_self, (T*)gm_out, th_scratch, st);
     });
     if (rc) return rc;
     GT_LAUNCH_CHECK("gt_aggregate_bwd");

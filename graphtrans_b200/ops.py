@@ -25,6 +25,8 @@ TABLE_GRAD_GEMM = int(os.environ.get("GT_TABLE_GRAD_GEMM", "1"))           # edg
 # contraction with the one-hot edge types; no [E, ld] tensor); same eligibility rule as csrc/aggregate.cu launch_bwd
 # Opt-in: at config 4 it measures 757 us against 796 us for adjoint + one-hot GEMM (both issue bound), see DESIGN.md
 TABLE_GRAD_FUSED = int(os.environ.get("GT_AGG_TABLE_FUSED", "0"))
+# GIN adjoint with the ReLU mask formed by packed bf16 compares against per-layer bf16 thresholds (exact; k_agg_bwd3p)
+AGG_PACKED = int(os.environ.get("GT_AGG_PACKED", "1"))
 MHA_IMPL = int(os.environ.get("GT_MHA_IMPL", "0"))
 # fp32 parity mode with every contraction ON the tcgen05 kernel: operands split into three bf16 terms, six products
 # accumulated in fp32 (SURVEY §7 "fp32 parity on tensor cores"); 0 = exact CUDA-core contractions (default parity path)
@@ -1106,11 +1108,16 @@ class _AggregateFn(torch.autograd.Function):
         split = ctx.split and need_tab and not fused
         gm = torch.empty(max(plan.E, 1), ld, dtype=x.dtype, device=x.device) if (split and ctx.tab_gemm) else None
         tself = _grad_target(pself)
+        # GIN + edge table in bf16: work buffer for the packed-mask adjoint (bf16 ReLU thresholds of this layer's table)
+        th = None
+        if (AGG_PACKED and edge_kind == EDGE_TABLE and conv == CONV_GIN and x.dtype == torch.bfloat16
+                and (split or not need_tab) and ld % 8 == 0 and ld <= 512):
+            th = torch.empty(table.shape[0] + 1, ld, dtype=torch.bfloat16, device=x.device)
         call("gt_aggregate_bwd", dt_of(x), conv, ptr(x), ptr(g), ptr(dx), N, d, ld, ptr(plan.rowptr_dst),
              ptr(plan.rowptr_src), ptr(plan.dst_by_src), ptr(plan.eid_by_src), edge_kind, ptr(edge_attr), kdim,
              ptr(edge_w), ptr(edge_b), ptr(etype), ptr(table), table.shape[0] if edge_kind == EDGE_TABLE else 0, ptr(sp),
              ptr(tw[0]), ptr(tb[0]), None if (split or not need_tab) else ptr(dtab), ptr(tself[0]), ptr(ctx.slots[0]), ptr(ctx.slots[1]),
-             ptr(ctx.slots[2]), ptr(gm))
+             ptr(ctx.slots[2]), ptr(gm), ptr(th))
         if split and gm is not None:
             oh, r_pad, _ = plan.type_onehot(ctx.slots[1], table.shape[0])
             with _WgradCtx(ctx.tab_side, gm, dtab, oh):

@@ -114,7 +114,9 @@ int gt_aggregate_fwd(int dt, int conv, const void* x, void* out, int64_t N, int3
                      const float* attr_slot, void* stream);
 /* adjoint: dx (same dtype), and fp32 accumulators (must be zeroed by the caller):
  * d_edge_w [d,kdim], d_edge_b [d] (LINEAR) or d_table [ntypes, ld] (TABLE; NULL = skipped here, see
- * gt_aggregate_table_grad), d_self ([d] or [1]). */
+ * gt_aggregate_table_grad), d_self ([d] or [1]).  th_scratch: optional bf16 [ntypes + 1, ld] work buffer (GIN, TABLE,
+ * bf16, d_table == NULL): the call first fills it with the bf16 ReLU thresholds of this layer's table and then runs the
+ * packed-mask adjoint (same results bit for bit: x + e > 0 <=> x > round-down-to-bf16(-e) for a bf16 x); NULL = fp32 mask. */
 int gt_aggregate_bwd(int dt, int conv, const void* x, const void* dout, void* dx, int64_t N,
                      int32_t d, int32_t ld,
                      const int32_t* rowptr_dst, const int32_t* rowptr_src, const int32_t* dst_by_src,
@@ -123,7 +125,7 @@ int gt_aggregate_bwd(int dt, int conv, const void* x, const void* dout, void* dx
                      const float* edge_b, const int32_t* etype, const float* table, int32_t ntypes,
                      const float* self_param,
                      float* d_edge_w, float* d_edge_b, float* d_table, float* d_self, const float* norm_slot,
-                     const int32_t* etype_slot, const float* attr_slot, void* gm_out, void* stream);
+                     const int32_t* etype_slot, const float* attr_slot, void* gm_out, void* th_scratch, void* stream);
 /* gm_out (optional, activation dtype [E, ld], source-sorted slot order = dst_by_src order): per-edge masked message
  * gradient norm_e * dout[dst_e] * 1[x[src_e] + ee_e > 0].  With it the edge-TABLE gradient is the contraction
  * d_table = OneHot(etype_slot)^T . gm (gt_onehot + gt_gemm) instead of gt_aggregate_table_grad's second gather pass. */

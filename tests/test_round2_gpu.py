@@ -445,3 +445,57 @@ def test_relu_bwd_colsum(dtype, M, N, ld):
     want = ref32.double()[:, :N].sum(0) + 0.5                     # fp32 products summed before the store rounds them;
                                                                   # accumulates into the target
     assert (cs.double() - want).abs().max() <= 1e-4 * max(1.0, float(want.abs().max()))
+
+
+@pytest.mark.parametrize("d,n_graphs", [(256, 300), (300, 40), (72, 40), (256, 1)])
+def test_gin_adjoint_packed_mask_is_exact(d, n_graphs):
+    """k_agg_bwd3p forms the ReLU mask with packed bf16 compares against round-down-to-bf16(-table) thresholds: for a
+    bf16 x that is the SAME predicate as x + e > 0 in fp32, so dx and the per-edge gradients (hence d_table) must equal
+    the fp32-mask kernel bit for bit.  The table holds values that are not bf16-representable, exact ties x == -e
+    (mask false on both paths) and entries just above / below a bf16 value."""
+    from graphtrans_b200._lib import CONV_GIN, EDGE_TABLE
+    batch = synth.gen_mol(n_graphs, seed=13)
+    ei = batch.edge_index.cuda()
+    N, E, ntypes = batch.batch.numel(), ei.shape[1], 60
+    ld = ops.ldp(d)
+    torch.manual_seed(6)
+    x0 = torch.zeros(N, ld, device="cuda")
+    x0[:, :d] = torch.randn(N, d, device="cuda")
+    xb = x0.bfloat16()
+    table0 = torch.zeros(ntypes, ld, device="cuda")
+    table0[:, :d] = torch.randn(ntypes, d, device="cuda") * 0.5
+    # ties and near-ties: -table equal to / one fp32 ulp above / below bf16 values that occur in x
+    vals = xb[torch.arange(ntypes, device="cuda") % N, :d].float()
+    table0[:, 0:d:7] = -vals[:, 0:d:7]
+    table0[:, 1:d:7] = -torch.nextafter(vals[:, 1:d:7], torch.full_like(vals[:, 1:d:7], 1e9))
+    table0[:, 2:d:7] = -torch.nextafter(vals[:, 2:d:7], torch.full_like(vals[:, 2:d:7], -1e9))
+    etype = torch.randint(0, ntypes, (E,), device="cuda", dtype=torch.int32)
+    src = ei[0]
+    etype[: min(E, N)] = (src[: min(E, N)] % ntypes).int()      # many edges whose source row hits its own tie row
+    gy = torch.zeros(N, ld, device="cuda")
+    gy[:, :d] = torch.randn(N, d, device="cuda")
+    gy = gy.bfloat16()
+
+    def run(packed):
+        prev = ops.AGG_PACKED
+        ops.AGG_PACKED = packed
+        try:
+            plan = ops.GraphPlan(ei, batch.batch.cuda(), n_graphs)
+            x = xb.clone().requires_grad_(True)
+            table = table0.clone().requires_grad_(True)
+            sp = torch.full((1,), 0.25, device="cuda").requires_grad_(True)
+            y = ops.aggregate(x, plan, CONV_GIN, d, sp, edge_kind=EDGE_TABLE, etype=etype, table=table)
+            return torch.autograd.grad(y, (x, table, sp), gy)
+        finally:
+            ops.AGG_PACKED = prev
+
+    dx1, dt1, ds1 = run(1)
+    dx0, dt0, ds0 = run(0)
+    assert torch.equal(dx1, dx0)
+    assert (dt1.double() - dt0.double()).norm() <= 1e-5 * dt0.double().norm()      # same gm, split-K reduction order only
+    assert (ds1.double() - ds0.double()).abs().max() <= 1e-3 * ds0.double().abs().max() + 1e-6
+    # and against the dense fp64 formula
+    xd, gd, td = xb.double()[:, :d], gy.double()[:, :d], table0.double()[:, :d]
+    gm = gd[ei[1]] * ((xd[src] + td[etype.long()]) > 0)
+    ref_dx = torch.zeros(N, d, device="cuda", dtype=torch.float64).index_add_(0, src, gm) + 1.25 * gd
+    assert (dx1[:, :d].double() - ref_dx).norm() / ref_dx.norm() < 1e-2

@@ -1,4 +1,3 @@
 #!/bin/bash
-timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -2 > gpurun_out/r02_tests_gpu_v3.txt; cat gpurun_out/r02_tests_gpu_v3.txt
-F="--steps 30 --warmup 5 --no-cpu-baseline --no-roofline --no-e2e --no-optimizer --no-extra-configs"
-for c in code2 code2-pna; do timeout 100 python bench.py $F --config $c 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['config']['workload'][:20], d['value'], d['ms_per_step'], d['clocks'])"; done
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+for c in molpcba; do timeout 200 python tools/graph_trace.py $c > gpurun_out/r02_graph_trace_${c}_q.txt 2>&1; grep -E "us/step|gt_aggregate" gpurun_out/r02_graph_trace_${c}_q.txt | cut -c1-140; done
