@@ -874,6 +874,9 @@ class _LinearFn(torch.autograd.Function):
         # The consumer opts in (a frozen BN, a standalone conv or any other reader keeps the real column sum).
         ctx.bias_grad_zero = False
         ctx.passthrough = bool(passthrough)
+        # no zero tensors for outputs without a gradient (the non-differentiable statistics output would otherwise cost
+        # one fill kernel per Linear + BatchNorm pair in every backward)
+        ctx.set_materialize_grads(False)
         if want_stats:
             ctx.mark_non_differentiable(stats)
             return y, stats

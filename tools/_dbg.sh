@@ -1,7 +1,5 @@
 #!/bin/bash
-B="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-roofline --no-e2e --no-optimizer --no-extra-configs"
-NCU="ncu --clock-control none --graph-profiling node"
-timeout 300 $NCU --set full --import-source on -k regex:"k_agg_bwd3p|k_mha_cls_" -s 6 -c 4 -f -o gpurun_out/r02_prof_agg3p_syn $B --config syn > /dev/null 2>&1
-python tools/ncu_summary.py gpurun_out/r02_prof_agg3p_syn.ncu-rep > gpurun_out/r02_ncu_agg3p_syn_v2.txt 2>&1
-rm -f gpurun_out/*.ncu-rep
-grep -E "^--|duration|warp instr|dram %|warps active|stalls" gpurun_out/r02_ncu_agg3p_syn_v2.txt | cut -c1-150 | head -24
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -2 > gpurun_out/r02_tests_gpu_v3.txt; cat gpurun_out/r02_tests_gpu_v3.txt
+F="--steps 30 --warmup 5 --no-cpu-baseline --no-roofline --no-e2e --no-optimizer --no-extra-configs"
+for c in molpcba code2; do timeout 100 python bench.py $F --config $c 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['config']['workload'][:20], d['value'], d['ms_per_step'], d['gpu_launches'])"; done
+timeout 100 python tools/aten_probe.py molpcba 2>/dev/null | awk '{n+=$1} END {print "aten rows total count", n}'
