@@ -39,6 +39,25 @@ struct LocParams {
 #define LOC_TRACE(slot) do { if (p.trace && blockIdx.x == 0 && blockIdx.y == 0) { unsigned long long t_; \
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); p.trace[slot] = t_; } } while (0)
 
+// Rows that belong to no graph (the unused tail of the static row bound: bucket slack, truncated graphs) are in no tile.
+// Every CTA (x, head) clears the head's column slice of such rows in its stripe of the row range, so the caller needs no
+// zero-fill pass over the whole output: `parts` column blocks of width ld_cols/parts... (out: 1 part of d; dqkv: 3 of d)
+template <int DH>
+__device__ __forceinline__ void loc_clear_tail(const int2* __restrict__ row_bounds, int64_t n_rows, bf16* __restrict__ dst,
+                                               int ld, int parts, int d, int h) {
+    const int64_t chunk = (n_rows + gridDim.x - 1) / gridDim.x;
+    const int64_t r0 = (int64_t)blockIdx.x * chunk, r1 = min(r0 + chunk, n_rows);
+    for (int64_t r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
+        const int2 rb = row_bounds[r];
+        if (rb.y > rb.x) continue;
+        for (int part = 0; part < parts; ++part) {
+            uint4* q = reinterpret_cast<uint4*>(dst + r * ld + part * d + h * DH);
+#pragma unroll
+            for (int i = 0; i < DH / 8; ++i) q[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
+    }
+}
+
 // store 8 consecutive bf16 of row r, columns [c, c+8) of a [128 x 128] two-block swizzled tile
 __device__ __forceinline__ void st_p8(uint32_t tile, int r, int c, const float (&v)[8]) {
     __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
@@ -84,6 +103,7 @@ k_mha_loc_fwd(const __grid_constant__ CUtensorMap tma_qkv, const LocParams p) {
             reinterpret_cast<bf16*>(p.out)[threadIdx.x] = __float2bfloat16_rn(__int_as_float(0x7fc00000));
         return;
     }
+    loc_clear_tail<DH>(p.row_bounds, p.n_rows, (bf16*)p.out, p.d, 1, p.d, (int)blockIdx.y);
     const int2 tile = p.tiles[blockIdx.x];
     const int row0 = tile.x, nrows = tile.y;
     if (nrows <= 0) return;                                   // unused slot of the (host-side) upper bound
@@ -243,6 +263,7 @@ k_mha_loc_bwd(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t ld_full, sdp_full, pds_full, acc_full;
     __shared__ uint32_t tmem_base_s;
+    loc_clear_tail<DH>(p.row_bounds, p.n_rows, (bf16*)p.dqkv, 3 * p.d, 3, p.d, (int)blockIdx.y);
     const int2 tile = p.tiles[blockIdx.x];
     const int row0 = tile.x, nrows = tile.y;
     if (nrows <= 0) return;

@@ -624,6 +624,17 @@ class GraphPlan:
             self._by_type[key] = hit
         return hit
 
+    def zero_table_grad(self, shape, device):
+        """zeroed fp32 [ntypes, ld] accumulation target for one layer's edge-table gradient: slices of ONE tensor per
+        step and table shape (one fill kernel for all layers instead of one per layer)"""
+        pool = self.__dict__.setdefault("_dtab_pool", {})
+        ent = pool.get(shape)
+        if ent is None or ent[1] >= ent[0].shape[0]:
+            ent = [torch.zeros((8,) + tuple(shape), dtype=torch.float32, device=device), 0]
+            pool[shape] = ent
+        ent[1] += 1
+        return ent[0][ent[1] - 1]
+
     def type_onehot(self, etype_slot, ntypes):
         """bf16 one-hot [E, ldp(ntypes)] of the per-slot edge types (once per batch, reused by every layer's
         edge-table gradient contraction)"""
@@ -1103,7 +1114,7 @@ class _AggregateFn(torch.autograd.Function):
         if edge_kind == EDGE_LINEAR:
             tw, tb = _grad_target(pw), _grad_target(pb)
         need_tab = edge_kind == EDGE_TABLE and ctx.needs_input_grad[9]     # a constant table has no gradient kernel
-        dtab = zeros_f32(tuple(table.shape), x.device) if need_tab else None
+        dtab = plan.zero_table_grad(tuple(table.shape), x.device) if need_tab else None
         # the edge-table gradient is a leaf gradient: computed by its own kernel over the type-sorted edges, on the
         # weight-gradient stream, instead of shared-memory atomics inside the adjoint (which then stays as cheap as
         # the forward)
@@ -1471,9 +1482,8 @@ class _MHAFn(torch.autograd.Function):
         # every graph inside one graph-aligned 128-row tile: loop-free tile-local kernels (attn_local.cu)
         local = (impl == 0 and key_start is None and getattr(plan, "loc_tiles", None) is not None
                  and qkv.dtype == torch.bfloat16 and dh in (32, 64))
-        # the tile-local kernels write the rows of their tiles only: rows past the last token are cleared up front
-        tail = local and getattr(plan, "has_tail", True)
-        out = (torch.zeros if tail else torch.empty)(n_rows, d, dtype=qkv.dtype, device=qkv.device)
+        # (the tile-local kernels clear the rows that belong to no graph themselves: no zero-fill of the output)
+        out = torch.empty(n_rows, d, dtype=qkv.dtype, device=qkv.device)
         if local:
             call("gt_mha_local_fwd", dt_of(qkv), ptr(qkv), ptr(plan.row_bounds), ptr(plan.loc_tiles), ptr(plan.loc_count),
                  plan.loc_max_tiles,
@@ -1494,7 +1504,7 @@ class _MHAFn(torch.autograd.Function):
         plan, nhead, dh, scale, key_start, drop_p, salt, impl, local = ctx.meta
         g = g.contiguous()
         n_rows = qkv.shape[0]
-        dqkv = torch.zeros_like(qkv) if (local and getattr(plan, "has_tail", True)) else torch.empty_like(qkv)
+        dqkv = torch.empty_like(qkv)
         if local:
             call("gt_mha_local_bwd", dt_of(qkv), ptr(qkv), ptr(out), ptr(g), ptr(lse), ptr(plan.row_bounds),
                  ptr(plan.loc_tiles), plan.loc_max_tiles, n_rows, nhead, dh, scale, ptr(dqkv), drop_p,
