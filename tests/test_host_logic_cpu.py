@@ -50,3 +50,35 @@ def test_every_signature_names_an_export_of_the_header():
         assert name in declared, name
     for name in _lib.KERNELS_PER_CALL:
         assert name in _lib.SIGNATURES
+
+
+def test_bf16_relu_threshold_identity():
+    """The packed-mask GIN adjoint (csrc/aggregate.cu k_agg_bwd3p) replaces the fp32 predicate  x + e > 0  (x a bf16
+    activation, e an fp32 edge-table entry; reference modules/conv.py:32 `F.relu(x_j + edge_attr)`) by the bf16 compare
+    x > th with th = round-DOWN-to-bf16(-e) (k_edge_table_thresholds: truncate, +1 ulp of magnitude when negative and
+    inexact).  Checked here for EVERY finite bf16 x against random and adversarial e (ties, one fp32 ulp either side of a
+    bf16 value, tiny / huge magnitudes): the two predicates agree exactly."""
+    import numpy as np
+    import torch
+
+    def thresholds(e):                      # bit-level restatement of k_edge_table_thresholds
+        v = (-e).astype(np.float32).view(np.uint32)
+        b = (v >> 16).astype(np.uint32)
+        b = np.where(((v & 0xFFFF) != 0) & ((v >> 31) != 0), b + 1, b)
+        return (b.astype(np.uint32) << 16).view(np.float32)      # the bf16 value, widened
+
+    bits = np.arange(1 << 16, dtype=np.uint32)
+    xs = (bits << 16).view(np.float32)
+    xs = xs[np.isfinite(xs)]
+    rng = np.random.default_rng(0)
+    es = [rng.standard_normal(64).astype(np.float32), (rng.standard_normal(16) * 1e-30).astype(np.float32),
+          (rng.standard_normal(16) * 1e30).astype(np.float32), np.array([0.0, -0.0, 1.0, -1.0], np.float32)]
+    near = xs[rng.integers(0, xs.size, 256)]
+    near = near[np.abs(near) < 1e30]
+    es += [-near, -np.nextafter(near, np.float32(np.inf)), -np.nextafter(near, np.float32(-np.inf))]
+    e = np.concatenate(es).astype(np.float32)
+    th = thresholds(e)
+    x = torch.from_numpy(xs)[:, None]
+    ref = (x + torch.from_numpy(e)[None, :]) > 0                 # fp32 add + compare, as the fp32-mask kernels do
+    got = x > torch.from_numpy(th)[None, :]
+    assert torch.equal(ref, got)
