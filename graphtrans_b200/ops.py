@@ -1132,6 +1132,8 @@ class _AggregateFn(torch.autograd.Function):
              ptr(edge_w), ptr(edge_b), ptr(etype), ptr(table), table.shape[0] if edge_kind == EDGE_TABLE else 0, ptr(sp),
              ptr(tw[0]), ptr(tb[0]), None if (split or not need_tab) else ptr(dtab), ptr(tself[0]), ptr(ctx.slots[0]), ptr(ctx.slots[1]),
              ptr(ctx.slots[2]), ptr(gm), ptr(th))
+        if th is not None:
+            _lib.kernel_count += 1          # the threshold builder in front of the packed-mask adjoint
         if split and gm is not None:
             oh, r_pad, _ = plan.type_onehot(ctx.slots[1], table.shape[0])
             with _WgradCtx(ctx.tab_side, gm, dtab, oh):
